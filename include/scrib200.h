@@ -1,0 +1,150 @@
+/*
+ * scrib200.h - C ABI of libscrib200.so, the sm_100a implementation of scri's data-parallel
+ * waveform-transformation hot path (reference: moble/scri 2024.0.13).
+ *
+ * The reference is pure Python + numba and has no FFI of its own; the boundary below mirrors the
+ * numba / third-party kernel signatures the reference crosses on this path, one entry
+ * point per kernel, so that a maintainer can bind them with ctypes in place of those calls
+ * (see INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; caller owns all buffers
+ *   - complex128 = interleaved double[2]; arrays are C-contiguous (row-major), 16-byte aligned
+ *   - (ell,m) mode layout: index = ell(ell+1) - ell_min^2 + m        (scri/waveform_modes.py:455)
+ *   - grid layout: index = j*n_phi + k, theta_j = pi j/(n_theta-1), phi_k = 2 pi k/n_phi
+ *                                                                    (scri/waveform_grid.py:130-135,594)
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued asynchronously on it
+ *   - return value: 0 = ok, negative = error (message via scrib200_last_error()); no hidden
+ *     allocation - scratch comes from the *_workspace_bytes queries
+ */
+#ifndef SCRIB200_H
+#define SCRIB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCRIB200_OK 0
+#define SCRIB200_EINVAL (-1)
+#define SCRIB200_ECUDA (-2)
+
+int scrib200_version(void);
+const char* scrib200_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t scrib200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Wigner-D rotation of modes, in place.
+ * Replaces  scri/rotations.py:370-392 `_rotate_decomposition_basis_by_series(data, R_basis, ell_min,
+ * ell_max, D)` (+ the per-step sf._Wigner_D_matrices call) and, with spinor_stride = 0,
+ * rotations.py:346-367 `_rotate_decomposition_basis_by_constant`.
+ *   data    [n_times, n_modes] complex128, n_modes = LM_total_size(ell_min, ell_max)
+ *   spinors [n_times, 2] complex128 (Ra = w + i z, Rb = y + i x)  - or a single pair if stride 0
+ *   seed    [(2L+1)^2], rec [L, 2L+1, 2L+1, 3]  recurrence tables for L = ell_max
+ *           (scri_b200._sf.wigner_tables)
+ */
+int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
+                          int64_t spinor_stride, const double* seed, const double* rec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SWSH synthesis with the BMS epilogue.
+ * Replaces  scri/waveform_grid.py:475-484 (np.tensordot of the modes with sf.SWSH_grid), the constant
+ * data-type correction :486-503 and the conformal factor :559:
+ *     F[i, g] = (sum_lm a[i, lm] Y[g, lm] - c[g]) * k[g]^w
+ * as one real FP64 tensor-core (DMMA) GEMM  [n_times, 2 n_modes] x [2 n_modes, 2 G].
+ *   modes   [n_times, n_modes] complex128
+ *   Bmat    [Kpad, Ncpad] real: packed table (scri_b200.plan.pack_synthesis_matrix);
+ *           Kpad = roundup(2 n_modes, 16), Ncpad = roundup(2 G, 64)
+ *   offset  [Ncpad] real (Re c, Im c interleaved), scale [Ncpad] real (k^w repeated twice)
+ *   F       [n_times, G] complex128 (output)
+ */
+int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, const double* Bmat, int Kpad,
+                             int Ncpad, const double* offset, const double* scale, int G, double* F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BMS retarded-time remap: batched not-a-knot cubic-spline construction + evaluation.
+ * Replaces  scri/waveform_grid.py:576-588 (two scipy InterpolatedUnivariateSpline builds per grid
+ * point, evaluated at u'):  for each g: knots x_i = k[g]*(t[i]-alpha[g]), values F[i,g] (Re and Im),
+ * out[i', g] = spline_g(uprm[i']).
+ *   t [n_times], F [n_times, G] complex128, kconf [G], alpha [G], uprm [n_out], out [n_out, G] complex128
+ *   chunk: knots per thread-chunk (0 = default), workspace: scrib200_spline_remap_workspace_bytes()
+ */
+size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int chunk);
+int scrib200_bms_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
+                              const double* alpha, const double* uprm, int64_t n_out, double* out, int chunk,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SWSH analysis, batched over time steps.
+ * Replaces  scri/waveform_grid.py:303-307 (spinsfast.map2salm per time step, first ell_min^2 modes
+ * dropped): phi-DFT followed by the Clenshaw-Curtis theta quadrature that Huffenberger & Wandelt's
+ * algorithm reduces to.
+ *   grid [n_times, n_theta, n_phi] complex128
+ *   E    [n_phi, 2 ell_max + 1] complex128, Wt [n_modes, n_theta] real (scri_b200._sf.analysis_tables)
+ *   out  [n_times, n_modes] complex128, n_modes = LM_total_size(ell_min, ell_max)
+ */
+size_t scrib200_map2salm_workspace_bytes(int64_t n_times, int n_theta, int n_phi, int ell_max);
+int scrib200_map2salm(const double* grid, int64_t n_times, int n_theta, int n_phi, const double* E,
+                      const double* Wt, int ell_min, int ell_max, double* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Time derivative of every mode through the not-a-knot cubic spline.
+ * Replaces  scri/waveform_base.py:689-695  CubicSpline(t, data).derivative(order)(t)  (data_dot, data_ddot).
+ *   data/out [n_times, ncol] complex128; ones/zeros: device arrays [ncol] of 1.0 / 0.0 (identity knot map);
+ *   workspace: scrib200_spline_remap_workspace_bytes(n_times, ncol, chunk)
+ */
+int scrib200_spline_derivative(const double* t, int64_t n_times, const double* data, int ncol, const double* ones,
+                               const double* zeros, int order, double* out, int chunk, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* sum_modes |a|^2 per time step.  Replaces scri/waveform_base.py:19-35 complex_array_norm. */
+int scrib200_norm(const double* data, int64_t n_times, int n_modes, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * <LL> matrix and <L d/dt> vector in one pass over the modes.
+ * Replaces  scri/mode_calculations.py:209-295 `_LLMatrix(data, lm, LL)` and :14-43
+ * `_LdtVector(data, datadot, lm, Ldt)`.  datadot/Ldt may both be NULL (LL only).
+ *   coef [n_modes, 5]: ladder-coefficient table (scri_b200.mode_calculations.ladder_table)
+ *   LL [n_times, 3, 3], Ldt [n_times, 3] real
+ */
+int scrib200_ll_ldt(const double* data, const double* datadot, int64_t n_times, int n_modes, const double* coef,
+                    double* LL, double* Ldt, void* stream);
+
+/* <L> vector.  Replaces scri/mode_calculations.py:60-89 `_LVector(data1, data2, lm, Lvec)`; Lvec [n_times,3] complex */
+int scrib200_l_vector(const double* data1, const double* data2, int64_t n_times, int n_modes, const double* coef,
+                      double* Lvec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dominant principal axis of <LL>, made continuous in time.
+ * Replaces  np.linalg.eigh(LL)[1][:, :, 2] + scri/mode_calculations.py:316-363
+ * `_LLDominantEigenvector(dpa, dpa_i, i_index)`.
+ *   LL [n_times,3,3]; rough_direction [3] (device); dpa [n_times,3] output
+ */
+size_t scrib200_dominant_eigenvector_workspace_bytes(int64_t n_times);
+int scrib200_dominant_eigenvector(const double* LL, int64_t n_times, const double* rough_direction,
+                                  int64_t rough_index, double* dpa, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* x = scale * A^{-1} b for n 3x3 systems (LU with partial pivoting).
+ * Replaces  np.linalg.solve at scri/mode_calculations.py:424 (scale = -1 gives omega). */
+int scrib200_solve3(const double* A, const double* b, int64_t n, double scale, double* x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K sparse expectation values <a|M_k|b>(t) in one pass over the rows.
+ * Replaces  scri/flux.py:40-78 `sparse_expectation_value(abar, rows, columns, values, b)` (called once per
+ * matrix by the reference).  Elements of matrix k are [seg[k], seg[k+1]); `a` is NOT pre-conjugated.
+ *   rows/cols int32 [nnz], vals complex128 [nnz], seg int32 [K+1] (seg_dev on device; seg_host may be NULL)
+ *   out [n_times, K] complex128
+ */
+int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_times, int n_modes, const int* rows,
+                                const int* cols, const double* vals, const int* seg_host, const int* seg_dev, int K,
+                                double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRIB200_H */

@@ -1,0 +1,387 @@
+// K5/K6/K7 and friends: per-time-step reductions over the modes (mode_calculations.py, flux.py).
+//
+//   norm                 scri/waveform_base.py:19-35          sum_lm |a|^2
+//   ll_ldt               scri/mode_calculations.py:14-43,209-295   <LL> (3x3 real sym.) and <L d/dt> (3-vector)
+//   l_vector             scri/mode_calculations.py:60-89      <L> (complex 3-vector)
+//   sym3_dominant_eig    np.linalg.eigh + [:, :, 2]           (mode_calculations.py:389-395)
+//   eig_sign_*           scri/mode_calculations.py:316-363    sequential sign-continuity pass as a 2-state scan
+//   solve3               np.linalg.solve (mode_calculations.py:424)
+//   sparse_expectation   scri/flux.py:40-78                   sum_e conj(a[row_e]) b[col_e] val_e
+//
+// All are HBM-bound: one warp per time step, lanes striding over modes (coalesced 16-byte loads of the
+// [time, mode] row), warp-shuffle reduction, a few bytes out per step.  The reference loops mode-outer /
+// time-inner with stride-n access; here each row is read exactly once.
+#include "common.cuh"
+
+namespace scrib200 {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ norm
+__global__ void norm_kernel(const double2* __restrict__ data, int64_t n_times, int n, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* row = data + t * n;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double2 a = row[i];
+        acc = fma(a.x, a.x, acc);
+        acc = fma(a.y, a.y, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[t] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ <LL>, <L dt>
+// coef[i][0..4] = { ladder(l,m) [0 if m+1>l], ladder(l,-m) [0 if m-1<-l], ladder(l,m+1)ladder(l,m) [0 if m+2>l],
+//                   ladder(l,-(m-1))ladder(l,-m) [0 if m-2<-l], m }
+constexpr int NCOEF = 5;
+
+template <bool WITH_LDT>
+__global__ void ll_ldt_kernel(const double2* __restrict__ data, const double2* __restrict__ datadot, int64_t n_times,
+                              int n, const double* __restrict__ coef, double* __restrict__ LL, double* __restrict__ Ldt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* row = data + t * n;
+    const double2* rowd = WITH_LDT ? datadot + t * n : nullptr;
+    double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0, lx = 0, ly = 0, lz = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double* c = coef + i * NCOEF;
+        const double cp = c[0], cm = c[1], cpp = c[2], cmm = c[3], M = c[4];
+        const double2 a = row[i];
+        const double2 ap1 = cconj(row[i + 1 < n ? i + 1 : i]);
+        const double2 am1 = cconj(row[i >= 1 ? i - 1 : i]);
+        const double2 ap2 = cconj(row[i + 2 < n ? i + 2 : i]);
+        const double2 am2 = cconj(row[i >= 2 ? i - 2 : i]);
+        const double aa = a.x * a.x + a.y * a.y;
+        // products in the (+,-,z) basis, as in the reference
+        const double2 LpLp = cscale(cpp, cmul(ap2, a));
+        const double2 LmLm = cscale(cmm, cmul(am2, a));
+        const double LpLm = (cm != 0.0) ? aa * (cm * cm) : 0.0;   // ladder(l,m-1)*ladder(l,-m) = ladder(l,-m)^2
+        const double LmLp = (cp != 0.0) ? aa * (cp * cp) : 0.0;   // ladder(l,-(m+1))*ladder(l,m) = ladder(l,m)^2
+        const double2 p1 = cmul(ap1, a), m1 = cmul(am1, a);
+        const double2 LpLz = cscale(cp * M, p1);
+        const double2 LzLp = cscale((M + 1.0) * cp, p1);
+        const double2 LmLz = cscale(cm * M, m1);
+        const double2 LzLm = cscale((M - 1.0) * cm, m1);
+        const double LzLz = aa * (M * M);
+        // real parts of the symmetrised (x,y,z) products
+        sxx += 0.25 * (LpLp.x + LmLm.x + LmLp + LpLm);
+        // LxLy + LyLx = -0.25j*(2 LpLp - 2 LmLm)  -> real part = 0.5*(Im LpLp - Im LmLm); halved by the symmetrisation
+        sxy += 0.25 * (LpLp.y - LmLm.y);
+        sxz += 0.25 * ((LpLz.x + LmLz.x) + (LzLp.x + LzLm.x));
+        syy += -0.25 * (LpLp.x - LmLp - LpLm + LmLm.x);
+        // LyLz + LzLy = -0.5j*((LpLz - LmLz) + (LzLp - LzLm)) -> real part = 0.5*Im(...); halved
+        syz += 0.25 * ((LpLz.y - LmLz.y) + (LzLp.y - LzLm.y));
+        szz += LzLz;
+        if (WITH_LDT) {
+            const double2 ad = rowd[i];
+            const double2 Lp = cscale(cp, cmul(ap1, ad));
+            const double2 Lm = cscale(cm, cmul(am1, ad));
+            const double2 Lz = cscale(M, cmul(cconj(a), ad));
+            lx += 0.5 * (Lp.y + Lm.y);
+            ly += -0.5 * (Lp.x - Lm.x);
+            lz += Lz.y;
+        }
+    }
+    sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
+    syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
+    if (WITH_LDT) { lx = warp_sum(lx); ly = warp_sum(ly); lz = warp_sum(lz); }
+    if (lane == 0) {
+        double* o = LL + t * 9;
+        o[0] = sxx; o[1] = sxy; o[2] = sxz;
+        o[3] = sxy; o[4] = syy; o[5] = syz;
+        o[6] = sxz; o[7] = syz; o[8] = szz;
+        if (WITH_LDT) {
+            double* v = Ldt + t * 3;
+            v[0] = lx; v[1] = ly; v[2] = lz;
+        }
+    }
+}
+
+// <L>^a = sum conj(a1[m']) <L_a> a2[m]  (complex 3-vector)
+__global__ void l_vector_kernel(const double2* __restrict__ d1, const double2* __restrict__ d2, int64_t n_times, int n,
+                                const double* __restrict__ coef, double2* __restrict__ Lvec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* r1 = d1 + t * n;
+    const double2* r2 = d2 + t * n;
+    double2 sx = make_double2(0, 0), sy = sx, sz = sx;
+    for (int i = lane; i < n; i += 32) {
+        const double* c = coef + i * NCOEF;
+        const double2 b = r2[i];
+        const double2 Lp = cscale(c[0], cmul(cconj(r1[i + 1 < n ? i + 1 : i]), b));
+        const double2 Lm = cscale(c[1], cmul(cconj(r1[i >= 1 ? i - 1 : i]), b));
+        const double2 Lz = cscale(c[4], cmul(cconj(r1[i]), b));
+        sx.x += 0.5 * (Lp.x + Lm.x); sx.y += 0.5 * (Lp.y + Lm.y);
+        // -0.5j * (Lp - Lm)
+        sy.x += 0.5 * (Lp.y - Lm.y); sy.y += -0.5 * (Lp.x - Lm.x);
+        sz.x += Lz.x; sz.y += Lz.y;
+    }
+    sx.x = warp_sum(sx.x); sx.y = warp_sum(sx.y);
+    sy.x = warp_sum(sy.x); sy.y = warp_sum(sy.y);
+    sz.x = warp_sum(sz.x); sz.y = warp_sum(sz.y);
+    if (lane == 0) {
+        Lvec[t * 3 + 0] = sx; Lvec[t * 3 + 1] = sy; Lvec[t * 3 + 2] = sz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 3x3 symmetric eigenvector
+// Cyclic Jacobi on the 3x3 symmetric matrix; returns the unit eigenvector of the largest eigenvalue.
+__device__ void sym3_dominant(const double* A, double* v) {
+    double a[3][3] = {{A[0], A[1], A[2]}, {A[3], A[4], A[5]}, {A[6], A[7], A[8]}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        const double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+        if (off <= 1e-300 || off <= 1e-18 * diag) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            const double apq = a[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+            const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+            const int r = 3 - p - q;
+            const double app = a[p][p], aqq = a[q][q];
+            a[p][p] = app - tt * apq;
+            a[q][q] = aqq + tt * apq;
+            a[p][q] = a[q][p] = 0.0;
+            const double arp = a[r][p], arq = a[r][q];
+            a[r][p] = a[p][r] = c * arp - s * arq;
+            a[r][q] = a[q][r] = s * arp + c * arq;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double vkp = V[k][p], vkq = V[k][q];
+                V[k][p] = c * vkp - s * vkq;
+                V[k][q] = s * vkp + c * vkq;
+            }
+        }
+    }
+    int best = 0;
+    if (a[1][1] > a[best][best]) best = 1;
+    if (a[2][2] > a[best][best]) best = 2;
+    double x = V[0][best], y = V[1][best], z = V[2][best];
+    const double nrm = sqrt(x * x + y * y + z * z);
+    v[0] = x / nrm; v[1] = y / nrm; v[2] = z / nrm;
+}
+
+__global__ void sym3_dominant_eig_kernel(const double* __restrict__ LL, int64_t n_times, double* __restrict__ dpa) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_times) return;
+    double A[9], v[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = LL[t * 9 + k];
+    sym3_dominant(A, v);
+    dpa[t * 3 + 0] = v[0]; dpa[t * 3 + 1] = v[1]; dpa[t * 3 + 2] = v[2];
+}
+
+// ---- sign continuity (mode_calculations.py:316-363) as a scan over 2-state maps.
+// For step i with predecessor j (= i-1 going forward from i_index, i+1 going backward) the reference flips
+// raw v_i iff |v_i - s_j v_j|^2 > |v_i|^2, s_j the sign already applied to v_j.  map bit0 = flip if s_j=+1,
+// bit1 = flip if s_j=-1.
+__global__ void eig_sign_map_kernel(const double* __restrict__ dpa, int64_t n, int64_t i_index, unsigned char* __restrict__ maps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == i_index) { maps[i] = 0; return; }
+    const int64_t j = (i > i_index) ? i - 1 : i + 1;
+    const double x = dpa[i * 3], y = dpa[i * 3 + 1], z = dpa[i * 3 + 2];
+    const double px = dpa[j * 3], py = dpa[j * 3 + 1], pz = dpa[j * 3 + 2];
+    const double Norm = x * x + y * y + z * z;
+    const double dp = (x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz);
+    const double dm = (x + px) * (x + px) + (y + py) * (y + py) + (z + pz) * (z + pz);
+    maps[i] = (unsigned char)((dp > Norm ? 1 : 0) | (dm > Norm ? 2 : 0));
+}
+
+// one thread walks each direction (the maps are 1 byte/step, so even 1e6 steps is ~ms); a segmented
+// parallel scan replaces this when profiles say so
+__global__ void eig_sign_apply_kernel(double* __restrict__ dpa, int64_t n, int64_t i_index, const double* __restrict__ rough,
+                                      const unsigned char* __restrict__ maps, signed char* __restrict__ signs) {
+    if (blockIdx.x == 0 && threadIdx.x < 2) {
+        const double d0 = rough[0] * dpa[i_index * 3] + rough[1] * dpa[i_index * 3 + 1] + rough[2] * dpa[i_index * 3 + 2];
+        const signed char s0 = (d0 < 0.0) ? -1 : 1;
+        signed char s = s0;
+        if (threadIdx.x == 0) {
+            signs[i_index] = s0;
+            for (int64_t i = i_index + 1; i < n; ++i) {
+                const unsigned char m = maps[i];
+                const bool flip = (s > 0) ? (m & 1) : (m & 2);
+                s = flip ? -1 : 1;
+                signs[i] = s;
+            }
+        } else {
+            for (int64_t i = i_index - 1; i >= 0; --i) {
+                const unsigned char m = maps[i];
+                const bool flip = (s > 0) ? (m & 1) : (m & 2);
+                s = flip ? -1 : 1;
+                signs[i] = s;
+            }
+        }
+    }
+}
+
+__global__ void eig_sign_finish_kernel(double* __restrict__ dpa, int64_t n, const signed char* __restrict__ signs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = dpa[i * 3], y = dpa[i * 3 + 1], z = dpa[i * 3 + 2];
+    const double s = (double)signs[i];
+    x *= s; y *= s; z *= s;
+    const double nrm = sqrt(x * x + y * y + z * z);
+    if (nrm != 0.0 && nrm != 1.0) { x /= nrm; y /= nrm; z /= nrm; }
+    dpa[i * 3] = x; dpa[i * 3 + 1] = y; dpa[i * 3 + 2] = z;
+}
+
+// ------------------------------------------------------------------------------------------ 3x3 solve (LU, partial pivoting as gesv)
+__global__ void solve3_kernel(const double* __restrict__ A9, const double* __restrict__ b3, int64_t n, double scale,
+                              double* __restrict__ x3) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double a[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[r][c] = A9[t * 9 + r * 3 + c];
+        a[r][3] = b3[t * 3 + r];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int piv = k;
+        for (int r = k + 1; r < 3; ++r)
+            if (fabs(a[r][k]) > fabs(a[piv][k])) piv = r;
+        if (piv != k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const double tmp = a[k][c]; a[k][c] = a[piv][c]; a[piv][c] = tmp; }
+        }
+        for (int r = k + 1; r < 3; ++r) {
+            const double f = a[r][k] / a[k][k];
+#pragma unroll
+            for (int c = k; c < 4; ++c) a[r][c] -= f * a[k][c];
+        }
+    }
+    double x[3];
+    x[2] = a[2][3] / a[2][2];
+    x[1] = (a[1][3] - a[1][2] * x[2]) / a[1][1];
+    x[0] = (a[0][3] - a[0][1] * x[1] - a[0][2] * x[2]) / a[0][0];
+    x3[t * 3] = scale * x[0]; x3[t * 3 + 1] = scale * x[1]; x3[t * 3 + 2] = scale * x[2];
+}
+
+// ------------------------------------------------------------------------------------------ sparse <a|M|b>
+// K matrices share one pass over the rows: elements of matrix k are [seg[k], seg[k+1]).
+__global__ void sparse_expectation_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t n_times,
+                                          int n, const int* __restrict__ rows, const int* __restrict__ cols,
+                                          const double2* __restrict__ vals, const int* __restrict__ seg, int K,
+                                          double2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* ra = a + t * n;
+    const double2* rb = b + t * n;
+    for (int k = 0; k < K; ++k) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int e = seg[k] + lane; e < seg[k + 1]; e += 32) {
+            const double2 p = cmul(cconj(ra[rows[e]]), rb[cols[e]]);
+            cfma(acc, p, vals[e]);
+        }
+        acc.x = warp_sum(acc.x);
+        acc.y = warp_sum(acc.y);
+        if (lane == 0) out[t * K + k] = acc;
+    }
+}
+
+static inline unsigned warp_blocks(int64_t n_times) { return (unsigned)((n_times * 32 + 127) / 128); }
+
+}  // namespace scrib200
+
+using namespace scrib200;
+
+extern "C" int scrib200_norm(const double* data, int64_t n_times, int n_modes, double* out, void* stream) {
+    SCRIB200_REQUIRE(data && out, "norm: null pointer");
+    if (n_times <= 0) return SCRIB200_OK;
+    norm_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(data), n_times,
+                                                                       n_modes, out);
+    SCRIB200_CHECK_LAUNCH("norm");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_ll_ldt(const double* data, const double* datadot, int64_t n_times, int n_modes,
+                               const double* coef, double* LL, double* Ldt, void* stream) {
+    SCRIB200_REQUIRE(data && coef && LL, "ll_ldt: null pointer");
+    SCRIB200_REQUIRE((datadot == nullptr) == (Ldt == nullptr), "ll_ldt: datadot and Ldt go together");
+    if (n_times <= 0) return SCRIB200_OK;
+    if (datadot)
+        ll_ldt_kernel<true><<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const double2*>(data), reinterpret_cast<const double2*>(datadot), n_times, n_modes, coef, LL, Ldt);
+    else
+        ll_ldt_kernel<false><<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const double2*>(data), nullptr, n_times, n_modes, coef, LL, nullptr);
+    SCRIB200_CHECK_LAUNCH("ll_ldt");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_l_vector(const double* data1, const double* data2, int64_t n_times, int n_modes,
+                                 const double* coef, double* Lvec, void* stream) {
+    SCRIB200_REQUIRE(data1 && data2 && coef && Lvec, "l_vector: null pointer");
+    if (n_times <= 0) return SCRIB200_OK;
+    l_vector_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(data1), reinterpret_cast<const double2*>(data2), n_times, n_modes, coef,
+        reinterpret_cast<double2*>(Lvec));
+    SCRIB200_CHECK_LAUNCH("l_vector");
+    return SCRIB200_OK;
+}
+
+extern "C" size_t scrib200_dominant_eigenvector_workspace_bytes(int64_t n_times) { return (size_t)n_times * 2 + 16; }
+
+extern "C" int scrib200_dominant_eigenvector(const double* LL, int64_t n_times, const double* rough_direction,
+                                             int64_t rough_index, double* dpa, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    SCRIB200_REQUIRE(LL && rough_direction && dpa && workspace, "dominant_eigenvector: null pointer");
+    SCRIB200_REQUIRE(workspace_bytes >= scrib200_dominant_eigenvector_workspace_bytes(n_times),
+                     "dominant_eigenvector: workspace too small");
+    if (n_times <= 0) return SCRIB200_OK;
+    if (rough_index < 0) rough_index += n_times;
+    SCRIB200_REQUIRE(rough_index >= 0 && rough_index < n_times, "dominant_eigenvector: rough_index out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* maps = reinterpret_cast<unsigned char*>(workspace);
+    signed char* signs = reinterpret_cast<signed char*>(maps + n_times);
+    const unsigned nb = (unsigned)((n_times + 127) / 128);
+    sym3_dominant_eig_kernel<<<nb, 128, 0, st>>>(LL, n_times, dpa);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(eig)");
+    eig_sign_map_kernel<<<nb, 128, 0, st>>>(dpa, n_times, rough_index, maps);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(map)");
+    eig_sign_apply_kernel<<<1, 32, 0, st>>>(dpa, n_times, rough_index, rough_direction, maps, signs);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(scan)");
+    eig_sign_finish_kernel<<<nb, 128, 0, st>>>(dpa, n_times, signs);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(finish)");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_solve3(const double* A, const double* b, int64_t n, double scale, double* x, void* stream) {
+    SCRIB200_REQUIRE(A && b && x, "solve3: null pointer");
+    if (n <= 0) return SCRIB200_OK;
+    solve3_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, b, n, scale, x);
+    SCRIB200_CHECK_LAUNCH("solve3");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_times, int n_modes,
+                                           const int* rows, const int* cols, const double* vals, const int* seg_host,
+                                           const int* seg_dev, int K, double* out, void* stream) {
+    SCRIB200_REQUIRE(a && b && rows && cols && vals && seg_dev && out, "sparse_expectation: null pointer");
+    SCRIB200_REQUIRE(K >= 1, "sparse_expectation: K=%d", K);
+    (void)seg_host;
+    if (n_times <= 0) return SCRIB200_OK;
+    sparse_expectation_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, rows, cols,
+        reinterpret_cast<const double2*>(vals), seg_dev, K, reinterpret_cast<double2*>(out));
+    SCRIB200_CHECK_LAUNCH("sparse_expectation");
+    return SCRIB200_OK;
+}

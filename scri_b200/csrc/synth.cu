@@ -1,0 +1,169 @@
+// K1: SWSH synthesis as one real FP64 tensor-core GEMM with the BMS epilogue fused.
+//
+// Replaces scri/waveform_grid.py:475-484 (np.tensordot -> zgemm), :486-503 (constant data-type
+// correction) and :559 (conformal factor):   F[i,g] = (sum_lm a[i,lm] Y[g,lm] - c[g]) * k[g]^w.
+//
+// The complex product is folded into a real GEMM: A = modes viewed as real [N, K=2n] (re,im
+// interleaved, exactly the caller's memory), B = packed real table [Kpad, Ncpad] with
+//   B[2lm, 2g] = Re Y, B[2lm+1, 2g] = -Im Y, B[2lm, 2g+1] = Im Y, B[2lm+1, 2g+1] = Re Y
+// so that C = A.B is F with re/im interleaved.  8*n*G flops per time step, none redundant.
+//
+// sm_100a has no tcgen05 kind for f64; the FP64 tensor path is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
+// CTA tile 128x64, 8 warps as 4(M) x 2(N), warp tile 32x32 = 4x4 DMMA tiles (32 accumulator doubles
+// per thread); K is streamed in BK=16 slabs through a 4-stage cp.async ring; shared-memory strides
+// (20 and 68 doubles) make both fragment loads bank-conflict free.
+#include "common.cuh"
+
+namespace scrib200 {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int AS = BK + 4;   // A smem row stride (doubles)
+constexpr int BS = BN + 4;   // B smem row stride (doubles)
+constexpr int A_STAGE = BM * AS;
+constexpr int B_STAGE = BK * BS;
+constexpr int SYNTH_THREADS = 256;
+constexpr size_t SYNTH_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(SYNTH_THREADS, 2)
+swsh_synth_dmma_kernel(const double* __restrict__ A, int64_t M, int K, const double* __restrict__ B, int Kpad,
+                       int Ncpad, const double* __restrict__ offset, const double* __restrict__ scale, int Nc,
+                       double* __restrict__ C) {
+    extern __shared__ __align__(16) double smem_d[];
+    double* sA = smem_d;
+    double* sB = smem_d + STAGES * A_STAGE;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;           // 4 x 2 warps
+    const int64_t row0 = (int64_t)blockIdx.y * BM;
+    const int col0 = blockIdx.x * BN;
+    const int KT = Kpad / BK;
+
+    auto load_stage = [&](int stage, int kt) {
+        const int k0 = kt * BK;
+        // A: 128 rows x 16 doubles = 128 x 8 chunks of 16 B -> 4 chunks per thread
+        double* a_dst = sA + stage * A_STAGE;
+#pragma unroll
+        for (int c = 0; c < (BM * BK / 2) / SYNTH_THREADS; ++c) {
+            int chunk = tid + c * SYNTH_THREADS;
+            int r = chunk >> 3, kc = (chunk & 7) * 2;
+            int64_t gr = row0 + r;
+            int k = k0 + kc;
+            int bytes = (gr < M && k < K) ? 16 : 0;   // K is even, so a chunk is all-in or all-out
+            const double* src = A + (bytes ? (gr * K + k) : 0);
+            cp_async16(a_dst + r * AS + kc, src, bytes);
+        }
+        // B: 16 rows x 64 doubles = 16 x 32 chunks -> 2 chunks per thread (table is pre-padded)
+        double* b_dst = sB + stage * B_STAGE;
+#pragma unroll
+        for (int c = 0; c < (BK * BN / 2) / SYNTH_THREADS; ++c) {
+            int chunk = tid + c * SYNTH_THREADS;
+            int r = chunk >> 5, nc = (chunk & 31) * 2;
+            cp_async16(b_dst + r * BS + nc, B + (size_t)(k0 + r) * Ncpad + col0 + nc, 16);
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    const int ar = lane >> 2, ak = lane & 3;   // A fragment: row = lane/4, k = lane%4
+    const int bk = lane & 3, bn = lane >> 2;   // B fragment: k = lane%4, n = lane/4
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk % STAGES, nk);
+            cp_async_commit();
+        }
+        const double* a_s = sA + (kt % STAGES) * A_STAGE + (wm * 32 + ar) * AS + ak;
+        const double* b_s = sB + (kt % STAGES) * B_STAGE + bk * BS + wn * 32 + bn;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = a_s[i * 8 * AS + ks * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[ks * 4 * BS + j * 8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: (acc - offset[col]) * scale[col]; C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+    const int cr = lane >> 2, cc = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int col = col0 + wn * 32 + j * 8 + cc;
+        if (col >= Nc) continue;
+        double2 off = *reinterpret_cast<const double2*>(offset + col);
+        double2 scl = *reinterpret_cast<const double2*>(scale + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int64_t row = row0 + wm * 32 + i * 8 + cr;
+            if (row >= M) continue;
+            double2 v;
+            v.x = (acc[i][j][0] - off.x) * scl.x;
+            v.y = (acc[i][j][1] - off.y) * scl.y;
+            *reinterpret_cast<double2*>(C + row * Nc + col) = v;
+        }
+    }
+}
+
+}  // namespace scrib200
+
+extern "C" int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, const double* Bmat,
+                                        int Kpad, int Ncpad, const double* offset, const double* scale, int G,
+                                        double* F, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(modes && Bmat && offset && scale && F, "swsh_synthesize: null pointer");
+    SCRIB200_REQUIRE(n_modes > 0 && G > 0, "swsh_synthesize: bad sizes n_modes=%d G=%d", n_modes, G);
+    const int K = 2 * n_modes, Nc = 2 * G;
+    SCRIB200_REQUIRE(Kpad % BK == 0 && Kpad >= K, "swsh_synthesize: Kpad=%d must be a multiple of %d >= %d", Kpad, BK, K);
+    SCRIB200_REQUIRE(Ncpad % BN == 0 && Ncpad >= Nc, "swsh_synthesize: Ncpad=%d must be a multiple of %d >= %d", Ncpad,
+                     BN, Nc);
+    SCRIB200_REQUIRE(aligned16(modes) && aligned16(Bmat) && aligned16(F) && aligned16(offset) && aligned16(scale),
+                     "swsh_synthesize: pointers must be 16-byte aligned");
+    if (n_times <= 0) return SCRIB200_OK;
+    cudaFuncSetAttribute(swsh_synth_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYNTH_SMEM);
+    // column tiles fastest so the CTAs sharing an A row-tile run together (A is then read from HBM once);
+    // gridDim.y is limited to 65535, so very long series go in slabs of rows
+    const int64_t max_rows = (int64_t)65535 * BM;
+    for (int64_t r0 = 0; r0 < n_times; r0 += max_rows) {
+        int64_t rows = n_times - r0 < max_rows ? n_times - r0 : max_rows;
+        dim3 grid(Ncpad / BN, (unsigned)((rows + BM - 1) / BM));
+        swsh_synth_dmma_kernel<<<grid, SYNTH_THREADS, SYNTH_SMEM, (cudaStream_t)stream>>>(
+            modes + r0 * K, rows, K, Bmat, Kpad, Ncpad, offset, scale, Nc, F + r0 * Nc);
+        SCRIB200_CHECK_LAUNCH("swsh_synthesize");
+    }
+    return SCRIB200_OK;
+}

@@ -1,0 +1,186 @@
+"""Energy / momentum / angular-momentum fluxes (mirrors scri/flux.py:11-441), expectation values on the GPU.
+
+The sparse matrix elements (p_z, p_+-, j_z, j_+-) are tiny host tables built once per (ell_min, ell_max) and
+cached, as in the reference (flux.py:11-37 lru_cache); the per-time-step sums <a|M|b>(t) - the hot loop
+flux.py:40-78 - run as one fused pass over the modes for all three components.
+"""
+import functools
+import math
+
+import numpy as np
+
+from . import _sf, ops
+from .constants import h as htype
+from .constants import hdot as hdottype
+
+
+@functools.lru_cache(maxsize=None)
+def _log_factorials(n):
+    out = [0.0] * (n + 1)
+    for i in range(2, n + 1):
+        out[i] = out[i - 1] + math.log(i)
+    return out
+
+
+def clebsch_gordan(j1, m1, j2, m2, j3, m3):
+    """<j1 m1 j2 m2|j3 m3> for integer arguments (sf.clebsch_gordan argument order; scri/flux.py:7)."""
+    if m1 + m2 != m3 or abs(m1) > j1 or abs(m2) > j2 or abs(m3) > j3 or j3 < abs(j1 - j2) or j3 > j1 + j2:
+        return 0.0
+    f = math.factorial
+    pre = (2 * j3 + 1) * f(j3 + j1 - j2) * f(j3 - j1 + j2) * f(j1 + j2 - j3) / f(j1 + j2 + j3 + 1)
+    pre *= f(j3 + m3) * f(j3 - m3) * f(j1 - m1) * f(j1 + m1) * f(j2 - m2) * f(j2 + m2)
+    s = 0.0
+    for k in range(max(0, j2 - j3 - m1, j1 - j3 + m2), min(j1 + j2 - j3, j1 - m1, j2 + m2) + 1):
+        s += (-1) ** k / (f(k) * f(j1 + j2 - j3 - k) * f(j1 - m1 - k) * f(j2 + m2 - k) * f(j3 - j2 + m1 + k) * f(j3 - j1 - m2 + k))
+    return math.sqrt(pre) * s
+
+
+def _as_matrix(elements, ell_min):
+    rows, cols, vals = zip(*((_sf.LM_index(lp, mp, ell_min), _sf.LM_index(l, m, ell_min), v) for lp, mp, l, m, v in elements))
+    return np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32), np.array(vals, dtype=complex)
+
+
+@functools.lru_cache(maxsize=None)
+def p_z(ell_min, ell_max, s=-2):
+    """<s,j,m|cos(theta)|s,l,m> (scri/flux.py:213-246)"""
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            for m in range(-ell, ell + 1):
+                if abs(m) > ellp:
+                    continue
+                v = math.sqrt((2.0 * ell + 1.0) / (2.0 * ellp + 1.0)) * clebsch_gordan(ell, m, 1, 0, ellp, m) * clebsch_gordan(ell, -s, 1, 0, ellp, -s)
+                out.append((ellp, m, ell, m, v))
+    return _as_matrix(out, ell_min)
+
+
+@functools.lru_cache(maxsize=None)
+def p_plusminus(ell_min, ell_max, sign, s=-2):
+    """p+- = sin(theta) exp(+-i phi) matrix elements (scri/flux.py:249-294)"""
+    if sign not in (1, -1):
+        raise ValueError("sign must be either 1 or -1 in p_plusminus")
+    prefac = -1.0 * sign * math.sqrt(8.0 * math.pi / 3.0)
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            for m in range(-ell, ell + 1):
+                mp = m + sign
+                if abs(mp) > ellp:
+                    continue
+                el = math.sqrt(3.0 * (2.0 * ell + 1.0) / (4.0 * math.pi * (2.0 * ellp + 1))) * clebsch_gordan(1, sign, ell, m, ellp, mp) * clebsch_gordan(1, 0, ell, -s, ellp, -s)
+                out.append((ellp, mp, ell, m, prefac * el))
+    return _as_matrix(out, ell_min)
+
+
+p_plus = functools.partial(p_plusminus, sign=+1)
+p_minus = functools.partial(p_plusminus, sign=-1)
+
+
+@functools.lru_cache(maxsize=None)
+def j_z(ell_min, ell_max):
+    """<j,n|j^z|l,m> = i m (scri/flux.py:345-358)"""
+    return _as_matrix([(ell, m, ell, m, 1.0j * m) for ell in range(ell_min, ell_max + 1) for m in range(-ell, ell + 1)], ell_min)
+
+
+@functools.lru_cache(maxsize=None)
+def j_plusminus(ell_min, ell_max, sign):
+    """<j,n|j^+-|l,m> = i sqrt((l-+m)(l+-m+1)) (scri/flux.py:361-385)"""
+    if sign not in (1, -1):
+        raise ValueError("sign must be either 1 or -1 in j_plusminus")
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for m in range(-ell, ell + 1):
+            mp = m + sign
+            if abs(mp) > ell:
+                continue
+            out.append((ell, mp, ell, m, 1.0j * math.sqrt((ell - m * sign) * (ell + m * sign + 1))))
+    return _as_matrix(out, ell_min)
+
+
+j_plus = functools.partial(j_plusminus, sign=+1)
+j_minus = functools.partial(j_plusminus, sign=-1)
+
+
+def sparse_expectation_value(abar, rows, columns, values, b):
+    """<a|M|b> given conj(a) - same contract as scri/flux.py:40-78."""
+    return ops.sparse_expectation(np.conj(abar), b, [(rows, columns, values)])[:, 0]
+
+
+def matrix_expectation_value(a, M, b, allow_LM_differ=False, allow_times_differ=False):
+    """(times, <a|M|b>(u)) (scri/flux.py:81-179).  `M(ell_min, ell_max)` returns (rows, columns, values)."""
+    if a.spin_weight != b.spin_weight:
+        raise ValueError("Spin weights must match in matrix_expectation_value")
+    if (a.ell_min != b.ell_min) or (a.ell_max != b.ell_max):
+        raise ValueError("ell_min and ell_max must match in matrix_expectation_value (allow_LM_differ is not supported on the GPU path)")
+    if not np.array_equal(a.t, b.t):
+        raise ValueError("Time samples must match in matrix_expectation_value (allow_times_differ is not supported on the GPU path)")
+    rows, columns, values = M(a.ell_min, a.ell_max)
+    return (a.t, ops.sparse_expectation(a.data, b.data, [(rows, columns, values)])[:, 0])
+
+
+def _hdot_of(hw, name):
+    from .waveform_modes import WaveformModes
+
+    if not isinstance(hw, WaveformModes):
+        raise ValueError(f"{name} can only be calculated from a `WaveformModes` object; this object is of type `{type(hw)}`.")
+    if hw.dataType == hdottype:
+        return hw.data
+    if hw.dataType == htype:
+        return hw.data_dot
+    raise ValueError(f"Input argument is expected to have data of type `h` or `hdot`; this waveform data has type `{hw.data_type_string}`")
+
+
+def energy_flux(h):
+    """dE/dt = sum |hdot|^2 / 16 pi (scri/flux.py:182-210, Ruiz et al. 2008 eq. 2.8)"""
+    hdot = _hdot_of(h, "Energy flux")
+    return ops.norm(hdot) / (16.0 * np.pi)
+
+
+def momentum_flux(h):
+    """dp/dt (scri/flux.py:303-342, Ruiz et al. 2008 eq. 2.11)"""
+    hdot = _hdot_of(h, "Momentum flux")
+    lmin, lmax = h.ell_min, h.ell_max
+    ev = ops.sparse_expectation(hdot, hdot, [p_plus(lmin, lmax, s=-2), p_minus(lmin, lmax, s=-2), p_z(lmin, lmax, s=-2)])
+    pdot = np.zeros((hdot.shape[0], 3), dtype=float)
+    pdot[:, 0] = 0.5 * (ev[:, 0].real + ev[:, 1].real)
+    pdot[:, 1] = 0.5 * (ev[:, 0].imag - ev[:, 1].imag)
+    pdot[:, 2] = ev[:, 2].real
+    pdot /= 16.0 * np.pi
+    return pdot
+
+
+def angular_momentum_flux(h, hdot=None):
+    """dJ/dt (scri/flux.py:394-441, Ruiz et al. 2008 eq. 2.24)"""
+    from .waveform_modes import WaveformModes
+
+    if not isinstance(h, WaveformModes):
+        raise ValueError(f"Angular momentum flux can only be calculated from a `WaveformModes` object; `h` is of type `{type(h)}`.")
+    if (hdot is not None) and (not isinstance(hdot, WaveformModes)):
+        raise ValueError(f"Angular momentum flux can only be calculated from a `WaveformModes` object; `hdot` is of type `{type(hdot)}`.")
+    if h.dataType != htype:
+        raise ValueError(f"Input argument `h` is expected to have data of type `h`; this `h` waveform data has type `{h.data_type_string}`")
+    if hdot is None:
+        hdot_data = h.data_dot
+    elif hdot.dataType != hdottype:
+        raise ValueError(f"Input argument `hdot` is expected to have data of type `hdot`; this `hdot` waveform data has type `{hdot.data_type_string}`")
+    else:
+        hdot_data = hdot.data
+    lmin, lmax = h.ell_min, h.ell_max
+    ev = ops.sparse_expectation(hdot_data, h.data, [j_plus(lmin, lmax), j_minus(lmin, lmax), j_z(lmin, lmax)])
+    jdot = np.zeros((h.n_times, 3), dtype=float)
+    jdot[:, 0] = 0.5 * (ev[:, 0].real + ev[:, 1].real)
+    jdot[:, 1] = 0.5 * (ev[:, 0].imag - ev[:, 1].imag)
+    jdot[:, 2] = ev[:, 2].real
+    jdot /= -16.0 * np.pi
+    return jdot
+
+
+def poincare_fluxes(h, hdot=None):
+    """(energy, momentum, angular-momentum) fluxes with one time derivative (scri/flux.py:750-797, without boost)."""
+    from .waveform_modes import WaveformModes
+
+    if hdot is None:
+        hdot = h.copy()
+        hdot.dataType = hdottype
+        hdot.data = h.data_dot
+    return (energy_flux(hdot), momentum_flux(hdot), angular_momentum_flux(h, hdot))

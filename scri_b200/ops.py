@@ -1,0 +1,273 @@
+"""Operator layer: numpy (host) in -> CUDA kernels through the C ABI -> numpy out.
+
+Each function is the drop-in for one numba / third-party kernel the reference calls on the hot path
+(SURVEY.md 8b).  Host arrays are staged through pinned memory; every function also accepts CUDA
+tensors (then nothing is copied and a CUDA tensor is returned), which is what bench.py's
+device-resident `value` uses.  No CPU fallback: without a CUDA device these raise Scrib200Error.
+"""
+import numpy as np
+
+from . import _lib, _sf
+from . import _quaternion as Q
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def is_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+def to_device(x, dtype=None):
+    """numpy -> CUDA tensor via pinned staging (no-op for CUDA tensors)."""
+    torch = _torch()
+    if is_tensor(x):
+        return x if x.is_cuda else x.cuda()
+    a = np.ascontiguousarray(x)
+    if dtype is not None and a.dtype != dtype:
+        a = a.astype(dtype)
+    th = torch.from_numpy(a)
+    try:
+        th = th.pin_memory()
+    except RuntimeError:
+        pass
+    return th.to("cuda", non_blocking=True)
+
+
+def to_host(x):
+    return x.cpu().numpy() if is_tensor(x) else x
+
+
+_table_cache = {}
+
+
+def wigner_tables_device(ell_max):
+    torch = _torch()
+    key = ("wig", ell_max, torch.cuda.current_device())
+    if key not in _table_cache:
+        seed, rec = _sf.wigner_tables(ell_max)
+        _table_cache[key] = (torch.from_numpy(np.ascontiguousarray(seed)).cuda(), torch.from_numpy(np.ascontiguousarray(rec)).cuda())
+    return _table_cache[key]
+
+
+def rotate_modes(data, R, ell_min, ell_max):
+    """In-place Wigner-D rotation  a'_{lm} = sum_m' a_{lm'} D^l_{m'm}(R)  (scri/rotations.py:346-392).
+
+    data: [n_times, n_modes] complex (numpy: rotated copy is written back into `data`; CUDA tensor: in place)
+    R: one rotor [4] or a series [n_times, 4] (float) - or CUDA tensor of spinors [n_times, 2] complex.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    d = to_device(data, np.complex128)
+    if is_tensor(R):
+        sp = R
+        stride = 2 if sp.shape[0] == d.shape[0] and sp.dim() == 2 else 0
+    else:
+        Rf = np.asarray(R, dtype=float)
+        sp_np = Q.as_spinor_array(Rf)
+        stride = 2 if Rf.ndim == 2 else 0
+        sp = to_device(sp_np, np.complex128)
+    seed, rec = wigner_tables_device(ell_max)
+    _lib.check(
+        lib.scrib200_rotate_modes(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(seed), _lib.ptr(rec), _lib.stream_ptr()),
+        "rotate_modes",
+    )
+    if is_tensor(data):
+        return data
+    data[...] = d.cpu().numpy()
+    return data
+
+
+def map2salm(grid, s, ell_max, n_theta=None, n_phi=None, ell_min=0):
+    """spinsfast.map2salm replacement, batched over leading axes: [..., n_theta, n_phi] -> [..., n_modes]."""
+    from .plan import map2salm as _m2s
+
+    torch = _torch()
+    if is_tensor(grid):
+        g = grid
+    else:
+        g = to_device(np.asarray(grid, dtype=complex), np.complex128)
+    if n_theta is None:
+        n_theta, n_phi = g.shape[-2:]
+    lead = g.shape[:-2] if g.dim() >= 2 and g.shape[-2:] == (n_theta, n_phi) else g.shape[:-1]
+    g2 = g.reshape(-1, n_theta * n_phi)
+    E, Wt = _sf.analysis_tables(s, ell_min, ell_max, n_theta, n_phi)
+    dE = torch.from_numpy(np.ascontiguousarray(E)).cuda()
+    dW = torch.from_numpy(Wt).cuda()
+    out = _m2s(g2, n_theta, n_phi, ell_min, ell_max, dE, dW).reshape(tuple(lead) + (-1,))
+    return out if is_tensor(grid) else out.cpu().numpy()
+
+
+def norm(data):
+    """sum_modes |a|^2 per time step (scri/waveform_base.py:19-35)."""
+    lib = _lib.load()
+    torch = _torch()
+    d = to_device(data, np.complex128)
+    out = torch.empty(d.shape[0], dtype=torch.float64, device="cuda")
+    _lib.check(lib.scrib200_norm(_lib.ptr(d), d.shape[0], d.shape[1], _lib.ptr(out), _lib.stream_ptr()), "norm")
+    return out if is_tensor(data) else out.cpu().numpy()
+
+
+def _ones_zeros(n):
+    torch = _torch()
+    key = ("oz", n, torch.cuda.current_device())
+    if key not in _table_cache:
+        _table_cache[key] = (torch.ones(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda"))
+    return _table_cache[key]
+
+
+def spline_calculus(t, data, kind, order=1, tprime=None):
+    """Not-a-knot cubic spline along time of every (complex) column: derivative at the knots, or evaluation.
+
+    Replaces CubicSpline(t, data).derivative(k)(t) (scri/waveform_base.py:689-695) and
+    CubicSpline(t, data)(tprime) (:964).  The antiderivatives (:697-703) are not on the GPU path yet.
+    """
+    lib = _lib.load()
+    torch = _torch()
+    tt = to_device(t, np.float64)
+    d = to_device(data, np.complex128)
+    N = d.shape[0]
+    d2 = d.reshape(N, -1)
+    ncol = d2.shape[1]
+    ones, zeros = _ones_zeros(ncol)
+    need = lib.scrib200_spline_remap_workspace_bytes(N, ncol, 0)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    if kind == "derivative":
+        out = torch.empty_like(d2)
+        _lib.check(
+            lib.scrib200_spline_derivative(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), int(order),
+                                           _lib.ptr(out), 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "spline_derivative",
+        )
+        out = out.reshape(d.shape)
+    elif kind == "evaluate":
+        tp = to_device(tprime, np.float64)
+        out = torch.empty((tp.shape[0], ncol), dtype=torch.complex128, device="cuda")
+        _lib.check(
+            lib.scrib200_bms_spline_remap(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), _lib.ptr(tp),
+                                          tp.shape[0], _lib.ptr(out), 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "bms_spline_remap",
+        )
+        out = out.reshape((tp.shape[0],) + tuple(d.shape[1:]))
+    else:
+        raise NotImplementedError(f"spline_calculus kind={kind!r} is not implemented on the GPU path")
+    return out if is_tensor(data) else out.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------- mode_calculations
+def ladder_table(ell_min, ell_max):
+    """[n_modes, 5] coefficient table for scrib200_ll_ldt / scrib200_l_vector.
+
+    Columns: ladder(l,m), ladder(l,-m), ladder(l,m+1)ladder(l,m), ladder(l,-(m-1))ladder(l,-m), m, with
+    ladder(l,m) = sqrt((l-m)(l+m+1)) (sf.ladder_operator_coefficient; scri/mode_calculations.py:9) and zeros
+    where the reference's `if M + 1 <= L` guards exclude the term.
+    """
+    import math
+
+    def lad(l, m):
+        v = (l - m) * (l + m + 1)
+        return math.sqrt(v) if v > 0 else 0.0
+
+    rows = []
+    for l in range(ell_min, ell_max + 1):
+        for m in range(-l, l + 1):
+            rows.append([
+                lad(l, m) if m + 1 <= l else 0.0,
+                lad(l, -m) if m - 1 >= -l else 0.0,
+                lad(l, m + 1) * lad(l, m) if m + 2 <= l else 0.0,
+                lad(l, -(m - 1)) * lad(l, -m) if m - 2 >= -l else 0.0,
+                float(m),
+            ])
+    return np.array(rows, dtype=float).reshape(-1, 5)
+
+
+def _ladder_device(ell_min, ell_max):
+    torch = _torch()
+    key = ("lad", ell_min, ell_max, torch.cuda.current_device())
+    if key not in _table_cache:
+        _table_cache[key] = torch.from_numpy(ladder_table(ell_min, ell_max)).cuda()
+    return _table_cache[key]
+
+
+def ll_ldt(data, datadot, ell_min, ell_max):
+    """(<LL> [N,3,3], <Ldt> [N,3] or None)  - scri/mode_calculations.py:14-43, 209-295."""
+    lib = _lib.load()
+    torch = _torch()
+    d = to_device(data, np.complex128)
+    dd = None if datadot is None else to_device(datadot, np.complex128)
+    N, n = d.shape
+    coef = _ladder_device(ell_min, ell_max)
+    LL = torch.empty((N, 3, 3), dtype=torch.float64, device="cuda")
+    Ldt = None if dd is None else torch.empty((N, 3), dtype=torch.float64, device="cuda")
+    _lib.check(
+        lib.scrib200_ll_ldt(_lib.ptr(d), None if dd is None else _lib.ptr(dd), N, n, _lib.ptr(coef), _lib.ptr(LL),
+                            None if Ldt is None else _lib.ptr(Ldt), _lib.stream_ptr()),
+        "ll_ldt",
+    )
+    if is_tensor(data):
+        return LL, Ldt
+    return LL.cpu().numpy(), (None if Ldt is None else Ldt.cpu().numpy())
+
+
+def l_vector(data1, data2, ell_min, ell_max):
+    """<L> complex [N,3] - scri/mode_calculations.py:60-89."""
+    lib = _lib.load()
+    torch = _torch()
+    d1 = to_device(data1, np.complex128)
+    d2 = d1 if data2 is data1 else to_device(data2, np.complex128)
+    N, n = d1.shape
+    coef = _ladder_device(ell_min, ell_max)
+    out = torch.empty((N, 3), dtype=torch.complex128, device="cuda")
+    _lib.check(lib.scrib200_l_vector(_lib.ptr(d1), _lib.ptr(d2), N, n, _lib.ptr(coef), _lib.ptr(out), _lib.stream_ptr()), "l_vector")
+    return out if is_tensor(data1) else out.cpu().numpy()
+
+
+def dominant_eigenvector(LL, rough_direction, rough_index):
+    """Dominant principal axis of LL made continuous - np.linalg.eigh + mode_calculations.py:316-363."""
+    lib = _lib.load()
+    torch = _torch()
+    L = to_device(LL, np.float64)
+    N = L.shape[0]
+    rd = rough_direction if is_tensor(rough_direction) else to_device(np.asarray(rough_direction, dtype=float), np.float64)
+    out = torch.empty((N, 3), dtype=torch.float64, device="cuda")
+    need = lib.scrib200_dominant_eigenvector_workspace_bytes(N)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _lib.check(
+        lib.scrib200_dominant_eigenvector(_lib.ptr(L), N, _lib.ptr(rd), int(rough_index), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+        "dominant_eigenvector",
+    )
+    return out if is_tensor(LL) else out.cpu().numpy()
+
+
+def solve3(A, b, scale=1.0):
+    """scale * A^-1 b for batched 3x3 systems - np.linalg.solve at mode_calculations.py:424."""
+    lib = _lib.load()
+    torch = _torch()
+    Ad = to_device(A, np.float64)
+    bd = to_device(b, np.float64)
+    x = torch.empty_like(bd)
+    _lib.check(lib.scrib200_solve3(_lib.ptr(Ad), _lib.ptr(bd), Ad.shape[0], float(scale), _lib.ptr(x), _lib.stream_ptr()), "solve3")
+    return x if is_tensor(A) else x.cpu().numpy()
+
+
+def sparse_expectation(a, b, matrices):
+    """[N, K] complex: <a|M_k|b>(t) for K sparse matrices (rows, cols, vals) - scri/flux.py:40-78."""
+    lib = _lib.load()
+    torch = _torch()
+    ad = to_device(a, np.complex128)
+    bd = ad if b is a else to_device(b, np.complex128)
+    N, n = ad.shape
+    rows = np.concatenate([np.asarray(m[0], dtype=np.int32) for m in matrices])
+    cols = np.concatenate([np.asarray(m[1], dtype=np.int32) for m in matrices])
+    vals = np.concatenate([np.asarray(m[2], dtype=complex) for m in matrices])
+    seg = np.zeros(len(matrices) + 1, dtype=np.int32)
+    seg[1:] = np.cumsum([len(m[0]) for m in matrices])
+    K = len(matrices)
+    dr, dc, dv, ds = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg))
+    out = torch.empty((N, K), dtype=torch.complex128, device="cuda")
+    _lib.check(
+        lib.scrib200_sparse_expectation(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dc), _lib.ptr(dv), None, _lib.ptr(ds), K, _lib.ptr(out), _lib.stream_ptr()),
+        "sparse_expectation",
+    )
+    return out if is_tensor(a) else out.cpu().numpy()

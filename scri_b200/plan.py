@@ -1,0 +1,362 @@
+"""Host-side planning for the BMS transformation and the device pipeline that executes it.
+
+`process_transformation_kwargs` mirrors scri/waveform_grid.py:20-190 (same keyword names, defaults,
+validation and exception types); it is O(G) host work done once per call, exactly as in the
+reference.  `TransformPlan` turns its result into device-resident tables and runs the three
+kernels of the path (SWSH synthesis -> retarded-time spline remap -> SWSH analysis) through the
+C ABI in include/scrib200.h.
+"""
+import math
+import pprint
+import warnings
+
+import numpy as np
+
+from . import _lib, _sf
+from . import _quaternion as Q
+from .constants import ConformalWeights, DataNames, RScaling, SpinWeights, h, hdot, news, psi0, psi1, psi2, psi3, psi4, sigma
+
+
+def process_transformation_kwargs(ell_max, **kwargs):
+    """Parse the BMS-transformation keywords (scri/waveform_grid.py:20-190).
+
+    Returns (supertranslation, ell_max_supertranslation, ell_max, n_theta, n_phi, boost_velocity, beta,
+    gamma, varphi, R_j_k, thetaprm_phiprm, kwargs) - `R_j_k` is a float array [n_theta, n_phi, 4].
+    """
+    supertranslation = np.zeros((4,), dtype=complex)
+    ell_max_supertranslation = 1
+    if "supertranslation" in kwargs:
+        supertranslation = np.array(kwargs.pop("supertranslation"), dtype=complex)
+        if supertranslation.dtype != "complex" and supertranslation.size > 0:
+            raise TypeError(
+                "\nInput argument `supertranslation` should be a complex array with size>0.\n"
+                f"Got a {supertranslation.dtype} array of shape {supertranslation.shape}."
+            )
+        if supertranslation.size <= 4:
+            supertranslation = np.pad(supertranslation, (0, 4 - supertranslation.size), "constant", constant_values=(0.0,))
+        ell_max_supertranslation = int(np.sqrt(len(supertranslation))) - 1
+        if (ell_max_supertranslation + 1) ** 2 != len(supertranslation):
+            raise ValueError(
+                "\nInput supertranslation parameter must contain modes from ell=0 up to some ell_max, including\n"
+                "all relevant m modes in standard order.  Thus, it must be an array with length given by a "
+                f"perfect square; its length is {len(supertranslation)}"
+            )
+        for ell in range(ell_max_supertranslation + 1):
+            for m in range(ell + 1):
+                i_pos = _sf.LM_index(ell, m, 0)
+                i_neg = _sf.LM_index(ell, -m, 0)
+                a = supertranslation[i_pos]
+                b = supertranslation[i_neg]
+                if abs(a - (-1.0) ** m * b.conjugate()) > 3e-16 + 1e-15 * abs(b):
+                    raise ValueError(
+                        f"\nsupertranslation[{i_pos}]={a}  # (ell,m)=({ell},{m})\n"
+                        f"supertranslation[{i_neg}]={b}  # (ell,m)=({ell},{-m})\n"
+                        "Will result in an imaginary supertranslation."
+                    )
+    s4pi = math.sqrt(4 * math.pi)
+    c1 = math.sqrt(2 * math.pi / 3)
+    c0 = math.sqrt(4 * math.pi / 3)
+
+    def vector_as_ell_1_modes(v):
+        return np.array([c1 * (v[0] + 1j * v[1]), c0 * v[2], c1 * (-v[0] + 1j * v[1])], dtype=complex)
+
+    def vector_from_ell_1_modes(a):
+        return np.array([(a[0] - a[2]) / (2 * c1), (a[0] + a[2]) / (2j * c1), a[1] / c0])
+
+    spacetime_translation = np.zeros((4,), dtype=float)
+    spacetime_translation[0] = (supertranslation[0] / s4pi).real
+    spacetime_translation[1:4] = -vector_from_ell_1_modes(supertranslation[1:4]).real
+    if "spacetime_translation" in kwargs:
+        st_trans = np.array(kwargs.pop("spacetime_translation"), dtype=float)
+        if st_trans.shape != (4,) or st_trans.dtype != "float":
+            raise TypeError(
+                "\nInput argument `spacetime_translation` should be a float array of shape (4,).\n"
+                f"Got a {st_trans.dtype} array of shape {st_trans.shape}."
+            )
+        spacetime_translation = st_trans[:]
+        supertranslation[0] = spacetime_translation[0] * s4pi
+        supertranslation[1:4] = vector_as_ell_1_modes(-spacetime_translation[1:4])
+    if "space_translation" in kwargs:
+        s_trans = np.array(kwargs.pop("space_translation"), dtype=float)
+        if s_trans.shape != (3,) or s_trans.dtype != "float":
+            raise TypeError(
+                "\nInput argument `space_translation` should be an array of floats of shape (3,).\n"
+                f"Got a {s_trans.dtype} array of shape {s_trans.shape}."
+            )
+        spacetime_translation[1:4] = s_trans[:]
+        supertranslation[1:4] = vector_as_ell_1_modes(-spacetime_translation[1:4])
+    if "time_translation" in kwargs:
+        t_trans = kwargs.pop("time_translation")
+        if not isinstance(t_trans, float):
+            raise TypeError(f"\nInput argument `time_translation` should be a single float.\nGot {t_trans}.")
+        spacetime_translation[0] = t_trans
+        supertranslation[0] = spacetime_translation[0] * s4pi
+
+    w_ell_max = ell_max
+    ell_max = w_ell_max + ell_max_supertranslation
+    n_theta = kwargs.pop("n_theta", 2 * ell_max + 1)
+    n_phi = kwargs.pop("n_phi", 2 * ell_max + 1)
+    if n_theta < 2 * ell_max + 1 and abs(supertranslation[1:]).max() > 0.0:
+        warnings.warn(
+            f"n_theta={n_theta} is small; because of the supertranslation, "
+            f"it will lose accuracy for anything less than 2*ell+1={ell_max}"
+        )
+    if n_theta < 2 * w_ell_max + 1:
+        raise ValueError(f"n_theta={n_theta} is too small; must be at least 2*ell+1={2 * w_ell_max + 1}")
+    if n_phi < 2 * ell_max + 1 and abs(supertranslation[1:]).max() > 0.0:
+        warnings.warn(
+            f"n_phi={n_phi} is small; because of the supertranslation, "
+            f"it will lose accuracy for anything less than 2*ell+1={ell_max}"
+        )
+    if n_phi < 2 * w_ell_max + 1:
+        raise ValueError(f"n_phi={n_phi} is too small; must be at least 2*ell+1={2 * w_ell_max + 1}")
+
+    frame_rotation = Q.as_float_quat(np.array(kwargs.pop("frame_rotation", [1, 0, 0, 0]), dtype=float))
+    if Q.qabs(frame_rotation) < 3e-16:
+        raise ValueError(f"frame_rotation={frame_rotation} should be a unit quaternion")
+    frame_rotation = Q.qnormalized(frame_rotation)
+
+    boost_velocity = np.array(kwargs.pop("boost_velocity", [0.0] * 3), dtype=float)
+    beta = np.linalg.norm(boost_velocity)
+    if boost_velocity.shape != (3,) or beta >= 1.0:
+        raise ValueError(
+            f"Input boost_velocity=`{boost_velocity}` should be a 3-vector with magnitude strictly less than 1.0."
+        )
+    gamma = 1 / math.sqrt(1 - beta**2)
+    varphi = math.atanh(beta)
+
+    thetaprm = np.linspace(0.0, np.pi, num=n_theta, endpoint=True)
+    phiprm = np.linspace(0.0, 2 * np.pi, num=n_phi, endpoint=False)
+    thetaprm_j_phiprm_k = np.stack(np.meshgrid(thetaprm, phiprm, indexing="ij"), axis=-1)
+
+    # rotors of the output grid carried back to the input frame: R = B'(theta,phi) * R_frame * R_{theta',phi'}
+    rotated = Q.qmul(frame_rotation, Q.from_spherical_coords(thetaprm_j_phiprm_k[..., 0], thetaprm_j_phiprm_k[..., 1]))
+    if beta > 3e-14:
+        vhat = boost_velocity / beta
+        th, ph = Q.as_spherical_coords(rotated)
+        rprm = np.stack([np.cos(ph) * np.sin(th), np.sin(ph) * np.sin(th), np.cos(th)], axis=-1)
+        Thetaprm = np.arccos(np.clip(rprm @ vhat, -1.0, 1.0))
+        Theta = 2 * np.arctan(math.exp(-varphi) * np.tan(Thetaprm / 2.0))
+        cross = np.cross(rprm, vhat)
+        cn = np.sqrt(np.sum(cross * cross, axis=-1))
+        safe = cn > 1e-200
+        nhat = np.where(safe[..., None], cross / np.where(safe, cn, 1.0)[..., None], 0.0)
+        B = Q.qexp_vec(nhat * ((Thetaprm - Theta) / 2)[..., None])
+        B[~safe] = np.array([1.0, 0.0, 0.0, 0.0])
+        R_j_k = Q.qmul(B, rotated)
+    else:
+        R_j_k = rotated
+
+    return (
+        supertranslation,
+        ell_max_supertranslation,
+        ell_max,
+        n_theta,
+        n_phi,
+        boost_velocity,
+        beta,
+        gamma,
+        varphi,
+        R_j_k,
+        thetaprm_j_phiprm_k,
+        kwargs,
+    )
+
+
+def _ell_factors(n, fn):
+    out = np.zeros(n)
+    i = 0
+    ell = 0
+    while i < n:
+        for m in range(-ell, ell + 1):
+            out[i] = fn(ell)
+            i += 1
+        ell += 1
+    return out
+
+
+def pack_synthesis_matrix(Y, ell_min, ell_max):
+    """Real GEMM operand for scrib200_swsh_synthesize from Y[g, LM_index(l,m,0)] (complex).
+
+    B[2lm, 2g] = Re Y, B[2lm+1, 2g] = -Im Y, B[2lm, 2g+1] = Im Y, B[2lm+1, 2g+1] = Re Y, zero padded to
+    [roundup(2n,16), roundup(2G,64)].
+    """
+    G = Y.shape[0]
+    Ys = Y[:, ell_min * ell_min : (ell_max + 1) ** 2]
+    n = Ys.shape[1]
+    Kpad = -(-2 * n // 16) * 16
+    Ncpad = -(-2 * G // 64) * 64
+    B = np.zeros((Kpad, Ncpad))
+    B[0 : 2 * n : 2, 0 : 2 * G : 2] = Ys.real.T
+    B[1 : 2 * n : 2, 0 : 2 * G : 2] = -Ys.imag.T
+    B[0 : 2 * n : 2, 1 : 2 * G : 2] = Ys.imag.T
+    B[1 : 2 * n : 2, 1 : 2 * G : 2] = Ys.real.T
+    return B, Kpad, Ncpad
+
+
+class TransformPlan:
+    """Device-resident tables for one BMS transformation of one kind of waveform.
+
+    Built from the same quantities scri/waveform_grid.py:431-474 computes on the host (rotor grid,
+    SWSH tables, conformal factor, supertranslation on the grid); executed by `run`.
+    """
+
+    def __init__(self, ell_min, ell_max, dataType, r_is_scaled_out=True, out_ell_max=None, device="cuda", **kwargs):
+        torch = _lib.require_cuda()
+        _lib.load()
+        self.torch = torch
+        self.device = torch.device(device)
+        self.ell_min, self.ell_max, self.dataType = int(ell_min), int(ell_max), int(dataType)
+        self.spin_weight = SpinWeights[self.dataType]
+        self.conformal_weight = ConformalWeights[self.dataType] - (RScaling[self.dataType] if r_is_scaled_out else 0)
+        (
+            supertranslation,
+            ell_max_st,
+            L,
+            n_theta,
+            n_phi,
+            boost_velocity,
+            beta,
+            gamma,
+            varphi,
+            R_j_k,
+            _,
+            leftover,
+        ) = process_transformation_kwargs(self.ell_max, **kwargs)
+        self.leftover_kwargs = leftover
+        self.supertranslation = supertranslation
+        self.L, self.n_theta, self.n_phi = L, n_theta, n_phi
+        self.G = n_theta * n_phi
+        self.gamma, self.beta = gamma, beta
+        self.out_ell_max = self.ell_max if out_ell_max is None else int(out_ell_max)
+        self.out_ell_min = abs(self.spin_weight)
+        s = self.spin_weight
+
+        R = R_j_k.reshape(-1, 4)
+        Y = _sf.SWSH_grid(R, s, max(L, self.ell_max))  # [G, (L+1)^2]
+        SH = _sf.SWSH_grid(R, 0, ell_max_st)
+        rhat = Q.rotate_z(R)
+        self.kconformal = 1.0 / (gamma * (1 - rhat @ boost_velocity))
+        self.alpha = (SH @ supertranslation).real
+        offset_c = np.zeros(self.G, dtype=complex)
+        nontrivial = beta != 0 or (supertranslation[1:] != 0).any()
+        if nontrivial:
+            nst = (ell_max_st + 1) ** 2
+            if self.dataType == h:
+                # 2 ethbar ethbar alpha (GHP): factor sqrt((l-1) l (l+1) (l+2))   (waveform_grid.py:486-494)
+                fac = _ell_factors(nst, lambda l: math.sqrt(max((l - 1) * l * (l + 1) * (l + 2), 0)))
+                offset_c = Y[:, :nst] @ (supertranslation * fac)
+            elif self.dataType == sigma:
+                # eth eth alpha (GHP): half of the above                         (waveform_grid.py:495-503)
+                fac = _ell_factors(nst, lambda l: 0.5 * math.sqrt(max((l - 1) * l * (l + 1) * (l + 2), 0)))
+                offset_c = Y[:, :nst] @ (supertranslation * fac)
+            elif self.dataType in (psi0, psi1, psi2, psi3):
+                raise NotImplementedError(
+                    f"BMS transformation of {DataNames[self.dataType]} (mixing with higher Weyl scalars, "
+                    "scri/waveform_grid.py:504-550) is not implemented in scri_b200 yet"
+                )
+            elif self.dataType not in (psi4, hdot, news):
+                warnings.warn(
+                    f"\nNo BMS transformation is implemented for waveform objects of dataType '{DataNames[self.dataType]}'. "
+                    "Proceeding with the transformation as if it were dataType 'Psi4'."
+                )
+        scale = self.kconformal**self.conformal_weight
+        B, self.Kpad, self.Ncpad = pack_synthesis_matrix(Y, self.ell_min, self.ell_max)
+        off = np.zeros(self.Ncpad)
+        off[0 : 2 * self.G : 2] = offset_c.real
+        off[1 : 2 * self.G : 2] = offset_c.imag
+        scl = np.zeros(self.Ncpad)
+        scl[0 : 2 * self.G : 2] = scale
+        scl[1 : 2 * self.G : 2] = scale
+        self.time_translation = (supertranslation[0] / math.sqrt(4 * math.pi)).real
+        E, Wt = _sf.analysis_tables(s, self.out_ell_min, self.out_ell_max, n_theta, n_phi)
+        self.n_modes_in = _sf.LM_total_size(self.ell_min, self.ell_max)
+        self.n_modes_out = _sf.LM_total_size(self.out_ell_min, self.out_ell_max)
+
+        dev = self.device
+        f64 = torch.float64
+        self.d_B = torch.from_numpy(B).to(dev)
+        self.d_offset = torch.from_numpy(off).to(dev)
+        self.d_scale = torch.from_numpy(scl).to(dev)
+        self.d_k = torch.from_numpy(np.ascontiguousarray(self.kconformal)).to(dev)
+        self.d_alpha = torch.from_numpy(np.ascontiguousarray(self.alpha)).to(dev)
+        self.d_E = torch.from_numpy(np.ascontiguousarray(E)).to(dev)
+        self.d_Wt = torch.from_numpy(Wt).to(dev)
+        self._ws = None
+        self.spline_chunk = 0
+
+    # -- the individual stages (device tensors in, device tensors out) ---------------------------
+    def synthesize(self, data):
+        """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-503,559)."""
+        torch = self.torch
+        lib = _lib.load()
+        N = data.shape[0]
+        F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
+        _lib.check(
+            lib.scrib200_swsh_synthesize(
+                _lib.ptr(data), N, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad, _lib.ptr(self.d_offset),
+                _lib.ptr(self.d_scale), self.G, _lib.ptr(F), _lib.stream_ptr(),
+            ),
+            "swsh_synthesize",
+        )
+        return F
+
+    def output_times(self, t):
+        """u'_i and the retained block (waveform_grid.py:564-568).  `t` is a device tensor."""
+        torch = self.torch
+        uprm = (1 / self.gamma) * (t - self.time_translation)
+        t0, t1 = float(t[0]), float(t[-1])
+        uprm_min = (self.kconformal * (t0 - self.alpha)).max()
+        uprm_max = (self.kconformal * (t1 - self.alpha)).min()
+        return uprm[(uprm >= uprm_min) & (uprm <= uprm_max)].contiguous()
+
+    def remap(self, t, F, uprm):
+        """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588)."""
+        torch = self.torch
+        lib = _lib.load()
+        N, n_out = t.shape[0], uprm.shape[0]
+        out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
+        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, self.spline_chunk)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(
+            lib.scrib200_bms_spline_remap(
+                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(uprm), n_out,
+                _lib.ptr(out), self.spline_chunk, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr(),
+            ),
+            "bms_spline_remap",
+        )
+        return out
+
+    def analyze(self, grid):
+        """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307)."""
+        return map2salm(grid, self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max, self.d_E, self.d_Wt)
+
+    def run(self, t, data, return_grid=False):
+        """Whole path on device tensors: returns (u', modes') or (u', grid')."""
+        F = self.synthesize(data)
+        uprm = self.output_times(t)
+        grid = self.remap(t, F, uprm)
+        del F
+        if return_grid:
+            return uprm, grid
+        return uprm, self.analyze(grid)
+
+
+def map2salm(grid, n_theta, n_phi, ell_min, ell_max, d_E, d_Wt):
+    """Device map2salm: grid [N, n_theta*n_phi] complex128 -> [N, LM_total_size(ell_min, ell_max)]."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    N = grid.shape[0]
+    n_modes = _sf.LM_total_size(ell_min, ell_max)
+    out = torch.empty((N, n_modes), dtype=torch.complex128, device=grid.device)
+    need = lib.scrib200_map2salm_workspace_bytes(N, n_theta, n_phi, ell_max)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=grid.device)
+    _lib.check(
+        lib.scrib200_map2salm(
+            _lib.ptr(grid), N, n_theta, n_phi, _lib.ptr(d_E), _lib.ptr(d_Wt), ell_min, ell_max, _lib.ptr(out),
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(),
+        ),
+        "map2salm",
+    )
+    return out
