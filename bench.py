@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py - mode-timesteps/s through WaveformModes.transform (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-times T]
+
+Workload (BASELINE.json configs[1]): fake_precessing_waveform, ell 2..8 (77 modes), ~1e5 time steps,
+transform(supertranslation with ell<=4, frame_rotation, boost_velocity) -> working band limit 12, 25x25 grid.
+A "step" is one pass of the whole path (synthesis -> spline remap -> analysis) over that waveform.
+For N > 1 GPUs every rank runs its own waveform of that size (batch of N waveforms sharded by waveform
+index, no data-path collective): weak scaling; value = total mode-timesteps of all ranks / max-over-ranks time.
+
+  value : device-resident - inputs and the plan's tables already in HBM, CUDA-event time of plan.run()
+  e2e   : the public call w.transform(**kwargs) on host numpy arrays: plan construction, H2D, kernels, D2H
+  --impl reference : the reference's CPU algorithm (oracle/, a port: the reference itself cannot be
+          imported here) on a bounded time-slice of the same waveform, grid points spread over all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "mode-timesteps/sec through WaveformModes.transform (ell_max=8)"
+UNIT = "mode-timesteps/s"
+
+
+def transformation_kwargs():
+    from scri_inputs import real_supertranslation
+
+    return dict(
+        supertranslation=real_supertranslation(4, seed=123, scale=1e-2),
+        frame_rotation=[1.0, 2.0, 3.0, 4.0],
+        boost_velocity=[0.01, 0.02, 0.03],
+    )
+
+
+def make_workload(n_times, corotating_only=False):
+    """(t, data[n_times, 77], frame) host arrays of the config-2 waveform (inertial frame needs the GPU)."""
+    import scri_b200 as sb
+
+    dt = 0.1
+    w = sb.sample_waveforms.fake_precessing_waveform(t_0=-20.0, t_1=-20.0 + dt * (n_times - 1), dt=dt, ell_max=8, inertial=not corotating_only)
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def measure_dgemm_peak(torch, n=6144, reps=5):
+    """cuBLAS DGEMM throughput (TFLOP/s) - the FP64 denominator MEASURED_PEAKS.json does not carry."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def cpu_baseline_sample(w_t, w_data, kw, n_sample, workers=1):
+    """Oracle (CPU port of the reference algorithm) on the first n_sample time steps; returns (value, seconds, n_out)."""
+    from oracle import scri_ref as R
+
+    Wo = R.Modes(t=w_t[:n_sample].copy(), data=w_data[:n_sample].copy())
+    t0 = time.perf_counter()
+    if workers > 1:
+        out = oracle_transform_parallel(Wo, kw, workers)
+    else:
+        out = R.transform(Wo, **kw)
+    dt = time.perf_counter() - t0
+    return 77.0 * n_sample / dt, dt, out.t.shape[0]
+
+
+def _spline_columns(args):
+    from scipy import interpolate
+
+    t, kc, al, cols_re, cols_im, uprm = args
+    out = np.empty((uprm.shape[0], cols_re.shape[1]), dtype=complex)
+    for c in range(cols_re.shape[1]):
+        x = kc[c] * (t - al[c])
+        out[:, c] = interpolate.InterpolatedUnivariateSpline(x, cols_re[:, c])(uprm) + 1j * interpolate.InterpolatedUnivariateSpline(x, cols_im[:, c])(uprm)
+    return out
+
+
+def oracle_transform_parallel(Wo, kw, workers):
+    """The oracle's transform with the per-grid-point spline loop (waveform_grid.py:576-588) spread over processes.
+
+    Same arithmetic per grid point as oracle.scri_ref.from_modes; everything else is the oracle itself.
+    """
+    import multiprocessing as mp
+
+    from oracle import scri_ref as R
+    from oracle import sf as osf
+
+    g, inter = R.from_modes(R.Modes(t=Wo.t[:8].copy(), data=Wo.data[:8].copy()), return_intermediates=True, **dict(kw))
+    # synthesis for the full sample with the oracle's own tables
+    SW = inter["SWSH_j_k"]
+    kc, al = inter["kconformal"], inter["alpha"]
+    nth, nph = kc.shape
+    (st, ell_st, L, _, _, bv, beta, gamma, _, R_j_k, _) = R.process_transformation_kwargs(Wo.ell_max, **dict(kw))
+    f = np.tensordot(Wo.data, SW[:, :, osf.LM_index(Wo.ell_min, -Wo.ell_min, 0) : osf.LM_index(Wo.ell_max, Wo.ell_max, 0) + 1], axes=([1], [2]))
+    deriv = 2 * osf.ethbar_GHP(osf.ethbar_GHP(st, 0, 0), -1, 0)
+    f -= np.tensordot(deriv, SW[:, :, : (ell_st + 1) ** 2], axes=([0], [2]))[None]
+    f *= (kc**Wo.conformal_weight)[None]
+    tt = osf.constant_from_ell_0_mode(st[0]).real
+    uprm_i = (1 / gamma) * (Wo.t - tt)
+    umin = (kc * (Wo.t[0] - al)).max()
+    umax = (kc * (Wo.t[-1] - al)).min()
+    uprm = uprm_i[(uprm_i >= umin) & (uprm_i <= umax)]
+    f2 = f.reshape(f.shape[0], -1)
+    G = f2.shape[1]
+    bounds = np.linspace(0, G, workers + 1).astype(int)
+    jobs = [(Wo.t, kc.ravel()[a:b], al.ravel()[a:b], np.ascontiguousarray(f2[:, a:b].real), np.ascontiguousarray(f2[:, a:b].imag), uprm) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_spline_columns, jobs)
+    grid = np.concatenate(parts, axis=1)
+    return R.to_modes(R.Grid(t=uprm, data=grid, n_theta=nth, n_phi=nph), Wo.ell_max)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kw = transformation_kwargs()
+    n_sample = args.ref_sample
+    import scri_b200 as sb  # host-only generator (corotating-frame data, rotated with the oracle)
+    from oracle import scri_ref as R
+
+    wc = make_workload(n_sample, corotating_only=True)
+    Wo = R.Modes(t=wc.t.copy(), data=wc.data.copy(), frame=wc.frame.copy(), frameType=R.Corotating)
+    R.to_inertial_frame(Wo)
+    cores = os.cpu_count() or 1
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle_transform_parallel(R.Modes(t=Wo.t, data=Wo.data), kw, cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = 77.0 * n_sample / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[1]: fake_precessing_waveform ell_max=8, transform(supertranslation ell<=4 + rotation + boost); bounded sample of {n_sample} time steps per step", "n_times": n_sample, "n_modes": 77, "grid": "25x25"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"first {n_sample} time steps of the configs[1] waveform, oracle/ port of scri's algorithm (scipy FITPACK splines), spline loop over {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import scri_b200 as sb
+    from scri_b200 import _lib, ops
+    from scri_b200.plan import TransformPlan
+
+    kw = transformation_kwargs()
+    N = args.n_times
+    w = make_workload(N)   # every rank builds the same-size waveform (its own unit of the batch)
+    n_modes = w.n_modes
+    plan = TransformPlan(w.ell_min, w.ell_max, w.dataType, r_is_scaled_out=True, **kw)
+    t_d = ops.to_device(w.t)
+    a_d = ops.to_device(w.data)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def staged_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        F = plan.synthesize(a_d)
+        ev[1].record()
+        up = plan.output_times(t_d)
+        ev[2].record()
+        grid = plan.remap(t_d, F, up)
+        ev[3].record()
+        m = plan.analyze(grid)
+        ev[4].record()
+        return ev, up, m
+
+    # ---- device-resident value
+    for _ in range(args.warmup):
+        staged_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    per_kernel = np.zeros(4)
+    total_ms = 0.0
+    n_out = 0
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)   # L2 flush between timed iterations (outside the per-step event pairs)
+        ev, up, m = staged_step()
+        torch.cuda.synchronize()
+        total_ms += ev[0].elapsed_time(ev[4])
+        per_kernel += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        n_out = up.shape[0]
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = total_ms / args.steps
+    per_kernel /= args.steps
+
+    # ---- e2e: the public API on host arrays (plan construction + H2D + kernels + D2H inside the timed region)
+    for _ in range(2):
+        w.transform(**kw)
+    barrier()
+    e2e_times = []
+    for _ in range(max(3, min(args.steps, 10))):
+        t0 = time.perf_counter()
+        out = w.transform(**kw)
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_ms = 1e3 * float(np.mean(e2e_times))
+    h2d = w.t.nbytes + w.data.nbytes
+    d2h = out.t.nbytes + out.data.nbytes
+
+    tms = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step_max, e2e_ms_max = float(tms[0]), float(tms[1])
+    units = float(n_modes) * N * world
+    value = units / (ms_step_max * 1e-3)
+    e2e_value = units / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        G = plan.G
+        # dominant kernel by time decides which roofline is quoted; all three are listed under "kernels"
+        dgemm_tf = measure_dgemm_peak(torch)
+        synth_flops = 8.0 * n_modes * G * N
+        remap_bytes = 32.0 * G * N          # read F (16 G) + write grid' (16 G) per time step
+        ana_bytes = (16.0 * G + 16.0 * n_modes) * n_out
+        kern = {
+            "swsh_synth_dmma": {"ms": per_kernel[0], "bound": "tensor(fp64)", "achieved_tflops": synth_flops / (per_kernel[0] * 1e-3) / 1e12},
+            "output_times(torch glue)": {"ms": per_kernel[1]},
+            "bms_spline_remap": {"ms": per_kernel[2], "bound": "hbm", "achieved_gbs": remap_bytes / (per_kernel[2] * 1e-3) / 1e9},
+            "map2salm_fused": {"ms": per_kernel[3], "bound": "hbm", "achieved_gbs": ana_bytes / (per_kernel[3] * 1e-3) / 1e9},
+        }
+        if per_kernel[2] >= per_kernel[0]:
+            ach = kern["bms_spline_remap"]["achieved_gbs"]
+            roof = {"kernel": "bms_spline_remap_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                    "algorithmic_bytes_per_launch": remap_bytes}
+        else:
+            ach = kern["swsh_synth_dmma"]["achieved_tflops"]
+            roof = {"kernel": "swsh_synth_dmma_kernel", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
+                    "frac": ach / dgemm_tf, "traffic": None,
+                    "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                    "algorithmic_flops_per_launch": synth_flops}
+        # CPU baseline: oracle port, single thread + BLAS, bounded sample
+        cpu_cores = 1
+        cval, csec, _ = cpu_baseline_sample(w.t, w.data, kw, args.cpu_sample, workers=1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: fake_precessing_waveform ell_max=8 (77 modes), transform(supertranslation ell<=4 + frame_rotation + boost_velocity), 25x25 grid; one such waveform per GPU (batch sharded by waveform index)",
+                "n_times": N, "n_out": n_out, "n_modes": n_modes, "grid": f"{plan.n_theta}x{plan.n_phi}",
+                "l2": "explicit 256 MiB L2 flush between timed iterations; intermediates (2 x 1 GB) exceed L2",
+            },
+            "roofline": roof, "kernels": kern, "fp64_dgemm_tflops_measured": dgemm_tf,
+            "cpu_baseline": {"value": cval, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                             "sample": f"first {args.cpu_sample} time steps of the same waveform through oracle/ (port of scri's algorithm, scipy FITPACK splines; reference packages not installable here), {csec:.1f} s; host has {os.cpu_count()} cores"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line, default=float))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-times", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="time steps in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=10_000, help="time steps per step of --impl reference")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,7 +95,21 @@ def Wigner_D_element(Ra, Rb, ell, mp, m):
     return _wigner_D_element_ld(Ra, Rb, ell, mp, m).astype(complex)
 
 
+_swsh_cache = {}
+
+
 def SWSH_grid(R, s, ell_max):
+    """Memoised front end of `_SWSH_grid` (the long-double evaluation is slow; sf's own is numba-fast)."""
+    R = np.ascontiguousarray(R, dtype=float)
+    key = (R.tobytes(), R.shape, s, ell_max)
+    if key not in _swsh_cache:
+        if len(_swsh_cache) > 64:
+            _swsh_cache.clear()
+        _swsh_cache[key] = _SWSH_grid(R, s, ell_max)
+    return _swsh_cache[key].copy()
+
+
+def _SWSH_grid(R, s, ell_max):
     """sf.SWSH_grid: Y[..., LM_index(l,m,0)] = (-1)^s sqrt((2l+1)/4pi) D^l_{m,-s}(R); zeros for l<|s|.
 
     R: float array [..., 4].  (scri/waveform_grid.py:470-471)
@@ -134,9 +148,15 @@ def ladder_operator_coefficient(ell, m):
     return math.sqrt((ell - m) * (ell + m + 1))
 
 
-@lru_cache(maxsize=None)
 def Wigner3j(j1, j2, j3, m1, m2, m3):
-    """Standard Wigner 3-j symbol (Racah formula, exact rational under the sqrt), integer args."""
+    """Standard Wigner 3-j symbol (Racah formula, exact rational arithmetic under the square root)."""
+    return _wigner3j(int(j1), int(j2), int(j3), int(m1), int(m2), int(m3))
+
+
+@lru_cache(maxsize=None)
+def _wigner3j(j1, j2, j3, m1, m2, m3):
+    from fractions import Fraction
+
     if m1 + m2 + m3 != 0:
         return 0.0
     if abs(m1) > j1 or abs(m2) > j2 or abs(m3) > j3:
@@ -144,8 +164,6 @@ def Wigner3j(j1, j2, j3, m1, m2, m3):
     if j3 < abs(j1 - j2) or j3 > j1 + j2:
         return 0.0
     f = math.factorial
-    from fractions import Fraction
-
     tri = Fraction(f(j1 + j2 - j3) * f(j1 - j2 + j3) * f(-j1 + j2 + j3), f(j1 + j2 + j3 + 1))
     pre = tri * f(j1 + m1) * f(j1 - m1) * f(j2 + m2) * f(j2 - m2) * f(j3 + m3) * f(j3 - m3)
     kmin = max(0, j2 - j3 - m1, j1 - j3 + m2)
@@ -156,18 +174,10 @@ def Wigner3j(j1, j2, j3, m1, m2, m3):
             (-1) ** k,
             f(k) * f(j1 + j2 - j3 - k) * f(j1 - m1 - k) * f(j2 + m2 - k) * f(j3 - j2 + m1 + k) * f(j3 - j1 - m2 + k),
         )
-    val = (-1) ** (j1 - j2 - m3) * s
-    # sqrt(pre) * val, with pre an exact Fraction
-    num = math.isqrt(pre.numerator)
-    den = math.isqrt(pre.denominator)
-    if num * num == pre.numerator and den * den == pre.denominator:
-        root = num / den
-    else:
-        root = math.sqrt(pre.numerator) / math.sqrt(pre.denominator) if pre.numerator < 2**1000 else float(
-            (pre.numerator // pre.denominator)
-        ) ** 0.5
-        root = math.sqrt(float(pre))
-    return float(val) * root
+    sign = -1 if (j1 - j2 - m3) % 2 else 1
+    # pre * s^2 is an exact rational; take one square root at the end
+    val2 = pre * s * s
+    return sign * (1 if s >= 0 else -1) * math.sqrt(val2.numerator) / math.sqrt(val2.denominator)
 
 
 def clebsch_gordan(j1, m1, j2, m2, j3, m3):

@@ -1,0 +1,211 @@
+"""CPU-side tests of the product's host logic: table builders, kwargs processing, API shell, C-ABI exports."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import scri_b200 as sb
+from scri_b200 import _lib, _sf, flux, ops, plan
+from scri_b200 import _quaternion as Q
+from oracle import quat, scri_ref as R, sf as osf, spinsfast as ospf
+from scri_inputs import real_supertranslation, rotor_set, smooth_modes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lm_layout_bit_exact():
+    """(ell,m) indexing must be bit-exact (scri/waveform_modes.py:404-455)."""
+    for lmin, lmax in [(0, 4), (2, 8), (1, 16)]:
+        LM = _sf.LM_range(lmin, lmax)
+        assert np.array_equal(LM, osf.LM_range(lmin, lmax))
+        assert LM.shape[0] == _sf.LM_total_size(lmin, lmax)
+        for i, (l, m) in enumerate(LM):
+            assert _sf.LM_index(l, m, lmin) == i
+        for l in range(lmin, lmax + 1):
+            assert _sf.D_offset(l, lmin) == osf.linear_matrix_offset(l, lmin)
+    w = sb.sample_waveforms.constant_waveform()
+    assert w.index(2, -2) == 0 and w.index(8, 8) == 76 and w.n_modes == 77
+    with pytest.raises(ValueError):
+        w.index(9, 0)
+
+
+def test_wigner_recurrence_matches_oracle():
+    rng = np.random.default_rng(0)
+    Rq = quat.normalized(rng.normal(size=(64, 4)))
+    Rq[0] = [1, 0, 0, 0]; Rq[1] = [0, 0, 1, 0]; Rq[2] = [0, 1, 0, 0]; Rq[3] = [0, 0, 0, 1]
+    Rq[4] = quat.normalized([1, 1e-9, 0, 0]); Rq[5] = quat.normalized([1e-9, 1e-10, 1, 0.3])
+    sp = quat.as_spinor_array(Rq)
+    for lmin, lmax in [(0, 12), (2, 8)]:
+        A = osf.Wigner_D_matrices(sp[:, 0], sp[:, 1], lmin, lmax)
+        B = _sf.wigner_D_matrices(sp[:, 0], sp[:, 1], lmin, lmax)
+        assert abs(A - B).max() < 2e-14
+    for s in (-2, 0, 1, 2):
+        assert abs(osf.SWSH_grid(Rq, s, 12) - _sf.SWSH_grid(Rq, s, 12)).max() < 2e-14
+
+
+@pytest.mark.parametrize("s,lmax,nth,nph", [(-2, 8, 19, 19), (-2, 8, 25, 25), (0, 4, 9, 9), (1, 5, 13, 11), (2, 6, 14, 16)])
+def test_analysis_tables_equal_huffenberger_wandelt(s, lmax, nth, nph):
+    """phi-DFT + Clenshaw-Curtis theta quadrature == the oracle's literal H&W map2salm, also on white noise."""
+    rng = np.random.default_rng(5)
+    f = rng.normal(size=(3, nth, nph)) + 1j * rng.normal(size=(3, nth, nph))
+    a = ospf.map2salm(f, s, lmax)
+    E, Wt = _sf.analysis_tables(s, 0, lmax, nth, nph)
+    fm = np.einsum("bjk,km->bjm", f, E)
+    b = np.zeros_like(a)
+    for l in range(lmax + 1):
+        for m in range(-l, l + 1):
+            b[:, l * (l + 1) + m] = fm[:, :, m + lmax] @ Wt[l * (l + 1) + m]
+    assert abs(a - b).max() < 1e-14
+
+
+def test_process_transformation_kwargs_matches_oracle():
+    kw = dict(supertranslation=real_supertranslation(4), frame_rotation=[1.0, 2.0, 3.0, 4.0], boost_velocity=[0.01, 0.02, 0.03])
+    a = plan.process_transformation_kwargs(8, **dict(kw))
+    b = R.process_transformation_kwargs(8, **dict(kw))
+    assert np.array_equal(a[0], b[0]) and a[1:5] == b[1:5]
+    assert a[7] == b[7] and a[8] == b[8]
+    assert abs(a[9] - b[9]).max() < 1e-15          # rotor grid
+    for kw2 in (dict(time_translation=1.5), dict(space_translation=[0.1, -0.2, 0.3]), dict(spacetime_translation=[1.0, 2.0, 3.0, 4.0]), {}):
+        a = plan.process_transformation_kwargs(8, **dict(kw2))
+        b = R.process_transformation_kwargs(8, **dict(kw2))
+        assert np.allclose(a[0], b[0], rtol=0, atol=0) and a[2:5] == b[2:5] and abs(a[9] - b[9]).max() < 1e-15
+
+
+def test_process_transformation_kwargs_errors():
+    """Same exception types as scri/waveform_grid.py:28-125."""
+    with pytest.raises(ValueError):
+        plan.process_transformation_kwargs(8, supertranslation=np.zeros(7))      # not a perfect square
+    bad = np.zeros(9, complex); bad[5] = 1.0
+    with pytest.raises(ValueError):
+        plan.process_transformation_kwargs(8, supertranslation=bad)               # imaginary supertranslation
+    with pytest.raises(TypeError):
+        plan.process_transformation_kwargs(8, time_translation=1)                 # int, not float
+    with pytest.raises(TypeError):
+        plan.process_transformation_kwargs(8, space_translation=[1.0, 2.0])
+    with pytest.raises(ValueError):
+        plan.process_transformation_kwargs(8, boost_velocity=[1.0, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        plan.process_transformation_kwargs(8, frame_rotation=[0.0, 0.0, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        plan.process_transformation_kwargs(8, n_theta=5)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        plan.process_transformation_kwargs(8, supertranslation=real_supertranslation(2), n_theta=17)
+        assert any("n_theta" in str(r.message) for r in rec)
+
+
+def test_pack_synthesis_matrix_is_the_complex_product():
+    rng = np.random.default_rng(2)
+    G, lmin, lmax = 11, 2, 4
+    Y = rng.normal(size=(G, (lmax + 1) ** 2)) + 1j * rng.normal(size=(G, (lmax + 1) ** 2))
+    B, Kpad, Ncpad = plan.pack_synthesis_matrix(Y, lmin, lmax)
+    n = _sf.LM_total_size(lmin, lmax)
+    a = rng.normal(size=(5, n)) + 1j * rng.normal(size=(5, n))
+    A = np.zeros((5, Kpad)); A[:, : 2 * n] = a.view(float)
+    C = (A @ B)[:, : 2 * G].copy().view(complex)
+    assert np.allclose(C, a @ Y[:, lmin * lmin :].T, rtol=1e-13)
+    assert Kpad % 16 == 0 and Ncpad % 64 == 0
+
+
+def test_flux_matrices_match_oracle():
+    for lmin, lmax in [(2, 8), (2, 5)]:
+        for mine, ref in [
+            (flux.p_z(lmin, lmax, s=-2), R.p_z(lmin, lmax, -2)),
+            (flux.p_plus(lmin, lmax, s=-2), R.p_plusminus(lmin, lmax, +1, -2)),
+            (flux.p_minus(lmin, lmax, s=-2), R.p_plusminus(lmin, lmax, -1, -2)),
+            (flux.j_z(lmin, lmax), R.j_z(lmin, lmax)),
+            (flux.j_plus(lmin, lmax), R.j_plusminus(lmin, lmax, +1)),
+            (flux.j_minus(lmin, lmax), R.j_plusminus(lmin, lmax, -1)),
+        ]:
+            assert np.array_equal(mine[0], ref[0]) and np.array_equal(mine[1], ref[1])
+            assert np.allclose(mine[2], ref[2], rtol=1e-14, atol=1e-15)
+
+
+def test_quaternion_helpers_match_oracle():
+    rng = np.random.default_rng(3)
+    p, q = rng.normal(size=(2, 20, 4))
+    assert np.allclose(Q.qmul(p, q), quat.mul(p, q))
+    assert np.allclose(Q.as_spinor_array(p), quat.as_spinor_array(p))
+    u = Q.qnormalized(p)
+    assert np.allclose(Q.rotate_z(u), quat.rotate_vector(u, np.array([0.0, 0.0, 1.0])))
+    th, ph = Q.as_spherical_coords(u)
+    assert np.allclose(np.stack([th, ph], -1), quat.as_spherical_coords(u))
+    assert np.allclose(Q.qmul(Q.qsqrt(u), Q.qsqrt(u)), u)
+
+
+def test_sample_waveforms_host_side():
+    w = sb.sample_waveforms.fake_precessing_waveform(t_1=500.0, inertial=False)
+    assert w.frameType == sb.Corotating and w.dataType == sb.h and w.n_modes == 77
+    assert not np.isnan(w.data).any() and w.frame.shape == (w.n_times, 4)
+    assert np.allclose(np.sum(w.frame**2, axis=1), 1.0)
+    # conjugate-pair structure of the PN amplitudes: h_{l,-m} = (-1)^l conj(h_{l,m}) up to the modulation
+    a = sb.sample_waveforms.pn_leading_order_amplitude(3, 2, 0.1, 2.0)
+    b = sb.sample_waveforms.pn_leading_order_amplitude(3, -2, 0.1, 2.0)
+    assert np.isclose(b, (-1) ** 3 * np.conj(a))
+    t, batch = sb.sample_waveforms.smooth_random_waveform(n_times=64, batch=3)
+    assert batch.shape == (3, 64, 77)
+
+
+def test_waveform_shell_history_copy_and_validity():
+    w = sb.sample_waveforms.constant_waveform()
+    c = w.copy()
+    assert c is not w and np.array_equal(c.data, w.data) and c.ell_min == 2 and c.ell_max == 8
+    assert c.spin_weight == -2 and c.conformal_weight == -1 and c.data_type_string == "h" and c.frame_type_string == "Inertial"
+    assert any("copy()" in line for line in c.history)
+    with pytest.raises(ValueError):
+        sb.WaveformModes(t=np.array([0.0, 1.0, 1.0]), data=np.zeros((3, 77), complex), ell_min=2, ell_max=8)
+    with pytest.raises(ValueError):
+        sb.WaveformModes(t=np.arange(3.0), data=np.zeros((3, 70), complex), ell_min=2, ell_max=8)
+    with pytest.raises(TypeError):
+        sb.WaveformGrid.from_modes("not a waveform")
+    corot = sb.WaveformModes(t=np.arange(5.0), data=np.zeros((5, 77), complex), ell_min=2, ell_max=8, frameType=sb.Corotating, dataType=sb.h)
+    with pytest.raises(ValueError):
+        corot.transform(time_translation=1.0)     # must be inertial (scri/waveform_grid.py:422-426)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the operators must fail loudly rather than compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    w = sb.sample_waveforms.constant_waveform()
+    with pytest.raises(_lib.Scrib200Error):
+        w.transform(time_translation=1.0)
+    with pytest.raises(_lib.Scrib200Error):
+        w.rotate_decomposition_basis(np.array([1.0, 0.0, 0.0, 0.0]))
+    with pytest.raises(_lib.Scrib200Error):
+        w.LLMatrix()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scri_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "scrib200.h")).read()
+    declared = set(re.findall(r"\b(scrib200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(_lib.LIB_PATH), "libscrib200.so not built (run __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/scrib200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.scrib200_version.restype = ctypes.c_int
+    assert lib.scrib200_version() >= 100
+
+
+def test_ladder_table():
+    tab = ops.ladder_table(2, 4)
+    LM = _sf.LM_range(2, 4)
+    for row, (l, m) in zip(tab, LM):
+        assert row[4] == m
+        assert np.isclose(row[0], np.sqrt((l - m) * (l + m + 1)) if m + 1 <= l else 0.0)
+        assert np.isclose(row[1], np.sqrt((l + m) * (l - m + 1)) if m - 1 >= -l else 0.0)

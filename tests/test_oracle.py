@@ -1,0 +1,217 @@
+"""Pins the CPU oracle: the reference's own analytic tests ported onto oracle/ (the reference stores no golden
+vectors and cannot be imported here), plus independent cross-checks against sympy / scipy.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import quat, scri_ref as R, sf, spinsfast as spf
+from scri_inputs import real_supertranslation, rotor_set, smooth_modes
+
+
+def constant_waveform(n_times=301):
+    # scri/sample_waveforms.py:70-87: data m - i m, inertial, h
+    t = np.linspace(-10.0, 100.0, n_times)
+    LM = sf.LM_range(2, 8)
+    data = np.zeros((t.size, LM.shape[0]), complex)
+    for i, m in enumerate(LM[:, 1]):
+        data[:, i] = m - 1j * m
+    return R.Modes(t=t, data=data)
+
+
+def test_wigner_d_against_sympy():
+    from sympy.physics.wigner import wigner_d_small
+
+    beta = 0.7
+    for ell in (1, 2, 4):
+        d = np.array(wigner_d_small(ell, beta).evalf(30).tolist(), dtype=float)
+        mine = np.array([[sf.wigner_d_small(beta, ell, mp, m) for m in range(ell, -ell - 1, -1)] for mp in range(ell, -ell - 1, -1)], dtype=float)
+        assert abs(mine - d.T).max() < 1e-14  # sf's d is the transpose of sympy's
+
+
+def test_swsh_against_scipy_and_closed_form():
+    from scipy.special import sph_harm_y
+
+    th, ph = 1.1, 2.3
+    Rq = quat.from_spherical_coords(th, ph)
+    Y = sf.SWSH_grid(Rq, 0, 8)
+    for l in range(9):
+        for m in range(-l, l + 1):
+            assert abs(Y[sf.LM_index(l, m, 0)] - sph_harm_y(l, m, th, ph)) < 5e-15
+    # -2Y22 = sqrt(5/64pi) (1+cos th)^2 e^{2i ph}
+    Y2 = sf.SWSH_grid(Rq, -2, 2)
+    assert abs(Y2[sf.LM_index(2, 2, 0)] - math.sqrt(5 / (64 * math.pi)) * (1 + math.cos(th)) ** 2 * np.exp(2j * ph)) < 1e-15
+
+
+def test_3j_and_cg_against_sympy():
+    from sympy.physics.wigner import clebsch_gordan, wigner_3j
+
+    for args in [(2, 2, 2, 0, 0, 0), (3, 4, 5, 1, -2, 1), (8, 4, 9, -3, 2, 1), (12, 4, 8, 5, -1, -4), (1, 8, 9, 1, -2, 1)]:
+        assert abs(sf.Wigner3j(*args) - float(wigner_3j(*args))) < 1e-14
+    assert abs(sf.clebsch_gordan(3, 1, 1, 0, 4, 1) - float(clebsch_gordan(3, 1, 4, 1, 0, 1))) < 1e-14
+
+
+def test_wigner_D_is_a_representation():
+    rng = np.random.default_rng(0)
+    R1, R2 = quat.normalized(rng.normal(size=4)), quat.normalized(rng.normal(size=4))
+    sp = quat.as_spinor_array
+    D1, D2, D12 = (sf.Wigner_D_matrices(*sp(q), 2, 5) for q in (R1, R2, quat.mul(R1, R2)))
+    off = 0
+    for ell in range(2, 6):
+        n = 2 * ell + 1
+        A, B, C = (D[off : off + n * n].reshape(n, n) for D in (D1, D2, D12))
+        assert abs(A @ B - C).max() < 2e-15
+        assert abs(A @ A.conj().T - np.eye(n)).max() < 2e-15
+        off += n * n
+
+
+@pytest.mark.parametrize("s,lmax,nth,nph", [(-2, 8, 19, 19), (0, 4, 9, 9), (1, 5, 13, 11), (2, 8, 25, 25), (-1, 6, 14, 13)])
+def test_spinsfast_round_trip(s, lmax, nth, nph):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(3, (lmax + 1) ** 2)) + 1j * rng.normal(size=(3, (lmax + 1) ** 2))
+    a[:, : s * s] = 0
+    assert abs(spf.map2salm(spf.salm2map(a, s, lmax, nth, nph), s, lmax) - a).max() < 2e-14
+
+
+def test_time_translation():
+    """reference tests/test_waveform_grid.py:17-27"""
+    dt = 1.469
+    w1 = constant_waveform()
+    w2 = R.transform(w1, time_translation=dt)
+    w3 = R.transform(w1, supertranslation=[math.sqrt(4 * math.pi) * dt])
+    assert np.allclose(w1.t, w2.t + dt, rtol=0.0, atol=2e-15)
+    assert np.allclose(w1.data, w2.data, rtol=0.0, atol=4e-14)
+    assert np.array_equal(w2.t, w3.t)
+    assert np.array_equal(w2.data, w3.data)
+
+
+def test_BMS_rotation():
+    """reference tests/test_waveform_grid.py:30-38: transform(frame_rotation=R) == rotate_decomposition_basis(R)"""
+    w1 = constant_waveform(101)
+    for Rq in rotor_set():
+        w2 = R.rotate_decomposition_basis(w1.copy(), Rq)
+        w3 = R.transform(w1, frame_rotation=Rq)
+        assert np.allclose(w2.data, w3.data, rtol=1e-15, atol=4e-13)
+
+
+@pytest.mark.parametrize("s,ell,m", [(-2, 2, 2), (-2, 3, -1), (-2, 8, 5), (-2, 5, 0)])
+def test_space_translation_analytic(s, ell, m):
+    """reference tests/test_waveform_grid.py:41-92 (slow there; a few (ell,m) here), analytic formula
+    scri/sample_waveforms.py:312-380: a beta*t mode supertranslated through 3j symbols."""
+    t = np.arange(-20.0, 20.0 + 0.1, 0.1)
+    n = sf.LM_total_size(2, 8)
+    for trans in ([1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]):
+        data = np.zeros((t.size, n), complex)
+        data[:, sf.LM_index(ell, m, 2)] = t
+        w1 = R.transform(R.Modes(t=t, data=data.copy(), dataType=R.psi4), space_translation=trans)
+        st = np.zeros(4, complex)
+        st[1:4] = -sf.vector_as_ell_1_modes(trans)
+        expect = np.zeros((t.size, n), complex)
+        expect[:, sf.LM_index(ell, m, 2)] = t
+        for i, (lpp, mpp) in enumerate(sf.LM_range(0, 1)):
+            if st[i] != 0.0:
+                mp = m + mpp
+                for lp in range(2, min(8, ell + lpp) + 1):
+                    if lp >= abs(mp):
+                        add = st[i] * math.sqrt(((2 * lpp + 1) * (2 * ell + 1) * (2 * lp + 1)) / (4 * math.pi)) * sf.Wigner3j(lpp, ell, lp, 0, -s, s) * sf.Wigner3j(lpp, ell, lp, mpp, m, -mp)
+                        if (s + mp) % 2 == 1:
+                            add *= -1
+                        expect[:, sf.LM_index(lp, mp, 2)] += add
+        i1 = np.argmin(abs(t - w1.t[0]))
+        i2 = np.argmin(abs(t - w1.t[-1]))
+        assert np.allclose(w1.data, expect[i1 : i2 + 1], rtol=0.0, atol=5e-14)
+
+
+def test_supertranslation_inverses():
+    """reference tests/test_waveform_grid.py:161-185 on smooth-in-time data (see SURVEY.md 7 on white noise)"""
+    t, data = smooth_modes(n_times=401, t0=-10.0, t1=30.0, seed=4)
+    data = data * 0 + (np.random.default_rng(4).normal(size=data.shape[1]) * (1 + 1j))[None, :] * t[:, None]
+    w1 = R.Modes(t=t, data=data, dataType=R.psi4)
+    for idx in (0, 2, 5, 12, 20):
+        st = np.zeros(25, complex)
+        lm = sf.LM_range(0, 4)[idx]
+        if lm[1] == 0:
+            st[idx] = 1.0
+        else:
+            st[sf.LM_index(lm[0], lm[1], 0)] = 1.0j
+            st[sf.LM_index(lm[0], -lm[1], 0)] = (-1.0) ** lm[1] * -1.0j
+        w2 = R.transform(R.transform(w1, supertranslation=st), supertranslation=-st)
+        expect = R.interpolate_data(w1, w2.t)
+        assert np.allclose(w2.data, expect, rtol=5e-10, atol=5e-12)
+
+
+def test_rotation_inverse_and_invariants():
+    """reference tests/test_rotations.py:14-129 (identity bit-exact, R then ~R, constant vs series)"""
+    t, data = smooth_modes(n_times=50)
+    W = R.Modes(t=t, data=data.copy())
+    R.rotate_decomposition_basis(W, np.array([1.0, 0, 0, 0]))
+    assert np.array_equal(W.data, data)
+    for Rq in rotor_set(3):
+        W = R.Modes(t=t, data=data.copy())
+        R.rotate_decomposition_basis(W, Rq)
+        Ws = R.Modes(t=t, data=data.copy())
+        R.rotate_decomposition_basis(Ws, np.tile(Rq, (t.size, 1)))
+        assert np.allclose(W.data, Ws.data, rtol=0, atol=1e-14)
+        assert np.allclose(R.norm(W), np.sum(abs(data) ** 2, axis=1), rtol=1e-13)
+        R.rotate_decomposition_basis(W, quat.conj(Rq))
+        assert np.allclose(W.data, data, rtol=0, atol=5e-14)
+
+
+def test_LL_and_angular_velocity_of_rotating_mode():
+    """reference tests/test_mode_calculations.py:14-126 (simple cases): a (2,2)+(2,-2) mode rotating about z
+    with frequency w has dominant axis z and angular velocity (0,0,w)."""
+    t = np.linspace(0.0, 20.0, 2001)
+    omega = 0.3
+    n = sf.LM_total_size(2, 4)
+    data = np.zeros((t.size, n), complex)
+    data[:, sf.LM_index(2, 2, 2)] = np.exp(-2j * omega * t)
+    data[:, sf.LM_index(2, -2, 2)] = np.exp(2j * omega * t)
+    W = R.Modes(t=t, data=data, ell_min=2, ell_max=4)
+    dpa = R.LLDominantEigenvector(W)
+    assert np.allclose(dpa, np.array([0, 0, 1.0])[None, :], atol=1e-14)
+    om = R.angular_velocity(W)
+    assert np.allclose(om[5:-5], np.array([0, 0, omega])[None, :], atol=1e-9)
+    # covariance: rotate the decomposition basis by a constant rotor; omega rotates as a vector
+    Rq = quat.normalized(np.array([1.0, 2.0, 3.0, 4.0]))
+    W2 = R.rotate_decomposition_basis(R.Modes(t=t, data=data.copy(), ell_min=2, ell_max=4), Rq)
+    om2 = R.angular_velocity(W2)
+    expect = quat.rotate_vector(quat.conj(Rq), np.array([0, 0, omega]))
+    assert np.allclose(om2[5:-5], expect[None, :], atol=1e-9)
+
+
+def test_flux_against_grid_integration():
+    """reference tests/test_flux.py:38-129: the CG-based sparse momentum / angular-momentum flux equals the
+    explicit integral over the sphere (here with the oracle's own salm2map and a Gauss-Legendre-free
+    Clenshaw-Curtis quadrature through map2salm of |hdot|^2 n^i)."""
+    t, data = smooth_modes(n_times=60, ell_max=6, seed=3)
+    W = R.Modes(t=t, data=data, ell_min=2, ell_max=6, dataType=R.hdot)
+    pdot = R.momentum_flux(W)
+    # explicit: dp^i/dt = (1/16pi) int |hdot|^2 n^i dOmega ; |hdot|^2 n^i has band limit 2*6+1
+    L = 14
+    nth = nph = 2 * L + 1
+    a = np.zeros((t.size, (6 + 1) ** 2), complex)
+    a[:, 4:] = data
+    f = spf.salm2map(a, -2, 6, nth, nph)
+    theta = np.linspace(0, np.pi, nth)
+    phi = np.linspace(0, 2 * np.pi, nph, endpoint=False)
+    nx = np.sin(theta)[:, None] * np.cos(phi)[None, :]
+    ny = np.sin(theta)[:, None] * np.sin(phi)[None, :]
+    nz = np.cos(theta)[:, None] * np.ones_like(phi)[None, :]
+    p2 = abs(f) ** 2
+    for i, nvec in enumerate((nx, ny, nz)):
+        integ = spf.map2salm(p2 * nvec[None], 0, 0)[:, 0].real * math.sqrt(4 * math.pi)
+        assert np.allclose(pdot[:, i], integ / (16 * math.pi), rtol=1e-12, atol=1e-13)
+    # energy: (1/16pi) int |hdot|^2
+    E = spf.map2salm(p2, 0, 0)[:, 0].real * math.sqrt(4 * math.pi) / (16 * math.pi)
+    assert np.allclose(R.energy_flux(W), E, rtol=1e-12)
+
+
+def test_golden_fixture_matches_oracle():
+    """The committed golden vectors (tests/golden/make_golden.py) still come out of the oracle."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "transform_small.npz"))
+    W = R.Modes(t=g["t"], data=g["data"])
+    out = R.transform(W, supertranslation=g["supertranslation"], frame_rotation=g["frame_rotation"], boost_velocity=g["boost_velocity"])
+    assert np.array_equal(out.t, g["out_t"])
+    assert np.allclose(out.data, g["out_data"], rtol=0, atol=1e-14)
