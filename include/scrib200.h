@@ -77,6 +77,13 @@ int scrib200_bms_spline_remap(const double* t, int64_t n_times, const double* F,
                               const double* alpha, const double* uprm, int64_t n_out, double* out, int chunk,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same remap, output written time-tiled: out[(i'/T)*(G*T) + g*T + i'%T], T = tile (power of two), buffer of
+ * ceil(n_out/T)*G*T elements: the layout the transform path hands to scrib200_map2salm_tiled (each thread's
+ * consecutive outputs are contiguous in HBM, each analysis CTA reads one contiguous [G, T] tile). */
+int scrib200_bms_spline_remap_tiled(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
+                                    const double* alpha, const double* uprm, int64_t n_out, double* out, int tile,
+                                    int chunk, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * SWSH analysis, batched over time steps.
  * Replaces  scri/waveform_grid.py:303-307 (spinsfast.map2salm per time step, first ell_min^2 modes
@@ -90,6 +97,14 @@ size_t scrib200_map2salm_workspace_bytes(int64_t n_times, int n_theta, int n_phi
 int scrib200_map2salm(const double* grid, int64_t n_times, int n_theta, int n_phi, const double* E,
                       const double* Wt, int ell_min, int ell_max, double* out, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Same analysis on a time-tiled grid (output of scrib200_bms_spline_remap_tiled with the same `tile`).
+ *   trig [n_phi, ell_max+1] complex128 = (cos, sin)(m phi_k)/n_phi  (scri_b200.plan: from the E table)
+ * scrib200_map2salm_tile_size returns the tile to use (8, 4 or 2) or 0 when the tables do not fit one CTA;
+ * callers then use the time-major pair scrib200_bms_spline_remap / scrib200_map2salm. */
+int scrib200_map2salm_tile_size(int n_theta, int n_phi, int ell_min, int ell_max);
+int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_times, int n_theta, int n_phi, const double* trig,
+                            const double* Wt, int ell_min, int ell_max, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Time derivative of every mode through the not-a-knot cubic spline.

@@ -28,6 +28,12 @@ SIGNATURES = {
         c_int,
         [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_sz, c_vp],
     ),
+    "scrib200_bms_spline_remap_tiled": (
+        c_int,
+        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_sz, c_vp],
+    ),
+    "scrib200_map2salm_tile_size": (c_int, [c_int, c_int, c_int, c_int]),
+    "scrib200_map2salm_tiled": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "scrib200_map2salm_workspace_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "scrib200_spline_derivative": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
     "scrib200_norm": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),

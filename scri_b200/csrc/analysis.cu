@@ -109,6 +109,130 @@ __global__ void map2salm_quad_kernel(const double2* __restrict__ fm, int64_t n_t
     out[idx] = acc;
 }
 
+// ---- fast path inside transform(): the grid arrives time-tiled, tile b = contiguous [G][T] block (what the
+// spline remap writes).  One elected thread pulls the whole tile into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier; the second CTA resident on the SM computes meanwhile), then one thread per
+// (theta ring j, time step tt) walks the ring's n_phi samples (quarter-warps read 128 contiguous bytes: no bank
+// conflicts) and accumulates all m at once.  The +m / -m pair shares its four real products:
+//   f (c -+ i s):  P1 = sum fr c, P2 = sum fi s, P3 = sum fi c, P4 = sum fr s;
+//   f_{+m} = (P1+P2) + i(P3-P4),  f_{-m} = (P1-P2) + i(P3+P4)            - half the FMAs of a complex DFT.
+// The f_m(theta_j) results overwrite the tile (after a barrier) and feed the theta quadrature.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+map2salm_tiled_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_theta, int n_phi,
+                      const double2* __restrict__ trig, const double* __restrict__ Wt, int ell_min, int ell_max,
+                      double2* __restrict__ out, int T, int alias) {
+    extern __shared__ __align__(128) double2 sm3[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int L = ell_max, nm = 2 * L + 1, np1 = L + 1;
+    const int G = n_theta * n_phi;
+    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    double2* sTile = sm3;                                                  // [G][T]
+    double2* sFm = alias ? sTile : sTile + (size_t)G * T;                  // [T][n_theta][nm]
+    const size_t fm_elems = (size_t)T * n_theta * nm, tile_elems = (size_t)G * T;
+    double2* sTrig = sTile + (alias ? (fm_elems > tile_elems ? fm_elems : tile_elems) : tile_elems + fm_elems);
+    double* sW = reinterpret_cast<double*>(sTrig + n_phi * np1);           // [n_modes][n_theta]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * T;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned total = (unsigned)(tile_elems * sizeof(double2));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+        const char* src = reinterpret_cast<const char*>(gridT + (int64_t)blockIdx.x * tile_elems);
+        char* dst = reinterpret_cast<char*>(sTile);
+        for (unsigned off = 0; off < total; off += 32768u) {
+            const unsigned n = (total - off < 32768u) ? (total - off) : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(dst + off)),
+                         "l"(src + off), "r"(n), "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+    }
+    for (int i = tid; i < n_phi * np1; i += nt) sTrig[i] = trig[i];
+    for (int i = tid; i < n_modes * n_theta; i += nt) sW[i] = Wt[i];
+    __syncthreads();   // tables visible; mbarrier initialised before anyone polls it
+    {
+        unsigned ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok)
+                         : "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+    }
+
+    const bool worker = tid < T * n_theta;
+    const int j = tid / T, tt = tid - (tid / T) * T;
+    for (int p0 = 0; p0 <= L; p0 += NP) {
+        double acc[NP][4];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+        if (worker) {
+            const double2* src = sTile + (size_t)j * n_phi * T + tt;
+#pragma unroll 5
+            for (int k = 0; k < n_phi; ++k) {
+                const double2 f = src[k * T];
+                const double2* cs = sTrig + k * np1 + p0;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (p0 + q <= L) {
+                        const double2 c = cs[q];
+                        acc[q][0] = fma(f.x, c.x, acc[q][0]);
+                        acc[q][1] = fma(f.y, c.y, acc[q][1]);
+                        acc[q][2] = fma(f.y, c.x, acc[q][2]);
+                        acc[q][3] = fma(f.x, c.y, acc[q][3]);
+                    }
+                }
+            }
+        }
+        if (alias) __syncthreads();   // single pass: everyone is done reading the tile before it is overwritten
+        if (worker) {
+            double2* dst = sFm + ((size_t)tt * n_theta + j) * nm + L;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int p = p0 + q;
+                if (p <= L) {
+                    dst[p] = make_double2(acc[q][0] + acc[q][1], acc[q][2] - acc[q][3]);
+                    if (p > 0) dst[-p] = make_double2(acc[q][0] - acc[q][1], acc[q][2] + acc[q][3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int Tv = (int)((n_times - t0 < T) ? (n_times - t0) : T);
+    for (int idx = tid; idx < Tv * n_modes; idx += nt) {
+        const int t2 = idx / n_modes;
+        const int lm = idx - t2 * n_modes;
+        int ell, m;
+        lm_from_index(lm, ell_min, ell, m);
+        const double2* fm = sFm + (size_t)t2 * n_theta * nm + (m + L);
+        const double* w = sW + lm * n_theta;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int jj = 0; jj < n_theta; ++jj) {
+            const double2 v = fm[jj * nm];
+            acc.x = fma(w[jj], v.x, acc.x);
+            acc.y = fma(w[jj], v.y, acc.y);
+        }
+        out[(t0 + t2) * n_modes + lm] = acc;
+    }
+}
+
+constexpr int TILED_NP = 9;
+
+static size_t gmajor_smem(int T, int n_theta, int n_phi, int ell_min, int ell_max) {
+    const size_t nm = 2 * ell_max + 1;
+    const size_t n_modes = (size_t)ell_max * (ell_max + 2) - (size_t)ell_min * ell_min + 1;
+    const size_t tile = (size_t)n_theta * n_phi * T, fm = (size_t)T * n_theta * nm;
+    const bool alias = (ell_max + 1 <= TILED_NP);
+    const size_t data = alias ? (tile > fm ? tile : fm) : tile + fm;
+    return (data + (size_t)n_phi * (ell_max + 1)) * sizeof(double2) + n_modes * n_theta * sizeof(double);
+}
+
 static size_t fused_smem(int T, int n_theta, int n_phi, int ell_min, int ell_max) {
     const size_t nm = 2 * ell_max + 1;
     const size_t n_modes = (size_t)ell_max * (ell_max + 2) - (size_t)ell_min * ell_min + 1;
@@ -162,5 +286,38 @@ extern "C" int scrib200_map2salm(const double* grid, int64_t n_times, int n_thet
     map2salm_quad_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(fm, n_times, n_theta, ell_min, ell_max, Wt,
                                                                           reinterpret_cast<double2*>(out));
     SCRIB200_CHECK_LAUNCH("map2salm(quad)");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_map2salm_tile_size(int n_theta, int n_phi, int ell_min, int ell_max) {
+    using namespace scrib200;
+    // largest time tile T (power of two <= 8) whose tables fit a CTA at >= 2 CTAs per SM; 0 = use scrib200_map2salm
+    for (int T = 8; T >= 2; T >>= 1)
+        if (T * n_theta <= 256 && gmajor_smem(T, n_theta, n_phi, ell_min, ell_max) <= 110 * 1024) return T;
+    return 0;
+}
+
+extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_times, int n_theta, int n_phi,
+                                       const double* trig, const double* Wt, int ell_min, int ell_max, double* out,
+                                       void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(gridT && trig && Wt && out, "map2salm_tiled: null pointer");
+    SCRIB200_REQUIRE(n_theta >= 2 && n_phi >= 1, "map2salm_tiled: bad grid %d x %d", n_theta, n_phi);
+    SCRIB200_REQUIRE(ell_min >= 0 && ell_max >= ell_min, "map2salm_tiled: bad ell range [%d, %d]", ell_min, ell_max);
+    SCRIB200_REQUIRE(aligned16(gridT) && aligned16(trig) && aligned16(out), "map2salm_tiled: pointers must be 16-byte aligned");
+    if (n_times <= 0) return SCRIB200_OK;
+    const int T = tile;
+    const size_t smem = gmajor_smem(T, n_theta, n_phi, ell_min, ell_max);
+    SCRIB200_REQUIRE(T >= 2 && T * n_theta <= 256 && smem <= 200 * 1024,
+                     "map2salm_tiled: tile %d with grid %d x %d, ell_max=%d does not fit one CTA (use scrib200_map2salm)", T,
+                     n_theta, n_phi, ell_max);
+    int threads = ((T * n_theta + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    cudaFuncSetAttribute(map2salm_tiled_kernel<TILED_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t blocks = (n_times + T - 1) / T;
+    map2salm_tiled_kernel<TILED_NP><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(gridT), n_times, n_theta, n_phi, reinterpret_cast<const double2*>(trig), Wt,
+        ell_min, ell_max, reinterpret_cast<double2*>(out), T, (ell_max + 1 <= TILED_NP) ? 1 : 0);
+    SCRIB200_CHECK_LAUNCH("map2salm_tiled");
     return SCRIB200_OK;
 }

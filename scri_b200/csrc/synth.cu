@@ -16,7 +16,7 @@
 
 namespace scrib200 {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
 constexpr int AS = BK + 4;   // A smem row stride (doubles)
 constexpr int BS = BN + 4;   // B smem row stride (doubles)
 constexpr int A_STAGE = BM * AS;

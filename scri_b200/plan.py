@@ -282,7 +282,12 @@ class TransformPlan:
         self.d_alpha = torch.from_numpy(np.ascontiguousarray(self.alpha)).to(dev)
         self.d_E = torch.from_numpy(np.ascontiguousarray(E)).to(dev)
         self.d_Wt = torch.from_numpy(Wt).to(dev)
+        # (cos, sin)(m phi_k)/n_phi for m = 0..L: the +m column of E is (cos - i sin)/n_phi
+        Lo = self.out_ell_max
+        trig = np.ascontiguousarray(np.conj(E[:, Lo:]))
+        self.d_trig = torch.from_numpy(trig).to(dev)
         self._ws = None
+        self._tile = None
         self.spline_chunk = 0
 
     # -- the individual stages (device tensors in, device tensors out) ---------------------------
@@ -301,14 +306,22 @@ class TransformPlan:
         )
         return F
 
-    def output_times(self, t):
-        """u'_i and the retained block (waveform_grid.py:564-568).  `t` is a device tensor."""
+    def output_times(self, t, t_ends=None):
+        """u'_i and the retained block (waveform_grid.py:564-568).  `t` is a device tensor; `t_ends` = (t[0], t[-1])
+        on the host saves one device read."""
         torch = self.torch
         uprm = (1 / self.gamma) * (t - self.time_translation)
-        t0, t1 = float(t[0]), float(t[-1])
-        uprm_min = (self.kconformal * (t0 - self.alpha)).max()
-        uprm_max = (self.kconformal * (t1 - self.alpha)).min()
-        return uprm[(uprm >= uprm_min) & (uprm <= uprm_max)].contiguous()
+        if t_ends is None:
+            ends = t[[0, -1]].cpu()
+            t_ends = (float(ends[0]), float(ends[1]))
+        uprm_min = (self.kconformal * (t_ends[0] - self.alpha)).max()
+        uprm_max = (self.kconformal * (t_ends[1] - self.alpha)).min()
+        # u' is increasing, so the retained samples (uprm_min <= u' <= uprm_max) are one contiguous block
+        bounds = torch.tensor([uprm_min, uprm_max], dtype=torch.float64, device=self.device)
+        lo = torch.searchsorted(uprm, bounds[:1], right=False)
+        hi = torch.searchsorted(uprm, bounds[1:], right=True)
+        lo_hi = torch.cat([lo, hi]).cpu()
+        return uprm[int(lo_hi[0]) : int(lo_hi[1])]
 
     def remap(self, t, F, uprm):
         """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588)."""
@@ -332,10 +345,55 @@ class TransformPlan:
         """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307)."""
         return map2salm(grid, self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max, self.d_E, self.d_Wt)
 
-    def run(self, t, data, return_grid=False):
-        """Whole path on device tensors: returns (u', modes') or (u', grid')."""
+    # -- g-major variants: the layout the fused transform path uses between remap and analysis ----
+    def remap_tiled(self, t, F, uprm):
+        """Same spline remap, result stored time-tiled: [ceil(N'/T), G, T] (T = self.tile)."""
+        torch = self.torch
+        lib = _lib.load()
+        N, n_out = t.shape[0], uprm.shape[0]
+        T = self.tile
+        out = torch.empty((-(-n_out // T), self.G, T), dtype=torch.complex128, device=self.device)
+        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, self.spline_chunk)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(
+            lib.scrib200_bms_spline_remap_tiled(
+                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(uprm), n_out,
+                _lib.ptr(out), T, self.spline_chunk, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr(),
+            ),
+            "bms_spline_remap_tiled",
+        )
+        return out
+
+    def analyze_tiled(self, gridT, n_out):
+        """gridT [ceil(N'/T), G, T] complex128 (time-tiled) -> [n_out, n_modes_out]."""
+        torch = self.torch
+        lib = _lib.load()
+        out = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, device=self.device)
+        _lib.check(
+            lib.scrib200_map2salm_tiled(
+                _lib.ptr(gridT), self.tile, n_out, self.n_theta, self.n_phi, _lib.ptr(self.d_trig), _lib.ptr(self.d_Wt),
+                self.out_ell_min, self.out_ell_max, _lib.ptr(out), _lib.stream_ptr(),
+            ),
+            "map2salm_tiled",
+        )
+        return out
+
+    @property
+    def tile(self):
+        """Time-tile size of the remap -> analysis hand-off (0: tables too large, use the time-major kernels)."""
+        if self._tile is None:
+            self._tile = int(_lib.load().scrib200_map2salm_tile_size(self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max))
+        return self._tile
+
+    def run(self, t, data, return_grid=False, t_ends=None):
+        """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major])."""
         F = self.synthesize(data)
-        uprm = self.output_times(t)
+        uprm = self.output_times(t, t_ends)
+        if self.tile and not return_grid:
+            gridT = self.remap_tiled(t, F, uprm)
+            del F
+            return uprm, self.analyze_tiled(gridT, uprm.shape[0])
         grid = self.remap(t, F, uprm)
         del F
         if return_grid:

@@ -97,7 +97,7 @@ class WaveformGrid(WaveformBase):
         )
         t_d = ops.to_device(w_modes.t, np.float64)
         a_d = ops.to_device(w_modes.data, np.complex128)
-        uprm, grid = plan.run(t_d, a_d, return_grid=True)
+        uprm, grid = plan.run(t_d, a_d, return_grid=True, t_ends=(w_modes.t[0], w_modes.t[-1]))
         g = cls(
             t=uprm.cpu().numpy(),
             data=grid.cpu().numpy(),
@@ -131,7 +131,7 @@ class WaveformGrid(WaveformBase):
         )
         t_d = ops.to_device(w_modes.t, np.float64)
         a_d = ops.to_device(w_modes.data, np.complex128)
-        uprm, modes = plan.run(t_d, a_d)
+        uprm, modes = plan.run(t_d, a_d, t_ends=(w_modes.t[0], w_modes.t[-1]))
         if plan.leftover_kwargs:
             warnings.warn("\nUnused kwargs passed to this function:\n{}".format(pprint.pformat(plan.leftover_kwargs, width=1)))
         return WaveformModes(
