@@ -7,10 +7,14 @@
 // scri/waveform_base.py:689-695 (CubicSpline(t, data).derivative(k)(t)) with k = 1, alpha = 0.
 //
 // The interpolating cubic spline is unique, so it is computed here in the moment (second-derivative)
-// form: tridiagonal system  h_{i-1} M_{i-1} + 2(h_{i-1}+h_i) M_i + h_i M_{i+1} = 6(d_i - d_{i-1})
-// with the not-a-knot conditions eliminated into the first and last rows, solved by a Thomas sweep.
-// The knots are the reference's own rounded abscissae (x_i computed as mul(k, sub(t, alpha)) with no
-// FMA contraction), because at t ~ 1e4 one ulp of x already moves the interpolant at the 1e-13 level.
+// form.  Row i of the tridiagonal system, multiplied through by h_{i-1} h_i so that no division is
+// needed to set it up:
+//     h_{i-1}^2 h_i M_{i-1} + 2 (h_{i-1}+h_i) h_{i-1} h_i M_i + h_{i-1} h_i^2 M_{i+1}
+//         = 6 (h_{i-1} (y_{i+1}-y_i) - h_i (y_i-y_{i-1}))
+// with the not-a-knot conditions eliminated into the first and last rows, solved by a Thomas sweep
+// (one reciprocal per row).  The knots are the reference's own rounded abscissae (x_i computed as
+// mul(k, sub(t, alpha)) with no FMA contraction), because at t ~ 1e4 one ulp of x already moves the
+// interpolant at the 1e-13 level.
 //
 // Parallelisation: one thread per (grid point, chunk of knots); lanes run along g so every access to
 // the [time, g] arrays is coalesced.  A chunk solves its knots plus a halo of HALO knots on each side
@@ -38,7 +42,7 @@ constexpr int CKB = 4;   // rows per checkpoint block
 struct Knots {
     const double* t;
     double k, alpha;
-    __device__ __forceinline__ double x(int64_t i) const { return __dmul_rn(k, __dsub_rn(t[i], alpha)); }
+    __device__ __forceinline__ double x(int i) const { return __dmul_rn(k, __dsub_rn(t[i], alpha)); }
 };
 
 __device__ __forceinline__ double2 eval_piece(double u, double xi, double xi1, double h, double inv_h, double2 yi,
@@ -56,42 +60,45 @@ __device__ __forceinline__ double2 eval_piece(double u, double xi, double xi1, d
 
 // Rolling state of the forward elimination at row i (before the row is processed).
 struct Sweep {
-    double x_i, h_im1, inv_him1, cp;
-    double2 y_i, d_im1, dp;
-    int64_t N, rs, re;
+    double x_i, h_im1, cp;
+    double2 y_i, dy_im1, dp;     // dy_im1 = y_i - y_{i-1}
+    int N, rs, re;
     bool true_lo, true_hi;
 
-    __device__ __forceinline__ void start(const Knots& kn, const double2* Fg, int G, int64_t i0, double cp0, double2 dp0) {
+    __device__ __forceinline__ void start(const Knots& kn, const double2* Fg, int G, int i0, double cp0, double2 dp0) {
         const double x_im1 = kn.x(i0 - 1);
         x_i = kn.x(i0);
-        const double2 y_im1 = Fg[(i0 - 1) * G];
-        y_i = Fg[i0 * G];
+        const double2 y_im1 = Fg[(int64_t)(i0 - 1) * G];
+        y_i = Fg[(int64_t)i0 * G];
         h_im1 = x_i - x_im1;
-        inv_him1 = 1.0 / h_im1;
-        d_im1 = make_double2((y_i.x - y_im1.x) * inv_him1, (y_i.y - y_im1.y) * inv_him1);
+        dy_im1 = make_double2(y_i.x - y_im1.x, y_i.y - y_im1.y);
         cp = cp0;
         dp = dp0;
     }
 
-    // eliminate row i given knot/value i+1; afterwards the state refers to row i+1
-    __device__ __forceinline__ void step(int64_t i, double x_ip1, double2 y_ip1) {
+    // eliminate row i given knot/value i+1; afterwards the state refers to row i+1.
+    // PLAIN: the row is neither the first nor the last of the window (no end conditions to apply).
+    template <bool PLAIN>
+    __device__ __forceinline__ void step(int i, double x_ip1, double2 y_ip1) {
         const double h_i = x_ip1 - x_i;
-        const double inv_hi = 1.0 / h_i;
-        const double2 d_i = make_double2((y_ip1.x - y_i.x) * inv_hi, (y_ip1.y - y_i.y) * inv_hi);
-        double sub = h_im1, diag = 2.0 * (h_im1 + h_i), sup = h_i;
-        if (i == 1 && true_lo) {          // not-a-knot at the left end, M_0 eliminated
-            sub = 0.0;
-            diag = (h_im1 + h_i) * (h_im1 + 2.0 * h_i) * inv_hi;
-            sup = (h_i * h_i - h_im1 * h_im1) * inv_hi;
+        const double2 dy_i = make_double2(y_ip1.x - y_i.x, y_ip1.y - y_i.y);
+        const double hh = h_im1 * h_i;
+        double sub = h_im1 * hh, diag = 2.0 * (h_im1 + h_i) * hh, sup = hh * h_i;
+        if (!PLAIN) {
+            if (i == 1 && true_lo) {          // not-a-knot at the left end, M_0 eliminated
+                sub = 0.0;
+                diag = (h_im1 + h_i) * (h_im1 + 2.0 * h_i) * h_im1;
+                sup = (h_i * h_i - h_im1 * h_im1) * h_im1;
+            }
+            if (i == N - 2 && true_hi) {      // not-a-knot at the right end, M_{N-1} eliminated
+                diag = (h_im1 + h_i) * (2.0 * h_im1 + h_i) * h_i;
+                sub = (h_im1 * h_im1 - h_i * h_i) * h_i;
+                sup = 0.0;
+            }
+            if (i == rs && !true_lo) sub = 0.0;   // natural cut: M_lo = 0
+            if (i == re && !true_hi) sup = 0.0;   // natural cut: M_hi = 0
         }
-        if (i == N - 2 && true_hi) {      // not-a-knot at the right end, M_{N-1} eliminated
-            diag = (h_im1 + h_i) * (2.0 * h_im1 + h_i) * inv_him1;
-            sub = (h_im1 * h_im1 - h_i * h_i) * inv_him1;
-            sup = 0.0;
-        }
-        if (i == rs && !true_lo) sub = 0.0;   // natural cut: M_lo = 0
-        if (i == re && !true_hi) sup = 0.0;   // natural cut: M_hi = 0
-        const double2 rhs = make_double2(6.0 * (d_i.x - d_im1.x), 6.0 * (d_i.y - d_im1.y));
+        const double2 rhs = make_double2(6.0 * (h_im1 * dy_i.x - h_i * dy_im1.x), 6.0 * (h_im1 * dy_i.y - h_i * dy_im1.y));
         const double inv_den = 1.0 / (diag - sub * cp);
         cp = sup * inv_den;
         dp.x = (rhs.x - sub * dp.x) * inv_den;
@@ -99,45 +106,43 @@ struct Sweep {
         x_i = x_ip1;
         y_i = y_ip1;
         h_im1 = h_i;
-        inv_him1 = inv_hi;
-        d_im1 = d_i;
+        dy_im1 = dy_i;
     }
 };
 
 // MODE 0: evaluate at up[] (the BMS remap); MODE 1 / 2: first / second derivative at the knots themselves
 // (out is then [N, G]; `up`/`Nout` unused).
 template <int MODE>
-__global__ void __launch_bounds__(64)
-spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __restrict__ F, int G,
+__global__ void __launch_bounds__(64, 8)
+spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restrict__ F, int G,
                    const double* __restrict__ kconf, const double* __restrict__ alpha, const double* __restrict__ up,
-                   int64_t Nout, double2* __restrict__ out, int64_t out_ld, int C, int NCK,
-                   double* __restrict__ ws_c, double2* __restrict__ ws_d) {
+                   int Nout, double2* __restrict__ out, int tshift, int C, int NCK, double* __restrict__ ws_c,
+                   double2* __restrict__ ws_d) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    // MODE 0 output layout: out_ld == 0 -> time-major out[i'*G + g]; out_ld = log2(T) > 0 -> time-tiled
+    // MODE 0 output layout: tshift == 0 -> time-major out[i'*G + g]; tshift = log2(T) > 0 -> time-tiled
     // out[(i'/T)*(G*T) + g*T + i'%T].  Tiling makes each thread's consecutive outputs contiguous (runs of T), so L2
     // merges them into full sectors (time-major 16-byte stores from lanes sitting at different i' never meet their
     // sector neighbour: 2x write traffic), and hands the analysis kernel one contiguous [G, T] tile per CTA.
-    const int tshift = (int)out_ld;
-    const int64_t tmask = ((int64_t)1 << tshift) - 1;
+    const int tmask = (1 << tshift) - 1;
     const int64_t tileGT = (int64_t)G << tshift;
     double2* og = out + (tshift > 0 ? ((int64_t)g << tshift) : (int64_t)g);
-#define SCRIB200_OIDX(ip_) (tshift > 0 ? ((ip_) >> tshift) * tileGT + ((ip_) & tmask) : (ip_) * (int64_t)G)
-    const int64_t chunk = blockIdx.y;
-    const int64_t a = chunk * C;                             // first interval of this chunk
-    const int64_t b = (a + C < N - 1) ? a + C : N - 1;       // intervals a .. b-1, knots a .. b
+#define SCRIB200_OIDX(ip_) (tshift > 0 ? (int64_t)((ip_) >> tshift) * tileGT + ((ip_) & tmask) : (int64_t)(ip_) * G)
+    const int chunk = blockIdx.y;
+    const int a = chunk * C;                                 // first interval of this chunk
+    const int b = (a + C < N - 1) ? a + C : N - 1;           // intervals a .. b-1, knots a .. b
     const bool last_chunk = (b == N - 1);
-    const int64_t lo = (a - HALO > 0) ? a - HALO : 0;
-    const int64_t hi = (b + HALO < N - 1) ? b + HALO : N - 1;
+    const int lo = (a - HALO > 0) ? a - HALO : 0;
+    const int hi = (b + HALO < N - 1) ? b + HALO : N - 1;
     const bool true_lo = (lo == 0), true_hi = (hi == N - 1);
-    const int64_t rs = lo + 1, re = hi - 1;                  // rows solved (N >= 4 => re >= rs + 1)
-    const int nrows = (int)(re - rs + 1);
+    const int rs = lo + 1, re = hi - 1;                      // rows solved (N >= 4 => re >= rs + 1)
+    const int nrows = re - rs + 1;
     const int nblocks = (nrows + CKB - 1) / CKB;
     const int first = nrows - (nblocks - 1) * CKB;           // size of block 0 (1..CKB); the others are full
     // first block the backward pass has to visit: the one holding row max(a, rs)
     int kmin = 0;
     if (a > rs) {
-        const int j = (int)(a - rs);
+        const int j = a - rs;
         kmin = (j < first) ? 0 : 1 + (j - first) / CKB;
     }
 
@@ -152,19 +157,25 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
     // ---------------- forward pass: only the checkpoints survive
     sw.start(kn, Fg, G, rs, 0.0, make_double2(0.0, 0.0));
     for (int k = 0; k + 1 < nblocks; ++k) {
-        const int64_t i0 = (k == 0) ? rs : rs + first + (int64_t)(k - 1) * CKB;
+        const int i0 = (k == 0) ? rs : rs + first + (k - 1) * CKB;
         const int nb = (k == 0) ? first : CKB;
         double xb[CKB];
         double2 yb[CKB];
+        const double2* prow = Fg + (int64_t)(i0 + 1) * G;
 #pragma unroll
         for (int r = 0; r < CKB; ++r)
             if (r < nb) {
-                yb[r] = Fg[(i0 + r + 1) * G];
+                yb[r] = prow[(int64_t)r * G];
                 xb[r] = kn.x(i0 + r + 1);
             }
+        if (k > 0) {   // full block strictly inside the window (the last block is never processed here)
 #pragma unroll
-        for (int r = 0; r < CKB; ++r)
-            if (r < nb) sw.step(i0 + r, xb[r], yb[r]);
+            for (int r = 0; r < CKB; ++r) sw.step<true>(i0 + r, xb[r], yb[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < CKB; ++r)
+                if (r < nb) sw.step<false>(i0 + r, xb[r], yb[r]);
+        }
         if (k + 1 >= kmin) {
             wc[(size_t)(k + 1) * G] = sw.cp;
             wd[(size_t)(k + 1) * G] = sw.dp;
@@ -172,15 +183,15 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
     }
 
     // ---------------- output pointer: last output handled by this chunk
-    int64_t ip = -1;
+    int ip = -1;
     if (MODE != 0) {
     } else if (last_chunk) {
         ip = Nout - 1;
     } else {
         const double xb_ = kn.x(b);
-        int64_t lo_s = 0, hi_s = Nout;     // count of up[] < x_b
+        int lo_s = 0, hi_s = Nout;     // count of up[] < x_b
         while (lo_s < hi_s) {
-            int64_t mid = (lo_s + hi_s) >> 1;
+            int mid = (lo_s + hi_s) >> 1;
             if (up[mid] < xb_) lo_s = mid + 1; else hi_s = mid;
         }
         ip = lo_s - 1;
@@ -192,7 +203,7 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
     double x_ip1 = 0.0;
     double2 y_ip1 = make_double2(0.0, 0.0);
     for (int k = nblocks - 1; k >= kmin; --k) {
-        const int64_t i0 = (k == 0) ? rs : rs + first + (int64_t)(k - 1) * CKB;
+        const int i0 = (k == 0) ? rs : rs + first + (k - 1) * CKB;
         const int nb = (k == 0) ? first : CKB;
         double cp0 = 0.0;
         double2 dp0 = make_double2(0.0, 0.0);
@@ -202,22 +213,32 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
         }
         double xb[CKB], cpb[CKB];
         double2 yb[CKB], dpb[CKB];
+        const double2* prow = Fg + (int64_t)(i0 + 1) * G;
 #pragma unroll
         for (int r = 0; r < CKB; ++r)
             if (r < nb) {
-                yb[r] = Fg[(i0 + r + 1) * G];
+                yb[r] = prow[(int64_t)r * G];
                 xb[r] = kn.x(i0 + r + 1);
             }
         sw.start(kn, Fg, G, i0, cp0, dp0);
         const double x_i0 = sw.x_i;
         const double2 y_i0 = sw.y_i;
+        if (k > 0 && k < nblocks - 1) {
 #pragma unroll
-        for (int r = 0; r < CKB; ++r)
-            if (r < nb) {
-                sw.step(i0 + r, xb[r], yb[r]);
+            for (int r = 0; r < CKB; ++r) {
+                sw.step<true>(i0 + r, xb[r], yb[r]);
                 cpb[r] = sw.cp;
                 dpb[r] = sw.dp;
             }
+        } else {
+#pragma unroll
+            for (int r = 0; r < CKB; ++r)
+                if (r < nb) {
+                    sw.step<false>(i0 + r, xb[r], yb[r]);
+                    cpb[r] = sw.cp;
+                    dpb[r] = sw.dp;
+                }
+        }
         if (k == nblocks - 1) {
             // moment at the upper end of the window (knot hi = re + 1); the last block has >= 2 rows
             if (true_hi) {
@@ -239,7 +260,7 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
 #pragma unroll
         for (int r = CKB - 1; r >= 0; --r) {
             if (r < nb) {
-                const int64_t i = i0 + r;
+                const int i = i0 + r;
                 double2 M_i;
                 if (i == re) M_i = dpb[r];
                 else M_i = make_double2(dpb[r].x - cpb[r] * M_ip1.x, dpb[r].y - cpb[r] * M_ip1.y);
@@ -258,13 +279,13 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
                     } else if (MODE == 1) {
                         const double h6 = h * (1.0 / 6.0);
                         const double2 dl = make_double2((y_ip1.x - yi.x) * inv_h, (y_ip1.y - yi.y) * inv_h);
-                        out[i * G + g] = make_double2(dl.x - h6 * (2.0 * M_i.x + M_ip1.x), dl.y - h6 * (2.0 * M_i.y + M_ip1.y));
+                        out[(int64_t)i * G + g] = make_double2(dl.x - h6 * (2.0 * M_i.x + M_ip1.x), dl.y - h6 * (2.0 * M_i.y + M_ip1.y));
                         if (i == N - 2)
-                            out[(N - 1) * G + g] =
+                            out[(int64_t)(N - 1) * G + g] =
                                 make_double2(dl.x + h6 * (M_i.x + 2.0 * M_ip1.x), dl.y + h6 * (M_i.y + 2.0 * M_ip1.y));
                     } else {
-                        out[i * G + g] = M_i;
-                        if (i == N - 2) out[(N - 1) * G + g] = M_ip1;
+                        out[(int64_t)i * G + g] = M_i;
+                        if (i == N - 2) out[(int64_t)(N - 1) * G + g] = M_ip1;
                     }
                 }
                 M_ip2 = M_ip1;
@@ -298,15 +319,17 @@ spline_ckpt_kernel(const double* __restrict__ t, int64_t N, const double2* __res
             out[g] = M0;
         }
     }
+#undef SCRIB200_OIDX
 }
 
 static inline int checkpoints_per_chunk(int chunk) { return (chunk + 2 * HALO + 2 + CKB - 1) / CKB + 2; }
 
 template <int MODE>
 static int launch_spline(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
-                         const double* alpha, const double* uprm, int64_t n_out, double* out, int64_t out_ld, int chunk,
+                         const double* alpha, const double* uprm, int64_t n_out, double* out, int tshift, int chunk,
                          void* workspace, size_t workspace_bytes, void* stream, const char* name) {
     if (chunk <= 0) chunk = DEFAULT_CHUNK;
+    SCRIB200_REQUIRE(n_times < (int64_t)2147483000 && n_out < (int64_t)2147483000, "%s: series longer than 2^31 samples", name);
     const size_t need = scrib200_spline_remap_workspace_bytes(n_times, G, chunk);
     SCRIB200_REQUIRE(workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", name, workspace_bytes, need);
     const int64_t nchunks = (n_times - 1 + chunk - 1) / chunk;
@@ -319,8 +342,8 @@ static int launch_spline(const double* t, int64_t n_times, const double* F, int 
     double2* ws_d = reinterpret_cast<double2*>(ws_c + nc);
     dim3 grid((G + 63) / 64, (unsigned)nchunks);
     spline_ckpt_kernel<MODE><<<grid, 64, 0, (cudaStream_t)stream>>>(
-        t, n_times, reinterpret_cast<const double2*>(F), G, kconf, alpha, uprm, n_out, reinterpret_cast<double2*>(out),
-        out_ld, chunk, NCK, ws_c, ws_d);
+        t, (int)n_times, reinterpret_cast<const double2*>(F), G, kconf, alpha, uprm, (int)n_out,
+        reinterpret_cast<double2*>(out), tshift, chunk, NCK, ws_c, ws_d);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }
