@@ -32,7 +32,7 @@ def LLDominantEigenvector(W, RoughDirection=np.array([0.0, 0.0, 1.0]), RoughDire
     torch_data = ops.to_device(W.data, np.complex128)
     LL, _ = ops.ll_ldt(torch_data, None, W.ell_min, W.ell_max)
     dpa = ops.dominant_eigenvector(LL, ops.to_device(np.asarray(RoughDirection, dtype=float)), RoughDirectionIndex)
-    return dpa.cpu().numpy()
+    return ops.to_host(dpa)
 
 
 def angular_velocity(W, include_frame_velocity=False):
@@ -41,7 +41,7 @@ def angular_velocity(W, include_frame_velocity=False):
     t = ops.to_device(W.t, np.float64)
     ddot = ops.spline_calculus(t, d, "derivative", 1)
     LL, Ldt = ops.ll_ldt(d, ddot, W.ell_min, W.ell_max)
-    omega = ops.solve3(LL, Ldt, scale=-1.0).cpu().numpy()
+    omega = ops.to_host(ops.solve3(LL, Ldt, scale=-1.0))
     if include_frame_velocity and len(W.frame) == W.n_times:
         from scipy.interpolate import CubicSpline
 

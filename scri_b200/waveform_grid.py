@@ -99,8 +99,8 @@ class WaveformGrid(WaveformBase):
         a_d = ops.to_device(w_modes.data, np.complex128)
         uprm, grid = plan.run(t_d, a_d, return_grid=True, t_ends=(w_modes.t[0], w_modes.t[-1]))
         g = cls(
-            t=uprm.cpu().numpy(),
-            data=grid.cpu().numpy(),
+            t=ops.to_host(uprm),
+            data=ops.to_host(grid),
             history=w_modes.history,
             n_theta=plan.n_theta,
             n_phi=plan.n_phi,
@@ -135,8 +135,8 @@ class WaveformGrid(WaveformBase):
         if plan.leftover_kwargs:
             warnings.warn("\nUnused kwargs passed to this function:\n{}".format(pprint.pformat(plan.leftover_kwargs, width=1)))
         return WaveformModes(
-            t=uprm.cpu().numpy(),
-            data=modes.cpu().numpy(),
+            t=ops.to_host(uprm),
+            data=ops.to_host(modes),
             history=w_modes.history,
             ell_min=plan.out_ell_min,
             ell_max=plan.out_ell_max,
