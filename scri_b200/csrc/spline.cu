@@ -38,6 +38,22 @@ namespace scrib200 {
 constexpr int HALO = 64;
 constexpr int DEFAULT_CHUNK = 512;
 constexpr int CKB = 4;   // rows per checkpoint block
+constexpr int PFD = 1;          // blocks of rows in flight beyond the ones the current block needs
+constexpr int RING = 16;        // rows per thread in the shared-memory ring: (PFD + 2) blocks of CKB rows + 2 start rows
+constexpr int SPLINE_THREADS = 64;
+static_assert((PFD + 2) * CKB + 2 <= RING, "ring too small");
+
+// Each thread streams its own column of F through a private ring in shared memory with cp.async: rows are in
+// flight PFD blocks ahead without costing registers, and only cp.async.wait_group (no CTA barrier) orders them.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 struct Knots {
     const double* t;
@@ -65,11 +81,10 @@ struct Sweep {
     int N, rs, re;
     bool true_lo, true_hi;
 
-    __device__ __forceinline__ void start(const Knots& kn, const double2* Fg, int G, int i0, double cp0, double2 dp0) {
+    __device__ __forceinline__ void start(const Knots& kn, double2 y_im1, double2 y_i0, int i0, double cp0, double2 dp0) {
         const double x_im1 = kn.x(i0 - 1);
         x_i = kn.x(i0);
-        const double2 y_im1 = Fg[(int64_t)(i0 - 1) * G];
-        y_i = Fg[(int64_t)i0 * G];
+        y_i = y_i0;
         h_im1 = x_i - x_im1;
         dy_im1 = make_double2(y_i.x - y_im1.x, y_i.y - y_im1.y);
         cp = cp0;
@@ -118,8 +133,7 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
                    const double* __restrict__ kconf, const double* __restrict__ alpha, const double* __restrict__ up,
                    int Nout, double2* __restrict__ out, int tshift, int C, int NCK, double* __restrict__ ws_c,
                    double2* __restrict__ ws_d) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;   // threads with g >= G only help load s_t[], then leave
     // MODE 0 output layout: tshift == 0 -> time-major out[i'*G + g]; tshift = log2(T) > 0 -> time-tiled
     // out[(i'/T)*(G*T) + g*T + i'%T].  Tiling makes each thread's consecutive outputs contiguous (runs of T), so L2
     // merges them into full sectors (time-major 16-byte stores from lanes sitting at different i' never meet their
@@ -146,7 +160,15 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
         kmin = (j < first) ? 0 : 1 + (j - first) / CKB;
     }
 
-    Knots kn{t, kconf[g], alpha[g]};
+    // the window's sample times go to shared memory once: every x_i below is then an LDS, not an L2 round trip
+    extern __shared__ __align__(16) double2 s_ring[];                  // [RING][SPLINE_THREADS]
+    double* s_t = reinterpret_cast<double*>(s_ring + RING * SPLINE_THREADS);
+    for (int j = threadIdx.x; j <= hi - lo; j += blockDim.x) s_t[j] = t[lo + j];
+    __syncthreads();
+    if (g >= G) return;
+    Knots kn{s_t - lo, kconf[g], alpha[g]};
+    double2* my_ring = s_ring + threadIdx.x;
+#define RING_AT(row_) my_ring[((row_) & (RING - 1)) * SPLINE_THREADS]
     double* wc = ws_c + ((size_t)chunk * NCK) * G + g;       // checkpoint k -> wc[k*G]
     double2* wd = ws_d + ((size_t)chunk * NCK) * G + g;
     const double2* Fg = F + g;
@@ -154,33 +176,48 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
     Sweep sw;
     sw.N = N; sw.rs = rs; sw.re = re; sw.true_lo = true_lo; sw.true_hi = true_hi;
 
-    // ---------------- forward pass: only the checkpoints survive
-    sw.start(kn, Fg, G, rs, 0.0, make_double2(0.0, 0.0));
-    for (int k = 0; k + 1 < nblocks; ++k) {
-        const int i0 = (k == 0) ? rs : rs + first + (k - 1) * CKB;
-        const int nb = (k == 0) ? first : CKB;
-        double xb[CKB];
-        double2 yb[CKB];
-        const double2* prow = Fg + (int64_t)(i0 + 1) * G;
-#pragma unroll
-        for (int r = 0; r < CKB; ++r)
-            if (r < nb) {
-                yb[r] = prow[(int64_t)r * G];
-                xb[r] = kn.x(i0 + r + 1);
+    // block k covers rows blk_i0(k) .. blk_i0(k)+blk_nb(k)-1 and needs F rows up to blk_i0(k)+blk_nb(k)
+#define BLK_I0(k_) ((k_) == 0 ? rs : rs + first + ((k_) - 1) * CKB)
+#define BLK_NB(k_) ((k_) == 0 ? first : CKB)
+    // issue the cp.async copies of the F rows block k_ brings in: rows i0+1 .. i0+nb (plus lo, rs for block 0)
+    auto issue_block = [&](int kk) {
+        if (kk >= 0 && kk < nblocks) {
+            const int i0 = BLK_I0(kk), nb = BLK_NB(kk);
+            if (kk == 0) {
+                cp_async16(&RING_AT(lo), Fg + (int64_t)lo * G);
+                cp_async16(&RING_AT(rs), Fg + (int64_t)rs * G);
             }
+#pragma unroll
+            for (int r = 0; r < CKB; ++r)
+                if (r < nb) cp_async16(&RING_AT(i0 + r + 1), Fg + (int64_t)(i0 + r + 1) * G);
+        }
+        cp_async_commit();   // always commit, so the group count stays in step with the block count
+    };
+
+    // ---------------- forward pass: only the checkpoints survive
+#pragma unroll
+    for (int kk = 0; kk <= PFD; ++kk) issue_block(kk < nblocks - 1 ? kk : -1);
+    for (int k = 0; k + 1 < nblocks; ++k) {
+        const int i0 = BLK_I0(k);
+        const int nb = BLK_NB(k);
+        cp_async_wait<PFD>();                // everything up to block k has landed (PFD younger groups may be in flight)
+        if (k == 0) sw.start(kn, RING_AT(lo), RING_AT(rs), rs, 0.0, make_double2(0.0, 0.0));
         if (k > 0) {   // full block strictly inside the window (the last block is never processed here)
 #pragma unroll
-            for (int r = 0; r < CKB; ++r) sw.step<true>(i0 + r, xb[r], yb[r]);
+            for (int r = 0; r < CKB; ++r) sw.step<true>(i0 + r, kn.x(i0 + r + 1), RING_AT(i0 + r + 1));
         } else {
 #pragma unroll
             for (int r = 0; r < CKB; ++r)
-                if (r < nb) sw.step<false>(i0 + r, xb[r], yb[r]);
+                if (r < nb) sw.step<false>(i0 + r, kn.x(i0 + r + 1), RING_AT(i0 + r + 1));
         }
         if (k + 1 >= kmin) {
             wc[(size_t)(k + 1) * G] = sw.cp;
             wd[(size_t)(k + 1) * G] = sw.dp;
         }
+        // the slots of rows <= i0+nb are free now (row i0+nb lives on in sw.y_i): bring in block k+PFD+1
+        issue_block(k + PFD + 1 < nblocks - 1 ? k + PFD + 1 : -1);
     }
+    cp_async_wait<0>();
 
     // ---------------- output pointer: last output handled by this chunk
     int ip = -1;
@@ -196,37 +233,47 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
         }
         ip = lo_s - 1;
     }
+    // u_cur = up[ip], u_nxt = up[ip-1]: fetched two outputs ahead so the interval test never waits on memory
     double u_cur = (MODE == 0 && ip >= 0) ? up[ip] : -CUDART_INF;
+    double u_nxt = (MODE == 0 && ip >= 1) ? up[ip - 1] : -CUDART_INF;
 
     // ---------------- backward pass, block by block from the right
     double2 M_ip1 = make_double2(0.0, 0.0), M_ip2 = make_double2(0.0, 0.0);
     double x_ip1 = 0.0;
     double2 y_ip1 = make_double2(0.0, 0.0);
-    for (int k = nblocks - 1; k >= kmin; --k) {
-        const int i0 = (k == 0) ? rs : rs + first + (k - 1) * CKB;
-        const int nb = (k == 0) ? first : CKB;
-        double cp0 = 0.0;
-        double2 dp0 = make_double2(0.0, 0.0);
-        if (k > 0) {
-            cp0 = wc[(size_t)k * G];
-            dp0 = wd[(size_t)k * G];
-        }
-        double xb[CKB], cpb[CKB];
-        double2 yb[CKB], dpb[CKB];
-        const double2* prow = Fg + (int64_t)(i0 + 1) * G;
+    // block k needs its own rows and (for the two rows below i0) block k-1's: PFD + 2 groups go out first
 #pragma unroll
-        for (int r = 0; r < CKB; ++r)
-            if (r < nb) {
-                yb[r] = prow[(int64_t)r * G];
-                xb[r] = kn.x(i0 + r + 1);
-            }
-        sw.start(kn, Fg, G, i0, cp0, dp0);
+    for (int d = 0; d <= PFD + 1; ++d) issue_block(nblocks - 1 - d >= kmin - 1 ? nblocks - 1 - d : -1);
+    double cpn = 0.0;                              // checkpoint of the block being processed, fetched one block early
+    double2 dpn = make_double2(0.0, 0.0);
+    if (nblocks - 1 > 0) {
+        cpn = wc[(size_t)(nblocks - 1) * G];
+        dpn = wd[(size_t)(nblocks - 1) * G];
+    }
+    for (int k = nblocks - 1; k >= kmin; --k) {
+        const int i0 = BLK_I0(k);
+        const int nb = BLK_NB(k);
+        const double cp0 = cpn;
+        const double2 dp0 = dpn;
+        if (k - 1 >= kmin && k - 1 > 0) {
+            cpn = wc[(size_t)(k - 1) * G];
+            dpn = wd[(size_t)(k - 1) * G];
+        } else {
+            cpn = 0.0;
+            dpn = make_double2(0.0, 0.0);
+        }
+        cp_async_wait<PFD>();                      // blocks k and k-1 have landed
+        double cpb[CKB];
+        double2 dpb[CKB];
+#define XB(r_) kn.x(i0 + (r_) + 1)
+#define YB(r_) RING_AT(i0 + (r_) + 1)
+        sw.start(kn, RING_AT(i0 - 1), RING_AT(i0), i0, cp0, dp0);
         const double x_i0 = sw.x_i;
         const double2 y_i0 = sw.y_i;
         if (k > 0 && k < nblocks - 1) {
 #pragma unroll
             for (int r = 0; r < CKB; ++r) {
-                sw.step<true>(i0 + r, xb[r], yb[r]);
+                sw.step<true>(i0 + r, XB(r), YB(r));
                 cpb[r] = sw.cp;
                 dpb[r] = sw.dp;
             }
@@ -234,7 +281,7 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
 #pragma unroll
             for (int r = 0; r < CKB; ++r)
                 if (r < nb) {
-                    sw.step<false>(i0 + r, xb[r], yb[r]);
+                    sw.step<false>(i0 + r, XB(r), YB(r));
                     cpb[r] = sw.cp;
                     dpb[r] = sw.dp;
                 }
@@ -264,17 +311,17 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
                 double2 M_i;
                 if (i == re) M_i = dpb[r];
                 else M_i = make_double2(dpb[r].x - cpb[r] * M_ip1.x, dpb[r].y - cpb[r] * M_ip1.y);
-                const double xi = (r == 0) ? x_i0 : xb[r > 0 ? r - 1 : 0];
-                const double2 yi = (r == 0) ? y_i0 : yb[r > 0 ? r - 1 : 0];
+                const double xi = (r == 0) ? x_i0 : XB(r - 1);
+                const double2 yi = (r == 0) ? y_i0 : YB(r - 1);
                 if (i < b && i >= a) {
                     const double h = x_ip1 - xi;
                     const double inv_h = 1.0 / h;
                     if (MODE == 0) {
-                        // u_cur = up[ip] is fetched one output ahead, so the test below never waits on memory
                         while (u_cur >= xi) {
                             og[SCRIB200_OIDX(ip)] = eval_piece(u_cur, xi, x_ip1, h, inv_h, yi, y_ip1, M_i, M_ip1);
                             --ip;
-                            u_cur = (ip >= 0) ? up[ip] : -CUDART_INF;
+                            u_cur = u_nxt;
+                            u_nxt = (ip >= 1) ? up[ip - 1] : -CUDART_INF;
                         }
                     } else if (MODE == 1) {
                         const double h6 = h * (1.0 / 6.0);
@@ -294,7 +341,10 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
                 y_ip1 = yi;
             }
         }
+        // rows above i0 are dead now (block k-1 needs nothing above its own i0+nb = this i0): refill their slots
+        issue_block(k - 2 - PFD >= kmin - 1 ? k - 2 - PFD : -1);
     }
+    cp_async_wait<0>();
     // interval 0 (knots 0,1) when the window starts at the true left end
     if (true_lo && a == 0) {
         // here M_ip1 = M_1, M_ip2 = M_2, x_ip1 = x_1, y_ip1 = F[1]
@@ -309,7 +359,8 @@ spline_ckpt_kernel(const double* __restrict__ t, int N, const double2* __restric
             while (ip >= 0) {
                 og[SCRIB200_OIDX(ip)] = eval_piece(u_cur, x0, x1, h0, inv_h, y0, y_ip1, M0, M_ip1);
                 --ip;
-                u_cur = (ip >= 0) ? up[ip] : -CUDART_INF;
+                u_cur = u_nxt;
+                u_nxt = (ip >= 1) ? up[ip - 1] : -CUDART_INF;
             }
         } else if (MODE == 1) {
             const double h6 = h0 * (1.0 / 6.0);
@@ -341,7 +392,12 @@ static int launch_spline(const double* t, int64_t n_times, const double* F, int 
     nc = (nc + 1) & ~(size_t)1;   // keep the double2 part 16-byte aligned
     double2* ws_d = reinterpret_cast<double2*>(ws_c + nc);
     dim3 grid((G + 63) / 64, (unsigned)nchunks);
-    spline_ckpt_kernel<MODE><<<grid, 64, 0, (cudaStream_t)stream>>>(
+    // per-thread row ring + the window's sample times
+    const size_t smem = (size_t)RING * SPLINE_THREADS * sizeof(double2) + (size_t)(chunk + 2 * HALO + 2) * sizeof(double);
+    SCRIB200_REQUIRE(smem <= 200 * 1024, "%s: chunk=%d too large for the shared-memory time window", name, chunk);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(spline_ckpt_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spline_ckpt_kernel<MODE><<<grid, 64, smem, (cudaStream_t)stream>>>(
         t, (int)n_times, reinterpret_cast<const double2*>(F), G, kconf, alpha, uprm, (int)n_out,
         reinterpret_cast<double2*>(out), tshift, chunk, NCK, ws_c, ws_d);
     SCRIB200_CHECK_LAUNCH(name);
