@@ -66,23 +66,32 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
 
 /* ---------------------------------------------------------------------------------------------
  * BMS retarded-time remap: batched not-a-knot cubic-spline construction + evaluation.
- * Replaces  scri/waveform_grid.py:576-588 (two scipy InterpolatedUnivariateSpline builds per grid
- * point, evaluated at u'):  for each g: knots x_i = k[g]*(t[i]-alpha[g]), values F[i,g] (Re and Im),
+ * Replaces  scri/waveform_grid.py:564-588: the output time grid u' = (1/gamma)(t - time_translation) restricted
+ * to [max_g k(t_0-alpha), min_g k(t_{N-1}-alpha)], and two scipy InterpolatedUnivariateSpline builds per grid point
+ * evaluated at u':  for each g: knots x_i = k[g]*(t[i]-alpha[g]), values F[i,g] (Re and Im),
  * out[i', g] = spline_g(uprm[i']).
- *   t [n_times], F [n_times, G] complex128, kconf [G], alpha [G], uprm [n_out], out [n_out, G] complex128
- *   chunk: knots per thread-chunk (0 = default), workspace: scrib200_spline_remap_workspace_bytes()
+ *
+ * scrib200_spline_prepare (once per time axis): the knots of all grid points are affine images of t, so the
+ * tridiagonal moment system is factorised once, in t-units:
+ *   tab  [n_times, 4]  (P, Q, W, c') per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
+ *   uprm [n_times]     u'_i for every input sample (may be NULL together with kconf/alpha: tables only)
+ *   info [8] (device)  [0] lo, [1] hi: the retained block is uprm[lo:hi];  [2], [3]: worst decay of the spline
+ *                      recurrences over any 32 / 64 consecutive rows (choose halo = 32 if [2] <= 1e-15, else 64 if
+ *                      [3] <= 1e-15, else 128);  [4], [5]: u'min, u'max
+ *
+ * scrib200_spline_remap: t [n_times], F [n_times, G] complex128, kconf [G], alpha [G], uprm [n_out] increasing,
+ *   tile == 0: out [n_out, G] complex128 time-major;  tile = T (power of two >= 2): out written time-tiled,
+ *   out[(i'/T)*(G*T) + g*T + i'%T], buffer of ceil(n_out/T)*G*T elements - the layout scrib200_map2salm_tiled reads
+ *   (stores are contiguous runs of T samples, each analysis CTA reads one contiguous [G, T] tile).
+ *   halo / body: rows of run-in on each side of a tile / intervals per tile (0 = defaults 32 / 256).
+ *   No workspace: a CTA keeps its tile of F in shared memory; F is read once.
  */
-size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int chunk);
-int scrib200_bms_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
-                              const double* alpha, const double* uprm, int64_t n_out, double* out, int chunk,
-                              void* workspace, size_t workspace_bytes, void* stream);
-
-/* Same remap, output written time-tiled: out[(i'/T)*(G*T) + g*T + i'%T], T = tile (power of two), buffer of
- * ceil(n_out/T)*G*T elements: the layout the transform path hands to scrib200_map2salm_tiled (each thread's
- * consecutive outputs are contiguous in HBM, each analysis CTA reads one contiguous [G, T] tile). */
-int scrib200_bms_spline_remap_tiled(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
-                                    const double* alpha, const double* uprm, int64_t n_out, double* out, int tile,
-                                    int chunk, void* workspace, size_t workspace_bytes, void* stream);
+int scrib200_spline_prepare(const double* t, int64_t n_times, double inv_gamma, double time_translation,
+                            const double* kconf, const double* alpha, int G, double* tab, double* uprm, double* info,
+                            void* stream);
+int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
+                          const double* alpha, const double* tab, const double* uprm, int64_t n_out, double* out,
+                          int tile, int halo, int body, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWSH analysis, batched over time steps.
@@ -98,23 +107,23 @@ int scrib200_map2salm(const double* grid, int64_t n_times, int n_theta, int n_ph
                       const double* Wt, int ell_min, int ell_max, double* out, void* workspace,
                       size_t workspace_bytes, void* stream);
 
-/* Same analysis on a time-tiled grid (output of scrib200_bms_spline_remap_tiled with the same `tile`).
+/* Same analysis on a time-tiled grid (output of scrib200_spline_remap with the same `tile`).
  *   trig [n_phi, ell_max+1] complex128 = (cos, sin)(m phi_k)/n_phi  (scri_b200.plan: from the E table)
  * scrib200_map2salm_tile_size returns the tile to use (8, 4 or 2) or 0 when the tables do not fit one CTA;
- * callers then use the time-major pair scrib200_bms_spline_remap / scrib200_map2salm. */
+ * callers then use the time-major pair scrib200_spline_remap(tile=0) / scrib200_map2salm. */
 int scrib200_map2salm_tile_size(int n_theta, int n_phi, int ell_min, int ell_max);
 int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_times, int n_theta, int n_phi, const double* trig,
                             const double* Wt, int ell_min, int ell_max, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Time derivative of every mode through the not-a-knot cubic spline.
- * Replaces  scri/waveform_base.py:689-695  CubicSpline(t, data).derivative(order)(t)  (data_dot, data_ddot).
- *   data/out [n_times, ncol] complex128; ones/zeros: device arrays [ncol] of 1.0 / 0.0 (identity knot map);
- *   workspace: scrib200_spline_remap_workspace_bytes(n_times, ncol, chunk)
+ * Time calculus of every mode through the not-a-knot cubic spline.
+ * Replaces  scri/waveform_base.py:689-703  CubicSpline(t, data).derivative(k)(t)  (data_dot, data_ddot; order = 1, 2)
+ * and .antiderivative(k)(t) (data_int, data_iint; order = -1, -2: exact integrals of the piecewise cubic, zero at t[0]).
+ *   data/out [n_times, ncol] complex128; tab from scrib200_spline_prepare(t); halo/body as in scrib200_spline_remap;
+ *   aux [n_times, ncol] complex128: needed for order -2 only (receives the first antiderivative), else may be NULL.
  */
-int scrib200_spline_derivative(const double* t, int64_t n_times, const double* data, int ncol, const double* ones,
-                               const double* zeros, int order, double* out, int chunk, void* workspace,
-                               size_t workspace_bytes, void* stream);
+int scrib200_spline_calculus(const double* t, int64_t n_times, const double* data, int ncol, const double* tab,
+                             int order, double* out, double* aux, int halo, int body, void* stream);
 
 /* sum_modes |a|^2 per time step.  Replaces scri/waveform_base.py:19-35 complex_array_norm. */
 int scrib200_norm(const double* data, int64_t n_times, int n_modes, double* out, void* stream);

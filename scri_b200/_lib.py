@@ -23,19 +23,15 @@ SIGNATURES = {
     "scrib200_launch_count": (c_i64, []),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
-    "scrib200_spline_remap_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
-    "scrib200_bms_spline_remap": (
+    "scrib200_spline_prepare": (c_int, [c_vp, c_i64, ctypes.c_double, ctypes.c_double, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "scrib200_spline_remap": (
         c_int,
-        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_sz, c_vp],
-    ),
-    "scrib200_bms_spline_remap_tiled": (
-        c_int,
-        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_sz, c_vp],
+        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp],
     ),
     "scrib200_map2salm_tile_size": (c_int, [c_int, c_int, c_int, c_int]),
     "scrib200_map2salm_tiled": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "scrib200_map2salm_workspace_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
-    "scrib200_spline_derivative": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "scrib200_spline_calculus": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     "scrib200_norm": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "scrib200_ll_ldt": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_l_vector": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),

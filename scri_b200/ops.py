@@ -158,11 +158,29 @@ def _ones_zeros(n):
     return _table_cache[key]
 
 
-def spline_calculus(t, data, kind, order=1, tprime=None):
-    """Not-a-knot cubic spline along time of every (complex) column: derivative at the knots, or evaluation.
+def spline_tables(tt):
+    """(tab [N, 4], halo) for the time axis `tt` (device tensor): the shared Thomas factorisation of the not-a-knot
+    moment system and the run-in length its decay calls for (scrib200_spline_prepare)."""
+    lib = _lib.load()
+    torch = _torch()
+    N = tt.shape[0]
+    tab = torch.empty((N, 4), dtype=torch.float64, device="cuda")
+    info = torch.empty(8, dtype=torch.float64, device="cuda")
+    _lib.check(
+        lib.scrib200_spline_prepare(_lib.ptr(tt), N, 1.0, 0.0, None, None, 0, _lib.ptr(tab), None, _lib.ptr(info), _lib.stream_ptr()),
+        "spline_prepare",
+    )
+    v = info.tolist()
+    halo = 32 if v[2] <= 1e-15 else (64 if v[3] <= 1e-15 else 128)
+    return tab, halo
 
-    Replaces CubicSpline(t, data).derivative(k)(t) (scri/waveform_base.py:689-695) and
-    CubicSpline(t, data)(tprime) (:964).  The antiderivatives (:697-703) are not on the GPU path yet.
+
+def spline_calculus(t, data, kind, order=1, tprime=None):
+    """Not-a-knot cubic spline along time of every (complex) column: derivative / antiderivative at the knots, or
+    evaluation at `tprime`.
+
+    Replaces CubicSpline(t, data).derivative(k)(t) (scri/waveform_base.py:689-695), .antiderivative(k)(t) (:697-703)
+    and CubicSpline(t, data)(tprime) (:964).
     """
     lib = _lib.load()
     torch = _torch()
@@ -171,24 +189,27 @@ def spline_calculus(t, data, kind, order=1, tprime=None):
     N = d.shape[0]
     d2 = d.reshape(N, -1)
     ncol = d2.shape[1]
-    ones, zeros = _ones_zeros(ncol)
-    need = lib.scrib200_spline_remap_workspace_bytes(N, ncol, 0)
-    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
-    if kind == "derivative":
+    tab, halo = spline_tables(tt)
+    if kind in ("derivative", "antiderivative"):
+        if kind == "derivative" and order not in (1, 2) or kind == "antiderivative" and order not in (1, 2):
+            raise ValueError(f"spline_calculus: order={order} is not supported for kind={kind!r}")
+        code = int(order) if kind == "derivative" else -int(order)
         out = torch.empty_like(d2)
+        aux = torch.empty_like(d2) if code == -2 else None
         _lib.check(
-            lib.scrib200_spline_derivative(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), int(order),
-                                           _lib.ptr(out), 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-            "spline_derivative",
+            lib.scrib200_spline_calculus(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(tab), code, _lib.ptr(out),
+                                         _lib.ptr(aux) if aux is not None else None, halo, 0, _lib.stream_ptr()),
+            "spline_calculus",
         )
         out = out.reshape(d.shape)
     elif kind == "evaluate":
         tp = to_device(tprime, np.float64)
+        ones, zeros = _ones_zeros(ncol)
         out = torch.empty((tp.shape[0], ncol), dtype=torch.complex128, device="cuda")
         _lib.check(
-            lib.scrib200_bms_spline_remap(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), _lib.ptr(tp),
-                                          tp.shape[0], _lib.ptr(out), 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-            "bms_spline_remap",
+            lib.scrib200_spline_remap(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), _lib.ptr(tab),
+                                      _lib.ptr(tp), tp.shape[0], _lib.ptr(out), 0, halo, 0, _lib.stream_ptr()),
+            "spline_remap",
         )
         out = out.reshape((tp.shape[0],) + tuple(d.shape[1:]))
     else:

@@ -286,9 +286,18 @@ class TransformPlan:
         Lo = self.out_ell_max
         trig = np.ascontiguousarray(np.conj(E[:, Lo:]))
         self.d_trig = torch.from_numpy(trig).to(dev)
-        self._ws = None
         self._tile = None
-        self.spline_chunk = 0
+        self._side = None
+        self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
+        self.spline_body = 0   # 0 = default intervals per tile
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = self.torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _info_host(self):
+        return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
     # -- the individual stages (device tensors in, device tensors out) ---------------------------
     def synthesize(self, data):
@@ -306,64 +315,48 @@ class TransformPlan:
         )
         return F
 
-    def output_times(self, t, t_ends=None):
-        """u'_i and the retained block (waveform_grid.py:564-568).  `t` is a device tensor; `t_ends` = (t[0], t[-1])
-        on the host saves one device read."""
-        torch = self.torch
-        uprm = (1 / self.gamma) * (t - self.time_translation)
-        if t_ends is None:
-            ends = t[[0, -1]].cpu()
-            t_ends = (float(ends[0]), float(ends[1]))
-        uprm_min = (self.kconformal * (t_ends[0] - self.alpha)).max()
-        uprm_max = (self.kconformal * (t_ends[1] - self.alpha)).min()
-        # u' is increasing, so the retained samples (uprm_min <= u' <= uprm_max) are one contiguous block
-        bounds = torch.tensor([uprm_min, uprm_max], dtype=torch.float64, device=self.device)
-        lo = torch.searchsorted(uprm, bounds[:1], right=False)
-        hi = torch.searchsorted(uprm, bounds[1:], right=True)
-        lo_hi = torch.cat([lo, hi]).cpu()
-        return uprm[int(lo_hi[0]) : int(lo_hi[1])]
+    def prepare(self, t):
+        """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
+        the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`."""
+        return TimePrep(self, t)
 
-    def remap(self, t, F, uprm):
-        """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588)."""
+    def output_times(self, t, t_ends=None):
+        """u'_i and the retained block (waveform_grid.py:564-568) as a device tensor.  `t_ends` is accepted for
+        backward compatibility and ignored (the block is found on the device)."""
+        return self.prepare(t).uprm
+
+    def _remap(self, t, F, uprm, prep, tile):
         torch = self.torch
         lib = _lib.load()
+        if prep is None:
+            prep = self.prepare(t)
         N, n_out = t.shape[0], uprm.shape[0]
-        out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
-        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, self.spline_chunk)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if tile:
+            out = torch.empty((-(-n_out // tile), self.G, tile), dtype=torch.complex128, device=self.device)
+        else:
+            out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
+        halo, body = prep.halo_body(self.spline_halo, self.spline_body)
         _lib.check(
-            lib.scrib200_bms_spline_remap(
-                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(uprm), n_out,
-                _lib.ptr(out), self.spline_chunk, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr(),
+            lib.scrib200_spline_remap(
+                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
+                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.stream_ptr(),
             ),
-            "bms_spline_remap",
+            "spline_remap",
         )
         return out
+
+    def remap(self, t, F, uprm, prep=None):
+        """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588); [N', G]."""
+        return self._remap(t, F, uprm, prep, 0)
 
     def analyze(self, grid):
         """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307)."""
         return map2salm(grid, self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max, self.d_E, self.d_Wt)
 
-    # -- g-major variants: the layout the fused transform path uses between remap and analysis ----
-    def remap_tiled(self, t, F, uprm):
+    # -- time-tiled variants: the layout the fused transform path uses between remap and analysis ----
+    def remap_tiled(self, t, F, uprm, prep=None):
         """Same spline remap, result stored time-tiled: [ceil(N'/T), G, T] (T = self.tile)."""
-        torch = self.torch
-        lib = _lib.load()
-        N, n_out = t.shape[0], uprm.shape[0]
-        T = self.tile
-        out = torch.empty((-(-n_out // T), self.G, T), dtype=torch.complex128, device=self.device)
-        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, self.spline_chunk)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        _lib.check(
-            lib.scrib200_bms_spline_remap_tiled(
-                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(uprm), n_out,
-                _lib.ptr(out), T, self.spline_chunk, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr(),
-            ),
-            "bms_spline_remap_tiled",
-        )
-        return out
+        return self._remap(t, F, uprm, prep, self.tile)
 
     def analyze_tiled(self, gridT, n_out):
         """gridT [ceil(N'/T), G, T] complex128 (time-tiled) -> [n_out, n_modes_out]."""
@@ -386,19 +379,79 @@ class TransformPlan:
             self._tile = int(_lib.load().scrib200_map2salm_tile_size(self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max))
         return self._tile
 
-    def run(self, t, data, return_grid=False, t_ends=None):
-        """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major])."""
+    def run(self, t, data, return_grid=False, t_ends=None, prep=None):
+        """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
+
+        The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
+        stream while the synthesis kernel runs.  `prep` (from `prepare(t)`) can be reused for waveforms that share
+        their time axis."""
+        if prep is None:
+            prep = self.prepare(t)
         F = self.synthesize(data)
-        uprm = self.output_times(t, t_ends)
+        uprm = prep.uprm
         if self.tile and not return_grid:
-            gridT = self.remap_tiled(t, F, uprm)
+            gridT = self.remap_tiled(t, F, uprm, prep)
             del F
             return uprm, self.analyze_tiled(gridT, uprm.shape[0])
-        grid = self.remap(t, F, uprm)
+        grid = self.remap(t, F, uprm, prep)
         del F
         if return_grid:
             return uprm, grid
         return uprm, self.analyze(grid)
+
+
+class TimePrep:
+    """Device-side products of scrib200_spline_prepare for one (plan, time axis): `tab`, `uprm_full`, `info`.
+
+    `resolve()` waits for the 64-byte read-back and returns (lo, hi); `uprm` is the retained block u'[lo:hi]
+    (scri/waveform_grid.py:564-568)."""
+
+    def __init__(self, plan, t):
+        torch = plan.torch
+        lib = _lib.load()
+        N = t.shape[0]
+        self.N = N
+        self.tab = torch.empty((N, 4), dtype=torch.float64, device=plan.device)
+        self.uprm_full = torch.empty(N, dtype=torch.float64, device=plan.device)
+        self.info = torch.empty(8, dtype=torch.float64, device=plan.device)
+        _lib.check(
+            lib.scrib200_spline_prepare(
+                _lib.ptr(t), N, 1 / plan.gamma, plan.time_translation, _lib.ptr(plan.d_k), _lib.ptr(plan.d_alpha), plan.G,
+                _lib.ptr(self.tab), _lib.ptr(self.uprm_full), _lib.ptr(self.info), _lib.stream_ptr(),
+            ),
+            "spline_prepare",
+        )
+        # read `info` back on a side stream so that kernels launched meanwhile on the caller's stream are not waited for
+        self._host = plan._info_host()
+        cur = torch.cuda.current_stream()
+        side = plan._side_stream()
+        self._ready = torch.cuda.Event()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._host.copy_(self.info, non_blocking=True)
+            self._ready.record(side)
+        self.info.record_stream(side)
+        self._resolved = None
+
+    def resolve(self):
+        if self._resolved is None:
+            self._ready.synchronize()
+            v = self._host.tolist()
+            self._resolved = (int(v[0]), max(int(v[0]), int(v[1])), float(v[2]), float(v[3]))
+        return self._resolved[:2]
+
+    @property
+    def uprm(self):
+        lo, hi = self.resolve()
+        return self.uprm_full[lo:hi]
+
+    def halo_body(self, halo=0, body=0):
+        """Rows of run-in per tile side from the measured decay of the recurrences (0.268^k on uniform samples)."""
+        self.resolve()
+        if not halo:
+            d32, d64 = self._resolved[2:]
+            halo = 32 if d32 <= 1e-15 else (64 if d64 <= 1e-15 else 128)
+        return int(halo), int(body)
 
 
 def map2salm(grid, n_theta, n_phi, ell_min, ell_max, d_E, d_Wt):

@@ -49,7 +49,7 @@ m_g2 = ops.map2salm(g_o.data.reshape(-1, g_o.n_theta, g_o.n_phi), -2, 8)[:, 4:]
 print("analysis(alone) rel err", rel(m_g2, m_o.data))
 
 # small chunk to exercise halos
-pl.spline_chunk = 100
+pl.spline_body = 100
 grid2 = pl.remap(td, F, up)
 print("remap chunk=100 rel err", rel(grid2.cpu().numpy(), g_o.data), "vs chunk default", rel(grid2.cpu().numpy(), grid.cpu().numpy()))
 
@@ -92,7 +92,7 @@ for it in range(3):
     torch.cuda.synchronize(); t0 = time.time()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record(); F = pl.synthesize(ad); ev[1].record(); up = pl.output_times(td); ev[2].record()
-    pl.spline_chunk = 0
+    pl.spline_body = 0
     grid = pl.remap(td, F, up); ev[3].record(); m = pl.analyze(grid); ev[4].record()
     torch.cuda.synchronize()
     print("N=1e5: synth %.3f ms, times %.3f ms, remap %.3f ms, analysis %.3f ms, wall %.3f ms" % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4]), (time.time() - t0) * 1e3))

@@ -104,9 +104,10 @@ def test_transform_stage_by_stage_vs_oracle():
     assert np.array_equal(up.cpu().numpy(), g_o.t)           # output time grid: bit-exact
     grid = pl.remap(td, F, up)
     assert rel(grid.cpu().numpy(), g_o.data) < 1e-13
-    for chunk in (50, 100, 333):                               # halo logic: every chunking gives the same spline
-        pl.spline_chunk = chunk
+    for body, halo in ((50, 32), (100, 64), (333, 32), (16, 128)):   # tiling logic: every tiling gives the same spline
+        pl.spline_body, pl.spline_halo = body, halo
         assert rel(pl.remap(td, F, up).cpu().numpy(), g_o.data) < 1e-13
+    pl.spline_body = pl.spline_halo = 0
     m_o = R.to_modes(g_o, 8)
     assert rel(pl.analyze(grid).cpu().numpy(), m_o.data) < 1e-13
     # analysis alone on the oracle's grid, all modes from ell=0 as spinsfast returns them
@@ -214,7 +215,7 @@ def test_edge_cases():
 # ------------------------------------------------------------------ full-size properties (config 2)
 def test_full_size_transform_inverse_round_trip():
     """1e5 time steps, l<=8: transform with (supertranslation+boost+rotation) then with the inverse rotation/
-    time structure checked through invariants the domain offers: (i) chunked == unchunked spline,
+    time structure checked through invariants the domain offers: (i) the spline does not depend on the tiling,
     (ii) a pure rotation through the BMS path equals the Wigner-D path, (iii) oracle parity on a window."""
     N = 100_000
     t = np.linspace(0.0, 1e4, N)
@@ -223,7 +224,7 @@ def test_full_size_transform_inverse_round_trip():
     td, ad = ops.to_device(t), ops.to_device(data)
     up, out = pl.run(td, ad)
     pl2 = P.TransformPlan(2, 8, sb.h, **BMS)
-    pl2.spline_chunk = 4096
+    pl2.spline_body, pl2.spline_halo = 160, 64
     up2, out2 = pl2.run(td, ad)
     assert np.array_equal(up.cpu().numpy(), up2.cpu().numpy())
     assert rel(out.cpu().numpy(), out2.cpu().numpy()) < 1e-14
@@ -274,10 +275,33 @@ def test_spline_calculus_vs_scipy():
             assert rel(ops.spline_calculus(t, data, "derivative", 2), CubicSpline(t, data).derivative(2)(t)) < 1e-10
         tp = np.linspace(t[0], t[-1], 1234)
         assert rel(ops.spline_calculus(t, data, "evaluate", tprime=tp), CubicSpline(t, data)(tp)) < 1e-13
+        # antiderivatives (scri/waveform_base.py:697-703): exact integrals of the piecewise cubic, zero at t[0]
+        assert rel(ops.spline_calculus(t, data, "antiderivative", 1), CubicSpline(t, data).antiderivative(1)(t)) < 1e-13
+        assert rel(ops.spline_calculus(t, data, "antiderivative", 2), CubicSpline(t, data).antiderivative(2)(t)) < 1e-13
     # linear data is reproduced exactly (reference tests/test_waveform.py:183-270)
     t = np.linspace(-10.0, 100.0, 1000)
     lin = (np.arange(77) - 1j * np.arange(77))[None, :] * t[:, None]
     assert np.allclose(ops.spline_calculus(t, lin, "evaluate", tprime=t[5:-5] + 0.01), (np.arange(77) - 1j * np.arange(77))[None, :] * (t[5:-5] + 0.01)[:, None], rtol=1e-14)
+
+
+def test_spline_strongly_nonuniform_steps():
+    """Geometrically shrinking / growing steps slow the decay of the spline recurrences (up to 2/3 per row instead of
+    0.27): scrib200_spline_prepare measures it and the tiles take a longer run-in.  Also the shortest series."""
+    from scipy.interpolate import CubicSpline
+
+    rng = np.random.default_rng(5)
+    h = np.concatenate([0.1 * 0.9 ** np.arange(150), 0.1 * 0.9 ** 150 * 1.1 ** np.arange(200), np.full(300, 0.05) * rng.uniform(0.2, 1.8, 300)])
+    t = np.concatenate([[0.0], np.cumsum(h)])
+    data = np.exp(1j * np.outer(t, np.linspace(0.3, 2.0, 9))) * (1.0 + 0.1 * t[:, None])
+    tp = np.sort(rng.uniform(t[0], t[-1], 3000))
+    assert rel(ops.spline_calculus(t, data, "evaluate", tprime=tp), CubicSpline(t, data)(tp)) < 1e-13
+    assert rel(ops.spline_calculus(t, data, "derivative", 1), CubicSpline(t, data).derivative()(t)) < 1e-12
+    for n in (4, 5, 6, 17):
+        tn = np.sort(rng.uniform(0.0, 1.0, n))
+        dn = rng.normal(size=(n, 3)) + 1j * rng.normal(size=(n, 3))
+        tpn = np.linspace(tn[0], tn[-1], 50)
+        assert rel(ops.spline_calculus(tn, dn, "evaluate", tprime=tpn), CubicSpline(tn, dn)(tpn)) < 1e-12
+        assert rel(ops.spline_calculus(tn, dn, "derivative", 1), CubicSpline(tn, dn).derivative()(tn)) < 1e-11
 
 
 def test_dominant_eigenvector_and_angular_velocity_physics():
