@@ -73,7 +73,7 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *
  * scrib200_spline_prepare (once per time axis): the knots of all grid points are affine images of t, so the
  * tridiagonal moment system is factorised once, in t-units:
- *   tab  [n_times, 4]  (P, Q, W, c') per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
+ *   tab  [n_times, 8]  (P, Q, W, 1/h, Phi, c', Psi, h) per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
  *   uprm [n_times]     u'_i for every input sample (may be NULL together with kconf/alpha: tables only)
  *   info [8] (device)  [0] lo, [1] hi: the retained block is uprm[lo:hi];  [2], [3]: worst decay of the spline
  *                      recurrences over any 32 / 64 consecutive rows (choose halo = 32 if [2] <= 1e-15, else 64 if
@@ -83,15 +83,18 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *   tile == 0: out [n_out, G] complex128 time-major;  tile = T (power of two >= 2): out written time-tiled,
  *   out[(i'/T)*(G*T) + g*T + i'%T], buffer of ceil(n_out/T)*G*T elements - the layout scrib200_map2salm_tiled reads
  *   (stores are contiguous runs of T samples, each analysis CTA reads one contiguous [G, T] tile).
- *   halo / body: rows of run-in on each side of a tile / intervals per tile (0 = defaults 32 / 256).
- *   No workspace: a CTA keeps its tile of F in shared memory; F is read once.
+ *   halo / body: rows of run-in on each side of a tile / intervals per tile, multiples of 16, body + 2 halo <= 384
+ *   (0 = defaults 32 / 224).
+ *   workspace: scrib200_spline_remap_workspace_bytes() - one int per (tile, grid point): the first output of each
+ *   tile.  A CTA keeps its tile of F in shared memory; F is read once.
  */
+size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int halo, int body);
 int scrib200_spline_prepare(const double* t, int64_t n_times, double inv_gamma, double time_translation,
                             const double* kconf, const double* alpha, int G, double* tab, double* uprm, double* info,
                             void* stream);
 int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
                           const double* alpha, const double* tab, const double* uprm, int64_t n_out, double* out,
-                          int tile, int halo, int body, void* stream);
+                          int tile, int halo, int body, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWSH analysis, batched over time steps.

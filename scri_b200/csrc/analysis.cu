@@ -11,6 +11,8 @@
 // and both tables in shared memory, does the DFT into shared memory, then the theta contraction, and
 // writes [T, n_modes] coalesced.  The grid is read from HBM exactly once.
 // Fallback for grids too large for shared memory: two passes through a workspace.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace scrib200 {
@@ -222,6 +224,167 @@ map2salm_tiled_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_
     }
 }
 
+// ---- DMMA variant of the tiled kernel (time tile T = 8).  For one theta ring j the phi-DFT of all 8 time steps is
+// the real GEMM   P[(part, t), n] = sum_k  part(f[j, k, t]) * B[k, n],   B = (cos(m phi_k), sin(m phi_k))/n_phi, m = 1..L,
+// i.e. M = 2 x 8 (Re / Im part x time), K = n_phi, N = 2 x 8 NT: FP64 tensor-core tiles m8n8k4 (SASS DMMA.8x8x4).  The
+// A fragment of BOTH M tiles is one 16-byte shared-memory load straight from the [G][8] tile the spline kernel wrote
+// (lane (t, kk) reads the complex sample (j, k0+kk, t): 512 contiguous-ish bytes per warp, the 4-wavefront minimum).
+// The four real products of a +-m pair share the fragments (see map2salm_tiled_kernel); m = 0 is the plain ring sum,
+// taken from the A fragments.  A warp owns up to two rings and keeps their accumulators in registers until every warp
+// has finished reading the tile, so f_m(theta_j) can overwrite it; the theta quadrature then runs as before.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(640)
+map2salm_dmma_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_theta, int n_phi,
+                     const double2* __restrict__ trig, const double* __restrict__ Wt, int ell_min, int ell_max,
+                     double2* __restrict__ out) {
+    constexpr int T = 8;
+    constexpr int BP = 16 * NT + 8;                        // pitch of the B table (doubles): 2-way banks = the minimum
+    extern __shared__ __align__(128) double2 smd[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int L = ell_max, nm = 2 * L + 1, np1 = L + 1;
+    const int G = n_theta * n_phi;
+    const int KS = (n_phi + 3) / 4;
+    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    double2* sTile = smd;                                  // [G + 4][T]  (4 zeroed pad rows: the K padding of the last ring)
+    double2* sFm = sTile;                                  // [T][nm][n_theta] after the barrier
+    double* sB = reinterpret_cast<double*>(sTile + (size_t)(G + 4) * T);   // [4 KS][BP]
+    double* sW = sB + (size_t)4 * KS * BP;                 // [n_modes][n_theta]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * T;
+    const size_t tile_elems = (size_t)G * T;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned total = (unsigned)(tile_elems * sizeof(double2));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+        const char* src = reinterpret_cast<const char*>(gridT + (int64_t)blockIdx.x * tile_elems);
+        char* dst = reinterpret_cast<char*>(sTile);
+        for (unsigned off = 0; off < total; off += 32768u) {
+            const unsigned n = (total - off < 32768u) ? (total - off) : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(dst + off)),
+                         "l"(src + off), "r"(n), "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+    }
+    for (int i = tid; i < 4 * T; i += nt) sTile[tile_elems + i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < 4 * KS * BP; i += nt) {
+        const int k = i / BP, n = i - k * BP;
+        double v = 0.0;
+        if (k < n_phi && n < 16 * NT) {
+            const int m = (n % (8 * NT)) + 1;
+            if (m <= L) {
+                const double2 cs = trig[k * np1 + m];
+                v = (n < 8 * NT) ? cs.x : cs.y;
+            }
+        }
+        sB[i] = v;
+    }
+    for (int i = tid; i < n_modes * n_theta; i += nt) sW[i] = Wt[i];
+    __syncthreads();   // tables visible; mbarrier initialised before anyone polls it
+    {
+        unsigned ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok)
+                         : "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+    }
+
+    // ---- phi-DFT on the tensor cores: rings warp, warp + nwarp
+    const int tq = lane >> 2, kk = lane & 3;               // fragment coordinates: row / column t (or n), K index kk
+    double acc[2][2][2 * NT][2];                           // [ring][Re/Im part][N tile][2]
+    double s0[2][2];
+    const double inv_nphi = trig[0].x;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        s0[r][0] = s0[r][1] = 0.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int n = 0; n < 2 * NT; ++n) acc[r][p][n][0] = acc[r][p][n][1] = 0.0;
+        const int j = warp + r * nwarp;
+        if (j < n_theta) {
+            const double2* arow = sTile + ((size_t)j * n_phi + kk) * T + tq;
+            const double* brow = sB + kk * BP + tq;
+#pragma unroll 2
+            for (int ks = 0; ks < KS; ++ks) {
+                const double2 a = arow[(size_t)ks * 4 * T];
+                if (4 * ks + kk < n_phi) {
+                    s0[r][0] += a.x;
+                    s0[r][1] += a.y;
+                }
+#pragma unroll
+                for (int n = 0; n < 2 * NT; ++n) {
+                    const double b = brow[ks * 4 * BP + n * 8];
+                    dmma884(acc[r][0][n][0], acc[r][0][n][1], a.x, b);
+                    dmma884(acc[r][1][n][0], acc[r][1][n][1], a.y, b);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                s0[r][p] += __shfl_xor_sync(0xffffffffu, s0[r][p], 1);
+                s0[r][p] += __shfl_xor_sync(0xffffffffu, s0[r][p], 2);
+            }
+        }
+    }
+    __syncthreads();   // every warp is done reading the tile: f_m(theta_j) may overwrite it
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = warp + r * nwarp;
+        if (j < n_theta) {
+            double2* frow = sFm + (size_t)tq * nm * n_theta + j;       // + mi * n_theta
+            if (kk == 0) frow[(size_t)L * n_theta] = make_double2(s0[r][0] * inv_nphi, s0[r][1] * inv_nphi);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int m = n * 8 + 2 * kk + i + 1;
+                    if (m <= L) {
+                        const double P1 = acc[r][0][n][i], P4 = acc[r][0][NT + n][i];
+                        const double P3 = acc[r][1][n][i], P2 = acc[r][1][NT + n][i];
+                        frow[(size_t)(L + m) * n_theta] = make_double2(P1 + P2, P3 - P4);
+                        frow[(size_t)(L - m) * n_theta] = make_double2(P1 - P2, P3 + P4);
+                    }
+                }
+        }
+    }
+    __syncthreads();
+
+    // ---- theta quadrature: (t, lm)
+    const int Tv = (int)((n_times - t0 < T) ? (n_times - t0) : T);
+    for (int idx = tid; idx < Tv * n_modes; idx += nt) {
+        const int t2 = idx / n_modes;
+        const int lm = idx - t2 * n_modes;
+        int ell, m;
+        lm_from_index(lm, ell_min, ell, m);
+        const double2* fm = sFm + ((size_t)t2 * nm + (m + L)) * n_theta;
+        const double* w = sW + lm * n_theta;
+        double2 acc2 = make_double2(0.0, 0.0);
+        for (int jj = 0; jj < n_theta; ++jj) {
+            const double2 v = fm[jj];
+            acc2.x = fma(w[jj], v.x, acc2.x);
+            acc2.y = fma(w[jj], v.y, acc2.y);
+        }
+        out[(t0 + t2) * n_modes + lm] = acc2;
+    }
+}
+
+static size_t dmma_smem(int n_theta, int n_phi, int ell_min, int ell_max, int NT) {
+    const size_t n_modes = (size_t)ell_max * (ell_max + 2) - (size_t)ell_min * ell_min + 1;
+    const size_t KS = (n_phi + 3) / 4;
+    return ((size_t)n_theta * n_phi + 4) * 8 * sizeof(double2) + (4 * KS * (16 * NT + 8) + n_modes * n_theta) * sizeof(double);
+}
+
 constexpr int TILED_NP = 9;
 
 static size_t gmajor_smem(int T, int n_theta, int n_phi, int ell_min, int ell_max) {
@@ -307,6 +470,30 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
     SCRIB200_REQUIRE(aligned16(gridT) && aligned16(trig) && aligned16(out), "map2salm_tiled: pointers must be 16-byte aligned");
     if (n_times <= 0) return SCRIB200_OK;
     const int T = tile;
+    {
+        // tensor-core path: time tile 8, up to two rings per warp, m = 1..ell_max in NT blocks of 8
+        const int NT = (ell_max + 7) / 8;
+        const int nwarp = (n_theta + 1) / 2;
+        const size_t smem_d = dmma_smem(n_theta, n_phi, ell_min, ell_max, NT);
+        const bool disabled = getenv("SCRIB200_ANALYSIS_SCALAR") != nullptr;
+        if (!disabled && T == 8 && ell_max >= 1 && NT <= 2 && nwarp <= 20 && 2 * ell_max + 1 <= n_phi && smem_d <= 200 * 1024) {
+            const int64_t blocks = (n_times + T - 1) / T;
+            const int threads = 32 * (nwarp < 4 ? 4 : nwarp);
+            if (NT == 1) {
+                cudaFuncSetAttribute(map2salm_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+                map2salm_dmma_kernel<1><<<(unsigned)blocks, threads, smem_d, (cudaStream_t)stream>>>(
+                    reinterpret_cast<const double2*>(gridT), n_times, n_theta, n_phi, reinterpret_cast<const double2*>(trig), Wt,
+                    ell_min, ell_max, reinterpret_cast<double2*>(out));
+            } else {
+                cudaFuncSetAttribute(map2salm_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+                map2salm_dmma_kernel<2><<<(unsigned)blocks, threads, smem_d, (cudaStream_t)stream>>>(
+                    reinterpret_cast<const double2*>(gridT), n_times, n_theta, n_phi, reinterpret_cast<const double2*>(trig), Wt,
+                    ell_min, ell_max, reinterpret_cast<double2*>(out));
+            }
+            SCRIB200_CHECK_LAUNCH("map2salm_tiled(dmma)");
+            return SCRIB200_OK;
+        }
+    }
     const size_t smem = gmajor_smem(T, n_theta, n_phi, ell_min, ell_max);
     SCRIB200_REQUIRE(T >= 2 && T * n_theta <= 256 && smem <= 200 * 1024,
                      "map2salm_tiled: tile %d with grid %d x %d, ell_max=%d does not fit one CTA (use scrib200_map2salm)", T,

@@ -4,26 +4,29 @@
 // x_i = k[g] (t[i] - alpha[g]), evaluated at the common output times u') and scri/waveform_base.py:689-703
 // (CubicSpline(t, data).derivative(k)(t), .antiderivative(k)(t)).
 //
-// Two observations shape the kernel:
+// Three observations shape the kernel:
 //  1. The knots of every grid point are an affine image of the same sample times t, and the interpolating cubic
 //     spline is affine-invariant.  In t-units the moment system  T(t) M = 6 [y_{i-1}, y_i, y_{i+1}]  has ONE matrix
-//     for all columns, so its Thomas factorisation is done once (`spline_factor_kernel`, one thread per row, the
-//     c' recurrence contracts by <= 1/12 per row so 24 rows of run-in reproduce it to rounding) and stored as a
-//     table of (P, Q, W, c') per row.  The per-column work is then division free:
+//     for all columns, so its Thomas factorisation is done once (`spline_factor_kernel`, one thread per row; the
+//     c' recurrence contracts by <= 1/12 per row, so 40 rows of run-in reproduce it to rounding) and stored as a
+//     table per row.  The per-column work is then division free:
 //         d_i = P_i (y_{i+1}-y_i) - Q_i (y_i-y_{i-1}) - W_i d_{i-1}        (forward)
 //         M_i = d_i - c'_i M_{i+1}                                         (backward)
 //     The evaluation still uses the reference's own rounded abscissae x_i = fl(k fl(t_i - alpha)) for the position
 //     inside the interval (one ulp of x at t ~ 1e4 moves the interpolant at the 1e-13 level); only the small
 //     curvature term uses the shared factorisation (h_t^2 M_t = h_x^2 M_x up to 1e-11 relative, i.e. < 1e-14 of the
 //     value).
-//  2. Both recurrences forget their start geometrically (|W| ~ 0.27 on uniform samples), so a tile of `body`
-//     intervals plus `halo` rows on each side is self-contained.  A CTA owns [body + 2 halo + 3] rows x 16 real
-//     columns (8 complex grid points = 128-byte rows) of F in shared memory, read from HBM exactly once
-//     (cp.async, 16 B per copy), sweeps them with half-warps (16 columns each) spread over sub-ranges of rows,
-//     and evaluates the outputs that fall into its intervals with lanes running along the output index, so the
-//     stores into the time-tiled output are full 128-byte runs.  No workspace, no checkpoints, F is never re-read.
-//
-// HBM traffic per (knot, complex column): 16 B x (1 + (2 halo + 3)/body) read + 16 B written.
+//  2. Both recurrences are linear, so rows are cut into global blocks of 16: a half-warp (16 real columns) sweeps one
+//     block from a zero start, and the exact coupling to the neighbouring blocks is restored with the column-independent
+//     products Phi_i = prod(-W) (from the block start to i) and Psi_i = prod(-c') (from i to the block end), which
+//     are table entries too:  d_i = d0_i + Phi_i d_{start-1},  M_i = m0_i + Psi_i M_{end+1}.  All blocks of a tile run
+//     in parallel with no run-in.
+//  3. Both recurrences forget their start geometrically (|W| ~ 0.27 on uniform samples), so a tile of `body`
+//     intervals plus `halo` rows on each side is self-contained (the halo is chosen from the measured decay).  A CTA
+//     owns [body + 2 halo + 2] rows x 16 real columns (8 complex grid points = 128-byte rows) of F in shared memory,
+//     read once, and evaluates the outputs that fall into its intervals with lanes running along the output index,
+//     so the stores into the time-tiled output are full 128-byte runs.  No workspace, F is never re-read from HBM
+//     (the halo rows of neighbouring tiles come from L2).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -33,11 +36,18 @@ namespace scrib200 {
 
 constexpr int ST_COLS = 16;            // real columns per CTA
 constexpr int ST_PITCH = ST_COLS + 2;  // doubles per shared-memory row (144 B: consecutive rows shift by 4 banks)
-constexpr int FACTOR_RUNIN = 24;
+constexpr int ST_BR = 16;              // rows per sweep block (global alignment)
+constexpr int ST_TAB = 8;              // doubles per table row: P, Q, W, 1/h | Phi, c', Psi, h
+constexpr int FACTOR_RUNIN = 40;
+constexpr int ST_MAXBLK = 24;          // max sweep blocks per tile (384 threads)
 
 __device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void st_cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void st_cp_async_commit_wait() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -63,11 +73,11 @@ __device__ __forceinline__ void nak_row(const double* __restrict__ t, int N, int
     }
 }
 
-// tab[i] = (P_i, Q_i, W_i, c'_i) for rows 1..N-2 (rows 0 and N-1 zero); also u'_i = inv_gamma (t_i - tt) and the
-// retained output block [lo, hi) = { i : umin <= u'_i <= umax } (waveform_grid.py:564-568), umin/umax reduced here
-// from k (t_0 - alpha), k (t_{N-1} - alpha) over the G grid points.
+// tab[i] = (P, Q, W, 1/h_i | Phi, c', Psi, h_i) for rows 1..N-2 (row 0 carries h_0, 1/h_0; row N-1 zeros); also
+// u'_i = inv_gamma (t_i - tt) and the retained output block [lo, hi) = { i : umin <= u'_i <= umax }
+// (waveform_grid.py:564-568), umin/umax reduced here from k (t_0 - alpha), k (t_{N-1} - alpha) over the G grid points.
 __global__ void __launch_bounds__(256)
-spline_factor_kernel(const double* __restrict__ t, int N, double4* __restrict__ tab, double inv_gamma, double tt,
+spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ tab, double inv_gamma, double tt,
                      const double* __restrict__ kconf, const double* __restrict__ alpha, int G,
                      double* __restrict__ uprm, double* __restrict__ info) {
     __shared__ double s_red[2][8];
@@ -110,20 +120,39 @@ spline_factor_kernel(const double* __restrict__ t, int N, double4* __restrict__ 
         }
     }
     if (i >= N) return;
-    double4 row = make_double4(0.0, 0.0, 0.0, 0.0);
+    double row[ST_TAB] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i <= N - 2) {
+        const double h = t[i + 1] - t[i];
+        row[3] = 1.0 / h;
+        row[7] = h;
+    }
     if (i >= 1 && i <= N - 2) {
+        const int bstart = (i & ~(ST_BR - 1)) > 1 ? (i & ~(ST_BR - 1)) : 1;
+        const int bend = ((i | (ST_BR - 1)) < N - 2) ? (i | (ST_BR - 1)) : N - 2;
         int r = i - FACTOR_RUNIN;
         if (r < 1) r = 1;
-        double cp = 0.0;
-        for (; r <= i; ++r) {
+        double cp = 0.0, phi = 1.0, psi = 1.0;
+        for (; r <= bend; ++r) {
             double sub, diag, sup, hm, hp;
             nak_row(t, N, r, sub, diag, sup, hm, hp);
             const double e = 1.0 / (diag - sub * cp);
             cp = sup * e;
-            if (r == i) row = make_double4(6.0 * e / hp, 6.0 * e / hm, sub * e, cp);
+            const double W = sub * e;
+            if (r >= bstart && r <= i) phi *= -W;
+            if (r >= i) psi *= -cp;
+            if (r == i) {
+                row[0] = 6.0 * e / hp;
+                row[1] = 6.0 * e / hm;
+                row[2] = W;
+                row[5] = cp;
+            }
         }
+        row[4] = phi;
+        row[6] = psi;
     }
-    tab[i] = row;
+    double4* dst = reinterpret_cast<double4*>(tab + (size_t)i * ST_TAB);
+    dst[0] = make_double4(row[0], row[1], row[2], row[3]);
+    dst[1] = make_double4(row[4], row[5], row[6], row[7]);
 }
 
 __global__ void spline_info_init_kernel(double* __restrict__ info, double n) {
@@ -133,15 +162,14 @@ __global__ void spline_info_init_kernel(double* __restrict__ info, double n) {
 // Worst decay of the two recurrences over any window of 32 / 64 consecutive rows:
 // info[2] = max_i prod_{r=i-31..i} |W_r| (forward) or prod |c'_r| (backward), info[3] the same for 64 rows.
 __global__ void __launch_bounds__(256)
-spline_decay_kernel(const double4* __restrict__ tab, int N, double* __restrict__ info) {
+spline_decay_kernel(const double* __restrict__ tab, int N, double* __restrict__ info) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double d32 = 0.0, d64 = 0.0;
     if (i >= 64 && i <= N - 2) {
         double pw = 1.0, pc = 1.0;
         for (int r = i; r > i - 64; --r) {
-            const double4 v = tab[r];
-            pw *= fabs(v.z);
-            pc *= fabs(v.w);
+            pw *= fabs(tab[(size_t)r * ST_TAB + 2]);
+            pc *= fabs(tab[(size_t)r * ST_TAB + 5]);
             if (r == i - 31) d32 = fmax(pw, pc);
         }
         d64 = fmax(pw, pc);
@@ -157,18 +185,42 @@ spline_decay_kernel(const double4* __restrict__ tab, int N, double* __restrict__
     }
 }
 
+// J[tile][g] = first output j with up[j] >= x_{tile*body}(g) (J[0][g] = 0, J[ntiles][g] = Nout): the outputs column g's
+// tile `tile` evaluates are J[tile][g] .. J[tile+1][g]-1.  One thread per entry: the 17 dependent probes of each binary
+// search are hidden by the parallelism here instead of sitting on every tile CTA's critical path.
+__global__ void __launch_bounds__(256)
+spline_jrange_kernel(const double* __restrict__ t, int N, int G, const double* __restrict__ kconf,
+                     const double* __restrict__ alpha, const double* __restrict__ up, int Nout, int body, int ntiles,
+                     int* __restrict__ J) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (ntiles + 1) * G) return;
+    const int tile = idx / G, g = idx - tile * G;
+    int j = (tile == 0) ? 0 : Nout;
+    if (tile > 0 && tile < ntiles) {
+        const double xb = __dmul_rn(kconf[g], __dsub_rn(t[tile * body], alpha[g]));
+        int lo_s = 0, hi_s = Nout;
+        while (lo_s < hi_s) {
+            const int mid = (lo_s + hi_s) >> 1;
+            if (up[mid] < xb) lo_s = mid + 1; else hi_s = mid;
+        }
+        j = lo_s;
+    }
+    J[idx] = j;
+}
+
 // MODE 0: evaluate at up[] (the BMS remap); MODE 1 / 2: first / second derivative at the knots; MODE 3: the
 // definite integral over [t_i, t_{i+1}] stored at row i+1 (row 0 = 0) - a column scan turns it into the antiderivative;
 // MODE 4: the increment of the second antiderivative, `up` then holding the (scanned) first antiderivative [N, G].
 // For MODE >= 1 `out` is [N, G] complex time-major and Nout/tshift are unused.
+// blockDim.x >= 16 * (body + 2 halo) / 16 (one half-warp per sweep block), body and halo multiples of 16.
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(ST_MAXBLK * ST_COLS, 2)
 spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict__ F, int G,
                    const double* __restrict__ kconf, const double* __restrict__ alpha,
-                   const double4* __restrict__ tab, const double* __restrict__ up, int Nout,
-                   double* __restrict__ out, int tshift, int body, int halo) {
+                   const double* __restrict__ tab, const double* __restrict__ up, int Nout,
+                   double* __restrict__ out, int tshift, int body, int halo, const int* __restrict__ J) {
     extern __shared__ __align__(16) double s_mem[];
-    __shared__ double s_k[ST_COLS / 2], s_al[ST_COLS / 2];
+    __shared__ double s_k[ST_COLS / 2], s_al[ST_COLS / 2], s_ik[ST_COLS / 2];
     __shared__ int s_jlo[ST_COLS / 2], s_jhi[ST_COLS / 2];
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -177,40 +229,41 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     const int a = blockIdx.y * body;                        // intervals a .. b-1, knots a .. b
     const int b = (a + body < N - 1) ? a + body : N - 1;
     const bool last_tile = (b == N - 1);
-    const int mhi = (b + halo < N - 2) ? b + halo : N - 2;  // last row of the backward sweep
-    const int dlo = (a - 2 > 1) ? a - 2 : 1;                // first row whose d is kept (two below a: the right-end formula)
-    const int flo = (a - halo > 1) ? a - halo : 1;          // first row of the forward sweep
-    const int ylo = flo - 1, yhi = mhi + 1;                 // rows of F resident in shared memory
+    const int slo = (a - halo > 1) ? a - halo : 1;          // rows slo .. shi are swept
+    const int shi = (b + halo - 1 < N - 2) ? b + halo - 1 : N - 2;
+    const int ylo = slo - 1, yhi = shi + 1;                 // rows resident in shared memory
     const int nyrows = yhi - ylo + 1;
-    const int ymax = body + 2 * halo + 3, dmax = body + halo + 4;
+    const int ymax = body + 2 * halo + 2;
+    const int qlo = slo / ST_BR, qhi = shi / ST_BR;         // sweep blocks of this tile
 
-    double* sY = s_mem;                                     // [ymax][ST_PITCH]     row r -> r - ylo
-    double* sD = sY + (size_t)ymax * ST_PITCH;              // [dmax][ST_PITCH]     row r -> r - a + 2   (d, then M)
-    double4* sTab = reinterpret_cast<double4*>(sD + (size_t)dmax * ST_PITCH);   // [ymax]   row r -> r - ylo
-    double* sT = reinterpret_cast<double*>(sTab + ymax);    // [ymax]               row r -> r - ylo
+    double* sY = s_mem;                                     // [ymax][ST_PITCH]  F            row r -> r - ylo
+    double* sD = sY + (size_t)ymax * ST_PITCH;              // [ymax][ST_PITCH]  d0, m0, M    row r -> r - ylo
+    double* sTab = sD + (size_t)ymax * ST_PITCH;            // [ymax][ST_TAB]                 row r -> r - ylo
+    double* sT = sTab + (size_t)ymax * ST_TAB;              // [ymax]                         row r -> r - ylo
+    double* sEdgeD = sT + ymax + (ymax & 1);                // [ST_MAXBLK][ST_COLS] d0 at the block ends
+    double* sEdgeM = sEdgeD + ST_MAXBLK * ST_COLS;          // [ST_MAXBLK][ST_COLS] m0 at the block starts
 #define SY(r_, c_) sY[((r_) - ylo) * ST_PITCH + (c_)]
-#define SD(r_, c_) sD[((r_) - a + 2) * ST_PITCH + (c_)]
-#define STAB(r_) sTab[(r_) - ylo]
+#define SD(r_, c_) sD[((r_) - ylo) * ST_PITCH + (c_)]
+#define STAB(r_, f_) sTab[((r_) - ylo) * ST_TAB + (f_)]
 #define STT(r_) sT[(r_) - ylo]
 
     // ---- stage the tile: F rows (16-byte copies, 8 per row), the factor table rows and the sample times
     {
-        const int nchunk = nyrows * (ST_COLS / 2);
-        for (int e = tid; e < nchunk; e += nthr) {
-            const int rr = e >> 3, ch = e & 7;
+        const int ch = tid & 7;
+        const bool colok = col0 + 2 * ch < G2;
+        const double* src = F + (size_t)ylo * G2 + col0 + 2 * ch;
+        for (int rr = tid >> 3; rr < nyrows; rr += nthr >> 3) {
             double* dst = sY + rr * ST_PITCH + 2 * ch;
-            if (col0 + 2 * ch < G2) {
-                st_cp_async16(dst, F + (size_t)(ylo + rr) * G2 + col0 + 2 * ch);
+            if (colok) {
+                st_cp_async16(dst, src + (size_t)rr * G2);
             } else {
                 dst[0] = 0.0;
                 dst[1] = 0.0;
             }
         }
-        for (int e = tid; e < nyrows; e += nthr) {
-            st_cp_async16(&sTab[e], &tab[ylo + e]);
-            st_cp_async16(reinterpret_cast<char*>(&sTab[e]) + 16, reinterpret_cast<const char*>(&tab[ylo + e]) + 16);
-            sT[e] = t[ylo + e];
-        }
+        const double* tsrc = tab + (size_t)ylo * ST_TAB;
+        for (int e = tid; e < nyrows * (ST_TAB / 2); e += nthr) st_cp_async16(sTab + 2 * e, tsrc + 2 * e);
+        for (int e = tid; e < nyrows; e += nthr) st_cp_async8(sT + e, t + ylo + e);
     }
     // per-column constants and (MODE 0) the output range of each complex column, found while the copies fly
     if (tid < ST_COLS) {
@@ -220,67 +273,96 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         if (which == 0) {
             s_k[c] = k;
             s_al[c] = al;
+            s_ik[c] = 1.0 / k;
         }
-        if (MODE == 0) {
-            int j = (which == 0) ? 0 : Nout;
-            const bool search = (which == 0) ? (a > 0) : !last_tile;
-            if (search && g < G) {
-                const double xb = __dmul_rn(k, __dsub_rn(t[which == 0 ? a : b], al));
-                int lo_s = 0, hi_s = Nout;     // first j with up[j] >= xb
-                while (lo_s < hi_s) {
-                    const int mid = (lo_s + hi_s) >> 1;
-                    if (up[mid] < xb) lo_s = mid + 1; else hi_s = mid;
-                }
-                j = lo_s;
-            }
-            if (which == 0) s_jlo[c] = j; else s_jhi[c] = j;
+        if (MODE == 0 && g < G) {
+            if (which == 0) s_jlo[c] = J[(size_t)blockIdx.y * G + g]; else s_jhi[c] = J[(size_t)(blockIdx.y + 1) * G + g];
         }
     }
     st_cp_async_commit_wait();
     __syncthreads();
 
-    // ---- sweeps: half-warp = 16 real columns of one sub-range of rows
+    // ---- sweeps: half-warp = 16 real columns of one block of 16 rows
     const int cc = tid & (ST_COLS - 1);
-    const int nsub = nthr / ST_COLS;
-    const int sidx = tid / ST_COLS;
-    const int nrows = mhi - dlo + 1;                        // rows dlo .. mhi get a moment
-    const int SR = (nrows + nsub - 1) / nsub;
-    const int rs = dlo + sidx * SR;
-    const int re = (rs + SR < mhi + 1) ? rs + SR : mhi + 1; // my rows: [rs, re)
-    if (rs < re) {
-        int r = (rs - halo > flo) ? rs - halo : flo;
-        double yc = SY(r, cc);
-        double dym = yc - SY(r - 1, cc);
-        double d = 0.0;
-        for (; r < rs; ++r) {                               // run-in: nothing stored
-            const double yn = SY(r + 1, cc);
-            const double dy = yn - yc;
-            const double4 tb = STAB(r);
-            d = fma(-tb.z, d, tb.x * dy - tb.y * dym);
-            yc = yn;
-            dym = dy;
+    const int q = qlo + tid / ST_COLS;
+    const bool active = (q <= qhi);
+    const int r0 = (q * ST_BR > slo) ? q * ST_BR : slo;
+    const int r1 = (q * ST_BR + ST_BR - 1 < shi) ? q * ST_BR + ST_BR - 1 : shi;
+    // (MODE 0) the first output times of my column are fetched now, so their latency hides behind the sweeps
+    constexpr int UPRE = 8;
+    double upre[UPRE];
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    int jlo0 = 0, jhi0 = 0;
+    if (MODE == 0 && warp < ST_COLS / 2 && blockIdx.x * (ST_COLS / 2) + warp < G) {
+        jlo0 = s_jlo[warp];
+        jhi0 = s_jhi[warp];
+#pragma unroll
+        for (int it = 0; it < UPRE; ++it) {
+            const int j = jlo0 + lane + 32 * it;
+            upre[it] = (j < jhi0) ? up[j] : 0.0;
         }
-        for (; r < re; ++r) {
+    }
+    const bool full = active && (r1 - r0 == ST_BR - 1);     // all but the blocks at the ends of the series
+    if (active) {                                           // forward from a zero start
+        double yc = SY(r0, cc);
+        double dym = yc - SY(r0 - 1, cc);
+        double d = 0.0;
+        auto step = [&](int r) {
             const double yn = SY(r + 1, cc);
             const double dy = yn - yc;
-            const double4 tb = STAB(r);
+            const double4 tb = *reinterpret_cast<const double4*>(&STAB(r, 0));
             d = fma(-tb.z, d, tb.x * dy - tb.y * dym);
             SD(r, cc) = d;
             yc = yn;
             dym = dy;
+        };
+        if (full) {
+#pragma unroll 8
+            for (int k = 0; k < ST_BR; ++k) step(r0 + k);
+        } else {
+            for (int r = r0; r <= r1; ++r) step(r);
         }
+        sEdgeD[(q - qlo) * ST_COLS + cc] = d;
     }
     __syncthreads();
-    double M = 0.0;
-    if (rs < re) {                                          // backward run-in over the rows above mine (read only)
-        int r = (re + halo - 1 < mhi) ? re + halo - 1 : mhi;
-        for (; r >= re; --r) M = fma(-STAB(r).w, M, SD(r, cc));
+    if (active) {
+        // true d at the row before my block: block-end values of the blocks below, weighted by their Phi products
+        double D = 0.0, w = 1.0;
+        for (int p = q - 1; p >= qlo; --p) {
+            D = fma(w, sEdgeD[(p - qlo) * ST_COLS + cc], D);
+            w *= STAB(p * ST_BR + ST_BR - 1, 4);
+            if (fabs(w) < 1e-24) break;
+        }
+        double m = 0.0;
+        auto step = [&](int r) {                            // backward from a zero start, on the corrected d
+            const double2 pc = *reinterpret_cast<const double2*>(&STAB(r, 4));
+            const double d = fma(pc.x, D, SD(r, cc));
+            m = fma(-pc.y, m, d);
+            SD(r, cc) = m;
+        };
+        if (full) {
+#pragma unroll 8
+            for (int k = ST_BR - 1; k >= 0; --k) step(r0 + k);
+        } else {
+            for (int r = r1; r >= r0; --r) step(r);
+        }
+        sEdgeM[(q - qlo) * ST_COLS + cc] = m;               // m0 at my block start
     }
     __syncthreads();
-    if (rs < re) {
-        for (int r = re - 1; r >= rs; --r) {
-            M = fma(-STAB(r).w, M, SD(r, cc));
-            SD(r, cc) = M;
+    if (active) {
+        double E = 0.0, w = 1.0;
+        for (int p = q + 1; p <= qhi; ++p) {
+            E = fma(w, sEdgeM[(p - qlo) * ST_COLS + cc], E);
+            w *= STAB(p * ST_BR, 6);
+            if (fabs(w) < 1e-24) break;
+        }
+        if (E != 0.0) {
+            if (full) {
+#pragma unroll
+                for (int k = 0; k < ST_BR; ++k) SD(r0 + k, cc) = fma(STAB(r0 + k, 6), E, SD(r0 + k, cc));
+            } else {
+                for (int r = r0; r <= r1; ++r) SD(r, cc) = fma(STAB(r, 6), E, SD(r, cc));
+            }
         }
     }
     __syncthreads();
@@ -292,28 +374,27 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     if (last_tile && tid >= 32 && tid < 32 + ST_COLS) {
         const int c = tid - 32;
         const double hm = STT(N - 2) - STT(N - 3), hp = STT(N - 1) - STT(N - 2);
-        // N == 4: M_2 and M_1 are both final; the formula reads M_{N-2}, M_{N-3}
         SD(N - 1, c) = ((hm + hp) * SD(N - 2, c) - hp * SD(N - 3, c)) / hm;
     }
     if (a == 0 || last_tile) __syncthreads();
 
     // ---- outputs
     if (MODE == 0) {
-        const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
         double2* o2 = reinterpret_cast<double2*>(out);
         const int tmask = (1 << tshift) - 1;
         const int64_t tileGT = (int64_t)G << tshift;
         for (int c = warp; c < ST_COLS / 2; c += nwarp) {
             const int g = blockIdx.x * (ST_COLS / 2) + c;
             if (g >= G) continue;
-            const double k = s_k[c], al = s_al[c];
+            const double k = s_k[c], al = s_al[c], ik = s_ik[c];
             const int jlo = s_jlo[c], jhi = s_jhi[c];
             const double xa = __dmul_rn(k, __dsub_rn(STT(a), al));
             const double xbv = __dmul_rn(k, __dsub_rn(STT(b), al));
-            const double slope = (double)(b - a) / (xbv - xa);
-            for (int j = jlo + lane; j < jhi; j += 32) {
-                const double u = up[j];
-                int i = a + (int)fmin(fmax((u - xa) * slope, 0.0), (double)(b - 1 - a));
+            const float slope = (float)((double)(b - a) / (xbv - xa));
+            double2* og = o2 + ((tshift > 0) ? ((int64_t)g << tshift) : (int64_t)g);
+            auto eval_one = [&](int j, double u) {
+                int i = a + __float2int_rd((float)(u - xa) * slope);    // guess, verified below
+                i = max(a, min(i, b - 1));
                 double xi = __dmul_rn(k, __dsub_rn(STT(i), al));
                 double xi1 = __dmul_rn(k, __dsub_rn(STT(i + 1), al));
                 if (!((xi <= u || i == a) && (u < xi1 || i == b - 1))) {
@@ -326,9 +407,19 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
                     xi = __dmul_rn(k, __dsub_rn(STT(i), al));
                     xi1 = __dmul_rn(k, __dsub_rn(STT(i + 1), al));
                 }
-                const double ht = STT(i + 1) - STT(i);
+                const double ht = STAB(i, 7);
                 const double hx = xi1 - xi;
-                const double inv_h = 1.0 / hx;
+                // 1/hx: hx = k h_t up to the rounding of the abscissae, so two Newton steps from (1/k)(1/h_t) are exact to
+                // rounding; a true division only if the abscissae have lost more than 3 digits of the step
+                double inv_h = ik * STAB(i, 3);
+                double e = fma(-hx, inv_h, 1.0);
+                if (fabs(e) < 1e-3) {
+                    inv_h = fma(inv_h, e, inv_h);
+                    e = fma(-hx, inv_h, 1.0);
+                    inv_h = fma(inv_h, e, inv_h);
+                } else {
+                    inv_h = 1.0 / hx;
+                }
                 const double A = (xi1 - u) * inv_h;
                 const double B = (u - xi) * inv_h;
                 const double h26 = ht * ht * (1.0 / 6.0);
@@ -341,17 +432,23 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
                 double2 r;
                 r.x = A * yi.x + B * yi1.x + (ca * Mi.x + cb * Mi1.x);
                 r.y = A * yi.y + B * yi1.y + (ca * Mi.y + cb * Mi1.y);
-                const int64_t o = (tshift > 0) ? (int64_t)(j >> tshift) * tileGT + ((int64_t)g << tshift) + (j & tmask)
-                                               : (int64_t)j * G + g;
-                o2[o] = r;
+                const int64_t o = (tshift > 0) ? (int64_t)(j >> tshift) * tileGT + (j & tmask) : (int64_t)j * G;
+                og[o] = r;
+            };
+            int j = jlo + lane;
+            if (c == warp) {                                // the prefetched output times
+#pragma unroll
+                for (int it = 0; it < UPRE; ++it, j += 32)
+                    if (j < jhi) eval_one(j, upre[it]);
             }
+            for (; j < jhi; j += 32) eval_one(j, up[j]);
         }
     } else {
         // one thread per (knot, real column): 128-byte row segments of the time-major output
         const int rstep = nthr / ST_COLS;
         const bool colok = col0 + cc < G2;
-        for (int i = a + sidx; i < b; i += rstep) {
-            const double ht = STT(i + 1) - STT(i);
+        for (int i = a + tid / ST_COLS; i < b; i += rstep) {
+            const double ht = STAB(i, 7);
             const double yi = SY(i, cc), yi1 = SY(i + 1, cc);
             const double Mi = SD(i, cc), Mi1 = SD(i + 1, cc);
             if (!colok) continue;
@@ -408,31 +505,43 @@ column_scan_kernel(double* __restrict__ x, int64_t N, int C) {
 }
 
 static size_t tile_smem_bytes(int body, int halo) {
-    const size_t ymax = (size_t)body + 2 * halo + 3, dmax = (size_t)body + halo + 4;
-    return (ymax + dmax) * ST_PITCH * sizeof(double) + ymax * (sizeof(double4) + sizeof(double));
+    const size_t ymax = (size_t)body + 2 * halo + 2;
+    return (2 * ymax * ST_PITCH + ymax * ST_TAB + ymax + (ymax & 1) + 2 * (size_t)ST_MAXBLK * ST_COLS) * sizeof(double);
+}
+
+static void resolve_tile(int& halo, int& body) {
+    if (halo <= 0) halo = 32;
+    if (body <= 0) body = (halo <= 32) ? 224 : (halo <= 64 ? 160 : 128);   // two CTAs per SM up to halo = 64
 }
 
 template <int MODE>
 static int launch_tile(const double* t, int64_t n_times, const double* F, int G, const double* kconf, const double* alpha,
                        const double* tab, const double* uprm, int64_t n_out, double* out, int tshift, int halo, int body,
-                       void* stream, const char* name) {
+                       void* workspace, size_t workspace_bytes, void* stream, const char* name) {
     SCRIB200_REQUIRE(n_times < (int64_t)2147483000 && n_out < (int64_t)2147483000, "%s: series longer than 2^31 samples", name);
-    if (halo <= 0) halo = 32;
-    if (body <= 0) body = (halo <= 32) ? 256 : (halo <= 64 ? 192 : 128);
+    resolve_tile(halo, body);
+    SCRIB200_REQUIRE(halo % ST_BR == 0 && body % ST_BR == 0, "%s: body=%d and halo=%d must be multiples of %d", name, body, halo, ST_BR);
     const size_t smem = tile_smem_bytes(body, halo);
-    SCRIB200_REQUIRE(halo <= 256 && body >= 16 && smem <= 220 * 1024, "%s: body=%d halo=%d does not fit shared memory", name, body, halo);
+    const int nblk = (body + 2 * halo) / ST_BR;
+    SCRIB200_REQUIRE(nblk <= ST_MAXBLK && smem <= 220 * 1024, "%s: body=%d halo=%d does not fit one CTA", name, body, halo);
     const int64_t ntiles = (n_times - 1 + body - 1) / body;
     SCRIB200_REQUIRE(ntiles <= 65535, "%s: too many time tiles (%lld); raise `body`", name, (long long)ntiles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(spline_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles);
-    int threads = 256;
-    if (const char* env = getenv("SCRIB200_SPLINE_THREADS")) {   // tuning knob (multiple of 32, 64..256)
-        const int v = atoi(env);
-        if (v >= 64 && v <= 256 && v % 32 == 0) threads = v;
+    const int threads = ((nblk * ST_COLS + 31) / 32) * 32;   // one half-warp per sweep block
+    int* J = nullptr;
+    if (MODE == 0) {
+        const size_t need = (size_t)(ntiles + 1) * G * sizeof(int);
+        SCRIB200_REQUIRE(workspace && workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", name, workspace_bytes, need);
+        J = reinterpret_cast<int*>(workspace);
+        const int64_t total = (ntiles + 1) * (int64_t)G;
+        spline_jrange_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            t, (int)n_times, G, kconf, alpha, uprm, (int)n_out, body, (int)ntiles, J);
+        SCRIB200_CHECK_LAUNCH(name);
     }
     spline_tile_kernel<MODE><<<grid, threads, smem, (cudaStream_t)stream>>>(
-        t, (int)n_times, F, G, kconf, alpha, reinterpret_cast<const double4*>(tab), uprm, (int)n_out, out, tshift, body, halo);
+        t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }
@@ -452,17 +561,26 @@ extern "C" int scrib200_spline_prepare(const double* t, int64_t n_times, double 
     // seed info in stream order (lo = hi = N means "empty / not found")
     spline_info_init_kernel<<<1, 32, 0, st>>>(info, (double)n_times);
     const unsigned blocks = (unsigned)((n_times + 255) / 256);
-    spline_factor_kernel<<<blocks, 256, 0, st>>>(t, (int)n_times, reinterpret_cast<double4*>(tab), inv_gamma,
+    spline_factor_kernel<<<blocks, 256, 0, st>>>(t, (int)n_times, tab, inv_gamma,
                                                  time_translation, kconf, alpha, G, uprm, info);
     SCRIB200_CHECK_LAUNCH("spline_prepare(factor)");
-    spline_decay_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const double4*>(tab), (int)n_times, info);
+    spline_decay_kernel<<<blocks, 256, 0, st>>>(tab, (int)n_times, info);
     SCRIB200_CHECK_LAUNCH("spline_prepare(decay)");
     return SCRIB200_OK;
 }
 
+extern "C" size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int halo, int body) {
+    using namespace scrib200;
+    resolve_tile(halo, body);
+    if (n_times < 2 || body <= 0) return 16;
+    const int64_t ntiles = (n_times - 1 + body - 1) / body;
+    return (size_t)(ntiles + 1) * (size_t)G * sizeof(int) + 16;
+}
+
 extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
                                      const double* alpha, const double* tab, const double* uprm, int64_t n_out,
-                                     double* out, int tile, int halo, int body, void* stream) {
+                                     double* out, int tile, int halo, int body, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
     using namespace scrib200;
     SCRIB200_REQUIRE(t && F && kconf && alpha && tab && uprm && out, "spline_remap: null pointer");
     SCRIB200_REQUIRE(n_times >= 4, "spline_remap: a cubic interpolating spline needs at least 4 knots; got %lld",
@@ -473,8 +591,8 @@ extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const dou
                      "spline_remap: G=%d, tile=%d must be 0 (time-major output) or a power of two >= 2", G, tile);
     SCRIB200_REQUIRE(aligned16(F) && aligned16(out) && aligned16(tab), "spline_remap: pointers must be 16-byte aligned");
     if (n_out <= 0) return SCRIB200_OK;
-    return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, stream,
-                          "spline_remap");
+    return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, workspace,
+                          workspace_bytes, stream, "spline_remap");
 }
 
 extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const double* data, int ncol,
@@ -489,17 +607,17 @@ extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const 
     SCRIB200_REQUIRE(ncol > 0, "spline_calculus: ncol=%d", ncol);
     SCRIB200_REQUIRE(aligned16(data) && aligned16(out) && aligned16(tab) && aligned16(aux), "spline_calculus: pointers must be 16-byte aligned");
     if (order == 1)
-        return launch_tile<1>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, out, 0, halo, body, stream, "spline_calculus");
+        return launch_tile<1>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (order == 2)
-        return launch_tile<2>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, out, 0, halo, body, stream, "spline_calculus");
+        return launch_tile<2>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     const int C = 2 * ncol;
     double* first = (order == -1) ? out : aux;
-    int rc = launch_tile<3>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, first, 0, halo, body, stream, "spline_calculus");
+    int rc = launch_tile<3>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, first, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
     column_scan_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(first, n_times, C);
     SCRIB200_CHECK_LAUNCH("spline_calculus(scan)");
     if (order == -1) return SCRIB200_OK;
-    rc = launch_tile<4>(t, n_times, data, ncol, nullptr, nullptr, tab, first, 0, out, 0, halo, body, stream, "spline_calculus");
+    rc = launch_tile<4>(t, n_times, data, ncol, nullptr, nullptr, tab, first, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
     column_scan_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(out, n_times, C);
     SCRIB200_CHECK_LAUNCH("spline_calculus(scan)");

@@ -159,12 +159,12 @@ def _ones_zeros(n):
 
 
 def spline_tables(tt):
-    """(tab [N, 4], halo) for the time axis `tt` (device tensor): the shared Thomas factorisation of the not-a-knot
+    """(tab [N, 8], halo) for the time axis `tt` (device tensor): the shared Thomas factorisation of the not-a-knot
     moment system and the run-in length its decay calls for (scrib200_spline_prepare)."""
     lib = _lib.load()
     torch = _torch()
     N = tt.shape[0]
-    tab = torch.empty((N, 4), dtype=torch.float64, device="cuda")
+    tab = torch.empty((N, 8), dtype=torch.float64, device="cuda")
     info = torch.empty(8, dtype=torch.float64, device="cuda")
     _lib.check(
         lib.scrib200_spline_prepare(_lib.ptr(tt), N, 1.0, 0.0, None, None, 0, _lib.ptr(tab), None, _lib.ptr(info), _lib.stream_ptr()),
@@ -206,9 +206,11 @@ def spline_calculus(t, data, kind, order=1, tprime=None):
         tp = to_device(tprime, np.float64)
         ones, zeros = _ones_zeros(ncol)
         out = torch.empty((tp.shape[0], ncol), dtype=torch.complex128, device="cuda")
+        ws = torch.empty(lib.scrib200_spline_remap_workspace_bytes(N, ncol, halo, 0), dtype=torch.uint8, device="cuda")
         _lib.check(
             lib.scrib200_spline_remap(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), _lib.ptr(tab),
-                                      _lib.ptr(tp), tp.shape[0], _lib.ptr(out), 0, halo, 0, _lib.stream_ptr()),
+                                      _lib.ptr(tp), tp.shape[0], _lib.ptr(out), 0, halo, 0, _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()),
             "spline_remap",
         )
         out = out.reshape((tp.shape[0],) + tuple(d.shape[1:]))

@@ -287,7 +287,9 @@ class TransformPlan:
         trig = np.ascontiguousarray(np.conj(E[:, Lo:]))
         self.d_trig = torch.from_numpy(trig).to(dev)
         self._tile = None
+        self._ws = None
         self._side = None
+        self._host_pool = []
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
         self.spline_body = 0   # 0 = default intervals per tile
 
@@ -297,6 +299,9 @@ class TransformPlan:
         return self._side
 
     def _info_host(self):
+        """A pinned 64-byte landing buffer for `info` (recycled: no allocation in steady state)."""
+        if self._host_pool:
+            return self._host_pool.pop()
         return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
     # -- the individual stages (device tensors in, device tensors out) ---------------------------
@@ -336,10 +341,14 @@ class TransformPlan:
         else:
             out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
         halo, body = prep.halo_body(self.spline_halo, self.spline_body)
+        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         _lib.check(
             lib.scrib200_spline_remap(
                 _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
-                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.stream_ptr(),
+                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.ptr(self._ws), self._ws.numel(),
+                _lib.stream_ptr(),
             ),
             "spline_remap",
         )
@@ -411,7 +420,7 @@ class TimePrep:
         lib = _lib.load()
         N = t.shape[0]
         self.N = N
-        self.tab = torch.empty((N, 4), dtype=torch.float64, device=plan.device)
+        self.tab = torch.empty((N, 8), dtype=torch.float64, device=plan.device)
         self.uprm_full = torch.empty(N, dtype=torch.float64, device=plan.device)
         self.info = torch.empty(8, dtype=torch.float64, device=plan.device)
         _lib.check(
@@ -423,6 +432,7 @@ class TimePrep:
         )
         # read `info` back on a side stream so that kernels launched meanwhile on the caller's stream are not waited for
         self._host = plan._info_host()
+        self._pool = plan._host_pool
         cur = torch.cuda.current_stream()
         side = plan._side_stream()
         self._ready = torch.cuda.Event()
@@ -437,6 +447,8 @@ class TimePrep:
         if self._resolved is None:
             self._ready.synchronize()
             v = self._host.tolist()
+            self._pool.append(self._host)
+            self._host = None
             self._resolved = (int(v[0]), max(int(v[0]), int(v[1])), float(v[2]), float(v[3]))
         return self._resolved[:2]
 

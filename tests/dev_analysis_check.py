@@ -1,4 +1,4 @@
-"""Developer script: spline_remap time at config-2 size against tile body / halo / CTA size."""
+"""Developer script: DMMA analysis kernel vs the scalar tiled kernel (same inputs), timing at config-2 size."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -13,16 +13,18 @@ kw = dict(supertranslation=real_supertranslation(4), frame_rotation=[1.0, 2.0, 3
 pl = P.TransformPlan(2, 8, sb.h, **kw)
 td = ops.to_device(t); ad = ops.to_device(data)
 prep = pl.prepare(td); F = pl.synthesize(ad); up = prep.uprm
-print("n_out", up.shape[0], "halo/body auto", prep.halo_body())
+gT = pl.remap_tiled(td, F, up, prep)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-ref = None
-for body, halo in ((96, 32), (128, 32), (160, 32), (192, 32), (224, 32), (256, 32), (320, 32), (160, 64)):
-    pl.spline_body, pl.spline_halo = body, halo
+res = {}
+for mode in ("scalar", "dmma"):
+    if mode == "scalar": os.environ["SCRIB200_ANALYSIS_SCALAR"] = "1"
+    else: os.environ.pop("SCRIB200_ANALYSIS_SCALAR", None)
     ts = []
     for it in range(4):
         flush.fill_(it)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); g = pl.remap_tiled(td, F, up, prep); e1.record(); torch.cuda.synchronize()
+        e0.record(); m = pl.analyze_tiled(gT, up.shape[0]); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    if ref is None: ref = g.clone()
-    print(f"body {body} halo {halo}: {min(ts[1:]):.3f} ms  maxdiff vs first {float((g - ref).abs().max()):.2e}")
+    res[mode] = m.clone()
+    print(f"{mode}: {min(ts[1:]):.3f} ms")
+print("max |dmma - scalar| / max|scalar| =", float((res["dmma"] - res["scalar"]).abs().max() / res["scalar"].abs().max()))

@@ -13,7 +13,7 @@ td, ad = ops.to_device(t), ops.to_device(data)
 F = pl.synthesize(ad)
 prep = pl.prepare(td)
 up = prep.uprm
-for body, halo in ((0, 0), (50, 32), (100, 64), (333, 32), (16, 128)):
+for body, halo in ((0, 0), (48, 32), (96, 64), (320, 32), (16, 128), (128, 128)):
     pl.spline_body, pl.spline_halo = body, halo
     print("body", body, "halo", halo, flush=True)
     g = pl.remap(td, F, up, prep)
