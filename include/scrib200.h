@@ -171,6 +171,13 @@ int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_time
                                 const int* cols, const double* vals, const int* seg_host, const int* seg_dev, int K,
                                 double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill
+ * chunk i+1 while the copy engine drains chunk i).  On return all of `src_host` has been read; the DMAs are ordered
+ * on `stream`.  Page-locked sources are copied directly.
+ */
+int scrib200_h2d(void* dst_device, const void* src_host, size_t nbytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

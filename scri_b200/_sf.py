@@ -96,33 +96,40 @@ def _phase_powers(z, kmax):
 def wigner_D_column(Ra, Rb, ell_max, m_col):
     """D^l_{mp, m_col}(R) for all l<=ell_max, all mp: returns [..., (ell_max+1)^2] indexed LM_index(l,mp,0).
 
-    Entries with l < |m_col| are zero.
+    Entries with l < |m_col| are zero.  The three-term recurrence in l runs for all mp at once (rows that have not
+    started yet hold zeros and their table coefficients are zero, so they stay zero until their seed is planted).
     """
     Ra = np.asarray(Ra, dtype=complex)
     Rb = np.asarray(Rb, dtype=complex)
+    shape = Ra.shape
+    Ra = Ra.reshape(-1)
+    Rb = Rb.reshape(-1)
     L = max(ell_max, abs(m_col))
     seed, rec = wigner_tables(L)
-    ra2 = Ra.real**2 + Ra.imag**2
-    rb2 = Rb.real**2 + Rb.imag**2
-    cosb = ra2 - rb2
+    cosb = (Ra.real**2 + Ra.imag**2) - (Rb.real**2 + Rb.imag**2)
     pa = _phase_powers(Ra, 2 * L)
     pb = _phase_powers(Rb, 2 * L)
-    out = np.zeros(Ra.shape + ((ell_max + 1) ** 2,), dtype=complex)
     m = m_col
-    for mp in range(-ell_max, ell_max + 1):
-        ka, kb = mp + m, m - mp
-        ph = (pa[ka] if ka >= 0 else np.conj(pa[-ka])) * (pb[kb] if kb >= 0 else np.conj(pb[-kb]))
-        l0 = max(abs(mp), abs(m))
-        if l0 > ell_max:
-            continue
-        Pm1 = np.zeros(Ra.shape)
-        P = np.full(Ra.shape, seed[mp + L, m + L])
-        for ell in range(l0, ell_max + 1):
-            out[..., LM_index(ell, mp, 0)] = ph * P
-            if ell < ell_max:
-                a, b, c = rec[ell, mp + L, m + L]
-                P, Pm1 = (a * cosb - b) * P - c * Pm1, P
-    return out
+    mps = np.arange(-ell_max, ell_max + 1)
+    ka, kb = mps + m, m - mps
+    ph = np.where((ka >= 0)[:, None], pa[np.abs(ka)], np.conj(pa[np.abs(ka)])) * np.where(
+        (kb >= 0)[:, None], pb[np.abs(kb)], np.conj(pb[np.abs(kb)])
+    )                                                                       # [n_mp, G]
+    l0 = np.maximum(np.abs(mps), abs(m))
+    seeds = seed[mps + L, m + L]
+    out = np.zeros((Ra.shape[0], (ell_max + 1) ** 2), dtype=complex)
+    P = np.zeros((mps.shape[0], Ra.shape[0]))
+    Pm1 = np.zeros_like(P)
+    for ell in range(abs(m) if abs(m) <= ell_max else ell_max + 1, ell_max + 1):
+        start = l0 == ell
+        if start.any():
+            P[start] = seeds[start][:, None]
+        lo, hi = ell_max - ell, ell_max + ell + 1                           # rows with |mp| <= ell
+        out[:, ell * ell : (ell + 1) ** 2] = (ph[lo:hi] * P[lo:hi]).T
+        if ell < ell_max:
+            abc = rec[ell, mps + L, m + L]                                  # [n_mp, 3]; zero rows where l0 > ell
+            P, Pm1 = (abc[:, 0:1] * cosb[None, :] - abc[:, 1:2]) * P - abc[:, 2:3] * Pm1, P
+    return out.reshape(shape + ((ell_max + 1) ** 2,))
 
 
 def wigner_D_matrices(Ra, Rb, ell_min, ell_max):
@@ -178,6 +185,7 @@ def clenshaw_curtis_theta_weights(n_theta):
     return q
 
 
+@lru_cache(maxsize=32)
 def analysis_tables(s, ell_min, ell_max, n_theta, n_phi):
     """Tables for map2salm as phi-DFT + theta quadrature.
 

@@ -19,26 +19,12 @@ def is_tensor(x):
     return type(x).__module__.startswith("torch")
 
 
-_STAGE_CHUNK = 16 << 20   # bytes per pipelined host->device chunk
-_stage = {}               # device index -> [pinned uint8 buffers (double-buffered), events]
-
-
-def _staging(torch, nbytes):
-    dev = torch.cuda.current_device()
-    st = _stage.get(dev)
-    if st is None or st[0][0].numel() < nbytes:
-        bufs = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-        st = (bufs, [torch.cuda.Event(), torch.cuda.Event()])
-        _stage[dev] = st
-    return st
-
-
 def to_device(x, dtype=None):
     """numpy -> CUDA tensor (no-op for CUDA tensors).
 
-    Large arrays go through two persistent pinned staging buffers in 16 MiB chunks: the (multi-threaded) host
-    copy of chunk i+1 overlaps the DMA of chunk i, so the transfer runs at host-memcpy speed instead of the
-    pageable-copy path's ~10 GB/s.
+    Large arrays go through the library's pinned staging ring (scrib200_h2d): worker threads copy chunk i+1 into
+    pinned memory while the copy engine drains chunk i, so the transfer runs at host-memcpy / PCIe speed instead of
+    the pageable-copy path's ~10 GB/s and does not depend on the host process's BLAS / OpenMP thread pools.
     """
     torch = _torch()
     if is_tensor(x):
@@ -46,22 +32,43 @@ def to_device(x, dtype=None):
     a = np.ascontiguousarray(x)
     if dtype is not None and a.dtype != dtype:
         a = a.astype(dtype)
-    src = torch.from_numpy(a)
     if a.nbytes < (1 << 20):
-        return src.cuda()
-    out = torch.empty(src.shape, dtype=src.dtype, device="cuda")
-    src_b = src.reshape(-1).view(torch.uint8)
-    out_b = out.reshape(-1).view(torch.uint8)
-    bufs, events = _staging(torch, _STAGE_CHUNK)
-    n = a.nbytes
-    for i, off in enumerate(range(0, n, _STAGE_CHUNK)):
-        m = min(_STAGE_CHUNK, n - off)
-        b = i & 1
-        events[b].synchronize()              # the DMA that last used this staging buffer has finished
-        bufs[b][:m].copy_(src_b[off : off + m])
-        out_b[off : off + m].copy_(bufs[b][:m], non_blocking=True)
-        events[b].record()
+        return torch.from_numpy(a).cuda()
+    out = torch.empty(a.shape, dtype=getattr(torch, a.dtype.name), device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.scrib200_h2d(_lib.ptr(out), a.ctypes.data, a.nbytes, _lib.stream_ptr()), "h2d")
     return out
+
+
+_h2d_pool = None
+
+
+def to_device_async(x, dtype=None):
+    """Start `to_device(x)` on a helper thread and return a future: the staging copy is C code that does not hold the
+    GIL, so the caller can keep building host-side tables (the transformation plan) while the waveform streams in."""
+    global _h2d_pool
+    torch = _torch()
+    if is_tensor(x) or np.asarray(x).nbytes < (1 << 20):
+        class _Done:
+            def __init__(self, v):
+                self.v = v
+
+            def result(self):
+                return self.v
+
+        return _Done(to_device(x, dtype))
+    if _h2d_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _h2d_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="scrib200-h2d")
+    dev = torch.cuda.current_device()
+    stream = torch.cuda.current_stream()
+
+    def work():
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            return to_device(x, dtype)
+
+    return _h2d_pool.submit(work)
 
 
 def to_host(x):

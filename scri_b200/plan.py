@@ -194,6 +194,20 @@ def pack_synthesis_matrix(Y, ell_min, ell_max):
     return B, Kpad, Ncpad
 
 
+def _quiet_blas():
+    """The plan's host algebra is a handful of tiny matrix products; run them on one BLAS thread.  A multi-threaded
+    BLAS leaves its 16 workers spinning for tens of milliseconds after each call, which is exactly when the pinned
+    staging copy of the waveform wants the cores (measured: 3 ms -> 10 ms for 124 MB)."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=1, user_api="blas")
+    except Exception:  # threadpoolctl missing: correctness does not depend on it
+        import contextlib
+
+        return contextlib.nullcontext()
+
+
 class TransformPlan:
     """Device-resident tables for one BMS transformation of one kind of waveform.
 
@@ -202,6 +216,10 @@ class TransformPlan:
     """
 
     def __init__(self, ell_min, ell_max, dataType, r_is_scaled_out=True, out_ell_max=None, device="cuda", **kwargs):
+        with _quiet_blas():
+            self._build(ell_min, ell_max, dataType, r_is_scaled_out, out_ell_max, device, kwargs)
+
+    def _build(self, ell_min, ell_max, dataType, r_is_scaled_out, out_ell_max, device, kwargs):
         torch = _lib.require_cuda()
         _lib.load()
         self.torch = torch

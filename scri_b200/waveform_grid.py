@@ -92,12 +92,15 @@ class WaveformGrid(WaveformBase):
         if w_modes.data.ndim != 2:
             raise ValueError("scri_b200 supports two-dimensional mode data [time, mode] only")
         original_kwargs = kwargs.copy()
-        plan = TransformPlan(
-            w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out, **kwargs
-        )
+        a_fut = ops.to_device_async(w_modes.data, np.complex128)   # streams in while the plan is built
+        try:
+            plan = TransformPlan(
+                w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out, **kwargs
+            )
+        finally:
+            a_d = a_fut.result()
         t_d = ops.to_device(w_modes.t, np.float64)
-        a_d = ops.to_device(w_modes.data, np.complex128)
-        uprm, grid = plan.run(t_d, a_d, return_grid=True, t_ends=(w_modes.t[0], w_modes.t[-1]))
+        uprm, grid = plan.run(t_d, a_d, return_grid=True)
         g = cls(
             t=ops.to_host(uprm),
             data=ops.to_host(grid),
@@ -125,13 +128,16 @@ class WaveformGrid(WaveformBase):
                 f"\nInput waveform object must be in an inertial frame; this is in a frame of type `{w_modes.frame_type_string}`"
             )
         original_kwargs = kwargs.copy()
-        plan = TransformPlan(
-            w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out,
-            out_ell_max=ell_max, **kwargs,
-        )
+        a_fut = ops.to_device_async(w_modes.data, np.complex128)   # streams in while the plan is built
+        try:
+            plan = TransformPlan(
+                w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out,
+                out_ell_max=ell_max, **kwargs,
+            )
+        finally:
+            a_d = a_fut.result()
         t_d = ops.to_device(w_modes.t, np.float64)
-        a_d = ops.to_device(w_modes.data, np.complex128)
-        uprm, modes = plan.run(t_d, a_d, t_ends=(w_modes.t[0], w_modes.t[-1]))
+        uprm, modes = plan.run(t_d, a_d)
         if plan.leftover_kwargs:
             warnings.warn("\nUnused kwargs passed to this function:\n{}".format(pprint.pformat(plan.leftover_kwargs, width=1)))
         return WaveformModes(
