@@ -172,6 +172,18 @@ int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_time
                                 double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weyl-scalar mixing under a BMS transformation, elementwise over synthesized grids.
+ * Replaces  scri/waveform_grid.py:504-550,559 (psi0..psi3 <- higher Weyl scalars times powers of eth u'/k) and the
+ * Horner ladders of scri/asymptotic_bondi_data/transformations.py:340-390:
+ *   out[i,g] = scale[g] * ( sum_q coef[q] fields[q][i,g] z^q - offset[g] ),   z = (t[i] - alpha[g]) A[g] - C[g]
+ *   fields: host array of n_fields (1..5) device pointers, each [n_times, G] complex128 (fields[0] may alias out);
+ *   coef [n_fields] (host), alpha/scale [G] real, A/C/offset [G] complex128 (offset may be NULL).
+ */
+int scrib200_weyl_mix(const double* const* fields, const double* coef, int n_fields, const double* t, int64_t n_times,
+                      int G, const double* alpha, const double* A, const double* C, const double* scale,
+                      const double* offset, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill
  * chunk i+1 while the copy engine drains chunk i).  On return all of `src_host` has been read; the DMAs are ordered
  * on `stream`.  Page-locked sources are copied directly.

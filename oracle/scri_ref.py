@@ -695,3 +695,135 @@ def angular_momentum_flux(W, hdot_data=None):
     jdot[:, 2] = jz.real
     jdot /= -16.0 * np.pi
     return jdot
+
+
+# ----------------------------------------------------------------------------- waveform_modes.py:478-562
+def ladder_factor(operations, s, ell, eth_convention="NP"):
+    op_dict = {"+": +1, "-": -1, +1: +1, -1: -1}
+    convention_factor = {"NP": 1.0, "GHP": 0.5}[eth_convention]
+    ladder = 1.0
+    sign_factor = 1.0
+    for op in reversed(operations):
+        sign = op_dict[op]
+        sign_factor *= sign
+        ladder *= (ell - s * sign) * (ell + s * sign + 1.0) if (ell >= abs(s)) else 0.0
+        ladder *= convention_factor
+        s += sign
+    return sign_factor * np.sqrt(ladder)
+
+
+def apply_eth(W, operations, eth_convention="NP"):
+    s = W.spin_weight
+    mode_data = W.data.copy()
+    for ell in range(W.ell_min, W.ell_max + 1):
+        f = ladder_factor(operations, s, ell, eth_convention=eth_convention)
+        idx = [sf.LM_index(ell, m, W.ell_min) for m in range(-ell, ell + 1)]
+        mode_data[:, idx] *= f
+    return mode_data
+
+
+# ----------------------------------------------------------------------------- flux.py:444-747
+@lru_cache(maxsize=None)
+def eth_chi_z(ell_min, ell_max, s=-2):
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            cg2 = sf.clebsch_gordan(ell, -s, 1, -1, ellp, -1 - s)
+            prefac = np.sqrt((2.0 * ell + 1.0) / (2.0 * ellp + 1.0))
+            for m in range(-ell, ell + 1):
+                if (m < -ellp) or (m > ellp):
+                    continue
+                cg1 = np.sqrt(2) * sf.clebsch_gordan(ell, m, 1, 0, ellp, m)
+                out.append((ellp, m, ell, m, prefac * cg1 * cg2))
+    return _to_matrix_indices(out, ell_min)
+
+
+@lru_cache(maxsize=None)
+def ethbar_chi_z(ell_min, ell_max, s=-2):
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            cg2 = sf.clebsch_gordan(ell, -s - 1, 1, 1, ellp, -s)
+            prefac = np.sqrt((2.0 * ell + 1.0) / (2.0 * ellp + 1.0))
+            for m in range(-ell, ell + 1):
+                if (m < -ellp) or (m > ellp):
+                    continue
+                cg1 = np.sqrt(2) * sf.clebsch_gordan(ell, m, 1, 0, ellp, m)
+                out.append((ellp, m, ell, m, prefac * cg1 * cg2))
+    return _to_matrix_indices(out, ell_min)
+
+
+@lru_cache(maxsize=None)
+def eth_chi_plusminus(ell_min, ell_max, sign, s=-2):
+    prefac = -1.0 * sign * np.sqrt(8.0 * np.pi / 3.0)
+
+    def mat_el(s, l3, m3, l1, m1, l2, m2):
+        cg1 = np.sqrt(2) * sf.clebsch_gordan(l1, m1, l2, m2, l3, m3)
+        cg2 = sf.clebsch_gordan(l1, -1, l2, -s, l3, -1 - s)
+        return np.sqrt((2.0 * l1 + 1.0) * (2.0 * l2 + 1.0) / (4.0 * np.pi * (2.0 * l3 + 1))) * cg1 * cg2
+
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            for m in range(-ell, ell + 1):
+                mp = round(m + 1 * sign)
+                if (mp < -ellp) or (mp > ellp):
+                    continue
+                out.append((ellp, mp, ell, m, prefac * mat_el(s, ellp, mp, 1, sign, ell, m)))
+    return _to_matrix_indices(out, ell_min)
+
+
+@lru_cache(maxsize=None)
+def ethbar_chi_plusminus(ell_min, ell_max, sign, s=-2):
+    prefac = -1.0 * sign * np.sqrt(8.0 * np.pi / 3.0)
+
+    def mat_el(s, l3, m3, l1, m1, l2, m2):
+        cg1 = np.sqrt(2) * sf.clebsch_gordan(l1, m1, l2, m2, l3, m3)
+        cg2 = sf.clebsch_gordan(l1, 1, l2, -1 - s, l3, -s)
+        return np.sqrt((2.0 * l1 + 1.0) * (2.0 * l2 + 1.0) / (4.0 * np.pi * (2.0 * l3 + 1))) * cg1 * cg2
+
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            for m in range(-ell, ell + 1):
+                mp = round(m + 1 * sign)
+                if (mp < -ellp) or (mp > ellp):
+                    continue
+                out.append((ellp, mp, ell, m, prefac * mat_el(s, ellp, mp, 1, sign, ell, m)))
+    return _to_matrix_indices(out, ell_min)
+
+
+def boost_flux(W, hdot_data=None):
+    """flux.py:444-747 (Flanagan & Nichols 2016 eq. C.1), the 27 expectation values in the reference's order."""
+    lo, hi = W.ell_min, W.ell_max
+    Wd = replace(W, data=data_dot(W) if hdot_data is None else hdot_data, dataType=hdot)
+    h_, hd_ = W.data, Wd.data
+    eth_h, ethbar_h = apply_eth(W, "+"), apply_eth(W, "-")
+    eth_hd, ethbar_hd = apply_eth(Wd, "+"), apply_eth(Wd, "-")
+    pp = lambda s: p_plusminus(lo, hi, +1, s)
+    pm = lambda s: p_plusminus(lo, hi, -1, s)
+    pz = lambda s: p_z(lo, hi, s)
+    out = np.zeros((W.n_times, 3), dtype=float)
+    comps = {}
+    for name, P, EC, EBC in (("plus", pp, eth_chi_plusminus(lo, hi, +1, -2), ethbar_chi_plusminus(lo, hi, +1, -2)),
+                             ("minus", pm, eth_chi_plusminus(lo, hi, -1, -2), ethbar_chi_plusminus(lo, hi, -1, -2)),
+                             ("z", pz, eth_chi_z(lo, hi, -2), ethbar_chi_z(lo, hi, -2))):
+        first = (1 / 8) * (
+            _mev(ethbar_hd, P(-3), ethbar_h)
+            - _mev(eth_hd, P(-1), eth_h)
+            + 6 * _mev(hd_, P(-2), h_)
+            + _mev(ethbar_h, P(-3), ethbar_hd)
+            - _mev(eth_h, P(-1), eth_hd)
+            + 6 * _mev(h_, P(-2), hd_)
+        )
+        second = (1 / 2) * np.multiply(W.t, _mev(hd_, P(-2), hd_))
+        a_, b_ = _mev(eth_hd, EC, h_), _mev(h_, EBC, eth_hd)
+        if name == "z":
+            comps[name] = first - second + (-1 / 4) * a_ + (1 / 4) * b_
+        else:
+            comps[name] = first - second - (1 / 4) * (a_ - b_)
+    out[:, 0] = 0.5 * (comps["plus"] + comps["minus"]).real
+    out[:, 1] = 0.5 * (comps["plus"] - comps["minus"]).imag
+    out[:, 2] = comps["z"].real
+    out /= -32 * np.pi
+    return out

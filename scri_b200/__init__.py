@@ -16,7 +16,7 @@ from .waveform_grid import WaveformGrid  # noqa: F401
 from .mode_calculations import (  # noqa: F401
     LdtVector, LVector, LLMatrix, LLDominantEigenvector, angular_velocity, corotating_frame,
 )
-from .flux import energy_flux, momentum_flux, angular_momentum_flux, poincare_fluxes  # noqa: F401
+from .flux import energy_flux, momentum_flux, angular_momentum_flux, boost_flux, poincare_fluxes  # noqa: F401
 from .rotations import (  # noqa: F401
     rotate_decomposition_basis, rotate_physical_system, to_coprecessing_frame, to_corotating_frame, to_inertial_frame,
 )
@@ -31,6 +31,7 @@ WaveformModes.angular_velocity = angular_velocity
 WaveformModes.energy_flux = energy_flux
 WaveformModes.momentum_flux = momentum_flux
 WaveformModes.angular_momentum_flux = angular_momentum_flux
+WaveformModes.boost_flux = boost_flux
 WaveformModes.poincare_fluxes = poincare_fluxes
 
 __version__ = "0.1.0"

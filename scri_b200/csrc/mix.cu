@@ -1,0 +1,70 @@
+// K10: Weyl-scalar mixing under a BMS transformation (elementwise over the synthesized grid).
+//
+// Replaces scri/waveform_grid.py:504-550, 559 (psi0..psi3 pick up the higher Weyl scalars multiplied by powers of the
+// time-dependent factor  z = eth u' / k = (t - alpha) gamma k eth(v.r) - eth alpha) and the Horner ladders of
+// scri/asymptotic_bondi_data/transformations.py:340-390 (z = (eth k / k)(u - alpha) - eth alpha).  Both are
+//     out[i, g] = scale[g] * ( c_0 F_0[i,g] + c_1 F_1[i,g] z + ... + c_Q F_Q[i,g] z^Q - offset[g] ),
+//     z[i, g]   = (t[i] - alpha[g]) * A[g] - C[g]                                    (complex A, C; Q <= 4)
+// evaluated by Horner's rule from the highest field.  HBM-bound: (Q+1) reads + 1 write of 16 bytes per element; one
+// thread owns one grid point (its constants stay in registers) and walks a slab of time steps, lanes along g.
+#include "common.cuh"
+
+namespace scrib200 {
+
+struct MixFields {
+    const double2* F[5];
+    double c[5];
+};
+
+__global__ void __launch_bounds__(128)
+weyl_mix_kernel(MixFields f, int nq, const double* __restrict__ t, int64_t N, int G, const double* __restrict__ alpha,
+                const double2* __restrict__ A, const double2* __restrict__ C, const double* __restrict__ scale,
+                const double2* __restrict__ offset, double2* __restrict__ out, int rows_per_cta) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const double al = alpha[g], sc = scale[g];
+    const double2 a = A[g], c = C[g];
+    const double2 off = offset ? offset[g] : make_double2(0.0, 0.0);
+    const int64_t i0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t i1 = (i0 + rows_per_cta < N) ? i0 + rows_per_cta : N;
+    for (int64_t i = i0; i < i1; ++i) {
+        const double dt = t[i] - al;
+        const double2 z = make_double2(dt * a.x - c.x, dt * a.y - c.y);
+        const int64_t e = i * G + g;
+        double2 acc = cscale(f.c[nq - 1], f.F[nq - 1][e]);
+        for (int q = nq - 2; q >= 0; --q) {
+            acc = cmul(acc, z);
+            const double2 v = f.F[q][e];
+            acc.x = fma(f.c[q], v.x, acc.x);
+            acc.y = fma(f.c[q], v.y, acc.y);
+        }
+        out[e] = make_double2(sc * (acc.x - off.x), sc * (acc.y - off.y));
+    }
+}
+
+}  // namespace scrib200
+
+extern "C" int scrib200_weyl_mix(const double* const* fields, const double* coef, int n_fields, const double* t,
+                                 int64_t n_times, int G, const double* alpha, const double* A, const double* C,
+                                 const double* scale, const double* offset, double* out, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(fields && coef && t && alpha && A && C && scale && out, "weyl_mix: null pointer");
+    SCRIB200_REQUIRE(n_fields >= 1 && n_fields <= 5, "weyl_mix: n_fields=%d must be 1..5", n_fields);
+    SCRIB200_REQUIRE(G > 0, "weyl_mix: G=%d", G);
+    if (n_times <= 0) return SCRIB200_OK;
+    MixFields f;
+    for (int q = 0; q < 5; ++q) {
+        f.F[q] = (q < n_fields) ? reinterpret_cast<const double2*>(fields[q]) : nullptr;
+        f.c[q] = (q < n_fields) ? coef[q] : 0.0;
+        SCRIB200_REQUIRE(q >= n_fields || (fields[q] && aligned16(fields[q])), "weyl_mix: field %d is null or misaligned", q);
+    }
+    SCRIB200_REQUIRE(aligned16(A) && aligned16(C) && aligned16(out) && aligned16(offset), "weyl_mix: pointers must be 16-byte aligned");
+    const int rows = 64;
+    dim3 grid((G + 127) / 128, (unsigned)((n_times + rows - 1) / rows));
+    SCRIB200_REQUIRE(grid.y <= 65535u * 16u, "weyl_mix: series too long");
+    weyl_mix_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        f, n_fields, t, n_times, G, alpha, reinterpret_cast<const double2*>(A), reinterpret_cast<const double2*>(C), scale,
+        reinterpret_cast<const double2*>(offset), reinterpret_cast<double2*>(out), rows);
+    SCRIB200_CHECK_LAUNCH("weyl_mix");
+    return SCRIB200_OK;
+}

@@ -175,12 +175,139 @@ def angular_momentum_flux(h, hdot=None):
     return jdot
 
 
+def _ladder(operations, s, ell, eth_convention="NP"):
+    from .waveform_modes import WaveformModes
+
+    return WaveformModes.ladder_factor(None, operations, s, ell, eth_convention=eth_convention)
+
+
+def _dressed(M, ell_min, ell_max, row_op, col_op, s, scale=1.0):
+    """The matrix of <op_row a| M |op_col b> acting on the undressed modes: eth / ethbar only multiply each (l, m) mode
+    by a real ladder factor, so  <f a|M|g b> = sum conj(a_r) (f_r M_rc g_c) b_c  and the 27 expectation values of the
+    boost flux need no copies of eth h, ethbar h, ... - only matrices."""
+    rows, cols, vals = M
+    ells = np.concatenate([np.full(2 * ell + 1, ell) for ell in range(ell_min, ell_max + 1)])
+    fr = np.array([_ladder(row_op, s, int(l)) if row_op else 1.0 for l in range(ell_min, ell_max + 1)])
+    fc = np.array([_ladder(col_op, s, int(l)) if col_op else 1.0 for l in range(ell_min, ell_max + 1)])
+    return rows, cols, scale * fr[ells[rows] - ell_min] * vals * fc[ells[cols] - ell_min]
+
+
+@functools.lru_cache(maxsize=None)
+def eth_chi_z(ell_min, ell_max, s=-2):
+    """<eth N|eth chi|h>, z direction (scri/flux.py:486-505)"""
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            cg2 = clebsch_gordan(ell, -s, 1, -1, ellp, -1 - s)
+            pre = math.sqrt((2.0 * ell + 1.0) / (2.0 * ellp + 1.0))
+            for m in range(-ell, ell + 1):
+                if abs(m) > ellp:
+                    continue
+                out.append((ellp, m, ell, m, pre * math.sqrt(2) * clebsch_gordan(ell, m, 1, 0, ellp, m) * cg2))
+    return _as_matrix(out, ell_min)
+
+
+@functools.lru_cache(maxsize=None)
+def ethbar_chi_z(ell_min, ell_max, s=-2):
+    """<h|ethbar chi|eth N>, z direction (scri/flux.py:507-526)"""
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            cg2 = clebsch_gordan(ell, -s - 1, 1, 1, ellp, -s)
+            pre = math.sqrt((2.0 * ell + 1.0) / (2.0 * ellp + 1.0))
+            for m in range(-ell, ell + 1):
+                if abs(m) > ellp:
+                    continue
+                out.append((ellp, m, ell, m, pre * math.sqrt(2) * clebsch_gordan(ell, m, 1, 0, ellp, m) * cg2))
+    return _as_matrix(out, ell_min)
+
+
+@functools.lru_cache(maxsize=None)
+def _chi_plusminus(ell_min, ell_max, sign, s, bar):
+    if sign not in (1, -1):
+        raise ValueError("sign must be either 1 or -1 in eth_chi_plusminus")
+    prefac = -1.0 * sign * math.sqrt(8.0 * math.pi / 3.0)
+    out = []
+    for ell in range(ell_min, ell_max + 1):
+        for ellp in range(max(ell_min, ell - 1), min(ell_max, ell + 1) + 1):
+            for m in range(-ell, ell + 1):
+                mp = m + sign
+                if abs(mp) > ellp:
+                    continue
+                cg1 = math.sqrt(2) * clebsch_gordan(1, sign, ell, m, ellp, mp)
+                cg2 = clebsch_gordan(1, 1, ell, -1 - s, ellp, -s) if bar else clebsch_gordan(1, -1, ell, -s, ellp, -1 - s)
+                el = math.sqrt(3.0 * (2.0 * ell + 1.0) / (4.0 * math.pi * (2.0 * ellp + 1))) * cg1 * cg2
+                out.append((ellp, mp, ell, m, prefac * el))
+    return _as_matrix(out, ell_min)
+
+
+def eth_chi_plusminus(ell_min, ell_max, sign, s=-2):
+    """<eth N|eth chi|h>, m = +-1 (scri/flux.py:528-568)"""
+    return _chi_plusminus(ell_min, ell_max, sign, s, False)
+
+
+def ethbar_chi_plusminus(ell_min, ell_max, sign, s=-2):
+    """<h|ethbar chi|eth N>, m = +-1 (scri/flux.py:575-615)"""
+    return _chi_plusminus(ell_min, ell_max, sign, s, True)
+
+
+def boost_flux(h, hdot=None):
+    """Boost flux, Flanagan & Nichols (2016) eq. C.1 (scri/flux.py:444-747).
+
+    The reference evaluates 27 `matrix_expectation_value`s on six copies of the data (h, eth h, ethbar h and the same
+    for hdot).  Here the ladder factors are folded into the sparse matrices and the terms are grouped by operand pair,
+    so the modes are read in three fused passes: <hdot|.|h> (15 matrices), <h|.|hdot> (12) and <hdot|.|hdot> (3).
+    """
+    from .waveform_modes import WaveformModes
+
+    if not isinstance(h, WaveformModes):
+        raise ValueError(f"Boost fluxes can only be calculated from a `WaveformModes` object; `h` is of type `{type(h)}`.")
+    if (hdot is not None) and (not isinstance(hdot, WaveformModes)):
+        raise ValueError(f"Boost fluxes can only be calculated from a `WaveformModes` object; `hdot` is of type `{type(hdot)}`.")
+    if h.dataType != htype:
+        raise ValueError(f"Input argument `h` is expected to have data of type `h`; this `h` waveform data has type `{h.data_type_string}`")
+    if hdot is None:
+        hdot_data = h.data_dot
+    elif hdot.dataType != hdottype:
+        raise ValueError(f"Input argument `hdot` is expected to have data of type `hdot`; this `hdot` waveform data has type `{h.data_type_string}`")
+    else:
+        hdot_data = hdot.data
+    lo, hi = h.ell_min, h.ell_max
+    s = -2
+    comps = []
+    for P, EC, EBC in (
+        (functools.partial(p_plusminus, lo, hi, +1), eth_chi_plusminus(lo, hi, +1, s), ethbar_chi_plusminus(lo, hi, +1, s)),
+        (functools.partial(p_plusminus, lo, hi, -1), eth_chi_plusminus(lo, hi, -1, s), ethbar_chi_plusminus(lo, hi, -1, s)),
+        (functools.partial(p_z, lo, hi), eth_chi_z(lo, hi, s), ethbar_chi_z(lo, hi, s)),
+    ):
+        comps.append(dict(
+            nh=[_dressed(P(s=-3), lo, hi, "-", "-", s), _dressed(P(s=-1), lo, hi, "+", "+", s), P(s=-2), _dressed(EC, lo, hi, "+", "", s)],
+            hn=[_dressed(P(s=-3), lo, hi, "-", "-", s), _dressed(P(s=-1), lo, hi, "+", "+", s), P(s=-2), _dressed(EBC, lo, hi, "", "+", s)],
+            nn=[P(s=-2)],
+        ))
+    ev_nh = ops.sparse_expectation(hdot_data, h.data, [m for c in comps for m in c["nh"]])      # <hdot| . |h>
+    ev_hn = ops.sparse_expectation(h.data, hdot_data, [m for c in comps for m in c["hn"]])      # <h| . |hdot>
+    ev_nn = ops.sparse_expectation(hdot_data, hdot_data, [m for c in comps for m in c["nn"]])   # <hdot| . |hdot>
+    t = np.asarray(h.t)
+    total = []
+    for i in range(3):
+        nh, hn = ev_nh[:, 4 * i : 4 * i + 4], ev_hn[:, 4 * i : 4 * i + 4]
+        first = (1 / 8) * (nh[:, 0] - nh[:, 1] + 6 * nh[:, 2] + hn[:, 0] - hn[:, 1] + 6 * hn[:, 2])
+        total.append(first - (1 / 2) * t * ev_nn[:, i] - (1 / 4) * (nh[:, 3] - hn[:, 3]))
+    out = np.zeros((h.n_times, 3), dtype=float)
+    out[:, 0] = 0.5 * (total[0] + total[1]).real
+    out[:, 1] = 0.5 * (total[0] - total[1]).imag
+    out[:, 2] = total[2].real
+    out /= -32 * np.pi
+    return out
+
+
 def poincare_fluxes(h, hdot=None):
-    """(energy, momentum, angular-momentum) fluxes with one time derivative (scri/flux.py:750-797, without boost)."""
+    """(energy, momentum, angular-momentum, boost) fluxes with one time derivative (scri/flux.py:750-797)."""
     from .waveform_modes import WaveformModes
 
     if hdot is None:
         hdot = h.copy()
         hdot.dataType = hdottype
         hdot.data = h.data_dot
-    return (energy_flux(hdot), momentum_flux(hdot), angular_momentum_flux(h, hdot))
+    return (energy_flux(hdot), momentum_flux(hdot), angular_momentum_flux(h, hdot), boost_flux(h, hdot))

@@ -257,6 +257,7 @@ class TransformPlan:
         self.kconformal = 1.0 / (gamma * (1 - rhat @ boost_velocity))
         self.alpha = (SH @ supertranslation).real
         offset_c = np.zeros(self.G, dtype=complex)
+        self.mix = []          # higher Weyl scalars mixed into psi0..psi3 (empty for every other data type)
         nontrivial = beta != 0 or (supertranslation[1:] != 0).any()
         if nontrivial:
             nst = (ell_max_st + 1) ** 2
@@ -269,23 +270,47 @@ class TransformPlan:
                 fac = _ell_factors(nst, lambda l: 0.5 * math.sqrt(max((l - 1) * l * (l + 1) * (l + 2), 0)))
                 offset_c = Y[:, :nst] @ (supertranslation * fac)
             elif self.dataType in (psi0, psi1, psi2, psi3):
-                raise NotImplementedError(
-                    f"BMS transformation of {DataNames[self.dataType]} (mixing with higher Weyl scalars, "
-                    "scri/waveform_grid.py:504-550) is not implemented in scri_b200 yet"
-                )
+                # psi_n picks up the higher Weyl scalars times powers of eth u'/k (waveform_grid.py:504-550):
+                #   f' = f + sum_{DT>dt} C(5-dt, 5-DT) f_DT z^(DT-dt),  z = (t - alpha) gamma k eth(v.r) - eth(alpha)
+                SW1 = _sf.SWSH_grid(R, 1, ell_max_st)
+                fac1 = _ell_factors((ell_max_st + 1) ** 2, lambda l: math.sqrt(l * (l + 1) / 2.0))      # eth_GHP on s = 0
+                eth_alpha = SW1 @ ((1 / math.sqrt(2)) * (supertranslation * fac1))
+                c1, c0 = math.sqrt(2 * math.pi / 3), math.sqrt(4 * math.pi / 3)
+                v = boost_velocity
+                v_modes = np.array([0.0, c1 * (v[0] + 1j * v[1]), c0 * v[2], c1 * (-v[0] + 1j * v[1])], dtype=complex)
+                eth_v_dot_rhat = _sf.SWSH_grid(R, 1, 1) @ ((1 / math.sqrt(2)) * v_modes)
+                self.mix_A = gamma * self.kconformal * eth_v_dot_rhat
+                self.mix_C = eth_alpha
+                from scipy.special import comb
+
+                for DT in range(self.dataType + 1, psi4 + 1):
+                    key = "psi{}_modes".format(DataNames[DT][-1])
+                    if key not in leftover:
+                        raise ValueError(
+                            "\nA BMS transformation of {} requires information from {}, which "
+                            "has not been supplied.".format(DataNames[self.dataType], DataNames[DT])
+                        )
+                    w_temp = leftover.pop(key)
+                    Yt = _sf.SWSH_grid(R, w_temp.spin_weight, w_temp.ell_max)
+                    Bt, Kp, Np = pack_synthesis_matrix(Yt, w_temp.ell_min, w_temp.ell_max)
+                    self.mix.append(dict(
+                        coef=float(comb(5 - self.dataType, 5 - DT)), data=w_temp.data, n_modes=w_temp.data.shape[1], Kpad=Kp,
+                        Ncpad=Np, d_B=torch.from_numpy(Bt).to(self.device),
+                    ))
             elif self.dataType not in (psi4, hdot, news):
                 warnings.warn(
                     f"\nNo BMS transformation is implemented for waveform objects of dataType '{DataNames[self.dataType]}'. "
                     "Proceeding with the transformation as if it were dataType 'Psi4'."
                 )
         scale = self.kconformal**self.conformal_weight
+        self.scale = scale
         B, self.Kpad, self.Ncpad = pack_synthesis_matrix(Y, self.ell_min, self.ell_max)
         off = np.zeros(self.Ncpad)
         off[0 : 2 * self.G : 2] = offset_c.real
         off[1 : 2 * self.G : 2] = offset_c.imag
         scl = np.zeros(self.Ncpad)
-        scl[0 : 2 * self.G : 2] = scale
-        scl[1 : 2 * self.G : 2] = scale
+        scl[0 : 2 * self.G : 2] = 1.0 if self.mix else scale     # with mixing the weight k^w is applied after the sum
+        scl[1 : 2 * self.G : 2] = 1.0 if self.mix else scale
         self.time_translation = (supertranslation[0] / math.sqrt(4 * math.pi)).real
         E, Wt = _sf.analysis_tables(s, self.out_ell_min, self.out_ell_max, n_theta, n_phi)
         self.n_modes_in = _sf.LM_total_size(self.ell_min, self.ell_max)
@@ -296,6 +321,13 @@ class TransformPlan:
         self.d_B = torch.from_numpy(B).to(dev)
         self.d_offset = torch.from_numpy(off).to(dev)
         self.d_scale = torch.from_numpy(scl).to(dev)
+        if self.mix:
+            self.d_unit = torch.zeros(self.Ncpad, dtype=f64, device=dev)
+            self.d_unit[: 2 * self.G] = 1.0
+            self.d_zero = torch.zeros(self.Ncpad, dtype=f64, device=dev)
+            self.d_mixA = torch.from_numpy(np.ascontiguousarray(self.mix_A)).to(dev)
+            self.d_mixC = torch.from_numpy(np.ascontiguousarray(self.mix_C)).to(dev)
+            self.d_mixscale = torch.from_numpy(np.ascontiguousarray(scale)).to(dev)
         self.d_k = torch.from_numpy(np.ascontiguousarray(self.kconformal)).to(dev)
         self.d_alpha = torch.from_numpy(np.ascontiguousarray(self.alpha)).to(dev)
         self.d_E = torch.from_numpy(np.ascontiguousarray(E)).to(dev)
@@ -323,8 +355,11 @@ class TransformPlan:
         return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
     # -- the individual stages (device tensors in, device tensors out) ---------------------------
-    def synthesize(self, data):
-        """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-503,559)."""
+    def synthesize(self, data, t=None):
+        """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-559).  `t` (device) is needed for
+        psi0..psi3 only, whose mixing factor depends on time."""
+        import ctypes
+
         torch = self.torch
         lib = _lib.load()
         N = data.shape[0]
@@ -335,6 +370,36 @@ class TransformPlan:
                 _lib.ptr(self.d_scale), self.G, _lib.ptr(F), _lib.stream_ptr(),
             ),
             "swsh_synthesize",
+        )
+        if not self.mix:
+            return F
+        if t is None:
+            raise ValueError("TransformPlan.synthesize needs the time axis for psi0..psi3")
+        from . import ops
+
+        fields, coefs = [F], [1.0]
+        for mx in self.mix:
+            d = ops.to_device(mx["data"], np.complex128)
+            if d.shape[0] != N:
+                raise ValueError("psi*_modes must share the time axis of the waveform being transformed")
+            Fq = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
+            _lib.check(
+                lib.scrib200_swsh_synthesize(
+                    _lib.ptr(d), N, mx["n_modes"], _lib.ptr(mx["d_B"]), mx["Kpad"], mx["Ncpad"], _lib.ptr(self.d_zero),
+                    _lib.ptr(self.d_unit), self.G, _lib.ptr(Fq), _lib.stream_ptr(),
+                ),
+                "swsh_synthesize",
+            )
+            fields.append(Fq)
+            coefs.append(mx["coef"])
+        ptrs = (ctypes.c_void_p * len(fields))(*[f.data_ptr() for f in fields])
+        cf = (ctypes.c_double * len(coefs))(*coefs)
+        _lib.check(
+            lib.scrib200_weyl_mix(
+                ptrs, cf, len(fields), _lib.ptr(t), N, self.G, _lib.ptr(self.d_alpha), _lib.ptr(self.d_mixA),
+                _lib.ptr(self.d_mixC), _lib.ptr(self.d_mixscale), None, _lib.ptr(F), _lib.stream_ptr(),
+            ),
+            "weyl_mix",
         )
         return F
 
@@ -414,7 +479,7 @@ class TransformPlan:
         their time axis."""
         if prep is None:
             prep = self.prepare(t)
-        F = self.synthesize(data)
+        F = self.synthesize(data, t)
         uprm = prep.uprm
         if self.tile and not return_grid:
             gridT = self.remap_tiled(t, F, uprm, prep)

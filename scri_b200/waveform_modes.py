@@ -90,6 +90,52 @@ class WaveformModes(WaveformBase):
         return [self.index(ell, m) for ell, m in args]
 
     # ------------------------------------------------------------------ BMS transformation
+    def ladder_factor(self, operations, s, ell, eth_convention="NP"):
+        """Factor a sequence of eth ('+', +1, 'ð') / ethbar ('-', -1, 'ð̅') operations, applied right to left, puts on
+        the spin-s mode of degree ell (scri/waveform_modes.py:478-520)."""
+        op_dict = {"ð": +1, "ð̅": -1, "+": +1, "-": -1, +1: +1, -1: -1}
+        conv_dict = {"NP": 1.0, "GHP": 0.5}
+        if isinstance(operations, str):
+            operations = operations.replace("ð̅", "-").replace("ð", "+")
+        keys = op_dict.keys()
+        key_strings = {key for key in keys if isinstance(key, str)}
+        if not set(operations).issubset(keys):
+            raise ValueError(
+                "operations must be a string composed of {} or a list with elements coming from the set {}".format(key_strings, set(keys))
+            )
+        if eth_convention not in conv_dict:
+            raise ValueError("eth_convention must be one of {}".format(set(conv_dict.keys())))
+        convention_factor = conv_dict[eth_convention]
+        ladder = 1.0
+        sign_factor = 1.0
+        for op in reversed(operations):
+            sign = op_dict[op]
+            sign_factor *= sign
+            ladder *= (ell - s * sign) * (ell + s * sign + 1.0) if (ell >= abs(s)) else 0.0
+            ladder *= convention_factor
+            s += sign
+        return sign_factor * np.sqrt(ladder)
+
+    def apply_eth(self, operations, eth_convention="NP"):
+        """Mode data with the spin raising / lowering operators applied (scri/waveform_modes.py:522-562): a per-ell
+        scale of the columns; the (ell, m) layout is unchanged."""
+        s = self.spin_weight
+        fac = np.concatenate([
+            np.full(2 * ell + 1, self.ladder_factor(operations, s, ell, eth_convention=eth_convention))
+            for ell in range(self.ell_min, self.ell_max + 1)
+        ])
+        return self.data * fac[None, :]
+
+    @property
+    def eth(self):
+        """Spin-raised mode data (scri/waveform_modes.py:564-567)."""
+        return self.apply_eth(operations="+")
+
+    @property
+    def ethbar(self):
+        """Spin-lowered mode data (scri/waveform_modes.py:569-572)."""
+        return self.apply_eth(operations="-")
+
     def transform(self, **kwargs):
         """Apply a BMS transformation; returns a new WaveformModes (scri/waveform_modes.py:705-719).
 

@@ -130,6 +130,25 @@ def test_transform_vs_oracle(dataType, uniform):
     assert rel(out.data, ref.data) < RTOL
 
 
+@pytest.mark.parametrize("dataType", [sb.psi0, sb.psi1, sb.psi2, sb.psi3])
+def test_transform_weyl_scalars_vs_oracle(dataType):
+    """psi0..psi3 mix with every higher Weyl scalar under supertranslations and boosts (scri/waveform_grid.py:504-550)."""
+    t = np.linspace(-10.0, 100.0, 400)
+    ws, wo = {}, {}
+    for DT in range(dataType, sb.psi4 + 1):
+        s = sb.SpinWeights[DT]
+        _, d = smooth_modes(n_times=400, ell_min=abs(s), seed=40 + DT)
+        ws[DT] = modes(t, d, ell_min=abs(s), dataType=DT)
+        wo[DT] = R.Modes(t=t, data=d.copy(), ell_min=abs(s), dataType=DT)
+    extra = {"psi{}_modes".format(sb.DataNames[DT][-1]): ws[DT] for DT in range(dataType + 1, sb.psi4 + 1)}
+    extra_o = {"psi{}_modes".format(sb.DataNames[DT][-1]): wo[DT] for DT in range(dataType + 1, sb.psi4 + 1)}
+    out = ws[dataType].transform(**BMS, **extra)
+    ref = R.transform(wo[dataType], **BMS, **extra_o)
+    assert np.array_equal(out.t, ref.t)
+    assert out.dataType == dataType and out.ell_min == abs(sb.SpinWeights[dataType])
+    assert rel(out.data, ref.data) < RTOL
+
+
 def test_transform_golden_fixture():
     g = np.load(os.path.join(GOLD, "transform_small.npz"))
     w = modes(g["t"], g["data"])
@@ -208,8 +227,8 @@ def test_edge_cases():
     out = modes(t, data, dataType=sb.psi4).transform(supertranslation=big)
     ref = R.transform(R.Modes(t=t, data=data.copy(), dataType=R.psi4), supertranslation=big) if False else None
     assert out.n_times <= t.size
-    with pytest.raises(NotImplementedError):
-        modes(t, data[:, : 80 - 4] if False else np.zeros((64, 80), complex), ell_min=1, ell_max=8, dataType=sb.psi1).transform(boost_velocity=[0.1, 0, 0])
+    with pytest.raises(ValueError, match="requires information from Psi2"):     # waveform_grid.py:529
+        modes(t, np.zeros((64, 80), complex), ell_min=1, ell_max=8, dataType=sb.psi1).transform(boost_velocity=[0.1, 0, 0])
 
 
 # ------------------------------------------------------------------ full-size properties (config 2)
@@ -304,6 +323,27 @@ def test_spline_strongly_nonuniform_steps():
         assert rel(ops.spline_calculus(tn, dn, "derivative", 1), CubicSpline(tn, dn).derivative()(tn)) < 1e-11
 
 
+def test_boost_flux_and_eth_vs_oracle():
+    """boost_flux (scri/flux.py:444-747, 27 expectation values in the reference) and apply_eth (waveform_modes.py:478-562)"""
+    t, data = smooth_modes(n_times=300, seed=17)
+    w = modes(t, data)
+    Wo = R.Modes(t=t, data=data.copy())
+    for ops_ in ("+", "-", "+-", "--", "-+"):
+        assert rel(w.apply_eth(ops_), R.apply_eth(Wo, ops_)) < 1e-15
+        assert rel(w.apply_eth(ops_, eth_convention="GHP"), R.apply_eth(Wo, ops_, "GHP")) < 1e-15
+    assert np.array_equal(w.eth, w.apply_eth("+")) and np.array_equal(w.ethbar, w.apply_eth("-"))
+    ref = R.boost_flux(Wo)
+    assert rel(w.boost_flux(), ref) < 1e-11
+    hd = w.copy()
+    hd.dataType = sb.hdot
+    hd.data = w.data_dot
+    assert rel(w.boost_flux(hd), ref) < 1e-11
+    E, p, J, B = w.poincare_fluxes()
+    assert rel(B, ref) < 1e-11 and rel(E, R.energy_flux(Wo)) < 1e-12
+    with pytest.raises(ValueError):
+        hd.boost_flux()
+
+
 def test_dominant_eigenvector_and_angular_velocity_physics():
     """reference tests/test_mode_calculations.py:14-126 (simple cases)"""
     t = np.linspace(0.0, 20.0, 2001)
@@ -342,9 +382,10 @@ def test_full_size_fluxes_config5_slice():
     N = 100_000
     t, data = smooth_modes(n_times=N, ell_max=16, t0=0.0, t1=1e4, seed=31)
     w = modes(t, data, ell_max=16)
-    E, p, J = w.poincare_fluxes()
+    E, p, J, Bst = w.poincare_fluxes()
     w2 = modes(t, 2.0 * data, ell_max=16)
-    E2, p2, J2 = w2.poincare_fluxes()
+    E2, p2, J2, Bst2 = w2.poincare_fluxes()
+    assert np.allclose(Bst2, 4 * Bst, rtol=1e-11, atol=1e-12 * abs(Bst).max())
     assert np.allclose(E2, 4 * E, rtol=1e-13) and np.allclose(p2, 4 * p, rtol=1e-12, atol=1e-14) and np.allclose(J2, 4 * J, rtol=1e-12, atol=1e-14)
     assert (E >= 0).all()
     lo, hi = 40_000, 41_000

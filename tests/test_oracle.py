@@ -157,6 +157,29 @@ def test_rotation_inverse_and_invariants():
         assert np.allclose(W.data, data, rtol=0, atol=5e-14)
 
 
+def test_boost_flux_is_a_vector_like_the_momentum_flux():
+    """The reference has no test for boost_flux (scri/flux.py:444-747): pin the restatement through covariance - under
+    a constant rotation of the decomposition basis the boost flux must turn with the same orthogonal matrix as the
+    momentum flux and the angular-momentum flux - and through its u-dependence: shifting the time origin by T adds
+    T/4 times the momentum flux (the -(u/2)<N|chi|N> term of Flanagan & Nichols C.1 over -32 pi against <N|chi|N>/16 pi)."""
+    t, data = smooth_modes(n_times=120, seed=3)
+    W = R.Modes(t=t, data=data.copy())
+    hd = R.data_dot(W)
+    B0, p0, J0 = R.boost_flux(W, hd), R.momentum_flux(R.Modes(t=t, data=hd, dataType=R.hdot)), R.angular_momentum_flux(W, hd)
+    for Rq in rotor_set(3)[-3:]:
+        Wr, Wd = R.Modes(t=t, data=data.copy()), R.Modes(t=t, data=hd.copy(), dataType=R.hdot)
+        R.rotate_decomposition_basis(Wr, Rq)
+        R.rotate_decomposition_basis(Wd, Rq)
+        p1, J1, B1 = R.momentum_flux(Wd), R.angular_momentum_flux(Wr, Wd.data), R.boost_flux(Wr, Wd.data)
+        M = np.linalg.lstsq(p0, p1, rcond=None)[0]                 # p1 = p0 @ M
+        assert np.allclose(M @ M.T, np.eye(3), atol=1e-12)
+        assert np.allclose(J0 @ M, J1, rtol=0, atol=1e-12 * abs(J0).max())
+        assert np.allclose(B0 @ M, B1, rtol=0, atol=1e-12 * abs(B0).max())
+    T = 37.5
+    Bs = R.boost_flux(R.Modes(t=t + T, data=data.copy()), hd)
+    assert np.allclose(Bs, B0 + 0.25 * T * p0, rtol=0, atol=1e-12 * abs(Bs).max())
+
+
 def test_LL_and_angular_velocity_of_rotating_mode():
     """reference tests/test_mode_calculations.py:14-126 (simple cases): a (2,2)+(2,-2) mode rotating about z
     with frequency w has dominant axis z and angular velocity (0,0,w)."""
