@@ -74,7 +74,9 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  * scrib200_spline_prepare (once per time axis): the knots of all grid points are affine images of t, so the
  * tridiagonal moment system is factorised once, in t-units:
  *   tab  [n_times, 8]  (P, Q, W, 1/h, Phi, c', Psi, h) per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
- *   uprm [n_times]     u'_i for every input sample (may be NULL together with kconf/alpha: tables only)
+ *   uprm [n_times]     u'_i = gamma_factor * (t_i - time_translation) (divide = 0, gamma_factor = 1/gamma: the
+ *                      WaveformGrid arithmetic) or (t_i - time_translation) / gamma_factor (divide = 1, gamma_factor =
+ *                      gamma: scri/asymptotic_bondi_data/transformations.py:393); may be NULL together with kconf/alpha
  *   info [8] (device)  [0] lo, [1] hi: the retained block is uprm[lo:hi];  [2], [3]: worst decay of the spline
  *                      recurrences over any 32 / 64 consecutive rows (choose halo = 32 if [2] <= 1e-15, else 64 if
  *                      [3] <= 1e-15, else 128);  [4], [5]: u'min, u'max
@@ -89,7 +91,7 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *   tile.  A CTA keeps its tile of F in shared memory; F is read once.
  */
 size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int halo, int body);
-int scrib200_spline_prepare(const double* t, int64_t n_times, double inv_gamma, double time_translation,
+int scrib200_spline_prepare(const double* t, int64_t n_times, double gamma_factor, int divide, double time_translation,
                             const double* kconf, const double* alpha, int G, double* tab, double* uprm, double* info,
                             void* stream);
 int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
@@ -182,6 +184,10 @@ int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_time
 int scrib200_weyl_mix(const double* const* fields, const double* coef, int n_fields, const double* t, int64_t n_times,
                       int G, const double* alpha, const double* A, const double* C, const double* scale,
                       const double* offset, double* out, void* stream);
+
+/* out[e] = a[e] * b[e] for n complex128 elements: the pointwise product of ModesTimeSeries.grid_multiply
+ * (scri/modes_time_series.py:190). */
+int scrib200_grid_product(const double* a, const double* b, double* out, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill

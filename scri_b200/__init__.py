@@ -21,6 +21,7 @@ from .rotations import (  # noqa: F401
     rotate_decomposition_basis, rotate_physical_system, to_coprecessing_frame, to_corotating_frame, to_inertial_frame,
 )
 from . import sample_waveforms  # noqa: F401
+from .asymptotic_bondi_data import AsymptoticBondiData, ModesTimeSeries  # noqa: F401
 
 # operators attached to the class, as scri/__init__.py:125-150 does
 WaveformModes.LdtVector = LdtVector

@@ -42,7 +42,27 @@ weyl_mix_kernel(MixFields f, int nq, const double* __restrict__ t, int64_t N, in
     }
 }
 
+// out[e] = a[e] * b[e] (complex), the pointwise product of ModesTimeSeries.grid_multiply (modes_time_series.py:190).
+__global__ void __launch_bounds__(256)
+grid_product_kernel(const double2* __restrict__ a, const double2* __restrict__ b, double2* __restrict__ out, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = cmul(a[e], b[e]);
+}
+
 }  // namespace scrib200
+
+extern "C" int scrib200_grid_product(const double* a, const double* b, double* out, int64_t n, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(a && b && out, "grid_product: null pointer");
+    SCRIB200_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "grid_product: pointers must be 16-byte aligned");
+    if (n <= 0) return SCRIB200_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    grid_product_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), reinterpret_cast<double2*>(out), n);
+    SCRIB200_CHECK_LAUNCH("grid_product");
+    return SCRIB200_OK;
+}
 
 extern "C" int scrib200_weyl_mix(const double* const* fields, const double* coef, int n_fields, const double* t,
                                  int64_t n_times, int G, const double* alpha, const double* A, const double* C,

@@ -77,7 +77,7 @@ __device__ __forceinline__ void nak_row(const double* __restrict__ t, int N, int
 // u'_i = inv_gamma (t_i - tt) and the retained output block [lo, hi) = { i : umin <= u'_i <= umax }
 // (waveform_grid.py:564-568), umin/umax reduced here from k (t_0 - alpha), k (t_{N-1} - alpha) over the G grid points.
 __global__ void __launch_bounds__(256)
-spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ tab, double inv_gamma, double tt,
+spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ tab, double inv_gamma, int divide, double tt,
                      const double* __restrict__ kconf, const double* __restrict__ alpha, int G,
                      double* __restrict__ uprm, double* __restrict__ info) {
     __shared__ double s_red[2][8];
@@ -107,10 +107,12 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
             umax = fmin(umax, s_red[1][w]);
         }
         if (i < N) {
-            const double u = __dmul_rn(inv_gamma, __dsub_rn(t[i], tt));
+            // waveform_grid.py:565 multiplies by 1/gamma, transformations.py:393 divides by gamma: both are reproduced
+            const double u = divide ? __ddiv_rn(__dsub_rn(t[i], tt), inv_gamma) : __dmul_rn(inv_gamma, __dsub_rn(t[i], tt));
             uprm[i] = u;
             // u' is non-decreasing: exactly one i starts / ends the retained block
-            const double up_prev = (i > 0) ? __dmul_rn(inv_gamma, __dsub_rn(t[i - 1], tt)) : -CUDART_INF;
+            double up_prev = -CUDART_INF;
+            if (i > 0) up_prev = divide ? __ddiv_rn(__dsub_rn(t[i - 1], tt), inv_gamma) : __dmul_rn(inv_gamma, __dsub_rn(t[i - 1], tt));
             if (u >= umin && !(up_prev >= umin)) info[0] = (double)i;          // lo: first u' >= umin
             if (u > umax && !(up_prev > umax)) info[1] = (double)i;            // hi: first u' >  umax
             if (i == 0) {
@@ -548,7 +550,7 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
 
 }  // namespace scrib200
 
-extern "C" int scrib200_spline_prepare(const double* t, int64_t n_times, double inv_gamma, double time_translation,
+extern "C" int scrib200_spline_prepare(const double* t, int64_t n_times, double gamma_factor, int divide, double time_translation,
                                        const double* kconf, const double* alpha, int G, double* tab, double* uprm,
                                        double* info, void* stream) {
     using namespace scrib200;
@@ -561,7 +563,7 @@ extern "C" int scrib200_spline_prepare(const double* t, int64_t n_times, double 
     // seed info in stream order (lo = hi = N means "empty / not found")
     spline_info_init_kernel<<<1, 32, 0, st>>>(info, (double)n_times);
     const unsigned blocks = (unsigned)((n_times + 255) / 256);
-    spline_factor_kernel<<<blocks, 256, 0, st>>>(t, (int)n_times, tab, inv_gamma,
+    spline_factor_kernel<<<blocks, 256, 0, st>>>(t, (int)n_times, tab, gamma_factor, divide,
                                                  time_translation, kconf, alpha, G, uprm, info);
     SCRIB200_CHECK_LAUNCH("spline_prepare(factor)");
     spline_decay_kernel<<<blocks, 256, 0, st>>>(tab, (int)n_times, info);

@@ -147,6 +147,94 @@ def map2salm(grid, s, ell_max, n_theta=None, n_phi=None, ell_min=0):
     return out if is_tensor(grid) else to_host(out)
 
 
+_analysis_cache = {}
+
+
+def _analysis_device_tables(s, ell_min, ell_max, n_theta, n_phi):
+    """(E, Wt, trig) of scri_b200._sf.analysis_tables on the current device, cached per (spin, ell range, grid)."""
+    torch = _torch()
+    key = (s, ell_min, ell_max, n_theta, n_phi, torch.cuda.current_device())
+    if key not in _analysis_cache:
+        E, Wt = _sf.analysis_tables(s, ell_min, ell_max, n_theta, n_phi)
+        trig = np.ascontiguousarray(np.conj(E[:, ell_max:]))
+        _analysis_cache[key] = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (E, Wt, trig))
+    return _analysis_cache[key]
+
+
+def map2salm_tiled_device(gridT, tile, n_out, s, ell_max, n_theta, n_phi, ell_min=0):
+    """Analysis of a time-tiled device grid [ceil(n_out/tile), G, tile] (the layout scrib200_spline_remap writes)."""
+    torch = _torch()
+    lib = _lib.load()
+    _, dW, dtrig = _analysis_device_tables(s, ell_min, ell_max, n_theta, n_phi)
+    out = torch.empty((n_out, _sf.LM_total_size(ell_min, ell_max)), dtype=torch.complex128, device="cuda")
+    _lib.check(
+        lib.scrib200_map2salm_tiled(_lib.ptr(gridT), tile, n_out, n_theta, n_phi, _lib.ptr(dtrig), _lib.ptr(dW), ell_min, ell_max,
+                                    _lib.ptr(out), _lib.stream_ptr()),
+        "map2salm_tiled",
+    )
+    return out
+
+
+_synth_cache = {}
+
+
+def _regular_grid_synthesis_matrix(s, ell_min, ell_max, n_theta, n_phi):
+    """Packed synthesis operand for the regular (theta, phi) grid of spinsfast (theta inclusive, phi half open)."""
+    from .plan import pack_synthesis_matrix
+
+    torch = _torch()
+    key = (s, ell_min, ell_max, n_theta, n_phi, torch.cuda.current_device())
+    if key not in _synth_cache:
+        theta = np.linspace(0.0, np.pi, n_theta)
+        phi = np.linspace(0.0, 2 * np.pi, n_phi, endpoint=False)
+        th, ph = np.meshgrid(theta, phi, indexing="ij")
+        R = Q.from_spherical_coords(th.ravel(), ph.ravel())
+        Y = _sf.SWSH_grid(R, s, ell_max)
+        B, Kpad, Ncpad = pack_synthesis_matrix(Y, ell_min, ell_max)
+        unit = np.zeros(Ncpad)
+        unit[: 2 * n_theta * n_phi] = 1.0
+        _synth_cache[key] = (torch.from_numpy(B).cuda(), Kpad, Ncpad, torch.from_numpy(unit).cuda(), torch.zeros(Ncpad, dtype=torch.float64, device="cuda"))
+    return _synth_cache[key]
+
+
+def salm2map(salm, s, ell_max, n_theta, n_phi, ell_min=0):
+    """spinsfast.salm2map replacement, batched over time: [N, n_modes] -> [N, n_theta, n_phi] (device tensor in ->
+    device tensor out).  Dense synthesis GEMM on the FP64 tensor cores (scrib200_swsh_synthesize)."""
+    torch = _torch()
+    lib = _lib.load()
+    d = to_device(salm, np.complex128)
+    dB, Kpad, Ncpad, unit, zero = _regular_grid_synthesis_matrix(s, ell_min, ell_max, n_theta, n_phi)
+    N, G = d.shape[0], n_theta * n_phi
+    F = torch.empty((N, G), dtype=torch.complex128, device="cuda")
+    _lib.check(
+        lib.scrib200_swsh_synthesize(_lib.ptr(d), N, d.shape[1], _lib.ptr(dB), Kpad, Ncpad, _lib.ptr(zero), _lib.ptr(unit), G, _lib.ptr(F),
+                                     _lib.stream_ptr()),
+        "swsh_synthesize",
+    )
+    F = F.reshape(N, n_theta, n_phi)
+    return F if is_tensor(salm) else to_host(F)
+
+
+def grid_multiply(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, working_ell_max, slab_bytes=2 << 30):
+    """Modes (from ell = 0 to working_ell_max) of the pointwise product of two mode series
+    (scri/modes_time_series.py:142-202): salm2map x 2 -> product -> map2salm with spin sa + sb, in slabs of time."""
+    torch = _torch()
+    lib = _lib.load()
+    N = a.shape[0]
+    G = n_theta * n_phi
+    n_out = (working_ell_max + 1) ** 2
+    out = np.empty((N, n_out), dtype=complex)
+    slab = max(1, min(N, int(slab_bytes // (16 * G * 3))))
+    for i0 in range(0, N, slab):
+        i1 = min(N, i0 + slab)
+        ga = salm2map(to_device(a[i0:i1], np.complex128), sa, a_ell_max, n_theta, n_phi, ell_min=a_ell_min)
+        gb = salm2map(to_device(b[i0:i1], np.complex128), sb, b_ell_max, n_theta, n_phi, ell_min=b_ell_min)
+        _lib.check(lib.scrib200_grid_product(_lib.ptr(ga), _lib.ptr(gb), _lib.ptr(ga), ga.numel(), _lib.stream_ptr()), "grid_product")
+        del gb
+        out[i0:i1] = to_host(map2salm(ga.reshape(i1 - i0, G), sa + sb, working_ell_max, n_theta, n_phi, ell_min=0))
+    return out
+
+
 def norm(data):
     """sum_modes |a|^2 per time step (scri/waveform_base.py:19-35)."""
     lib = _lib.load()
@@ -174,7 +262,7 @@ def spline_tables(tt):
     tab = torch.empty((N, 8), dtype=torch.float64, device="cuda")
     info = torch.empty(8, dtype=torch.float64, device="cuda")
     _lib.check(
-        lib.scrib200_spline_prepare(_lib.ptr(tt), N, 1.0, 0.0, None, None, 0, _lib.ptr(tab), None, _lib.ptr(info), _lib.stream_ptr()),
+        lib.scrib200_spline_prepare(_lib.ptr(tt), N, 1.0, 0, 0.0, None, None, 0, _lib.ptr(tab), None, _lib.ptr(info), _lib.stream_ptr()),
         "spline_prepare",
     )
     v = info.tolist()

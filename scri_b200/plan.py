@@ -17,6 +17,34 @@ from . import _quaternion as Q
 from .constants import ConformalWeights, DataNames, RScaling, SpinWeights, h, hdot, news, psi0, psi1, psi2, psi3, psi4, sigma
 
 
+def boosted_rotor_grid(frame_rotation, boost_velocity, n_theta, n_phi):
+    """Rotors of the output (theta', phi') grid carried back to the input frame, R = B'(theta, phi) R_frame R_{theta'phi'}
+    (scri/waveform_grid.py:130-174 and scri/asymptotic_bondi_data/transformations.py:100-148), vectorised.
+    Returns (R_j_k [n_theta, n_phi, 4], thetaprm_phiprm [n_theta, n_phi, 2])."""
+    beta = np.linalg.norm(boost_velocity)
+    varphi = math.atanh(beta)
+    thetaprm = np.linspace(0.0, np.pi, num=n_theta, endpoint=True)
+    phiprm = np.linspace(0.0, 2 * np.pi, num=n_phi, endpoint=False)
+    thetaprm_j_phiprm_k = np.stack(np.meshgrid(thetaprm, phiprm, indexing="ij"), axis=-1)
+    rotated = Q.qmul(frame_rotation, Q.from_spherical_coords(thetaprm_j_phiprm_k[..., 0], thetaprm_j_phiprm_k[..., 1]))
+    if beta > 3e-14:
+        vhat = boost_velocity / beta
+        th, ph = Q.as_spherical_coords(rotated)
+        rprm = np.stack([np.cos(ph) * np.sin(th), np.sin(ph) * np.sin(th), np.cos(th)], axis=-1)
+        Thetaprm = np.arccos(np.clip(rprm @ vhat, -1.0, 1.0))
+        Theta = 2 * np.arctan(math.exp(-varphi) * np.tan(Thetaprm / 2.0))
+        cross = np.cross(rprm, vhat)
+        cn = np.sqrt(np.sum(cross * cross, axis=-1))
+        safe = cn > 1e-200
+        nhat = np.where(safe[..., None], cross / np.where(safe, cn, 1.0)[..., None], 0.0)
+        B = Q.qexp_vec(nhat * ((Thetaprm - Theta) / 2)[..., None])
+        B[~safe] = np.array([1.0, 0.0, 0.0, 0.0])
+        R_j_k = Q.qmul(B, rotated)
+    else:
+        R_j_k = rotated
+    return R_j_k, thetaprm_j_phiprm_k
+
+
 def process_transformation_kwargs(ell_max, **kwargs):
     """Parse the BMS-transformation keywords (scri/waveform_grid.py:20-190).
 
@@ -125,27 +153,7 @@ def process_transformation_kwargs(ell_max, **kwargs):
     gamma = 1 / math.sqrt(1 - beta**2)
     varphi = math.atanh(beta)
 
-    thetaprm = np.linspace(0.0, np.pi, num=n_theta, endpoint=True)
-    phiprm = np.linspace(0.0, 2 * np.pi, num=n_phi, endpoint=False)
-    thetaprm_j_phiprm_k = np.stack(np.meshgrid(thetaprm, phiprm, indexing="ij"), axis=-1)
-
-    # rotors of the output grid carried back to the input frame: R = B'(theta,phi) * R_frame * R_{theta',phi'}
-    rotated = Q.qmul(frame_rotation, Q.from_spherical_coords(thetaprm_j_phiprm_k[..., 0], thetaprm_j_phiprm_k[..., 1]))
-    if beta > 3e-14:
-        vhat = boost_velocity / beta
-        th, ph = Q.as_spherical_coords(rotated)
-        rprm = np.stack([np.cos(ph) * np.sin(th), np.sin(ph) * np.sin(th), np.cos(th)], axis=-1)
-        Thetaprm = np.arccos(np.clip(rprm @ vhat, -1.0, 1.0))
-        Theta = 2 * np.arctan(math.exp(-varphi) * np.tan(Thetaprm / 2.0))
-        cross = np.cross(rprm, vhat)
-        cn = np.sqrt(np.sum(cross * cross, axis=-1))
-        safe = cn > 1e-200
-        nhat = np.where(safe[..., None], cross / np.where(safe, cn, 1.0)[..., None], 0.0)
-        B = Q.qexp_vec(nhat * ((Thetaprm - Theta) / 2)[..., None])
-        B[~safe] = np.array([1.0, 0.0, 0.0, 0.0])
-        R_j_k = Q.qmul(B, rotated)
-    else:
-        R_j_k = rotated
+    R_j_k, thetaprm_j_phiprm_k = boosted_rotor_grid(frame_rotation, boost_velocity, n_theta, n_phi)
 
     return (
         supertranslation,
@@ -208,7 +216,110 @@ def _quiet_blas():
         return contextlib.nullcontext()
 
 
-class TransformPlan:
+class GridPlan:
+    """What every transformation shares once the rotor grid is fixed: the conformal factor and supertranslation on the
+    grid (device arrays `d_k`, `d_alpha`), the output time axis, and the spline remap / analysis launches."""
+
+    divide_by_gamma = False   # u' = (1/gamma)(t - dt) as in waveform_grid.py:565; the ABD path divides by gamma instead
+
+    def _init_grid(self, device, n_theta, n_phi, gamma, time_translation, kconformal, alpha):
+        torch = _lib.require_cuda()
+        _lib.load()
+        self.torch = torch
+        self.device = torch.device(device)
+        self.n_theta, self.n_phi = int(n_theta), int(n_phi)
+        self.G = self.n_theta * self.n_phi
+        self.gamma = gamma
+        self.time_translation = time_translation
+        self.kconformal, self.alpha = kconformal, alpha
+        self.d_k = torch.from_numpy(np.ascontiguousarray(kconformal)).to(self.device)
+        self.d_alpha = torch.from_numpy(np.ascontiguousarray(alpha)).to(self.device)
+        self._ws = None
+        self._side = None
+        self._host_pool = []
+        self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
+        self.spline_body = 0   # 0 = default intervals per tile
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = self.torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _info_host(self):
+        """A pinned 64-byte landing buffer for `info` (recycled: no allocation in steady state)."""
+        if self._host_pool:
+            return self._host_pool.pop()
+        return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
+
+    def prepare(self, t):
+        """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
+        the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`."""
+        return TimePrep(self, t)
+
+    def output_times(self, t, t_ends=None):
+        """u'_i and the retained block (waveform_grid.py:564-568) as a device tensor.  `t_ends` is accepted for
+        backward compatibility and ignored (the block is found on the device)."""
+        return self.prepare(t).uprm
+
+    def _remap(self, t, F, uprm, prep, tile):
+        torch = self.torch
+        lib = _lib.load()
+        if prep is None:
+            prep = self.prepare(t)
+        N, n_out = t.shape[0], uprm.shape[0]
+        if tile:
+            out = torch.empty((-(-n_out // tile), self.G, tile), dtype=torch.complex128, device=self.device)
+        else:
+            out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
+        halo, body = prep.halo_body(self.spline_halo, self.spline_body)
+        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(
+            lib.scrib200_spline_remap(
+                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
+                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.ptr(self._ws), self._ws.numel(),
+                _lib.stream_ptr(),
+            ),
+            "spline_remap",
+        )
+        return out
+
+    def remap(self, t, F, uprm, prep=None):
+        """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588); [N', G]."""
+        return self._remap(t, F, uprm, prep, 0)
+
+    def synthesize_with(self, data, d_B, n_modes, Kpad, Ncpad, d_offset, d_scale):
+        """One scrib200_swsh_synthesize launch: [N, n_modes] complex128 -> [N, G]."""
+        torch = self.torch
+        N = data.shape[0]
+        F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
+        _lib.check(
+            _lib.load().scrib200_swsh_synthesize(
+                _lib.ptr(data), N, n_modes, _lib.ptr(d_B), Kpad, Ncpad, _lib.ptr(d_offset), _lib.ptr(d_scale), self.G,
+                _lib.ptr(F), _lib.stream_ptr(),
+            ),
+            "swsh_synthesize",
+        )
+        return F
+
+    def weyl_mix(self, fields, coefs, t, d_A, d_C, d_scale, d_offset, out):
+        """One scrib200_weyl_mix launch (see include/scrib200.h)."""
+        import ctypes
+
+        ptrs = (ctypes.c_void_p * len(fields))(*[f.data_ptr() for f in fields])
+        cf = (ctypes.c_double * len(coefs))(*[float(c) for c in coefs])
+        _lib.check(
+            _lib.load().scrib200_weyl_mix(
+                ptrs, cf, len(fields), _lib.ptr(t), t.shape[0], self.G, _lib.ptr(self.d_alpha), _lib.ptr(d_A), _lib.ptr(d_C),
+                _lib.ptr(d_scale), _lib.ptr(d_offset) if d_offset is not None else None, _lib.ptr(out), _lib.stream_ptr(),
+            ),
+            "weyl_mix",
+        )
+        return out
+
+
+class TransformPlan(GridPlan):
     """Device-resident tables for one BMS transformation of one kind of waveform.
 
     Built from the same quantities scri/waveform_grid.py:431-474 computes on the host (rotor grid,
@@ -343,18 +454,6 @@ class TransformPlan:
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
         self.spline_body = 0   # 0 = default intervals per tile
 
-    def _side_stream(self):
-        if self._side is None:
-            self._side = self.torch.cuda.Stream(device=self.device)
-        return self._side
-
-    def _info_host(self):
-        """A pinned 64-byte landing buffer for `info` (recycled: no allocation in steady state)."""
-        if self._host_pool:
-            return self._host_pool.pop()
-        return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
-
-    # -- the individual stages (device tensors in, device tensors out) ---------------------------
     def synthesize(self, data, t=None):
         """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-559).  `t` (device) is needed for
         psi0..psi3 only, whose mixing factor depends on time."""
@@ -402,44 +501,6 @@ class TransformPlan:
             "weyl_mix",
         )
         return F
-
-    def prepare(self, t):
-        """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
-        the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`."""
-        return TimePrep(self, t)
-
-    def output_times(self, t, t_ends=None):
-        """u'_i and the retained block (waveform_grid.py:564-568) as a device tensor.  `t_ends` is accepted for
-        backward compatibility and ignored (the block is found on the device)."""
-        return self.prepare(t).uprm
-
-    def _remap(self, t, F, uprm, prep, tile):
-        torch = self.torch
-        lib = _lib.load()
-        if prep is None:
-            prep = self.prepare(t)
-        N, n_out = t.shape[0], uprm.shape[0]
-        if tile:
-            out = torch.empty((-(-n_out // tile), self.G, tile), dtype=torch.complex128, device=self.device)
-        else:
-            out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
-        halo, body = prep.halo_body(self.spline_halo, self.spline_body)
-        need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        _lib.check(
-            lib.scrib200_spline_remap(
-                _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
-                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.ptr(self._ws), self._ws.numel(),
-                _lib.stream_ptr(),
-            ),
-            "spline_remap",
-        )
-        return out
-
-    def remap(self, t, F, uprm, prep=None):
-        """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588); [N', G]."""
-        return self._remap(t, F, uprm, prep, 0)
 
     def analyze(self, grid):
         """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307)."""
@@ -508,7 +569,8 @@ class TimePrep:
         self.info = torch.empty(8, dtype=torch.float64, device=plan.device)
         _lib.check(
             lib.scrib200_spline_prepare(
-                _lib.ptr(t), N, 1 / plan.gamma, plan.time_translation, _lib.ptr(plan.d_k), _lib.ptr(plan.d_alpha), plan.G,
+                _lib.ptr(t), N, plan.gamma if plan.divide_by_gamma else 1 / plan.gamma, int(plan.divide_by_gamma),
+                plan.time_translation, _lib.ptr(plan.d_k), _lib.ptr(plan.d_alpha), plan.G,
                 _lib.ptr(self.tab), _lib.ptr(self.uprm_full), _lib.ptr(self.info), _lib.stream_ptr(),
             ),
             "spline_prepare",

@@ -393,3 +393,86 @@ def test_full_size_fluxes_config5_slice():
     assert rel(E[lo + 200 : hi - 200], R.energy_flux(Wo)[200:-200]) < 1e-11
     assert rel(p[lo + 200 : hi - 200], R.momentum_flux(Wo)[200:-200]) < 1e-11
     assert rel(J[lo + 200 : hi - 200], R.angular_momentum_flux(Wo)[200:-200]) < 1e-11
+
+
+# ------------------------------------------------------------------ AsymptoticBondiData, grid_multiply (a23, a24)
+def _random_abd(ell_max=4, n_times=240, seed=11):
+    from oracle import abd_ref as A
+
+    rng = np.random.default_rng(seed)
+    u = np.linspace(-10.0, 30.0, n_times)
+    n = (ell_max + 1) ** 2
+    data = {}
+    for name, s in A.SPINS.items():
+        c = rng.normal(size=n) + 1j * rng.normal(size=n)
+        w = rng.uniform(0.05, 0.5, size=n)
+        d = 0.1 * c[None, :] * np.exp(1j * w[None, :] * u[:, None])
+        d[:, : s * s] = 0.0                                   # no modes below |s|
+        data[name] = d
+    mine = sb.AsymptoticBondiData(u, ell_max)
+    for name in A.FIELDS:
+        setattr(mine, name, data[name])
+    return mine, A.ABD(u, ell_max, {k: v.copy() for k, v in data.items()})
+
+
+@pytest.mark.parametrize("kw", [
+    dict(supertranslation=real_supertranslation(2, seed=9), frame_rotation=[1.0, 2.0, 3.0, 4.0], boost_velocity=[0.01, 0.02, 0.03]),
+    dict(boost_velocity=[0.0, 0.05, -0.02]),
+    dict(time_translation=1.5, frame_rotation=[0.3, -0.4, 0.5, 0.7]),
+    dict(space_translation=np.array([0.1, -0.2, 0.3]), output_ell_max=3, working_ell_max=9),
+])
+def test_abd_transform_vs_oracle(kw):
+    """All six fields through scri/asymptotic_bondi_data/transformations.py:199-431 (Horner ladders in eth u'/k)."""
+    from oracle import abd_ref as A
+
+    mine, ref = _random_abd()
+    out = mine.transform(**kw)
+    exp = A.transform(ref, **kw)
+    assert np.array_equal(out.u, exp.u)                       # output time grid: bit-exact ((u - dt) / gamma, masked)
+    assert out.ell_max == exp.ell_max
+    for name in A.FIELDS:
+        assert rel(getattr(out, name).ndarray, exp.data[name]) < RTOL, name
+
+
+def test_abd_schwarzschild_boost_and_charges():
+    """reference tests/test_asymptoticbondidata.py:96-117 on the GPU path"""
+    import math
+
+    mass, ell_max = 1.0, 4
+    u = np.linspace(0, 100, num=200)
+    abd = sb.AsymptoticBondiData(u, ell_max)
+    psi2 = np.zeros((ell_max + 1) ** 2, complex)
+    psi2[0] = -mass * math.sqrt(4 * math.pi)
+    abd.psi2 = psi2
+    assert np.allclose(abd.bondi_rest_mass(), mass, atol=1e-14)
+    for v in [np.array([0.1, 0.0, 0.0]), np.array([0.0, 0.1, 0.0]), np.array([0.0, 0.0, 0.1])]:
+        gamma = 1 / np.sqrt(1 - v @ v)
+        abdprime = abd.transform(boost_velocity=v)
+        assert np.allclose(abdprime.bondi_four_momentum(), mass * gamma * np.array([1, *-v]), atol=1e-13, rtol=1e-13)
+        assert np.allclose(abdprime.bondi_rest_mass(), mass, atol=1e-13)
+
+
+def test_grid_multiply_and_modes_time_series_vs_oracle():
+    """scri/modes_time_series.py:72-202"""
+    from oracle import abd_ref as A
+    from scipy.interpolate import CubicSpline
+
+    mine, ref = _random_abd(ell_max=5, n_times=150, seed=3)
+    sig, p3 = mine.sigma, mine.psi3
+    prod = sig.grid_multiply(p3)
+    assert prod.spin_weight == 1 and prod.ell_max == 5
+    assert rel(prod.ndarray, A.grid_multiply(ref.data["sigma"], 2, ref.data["psi3"], -1)) < RTOL
+    prod2 = sig.grid_multiply(sig.bar, working_ell_max=12, output_ell_max=7)
+    assert prod2.spin_weight == 0 and prod2.ell_max == 7
+    assert rel(prod2.ndarray, A.grid_multiply(ref.data["sigma"], 2, A.modes_bar(ref.data["sigma"], 2), -2, working_ell_max=12, output_ell_max=7)) < RTOL
+    assert rel(sig.bar.ndarray, A.modes_bar(ref.data["sigma"], 2)) == 0.0
+    assert rel(sig.dot.ndarray, CubicSpline(ref.u, ref.data["sigma"]).derivative()(ref.u)) < 1e-11
+    assert rel(sig.int.ndarray, CubicSpline(ref.u, ref.data["sigma"]).antiderivative()(ref.u)) < 1e-12
+    tn = np.linspace(ref.u[3], ref.u[-3], 77)
+    assert rel(mine.interpolate(tn).psi1.ndarray, CubicSpline(ref.u, ref.data["psi1"])(tn)) < 1e-12
+    assert rel(mine.psi2.eth_GHP.ndarray, A.modes_eth(ref.data["psi2"], 0) / np.sqrt(2)) < 1e-15
+    # salm2map alone against the restated spinsfast
+    from oracle import spinsfast as ospf
+
+    g = ops.salm2map(ref.data["psi3"][:20], -1, 5, 13, 13)
+    assert rel(g, ospf.salm2map(ref.data["psi3"][:20], -1, 5, 13, 13)) < 1e-13

@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from oracle import quat, scri_ref as R, sf, spinsfast as spf
+from oracle import abd_ref as A, quat, scri_ref as R, sf, spinsfast as spf
 from scri_inputs import real_supertranslation, rotor_set, smooth_modes
 
 
@@ -178,6 +178,47 @@ def test_boost_flux_is_a_vector_like_the_momentum_flux():
     T = 37.5
     Bs = R.boost_flux(R.Modes(t=t + T, data=data.copy()), hd)
     assert np.allclose(Bs, B0 + 0.25 * T * p0, rtol=0, atol=1e-12 * abs(Bs).max())
+
+
+def test_abd_schwarzschild_transform():
+    """reference tests/test_asymptoticbondidata.py:96-117: a boosted Schwarzschild ABD has four-momentum M gamma (1, -v)."""
+    mass, ell_max = 1.0, 4
+    u = np.linspace(0, 100, num=80)
+    psi2 = np.zeros((ell_max + 1) ** 2, complex)
+    psi2[0] = -mass * math.sqrt(4 * math.pi)                # kerr_schild(mass, 0, ell_max)[0]
+    abd = A.ABD(u, ell_max, {"psi2": psi2})
+    assert np.allclose(A.bondi_four_momentum(abd), [mass, 0, 0, 0], atol=1e-14)
+    for v in [np.array([0.1, 0.0, 0.0]), np.array([0.0, 0.1, 0.0]), np.array([0.0, 0.0, 0.1])]:
+        gamma = 1 / np.sqrt(1 - v @ v)
+        p = A.bondi_four_momentum(A.transform(abd, boost_velocity=v))
+        assert np.allclose(p, mass * gamma * np.array([1, *-v]), atol=1e-14, rtol=1e-14)
+        assert np.allclose(np.sqrt(p[:, 0] ** 2 - np.sum(p[:, 1:] ** 2, axis=1)), mass, atol=1e-14)
+
+
+def test_abd_shear_against_WaveformModes_strain():
+    """reference tests/test_asymptoticbondidata.py:165-214: a general BMS transformation of an ABD's shear equals the
+    transformation of the strain h = 2 bar(sigma) as a WaveformModes object (two independent code paths of the reference)."""
+    rng = np.random.default_rng(123)
+    ell_max = 4
+    u = np.linspace(-10, 10, num=200)
+    n = (ell_max + 1) ** 2
+    c = 0.01 * (rng.uniform(size=(3, n)) - 0.5 + 1j * (rng.uniform(size=(3, n)) - 0.5))
+    c[:, :4] = 0
+    sigma = c[0][None, :] + 0.02 * c[1][None, :] * u[:, None] + 0.003 * c[2][None, :] * u[:, None] ** 2
+    abd = A.ABD(u, ell_max, {"sigma": sigma})
+    h = R.Modes(t=u, data=(2 * A.modes_bar(sigma, 2))[:, 4:], ell_min=2, ell_max=ell_max)
+    alpha = real_supertranslation(ell_max, seed=5, scale=1e-2)
+    Rq = quat.normalized(rng.normal(size=4))
+    v = 0.01 * (rng.uniform(size=3) - 0.5)
+    abdp = A.transform(abd, supertranslation=alpha, frame_rotation=Rq, boost_velocity=v)
+    hp = R.transform(h, supertranslation=alpha, frame_rotation=Rq, boost_velocity=v)
+    t = hp.t[(hp.t >= abdp.u[0]) & (hp.t <= abdp.u[-1])]
+    from scipy.interpolate import CubicSpline
+
+    a = CubicSpline(hp.t, hp.data)(t)
+    b = CubicSpline(abdp.u, 2 * A.modes_bar(abdp.data["sigma"], 2))(t)[:, 4:]
+    assert t.size > 150
+    assert np.allclose(a, b, atol=4e-12, rtol=4e-12)
 
 
 def test_LL_and_angular_velocity_of_rotating_mode():
