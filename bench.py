@@ -250,9 +250,10 @@ def run_ours(args):
         # same calls as TransformPlan.run(), with events between the stages
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        prep = plan.prepare(t_d)        # spline factor table, u', retained block: 3 tiny kernels, read back on a side stream
-        ev[1].record()
         F = plan.synthesize(a_d)
+        ev[1].record()
+        prep = plan.prepare(t_d, overlapped=True, after=ev[0])   # spline factor table, u', retained block: 4 tiny kernels on a
+        torch.cuda.current_stream().wait_event(prep.done)        # side stream, running under the synthesis GEMM
         ev[2].record()
         up = prep.uprm
         if plan.tile:
@@ -328,12 +329,12 @@ def run_ours(args):
         remap_bytes = 32.0 * G * N          # read F (16 G) + write grid' (16 G) per time step
         ana_bytes = (16.0 * G + 16.0 * n_modes) * n_out
         kern = {
-            "spline_prepare(factor table, u', retained block)": {"ms": per_kernel[0]},
-            "swsh_synth_dmma": {"ms": per_kernel[1], "bound": "tensor(fp64)", "achieved_tflops": synth_flops / (per_kernel[1] * 1e-3) / 1e12},
+            "swsh_synth_dmma": {"ms": per_kernel[0], "bound": "tensor(fp64)", "achieved_tflops": synth_flops / (per_kernel[0] * 1e-3) / 1e12},
+            "spline_prepare(factor table, u', retained block; side stream, overlapped with the synthesis)": {"ms_exposed_on_main_stream": per_kernel[1]},
             "spline_tile(spline_remap)": {"ms": per_kernel[2], "bound": "hbm", "achieved_gbs": remap_bytes / (per_kernel[2] * 1e-3) / 1e9},
             "map2salm_tiled": {"ms": per_kernel[3], "bound": "hbm", "achieved_gbs": ana_bytes / (per_kernel[3] * 1e-3) / 1e9},
         }
-        if per_kernel[2] >= per_kernel[1]:
+        if per_kernel[2] >= per_kernel[0]:
             ach = kern["spline_tile(spline_remap)"]["achieved_gbs"]
             roof = {"kernel": "spline_tile_kernel<0>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
@@ -370,7 +371,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-times", type=int, default=100_000)

@@ -379,6 +379,191 @@ map2salm_dmma_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_t
     }
 }
 
+// ---- persistent DMMA kernel: one CTA per SM walks the time tiles with two tile buffers in shared memory, so the TMA
+// bulk load of tile i+1 flies under the arithmetic of tile i, and the tables are set up once per CTA instead of once
+// per 8 time steps.  Both contractions run on the FP64 tensor cores:
+//   phi-DFT   (as map2salm_dmma_kernel): M = (Re/Im part, t), K = k, N = trig columns;
+//   theta quadrature, per m:  a[(l, m), (t, part)] = sum_j W[(l, m), j] f_m[t][j][part]:  M = l (rows of Wt, read through
+//   L1), K = j, N = t for the Re and the Im tile - the B fragment of both is one 16-byte load of f_m(theta_j) from the
+//   buffer the DFT results were written to (which is the tile buffer itself, after a barrier).
+template <int NT>
+__global__ void __launch_bounds__(640, 1)
+map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_theta, int n_phi,
+                        const double2* __restrict__ trig, const double* __restrict__ Wt, int ell_min, int ell_max,
+                        double2* __restrict__ out) {
+    constexpr int T = 8;
+    constexpr int BP = 16 * NT + 8;
+    extern __shared__ __align__(128) double2 smp[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int L = ell_max, nm = 2 * L + 1, np1 = L + 1;
+    const int G = n_theta * n_phi;
+    const int KS = (n_phi + 3) / 4, KQ = (n_theta + 3) / 4;
+    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    const size_t tile_elems = (size_t)G * T;
+    const size_t buf_elems = (size_t)(G + 4) * T;
+    double2* sBuf[2] = {smp, smp + buf_elems};
+    double* sB = reinterpret_cast<double*>(smp + 2 * buf_elems);             // [4 KS][BP]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const int64_t ntiles = (n_times + T - 1) / T;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double2));
+
+    auto issue = [&](int64_t tile, int b) {   // thread 0 only
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[b])), "r"(tile_bytes) : "memory");
+        const char* src = reinterpret_cast<const char*>(gridT + tile * (int64_t)tile_elems);
+        char* dst = reinterpret_cast<char*>(sBuf[b]);
+        for (unsigned off = 0; off < tile_bytes; off += 32768u) {
+            const unsigned n = (tile_bytes - off < 32768u) ? (tile_bytes - off) : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(dst + off)),
+                         "l"(src + off), "r"(n), "r"(smem_u32(&mbar[b]))
+                         : "memory");
+        }
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+        if ((int64_t)blockIdx.x + gridDim.x < ntiles) issue((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    for (int b = 0; b < 2; ++b)
+        for (int i = tid; i < 4 * T; i += nt) sBuf[b][tile_elems + i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < 4 * KS * BP; i += nt) {
+        const int k = i / BP, n = i - k * BP;
+        double v = 0.0;
+        if (k < n_phi && n < 16 * NT) {
+            const int m = (n % (8 * NT)) + 1;
+            if (m <= L) {
+                const double2 cs = trig[k * np1 + m];
+                v = (n < 8 * NT) ? cs.x : cs.y;
+            }
+        }
+        sB[i] = v;
+    }
+    __syncthreads();
+    const int tq = lane >> 2, kk = lane & 3;
+    const double inv_nphi = trig[0].x;
+    const int MT = (L - ell_min + 8) / 8;                                    // 8-row blocks of l for the longest m column
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const unsigned parity = (unsigned)((it >> 1) & 1);
+        {
+            unsigned ok = 0;
+            while (!ok) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok)
+                             : "r"(smem_u32(&mbar[b])), "r"(parity)
+                             : "memory");
+            }
+        }
+        const double2* sTile = sBuf[b];
+        double2* sFm = sBuf[b];                                              // [T][nm][n_theta] after the barrier
+        // ---- phi-DFT: rings warp, warp + nwarp
+        double acc[2][2][2 * NT][2];
+        double s0[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            s0[r][0] = s0[r][1] = 0.0;
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int n = 0; n < 2 * NT; ++n) acc[r][p][n][0] = acc[r][p][n][1] = 0.0;
+            const int j = warp + r * nwarp;
+            if (j < n_theta) {
+                const double2* arow = sTile + ((size_t)j * n_phi + kk) * T + tq;
+                const double* brow = sB + kk * BP + tq;
+#pragma unroll 2
+                for (int ks = 0; ks < KS; ++ks) {
+                    double2 a = arow[(size_t)ks * 4 * T];
+                    if (ks == KS - 1 && 4 * ks + kk >= n_phi) a = make_double2(0.0, 0.0);   // K padding: next ring's samples
+                    s0[r][0] += a.x;
+                    s0[r][1] += a.y;
+#pragma unroll
+                    for (int n = 0; n < 2 * NT; ++n) {
+                        const double bv = brow[ks * 4 * BP + n * 8];
+                        dmma884(acc[r][0][n][0], acc[r][0][n][1], a.x, bv);
+                        dmma884(acc[r][1][n][0], acc[r][1][n][1], a.y, bv);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    s0[r][p] += __shfl_xor_sync(0xffffffffu, s0[r][p], 1);
+                    s0[r][p] += __shfl_xor_sync(0xffffffffu, s0[r][p], 2);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done reading the tile: f_m(theta_j) may overwrite it
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = warp + r * nwarp;
+            if (j < n_theta) {
+                double2* frow = sFm + (size_t)tq * nm * n_theta + j;       // + mi * n_theta
+                if (kk == 0) frow[(size_t)L * n_theta] = make_double2(s0[r][0] * inv_nphi, s0[r][1] * inv_nphi);
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int m = n * 8 + 2 * kk + i + 1;
+                        if (m <= L) {
+                            const double P1 = acc[r][0][n][i], P4 = acc[r][0][NT + n][i];
+                            const double P3 = acc[r][1][n][i], P2 = acc[r][1][NT + n][i];
+                            frow[(size_t)(L + m) * n_theta] = make_double2(P1 + P2, P3 - P4);
+                            frow[(size_t)(L - m) * n_theta] = make_double2(P1 - P2, P3 + P4);
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- theta quadrature on the tensor cores: units (mi, 8-row block of l)
+        const int64_t t0 = tile * T;
+        for (int unit = warp; unit < nm * MT; unit += nwarp) {
+            const int mi = unit / MT, mt = unit - mi * MT;
+            const int m = mi - L;
+            const int am = m < 0 ? -m : m;
+            const int lstart = (am > ell_min ? am : ell_min) + 8 * mt;
+            if (lstart > L) continue;
+            const int la = lstart + tq;                                      // my row of the A fragment
+            const bool rowok = la <= L;
+            const double* wrow = Wt + (size_t)(la * (la + 1) - ell_min * ell_min + m) * n_theta;
+            const double2* fcol = sFm + ((size_t)tq * nm + mi) * n_theta;    // B fragment: column t = tq, rows j
+            double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
+#pragma unroll 2
+            for (int kq = 0; kq < KQ; ++kq) {
+                const int jj = 4 * kq + kk;
+                const bool jok = jj < n_theta;
+                const double av = (rowok && jok) ? __ldg(wrow + jj) : 0.0;
+                const double2 bv = jok ? fcol[jj] : make_double2(0.0, 0.0);
+                dmma884(cre[0], cre[1], av, bv.x);
+                dmma884(cim[0], cim[1], av, bv.y);
+            }
+            if (rowok) {
+                const int lm = la * (la + 1) - ell_min * ell_min + m;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int64_t tt = t0 + 2 * kk + i;
+                    if (tt < n_times) out[tt * n_modes + lm] = make_double2(cre[i], cim[i]);
+                }
+            }
+        }
+        __syncthreads();   // the buffer is free again
+        if (tid == 0) {
+            const int64_t nxt = tile + 2 * (int64_t)gridDim.x;
+            if (nxt < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (f_m) before the async-proxy refill
+                issue(nxt, b);
+            }
+        }
+    }
+}
+
+static size_t persist_smem(int n_theta, int n_phi, int NT) {
+    const size_t KS = (n_phi + 3) / 4;
+    return 2 * ((size_t)n_theta * n_phi + 4) * 8 * sizeof(double2) + 4 * KS * (16 * NT + 8) * sizeof(double);
+}
+
 static size_t dmma_smem(int n_theta, int n_phi, int ell_min, int ell_max, int NT) {
     const size_t n_modes = (size_t)ell_max * (ell_max + 2) - (size_t)ell_min * ell_min + 1;
     const size_t KS = (n_phi + 3) / 4;
@@ -476,6 +661,32 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
         const int nwarp = (n_theta + 1) / 2;
         const size_t smem_d = dmma_smem(n_theta, n_phi, ell_min, ell_max, NT);
         const bool disabled = getenv("SCRIB200_ANALYSIS_SCALAR") != nullptr;
+        const size_t smem_p = persist_smem(n_theta, n_phi, NT);
+        if (!disabled && !getenv("SCRIB200_ANALYSIS_NONPERSISTENT") && T == 8 && ell_max >= 1 && NT <= 2 && nwarp <= 20 &&
+            2 * ell_max + 1 <= n_phi && 2 * ell_max + 1 <= n_theta + 0 * n_phi && smem_p <= 225 * 1024) {
+            static int n_sm = 0;
+            if (n_sm == 0) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            }
+            const int64_t ntiles = (n_times + T - 1) / T;
+            const unsigned blocks = (unsigned)(ntiles < n_sm ? ntiles : n_sm);
+            const int threads = 32 * (nwarp < 4 ? 4 : nwarp);
+            if (NT == 1) {
+                cudaFuncSetAttribute(map2salm_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+                map2salm_persist_kernel<1><<<blocks, threads, smem_p, (cudaStream_t)stream>>>(
+                    reinterpret_cast<const double2*>(gridT), n_times, n_theta, n_phi, reinterpret_cast<const double2*>(trig), Wt,
+                    ell_min, ell_max, reinterpret_cast<double2*>(out));
+            } else {
+                cudaFuncSetAttribute(map2salm_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+                map2salm_persist_kernel<2><<<blocks, threads, smem_p, (cudaStream_t)stream>>>(
+                    reinterpret_cast<const double2*>(gridT), n_times, n_theta, n_phi, reinterpret_cast<const double2*>(trig), Wt,
+                    ell_min, ell_max, reinterpret_cast<double2*>(out));
+            }
+            SCRIB200_CHECK_LAUNCH("map2salm_tiled(persistent dmma)");
+            return SCRIB200_OK;
+        }
         if (!disabled && T == 8 && ell_max >= 1 && NT <= 2 && nwarp <= 20 && 2 * ell_max + 1 <= n_phi && smem_d <= 200 * 1024) {
             const int64_t blocks = (n_times + T - 1) / T;
             const int threads = 32 * (nwarp < 4 ? 4 : nwarp);

@@ -251,10 +251,13 @@ class GridPlan:
             return self._host_pool.pop()
         return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
-    def prepare(self, t):
+    def prepare(self, t, overlapped=False, after=None):
         """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
-        the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`."""
-        return TimePrep(self, t)
+        the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`.
+        `overlapped=True` launches on the plan's side stream so the (tiny, latency-bound) kernels run under the
+        synthesis GEMM; the caller's stream must then `wait_event(prep.done)` before it consumes the tables.  `after`
+        (an event recorded when `t` became ready) lets the side stream start without waiting for work queued since."""
+        return TimePrep(self, t, overlapped, after)
 
     def output_times(self, t, t_ends=None):
         """u'_i and the retained block (waveform_grid.py:564-568) as a device tensor.  `t_ends` is accepted for
@@ -538,9 +541,13 @@ class TransformPlan(GridPlan):
         The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
         stream while the synthesis kernel runs.  `prep` (from `prepare(t)`) can be reused for waveforms that share
         their time axis."""
+        cur = self.torch.cuda.current_stream()
+        ready = self.torch.cuda.Event()
+        ready.record(cur)
+        F = self.synthesize(data, t)            # queued first: the GPU is busy while the host launches the preparation
         if prep is None:
-            prep = self.prepare(t)
-        F = self.synthesize(data, t)
+            prep = self.prepare(t, overlapped=True, after=ready)
+        cur.wait_event(prep.done)
         uprm = prep.uprm
         if self.tile and not return_grid:
             gridT = self.remap_tiled(t, F, uprm, prep)
@@ -559,7 +566,7 @@ class TimePrep:
     `resolve()` waits for the 64-byte read-back and returns (lo, hi); `uprm` is the retained block u'[lo:hi]
     (scri/waveform_grid.py:564-568)."""
 
-    def __init__(self, plan, t):
+    def __init__(self, plan, t, overlapped=False, after=None):
         torch = plan.torch
         lib = _lib.load()
         N = t.shape[0]
@@ -567,25 +574,41 @@ class TimePrep:
         self.tab = torch.empty((N, 8), dtype=torch.float64, device=plan.device)
         self.uprm_full = torch.empty(N, dtype=torch.float64, device=plan.device)
         self.info = torch.empty(8, dtype=torch.float64, device=plan.device)
-        _lib.check(
-            lib.scrib200_spline_prepare(
-                _lib.ptr(t), N, plan.gamma if plan.divide_by_gamma else 1 / plan.gamma, int(plan.divide_by_gamma),
-                plan.time_translation, _lib.ptr(plan.d_k), _lib.ptr(plan.d_alpha), plan.G,
-                _lib.ptr(self.tab), _lib.ptr(self.uprm_full), _lib.ptr(self.info), _lib.stream_ptr(),
-            ),
-            "spline_prepare",
-        )
-        # read `info` back on a side stream so that kernels launched meanwhile on the caller's stream are not waited for
         self._host = plan._info_host()
         self._pool = plan._host_pool
         cur = torch.cuda.current_stream()
         side = plan._side_stream()
         self._ready = torch.cuda.Event()
-        side.wait_stream(cur)
+        self.done = torch.cuda.Event()
+
+        def launch():
+            _lib.check(
+                lib.scrib200_spline_prepare(
+                    _lib.ptr(t), N, plan.gamma if plan.divide_by_gamma else 1 / plan.gamma, int(plan.divide_by_gamma),
+                    plan.time_translation, _lib.ptr(plan.d_k), _lib.ptr(plan.d_alpha), plan.G,
+                    _lib.ptr(self.tab), _lib.ptr(self.uprm_full), _lib.ptr(self.info), _lib.stream_ptr(),
+                ),
+                "spline_prepare",
+            )
+
+        if overlapped:
+            if after is not None:
+                side.wait_event(after)     # t (and the tables of the plan) were ready when `after` was recorded
+            else:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                launch()
+                self.done.record(side)
+        else:
+            launch()
+            self.done.record(cur)
+            side.wait_stream(cur)
+        # `info` is read back on the side stream so that kernels launched meanwhile on the caller's stream are not waited for
         with torch.cuda.stream(side):
             self._host.copy_(self.info, non_blocking=True)
             self._ready.record(side)
-        self.info.record_stream(side)
+        for x in (self.info, self.tab, self.uprm_full):
+            x.record_stream(side)
         self._resolved = None
 
     def resolve(self):

@@ -16,9 +16,10 @@ prep = pl.prepare(td); F = pl.synthesize(ad); up = prep.uprm
 gT = pl.remap_tiled(td, F, up, prep)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 res = {}
-for mode in ("scalar", "dmma"):
+for mode in ("scalar", "dmma", "persistent"):
+    os.environ.pop("SCRIB200_ANALYSIS_SCALAR", None); os.environ.pop("SCRIB200_ANALYSIS_NONPERSISTENT", None)
     if mode == "scalar": os.environ["SCRIB200_ANALYSIS_SCALAR"] = "1"
-    else: os.environ.pop("SCRIB200_ANALYSIS_SCALAR", None)
+    if mode == "dmma": os.environ["SCRIB200_ANALYSIS_NONPERSISTENT"] = "1"
     ts = []
     for it in range(4):
         flush.fill_(it)
@@ -27,4 +28,5 @@ for mode in ("scalar", "dmma"):
         ts.append(e0.elapsed_time(e1))
     res[mode] = m.clone()
     print(f"{mode}: {min(ts[1:]):.3f} ms")
-print("max |dmma - scalar| / max|scalar| =", float((res["dmma"] - res["scalar"]).abs().max() / res["scalar"].abs().max()))
+for k in ("dmma", "persistent"):
+    print(f"max |{k} - scalar| / max|scalar| =", float((res[k] - res["scalar"]).abs().max() / res["scalar"].abs().max()))
