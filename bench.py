@@ -345,6 +345,19 @@ def run_ours(args):
                     "frac": ach / dgemm_tf, "traffic": None,
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "algorithmic_flops_per_launch": synth_flops}
+        # DRAM traffic per launch from the committed ncu --set full capture of the same kernels (profiles/), never measured here
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
+                traffic = json.load(f)
+            names = {"swsh_synth_dmma": "swsh_synth_dmma_kernel", "spline_tile(spline_remap)": "spline_tile_kernel<0>",
+                     "map2salm_tiled": "map2salm_persist_kernel<1>"}
+            for kname, ncu_name in names.items():
+                if ncu_name in traffic:
+                    kern[kname]["dram_bytes_per_launch(ncu, profiles/r01b_ncu_summary.md)"] = traffic[ncu_name]["dram_bytes_per_launch"]
+            roof["traffic"] = traffic.get(roof["kernel"], {}).get("dram_bytes_per_launch")
+            roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01b_ncu_summary.md (N = 1e5 capture)"
+        except Exception:
+            pass
         # CPU baseline: oracle port, single thread + BLAS, bounded sample
         cpu_cores = 1
         cval, csec, _ = cpu_baseline_sample(w.t, w.data, kw, args.cpu_sample, workers=1)
