@@ -44,10 +44,12 @@ int64_t scrib200_launch_count(void);
  *   data    [n_times, n_modes] complex128, n_modes = LM_total_size(ell_min, ell_max)
  *   spinors [n_times, 2] complex128 (Ra = w + i z, Rb = y + i x)  - or a single pair if stride 0
  *   seed    [(2L+1)^2], rec [L, 2L+1, 2L+1, 3]  recurrence tables for L = ell_max
- *           (scri_b200._sf.wigner_tables)
+ *           (scri_b200._sf.wigner_tables); uv [L, 2L+1, 2] the factored coefficients
+ *           U[l][m] = sqrt((2l+1)(l+1)/((l+1)^2-m^2)), V[l][m] = sqrt((l+1)(l^2-m^2)/(l((l+1)^2-m^2)))
+ *           (scri_b200._sf.wigner_factor_table).  ell_max <= 16 uses `uv` (rec may be NULL); larger uses `rec`.
  */
 int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
-                          int64_t spinor_stride, const double* seed, const double* rec, void* stream);
+                          int64_t spinor_stride, const double* seed, const double* rec, const double* uv, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWSH synthesis with the BMS epilogue.
@@ -86,7 +88,7 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *   out[(i'/T)*(G*T) + g*T + i'%T], buffer of ceil(n_out/T)*G*T elements - the layout scrib200_map2salm_tiled reads
  *   (stores are contiguous runs of T samples, each analysis CTA reads one contiguous [G, T] tile).
  *   halo / body: rows of run-in on each side of a tile / intervals per tile, multiples of 16, body + 2 halo <= 384
- *   (0 = defaults 32 / 224).
+ *   (0 = defaults 32 / 240).
  *   workspace: scrib200_spline_remap_workspace_bytes() - one int per (tile, grid point): the first output of each
  *   tile.  A CTA keeps its tile of F in shared memory; F is read once.
  */

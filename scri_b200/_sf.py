@@ -84,6 +84,20 @@ def wigner_tables(ell_max):
     return seed, rec
 
 
+@lru_cache(maxsize=None)
+def wigner_factor_table(ell_max):
+    """uv[l, m+L] = (U, V) with the l -> l+1 recurrence coefficients a = U[l][m']U[l][m], c = V[l][m']V[l][m] and
+    b = a m'm/(l(l+1))  (the same coefficients as `_rec_coeffs`, factored so that the table is O(L^2))."""
+    L = ell_max
+    out = np.zeros((max(L, 1), 2 * L + 1, 2))
+    for ell in range(L):
+        for m in range(-ell, ell + 1):
+            d = (ell + 1) ** 2 - m * m
+            out[ell, m + L, 0] = math.sqrt((2 * ell + 1) * (ell + 1) / d)
+            out[ell, m + L, 1] = math.sqrt((ell + 1) * (ell * ell - m * m) / (ell * d)) if ell > 0 else 0.0
+    return out
+
+
 def _phase_powers(z, kmax):
     """[kmax+1, ...] powers z^0..z^kmax by repeated multiplication."""
     out = np.empty((kmax + 1,) + z.shape, dtype=complex)

@@ -202,30 +202,85 @@ __global__ void eig_sign_map_kernel(const double* __restrict__ dpa, int64_t n, i
     maps[i] = (unsigned char)((dp > Norm ? 1 : 0) | (dm > Norm ? 2 : 0));
 }
 
-// one thread walks each direction (the maps are 1 byte/step, so even 1e6 steps is ~ms); a segmented
-// parallel scan replaces this when profiles say so
-__global__ void eig_sign_apply_kernel(double* __restrict__ dpa, int64_t n, int64_t i_index, const double* __restrict__ rough,
-                                      const unsigned char* __restrict__ maps, signed char* __restrict__ signs) {
-    if (blockIdx.x == 0 && threadIdx.x < 2) {
-        const double d0 = rough[0] * dpa[i_index * 3] + rough[1] * dpa[i_index * 3 + 1] + rough[2] * dpa[i_index * 3 + 2];
-        const signed char s0 = (d0 < 0.0) ? -1 : 1;
-        signed char s = s0;
-        if (threadIdx.x == 0) {
-            signs[i_index] = s0;
-            for (int64_t i = i_index + 1; i < n; ++i) {
-                const unsigned char m = maps[i];
-                const bool flip = (s > 0) ? (m & 1) : (m & 2);
-                s = flip ? -1 : 1;
-                signs[i] = s;
-            }
-        } else {
-            for (int64_t i = i_index - 1; i >= 0; --i) {
-                const unsigned char m = maps[i];
-                const bool flip = (s > 0) ? (m & 1) : (m & 2);
-                s = flip ? -1 : 1;
-                signs[i] = s;
-            }
+// The walk s_i = f_i(s_{i-1}) over the 2-state maps is a scan over function composition, done in three parallel
+// phases per direction (forward from i_index+1, backward from i_index-1): (A) every thread composes a block of
+// SIGN_BLK consecutive maps into one map; (B) one CTA stages the block maps in shared memory and a single thread per
+// direction walks them (n / SIGN_BLK cheap steps) recording the state entering every block; (C) every thread re-walks
+// its block from that state and writes the signs.
+constexpr int SIGN_BLK = 256;
+
+__device__ __forceinline__ int64_t sign_len(int dir, int64_t n, int64_t i_index) { return dir == 0 ? n - 1 - i_index : i_index; }
+__device__ __forceinline__ int64_t sign_pos(int dir, int64_t i_index, int64_t p) { return dir == 0 ? i_index + 1 + p : i_index - 1 - p; }
+// state: 0 = sign +1, 1 = sign -1;  next state under map m
+__device__ __forceinline__ int sign_next(unsigned char m, int s) { return s == 0 ? (m & 1) : ((m >> 1) & 1); }
+
+__global__ void eig_sign_blocks_kernel(const unsigned char* __restrict__ maps, int64_t n, int64_t i_index, int64_t nblk_dir,
+                                       unsigned char* __restrict__ blkmap) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * nblk_dir) return;
+    const int dir = id >= nblk_dir;
+    const int64_t bidx = id - dir * nblk_dir;
+    const int64_t len = sign_len(dir, n, i_index);
+    int a = 0, b = 1;   // images of +1 and -1
+    const int64_t p1 = (bidx + 1) * SIGN_BLK < len ? (bidx + 1) * SIGN_BLK : len;
+    for (int64_t p = bidx * SIGN_BLK; p < p1; ++p) {
+        const unsigned char m = maps[sign_pos(dir, i_index, p)];
+        a = sign_next(m, a);
+        b = sign_next(m, b);
+    }
+    blkmap[id] = (unsigned char)(a | (b << 1));
+}
+
+__global__ void eig_sign_walk_kernel(const double* __restrict__ dpa, int64_t i_index, const double* __restrict__ rough,
+                                     int64_t nblk_dir, const unsigned char* __restrict__ blkmap,
+                                     unsigned char* __restrict__ blkstate, signed char* __restrict__ signs) {
+    extern __shared__ unsigned char s_blk[];
+    const double d0 = rough[0] * dpa[i_index * 3] + rough[1] * dpa[i_index * 3 + 1] + rough[2] * dpa[i_index * 3 + 2];
+    const int s0 = (d0 < 0.0) ? 1 : 0;
+    if (threadIdx.x == 0) signs[i_index] = s0 ? -1 : 1;
+    // walk in slabs that fit shared memory
+    const int64_t SLAB = 16384;
+    int state[2] = {s0, s0};
+    for (int64_t base = 0; base < nblk_dir; base += SLAB) {
+        const int64_t cnt = nblk_dir - base < SLAB ? nblk_dir - base : SLAB;
+        __syncthreads();
+        for (int64_t e = threadIdx.x; e < 2 * cnt; e += blockDim.x) {
+            const int dir = e >= cnt;
+            s_blk[e] = blkmap[dir * nblk_dir + base + (e - dir * cnt)];
         }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int dir = threadIdx.x;
+            int s = state[dir];
+            for (int64_t q = 0; q < cnt; ++q) {
+                const unsigned char m = s_blk[dir * cnt + q];
+                s_blk[dir * cnt + q] = (unsigned char)s;          // the state entering block q
+                s = sign_next(m, s);
+            }
+            state[dir] = s;
+        }
+        __syncthreads();
+        for (int64_t e = threadIdx.x; e < 2 * cnt; e += blockDim.x) {
+            const int dir = e >= cnt;
+            blkstate[dir * nblk_dir + base + (e - dir * cnt)] = s_blk[e] & 1;
+        }
+        // thread 0 / 1 carry `state` themselves; the others never use it
+    }
+}
+
+__global__ void eig_sign_fill_kernel(const unsigned char* __restrict__ maps, int64_t n, int64_t i_index, int64_t nblk_dir,
+                                     const unsigned char* __restrict__ blkstate, signed char* __restrict__ signs) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * nblk_dir) return;
+    const int dir = id >= nblk_dir;
+    const int64_t bidx = id - dir * nblk_dir;
+    const int64_t len = sign_len(dir, n, i_index);
+    int s = blkstate[id];
+    const int64_t p1 = (bidx + 1) * SIGN_BLK < len ? (bidx + 1) * SIGN_BLK : len;
+    for (int64_t p = bidx * SIGN_BLK; p < p1; ++p) {
+        const int64_t i = sign_pos(dir, i_index, p);
+        s = sign_next(maps[i], s);
+        signs[i] = s ? -1 : 1;
     }
 }
 
@@ -275,25 +330,52 @@ __global__ void solve3_kernel(const double* __restrict__ A9, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------ sparse <a|M|b>
-// K matrices share one pass over the rows: elements of matrix k are [seg[k], seg[k+1]).
-__global__ void sparse_expectation_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t n_times,
-                                          int n, const int* __restrict__ rows, const int* __restrict__ cols,
-                                          const double2* __restrict__ vals, const int* __restrict__ seg, int K,
-                                          double2* __restrict__ out) {
+// K matrices share one pass over the rows: elements of matrix k are [seg[k], seg[k+1]).  A warp owns ST consecutive
+// time steps, so every (row, col, value) triple fetched serves ST products: the kernel is bound by load issue, not
+// by HBM, and the index / value loads were 3 of the 5 loads per element.
+constexpr int SPARSE_ST = 1;   // measured: 2 and 4 steps per warp are slower (fewer warps in flight outweigh the saved index loads)
+
+__global__ void __launch_bounds__(128)
+sparse_expectation_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t n_times,
+                          int n, const int* __restrict__ rows, const int* __restrict__ cols,
+                          const double2* __restrict__ vals, const int* __restrict__ seg, int K,
+                          double2* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= n_times) return;
-    const double2* ra = a + t * n;
-    const double2* rb = b + t * n;
+    const int64_t t0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SPARSE_ST;
+    if (t0 >= n_times) return;
+    const int nst = (n_times - t0 < SPARSE_ST) ? (int)(n_times - t0) : SPARSE_ST;
+    const double2* ra = a + t0 * n;
+    const double2* rb = b + t0 * n;
     for (int k = 0; k < K; ++k) {
-        double2 acc = make_double2(0.0, 0.0);
-        for (int e = seg[k] + lane; e < seg[k + 1]; e += 32) {
-            const double2 p = cmul(cconj(ra[rows[e]]), rb[cols[e]]);
-            cfma(acc, p, vals[e]);
+        double2 acc[SPARSE_ST];
+#pragma unroll
+        for (int s = 0; s < SPARSE_ST; ++s) acc[s] = make_double2(0.0, 0.0);
+        if (nst == SPARSE_ST) {
+            for (int e = seg[k] + lane; e < seg[k + 1]; e += 32) {
+                const int r = rows[e], c = cols[e];
+                const double2 v = vals[e];
+#pragma unroll
+                for (int s = 0; s < SPARSE_ST; ++s) {
+                    const double2 p = cmul(cconj(ra[(size_t)s * n + r]), rb[(size_t)s * n + c]);
+                    cfma(acc[s], p, v);
+                }
+            }
+        } else {
+            for (int e = seg[k] + lane; e < seg[k + 1]; e += 32) {
+                const int r = rows[e], c = cols[e];
+                const double2 v = vals[e];
+                for (int s = 0; s < nst; ++s) {
+                    const double2 p = cmul(cconj(ra[(size_t)s * n + r]), rb[(size_t)s * n + c]);
+                    cfma(acc[s], p, v);
+                }
+            }
         }
-        acc.x = warp_sum(acc.x);
-        acc.y = warp_sum(acc.y);
-        if (lane == 0) out[t * K + k] = acc;
+#pragma unroll
+        for (int s = 0; s < SPARSE_ST; ++s) {
+            acc[s].x = warp_sum(acc[s].x);
+            acc[s].y = warp_sum(acc[s].y);
+            if (lane == 0 && s < nst) out[(t0 + s) * K + k] = acc[s];
+        }
     }
 }
 
@@ -338,7 +420,10 @@ extern "C" int scrib200_l_vector(const double* data1, const double* data2, int64
     return SCRIB200_OK;
 }
 
-extern "C" size_t scrib200_dominant_eigenvector_workspace_bytes(int64_t n_times) { return (size_t)n_times * 2 + 16; }
+extern "C" size_t scrib200_dominant_eigenvector_workspace_bytes(int64_t n_times) {
+    const size_t nblk = (size_t)(n_times + SIGN_BLK - 1) / SIGN_BLK + 1;
+    return (size_t)n_times * 2 + 4 * nblk + 16;
+}
 
 extern "C" int scrib200_dominant_eigenvector(const double* LL, int64_t n_times, const double* rough_direction,
                                              int64_t rough_index, double* dpa, void* workspace, size_t workspace_bytes,
@@ -357,8 +442,16 @@ extern "C" int scrib200_dominant_eigenvector(const double* LL, int64_t n_times, 
     SCRIB200_CHECK_LAUNCH("dominant_eigenvector(eig)");
     eig_sign_map_kernel<<<nb, 128, 0, st>>>(dpa, n_times, rough_index, maps);
     SCRIB200_CHECK_LAUNCH("dominant_eigenvector(map)");
-    eig_sign_apply_kernel<<<1, 32, 0, st>>>(dpa, n_times, rough_index, rough_direction, maps, signs);
-    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(scan)");
+    const int64_t nblk_dir = (n_times + SIGN_BLK - 1) / SIGN_BLK + 1;   // blocks per direction (upper bound)
+    unsigned char* blkmap = reinterpret_cast<unsigned char*>(signs + n_times);
+    unsigned char* blkstate = blkmap + 2 * nblk_dir;
+    const unsigned nbb = (unsigned)((2 * nblk_dir + 127) / 128);
+    eig_sign_blocks_kernel<<<nbb, 128, 0, st>>>(maps, n_times, rough_index, nblk_dir, blkmap);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(scan: blocks)");
+    eig_sign_walk_kernel<<<1, 256, 2 * 16384, st>>>(dpa, rough_index, rough_direction, nblk_dir, blkmap, blkstate, signs);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(scan: walk)");
+    eig_sign_fill_kernel<<<nbb, 128, 0, st>>>(maps, n_times, rough_index, nblk_dir, blkstate, signs);
+    SCRIB200_CHECK_LAUNCH("dominant_eigenvector(scan: fill)");
     eig_sign_finish_kernel<<<nb, 128, 0, st>>>(dpa, n_times, signs);
     SCRIB200_CHECK_LAUNCH("dominant_eigenvector(finish)");
     return SCRIB200_OK;
@@ -379,7 +472,7 @@ extern "C" int scrib200_sparse_expectation(const double* a, const double* b, int
     SCRIB200_REQUIRE(K >= 1, "sparse_expectation: K=%d", K);
     (void)seg_host;
     if (n_times <= 0) return SCRIB200_OK;
-    sparse_expectation_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+    sparse_expectation_kernel<<<warp_blocks((n_times + SPARSE_ST - 1) / SPARSE_ST), 128, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, rows, cols,
         reinterpret_cast<const double2*>(vals), seg_dev, K, reinterpret_cast<double2*>(out));
     SCRIB200_CHECK_LAUNCH("sparse_expectation");

@@ -242,8 +242,9 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     double* sD = sY + (size_t)ymax * ST_PITCH;              // [ymax][ST_PITCH]  d0, m0, M    row r -> r - ylo
     double* sTab = sD + (size_t)ymax * ST_PITCH;            // [ymax][ST_TAB]                 row r -> r - ylo
     double* sT = sTab + (size_t)ymax * ST_TAB;              // [ymax]                         row r -> r - ylo
-    double* sEdgeD = sT + ymax + (ymax & 1);                // [ST_MAXBLK][ST_COLS] d0 at the block ends
-    double* sEdgeM = sEdgeD + ST_MAXBLK * ST_COLS;          // [ST_MAXBLK][ST_COLS] m0 at the block starts
+    const int nblk_max = (body + 2 * halo) / ST_BR;
+    double* sEdgeD = sT + ymax + (ymax & 1);                // [nblk_max][ST_COLS] d0 at the block ends
+    double* sEdgeM = sEdgeD + nblk_max * ST_COLS;           // [nblk_max][ST_COLS] m0 at the block starts
 #define SY(r_, c_) sY[((r_) - ylo) * ST_PITCH + (c_)]
 #define SD(r_, c_) sD[((r_) - ylo) * ST_PITCH + (c_)]
 #define STAB(r_, f_) sTab[((r_) - ylo) * ST_TAB + (f_)]
@@ -480,40 +481,77 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
 #undef STT
 }
 
-// Inclusive scan down the columns of x[N, C] (in place), one CTA per 32 real columns, rows in slabs: used to turn the
-// per-interval integrals into the antiderivative (waveform_base.py:697-703).  C is small (hundreds), N long: each
-// thread owns one column and a contiguous slab of rows; slab totals are combined through shared memory.
-__global__ void __launch_bounds__(1024)
-column_scan_kernel(double* __restrict__ x, int64_t N, int C) {
-    __shared__ double s_tot[32][33];
-    const int col = blockIdx.x * 32 + threadIdx.x;
-    const int slab = threadIdx.y;                   // 0..31
-    const int64_t per = (N + 31) / 32;
-    const int64_t r0 = slab * per, r1 = (r0 + per < N) ? r0 + per : N;
-    double acc = 0.0;
-    if (col < C)
-        for (int64_t r = r0; r < r1; ++r) acc += x[r * C + col];
-    s_tot[slab][threadIdx.x] = acc;
-    __syncthreads();
-    double base = 0.0;
-    for (int s = 0; s < slab; ++s) base += s_tot[s][threadIdx.x];
-    if (col < C) {
-        double run = base;
-        for (int64_t r = r0; r < r1; ++r) {
-            run += x[r * C + col];
-            x[r * C + col] = run;
-        }
+// Inclusive scan down the columns of x[N, C] (in place): turns the per-interval integrals into the antiderivative
+// (waveform_base.py:697-703).  Three phases, no workspace: (A) every (chunk of SCAN_ROWS rows, 128 columns) CTA scans
+// its chunk locally - its last row then holds the chunk total; (B) one thread per column turns the chunk totals into
+// global values (N / SCAN_ROWS steps); (C) every chunk but the first adds the value at the end of the previous chunk to
+// all its rows but the last.  Lanes run along the columns: every access is a coalesced 1 KB row segment.
+constexpr int SCAN_ROWS = 512;
+
+__global__ void __launch_bounds__(128)
+column_scan_local_kernel(double* __restrict__ x, int64_t N, int C) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= C) return;
+    const int64_t r0 = (int64_t)blockIdx.y * SCAN_ROWS, r1 = (r0 + SCAN_ROWS < N) ? r0 + SCAN_ROWS : N;
+    double run = 0.0;
+    double* p = x + r0 * C + col;
+#pragma unroll 8
+    for (int64_t r = r0; r < r1; ++r, p += C) {
+        run += *p;
+        *p = run;
     }
+}
+
+__global__ void __launch_bounds__(128)
+column_scan_totals_kernel(double* __restrict__ x, int64_t N, int C) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= C) return;
+    double run = 0.0;
+#pragma unroll 8
+    for (int64_t last = SCAN_ROWS - 1; last < N; last += SCAN_ROWS) {   // full chunks only: a partial last chunk has no successor
+        run += x[last * C + col];
+        x[last * C + col] = run;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+column_scan_add_kernel(double* __restrict__ x, int64_t N, int C) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= C) return;
+    const int64_t r0 = (int64_t)(blockIdx.y + 1) * SCAN_ROWS;          // chunk 0 needs nothing
+    if (r0 >= N) return;
+    const bool full = r0 + SCAN_ROWS <= N;
+    const int64_t r1 = full ? r0 + SCAN_ROWS - 1 : N;                   // the last row of a full chunk is already global
+    const double base = x[(r0 - 1) * C + col];
+    double* p = x + r0 * C + col;
+#pragma unroll 8
+    for (int64_t r = r0; r < r1; ++r, p += C) *p += base;
+}
+
+static int launch_column_scan(double* x, int64_t N, int C, cudaStream_t st) {
+    const unsigned gx = (unsigned)((C + 127) / 128);
+    const int64_t nch = (N + SCAN_ROWS - 1) / SCAN_ROWS;
+    SCRIB200_REQUIRE(nch <= 65535, "spline_calculus(scan): series too long (%lld rows)", (long long)N);
+    column_scan_local_kernel<<<dim3(gx, (unsigned)nch), 128, 0, st>>>(x, N, C);
+    SCRIB200_CHECK_LAUNCH("spline_calculus(scan: local)");
+    if (nch > 1) {
+        column_scan_totals_kernel<<<gx, 128, 0, st>>>(x, N, C);
+        SCRIB200_CHECK_LAUNCH("spline_calculus(scan: totals)");
+        column_scan_add_kernel<<<dim3(gx, (unsigned)(nch - 1)), 128, 0, st>>>(x, N, C);
+        SCRIB200_CHECK_LAUNCH("spline_calculus(scan: add)");
+    }
+    return SCRIB200_OK;
 }
 
 static size_t tile_smem_bytes(int body, int halo) {
     const size_t ymax = (size_t)body + 2 * halo + 2;
-    return (2 * ymax * ST_PITCH + ymax * ST_TAB + ymax + (ymax & 1) + 2 * (size_t)ST_MAXBLK * ST_COLS) * sizeof(double);
+    const size_t nblk = ((size_t)body + 2 * halo) / ST_BR;
+    return (2 * ymax * ST_PITCH + ymax * ST_TAB + ymax + (ymax & 1) + 2 * nblk * ST_COLS) * sizeof(double);
 }
 
 static void resolve_tile(int& halo, int& body) {
     if (halo <= 0) halo = 32;
-    if (body <= 0) body = (halo <= 32) ? 224 : (halo <= 64 ? 160 : 128);   // two CTAs per SM up to halo = 64
+    if (body <= 0) body = (halo <= 32) ? 240 : (halo <= 64 ? 176 : 128);   // two CTAs per SM up to halo = 64
 }
 
 template <int MODE>
@@ -616,12 +654,10 @@ extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const 
     double* first = (order == -1) ? out : aux;
     int rc = launch_tile<3>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, first, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
-    column_scan_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(first, n_times, C);
-    SCRIB200_CHECK_LAUNCH("spline_calculus(scan)");
+    rc = launch_column_scan(first, n_times, C, (cudaStream_t)stream);
+    if (rc != SCRIB200_OK) return rc;
     if (order == -1) return SCRIB200_OK;
     rc = launch_tile<4>(t, n_times, data, ncol, nullptr, nullptr, tab, first, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
-    column_scan_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(out, n_times, C);
-    SCRIB200_CHECK_LAUNCH("spline_calculus(scan)");
-    return SCRIB200_OK;
+    return launch_column_scan(out, n_times, C, (cudaStream_t)stream);
 }

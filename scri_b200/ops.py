@@ -95,7 +95,8 @@ def wigner_tables_device(ell_max):
     key = ("wig", ell_max, torch.cuda.current_device())
     if key not in _table_cache:
         seed, rec = _sf.wigner_tables(ell_max)
-        _table_cache[key] = (torch.from_numpy(np.ascontiguousarray(seed)).cuda(), torch.from_numpy(np.ascontiguousarray(rec)).cuda())
+        uv = _sf.wigner_factor_table(ell_max)
+        _table_cache[key] = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (seed, rec, uv))
     return _table_cache[key]
 
 
@@ -116,9 +117,10 @@ def rotate_modes(data, R, ell_min, ell_max):
         sp_np = Q.as_spinor_array(Rf)
         stride = 2 if Rf.ndim == 2 else 0
         sp = to_device(sp_np, np.complex128)
-    seed, rec = wigner_tables_device(ell_max)
+    seed, rec, uv = wigner_tables_device(ell_max)
     _lib.check(
-        lib.scrib200_rotate_modes(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(seed), _lib.ptr(rec), _lib.stream_ptr()),
+        lib.scrib200_rotate_modes(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(seed), _lib.ptr(rec),
+                                  _lib.ptr(uv), _lib.stream_ptr()),
         "rotate_modes",
     )
     if is_tensor(data):

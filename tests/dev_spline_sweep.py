@@ -16,7 +16,7 @@ prep = pl.prepare(td); F = pl.synthesize(ad); up = prep.uprm
 print("n_out", up.shape[0], "halo/body auto", prep.halo_body())
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 ref = None
-for body, halo in ((96, 32), (128, 32), (160, 32), (192, 32), (224, 32), (256, 32), (320, 32), (160, 64)):
+for body, halo in ((112, 32), (128, 32), (144, 32), (192, 32), (224, 32), (240, 32)):
     pl.spline_body, pl.spline_halo = body, halo
     ts = []
     for it in range(4):
