@@ -149,6 +149,12 @@ int scrib200_ll_ldt(const double* data, const double* datadot, int64_t n_times, 
 int scrib200_l_vector(const double* data1, const double* data2, int64_t n_times, int n_modes, const double* coef,
                       double* Lvec, void* stream);
 
+/* <LL>^{ab} between two waveforms, complex [n_times, 3, 3], not symmetrised.
+ * Replaces  scri/mode_calculations.py:106-206 `_LLComparisonMatrix(data1, data2, lm, LL)` literally (the reference adds
+ * its (y,z) term to element (y,y); so does this). coef as for scrib200_ll_ldt. */
+int scrib200_ll_comparison(const double* data1, const double* data2, int64_t n_times, int n_modes, const double* coef,
+                           double* LL, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Dominant principal axis of <LL>, made continuous in time.
  * Replaces  np.linalg.eigh(LL)[1][:, :, 2] + scri/mode_calculations.py:316-363

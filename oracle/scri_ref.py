@@ -503,6 +503,40 @@ def _LLMatrix(data, lm, LL):
 
 
 @jit
+def _LLComparisonMatrix(data1, data2, lm, LL):
+    # mode_calculations.py:106-192, literally (LL[1,1] receives two terms and LL[1,2] none, as in the reference)
+    for i_mode in range(lm.shape[0]):
+        L = lm[i_mode, 0]
+        M = lm[i_mode, 1]
+        for i_time in range(data1.shape[0]):
+            LpLp = np.conjugate(data1[i_time, i_mode + 2]) * data2[i_time, i_mode] * (_ladder(L, M + 1) * _ladder(L, M)) if M + 2 <= L else 0.0 + 0.0j
+            LpLm = np.conjugate(data1[i_time, i_mode]) * data2[i_time, i_mode] * (_ladder(L, M - 1) * _ladder(L, -M)) if M - 1 >= -L else 0.0 + 0.0j
+            LmLp = np.conjugate(data1[i_time, i_mode]) * data2[i_time, i_mode] * (_ladder(L, -(M + 1)) * _ladder(L, M)) if M + 1 <= L else 0.0 + 0.0j
+            LmLm = np.conjugate(data1[i_time, i_mode - 2]) * data2[i_time, i_mode] * (_ladder(L, -(M - 1)) * _ladder(L, -M)) if M - 2 >= -L else 0.0 + 0.0j
+            LpLz = np.conjugate(data1[i_time, i_mode + 1]) * data2[i_time, i_mode] * (_ladder(L, M) * M) if M + 1 <= L else 0.0 + 0.0j
+            LzLp = np.conjugate(data1[i_time, i_mode + 1]) * data2[i_time, i_mode] * ((M + 1) * _ladder(L, M)) if M + 1 <= L else 0.0 + 0.0j
+            LmLz = np.conjugate(data1[i_time, i_mode - 1]) * data2[i_time, i_mode] * (_ladder(L, -M) * M) if M - 1 >= -L else 0.0 + 0.0j
+            LzLm = np.conjugate(data1[i_time, i_mode - 1]) * data2[i_time, i_mode] * ((M - 1) * _ladder(L, -M)) if M - 1 >= -L else 0.0 + 0.0j
+            LzLz = np.conjugate(data1[i_time, i_mode]) * data2[i_time, i_mode] * M**2
+            LL[i_time, 0, 0] += 0.25 * (LpLp + LmLm + LmLp + LpLm)
+            LL[i_time, 0, 1] += -0.25j * (LpLp - LmLm + LmLp - LpLm)
+            LL[i_time, 0, 2] += 0.5 * (LpLz + LmLz)
+            LL[i_time, 1, 0] += -0.25j * (LpLp - LmLp + LpLm - LmLm)
+            LL[i_time, 1, 1] += -0.25 * (LpLp - LmLp - LpLm + LmLm)
+            LL[i_time, 1, 1] += -0.5j * (LpLz - LmLz)
+            LL[i_time, 2, 0] += 0.5 * (LzLp + LzLm)
+            LL[i_time, 2, 1] += -0.5j * (LzLp - LzLm)
+            LL[i_time, 2, 2] += LzLz
+
+
+def LLComparisonMatrix(W1, W2):
+    # mode_calculations.py:195-206
+    LL = np.zeros((W1.n_times, 3, 3), dtype=complex)
+    _LLComparisonMatrix(W1.data, W2.data, W1.LM, LL)
+    return LL
+
+
+@jit
 def _LLDominantEigenvector(dpa, dpa_i, i_index):
     # mode_calculations.py:316-363
     if (dpa_i[0] * dpa[i_index, 0] + dpa_i[1] * dpa[i_index, 1] + dpa_i[2] * dpa[i_index, 2]) < 0.0:

@@ -14,7 +14,7 @@ from .waveform_base import WaveformBase  # noqa: F401
 from .waveform_modes import WaveformModes
 from .waveform_grid import WaveformGrid  # noqa: F401
 from .mode_calculations import (  # noqa: F401
-    LdtVector, LVector, LLMatrix, LLDominantEigenvector, angular_velocity, corotating_frame,
+    LdtVector, LVector, LLMatrix, LLComparisonMatrix, LLDominantEigenvector, angular_velocity, corotating_frame,
 )
 from .flux import energy_flux, momentum_flux, angular_momentum_flux, boost_flux, poincare_fluxes  # noqa: F401
 from .rotations import (  # noqa: F401
@@ -27,6 +27,7 @@ from .asymptotic_bondi_data import AsymptoticBondiData, ModesTimeSeries  # noqa:
 WaveformModes.LdtVector = LdtVector
 WaveformModes.LVector = LVector
 WaveformModes.LLMatrix = LLMatrix
+WaveformModes.LLComparisonMatrix = LLComparisonMatrix
 WaveformModes.LLDominantEigenvector = LLDominantEigenvector
 WaveformModes.angular_velocity = angular_velocity
 WaveformModes.energy_flux = energy_flux

@@ -38,6 +38,7 @@ SIGNATURES = {
     "scrib200_spline_calculus": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
     "scrib200_norm": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "scrib200_ll_ldt": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "scrib200_ll_comparison": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "scrib200_l_vector": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "scrib200_dominant_eigenvector_workspace_bytes": (c_sz, [c_i64]),
     "scrib200_dominant_eigenvector": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

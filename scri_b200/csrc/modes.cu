@@ -105,6 +105,65 @@ __global__ void ll_ldt_kernel(const double2* __restrict__ data, const double2* _
     }
 }
 
+// <LL>^{ab} between two waveforms (mode_calculations.py:106-206), complex and NOT symmetrised, reproduced literally -
+// including the reference's accumulation of the (y,z) element into (y,y) (LL[1,1] receives two terms, LL[1,2] none).
+__global__ void ll_comparison_kernel(const double2* __restrict__ d1, const double2* __restrict__ d2, int64_t n_times, int n,
+                                     const double* __restrict__ coef, double2* __restrict__ LL) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* r1 = d1 + t * n;
+    const double2* r2 = d2 + t * n;
+    double2 s[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s[q] = make_double2(0.0, 0.0);
+    for (int i = lane; i < n; i += 32) {
+        const double* c = coef + i * NCOEF;
+        const double cp = c[0], cm = c[1], cpp = c[2], cmm = c[3], M = c[4];
+        const double2 g = r2[i];
+        const double2 f0 = cmul(cconj(r1[i]), g);
+        const double2 fp1 = cmul(cconj(r1[i + 1 < n ? i + 1 : i]), g), fm1 = cmul(cconj(r1[i >= 1 ? i - 1 : i]), g);
+        const double2 fp2 = cmul(cconj(r1[i + 2 < n ? i + 2 : i]), g), fm2 = cmul(cconj(r1[i >= 2 ? i - 2 : i]), g);
+        const double2 LpLp = cscale(cpp, fp2), LmLm = cscale(cmm, fm2);
+        const double2 LpLm = cscale(cm * cm, f0), LmLp = cscale(cp * cp, f0);
+        const double2 LpLz = cscale(cp * M, fp1), LzLp = cscale((M + 1.0) * cp, fp1);
+        const double2 LmLz = cscale(cm * M, fm1), LzLm = cscale((M - 1.0) * cm, fm1);
+        const double2 LzLz = cscale(M * M, f0);
+        auto add = [](double2& acc, double re, double im) { acc.x += re; acc.y += im; };
+        // 0.25 (LpLp + LmLm + LmLp + LpLm)
+        add(s[0], 0.25 * (LpLp.x + LmLm.x + LmLp.x + LpLm.x), 0.25 * (LpLp.y + LmLm.y + LmLp.y + LpLm.y));
+        {   // -0.25j (LpLp - LmLm + LmLp - LpLm):  -j (x + i y) = y - i x
+            const double x = LpLp.x - LmLm.x + LmLp.x - LpLm.x, y = LpLp.y - LmLm.y + LmLp.y - LpLm.y;
+            add(s[1], 0.25 * y, -0.25 * x);
+        }
+        add(s[2], 0.5 * (LpLz.x + LmLz.x), 0.5 * (LpLz.y + LmLz.y));
+        {   // -0.25j (LpLp - LmLp + LpLm - LmLm)
+            const double x = LpLp.x - LmLp.x + LpLm.x - LmLm.x, y = LpLp.y - LmLp.y + LpLm.y - LmLm.y;
+            add(s[3], 0.25 * y, -0.25 * x);
+        }
+        add(s[4], -0.25 * (LpLp.x - LmLp.x - LpLm.x + LmLm.x), -0.25 * (LpLp.y - LmLp.y - LpLm.y + LmLm.y));
+        {   // the reference adds -0.5j (LpLz - LmLz) to element (1,1) as well
+            const double x = LpLz.x - LmLz.x, y = LpLz.y - LmLz.y;
+            add(s[4], 0.5 * y, -0.5 * x);
+        }
+        add(s[6], 0.5 * (LzLp.x + LzLm.x), 0.5 * (LzLp.y + LzLm.y));
+        {   // -0.5j (LzLp - LzLm)
+            const double x = LzLp.x - LzLm.x, y = LzLp.y - LzLm.y;
+            add(s[7], 0.5 * y, -0.5 * x);
+        }
+        add(s[8], LzLz.x, LzLz.y);
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        s[q].x = warp_sum(s[q].x);
+        s[q].y = warp_sum(s[q].y);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) LL[t * 9 + q] = s[q];
+    }
+}
+
 // <L>^a = sum conj(a1[m']) <L_a> a2[m]  (complex 3-vector)
 __global__ void l_vector_kernel(const double2* __restrict__ d1, const double2* __restrict__ d2, int64_t n_times, int n,
                                 const double* __restrict__ coef, double2* __restrict__ Lvec) {
@@ -417,6 +476,17 @@ extern "C" int scrib200_l_vector(const double* data1, const double* data2, int64
         reinterpret_cast<const double2*>(data1), reinterpret_cast<const double2*>(data2), n_times, n_modes, coef,
         reinterpret_cast<double2*>(Lvec));
     SCRIB200_CHECK_LAUNCH("l_vector");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_ll_comparison(const double* data1, const double* data2, int64_t n_times, int n_modes,
+                                      const double* coef, double* LL, void* stream) {
+    SCRIB200_REQUIRE(data1 && data2 && coef && LL, "ll_comparison: null pointer");
+    if (n_times <= 0) return SCRIB200_OK;
+    ll_comparison_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(data1), reinterpret_cast<const double2*>(data2), n_times, n_modes, coef,
+        reinterpret_cast<double2*>(LL));
+    SCRIB200_CHECK_LAUNCH("ll_comparison");
     return SCRIB200_OK;
 }
 

@@ -27,6 +27,12 @@ def LLMatrix(W):
     return LL
 
 
+def LLComparisonMatrix(W1, W2):
+    r"""<LL>^{ab} = sum conj(f)^{l,m'} <l,m'|L_a L_b|l,m> g^{l,m} between two waveforms, complex
+    (scri/mode_calculations.py:195-206)"""
+    return ops.ll_comparison(W1.data, W2.data, W1.ell_min, W1.ell_max)
+
+
 def LLDominantEigenvector(W, RoughDirection=np.array([0.0, 0.0, 1.0]), RoughDirectionIndex=0):
     """Principal axis of <LL>, sign-continuous in time (scri/mode_calculations.py:366-399)."""
     torch_data = ops.to_device(W.data, np.complex128)

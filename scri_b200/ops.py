@@ -371,6 +371,21 @@ def ll_ldt(data, datadot, ell_min, ell_max):
     return to_host(LL), (None if Ldt is None else to_host(Ldt))
 
 
+def ll_comparison(data1, data2, ell_min, ell_max):
+    """<LL> between two waveforms, complex [N,3,3] - scri/mode_calculations.py:106-206."""
+    lib = _lib.load()
+    torch = _torch()
+    d1 = to_device(data1, np.complex128)
+    d2 = d1 if data2 is data1 else to_device(data2, np.complex128)
+    N, n = d1.shape
+    if d2.shape != d1.shape:
+        raise ValueError("ll_comparison: the two waveforms must have the same shape")
+    coef = _ladder_device(ell_min, ell_max)
+    out = torch.empty((N, 3, 3), dtype=torch.complex128, device="cuda")
+    _lib.check(lib.scrib200_ll_comparison(_lib.ptr(d1), _lib.ptr(d2), N, n, _lib.ptr(coef), _lib.ptr(out), _lib.stream_ptr()), "ll_comparison")
+    return out if is_tensor(data1) else to_host(out)
+
+
 def l_vector(data1, data2, ell_min, ell_max):
     """<L> complex [N,3] - scri/mode_calculations.py:60-89."""
     lib = _lib.load()

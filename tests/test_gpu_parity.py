@@ -344,6 +344,23 @@ def test_boost_flux_and_eth_vs_oracle():
         hd.boost_flux()
 
 
+def test_LLComparisonMatrix_vs_oracle():
+    """scri/mode_calculations.py:106-206 (complex, not symmetrised; the reference's (y,y)/(y,z) accumulation included)"""
+    t, d1 = smooth_modes(n_times=120, seed=51)
+    _, d2 = smooth_modes(n_times=120, seed=52)
+    w1, w2 = modes(t, d1), modes(t, d2)
+    ref = R.LLComparisonMatrix(R.Modes(t=t, data=d1.copy()), R.Modes(t=t, data=d2.copy()))
+    out = w1.LLComparisonMatrix(w2)
+    assert out.shape == (120, 3, 3) and out.dtype == complex
+    assert rel(out, ref) < 1e-13
+    assert np.all(out[:, 1, 2] == 0)
+    # with W1 = W2 the symmetrised real part of the well-formed elements is <LL>
+    same = w1.LLComparisonMatrix(w1)
+    LL = w1.LLMatrix()
+    assert rel(same[:, 0, 0].real, LL[:, 0, 0]) < 1e-13 and rel(same[:, 2, 2].real, LL[:, 2, 2]) < 1e-13
+    assert rel(0.5 * (same[:, 0, 1] + same[:, 1, 0]).real, LL[:, 0, 1]) < 1e-13
+
+
 def test_dominant_eigenvector_and_angular_velocity_physics():
     """reference tests/test_mode_calculations.py:14-126 (simple cases)"""
     t = np.linspace(0.0, 20.0, 2001)
