@@ -381,6 +381,85 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_batch_workload(args):
+    """BASELINE configs[2]: a batch of random-mode waveforms (l <= 8, 2048 steps each) sharing one BMS transformation,
+    sharded by waveform index over the ranks (strong scaling: the batch is fixed).  Optional workload, not the
+    default bench line; device-resident only (the reference has no batched call to mirror end to end)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import scri_b200 as sb
+    from scri_b200 import _lib, parallel
+    from scri_b200.plan import TransformPlan
+
+    kw = transformation_kwargs()
+    B, N, n = args.batch, 2048, 77
+    lo, hi = parallel.shard_range(B, rank, world)
+    plan = TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **kw)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    t = torch.linspace(0.0, 204.7, N, dtype=torch.float64, device="cuda")
+    sub = 512
+    chunks = []
+    for b0 in range(lo, hi, sub):
+        bn = min(sub, hi - b0)
+        w = torch.rand(bn, 1, n, dtype=torch.float64, device="cuda", generator=g) * 0.45 + 0.05
+        c = torch.randn(bn, 1, n, dtype=torch.complex128, device="cuda", generator=g)
+        chunks.append(c * torch.exp(1j * w * t[None, :, None]))
+
+    def step():
+        n_out = 0
+        for d in chunks:
+            up, out = plan.run_batch(t, d)
+            n_out = up.shape[0]
+        return n_out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        n_out = step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": float(n) * N * B / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: batch of {B} random-mode waveforms, ell 2..8 (77 modes), {N} steps each, one shared transformation (supertranslation ell<=4 + rotation + boost); sharded by waveform index, sub-batches of {sub}",
+                       "n_out": n_out, "grid": f"{plan.n_theta}x{plan.n_phi}",
+                       "l2": "every sub-batch streams > 20 GB of intermediates: far beyond L2"},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line, default=float))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,11 +469,15 @@ def main():
     ap.add_argument("--n-times", type=int, default=100_000)
     ap.add_argument("--cpu-sample", type=int, default=4000, help="time steps in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=10_000, help="time steps per step of --impl reference")
+    ap.add_argument("--workload", default="transform", choices=["transform", "batch"], help="transform = configs[1] (the bench line); batch = configs[2]")
+    ap.add_argument("--batch", type=int, default=4096, help="waveforms in the batch workload (all ranks together)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "batch":
+        run_batch_workload(args)
     else:
         run_ours(args)
 

@@ -89,6 +89,8 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *   (stores are contiguous runs of T samples, each analysis CTA reads one contiguous [G, T] tile).
  *   halo / body: rows of run-in on each side of a tile / intervals per tile, multiples of 16, body + 2 halo <= 384
  *   (0 = defaults 32 / 240).
+ *   n_series >= 1: a batch of series sharing t, kconf, alpha and uprm: F is [n_series, n_times, G] and the outputs of
+ *   series b are rows b*n_out .. (b+1)*n_out-1 of `out` (time-major) or of the time-tiled index space (tile = T).
  *   workspace: scrib200_spline_remap_workspace_bytes() - one int per (tile, grid point): the first output of each
  *   tile.  A CTA keeps its tile of F in shared memory; F is read once.
  */
@@ -98,7 +100,8 @@ int scrib200_spline_prepare(const double* t, int64_t n_times, double gamma_facto
                             void* stream);
 int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
                           const double* alpha, const double* tab, const double* uprm, int64_t n_out, double* out,
-                          int tile, int halo, int body, void* workspace, size_t workspace_bytes, void* stream);
+                          int tile, int halo, int body, int n_series, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWSH analysis, batched over time steps.

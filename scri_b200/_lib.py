@@ -29,7 +29,7 @@ SIGNATURES = {
     "scrib200_spline_prepare": (c_int, [c_vp, c_i64, ctypes.c_double, c_int, ctypes.c_double, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_spline_remap": (
         c_int,
-        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_sz, c_vp],
+        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp],
     ),
     "scrib200_spline_remap_workspace_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "scrib200_map2salm_tile_size": (c_int, [c_int, c_int, c_int, c_int]),

@@ -254,7 +254,7 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     {
         const int ch = tid & 7;
         const bool colok = col0 + 2 * ch < G2;
-        const double* src = F + (size_t)ylo * G2 + col0 + 2 * ch;
+        const double* src = F + ((size_t)blockIdx.z * N + ylo) * G2 + col0 + 2 * ch;   // blockIdx.z: series of a batch
         for (int rr = tid >> 3; rr < nyrows; rr += nthr >> 3) {
             double* dst = sY + rr * ST_PITCH + 2 * ch;
             if (colok) {
@@ -435,7 +435,8 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
                 double2 r;
                 r.x = A * yi.x + B * yi1.x + (ca * Mi.x + cb * Mi1.x);
                 r.y = A * yi.y + B * yi1.y + (ca * Mi.y + cb * Mi1.y);
-                const int64_t o = (tshift > 0) ? (int64_t)(j >> tshift) * tileGT + (j & tmask) : (int64_t)j * G;
+                const int64_t jg = (int64_t)blockIdx.z * Nout + j;       // output row across the batch
+                const int64_t o = (tshift > 0) ? (jg >> tshift) * tileGT + (jg & tmask) : jg * G;
                 og[o] = r;
             };
             int j = jlo + lane;
@@ -450,6 +451,8 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         // one thread per (knot, real column): 128-byte row segments of the time-major output
         const int rstep = nthr / ST_COLS;
         const bool colok = col0 + cc < G2;
+        out += (size_t)blockIdx.z * N * G2;
+        if (MODE == 4) up += (size_t)blockIdx.z * N * G2;
         for (int i = a + tid / ST_COLS; i < b; i += rstep) {
             const double ht = STAB(i, 7);
             const double yi = SY(i, cc), yi1 = SY(i + 1, cc);
@@ -557,7 +560,7 @@ static void resolve_tile(int& halo, int& body) {
 template <int MODE>
 static int launch_tile(const double* t, int64_t n_times, const double* F, int G, const double* kconf, const double* alpha,
                        const double* tab, const double* uprm, int64_t n_out, double* out, int tshift, int halo, int body,
-                       void* workspace, size_t workspace_bytes, void* stream, const char* name) {
+                       void* workspace, size_t workspace_bytes, void* stream, const char* name, int n_series = 1) {
     SCRIB200_REQUIRE(n_times < (int64_t)2147483000 && n_out < (int64_t)2147483000, "%s: series longer than 2^31 samples", name);
     resolve_tile(halo, body);
     SCRIB200_REQUIRE(halo % ST_BR == 0 && body % ST_BR == 0, "%s: body=%d and halo=%d must be multiples of %d", name, body, halo, ST_BR);
@@ -568,7 +571,8 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     SCRIB200_REQUIRE(ntiles <= 65535, "%s: too many time tiles (%lld); raise `body`", name, (long long)ntiles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(spline_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles);
+    SCRIB200_REQUIRE(n_series >= 1 && n_series <= 65535, "%s: n_series=%d must be 1..65535", name, n_series);
+    dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles, (unsigned)n_series);
     const int threads = ((nblk * ST_COLS + 31) / 32) * 32;   // one half-warp per sweep block
     int* J = nullptr;
     if (MODE == 0) {
@@ -619,8 +623,8 @@ extern "C" size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, 
 
 extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
                                      const double* alpha, const double* tab, const double* uprm, int64_t n_out,
-                                     double* out, int tile, int halo, int body, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+                                     double* out, int tile, int halo, int body, int n_series, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
     using namespace scrib200;
     SCRIB200_REQUIRE(t && F && kconf && alpha && tab && uprm && out, "spline_remap: null pointer");
     SCRIB200_REQUIRE(n_times >= 4, "spline_remap: a cubic interpolating spline needs at least 4 knots; got %lld",
@@ -632,7 +636,7 @@ extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const dou
     SCRIB200_REQUIRE(aligned16(F) && aligned16(out) && aligned16(tab), "spline_remap: pointers must be 16-byte aligned");
     if (n_out <= 0) return SCRIB200_OK;
     return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, workspace,
-                          workspace_bytes, stream, "spline_remap");
+                          workspace_bytes, stream, "spline_remap", n_series);
 }
 
 extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const double* data, int ncol,

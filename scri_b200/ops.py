@@ -306,7 +306,7 @@ def spline_calculus(t, data, kind, order=1, tprime=None):
         ws = torch.empty(lib.scrib200_spline_remap_workspace_bytes(N, ncol, halo, 0), dtype=torch.uint8, device="cuda")
         _lib.check(
             lib.scrib200_spline_remap(_lib.ptr(tt), N, _lib.ptr(d2), ncol, _lib.ptr(ones), _lib.ptr(zeros), _lib.ptr(tab),
-                                      _lib.ptr(tp), tp.shape[0], _lib.ptr(out), 0, halo, 0, _lib.ptr(ws), ws.numel(),
+                                      _lib.ptr(tp), tp.shape[0], _lib.ptr(out), 0, halo, 0, 1, _lib.ptr(ws), ws.numel(),
                                       _lib.stream_ptr()),
             "spline_remap",
         )

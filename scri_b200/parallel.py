@@ -86,10 +86,5 @@ def gather_batch(local, counts, group=None):
 
 
 def transform_batch(plan, t, data_batch):
-    """Run one TransformPlan over a local shard `data_batch[B_local, N, n]` (device tensors)."""
-    outs = []
-    uprm = None
-    for b in range(data_batch.shape[0]):
-        uprm, modes = plan.run(t, data_batch[b])
-        outs.append(modes)
-    return uprm, outs
+    """Run one TransformPlan over a local shard `data_batch[B_local, N, n]` (device tensors): (u', modes'[B_local, N', n'])."""
+    return plan.run_batch(t, data_batch)

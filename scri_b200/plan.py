@@ -264,16 +264,18 @@ class GridPlan:
         backward compatibility and ignored (the block is found on the device)."""
         return self.prepare(t).uprm
 
-    def _remap(self, t, F, uprm, prep, tile):
+    def _remap(self, t, F, uprm, prep, tile, n_series=1):
+        """F [n_series * N, G] (series stacked along time) -> remapped grid; rows b*n_out.. belong to series b."""
         torch = self.torch
         lib = _lib.load()
         if prep is None:
             prep = self.prepare(t)
         N, n_out = t.shape[0], uprm.shape[0]
+        rows = n_out * n_series
         if tile:
-            out = torch.empty((-(-n_out // tile), self.G, tile), dtype=torch.complex128, device=self.device)
+            out = torch.empty((-(-rows // tile), self.G, tile), dtype=torch.complex128, device=self.device)
         else:
-            out = torch.empty((n_out, self.G), dtype=torch.complex128, device=self.device)
+            out = torch.empty((rows, self.G), dtype=torch.complex128, device=self.device)
         halo, body = prep.halo_body(self.spline_halo, self.spline_body)
         need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
         if self._ws is None or self._ws.numel() < need:
@@ -281,7 +283,7 @@ class GridPlan:
         _lib.check(
             lib.scrib200_spline_remap(
                 _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
-                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, _lib.ptr(self._ws), self._ws.numel(),
+                _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, n_series, _lib.ptr(self._ws), self._ws.numel(),
                 _lib.stream_ptr(),
             ),
             "spline_remap",
@@ -558,6 +560,39 @@ class TransformPlan(GridPlan):
         if return_grid:
             return uprm, grid
         return uprm, self.analyze(grid)
+
+
+def _run_batch(self, t, data_batch, prep=None):
+    """A batch of waveforms sharing the time axis and the transformation (BASELINE config 3): data_batch
+    [B, N, n_modes] device tensor -> (u' [N'], modes' [B, N', n_modes_out]).  One synthesis launch over all B*N rows,
+    one spline launch with the batch in gridDim.z, one analysis launch over all B*N' rows."""
+    torch = self.torch
+    B, N = int(data_batch.shape[0]), int(data_batch.shape[1])
+    if t.shape[0] != N:
+        raise ValueError("run_batch: the time axis must match dimension 1 of the batch")
+    if self.mix:
+        raise NotImplementedError("run_batch does not cover psi0..psi3 (they need their companion fields per waveform)")
+    cur = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    F = self.synthesize(data_batch.reshape(B * N, -1))
+    if prep is None:
+        prep = self.prepare(t, overlapped=True, after=ready)
+    cur.wait_event(prep.done)
+    uprm = prep.uprm
+    n_out = uprm.shape[0]
+    if self.tile:
+        gridT = self._remap(t, F, uprm, prep, self.tile, n_series=B)
+        del F
+        modes = self.analyze_tiled(gridT, B * n_out)
+    else:
+        grid = self._remap(t, F, uprm, prep, 0, n_series=B)
+        del F
+        modes = self.analyze(grid)
+    return uprm, modes.reshape(B, n_out, -1)
+
+
+TransformPlan.run_batch = _run_batch
 
 
 class TimePrep:
