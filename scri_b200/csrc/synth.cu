@@ -9,20 +9,25 @@
 // so that C = A.B is F with re/im interleaved.  8*n*G flops per time step, none redundant.
 //
 // sm_100a has no tcgen05 kind for f64; the FP64 tensor path is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
-// CTA tile 128x64, 8 warps as 4(M) x 2(N), warp tile 32x32 = 4x4 DMMA tiles (32 accumulator doubles
-// per thread); K is streamed in BK=16 slabs through a 4-stage cp.async ring; shared-memory strides
-// (20 and 68 doubles) make both fragment loads bank-conflict free.
+// CTA tile 64x64, 4 warps as 2(M) x 2(N), warp tile 32x32 = 4x4 DMMA tiles (32 accumulator doubles per thread), four
+// CTAs per SM (small independent CTAs beat 128x64 ones by 12 %: fewer warps wait on each barrier); K is streamed in
+// BK=8 slabs through a 4-stage cp.async ring; shared-memory strides BK+4 and 68 doubles for the fragment loads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace scrib200 {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
-constexpr int AS = BK + 4;   // A smem row stride (doubles)
+constexpr int BN = 64;
 constexpr int BS = BN + 4;   // B smem row stride (doubles)
-constexpr int A_STAGE = BM * AS;
-constexpr int B_STAGE = BK * BS;
-constexpr int SYNTH_THREADS = 256;
-constexpr size_t SYNTH_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+template <int BK, int STAGES, int BM = 128>
+struct SynthCfg {
+    static constexpr int THREADS = 2 * BM;   // (BM / 32) x 2 warps of 32 x 32
+    static constexpr int AS = BK + 4;   // A smem row stride (doubles)
+    static constexpr int A_STAGE = BM * AS;
+    static constexpr int B_STAGE = BK * BS;
+    static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -40,10 +45,13 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(SYNTH_THREADS, 2)
+template <int BK, int STAGES, int BM>
+__global__ void __launch_bounds__(2 * BM, 256 / BM)
 swsh_synth_dmma_kernel(const double* __restrict__ A, int64_t M, int K, const double* __restrict__ B, int Kpad,
                        int Ncpad, const double* __restrict__ offset, const double* __restrict__ scale, int Nc,
                        double* __restrict__ C) {
+    constexpr int AS = SynthCfg<BK, STAGES, BM>::AS, A_STAGE = SynthCfg<BK, STAGES, BM>::A_STAGE, B_STAGE = SynthCfg<BK, STAGES, BM>::B_STAGE;
+    constexpr int SYNTH_THREADS = 2 * BM;
     extern __shared__ __align__(16) double smem_d[];
     double* sA = smem_d;
     double* sB = smem_d + STAGES * A_STAGE;
@@ -62,7 +70,7 @@ swsh_synth_dmma_kernel(const double* __restrict__ A, int64_t M, int K, const dou
 #pragma unroll
         for (int c = 0; c < (BM * BK / 2) / SYNTH_THREADS; ++c) {
             int chunk = tid + c * SYNTH_THREADS;
-            int r = chunk >> 3, kc = (chunk & 7) * 2;
+            int r = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
             int64_t gr = row0 + r;
             int k = k0 + kc;
             int bytes = (gr < M && k < K) ? 16 : 0;   // K is even, so a chunk is all-in or all-out
@@ -148,21 +156,32 @@ extern "C" int scrib200_swsh_synthesize(const double* modes, int64_t n_times, in
     SCRIB200_REQUIRE(modes && Bmat && offset && scale && F, "swsh_synthesize: null pointer");
     SCRIB200_REQUIRE(n_modes > 0 && G > 0, "swsh_synthesize: bad sizes n_modes=%d G=%d", n_modes, G);
     const int K = 2 * n_modes, Nc = 2 * G;
-    SCRIB200_REQUIRE(Kpad % BK == 0 && Kpad >= K, "swsh_synthesize: Kpad=%d must be a multiple of %d >= %d", Kpad, BK, K);
+    SCRIB200_REQUIRE(Kpad % 16 == 0 && Kpad >= K, "swsh_synthesize: Kpad=%d must be a multiple of 16 >= %d", Kpad, K);
     SCRIB200_REQUIRE(Ncpad % BN == 0 && Ncpad >= Nc, "swsh_synthesize: Ncpad=%d must be a multiple of %d >= %d", Ncpad,
                      BN, Nc);
     SCRIB200_REQUIRE(aligned16(modes) && aligned16(Bmat) && aligned16(F) && aligned16(offset) && aligned16(scale),
                      "swsh_synthesize: pointers must be 16-byte aligned");
     if (n_times <= 0) return SCRIB200_OK;
-    cudaFuncSetAttribute(swsh_synth_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYNTH_SMEM);
+    int variant = 0;
+    if (const char* env = getenv("SCRIB200_SYNTH_VARIANT")) variant = atoi(env);
     // column tiles fastest so the CTAs sharing an A row-tile run together (A is then read from HBM once);
     // gridDim.y is limited to 65535, so very long series go in slabs of rows
-    const int64_t max_rows = (int64_t)65535 * BM;
+    const int64_t max_rows = (int64_t)65535 * 64;
     for (int64_t r0 = 0; r0 < n_times; r0 += max_rows) {
         int64_t rows = n_times - r0 < max_rows ? n_times - r0 : max_rows;
-        dim3 grid(Ncpad / BN, (unsigned)((rows + BM - 1) / BM));
-        swsh_synth_dmma_kernel<<<grid, SYNTH_THREADS, SYNTH_SMEM, (cudaStream_t)stream>>>(
-            modes + r0 * K, rows, K, Bmat, Kpad, Ncpad, offset, scale, Nc, F + r0 * Nc);
+#define SYNTH_LAUNCH(BK_, ST_, BM_)                                                                                    \
+    do {                                                                                                               \
+        dim3 grid_(Ncpad / BN, (unsigned)((rows + BM_ - 1) / BM_));                                                    \
+        cudaFuncSetAttribute(swsh_synth_dmma_kernel<BK_, ST_, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                             (int)SynthCfg<BK_, ST_, BM_>::SMEM);                                                      \
+        swsh_synth_dmma_kernel<BK_, ST_, BM_><<<grid_, 2 * BM_, SynthCfg<BK_, ST_, BM_>::SMEM, (cudaStream_t)stream>>>( \
+            modes + r0 * K, rows, K, Bmat, Kpad, Ncpad, offset, scale, Nc, F + r0 * Nc);                               \
+    } while (0)
+        // measured at config 2 (K = 160): 128x64 / BK16 / 3 stages 1.47 ms, 64x64 / BK16 / 3 stages 1.33 ms, 64x64 / BK8 / 4 stages 1.30 ms
+        if (variant == 1) SYNTH_LAUNCH(16, 3, 128);
+        else if (variant == 2) SYNTH_LAUNCH(16, 3, 64);
+        else SYNTH_LAUNCH(8, 4, 64);
+#undef SYNTH_LAUNCH
         SCRIB200_CHECK_LAUNCH("swsh_synthesize");
     }
     return SCRIB200_OK;
