@@ -75,7 +75,7 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *
  * scrib200_spline_prepare (once per time axis): the knots of all grid points are affine images of t, so the
  * tridiagonal moment system is factorised once, in t-units:
- *   tab  [n_times, 8]  (P, Q, W, 1/h, Phi, c', Psi, h) per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
+ *   tab  [n_times, 8]  (P, Q, Phi, c', W, Psi, h, 1/h) per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
  *   uprm [n_times]     u'_i = gamma_factor * (t_i - time_translation) (divide = 0, gamma_factor = 1/gamma: the
  *                      WaveformGrid arithmetic) or (t_i - time_translation) / gamma_factor (divide = 1, gamma_factor =
  *                      gamma: scri/asymptotic_bondi_data/transformations.py:393); may be NULL together with kconf/alpha

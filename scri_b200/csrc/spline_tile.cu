@@ -37,7 +37,8 @@ namespace scrib200 {
 constexpr int ST_COLS = 16;            // real columns per CTA
 constexpr int ST_PITCH = ST_COLS + 2;  // doubles per shared-memory row (144 B: consecutive rows shift by 4 banks)
 constexpr int ST_BR = 16;              // rows per sweep block (global alignment)
-constexpr int ST_TAB = 8;              // doubles per table row: P, Q, W, 1/h | Phi, c', Psi, h
+constexpr int ST_TAB = 8;              // doubles per table row in HBM: P, Q, Phi, c' | W, Psi, h, 1/h
+constexpr int ST_TAB6 = 6;             // the first six live in the sweep table in shared memory, (h, 1/h) in a compact array
 constexpr int FACTOR_RUNIN = 40;
 constexpr int ST_MAXBLK = 24;          // max sweep blocks per tile (384 threads)
 
@@ -125,8 +126,8 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
     double row[ST_TAB] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (i <= N - 2) {
         const double h = t[i + 1] - t[i];
-        row[3] = 1.0 / h;
-        row[7] = h;
+        row[6] = h;
+        row[7] = 1.0 / h;
     }
     if (i >= 1 && i <= N - 2) {
         const int bstart = (i & ~(ST_BR - 1)) > 1 ? (i & ~(ST_BR - 1)) : 1;
@@ -145,12 +146,12 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
             if (r == i) {
                 row[0] = 6.0 * e / hp;
                 row[1] = 6.0 * e / hm;
-                row[2] = W;
-                row[5] = cp;
+                row[4] = W;
+                row[3] = cp;
             }
         }
-        row[4] = phi;
-        row[6] = psi;
+        row[2] = phi;
+        row[5] = psi;
     }
     double4* dst = reinterpret_cast<double4*>(tab + (size_t)i * ST_TAB);
     dst[0] = make_double4(row[0], row[1], row[2], row[3]);
@@ -170,8 +171,8 @@ spline_decay_kernel(const double* __restrict__ tab, int N, double* __restrict__ 
     if (i >= 64 && i <= N - 2) {
         double pw = 1.0, pc = 1.0;
         for (int r = i; r > i - 64; --r) {
-            pw *= fabs(tab[(size_t)r * ST_TAB + 2]);
-            pc *= fabs(tab[(size_t)r * ST_TAB + 5]);
+            pw *= fabs(tab[(size_t)r * ST_TAB + 4]);
+            pc *= fabs(tab[(size_t)r * ST_TAB + 3]);
             if (r == i - 31) d32 = fmax(pw, pc);
         }
         d64 = fmax(pw, pc);
@@ -215,8 +216,8 @@ spline_jrange_kernel(const double* __restrict__ t, int N, int G, const double* _
 // MODE 4: the increment of the second antiderivative, `up` then holding the (scanned) first antiderivative [N, G].
 // For MODE >= 1 `out` is [N, G] complex time-major and Nout/tshift are unused.
 // blockDim.x >= 16 * (body + 2 halo) / 16 (one half-warp per sweep block), body and halo multiples of 16.
-template <int MODE>
-__global__ void __launch_bounds__(ST_MAXBLK * ST_COLS, 2)
+template <int MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
 spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict__ F, int G,
                    const double* __restrict__ kconf, const double* __restrict__ alpha,
                    const double* __restrict__ tab, const double* __restrict__ up, int Nout,
@@ -240,14 +241,17 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
 
     double* sY = s_mem;                                     // [ymax][ST_PITCH]  F            row r -> r - ylo
     double* sD = sY + (size_t)ymax * ST_PITCH;              // [ymax][ST_PITCH]  d0, m0, M    row r -> r - ylo
-    double* sTab = sD + (size_t)ymax * ST_PITCH;            // [ymax][ST_TAB]                 row r -> r - ylo
-    double* sT = sTab + (size_t)ymax * ST_TAB;              // [ymax]                         row r -> r - ylo
+    double* sTab = sD + (size_t)ymax * ST_PITCH;            // [ymax][ST_TAB6] P, Q, Phi, c', W, Psi   row r -> r - ylo
+    double2* sH = reinterpret_cast<double2*>(sTab + (size_t)ymax * ST_TAB6);   // [ymax] (h, 1/h): consecutive rows are
+                                                            //          contiguous, so the evaluation's gathers are conflict free
+    double* sT = reinterpret_cast<double*>(sH + ymax);      // [ymax]                         row r -> r - ylo
     const int nblk_max = (body + 2 * halo) / ST_BR;
     double* sEdgeD = sT + ymax + (ymax & 1);                // [nblk_max][ST_COLS] d0 at the block ends
     double* sEdgeM = sEdgeD + nblk_max * ST_COLS;           // [nblk_max][ST_COLS] m0 at the block starts
 #define SY(r_, c_) sY[((r_) - ylo) * ST_PITCH + (c_)]
 #define SD(r_, c_) sD[((r_) - ylo) * ST_PITCH + (c_)]
-#define STAB(r_, f_) sTab[((r_) - ylo) * ST_TAB + (f_)]
+#define STAB(r_, f_) sTab[((r_) - ylo) * ST_TAB6 + (f_)]
+#define SH(r_) sH[(r_) - ylo]
 #define STT(r_) sT[(r_) - ylo]
 
     // ---- stage the tile: F rows (16-byte copies, 8 per row), the factor table rows and the sample times
@@ -265,7 +269,11 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
             }
         }
         const double* tsrc = tab + (size_t)ylo * ST_TAB;
-        for (int e = tid; e < nyrows * (ST_TAB / 2); e += nthr) st_cp_async16(sTab + 2 * e, tsrc + 2 * e);
+        for (int e = tid; e < nyrows * (ST_TAB / 2); e += nthr) {
+            const int rr = e >> 2, ch = e & 3;             // chunks 0..2 -> sweep table, chunk 3 -> (h, 1/h)
+            if (ch < 3) st_cp_async16(sTab + rr * ST_TAB6 + 2 * ch, tsrc + 2 * e);
+            else st_cp_async16(sH + rr, tsrc + 2 * e);
+        }
         for (int e = tid; e < nyrows; e += nthr) st_cp_async8(sT + e, t + ylo + e);
     }
     // per-column constants and (MODE 0) the output range of each complex column, found while the copies fly
@@ -295,14 +303,23 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     constexpr int UPRE = 8;
     double upre[UPRE];
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    int jlo0 = 0, jhi0 = 0;
-    if (MODE == 0 && warp < ST_COLS / 2 && blockIdx.x * (ST_COLS / 2) + warp < G) {
-        jlo0 = s_jlo[warp];
-        jhi0 = s_jhi[warp];
+    // evaluation work items: (complex column, part of its output range); with >= 16 warps a column is split in two
+    const int nsplit = (nwarp >= ST_COLS) ? 2 : 1;
+    auto item_range = [&](int item, int& c, int& j0, int& j1) {
+        c = item % (ST_COLS / 2);
+        const int part = item / (ST_COLS / 2);
+        const int jlo = s_jlo[c], jhi = s_jhi[c];
+        const int chunk = (((jhi - jlo + nsplit - 1) / nsplit) + 31) & ~31;
+        j0 = jlo + part * chunk;
+        j1 = (j0 + chunk < jhi) ? j0 + chunk : jhi;
+    };
+    if (MODE == 0 && warp < nsplit * (ST_COLS / 2) && blockIdx.x * (ST_COLS / 2) + warp % (ST_COLS / 2) < G) {
+        int c, j0, j1;
+        item_range(warp, c, j0, j1);
 #pragma unroll
         for (int it = 0; it < UPRE; ++it) {
-            const int j = jlo0 + lane + 32 * it;
-            upre[it] = (j < jhi0) ? up[j] : 0.0;
+            const int j = j0 + lane + 32 * it;
+            upre[it] = (j < j1) ? up[j] : 0.0;
         }
     }
     const bool full = active && (r1 - r0 == ST_BR - 1);     // all but the blocks at the ends of the series
@@ -313,8 +330,8 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         auto step = [&](int r) {
             const double yn = SY(r + 1, cc);
             const double dy = yn - yc;
-            const double4 tb = *reinterpret_cast<const double4*>(&STAB(r, 0));
-            d = fma(-tb.z, d, tb.x * dy - tb.y * dym);
+            const double2 pq = *reinterpret_cast<const double2*>(&STAB(r, 0));
+            d = fma(-STAB(r, 4), d, pq.x * dy - pq.y * dym);
             SD(r, cc) = d;
             yc = yn;
             dym = dy;
@@ -333,12 +350,12 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         double D = 0.0, w = 1.0;
         for (int p = q - 1; p >= qlo; --p) {
             D = fma(w, sEdgeD[(p - qlo) * ST_COLS + cc], D);
-            w *= STAB(p * ST_BR + ST_BR - 1, 4);
+            w *= STAB(p * ST_BR + ST_BR - 1, 2);
             if (fabs(w) < 1e-24) break;
         }
         double m = 0.0;
         auto step = [&](int r) {                            // backward from a zero start, on the corrected d
-            const double2 pc = *reinterpret_cast<const double2*>(&STAB(r, 4));
+            const double2 pc = *reinterpret_cast<const double2*>(&STAB(r, 2));
             const double d = fma(pc.x, D, SD(r, cc));
             m = fma(-pc.y, m, d);
             SD(r, cc) = m;
@@ -356,15 +373,15 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         double E = 0.0, w = 1.0;
         for (int p = q + 1; p <= qhi; ++p) {
             E = fma(w, sEdgeM[(p - qlo) * ST_COLS + cc], E);
-            w *= STAB(p * ST_BR, 6);
+            w *= STAB(p * ST_BR, 5);
             if (fabs(w) < 1e-24) break;
         }
         if (E != 0.0) {
             if (full) {
 #pragma unroll
-                for (int k = 0; k < ST_BR; ++k) SD(r0 + k, cc) = fma(STAB(r0 + k, 6), E, SD(r0 + k, cc));
+                for (int k = 0; k < ST_BR; ++k) SD(r0 + k, cc) = fma(STAB(r0 + k, 5), E, SD(r0 + k, cc));
             } else {
-                for (int r = r0; r <= r1; ++r) SD(r, cc) = fma(STAB(r, 6), E, SD(r, cc));
+                for (int r = r0; r <= r1; ++r) SD(r, cc) = fma(STAB(r, 5), E, SD(r, cc));
             }
         }
     }
@@ -386,11 +403,12 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         double2* o2 = reinterpret_cast<double2*>(out);
         const int tmask = (1 << tshift) - 1;
         const int64_t tileGT = (int64_t)G << tshift;
-        for (int c = warp; c < ST_COLS / 2; c += nwarp) {
+        for (int item = warp; item < nsplit * (ST_COLS / 2); item += nwarp) {
+            int c, jlo, jhi;
+            item_range(item, c, jlo, jhi);
             const int g = blockIdx.x * (ST_COLS / 2) + c;
             if (g >= G) continue;
             const double k = s_k[c], al = s_al[c], ik = s_ik[c];
-            const int jlo = s_jlo[c], jhi = s_jhi[c];
             const double xa = __dmul_rn(k, __dsub_rn(STT(a), al));
             const double xbv = __dmul_rn(k, __dsub_rn(STT(b), al));
             const float slope = (float)((double)(b - a) / (xbv - xa));
@@ -410,11 +428,12 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
                     xi = __dmul_rn(k, __dsub_rn(STT(i), al));
                     xi1 = __dmul_rn(k, __dsub_rn(STT(i + 1), al));
                 }
-                const double ht = STAB(i, 7);
+                const double2 hh = SH(i);
+                const double ht = hh.x;
                 const double hx = xi1 - xi;
                 // 1/hx: hx = k h_t up to the rounding of the abscissae, so two Newton steps from (1/k)(1/h_t) are exact to
                 // rounding; a true division only if the abscissae have lost more than 3 digits of the step
-                double inv_h = ik * STAB(i, 3);
+                double inv_h = ik * hh.y;
                 double e = fma(-hx, inv_h, 1.0);
                 if (fabs(e) < 1e-3) {
                     inv_h = fma(inv_h, e, inv_h);
@@ -440,7 +459,7 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
                 og[o] = r;
             };
             int j = jlo + lane;
-            if (c == warp) {                                // the prefetched output times
+            if (item == warp) {                             // the prefetched output times
 #pragma unroll
                 for (int it = 0; it < UPRE; ++it, j += 32)
                     if (j < jhi) eval_one(j, upre[it]);
@@ -454,7 +473,7 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
         out += (size_t)blockIdx.z * N * G2;
         if (MODE == 4) up += (size_t)blockIdx.z * N * G2;
         for (int i = a + tid / ST_COLS; i < b; i += rstep) {
-            const double ht = STAB(i, 7);
+            const double ht = SH(i).x;
             const double yi = SY(i, cc), yi1 = SY(i + 1, cc);
             const double Mi = SD(i, cc), Mi1 = SD(i + 1, cc);
             if (!colok) continue;
@@ -481,6 +500,7 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
 #undef SY
 #undef SD
 #undef STAB
+#undef SH
 #undef STT
 }
 
@@ -569,11 +589,18 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     SCRIB200_REQUIRE(nblk <= ST_MAXBLK && smem <= 220 * 1024, "%s: body=%d halo=%d does not fit one CTA", name, body, halo);
     const int64_t ntiles = (n_times - 1 + body - 1) / body;
     SCRIB200_REQUIRE(ntiles <= 65535, "%s: too many time tiles (%lld); raise `body`", name, (long long)ntiles);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(spline_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int threads = ((nblk * ST_COLS + 31) / 32) * 32;         // one half-warp per sweep block
+    bool wide = false;
+    if (MODE == 0 && getenv("SCRIB200_SPLINE_WIDE") != nullptr) {   // 16 warps: two warps share a column in the evaluation
+        threads = 512;
+        wide = true;
+    }
+    if (smem > 48 * 1024) {
+        if (wide) cudaFuncSetAttribute(spline_tile_kernel<MODE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     SCRIB200_REQUIRE(n_series >= 1 && n_series <= 65535, "%s: n_series=%d must be 1..65535", name, n_series);
     dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles, (unsigned)n_series);
-    const int threads = ((nblk * ST_COLS + 31) / 32) * 32;   // one half-warp per sweep block
     int* J = nullptr;
     if (MODE == 0) {
         const size_t need = (size_t)(ntiles + 1) * G * sizeof(int);
@@ -584,8 +611,12 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
             t, (int)n_times, G, kconf, alpha, uprm, (int)n_out, body, (int)ntiles, J);
         SCRIB200_CHECK_LAUNCH(name);
     }
-    spline_tile_kernel<MODE><<<grid, threads, smem, (cudaStream_t)stream>>>(
-        t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
+    if (wide)
+        spline_tile_kernel<MODE, 512><<<grid, threads, smem, (cudaStream_t)stream>>>(
+            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
+    else
+        spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS><<<grid, threads, smem, (cudaStream_t)stream>>>(
+            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }
