@@ -196,6 +196,14 @@ int scrib200_weyl_mix(const double* const* fields, const double* coef, int n_fie
                       int G, const double* alpha, const double* A, const double* C, const double* scale,
                       const double* offset, double* out, void* stream);
 
+/* The packed real operand `Bmat` of scrib200_swsh_synthesize built on the device from the rotor grid:
+ * Y[g, (l,m)] = (-1)^s sqrt((2l+1)/4pi) D^l_{m,-s}(R_g) - replaces sf.SWSH_grid(R_j_k, s, ell_max)
+ * (scri/waveform_grid.py:470-471) and the host-side packing.
+ *   rotors [G, 4] (w, x, y, z) unit quaternions; seed [(2Lt+1)^2], uv [Lt, 2Lt+1, 2]: scri_b200._sf.wigner_tables /
+ *   wigner_factor_table for Lt = table_ell_max >= max(ell_max, |spin|); Bmat [Kpad, Ncpad] is zero-filled first. */
+int scrib200_swsh_pack(const double* rotors, int G, int spin, int ell_min, int ell_max, const double* seed,
+                       const double* uv, int table_ell_max, double* Bmat, int Kpad, int Ncpad, void* stream);
+
 /* out[e] = a[e] * b[e] for n complex128 elements: the pointwise product of ModesTimeSeries.grid_multiply
  * (scri/modes_time_series.py:190). */
 int scrib200_grid_product(const double* a, const double* b, double* out, int64_t n, void* stream);

@@ -88,3 +88,81 @@ extern "C" int scrib200_weyl_mix(const double* const* fields, const double* coef
     SCRIB200_CHECK_LAUNCH("weyl_mix");
     return SCRIB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The packed synthesis operand of scrib200_swsh_synthesize, built on the device from the rotor grid:
+//   Y[g, (l, m)] = (-1)^s sqrt((2l+1)/4pi) D^l_{m,-s}(R_g)      (sf.SWSH_grid, scri/waveform_grid.py:470-471)
+//   B[2lm, 2g] = Re Y, B[2lm+1, 2g] = -Im Y, B[2lm, 2g+1] = Im Y, B[2lm+1, 2g+1] = Re Y   (lm counted from ell_min).
+// One thread per (grid point, m): phases from powers of the spinor components, the real factor advanced in l by the
+// three-term recurrence (seed / factored coefficient tables of scri_b200._sf, the same as the rotation kernel's).
+namespace scrib200 {
+
+__global__ void __launch_bounds__(128)
+swsh_pack_kernel(const double* __restrict__ R, int G, int s, int ell_min, int ell_max, const double* __restrict__ seed,
+                 const double2* __restrict__ uv, int Lt, double* __restrict__ B, int Ncpad) {
+    const int nm_out = 2 * ell_max + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= G * nm_out) return;
+    const int g = idx / nm_out, mp = idx - g * nm_out - ell_max;
+    const int m = -s;                                  // column of D
+    const int nmt = 2 * Lt + 1;
+    const double w = R[4 * g], x = R[4 * g + 1], y = R[4 * g + 2], z = R[4 * g + 3];
+    const double2 Ra = make_double2(w, z), Rb = make_double2(y, x);
+    const double cosb = (Ra.x * Ra.x + Ra.y * Ra.y) - (Rb.x * Rb.x + Rb.y * Rb.y);
+    const int amp = mp < 0 ? -mp : mp, am = m < 0 ? -m : m;
+    const int l0 = amp > am ? amp : am;
+    if (l0 > ell_max) return;
+    auto cpow = [](double2 zz, int k) {               // zz^k for k >= 0, conj(zz)^|k| for k < 0
+        if (k < 0) { zz = cconj(zz); k = -k; }
+        double2 acc = make_double2(1.0, 0.0);
+        for (int i = 0; i < k; ++i) acc = cmul(acc, zz);
+        return acc;
+    };
+    const double2 ph = cmul(cpow(Ra, mp + m), cpow(Rb, m - mp));
+    double P = seed[(mp + Lt) * nmt + (m + Lt)], Pm1 = 0.0;
+    const double sgn = (s & 1) ? -1.0 : 1.0;
+    const double mmp = (double)(m * mp);
+    for (int l = l0; l <= ell_max; ++l) {
+        if (l >= ell_min) {
+            const double f = sgn * sqrt((2.0 * l + 1.0) / (4.0 * 3.14159265358979323846)) * P;
+            const double re = f * ph.x, im = f * ph.y;
+            const size_t lm = (size_t)(l * (l + 1) - ell_min * ell_min + mp);
+            double* b0 = B + (2 * lm) * Ncpad + 2 * g;
+            double* b1 = b0 + Ncpad;
+            b0[0] = re;
+            b0[1] = im;
+            b1[0] = -im;
+            b1[1] = re;
+        }
+        if (l < ell_max) {
+            const double2 f1 = uv[l * nmt + mp + Lt], f2 = uv[l * nmt + m + Lt];
+            const double rl = (l > 0) ? 1.0 / (double)(l * (l + 1)) : 0.0;
+            const double Pn = (f1.x * f2.x) * (cosb - mmp * rl) * P - (f1.y * f2.y) * Pm1;
+            Pm1 = P;
+            P = Pn;
+        }
+    }
+}
+
+}  // namespace scrib200
+
+extern "C" int scrib200_swsh_pack(const double* rotors, int G, int spin, int ell_min, int ell_max, const double* seed,
+                                  const double* uv, int table_ell_max, double* Bmat, int Kpad, int Ncpad, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(rotors && seed && uv && Bmat, "swsh_pack: null pointer");
+    SCRIB200_REQUIRE(G > 0 && ell_min >= 0 && ell_max >= ell_min, "swsh_pack: bad sizes G=%d ell=[%d, %d]", G, ell_min, ell_max);
+    const int as = spin < 0 ? -spin : spin;
+    SCRIB200_REQUIRE(table_ell_max >= ell_max && table_ell_max >= as, "swsh_pack: tables for ell <= %d cannot serve ell_max=%d, |s|=%d",
+                     table_ell_max, ell_max, as);
+    const int n = ell_max * (ell_max + 2) - ell_min * ell_min + 1;
+    SCRIB200_REQUIRE(Kpad >= 2 * n && Ncpad >= 2 * G, "swsh_pack: Bmat [%d, %d] too small for %d modes x %d points", Kpad, Ncpad, n, G);
+    SCRIB200_REQUIRE(aligned16(uv), "swsh_pack: uv must be 16-byte aligned");
+    cudaError_t e = cudaMemsetAsync(Bmat, 0, (size_t)Kpad * Ncpad * sizeof(double), (cudaStream_t)stream);
+    SCRIB200_REQUIRE(e == cudaSuccess, "swsh_pack: %s", cudaGetErrorString(e));
+    const int total = G * (2 * ell_max + 1);
+    swsh_pack_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rotors, G, spin, ell_min, ell_max, seed,
+                                                                             reinterpret_cast<const double2*>(uv), table_ell_max,
+                                                                             Bmat, Ncpad);
+    SCRIB200_CHECK_LAUNCH("swsh_pack");
+    return SCRIB200_OK;
+}

@@ -71,6 +71,66 @@ def to_device_async(x, dtype=None):
     return _h2d_pool.submit(work)
 
 
+_copy_streams = {}
+
+
+def to_device_slabs(x, dtype=None, n_slabs=4):
+    """Start copying a large host array to the device in `n_slabs` row slabs on a dedicated copy stream (helper thread,
+    GIL-free staging).  Returns (device tensor, slabs, future): slabs = [(row_lo, row_hi, event, flag)], the event of a slab
+    fires when its rows have landed (the host flag says the event has been recorded); `future.result()` returns once every slab has been queued.  Consumers order their
+    kernels after the slab events (TransformPlan.synthesize(slabs=...)), so compute overlaps the rest of the transfer."""
+    global _h2d_pool
+    torch = _torch()
+    a = np.ascontiguousarray(x)
+    if dtype is not None and a.dtype != dtype:
+        a = a.astype(dtype)
+    N = a.shape[0]
+    dev = torch.cuda.current_device()
+    if dev not in _copy_streams:
+        _copy_streams[dev] = torch.cuda.Stream()
+    cs = _copy_streams[dev]
+    out = torch.empty(a.shape, dtype=getattr(torch, a.dtype.name), device="cuda")
+    out.record_stream(cs)
+    cs.wait_stream(torch.cuda.current_stream())          # the allocation (and whatever freed it before) is ordered first
+    bounds = [N * k // n_slabs for k in range(n_slabs + 1)]
+    import threading
+
+    # (row_lo, row_hi, CUDA event recorded once the slab's copies are queued, host flag set once that event exists:
+    #  waiting on an event that has not been recorded yet is a no-op in CUDA, so consumers wait for the flag first)
+    slabs = [(bounds[k], bounds[k + 1], torch.cuda.Event(), threading.Event()) for k in range(n_slabs)]
+    lib = _lib.load()
+    row_bytes = a.nbytes // max(N, 1)
+    if _h2d_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _h2d_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="scrib200-h2d")
+
+    def work():
+        try:
+            with torch.cuda.device(dev):
+                for lo, hi, ev, flag in slabs:
+                    if hi > lo:
+                        _lib.check(
+                            lib.scrib200_h2d(out.data_ptr() + lo * row_bytes, a.ctypes.data + lo * row_bytes, (hi - lo) * row_bytes,
+                                             ctypes_void(cs.cuda_stream)),
+                            "h2d",
+                        )
+                    ev.record(cs)
+                    flag.set()
+        finally:
+            for _, _, _, flag in slabs:      # never leave a consumer waiting if the copy failed
+                flag.set()
+        return out
+
+    return out, slabs, _h2d_pool.submit(work)
+
+
+def ctypes_void(v):
+    import ctypes
+
+    return ctypes.c_void_p(v)
+
+
 def to_host(x):
     """CUDA tensor -> numpy.  The copy lands in pinned memory from torch's caching host allocator (DMA at full PCIe
     rate, no page-fault cost after the first call); the returned array owns that block until it is collected."""

@@ -202,14 +202,20 @@ def pack_synthesis_matrix(Y, ell_min, ell_max):
     return B, Kpad, Ncpad
 
 
+_blas_controller = None
+
+
 def _quiet_blas():
     """The plan's host algebra is a handful of tiny matrix products; run them on one BLAS thread.  A multi-threaded
     BLAS leaves its 16 workers spinning for tens of milliseconds after each call, which is exactly when the pinned
     staging copy of the waveform wants the cores (measured: 3 ms -> 10 ms for 124 MB)."""
+    global _blas_controller
     try:
-        from threadpoolctl import threadpool_limits
+        if _blas_controller is None:
+            from threadpoolctl import ThreadpoolController
 
-        return threadpool_limits(limits=1, user_api="blas")
+            _blas_controller = ThreadpoolController()   # introspecting the loaded libraries costs ~2 ms: do it once
+        return _blas_controller.limit(limits=1, user_api="blas")
     except Exception:  # threadpoolctl missing: correctness does not depend on it
         import contextlib
 
@@ -367,7 +373,9 @@ class TransformPlan(GridPlan):
         s = self.spin_weight
 
         R = R_j_k.reshape(-1, 4)
-        Y = _sf.SWSH_grid(R, s, max(L, self.ell_max))  # [G, (L+1)^2]
+        # the big table sY_lm(R_g) for the waveform's own modes is built on the device (scrib200_swsh_pack); the host only
+        # needs the few columns l <= ell_max_st that enter the constant corrections below
+        Y = _sf.SWSH_grid(R, s, ell_max_st) if self.dataType in (h, sigma) else None
         SH = _sf.SWSH_grid(R, 0, ell_max_st)
         rhat = Q.rotate_z(R)
         self.kconformal = 1.0 / (gamma * (1 - rhat @ boost_velocity))
@@ -420,7 +428,8 @@ class TransformPlan(GridPlan):
                 )
         scale = self.kconformal**self.conformal_weight
         self.scale = scale
-        B, self.Kpad, self.Ncpad = pack_synthesis_matrix(Y, self.ell_min, self.ell_max)
+        self.Kpad = -(-2 * _sf.LM_total_size(self.ell_min, self.ell_max) // 16) * 16
+        self.Ncpad = -(-2 * self.G // 64) * 64
         off = np.zeros(self.Ncpad)
         off[0 : 2 * self.G : 2] = offset_c.real
         off[1 : 2 * self.G : 2] = offset_c.imag
@@ -434,7 +443,19 @@ class TransformPlan(GridPlan):
 
         dev = self.device
         f64 = torch.float64
-        self.d_B = torch.from_numpy(B).to(dev)
+        from . import ops
+
+        Lt = max(self.ell_max, abs(s))
+        seed_d, _, uv_d = ops.wigner_tables_device(Lt)
+        d_R = torch.from_numpy(np.ascontiguousarray(R)).to(dev)
+        self.d_B = torch.empty((self.Kpad, self.Ncpad), dtype=f64, device=dev)
+        _lib.check(
+            _lib.load().scrib200_swsh_pack(
+                _lib.ptr(d_R), self.G, s, self.ell_min, self.ell_max, _lib.ptr(seed_d), _lib.ptr(uv_d), Lt, _lib.ptr(self.d_B),
+                self.Kpad, self.Ncpad, _lib.stream_ptr(),
+            ),
+            "swsh_pack",
+        )
         self.d_offset = torch.from_numpy(off).to(dev)
         self.d_scale = torch.from_numpy(scl).to(dev)
         if self.mix:
@@ -459,22 +480,31 @@ class TransformPlan(GridPlan):
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
         self.spline_body = 0   # 0 = default intervals per tile
 
-    def synthesize(self, data, t=None):
+    def synthesize(self, data, t=None, slabs=None):
         """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-559).  `t` (device) is needed for
-        psi0..psi3 only, whose mixing factor depends on time."""
+        psi0..psi3 only, whose mixing factor depends on time.  `slabs` = [(row_lo, row_hi, event, flag), ...]: the rows of
+        `data` are still arriving from the host slab by slab (ops.to_device_slabs); each slab is synthesized as soon as its
+        event has fired, so the GEMM runs under the rest of the transfer."""
         import ctypes
 
         torch = self.torch
         lib = _lib.load()
         N = data.shape[0]
         F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
-        _lib.check(
-            lib.scrib200_swsh_synthesize(
-                _lib.ptr(data), N, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad, _lib.ptr(self.d_offset),
-                _lib.ptr(self.d_scale), self.G, _lib.ptr(F), _lib.stream_ptr(),
-            ),
-            "swsh_synthesize",
-        )
+        cur = torch.cuda.current_stream()
+        for lo, hi, ev, flag in (slabs or [(0, N, None, None)]):
+            if ev is not None:
+                flag.wait()            # the copy thread has recorded the event (waiting on an unrecorded event is a no-op)
+                cur.wait_event(ev)
+            if hi <= lo:
+                continue
+            _lib.check(
+                lib.scrib200_swsh_synthesize(
+                    _lib.ptr(data[lo:hi]), hi - lo, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad,
+                    _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F[lo:hi]), _lib.stream_ptr(),
+                ),
+                "swsh_synthesize",
+            )
         if not self.mix:
             return F
         if t is None:
@@ -537,7 +567,7 @@ class TransformPlan(GridPlan):
             self._tile = int(_lib.load().scrib200_map2salm_tile_size(self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max))
         return self._tile
 
-    def run(self, t, data, return_grid=False, t_ends=None, prep=None):
+    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
 
         The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
@@ -546,7 +576,7 @@ class TransformPlan(GridPlan):
         cur = self.torch.cuda.current_stream()
         ready = self.torch.cuda.Event()
         ready.record(cur)
-        F = self.synthesize(data, t)            # queued first: the GPU is busy while the host launches the preparation
+        F = self.synthesize(data, t, slabs)     # queued first: the GPU is busy while the host launches the preparation
         if prep is None:
             prep = self.prepare(t, overlapped=True, after=ready)
         cur.wait_event(prep.done)

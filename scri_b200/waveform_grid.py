@@ -128,16 +128,29 @@ class WaveformGrid(WaveformBase):
                 f"\nInput waveform object must be in an inertial frame; this is in a frame of type `{w_modes.frame_type_string}`"
             )
         original_kwargs = kwargs.copy()
-        a_fut = ops.to_device_async(w_modes.data, np.complex128)   # streams in while the plan is built
+        # the modes stream in slab by slab on a copy stream while the plan is built; each slab is synthesized as it lands
+        big = w_modes.data.nbytes >= (8 << 20)
+        if big:
+            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128)
+        else:
+            a_d, slabs, a_fut = ops.to_device(w_modes.data, np.complex128), None, None
         try:
             plan = TransformPlan(
                 w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out,
                 out_ell_max=ell_max, **kwargs,
             )
-        finally:
-            a_d = a_fut.result()
-        t_d = ops.to_device(w_modes.t, np.float64)
-        uprm, modes = plan.run(t_d, a_d)
+            t_d = ops.to_device(w_modes.t, np.float64)
+        except BaseException:
+            if a_fut is not None:
+                a_fut.result()                   # let the copy thread finish with w_modes.data before unwinding
+            raise
+        if plan.mix and slabs is not None:       # the Weyl mixing reads whole fields: wait for the transfer
+            a_fut.result()
+            _lib.require_cuda().cuda.current_stream().wait_event(slabs[-1][2])
+            slabs = None
+        uprm, modes = plan.run(t_d, a_d, slabs=slabs)
+        if a_fut is not None:
+            a_fut.result()                       # surfaces a failed copy
         if plan.leftover_kwargs:
             warnings.warn("\nUnused kwargs passed to this function:\n{}".format(pprint.pformat(plan.leftover_kwargs, width=1)))
         return WaveformModes(
