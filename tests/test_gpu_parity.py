@@ -544,3 +544,22 @@ def test_batched_transform_equals_single_transforms():
 
     up2, out2 = parallel.transform_batch(pl, td, bd)
     assert torch.equal(out2, out)
+
+
+def test_million_step_transform_window_vs_oracle():
+    """Largest size of BASELINE.json (1e6 time steps): 4167 time tiles, 10 GB of intermediates, 64-bit indexing.  The
+    spline couples samples only locally, so a 3000-sample window of the input reproduces the interior of the full result."""
+    N = 1_000_000
+    t = np.linspace(0.0, 1e5, N)
+    _, data = smooth_modes(n_times=N, t0=0.0, t1=1e5, seed=16)
+    kw = dict(supertranslation=real_supertranslation(3, seed=2), frame_rotation=[1.0, -2.0, 0.5, 3.0])     # no boost: the window stays put
+    pl = P.TransformPlan(2, 8, sb.h, **kw)
+    up, out = pl.run(ops.to_device(t), ops.to_device(data))
+    upn, outn = up.cpu().numpy(), out.cpu().numpy()
+    assert upn.shape[0] > N - 10 and np.all(np.diff(upn) > 0)
+    for lo in (0, 499_000, N - 3000):
+        ref = R.transform(R.Modes(t=t[lo : lo + 3000], data=data[lo : lo + 3000].copy()), **kw)
+        inner = ref.t[200:-200]
+        sel = np.searchsorted(upn, inner)
+        assert np.array_equal(upn[sel], inner)
+        assert rel(outn[sel], ref.data[200:-200]) < RTOL
