@@ -336,26 +336,26 @@ def run_ours(args):
         }
         if per_kernel[2] >= per_kernel[0]:
             ach = kern["spline_tile(spline_remap)"]["achieved_gbs"]
-            roof = {"kernel": "spline_tile_kernel<0>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            roof = {"kernel": "spline_tile_kernel<0, 384>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                     "algorithmic_bytes_per_launch": remap_bytes}
         else:
             ach = kern["swsh_synth_dmma"]["achieved_tflops"]
-            roof = {"kernel": "swsh_synth_dmma_kernel", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
+            roof = {"kernel": "swsh_synth_dmma_kernel<8, 4, 64>", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
                     "frac": ach / dgemm_tf, "traffic": None,
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "algorithmic_flops_per_launch": synth_flops}
         # DRAM traffic per launch from the committed ncu --set full capture of the same kernels (profiles/), never measured here
         try:
-            with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
                 traffic = json.load(f)
-            names = {"swsh_synth_dmma": "swsh_synth_dmma_kernel", "spline_tile(spline_remap)": "spline_tile_kernel<0>",
+            names = {"swsh_synth_dmma": "swsh_synth_dmma_kernel<8, 4, 64>", "spline_tile(spline_remap)": "spline_tile_kernel<0, 384>",
                      "map2salm_tiled": "map2salm_persist_kernel<1>"}
             for kname, ncu_name in names.items():
                 if ncu_name in traffic:
-                    kern[kname]["dram_bytes_per_launch(ncu, profiles/r01b_ncu_summary.md)"] = traffic[ncu_name]["dram_bytes_per_launch"]
+                    kern[kname]["dram_bytes_per_launch(ncu, profiles/r01c_ncu_summary.md)"] = traffic[ncu_name]["dram_bytes_per_launch"]
             roof["traffic"] = traffic.get(roof["kernel"], {}).get("dram_bytes_per_launch")
-            roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01b_ncu_summary.md (N = 1e5 capture)"
+            roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01c_ncu_summary.md (N = 1e5 capture)"
         except Exception:
             pass
         # CPU baseline: oracle port, single thread + BLAS, bounded sample
