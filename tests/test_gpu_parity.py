@@ -563,3 +563,53 @@ def test_million_step_transform_window_vs_oracle():
         sel = np.searchsorted(upn, inner)
         assert np.array_equal(upn[sel], inner)
         assert rel(outn[sel], ref.data[200:-200]) < RTOL
+
+
+def _sharded_flux_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from scri_b200 import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # one GPU here: gloo carries the halos (NCCL on a real node)
+    try:
+        t, data = smooth_modes(n_times=4000, t0=0.0, t1=400.0, seed=23)
+        lo, hi = parallel.shard_range(t.size, rank, world)
+        td, dd = ops.to_device(t[lo:hi].copy()), ops.to_device(data[lo:hi].copy())
+        e, p, j = parallel.sharded_fluxes(td, dd, 2, 8)
+        d2 = parallel.sharded_time_derivative(td, dd, 2)
+        q.put((rank, lo, hi, e.cpu().numpy(), p.cpu().numpy(), j.cpu().numpy(), d2.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_sharded_fluxes_world2():
+    """time sharding - halo exchange of input modes, local spline derivative, pointwise fluxes - equals the
+    single-process result (two ranks sharing the one GPU of the test box, gloo for the halos)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s_ = socket.socket()
+    s_.bind(("127.0.0.1", 0))
+    port = s_.getsockname()[1]
+    s_.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_flux_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    t, data = smooth_modes(n_times=4000, t0=0.0, t1=400.0, seed=23)
+    w = modes(t, data)
+    E, pd, J = w.energy_flux(), w.momentum_flux(), w.angular_momentum_flux()
+    dd = w.data_ddot
+    assert (res[0][1], res[0][2], res[1][2]) == (0, 2000, 4000)
+    assert rel(np.concatenate([r[3] for r in res]), E) < 1e-12
+    assert rel(np.concatenate([r[4] for r in res]), pd) < 1e-12
+    assert rel(np.concatenate([r[5] for r in res]), J) < 1e-12
+    assert rel(np.concatenate([r[6] for r in res]), dd) < 1e-10
