@@ -613,3 +613,19 @@ def test_time_sharded_fluxes_world2():
     assert rel(np.concatenate([r[4] for r in res]), pd) < 1e-12
     assert rel(np.concatenate([r[5] for r in res]), J) < 1e-12
     assert rel(np.concatenate([r[6] for r in res]), dd) < 1e-10
+
+
+@pytest.mark.parametrize("grid", [dict(n_theta=27, n_phi=31), dict(n_theta=33, n_phi=25), dict(n_theta=26, n_phi=26, ell_max=5)])
+def test_transform_on_user_chosen_grids(grid):
+    """`n_theta`, `n_phi` and the output `ell_max` are user keywords (scri/waveform_grid.py:97-110, 627): non-square and
+    oversampled grids take the general analysis path (quadrature tables and tile sizes follow the grid)."""
+    t, data = smooth_modes(n_times=300, seed=12)
+    kw = dict(BMS, **grid)
+    out = modes(t, data).transform(**kw)
+    ref = R.transform(R.Modes(t=t, data=data.copy()), **kw)
+    assert np.array_equal(out.t, ref.t)
+    assert out.ell_max == grid.get("ell_max", 8) and out.data.shape == ref.data.shape
+    assert rel(out.data, ref.data) < RTOL
+    g = modes(t, data).to_grid(**{k: v for k, v in kw.items() if k != "ell_max"})
+    go = R.from_modes(R.Modes(t=t, data=data.copy()), **{k: v for k, v in kw.items() if k != "ell_max"})
+    assert (g.n_theta, g.n_phi) == (go.n_theta, go.n_phi) and rel(g.data, go.data) < RTOL
