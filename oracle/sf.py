@@ -245,3 +245,29 @@ def vector_from_ell_1_modes(modes):
             a1 / math.sqrt(4 * math.pi / 3),
         ]
     )
+
+
+# ----------------------------------------------------------------------------- Modes.multiply (3j product)
+def modes_multiply(a, s1, ell1_max, b, s2, ell2_max, ell_out):
+    """Exact mode weights of the product of two spin-weighted functions, truncated at ell_out: the sum over Wigner 3j
+    symbols that spherical_functions' Modes.multiply evaluates (called at scri/asymptotic_bondi_data/bms_charges.py:40-187):
+      (fg)_{lm} = sum f_{l1 m1} g_{l2 m2} (-1)^{m+s} sqrt((2l1+1)(2l2+1)(2l+1)/4pi)
+                      (l1 l2 l; m1 m2 -m) (l1 l2 l; -s1 -s2 s),     s = s1 + s2, m = m1 + m2,
+    modes of both factors and of the result stored from ell = 0.  Pinned by tests/test_oracle.py against the grid
+    product of the pinned spinsfast restatement (the two are independent computations of the same coefficients)."""
+    s = s1 + s2
+    out = np.zeros(a.shape[:-1] + ((ell_out + 1) ** 2,), dtype=complex)
+    for l1 in range(abs(s1), ell1_max + 1):
+        for l2 in range(abs(s2), ell2_max + 1):
+            for l in range(max(abs(l1 - l2), abs(s)), min(l1 + l2, ell_out) + 1):
+                w_s = Wigner3j(l1, l2, l, -s1, -s2, s)
+                if w_s == 0.0:
+                    continue
+                pref = math.sqrt((2 * l1 + 1) * (2 * l2 + 1) * (2 * l + 1) / (4 * math.pi)) * w_s
+                for m1 in range(-l1, l1 + 1):
+                    for m2 in range(max(-l2, -l - m1), min(l2, l - m1) + 1):
+                        m = m1 + m2
+                        w = Wigner3j(l1, l2, l, m1, m2, -m)
+                        if w != 0.0:
+                            out[..., l * (l + 1) + m] += ((-1) ** ((m + s) % 2) * pref * w) * a[..., l1 * (l1 + 1) + m1] * b[..., l2 * (l2 + 1) + m2]
+    return out

@@ -24,6 +24,11 @@ SIGNATURES = {
     "scrib200_weyl_mix": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_swsh_pack": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp]),
     "scrib200_grid_product": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "scrib200_modes_product_max_shared_bytes": (c_sz, []),
+    "scrib200_modes_product": (
+        c_int,
+        [c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp],
+    ),
     "scrib200_h2d": (c_int, [c_vp, c_vp, c_sz, c_vp]),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),

@@ -1,0 +1,126 @@
+"""Host tables of the fused, separable mode product (K9, csrc/product.cu).
+
+`ModesTimeSeries.grid_multiply` (scri/modes_time_series.py:142-202) evaluates both factors on spinsfast's regular
+(theta, phi) grid, multiplies pointwise and analyses the product.  On that grid sY_lm(theta_j, phi_k) =
+lambda_lm(theta_j) e^{i m phi_k}, so the whole chain is, ring by ring, a Wigner-d contraction over l, a convolution
+over m and a theta quadrature; the kernel needs the lambda and quadrature tables laid out as DMMA fragments and the
+mode permutation that makes the l of one m contiguous in shared memory.  Pure layout work: no data-path arithmetic.
+"""
+from functools import lru_cache
+
+import numpy as np
+
+from . import _sf
+
+GM = 9          # consecutive M per convolution warp (csrc/product.cu: PRODUCT_GM)
+T = 4           # time steps per CTA pass (PRODUCT_T)
+MAX_WARPS = 8
+MAX_TILES_PER_WARP = 21
+MAX_KSTEPS = 9
+MAX_SMEM = 227 * 1024
+
+
+class ProductTables:
+    """Numpy tables + the configuration vector of scrib200_modes_product; `fits` is False when one CTA cannot hold the
+    problem (callers then use the dense synthesis / analysis kernels)."""
+
+
+def _lambda(s, ell_max, n_theta):
+    """lambda_lm(theta_j) = sY_lm(theta_j, 0) on spinsfast's rings theta_j = pi j / (n_theta - 1): [n_theta, (ell_max+1)^2]."""
+    theta = np.pi * np.arange(n_theta) / (n_theta - 1)
+    R = np.stack([np.cos(theta / 2), np.zeros_like(theta), np.sin(theta / 2), np.zeros_like(theta)], axis=-1)
+    return np.ascontiguousarray(_sf.SWSH_grid(R, s, ell_max).real)
+
+
+def _field_layout(ell_min, ell_max):
+    """m-major layout of one factor: for every m the l = max(|m|, ell_min) .. ell_max are contiguous and padded to a
+    multiple of 4 (one DMMA k-step).  Returns (pos[m + ell_max], ksteps[m + ell_max], padded size, perm[idx])."""
+    ms = np.arange(-ell_max, ell_max + 1)
+    l_lo = np.maximum(np.abs(ms), ell_min)
+    ks = (ell_max - l_lo + 1 + 3) // 4
+    pos = np.concatenate([[0], np.cumsum(4 * ks)])
+    perm = np.empty((ell_max + 1) ** 2 - ell_min**2, dtype=np.int64)
+    for l in range(ell_min, ell_max + 1):
+        m = np.arange(-l, l + 1)
+        perm[l * (l + 1) + m - ell_min**2] = pos[m + ell_max] + (l - l_lo[m + ell_max])
+    return pos[:-1], ks, int(pos[-1]), perm, l_lo
+
+
+@lru_cache(maxsize=16)
+def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out):
+    tb = ProductTables()
+    n_chunks = (n_theta + 7) // 8
+    n_rings = 8 * n_chunks
+    n_mout = 2 * L_out + 1
+    n_groups = (n_mout + GM - 1) // GM
+    nwarps = max(n_groups, min(MAX_WARPS, 4))
+    fields = []
+    base = 0
+    for s, lmin, lmax in ((s1, ell1_min, ell1_max), (s2, ell2_min, ell2_max)):
+        pos, ks, PA, perm, l_lo = _field_layout(lmin, lmax)
+        fields.append(dict(s=s, lmin=lmin, lmax=lmax, pos=pos, ks=ks, PA=PA, perm=perm, l_lo=l_lo, base=base))
+        base += PA
+    PA_total = base
+    szA = 8 * PA_total                                     # doubles: [pos][t = 4][re, im]
+    offF1 = szA
+    nF1 = max(2 * ell1_max + 1, n_mout)                     # the product P_M overwrites F1
+    offF2 = offF1 + 64 * nF1
+    smem_doubles = offF2 + 64 * (2 * ell2_max + 1)
+
+    # output tiles: 8 consecutive l of one M
+    tiles = [(M + L_out, l0) for M in range(-L_out, L_out + 1) for l0 in range(abs(M), L_out + 1, 8)]
+    n_tiles = len(tiles)
+    max_ks = int(max(f["ks"].max() for f in fields))
+    tb.fits = (
+        8 * smem_doubles <= MAX_SMEM
+        and n_groups <= MAX_WARPS
+        and -(-n_tiles // nwarps) <= MAX_TILES_PER_WARP
+        and max_ks <= MAX_KSTEPS
+        and n_theta >= 2
+    )
+    tb.smem_bytes = 8 * smem_doubles
+    if not tb.fits:
+        return tb
+
+    # stage A: lambda fragments.  lam_pad[ring, base + pos] in the m-major padded order, then per (chunk, k-step) the
+    # 8 rings x 4 l block in lane order (row = lane/4 = ring, k = lane%4 = l)
+    lam_pad = np.zeros((n_rings, PA_total))
+    tasks = []
+    for fi, f in enumerate(fields):
+        lam = _lambda(f["s"], f["lmax"], n_theta)           # [n_theta, (lmax+1)^2], zero for l < |s|
+        n = f["perm"].shape[0]
+        lam_pad[:n_theta, f["base"] + f["perm"]] = lam[:, f["lmin"] ** 2 : f["lmin"] ** 2 + n]
+        offF = offF1 if fi == 0 else offF2
+        for mi in range(2 * f["lmax"] + 1):
+            tasks.append((8 * (f["base"] + int(f["pos"][mi])), int(f["ks"][mi]), 32 * ((f["base"] + int(f["pos"][mi])) // 4), offF + 64 * mi))
+    # longest first, dealt round-robin: the warps finish stage A together
+    tasks.sort(key=lambda x: -x[1])
+    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8)
+
+    # stage C: quadrature fragments W[(l0 + lane/4, M), ring = 8c + 4ks + lane%4]
+    _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)       # [(L_out+1)^2, n_theta]
+    W_rows = np.zeros((n_tiles, 8, n_rings))
+    for ti, (Mi, l0) in enumerate(tiles):
+        M = Mi - L_out
+        ls = np.arange(l0, min(l0 + 8, L_out + 1))
+        W_rows[ti, : ls.shape[0], :n_theta] = Wt[ls * (ls + 1) + M]
+    wtfrag = W_rows.reshape(n_tiles, 8, n_chunks, 2, 4).transpose(2, 0, 3, 1, 4).reshape(n_chunks, n_tiles * 64)
+
+    qmax = (ell1_max + ell2_max + L_out) // n_phi
+    tb.perm1 = (8 * (fields[0]["base"] + fields[0]["perm"])).astype(np.int32)
+    tb.perm2 = (8 * (fields[1]["base"] + fields[1]["perm"])).astype(np.int32)
+    tb.tasks = np.ascontiguousarray(np.array(tasks, dtype=np.int32))
+    tb.lamfrag = np.ascontiguousarray(lamfrag)
+    tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
+    tb.wtfrag = np.ascontiguousarray(wtfrag)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks], dtype=np.int32)
+    tb.n_out = (L_out + 1) ** 2
+    tb.nwarps = nwarps
+    # algorithmic work per time step
+    tb.flops_per_step = float(
+        4 * n_theta * (fields[0]["perm"].shape[0] + fields[1]["perm"].shape[0])            # (A) real lambda x complex mode
+        + 8 * n_theta * sum(                                                               # (B) complex multiply-add per (m1, m2) pair
+            max(0, min(ell1_max, M + ell2_max) - max(-ell1_max, M - ell2_max) + 1) for M in range(-L_out, L_out + 1))
+        + 4 * n_theta * tb.n_out                                                           # (C) real weight x complex P_M
+    )
+    return tb

@@ -155,9 +155,28 @@ class ModesTimeSeries:
             raise ValueError("The time series of objects to be multiplied must be the same.")
         n_theta = n_phi = 2 * working_ell_max + 1
         out = ops.grid_multiply(self.ndarray, self.spin_weight, self.ell_min, self.ell_max, mts.ndarray, mts.spin_weight,
-                                mts.ell_min, mts.ell_max, n_theta, n_phi, working_ell_max)
+                                mts.ell_min, mts.ell_max, n_theta, n_phi, working_ell_max, output_ell_max=output_ell_max)
         n_keep = (output_ell_max + 1) ** 2
         return ModesTimeSeries(out[:, :n_keep], self.t, self.spin_weight + mts.spin_weight, ell_min=0, multiplication_truncator=max)
+
+    def multiply(self, other, truncator=None):
+        """Exact product of two spin-weighted functions, truncated to ell <= truncator((ell_max1, ell_max2))
+        (spherical_functions' Modes.multiply as scri/asymptotic_bondi_data/bms_charges.py:40-187 calls it; there the sum
+        runs over Wigner 3j symbols).  The product of band-limited functions has band limit ell1 + ell2, for which the
+        grid quadrature of `grid_multiply` is exact, so the same fused kernel is used with working_ell_max = ell1 + ell2."""
+        if not isinstance(other, ModesTimeSeries):
+            return self * other
+        truncator = truncator or self.multiplication_truncator
+        new_ell_max = int(truncator((self.ell_max, other.ell_max)))
+        full = self.ell_max + other.ell_max
+        keep = min(new_ell_max, full)
+        out = self.grid_multiply(other, working_ell_max=full, output_ell_max=keep)
+        if new_ell_max > keep:   # nothing lives above ell1 + ell2
+            data = np.zeros((self.n_times, (new_ell_max + 1) ** 2), dtype=complex)
+            data[:, : (keep + 1) ** 2] = out.ndarray
+            out = ModesTimeSeries(data, self.t, out.spin_weight, ell_min=0, multiplication_truncator=max)
+        out.multiplication_truncator = truncator
+        return out
 
 
 class AsymptoticBondiData:

@@ -1,0 +1,272 @@
+// K9: modes of the pointwise product of two spin-weighted fields, separable and fused - the (theta, phi) grids never
+// exist in HBM.
+//
+// Replaces the chain of scri/modes_time_series.py:177-193 (ModesTimeSeries.grid_multiply):
+//   spinsfast.salm2map(a1, s1) ; spinsfast.salm2map(a2, s2) ; product ; spinsfast.map2salm(., s1+s2, L_w)[: (L_out+1)^2]
+// on spinsfast's regular grid theta_j = pi j/(n_theta-1), phi_k = 2 pi k/n_phi, where sY_lm(theta_j, phi_k) =
+// lambda_lm(theta_j) e^{i m phi_k} separates.  Per time step and ring j:
+//   (A) F1_m(j) = sum_l lambda1_lm(j) a1_lm,  F2_m(j) likewise      - Wigner-d contraction over l, FP64 DMMA,
+//                                                                     rows = 8 rings, columns = 4 time steps x (re, im)
+//   (B) P_M(j)  = sum_{m1+m2 = M (mod n_phi)} F1_m1(j) F2_m2(j)      - what phi-synthesis, product and the phi-DFT of the
+//                                                                     analysis amount to (DFT convolution theorem, the
+//                                                                     aliases of an undersampled n_phi included); FP64 FMA
+//   (C) out_lM += W_lM(j) P_M(j)                                     - theta quadrature (Clenshaw-Curtis weights folded
+//                                                                     into W), FP64 DMMA, accumulators in registers
+// One persistent CTA per SM owns 4 consecutive time steps: their modes are staged once in shared memory in m-major order
+// and the CTA walks the rings in chunks of 8; the tables (fragment-ordered by the host, L2 resident) stream through
+// registers.  Algorithmic HBM traffic: 16 (n1 + n2 + n_out) bytes per time step.
+#include "common.cuh"
+
+namespace scrib200 {
+
+struct ProductParams {
+    const double2* a1;
+    const double2* a2;
+    double2* out;
+    int64_t n_times;
+    int n1, n2, n_out;
+    const int* perm1;       // [n1]  double offset in shared memory of mode idx of field 1 (m-major, padded to 4 per m)
+    const int* perm2;       // [n2]
+    const int4* tasks;      // [n_tasks] (smem double offset of the first l of this m, k-steps, fragment offset, smem offset of F_m)
+    int n_tasks;
+    const double* lamfrag;  // [n_chunks, lam_stride] A fragments of stage A
+    int64_t lam_stride;
+    const int2* tiles;      // [n_tiles] (M + L_out, l0)
+    int n_tiles;
+    const double* wtfrag;   // [n_chunks, n_tiles, 2, 32] A fragments of stage C
+    int64_t wt_stride;
+    int ell1, ell2, L_out, n_phi, n_chunks, qmax;
+    int szA;                // doubles of the two staged mode tiles (also the output staging area)
+    int offF1, offF2;       // double offsets of the F1 / P buffer and the F2 buffer
+    int stage_out;
+};
+
+__device__ __forceinline__ void dmma_p(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int PRODUCT_GM = 9;  // consecutive M per convolution warp (65 = 2*32+1 values of M over 8 warps, two per SM sub-partition)
+constexpr int PRODUCT_T = 4;   // time steps per CTA pass: 4 x (re, im) = the 8 columns of one DMMA tile
+
+template <int MAXT, int MAXKS, int MAXTHREADS>
+__global__ void __launch_bounds__(MAXTHREADS, 1)
+modes_product_kernel(const ProductParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    double2* sF1 = reinterpret_cast<double2*>(sm + p.offF1);
+    const double2* sF2 = reinterpret_cast<const double2*>(sm + p.offF2);
+    const int n_mout = 2 * p.L_out + 1;
+    constexpr int GM = PRODUCT_GM;
+    const int n_groups = (n_mout + GM - 1) / GM;
+    const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
+    const int fr = (lane & 3) * 8 + (lane >> 2);   // B fragment of an [k = 4 rows][8 columns] block stored 8 doubles per row
+
+    for (int64_t tg = blockIdx.x; tg < n_tg; tg += gridDim.x) {
+        const int64_t t0 = tg * PRODUCT_T;
+        const int nt = (int)min((int64_t)PRODUCT_T, p.n_times - t0);
+        // ---- stage the modes of these time steps, m-major: sm[perm[idx] + 2 t + (re, im)]
+        for (int i = tid; i < p.szA / 2; i += nthreads) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+        __syncthreads();
+        for (int e = tid; e < nt * p.n1; e += nthreads) {
+            int t = e / p.n1, idx = e - t * p.n1;
+            *reinterpret_cast<double2*>(sm + __ldg(p.perm1 + idx) + 2 * t) = p.a1[t0 * p.n1 + e];
+        }
+        for (int e = tid; e < nt * p.n2; e += nthreads) {
+            int t = e / p.n2, idx = e - t * p.n2;
+            *reinterpret_cast<double2*>(sm + __ldg(p.perm2 + idx) + 2 * t) = p.a2[t0 * p.n2 + e];
+        }
+        __syncthreads();
+
+        double acc[MAXT][2];
+#pragma unroll
+        for (int s = 0; s < MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
+
+        for (int c = 0; c < p.n_chunks; ++c) {
+            // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7: one (field, m) per task, fragments of the
+            //      next task in flight while the DMMA chain of this one runs
+            {
+                const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
+                int i = warp;
+                int4 tk = make_int4(0, 0, 0, 0);
+                double af[MAXKS];
+                if (i < p.n_tasks) {
+                    tk = __ldg(p.tasks + i);
+#pragma unroll
+                    for (int ks = 0; ks < MAXKS; ++ks) af[ks] = ks < tk.y ? __ldg(lf + tk.z + ks * 32) : 0.0;
+                }
+                while (i < p.n_tasks) {
+                    const int inext = i + nwarps;
+                    int4 tn = make_int4(0, 0, 0, 0);
+                    double an[MAXKS];
+                    if (inext < p.n_tasks) {
+                        tn = __ldg(p.tasks + inext);
+#pragma unroll
+                        for (int ks = 0; ks < MAXKS; ++ks) an[ks] = ks < tn.y ? __ldg(lf + tn.z + ks * 32) : 0.0;
+                    }
+                    double c0 = 0.0, c1 = 0.0;
+                    const double* bsrc = sm + tk.x + fr;
+#pragma unroll
+                    for (int ks = 0; ks < MAXKS; ++ks)
+                        if (ks < tk.y) dmma_p(c0, c1, af[ks], bsrc[ks * 32]);
+                    *reinterpret_cast<double2*>(sm + tk.w + 2 * lane) = make_double2(c0, c1);   // F_m[item = ring*4 + t]
+                    tk = tn;
+#pragma unroll
+                    for (int ks = 0; ks < MAXKS; ++ks) af[ks] = an[ks];
+                    i = inext;
+                }
+            }
+            __syncthreads();
+
+            // ---- (B) convolution over m for the 32 (ring, time) items of the chunk: lane = item, warp = GM consecutive M
+            double2 pacc[GM];
+#pragma unroll
+            for (int q = 0; q < GM; ++q) pacc[q] = make_double2(0.0, 0.0);
+            if (warp < n_groups) {
+                const int M0 = -p.L_out + GM * warp;
+                const double2* f1 = sF1 + lane;
+                const double2* f2 = sF2 + lane;
+                const int l2 = p.ell2;
+                auto ld2 = [&](int m2) -> double2 {
+                    return (m2 >= -l2 && m2 <= l2) ? f2[(m2 + l2) * 32] : make_double2(0.0, 0.0);
+                };
+                for (int q = -p.qmax; q <= p.qmax; ++q) {
+                    const int Me = M0 + q * p.n_phi;
+                    const int lo = max(-p.ell1, Me - l2), hi = min(p.ell1, Me + GM - 1 + l2);
+                    if (lo > hi) continue;
+                    double2 y[GM + 3];   // y[k] <-> m2 = Me - m1b - 3 + k
+#pragma unroll
+                    for (int k = 0; k < GM - 1; ++k) y[k] = ld2(Me - lo + 1 + k);
+                    for (int m1b = lo; m1b <= hi; m1b += 4) {
+#pragma unroll
+                        for (int k = GM - 2; k >= 0; --k) y[k + 4] = y[k];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = ld2(Me - m1b - 3 + k);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double2 x = (m1b + i <= hi) ? f1[(m1b + i + p.ell1) * 32] : make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int qq = 0; qq < GM; ++qq) cfma(pacc[qq], x, y[qq - i + 3]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (warp < n_groups) {
+#pragma unroll
+                for (int qq = 0; qq < GM; ++qq)
+                    if (GM * warp + qq < n_mout) sF1[(GM * warp + qq) * 32 + lane] = pacc[qq];
+            }
+            __syncthreads();
+
+            // ---- (C) theta quadrature: out[l, M] += sum over the 8 rings of W[lM, ring] P_M[ring]
+            {
+                const double* wf = p.wtfrag + (int64_t)c * p.wt_stride + lane;
+#pragma unroll
+                for (int s = 0; s < MAXT; ++s) {
+                    const int ti = warp + s * nwarps;
+                    if (ti < p.n_tiles) {
+                        const int2 tl = __ldg(p.tiles + ti);
+                        const double w0 = __ldg(wf + ti * 64), w1 = __ldg(wf + ti * 64 + 32);
+                        const double* bsrc = sm + p.offF1 + tl.x * 64 + fr;
+                        dmma_p(acc[s][0], acc[s][1], w0, bsrc[0]);
+                        dmma_p(acc[s][0], acc[s][1], w1, bsrc[32]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- modes of the product: C fragment row = l0 + lane/4, columns (t = lane%4, re/im)
+        {
+            const int t = lane & 3;
+            double2* so = reinterpret_cast<double2*>(sm);
+#pragma unroll
+            for (int s = 0; s < MAXT; ++s) {
+                const int ti = warp + s * nwarps;
+                if (ti < p.n_tiles) {
+                    const int2 tl = __ldg(p.tiles + ti);
+                    const int l = tl.y + (lane >> 2), M = tl.x - p.L_out;
+                    if (l <= p.L_out && t < nt) {
+                        const int idx = l * (l + 1) + M;
+                        if (p.stage_out) so[t * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
+                        else p.out[(t0 + t) * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
+                    }
+                }
+            }
+            if (p.stage_out) {
+                __syncthreads();
+                for (int e = tid; e < nt * p.n_out; e += nthreads) p.out[t0 * p.n_out + e] = so[e];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace scrib200
+
+extern "C" size_t scrib200_modes_product_max_shared_bytes(void) { return 227u * 1024u; }
+
+extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, int64_t n_times,
+                                      const int* perm1, const int* perm2, const int* tasks, int n_tasks,
+                                      const double* lamfrag, int64_t lam_stride, const int* tiles, int n_tiles,
+                                      const double* wtfrag, int64_t wt_stride, const int* cfg, double* out,
+                                      int n_ctas, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(a1 && a2 && perm1 && perm2 && tasks && lamfrag && tiles && wtfrag && cfg && out, "modes_product: null pointer");
+    SCRIB200_REQUIRE(aligned16(a1) && aligned16(a2) && aligned16(out) && aligned16(tasks), "modes_product: pointers must be 16-byte aligned");
+    ProductParams p;
+    p.a1 = reinterpret_cast<const double2*>(a1);
+    p.a2 = reinterpret_cast<const double2*>(a2);
+    p.out = reinterpret_cast<double2*>(out);
+    p.n_times = n_times;
+    p.n1 = n1;
+    p.n2 = n2;
+    p.perm1 = perm1;
+    p.perm2 = perm2;
+    p.tasks = reinterpret_cast<const int4*>(tasks);
+    p.n_tasks = n_tasks;
+    p.lamfrag = lamfrag;
+    p.lam_stride = lam_stride;
+    p.tiles = reinterpret_cast<const int2*>(tiles);
+    p.n_tiles = n_tiles;
+    p.wtfrag = wtfrag;
+    p.wt_stride = wt_stride;
+    p.ell1 = cfg[0];
+    p.ell2 = cfg[1];
+    p.L_out = cfg[2];
+    p.n_phi = cfg[3];
+    p.n_chunks = cfg[4];
+    p.qmax = cfg[5];
+    p.szA = cfg[6];
+    p.offF1 = cfg[7];
+    p.offF2 = cfg[8];
+    const int smem_doubles = cfg[9], nwarps = cfg[10], max_ks = cfg[11];
+    p.n_out = (p.L_out + 1) * (p.L_out + 1);
+    p.stage_out = (PRODUCT_T * p.n_out * 2 <= p.szA) ? 1 : 0;
+    SCRIB200_REQUIRE(n1 > 0 && n2 > 0 && n_tasks > 0 && n_tiles > 0 && p.n_chunks > 0, "modes_product: empty tables");
+    SCRIB200_REQUIRE(p.ell1 >= 0 && p.ell2 >= 0 && p.L_out >= 0 && p.n_phi > 0 && p.qmax >= 0, "modes_product: bad band limits");
+    SCRIB200_REQUIRE((p.szA & 1) == 0 && (p.offF1 & 1) == 0 && (p.offF2 & 1) == 0, "modes_product: shared-memory offsets must be even");
+    const size_t smem = (size_t)smem_doubles * sizeof(double);
+    SCRIB200_REQUIRE(smem <= scrib200_modes_product_max_shared_bytes(), "modes_product: %zu bytes of shared memory needed (limit %zu); use the dense path", smem,
+                     scrib200_modes_product_max_shared_bytes());
+    const int n_groups = (2 * p.L_out + 1 + PRODUCT_GM - 1) / PRODUCT_GM;
+    SCRIB200_REQUIRE(nwarps >= n_groups && nwarps >= 1 && nwarps <= 8, "modes_product: %d warps for %d groups of M (at most 8 supported)", nwarps, n_groups);
+    SCRIB200_REQUIRE((n_tiles + nwarps - 1) / nwarps <= 21, "modes_product: %d output tiles over %d warps exceed the register budget", n_tiles, nwarps);
+    SCRIB200_REQUIRE(max_ks >= 1 && max_ks <= 9, "modes_product: %d k-steps per m (at most 9, ell <= 35)", max_ks);
+    if (n_times <= 0) return SCRIB200_OK;
+    int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
+    if (n_ctas <= 0) n_ctas = 148;
+    int64_t grid = n_tg < n_ctas ? n_tg : n_ctas;
+    auto kern = modes_product_kernel<21, 9, 256>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+        set_error("modes_product: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return SCRIB200_ECUDA;
+    }
+    kern<<<(unsigned)grid, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
+    SCRIB200_CHECK_LAUNCH("modes_product");
+    return SCRIB200_OK;
+}

@@ -5,6 +5,8 @@ Each function is the drop-in for one numba / third-party kernel the reference ca
 tensors (then nothing is copied and a CUDA tensor is returned), which is what bench.py's
 device-resident `value` uses.  No CPU fallback: without a CUDA device these raise Scrib200Error.
 """
+import ctypes
+
 import numpy as np
 
 from . import _lib, _sf
@@ -277,12 +279,62 @@ def salm2map(salm, s, ell_max, n_theta, n_phi, ell_min=0):
     return F if is_tensor(salm) else to_host(F)
 
 
-def grid_multiply(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, working_ell_max, slab_bytes=2 << 30):
-    """Modes (from ell = 0 to working_ell_max) of the pointwise product of two mode series
-    (scri/modes_time_series.py:142-202): salm2map x 2 -> product -> map2salm with spin sa + sb, in slabs of time."""
+_product_cache = {}
+
+
+def _product_device_tables(key):
+    torch = _torch()
+    from . import _product
+
+    dkey = key + (torch.cuda.current_device(),)
+    if dkey not in _product_cache:
+        tb = _product.product_tables(*key)
+        dev = None
+        if tb.fits:
+            dev = {k: torch.from_numpy(getattr(tb, k)).cuda() for k in ("perm1", "perm2", "tasks", "lamfrag", "tiles", "wtfrag")}
+        _product_cache[dkey] = (tb, dev)
+    return _product_cache[dkey]
+
+
+def modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max, n_ctas=0):
+    """Fused separable product (scrib200_modes_product, K9): device/host mode series in, modes of the product from
+    ell = 0 to output_ell_max out; None when the problem does not fit one CTA (callers use the dense path)."""
+    torch = _torch()
+    lib = _lib.load()
+    tb, dev = _product_device_tables((sa, a_ell_min, a_ell_max, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max))
+    if not tb.fits:
+        return None
+    da = to_device(a, np.complex128)
+    db = to_device(b, np.complex128)
+    N = da.shape[0]
+    if db.shape[0] != N:
+        raise ValueError("modes_product: the two series must have the same number of time steps")
+    out = torch.empty((N, tb.n_out), dtype=torch.complex128, device="cuda")
+    _lib.check(
+        lib.scrib200_modes_product(
+            _lib.ptr(da), da.shape[1], _lib.ptr(db), db.shape[1], N, _lib.ptr(dev["perm1"]), _lib.ptr(dev["perm2"]),
+            _lib.ptr(dev["tasks"]), dev["tasks"].shape[0], _lib.ptr(dev["lamfrag"]), dev["lamfrag"].shape[1],
+            _lib.ptr(dev["tiles"]), dev["tiles"].shape[0], _lib.ptr(dev["wtfrag"]), dev["wtfrag"].shape[1],
+            tb.cfg.ctypes.data_as(ctypes.c_void_p), _lib.ptr(out), n_ctas, _lib.stream_ptr(),
+        ),
+        "modes_product",
+    )
+    return out if (is_tensor(a) or is_tensor(b)) else to_host(out)
+
+
+def grid_multiply(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, working_ell_max, slab_bytes=2 << 30,
+                  output_ell_max=None, fused=True):
+    """Modes (from ell = 0 to working_ell_max, or to output_ell_max when given) of the pointwise product of two mode
+    series (scri/modes_time_series.py:142-202).  Fused separable kernel when the tables fit one CTA (ell up to ~35);
+    otherwise salm2map x 2 -> product -> map2salm with spin sa + sb through the dense kernels, in slabs of time."""
     torch = _torch()
     lib = _lib.load()
     N = a.shape[0]
+    L_out = working_ell_max if output_ell_max is None else min(output_ell_max, working_ell_max)
+    if fused:
+        out = modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, L_out)
+        if out is not None:
+            return out
     G = n_theta * n_phi
     n_out = (working_ell_max + 1) ** 2
     out = np.empty((N, n_out), dtype=complex)
@@ -294,7 +346,7 @@ def grid_multiply(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_th
         _lib.check(lib.scrib200_grid_product(_lib.ptr(ga), _lib.ptr(gb), _lib.ptr(ga), ga.numel(), _lib.stream_ptr()), "grid_product")
         del gb
         out[i0:i1] = to_host(map2salm(ga.reshape(i1 - i0, G), sa + sb, working_ell_max, n_theta, n_phi, ell_min=0))
-    return out
+    return out[:, : (L_out + 1) ** 2]
 
 
 def norm(data):

@@ -629,3 +629,60 @@ def test_transform_on_user_chosen_grids(grid):
     g = modes(t, data).to_grid(**{k: v for k, v in kw.items() if k != "ell_max"})
     go = R.from_modes(R.Modes(t=t, data=data.copy()), **{k: v for k, v in kw.items() if k != "ell_max"})
     assert (g.n_theta, g.n_phi) == (go.n_theta, go.n_phi) and rel(g.data, go.data) < RTOL
+
+
+def _rand_modes(rng, N, L, s, ell_min=0):
+    a = rng.normal(size=(N, (L + 1) ** 2)) + 1j * rng.normal(size=(N, (L + 1) ** 2))
+    a[:, : s * s] = 0.0
+    return a[:, ell_min**2 :]
+
+
+@pytest.mark.parametrize("case", [(2, 3, -2, 4, None, None, 6), (0, 4, 1, 2, None, 6, 1), (2, 5, -2, 5, 6, 4, 9), (-1, 3, 0, 3, 3, 3, 4),
+                                  (2, 8, -2, 8, None, 8, 37), (0, 12, 2, 8, None, 20, 10)])
+def test_fused_modes_product_vs_oracle(case):
+    """K9 (scrib200_modes_product) against the oracle's grid_multiply (scri/modes_time_series.py:142-202): default and
+    aliased working grids, ragged time counts (the kernel walks 4 steps at a time), output band limits above and below
+    the factors'."""
+    from oracle import abd_ref as A
+
+    s1, L1, s2, L2, Lw, Lo, N = case
+    rng = np.random.default_rng(21)
+    a, b = _rand_modes(rng, N, L1, s1), _rand_modes(rng, N, L2, s2)
+    ref = A.grid_multiply(a, s1, b, s2, working_ell_max=Lw, output_ell_max=Lo)
+    n = 2 * (L1 + L2 if Lw is None else Lw) + 1
+    out = ops.modes_product(a, s1, 0, L1, b, s2, 0, L2, n, n, L1 if Lo is None else Lo)
+    assert out is not None and out.shape == ref.shape
+    assert rel(out, ref) < RTOL
+
+
+def test_fused_modes_product_ell_min_and_3j_multiply():
+    """A factor stored from ell_min = 2 (as WaveformModes data is) and ModesTimeSeries.multiply against the 3j sums of
+    spherical_functions' Modes.multiply (oracle.sf.modes_multiply; bms_charges.py:40-187)."""
+    from oracle import abd_ref as A, sf as osf
+
+    rng = np.random.default_rng(22)
+    N = 11
+    a0, b = _rand_modes(rng, N, 5, 2), _rand_modes(rng, N, 4, -1)
+    out = ops.modes_product(a0[:, 4:], 2, 2, 5, b, -1, 0, 4, 19, 19, 5)
+    assert rel(out, A.grid_multiply(a0, 2, b, -1)) < RTOL
+    t = np.linspace(0.0, 1.0, N)
+    f, g = sb.ModesTimeSeries(a0, t, 2), sb.ModesTimeSeries(b, t, -1)
+    for trunc, Lo in ((max, 5), (sum, 9), (lambda tup: 3, 3), (lambda tup: 12, 12)):
+        p = f.multiply(g, truncator=trunc)
+        assert p.spin_weight == 1 and p.ell_max == Lo
+        assert rel(p.ndarray, osf.modes_multiply(a0, 2, 5, b, -1, 4, Lo)) < RTOL
+
+
+def test_fused_modes_product_config4_size_equals_dense_path():
+    """BASELINE config 4 size (ell <= 32 factors, 129 x 129 working grid): the fused separable kernel against the dense
+    synthesis GEMM -> product -> analysis chain of the same library, and linearity in each factor."""
+    rng = np.random.default_rng(23)
+    N, L = 10, 32
+    a, b = _rand_modes(rng, N, L, 2), _rand_modes(rng, N, L, -2)
+    fused = ops.grid_multiply(a, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)
+    dense = ops.grid_multiply(a, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32, fused=False)
+    assert fused.shape == dense.shape == (N, 33 * 33)
+    assert rel(fused, dense) < RTOL
+    a2 = _rand_modes(rng, N, L, 2)
+    lin = ops.grid_multiply(a + 0.5 * a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)
+    assert rel(lin, fused + 0.5 * ops.grid_multiply(a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)) < RTOL

@@ -209,3 +209,37 @@ def test_ladder_table():
         assert row[4] == m
         assert np.isclose(row[0], np.sqrt((l - m) * (l + m + 1)) if m + 1 <= l else 0.0)
         assert np.isclose(row[1], np.sqrt((l + m) * (l - m + 1)) if m - 1 >= -l else 0.0)
+
+
+@pytest.mark.parametrize("case", [(2, 3, -2, 4, None, None), (0, 4, 1, 2, None, 6), (2, 5, -2, 5, 6, 4), (-1, 3, 0, 3, 3, 3)])
+def test_product_tables_through_a_numpy_emulation_of_the_kernel(case):
+    """Host tables of the fused separable product (scri_b200/_product.py: mode permutation, DMMA fragment order of the
+    Wigner-d and quadrature tables, alias range of the m-convolution) drive a numpy emulation of csrc/product.cu's
+    three stages; the result is ModesTimeSeries.grid_multiply's (scri/modes_time_series.py:142-202), aliased working
+    grids (working_ell_max < ell1 + ell2) included."""
+    from oracle import abd_ref
+    from product_emulator import emulate
+    from scri_b200 import _product
+
+    s1, L1, s2, L2, Lw, Lo = case
+    rng = np.random.default_rng(0)
+
+    def rnd(L, s):
+        a = rng.normal(size=(6, (L + 1) ** 2)) + 1j * rng.normal(size=(6, (L + 1) ** 2))
+        a[:, : s * s] = 0
+        return a
+
+    a, b = rnd(L1, s1), rnd(L2, s2)
+    ref = abd_ref.grid_multiply(a, s1, b, s2, working_ell_max=Lw, output_ell_max=Lo)
+    n = 2 * (L1 + L2 if Lw is None else Lw) + 1
+    tb = _product.product_tables(s1, 0, L1, s2, 0, L2, n, n, L1 if Lo is None else Lo)
+    assert tb.fits
+    assert np.abs(emulate(tb, a, b) - ref).max() < 1e-14 * np.abs(ref).max()
+
+
+def test_product_tables_config4_fit_one_cta():
+    from scri_b200 import _product
+
+    tb = _product.product_tables(2, 0, 32, -2, 0, 32, 129, 129, 32)
+    assert tb.fits and tb.smem_bytes <= 227 * 1024 and tb.nwarps == 8
+    assert not _product.product_tables(2, 0, 64, -2, 0, 64, 257, 257, 64).fits   # the dense kernels take over

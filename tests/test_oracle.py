@@ -279,3 +279,20 @@ def test_golden_fixture_matches_oracle():
     out = R.transform(W, supertranslation=g["supertranslation"], frame_rotation=g["frame_rotation"], boost_velocity=g["boost_velocity"])
     assert np.array_equal(out.t, g["out_t"])
     assert np.allclose(out.data, g["out_data"], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("s1,L1,s2,L2,Lo", [(2, 3, -2, 3, 4), (0, 2, 1, 3, 5), (-1, 2, -1, 2, 4), (2, 3, 2, 3, 6)])
+def test_3j_product_equals_grid_product(s1, L1, s2, L2, Lo):
+    """sf.Modes.multiply (3j sums; bms_charges.py:40-187) and ModesTimeSeries.grid_multiply (modes_time_series.py:142-202)
+    compute the same coefficients once working_ell_max >= ell1 + ell2: two independent restatements pin each other."""
+    rng = np.random.default_rng(1)
+
+    def rnd(L, s):
+        a = rng.normal(size=(2, (L + 1) ** 2)) + 1j * rng.normal(size=(2, (L + 1) ** 2))
+        a[:, : s * s] = 0
+        return a
+
+    a, b = rnd(L1, s1), rnd(L2, s2)
+    ref = A.grid_multiply(a, s1, b, s2, working_ell_max=L1 + L2, output_ell_max=Lo)
+    out = sf.modes_multiply(a, s1, L1, b, s2, L2, Lo)
+    assert np.abs(out - ref).max() < 5e-15 * np.abs(ref).max()
