@@ -12,10 +12,9 @@ import numpy as np
 
 from . import _sf
 
-GM = 9          # consecutive M per convolution warp (csrc/product.cu: PRODUCT_GM)
 T = 4           # time steps per CTA pass (PRODUCT_T)
-MAX_WARPS = 8
-MAX_TILES_PER_WARP = 21
+# kernel shapes instantiated in csrc/product.cu: (consecutive M per convolution warp, warps, output tiles per warp)
+SHAPES = ((5, 16, 11), (9, 8, 21))
 MAX_KSTEPS = 9
 MAX_SMEM = 227 * 1024
 
@@ -47,13 +46,11 @@ def _field_layout(ell_min, ell_max):
 
 
 @lru_cache(maxsize=16)
-def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out):
+def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, shape=None):
     tb = ProductTables()
     n_chunks = (n_theta + 7) // 8
     n_rings = 8 * n_chunks
     n_mout = 2 * L_out + 1
-    n_groups = (n_mout + GM - 1) // GM
-    nwarps = max(n_groups, min(MAX_WARPS, 4))
     fields = []
     base = 0
     for s, lmin, lmax in ((s1, ell1_min, ell1_max), (s2, ell2_min, ell2_max)):
@@ -69,16 +66,19 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
 
     # output tiles: 8 consecutive l of one M
     tiles = [(M + L_out, l0) for M in range(-L_out, L_out + 1) for l0 in range(abs(M), L_out + 1, 8)]
-    n_tiles = len(tiles)
     max_ks = int(max(f["ks"].max() for f in fields))
-    tb.fits = (
-        8 * smem_doubles <= MAX_SMEM
-        and n_groups <= MAX_WARPS
-        and -(-n_tiles // nwarps) <= MAX_TILES_PER_WARP
-        and max_ks <= MAX_KSTEPS
-        and n_theta >= 2
-    )
+    chosen = None
+    for sh in SHAPES if shape is None else (SHAPES[shape],):
+        gm, nw, maxt = sh
+        if -(-n_mout // gm) <= nw and len(tiles) <= nw * maxt:
+            chosen = sh
+            break
+    tb.fits = chosen is not None and 8 * smem_doubles <= MAX_SMEM and max_ks <= MAX_KSTEPS and n_theta >= 2
     tb.smem_bytes = 8 * smem_doubles
+    if tb.fits:
+        GM, nwarps, maxt = chosen
+        tiles += [(0, L_out + 1)] * (nwarps * maxt - len(tiles))     # empty tiles: every warp walks `maxt` of them
+    n_tiles = len(tiles)
     if not tb.fits:
         return tb
 
@@ -97,14 +97,14 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     tasks.sort(key=lambda x: -x[1])
     lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8)
 
-    # stage C: quadrature fragments W[(l0 + lane/4, M), ring = 8c + 4ks + lane%4]
+    # stage C: quadrature fragments W[(l0 + lane/4, M), ring = 8c + 4ks + lane%4], the two k-steps of a lane adjacent
     _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)       # [(L_out+1)^2, n_theta]
     W_rows = np.zeros((n_tiles, 8, n_rings))
     for ti, (Mi, l0) in enumerate(tiles):
         M = Mi - L_out
         ls = np.arange(l0, min(l0 + 8, L_out + 1))
         W_rows[ti, : ls.shape[0], :n_theta] = Wt[ls * (ls + 1) + M]
-    wtfrag = W_rows.reshape(n_tiles, 8, n_chunks, 2, 4).transpose(2, 0, 3, 1, 4).reshape(n_chunks, n_tiles * 64)
+    wtfrag = W_rows.reshape(n_tiles, 8, n_chunks, 2, 4).transpose(2, 0, 1, 4, 3).reshape(n_chunks, n_tiles * 64)   # [chunk][tile][lane][k-step]
 
     qmax = (ell1_max + ell2_max + L_out) // n_phi
     tb.perm1 = (8 * (fields[0]["base"] + fields[0]["perm"])).astype(np.int32)
@@ -113,9 +113,10 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     tb.lamfrag = np.ascontiguousarray(lamfrag)
     tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
     tb.wtfrag = np.ascontiguousarray(wtfrag)
-    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks], dtype=np.int32)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks, GM, maxt], dtype=np.int32)
     tb.n_out = (L_out + 1) ** 2
     tb.nwarps = nwarps
+    tb.gm = GM
     # algorithmic work per time step
     tb.flops_per_step = float(
         4 * n_theta * (fields[0]["perm"].shape[0] + fields[1]["perm"].shape[0])            # (A) real lambda x complex mode

@@ -47,10 +47,11 @@ __device__ __forceinline__ void dmma_p(double& d0, double& d1, double a, double 
                  : "d"(a), "d"(b));
 }
 
-constexpr int PRODUCT_GM = 9;  // consecutive M per convolution warp (65 = 2*32+1 values of M over 8 warps, two per SM sub-partition)
 constexpr int PRODUCT_T = 4;   // time steps per CTA pass: 4 x (re, im) = the 8 columns of one DMMA tile
 
-template <int MAXT, int MAXKS, int MAXTHREADS>
+// GM = consecutive M per convolution warp, MAXT = output tiles per warp, MAXKS = k-steps (4 l each) per m.
+// Two shapes are instantiated: 16 warps x 5 M (ell_out <= 39) and 8 warps x 9 M; the host picks by table size.
+template <int GM, int MAXT, int MAXKS, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1)
 modes_product_kernel(const ProductParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -59,10 +60,14 @@ modes_product_kernel(const ProductParams p) {
     double2* sF1 = reinterpret_cast<double2*>(sm + p.offF1);
     const double2* sF2 = reinterpret_cast<const double2*>(sm + p.offF2);
     const int n_mout = 2 * p.L_out + 1;
-    constexpr int GM = PRODUCT_GM;
     const int n_groups = (n_mout + GM - 1) / GM;
     const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
     const int fr = (lane & 3) * 8 + (lane >> 2);   // B fragment of an [k = 4 rows][8 columns] block stored 8 doubles per row
+
+    // this warp's output tiles (the same for every chunk and time group; the table is padded with empty tiles)
+    int tile_m[MAXT];
+#pragma unroll
+    for (int s = 0; s < MAXT; ++s) tile_m[s] = __ldg(p.tiles + warp + s * nwarps).x * 64;
 
     for (int64_t tg = blockIdx.x; tg < n_tg; tg += gridDim.x) {
         const int64_t t0 = tg * PRODUCT_T;
@@ -85,37 +90,35 @@ modes_product_kernel(const ProductParams p) {
         for (int s = 0; s < MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
 
         for (int c = 0; c < p.n_chunks; ++c) {
-            // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7: one (field, m) per task, fragments of the
-            //      next task in flight while the DMMA chain of this one runs
+            // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7: one (field, m) per task; the fragments of
+            //      the next two tasks are in flight (L2 latency) while the DMMA chain of this one runs
             {
                 const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
-                int i = warp;
-                int4 tk = make_int4(0, 0, 0, 0);
-                double af[MAXKS];
-                if (i < p.n_tasks) {
-                    tk = __ldg(p.tasks + i);
+                auto fetch = [&](int i, int4& tk, double (&af)[MAXKS]) {
+                    tk = (i < p.n_tasks) ? __ldg(p.tasks + i) : make_int4(0, 0, 0, -1);
 #pragma unroll
                     for (int ks = 0; ks < MAXKS; ++ks) af[ks] = ks < tk.y ? __ldg(lf + tk.z + ks * 32) : 0.0;
-                }
-                while (i < p.n_tasks) {
-                    const int inext = i + nwarps;
-                    int4 tn = make_int4(0, 0, 0, 0);
-                    double an[MAXKS];
-                    if (inext < p.n_tasks) {
-                        tn = __ldg(p.tasks + inext);
-#pragma unroll
-                        for (int ks = 0; ks < MAXKS; ++ks) an[ks] = ks < tn.y ? __ldg(lf + tn.z + ks * 32) : 0.0;
-                    }
+                };
+                auto run = [&](const int4& tk, const double (&af)[MAXKS]) {
+                    if (tk.w < 0) return;
                     double c0 = 0.0, c1 = 0.0;
                     const double* bsrc = sm + tk.x + fr;
 #pragma unroll
                     for (int ks = 0; ks < MAXKS; ++ks)
                         if (ks < tk.y) dmma_p(c0, c1, af[ks], bsrc[ks * 32]);
                     *reinterpret_cast<double2*>(sm + tk.w + 2 * lane) = make_double2(c0, c1);   // F_m[item = ring*4 + t]
-                    tk = tn;
-#pragma unroll
-                    for (int ks = 0; ks < MAXKS; ++ks) af[ks] = an[ks];
-                    i = inext;
+                };
+                int4 k0, k1, k2;
+                double f0[MAXKS], f1[MAXKS], f2[MAXKS];
+                fetch(warp, k0, f0);
+                fetch(warp + nwarps, k1, f1);
+                for (int i = warp; i < p.n_tasks; i += 3 * nwarps) {
+                    fetch(i + 2 * nwarps, k2, f2);
+                    run(k0, f0);
+                    fetch(i + 3 * nwarps, k0, f0);
+                    run(k1, f1);
+                    fetch(i + 4 * nwarps, k1, f1);
+                    run(k2, f2);
                 }
             }
             __syncthreads();
@@ -153,6 +156,13 @@ modes_product_kernel(const ProductParams p) {
                     }
                 }
             }
+            // quadrature fragments of this chunk: issued now, consumed after the two barriers below
+            double2 w[MAXT];
+            {
+                const double2* wf = reinterpret_cast<const double2*>(p.wtfrag + (int64_t)c * p.wt_stride) + lane;
+#pragma unroll
+                for (int s = 0; s < MAXT; ++s) w[s] = __ldg(wf + (warp + s * nwarps) * 32);
+            }
             __syncthreads();
             if (warp < n_groups) {
 #pragma unroll
@@ -162,19 +172,11 @@ modes_product_kernel(const ProductParams p) {
             __syncthreads();
 
             // ---- (C) theta quadrature: out[l, M] += sum over the 8 rings of W[lM, ring] P_M[ring]
-            {
-                const double* wf = p.wtfrag + (int64_t)c * p.wt_stride + lane;
 #pragma unroll
-                for (int s = 0; s < MAXT; ++s) {
-                    const int ti = warp + s * nwarps;
-                    if (ti < p.n_tiles) {
-                        const int2 tl = __ldg(p.tiles + ti);
-                        const double w0 = __ldg(wf + ti * 64), w1 = __ldg(wf + ti * 64 + 32);
-                        const double* bsrc = sm + p.offF1 + tl.x * 64 + fr;
-                        dmma_p(acc[s][0], acc[s][1], w0, bsrc[0]);
-                        dmma_p(acc[s][0], acc[s][1], w1, bsrc[32]);
-                    }
-                }
+            for (int s = 0; s < MAXT; ++s) {
+                const double* bsrc = sm + p.offF1 + tile_m[s] + fr;
+                dmma_p(acc[s][0], acc[s][1], w[s].x, bsrc[0]);
+                dmma_p(acc[s][0], acc[s][1], w[s].y, bsrc[32]);
             }
             __syncthreads();
         }
@@ -185,15 +187,12 @@ modes_product_kernel(const ProductParams p) {
             double2* so = reinterpret_cast<double2*>(sm);
 #pragma unroll
             for (int s = 0; s < MAXT; ++s) {
-                const int ti = warp + s * nwarps;
-                if (ti < p.n_tiles) {
-                    const int2 tl = __ldg(p.tiles + ti);
-                    const int l = tl.y + (lane >> 2), M = tl.x - p.L_out;
-                    if (l <= p.L_out && t < nt) {
-                        const int idx = l * (l + 1) + M;
-                        if (p.stage_out) so[t * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
-                        else p.out[(t0 + t) * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
-                    }
+                const int2 tl = __ldg(p.tiles + warp + s * nwarps);
+                const int l = tl.y + (lane >> 2), M = tl.x - p.L_out;
+                if (l <= p.L_out && t < nt) {
+                    const int idx = l * (l + 1) + M;
+                    if (p.stage_out) so[t * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
+                    else p.out[(t0 + t) * p.n_out + idx] = make_double2(acc[s][0], acc[s][1]);
                 }
             }
             if (p.stage_out) {
@@ -243,7 +242,7 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     p.szA = cfg[6];
     p.offF1 = cfg[7];
     p.offF2 = cfg[8];
-    const int smem_doubles = cfg[9], nwarps = cfg[10], max_ks = cfg[11];
+    const int smem_doubles = cfg[9], nwarps = cfg[10], max_ks = cfg[11], gm = cfg[12], maxt = cfg[13];
     p.n_out = (p.L_out + 1) * (p.L_out + 1);
     p.stage_out = (PRODUCT_T * p.n_out * 2 <= p.szA) ? 1 : 0;
     SCRIB200_REQUIRE(n1 > 0 && n2 > 0 && n_tasks > 0 && n_tiles > 0 && p.n_chunks > 0, "modes_product: empty tables");
@@ -252,15 +251,17 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     const size_t smem = (size_t)smem_doubles * sizeof(double);
     SCRIB200_REQUIRE(smem <= scrib200_modes_product_max_shared_bytes(), "modes_product: %zu bytes of shared memory needed (limit %zu); use the dense path", smem,
                      scrib200_modes_product_max_shared_bytes());
-    const int n_groups = (2 * p.L_out + 1 + PRODUCT_GM - 1) / PRODUCT_GM;
-    SCRIB200_REQUIRE(nwarps >= n_groups && nwarps >= 1 && nwarps <= 8, "modes_product: %d warps for %d groups of M (at most 8 supported)", nwarps, n_groups);
-    SCRIB200_REQUIRE((n_tiles + nwarps - 1) / nwarps <= 21, "modes_product: %d output tiles over %d warps exceed the register budget", n_tiles, nwarps);
+    SCRIB200_REQUIRE((gm == 5 && nwarps == 16 && maxt == 11) || (gm == 9 && nwarps == 8 && maxt == 21),
+                     "modes_product: unsupported kernel shape (gm %d, warps %d, tiles per warp %d)", gm, nwarps, maxt);
+    const int n_groups = (2 * p.L_out + 1 + gm - 1) / gm;
+    SCRIB200_REQUIRE(nwarps >= n_groups, "modes_product: %d warps for %d groups of M", nwarps, n_groups);
+    SCRIB200_REQUIRE(n_tiles == nwarps * maxt, "modes_product: the tile table must be padded to warps x tiles per warp (%d != %d x %d)", n_tiles, nwarps, maxt);
     SCRIB200_REQUIRE(max_ks >= 1 && max_ks <= 9, "modes_product: %d k-steps per m (at most 9, ell <= 35)", max_ks);
     if (n_times <= 0) return SCRIB200_OK;
     int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
     if (n_ctas <= 0) n_ctas = 148;
     int64_t grid = n_tg < n_ctas ? n_tg : n_ctas;
-    auto kern = modes_product_kernel<21, 9, 256>;
+    auto kern = (gm == 5) ? modes_product_kernel<5, 11, 9, 512> : modes_product_kernel<9, 21, 9, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
         set_error("modes_product: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

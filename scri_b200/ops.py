@@ -296,12 +296,12 @@ def _product_device_tables(key):
     return _product_cache[dkey]
 
 
-def modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max, n_ctas=0):
+def modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max, n_ctas=0, shape=None):
     """Fused separable product (scrib200_modes_product, K9): device/host mode series in, modes of the product from
     ell = 0 to output_ell_max out; None when the problem does not fit one CTA (callers use the dense path)."""
     torch = _torch()
     lib = _lib.load()
-    tb, dev = _product_device_tables((sa, a_ell_min, a_ell_max, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max))
+    tb, dev = _product_device_tables((sa, a_ell_min, a_ell_max, sb, b_ell_min, b_ell_max, n_theta, n_phi, output_ell_max, shape))
     if not tb.fits:
         return None
     da = to_device(a, np.complex128)

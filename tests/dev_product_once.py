@@ -1,0 +1,17 @@
+"""One launch of the fused product kernel at config-4 size (for ncu).  Dev tool (GPU)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from scri_b200 import ops  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
+L = 32
+g = torch.Generator(device="cuda").manual_seed(0)
+a = torch.view_as_complex(torch.randn((N, (L + 1) ** 2, 2), dtype=torch.float64, device="cuda", generator=g))
+b = torch.view_as_complex(torch.randn((N, (L + 1) ** 2, 2), dtype=torch.float64, device="cuda", generator=g))
+for _ in range(2):
+    out = ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32)
+torch.cuda.synchronize()
+print(out.abs().max().item())

@@ -33,9 +33,9 @@ def timed(fn, reps=3):
     return min(ts)
 
 
-for n_ctas in (148, 296):
-    ms = timed(lambda: ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, n_ctas=n_ctas))
-    print(f"fused N={N} ctas={n_ctas}: {ms:.2f} ms  {tb.flops_per_step * N / ms / 1e9:.2f} TFLOP/s algorithmic  "
+for shape in (0, 1):
+    ms = timed(lambda: ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape))
+    print(f"fused N={N} shape={_product.SHAPES[shape]}: {ms:.2f} ms  {tb.flops_per_step * N / ms / 1e9:.2f} TFLOP/s algorithmic  "
           f"{16 * 3 * 1089 * N / ms / 1e6:.0f} GB/s algorithmic", flush=True)
 Nd = min(N, 2000)
 ms = timed(lambda: ops.grid_multiply(a[:Nd], 2, 0, L, b[:Nd], -2, 0, L, 129, 129, 64, output_ell_max=32, fused=False), reps=1)

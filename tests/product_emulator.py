@@ -7,11 +7,10 @@ from scri_b200 import _product
 
 def emulate(tb, a1, a2):
     cfg = [int(x) for x in tb.cfg]
-    ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem, nwarps, max_ks = cfg
+    ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem, nwarps, max_ks, GM, maxt = cfg
     N = a1.shape[0]
     n_out = (L_out + 1) ** 2
     out = np.zeros((N, n_out), dtype=complex)
-    GM = _product.GM
     for t0 in range(0, N, 4):
         nt = min(4, N - t0)
         sm = np.zeros(smem)
@@ -42,7 +41,7 @@ def emulate(tb, a1, a2):
             sm[offF1 : offF1 + 64 * (2 * L_out + 1)] = np.stack([P.real, P.imag], axis=-1).reshape(-1)
             for ti, (Mi, l0) in enumerate(tb.tiles):
                 for k in range(2):
-                    A = tb.wtfrag[c, ti * 64 + 32 * k : ti * 64 + 32 * k + 32].reshape(8, 4)
+                    A = tb.wtfrag[c, ti * 64 : ti * 64 + 64].reshape(8, 4, 2)[:, :, k]
                     B = sm[offF1 + Mi * 64 + 32 * k : offF1 + Mi * 64 + 32 * k + 32].reshape(4, 8)
                     acc[ti] += A @ B
         for ti, (Mi, l0) in enumerate(tb.tiles):

@@ -683,6 +683,8 @@ def test_fused_modes_product_config4_size_equals_dense_path():
     dense = ops.grid_multiply(a, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32, fused=False)
     assert fused.shape == dense.shape == (N, 33 * 33)
     assert rel(fused, dense) < RTOL
+    for shape in (0, 1):   # both instantiated kernel shapes (16 warps x 5 M, 8 warps x 9 M)
+        assert rel(ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape), dense) < RTOL
     a2 = _rand_modes(rng, N, L, 2)
     lin = ops.grid_multiply(a + 0.5 * a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)
     assert rel(lin, fused + 0.5 * ops.grid_multiply(a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)) < RTOL

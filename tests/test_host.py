@@ -241,5 +241,6 @@ def test_product_tables_config4_fit_one_cta():
     from scri_b200 import _product
 
     tb = _product.product_tables(2, 0, 32, -2, 0, 32, 129, 129, 32)
-    assert tb.fits and tb.smem_bytes <= 227 * 1024 and tb.nwarps == 8
+    assert tb.fits and tb.smem_bytes <= 227 * 1024 and (tb.gm, tb.nwarps) == (5, 16)
+    assert _product.product_tables(2, 0, 32, -2, 0, 32, 129, 129, 32, shape=1).nwarps == 8
     assert not _product.product_tables(2, 0, 64, -2, 0, 64, 257, 257, 64).fits   # the dense kernels take over
