@@ -215,8 +215,8 @@ int scrib200_grid_product(const double* a, const double* b, double* out, int64_t
  *   a1 [n_times, n1], a2 [n_times, n2] complex128 mode series; out [n_times, (L_out+1)^2] (modes from ell = 0);
  *   perm1/perm2, tasks [n_tasks, 4], lamfrag [n_chunks, lam_stride], tiles [n_tiles, 2], wtfrag [n_chunks, wt_stride]:
  *   device tables from scri_b200._product.product_tables (Wigner-d values and quadrature weights per ring, laid out as
- *   DMMA fragments); cfg: HOST int[14] = (ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem doubles,
- *   warps, max k-steps, M per convolution warp, tiles per warp).  n_ctas <= 0 selects one persistent CTA per SM.  Fails (SCRIB200_EINVAL) when the tables do
+ *   DMMA fragments); cfg: HOST int[15] = (ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem doubles,
+ *   warps, max k-steps, M per convolution warp, tiles per warp, 0).  n_ctas <= 0 selects one persistent CTA per SM.  Fails (SCRIB200_EINVAL) when the tables do
  *   not fit one CTA (ell beyond ~35): callers then use scrib200_swsh_synthesize / scrib200_grid_product / scrib200_map2salm. */
 size_t scrib200_modes_product_max_shared_bytes(void);
 int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, int64_t n_times, const int* perm1,

@@ -61,8 +61,9 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     szA = 8 * PA_total                                     # doubles: [pos][t = 4][re, im]
     offF1 = szA
     nF1 = max(2 * ell1_max + 1, n_mout)                     # the product P_M overwrites F1
-    offF2 = offF1 + 64 * nF1
-    smem_doubles = offF2 + 64 * (2 * ell2_max + 1)
+    gm_max = max(sh[0] for sh in SHAPES)
+    offF2 = offF1 + 64 * nF1 + 64 * (gm_max + 2)           # zero guards around F2: GM + 2 entries below, GM - 1 above
+    smem_doubles = offF2 + 64 * (2 * ell2_max + 1) + 64 * (gm_max - 1)
 
     # output tiles: 8 consecutive l of one M
     tiles = [(M + L_out, l0) for M in range(-L_out, L_out + 1) for l0 in range(abs(M), L_out + 1, 8)]
@@ -113,7 +114,7 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     tb.lamfrag = np.ascontiguousarray(lamfrag)
     tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
     tb.wtfrag = np.ascontiguousarray(wtfrag)
-    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks, GM, maxt], dtype=np.int32)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks, GM, maxt, 0], dtype=np.int32)
     tb.n_out = (L_out + 1) ** 2
     tb.nwarps = nwarps
     tb.gm = GM

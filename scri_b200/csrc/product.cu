@@ -15,6 +15,8 @@
 // One persistent CTA per SM owns 4 consecutive time steps: their modes are staged once in shared memory in m-major order
 // and the CTA walks the rings in chunks of 8; the tables (fragment-ordered by the host, L2 resident) stream through
 // registers.  Algorithmic HBM traffic: 16 (n1 + n2 + n_out) bytes per time step.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace scrib200 {
@@ -39,12 +41,19 @@ struct ProductParams {
     int szA;                // doubles of the two staged mode tiles (also the output staging area)
     int offF1, offF2;       // double offsets of the F1 / P buffer and the F2 buffer
     int stage_out;
+    int smem_doubles;
+    int skip;               // development: bit 0 / 1 / 2 skips stage A / B / C (timing only; 0 in production)
 };
 
 __device__ __forceinline__ void dmma_p(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16_p(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 
 constexpr int PRODUCT_T = 4;   // time steps per CTA pass: 4 x (re, im) = the 8 columns of one DMMA tile
@@ -64,6 +73,7 @@ modes_product_kernel(const ProductParams p) {
     const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
     const int fr = (lane & 3) * 8 + (lane >> 2);   // B fragment of an [k = 4 rows][8 columns] block stored 8 doubles per row
 
+    for (int i = p.offF1 / 2 + tid; i < p.smem_doubles / 2; i += nthreads) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);   // guards of F2
     // this warp's output tiles (the same for every chunk and time group; the table is padded with empty tiles)
     int tile_m[MAXT];
 #pragma unroll
@@ -75,14 +85,16 @@ modes_product_kernel(const ProductParams p) {
         // ---- stage the modes of these time steps, m-major: sm[perm[idx] + 2 t + (re, im)]
         for (int i = tid; i < p.szA / 2; i += nthreads) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
         __syncthreads();
-        for (int e = tid; e < nt * p.n1; e += nthreads) {
+        for (int e = tid; e < nt * p.n1; e += nthreads) {   // 16-byte asynchronous copies: all in flight at once
             int t = e / p.n1, idx = e - t * p.n1;
-            *reinterpret_cast<double2*>(sm + __ldg(p.perm1 + idx) + 2 * t) = p.a1[t0 * p.n1 + e];
+            cp_async16_p(sm + __ldg(p.perm1 + idx) + 2 * t, p.a1 + t0 * p.n1 + e);
         }
         for (int e = tid; e < nt * p.n2; e += nthreads) {
             int t = e / p.n2, idx = e - t * p.n2;
-            *reinterpret_cast<double2*>(sm + __ldg(p.perm2 + idx) + 2 * t) = p.a2[t0 * p.n2 + e];
+            cp_async16_p(sm + __ldg(p.perm2 + idx) + 2 * t, p.a2 + t0 * p.n2 + e);
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
 
         double acc[MAXT][2];
@@ -92,7 +104,7 @@ modes_product_kernel(const ProductParams p) {
         for (int c = 0; c < p.n_chunks; ++c) {
             // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7: one (field, m) per task; the fragments of
             //      the next two tasks are in flight (L2 latency) while the DMMA chain of this one runs
-            {
+            if (!(p.skip & 1)) {
                 const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
                 auto fetch = [&](int i, int4& tk, double (&af)[MAXKS]) {
                     tk = (i < p.n_tasks) ? __ldg(p.tasks + i) : make_int4(0, 0, 0, -1);
@@ -101,12 +113,12 @@ modes_product_kernel(const ProductParams p) {
                 };
                 auto run = [&](const int4& tk, const double (&af)[MAXKS]) {
                     if (tk.w < 0) return;
-                    double c0 = 0.0, c1 = 0.0;
+                    double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};   // three short DMMA chains instead of one long one
                     const double* bsrc = sm + tk.x + fr;
 #pragma unroll
                     for (int ks = 0; ks < MAXKS; ++ks)
-                        if (ks < tk.y) dmma_p(c0, c1, af[ks], bsrc[ks * 32]);
-                    *reinterpret_cast<double2*>(sm + tk.w + 2 * lane) = make_double2(c0, c1);   // F_m[item = ring*4 + t]
+                        if (ks < tk.y) dmma_p(c0[ks % 3], c1[ks % 3], af[ks], bsrc[ks * 32]);
+                    *reinterpret_cast<double2*>(sm + tk.w + 2 * lane) = make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);   // F_m[item = ring*4 + t]
                 };
                 int4 k0, k1, k2;
                 double f0[MAXKS], f1[MAXKS], f2[MAXKS];
@@ -127,33 +139,37 @@ modes_product_kernel(const ProductParams p) {
             double2 pacc[GM];
 #pragma unroll
             for (int q = 0; q < GM; ++q) pacc[q] = make_double2(0.0, 0.0);
-            if (warp < n_groups) {
+            if (warp < n_groups && !(p.skip & 2)) {
                 const int M0 = -p.L_out + GM * warp;
                 const double2* f1 = sF1 + lane;
                 const double2* f2 = sF2 + lane;
                 const int l2 = p.ell2;
-                auto ld2 = [&](int m2) -> double2 {
-                    return (m2 >= -l2 && m2 <= l2) ? f2[(m2 + l2) * 32] : make_double2(0.0, 0.0);
-                };
                 for (int q = -p.qmax; q <= p.qmax; ++q) {
                     const int Me = M0 + q * p.n_phi;
                     const int lo = max(-p.ell1, Me - l2), hi = min(p.ell1, Me + GM - 1 + l2);
                     if (lo > hi) continue;
+                    // F2 carries zero guard entries (GM + 2 below, GM - 1 above), so its loads need no range checks
                     double2 y[GM + 3];   // y[k] <-> m2 = Me - m1b - 3 + k
+                    const double2* f2q = f2 + (Me + l2) * 32;
 #pragma unroll
-                    for (int k = 0; k < GM - 1; ++k) y[k] = ld2(Me - lo + 1 + k);
-                    for (int m1b = lo; m1b <= hi; m1b += 4) {
+                    for (int k = 0; k < GM - 1; ++k) y[k] = f2q[(1 + k - lo) * 32];
+                    auto block = [&](int m1b, auto tail) {
 #pragma unroll
                         for (int k = GM - 2; k >= 0; --k) y[k + 4] = y[k];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) y[k] = ld2(Me - m1b - 3 + k);
+                        for (int k = 0; k < 4; ++k) y[k] = f2q[(k - 3 - m1b) * 32];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const double2 x = (m1b + i <= hi) ? f1[(m1b + i + p.ell1) * 32] : make_double2(0.0, 0.0);
+                            double2 x = make_double2(0.0, 0.0);
+                            if (!decltype(tail)::value || m1b + i <= hi) x = f1[(m1b + i + p.ell1) * 32];
 #pragma unroll
                             for (int qq = 0; qq < GM; ++qq) cfma(pacc[qq], x, y[qq - i + 3]);
                         }
-                    }
+                    };
+                    int m1b = lo;
+#pragma unroll 2
+                    for (; m1b + 3 <= hi; m1b += 4) block(m1b, std::false_type{});
+                    if (m1b <= hi) block(m1b, std::true_type{});
                 }
             }
             // quadrature fragments of this chunk: issued now, consumed after the two barriers below
@@ -172,6 +188,7 @@ modes_product_kernel(const ProductParams p) {
             __syncthreads();
 
             // ---- (C) theta quadrature: out[l, M] += sum over the 8 rings of W[lM, ring] P_M[ring]
+            if (!(p.skip & 4))
 #pragma unroll
             for (int s = 0; s < MAXT; ++s) {
                 const double* bsrc = sm + p.offF1 + tile_m[s] + fr;
@@ -243,6 +260,8 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     p.offF1 = cfg[7];
     p.offF2 = cfg[8];
     const int smem_doubles = cfg[9], nwarps = cfg[10], max_ks = cfg[11], gm = cfg[12], maxt = cfg[13];
+    p.skip = cfg[14];
+    p.smem_doubles = smem_doubles;
     p.n_out = (p.L_out + 1) * (p.L_out + 1);
     p.stage_out = (PRODUCT_T * p.n_out * 2 <= p.szA) ? 1 : 0;
     SCRIB200_REQUIRE(n1 > 0 && n2 > 0 && n_tasks > 0 && n_tiles > 0 && p.n_chunks > 0, "modes_product: empty tables");

@@ -37,6 +37,13 @@ for shape in (0, 1):
     ms = timed(lambda: ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape))
     print(f"fused N={N} shape={_product.SHAPES[shape]}: {ms:.2f} ms  {tb.flops_per_step * N / ms / 1e9:.2f} TFLOP/s algorithmic  "
           f"{16 * 3 * 1089 * N / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+for shape in (0, 1):
+    tbs = ops._product_device_tables((2, 0, L, -2, 0, L, 129, 129, 32, shape))[0]
+    for skip in (1, 2, 4, 3, 5, 6, 7):
+        tbs.cfg[14] = skip
+        ms = timed(lambda: ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape))
+        print(f"  shape {shape} skipping stages {[x for i, x in enumerate('ABC') if skip >> i & 1]}: {ms:.2f} ms")
+    tbs.cfg[14] = 0
 Nd = min(N, 2000)
 ms = timed(lambda: ops.grid_multiply(a[:Nd], 2, 0, L, b[:Nd], -2, 0, L, 129, 129, 64, output_ell_max=32, fused=False), reps=1)
 print(f"dense chain N={Nd}: {ms:.2f} ms -> {ms * N / Nd:.1f} ms scaled to N={N}")

@@ -7,7 +7,7 @@ from scri_b200 import _product
 
 def emulate(tb, a1, a2):
     cfg = [int(x) for x in tb.cfg]
-    ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem, nwarps, max_ks, GM, maxt = cfg
+    ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem, nwarps, max_ks, GM, maxt, _ = cfg
     N = a1.shape[0]
     n_out = (L_out + 1) ** 2
     out = np.zeros((N, n_out), dtype=complex)
