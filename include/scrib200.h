@@ -213,14 +213,14 @@ int scrib200_grid_product(const double* a, const double* b, double* out, int64_t
  * ModesTimeSeries.grid_multiply (scri/modes_time_series.py:177-193), and sf.Modes.multiply as bms_charges.py:40-187
  * calls it (the quadrature is exact once the working band limit reaches ell1 + ell2).
  *   a1 [n_times, n1], a2 [n_times, n2] complex128 mode series; out [n_times, (L_out+1)^2] (modes from ell = 0);
- *   perm1/perm2, tasks [n_tasks, 4], lamfrag [n_chunks, lam_stride], tiles [n_tiles, 2], wtfrag [n_chunks, wt_stride]:
+ *   perm1/perm2, ctl [n_steps], lamfrag [n_chunks, lam_stride], tiles [n_tiles, 2], wtfrag [n_chunks, wt_stride]:
  *   device tables from scri_b200._product.product_tables (Wigner-d values and quadrature weights per ring, laid out as
  *   DMMA fragments); cfg: HOST int[15] = (ell1, ell2, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem doubles,
  *   warps, max k-steps, M per convolution warp, tiles per warp, 0).  n_ctas <= 0 selects one persistent CTA per SM.  Fails (SCRIB200_EINVAL) when the tables do
  *   not fit one CTA (ell beyond ~35): callers then use scrib200_swsh_synthesize / scrib200_grid_product / scrib200_map2salm. */
 size_t scrib200_modes_product_max_shared_bytes(void);
 int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, int64_t n_times, const int* perm1,
-                           const int* perm2, const int* tasks, int n_tasks, const double* lamfrag, int64_t lam_stride,
+                           const int* perm2, const int* ctl, int n_steps, const double* lamfrag, int64_t lam_stride,
                            const int* tiles, int n_tiles, const double* wtfrag, int64_t wt_stride, const int* cfg,
                            double* out, int n_ctas, void* stream);
 

@@ -13,9 +13,8 @@ import numpy as np
 from . import _sf
 
 T = 4           # time steps per CTA pass (PRODUCT_T)
-# kernel shapes instantiated in csrc/product.cu: (consecutive M per convolution warp, warps, output tiles per warp)
-SHAPES = ((5, 16, 11), (9, 8, 21))
-MAX_KSTEPS = 9
+# kernel shapes instantiated in csrc/product.cu: (consecutive M per convolution warp, warps, output tiles per warp, fragment ring depth)
+SHAPES = ((5, 16, 11, 9), (9, 8, 21, 18))
 MAX_SMEM = 227 * 1024
 
 
@@ -67,17 +66,17 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
 
     # output tiles: 8 consecutive l of one M
     tiles = [(M + L_out, l0) for M in range(-L_out, L_out + 1) for l0 in range(abs(M), L_out + 1, 8)]
-    max_ks = int(max(f["ks"].max() for f in fields))
+    n_steps = PA_total // 4
     chosen = None
     for sh in SHAPES if shape is None else (SHAPES[shape],):
-        gm, nw, maxt = sh
+        gm, nw, maxt, _ = sh
         if -(-n_mout // gm) <= nw and len(tiles) <= nw * maxt:
             chosen = sh
             break
-    tb.fits = chosen is not None and 8 * smem_doubles <= MAX_SMEM and max_ks <= MAX_KSTEPS and n_theta >= 2
-    tb.smem_bytes = 8 * smem_doubles
+    tb.fits = chosen is not None and 8 * smem_doubles + 4 * (n_steps + 17 + 17 * 18) <= MAX_SMEM and n_steps < 65536 and n_theta >= 2
+    tb.smem_bytes = 8 * smem_doubles + 4 * (n_steps + 17 + 17 * 18)
     if tb.fits:
-        GM, nwarps, maxt = chosen
+        GM, nwarps, maxt, DA = chosen
         tiles += [(0, L_out + 1)] * (nwarps * maxt - len(tiles))     # empty tiles: every warp walks `maxt` of them
     n_tiles = len(tiles)
     if not tb.fits:
@@ -91,12 +90,22 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
         lam = _lambda(f["s"], f["lmax"], n_theta)           # [n_theta, (lmax+1)^2], zero for l < |s|
         n = f["perm"].shape[0]
         lam_pad[:n_theta, f["base"] + f["perm"]] = lam[:, f["lmin"] ** 2 : f["lmin"] ** 2 + n]
-        offF = offF1 if fi == 0 else offF2
+        entry0 = 0 if fi == 0 else (offF2 - offF1) // 64
         for mi in range(2 * f["lmax"] + 1):
-            tasks.append((8 * (f["base"] + int(f["pos"][mi])), int(f["ks"][mi]), 32 * ((f["base"] + int(f["pos"][mi])) // 4), offF + 64 * mi))
-    # longest first, dealt round-robin: the warps finish stage A together
+            tasks.append(((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi))   # (first k-step, k-steps, F entry)
+    # per-warp streams of k-steps: tasks longest first, each to the warp with the shortest stream so far
     tasks.sort(key=lambda x: -x[1])
-    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8)
+    streams = [[] for _ in range(nwarps)]
+    for g0, ks, entry in tasks:
+        st = min(streams, key=len)
+        st.extend((g0 + k) | (entry << 16) | ((1 << 31) if k == ks - 1 else 0) for k in range(ks))
+    nop = n_steps                                            # an all-zero fragment appended to every chunk row
+    for st in streams:
+        st.extend([nop] * (-len(st) % DA))
+    woff = (nwarps + 1) + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
+    ctl = np.array(list(woff) + [u for st in streams for u in st] + [nop] * DA, dtype=np.uint32)
+    lam_pad = np.concatenate([lam_pad, np.zeros((n_rings, 4))], axis=1)
+    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8 + 32)
 
     # stage C: quadrature fragments W[(l0 + lane/4, M), ring = 8c + 4ks + lane%4], the two k-steps of a lane adjacent
     _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)       # [(L_out+1)^2, n_theta]
@@ -110,11 +119,12 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     qmax = (ell1_max + ell2_max + L_out) // n_phi
     tb.perm1 = (8 * (fields[0]["base"] + fields[0]["perm"])).astype(np.int32)
     tb.perm2 = (8 * (fields[1]["base"] + fields[1]["perm"])).astype(np.int32)
-    tb.tasks = np.ascontiguousarray(np.array(tasks, dtype=np.int32))
+    tb.ctl = ctl.view(np.int32)
+    tb.n_ctl = int(ctl.shape[0])
     tb.lamfrag = np.ascontiguousarray(lamfrag)
     tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
     tb.wtfrag = np.ascontiguousarray(wtfrag)
-    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, max_ks, GM, maxt, 0], dtype=np.int32)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, 0, GM, maxt, 0], dtype=np.int32)
     tb.n_out = (L_out + 1) ** 2
     tb.nwarps = nwarps
     tb.gm = GM

@@ -29,8 +29,8 @@ struct ProductParams {
     int n1, n2, n_out;
     const int* perm1;       // [n1]  double offset in shared memory of mode idx of field 1 (m-major, padded to 4 per m)
     const int* perm2;       // [n2]
-    const int4* tasks;      // [n_tasks] (smem double offset of the first l of this m, k-steps, fragment offset, smem offset of F_m)
-    int n_tasks;
+    const unsigned* ctl;    // [n_ctl] stage A: first entry of every warp's stream (nwarps + 1 entries), then the streams: per k-step
+    int n_steps;            //   (global k-step index | F entry << 16 | last-of-task << 31), padded per warp to the ring depth; n_steps = n_ctl
     const double* lamfrag;  // [n_chunks, lam_stride] A fragments of stage A
     int64_t lam_stride;
     const int2* tiles;      // [n_tiles] (M + L_out, l0)
@@ -41,7 +41,7 @@ struct ProductParams {
     int szA;                // doubles of the two staged mode tiles (also the output staging area)
     int offF1, offF2;       // double offsets of the F1 / P buffer and the F2 buffer
     int stage_out;
-    int smem_doubles;
+    int smem_doubles;       // data region; the control words of stage A follow it
     int skip;               // development: bit 0 / 1 / 2 skips stage A / B / C (timing only; 0 in production)
 };
 
@@ -58,9 +58,9 @@ __device__ __forceinline__ void cp_async16_p(void* smem, const void* gmem) {
 
 constexpr int PRODUCT_T = 4;   // time steps per CTA pass: 4 x (re, im) = the 8 columns of one DMMA tile
 
-// GM = consecutive M per convolution warp, MAXT = output tiles per warp, MAXKS = k-steps (4 l each) per m.
+// GM = consecutive M per convolution warp, MAXT = output tiles per warp, DA = table fragments in flight per lane in stage A.
 // Two shapes are instantiated: 16 warps x 5 M (ell_out <= 39) and 8 warps x 9 M; the host picks by table size.
-template <int GM, int MAXT, int MAXKS, int MAXTHREADS>
+template <int GM, int MAXT, int DA, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1)
 modes_product_kernel(const ProductParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -74,6 +74,8 @@ modes_product_kernel(const ProductParams p) {
     const int fr = (lane & 3) * 8 + (lane >> 2);   // B fragment of an [k = 4 rows][8 columns] block stored 8 doubles per row
 
     for (int i = p.offF1 / 2 + tid; i < p.smem_doubles / 2; i += nthreads) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);   // guards of F2
+    unsigned* sctl = reinterpret_cast<unsigned*>(sm + p.smem_doubles);
+    for (int i = tid; i < p.n_steps; i += nthreads) sctl[i] = __ldg(p.ctl + i);
     // this warp's output tiles (the same for every chunk and time group; the table is padded with empty tiles)
     int tile_m[MAXT];
 #pragma unroll
@@ -102,35 +104,35 @@ modes_product_kernel(const ProductParams p) {
         for (int s = 0; s < MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
 
         for (int c = 0; c < p.n_chunks; ++c) {
-            // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7: one (field, m) per task; the fragments of
-            //      the next two tasks are in flight (L2 latency) while the DMMA chain of this one runs
+            // ---- (A) theta synthesis of both fields for rings 8c .. 8c+7.  Every warp walks its own stream of k-steps
+            //      (its share of the (field, m) tasks back to back); a ring of DA table fragments per lane is in flight so
+            //      the L2 latency hides behind ~DA DMMA slots whatever the length of the individual tasks
             if (!(p.skip & 1)) {
                 const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
-                auto fetch = [&](int i, int4& tk, double (&af)[MAXKS]) {
-                    tk = (i < p.n_tasks) ? __ldg(p.tasks + i) : make_int4(0, 0, 0, -1);
+                const int s0 = (int)sctl[warp], n = (int)sctl[warp + 1] - s0;   // n is a multiple of DA (padded with no-op steps)
+                const unsigned* ctl = sctl + s0;
+                double fq[DA];
+                unsigned cq[DA];
 #pragma unroll
-                    for (int ks = 0; ks < MAXKS; ++ks) af[ks] = ks < tk.y ? __ldg(lf + tk.z + ks * 32) : 0.0;
-                };
-                auto run = [&](const int4& tk, const double (&af)[MAXKS]) {
-                    if (tk.w < 0) return;
-                    double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};   // three short DMMA chains instead of one long one
-                    const double* bsrc = sm + tk.x + fr;
+                for (int d = 0; d < DA; ++d) {
+                    cq[d] = ctl[d];
+                    fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+                }
+                double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};   // three short DMMA chains per task
+                for (int base = 0; base < n; base += DA) {
+                    ctl += DA;
 #pragma unroll
-                    for (int ks = 0; ks < MAXKS; ++ks)
-                        if (ks < tk.y) dmma_p(c0[ks % 3], c1[ks % 3], af[ks], bsrc[ks * 32]);
-                    *reinterpret_cast<double2*>(sm + tk.w + 2 * lane) = make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);   // F_m[item = ring*4 + t]
-                };
-                int4 k0, k1, k2;
-                double f0[MAXKS], f1[MAXKS], f2[MAXKS];
-                fetch(warp, k0, f0);
-                fetch(warp + nwarps, k1, f1);
-                for (int i = warp; i < p.n_tasks; i += 3 * nwarps) {
-                    fetch(i + 2 * nwarps, k2, f2);
-                    run(k0, f0);
-                    fetch(i + 3 * nwarps, k0, f0);
-                    run(k1, f1);
-                    fetch(i + 4 * nwarps, k1, f1);
-                    run(k2, f2);
+                    for (int d = 0; d < DA; ++d) {   // branch-free: the scheduler batches the shared-memory operand loads
+                        const unsigned u = cq[d];
+                        dmma_p(c0[d % 3], c1[d % 3], fq[d], sm[(u & 0xffffu) * 32 + fr]);
+                        if (u >> 31) {   // F_m[item = ring*4 + t] of this (field, m) is complete
+                            *reinterpret_cast<double2*>(sm + p.offF1 + ((u >> 16) & 0x7fffu) * 64 + 2 * lane) =
+                                make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);
+                            c0[0] = c0[1] = c0[2] = c1[0] = c1[1] = c1[2] = 0.0;
+                        }
+                        cq[d] = ctl[d];   // next turn of the ring (past the end of the stream: harmless in-range loads)
+                        fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+                    }
                 }
             }
             __syncthreads();
@@ -226,13 +228,13 @@ modes_product_kernel(const ProductParams p) {
 extern "C" size_t scrib200_modes_product_max_shared_bytes(void) { return 227u * 1024u; }
 
 extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, int64_t n_times,
-                                      const int* perm1, const int* perm2, const int* tasks, int n_tasks,
+                                      const int* perm1, const int* perm2, const int* ctl, int n_steps,
                                       const double* lamfrag, int64_t lam_stride, const int* tiles, int n_tiles,
                                       const double* wtfrag, int64_t wt_stride, const int* cfg, double* out,
                                       int n_ctas, void* stream) {
     using namespace scrib200;
-    SCRIB200_REQUIRE(a1 && a2 && perm1 && perm2 && tasks && lamfrag && tiles && wtfrag && cfg && out, "modes_product: null pointer");
-    SCRIB200_REQUIRE(aligned16(a1) && aligned16(a2) && aligned16(out) && aligned16(tasks), "modes_product: pointers must be 16-byte aligned");
+    SCRIB200_REQUIRE(a1 && a2 && perm1 && perm2 && ctl && lamfrag && tiles && wtfrag && cfg && out, "modes_product: null pointer");
+    SCRIB200_REQUIRE(aligned16(a1) && aligned16(a2) && aligned16(out) && aligned16(wtfrag), "modes_product: pointers must be 16-byte aligned");
     ProductParams p;
     p.a1 = reinterpret_cast<const double2*>(a1);
     p.a2 = reinterpret_cast<const double2*>(a2);
@@ -242,8 +244,8 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     p.n2 = n2;
     p.perm1 = perm1;
     p.perm2 = perm2;
-    p.tasks = reinterpret_cast<const int4*>(tasks);
-    p.n_tasks = n_tasks;
+    p.ctl = reinterpret_cast<const unsigned*>(ctl);
+    p.n_steps = n_steps;
     p.lamfrag = lamfrag;
     p.lam_stride = lam_stride;
     p.tiles = reinterpret_cast<const int2*>(tiles);
@@ -259,15 +261,15 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     p.szA = cfg[6];
     p.offF1 = cfg[7];
     p.offF2 = cfg[8];
-    const int smem_doubles = cfg[9], nwarps = cfg[10], max_ks = cfg[11], gm = cfg[12], maxt = cfg[13];
+    const int smem_doubles = cfg[9], nwarps = cfg[10], gm = cfg[12], maxt = cfg[13];
     p.skip = cfg[14];
     p.smem_doubles = smem_doubles;
     p.n_out = (p.L_out + 1) * (p.L_out + 1);
     p.stage_out = (PRODUCT_T * p.n_out * 2 <= p.szA) ? 1 : 0;
-    SCRIB200_REQUIRE(n1 > 0 && n2 > 0 && n_tasks > 0 && n_tiles > 0 && p.n_chunks > 0, "modes_product: empty tables");
+    SCRIB200_REQUIRE(n1 > 0 && n2 > 0 && n_steps > 0 && n_steps < 65536 && n_tiles > 0 && p.n_chunks > 0, "modes_product: empty tables");
     SCRIB200_REQUIRE(p.ell1 >= 0 && p.ell2 >= 0 && p.L_out >= 0 && p.n_phi > 0 && p.qmax >= 0, "modes_product: bad band limits");
     SCRIB200_REQUIRE((p.szA & 1) == 0 && (p.offF1 & 1) == 0 && (p.offF2 & 1) == 0, "modes_product: shared-memory offsets must be even");
-    const size_t smem = (size_t)smem_doubles * sizeof(double);
+    const size_t smem = (size_t)smem_doubles * sizeof(double) + (size_t)n_steps * sizeof(unsigned);
     SCRIB200_REQUIRE(smem <= scrib200_modes_product_max_shared_bytes(), "modes_product: %zu bytes of shared memory needed (limit %zu); use the dense path", smem,
                      scrib200_modes_product_max_shared_bytes());
     SCRIB200_REQUIRE((gm == 5 && nwarps == 16 && maxt == 11) || (gm == 9 && nwarps == 8 && maxt == 21),
@@ -275,12 +277,11 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     const int n_groups = (2 * p.L_out + 1 + gm - 1) / gm;
     SCRIB200_REQUIRE(nwarps >= n_groups, "modes_product: %d warps for %d groups of M", nwarps, n_groups);
     SCRIB200_REQUIRE(n_tiles == nwarps * maxt, "modes_product: the tile table must be padded to warps x tiles per warp (%d != %d x %d)", n_tiles, nwarps, maxt);
-    SCRIB200_REQUIRE(max_ks >= 1 && max_ks <= 9, "modes_product: %d k-steps per m (at most 9, ell <= 35)", max_ks);
     if (n_times <= 0) return SCRIB200_OK;
     int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
     if (n_ctas <= 0) n_ctas = 148;
     int64_t grid = n_tg < n_ctas ? n_tg : n_ctas;
-    auto kern = (gm == 5) ? modes_product_kernel<5, 11, 9, 512> : modes_product_kernel<9, 21, 9, 256>;
+    auto kern = (gm == 5) ? modes_product_kernel<5, 11, 9, 512> : modes_product_kernel<9, 21, 18, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
         set_error("modes_product: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

@@ -291,7 +291,7 @@ def _product_device_tables(key):
         tb = _product.product_tables(*key)
         dev = None
         if tb.fits:
-            dev = {k: torch.from_numpy(getattr(tb, k)).cuda() for k in ("perm1", "perm2", "tasks", "lamfrag", "tiles", "wtfrag")}
+            dev = {k: torch.from_numpy(getattr(tb, k)).cuda() for k in ("perm1", "perm2", "ctl", "lamfrag", "tiles", "wtfrag")}
         _product_cache[dkey] = (tb, dev)
     return _product_cache[dkey]
 
@@ -313,7 +313,7 @@ def modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_th
     _lib.check(
         lib.scrib200_modes_product(
             _lib.ptr(da), da.shape[1], _lib.ptr(db), db.shape[1], N, _lib.ptr(dev["perm1"]), _lib.ptr(dev["perm2"]),
-            _lib.ptr(dev["tasks"]), dev["tasks"].shape[0], _lib.ptr(dev["lamfrag"]), dev["lamfrag"].shape[1],
+            _lib.ptr(dev["ctl"]), tb.n_ctl, _lib.ptr(dev["lamfrag"]), dev["lamfrag"].shape[1],
             _lib.ptr(dev["tiles"]), dev["tiles"].shape[0], _lib.ptr(dev["wtfrag"]), dev["wtfrag"].shape[1],
             tb.cfg.ctypes.data_as(ctypes.c_void_p), _lib.ptr(out), n_ctas, _lib.stream_ptr(),
         ),

@@ -11,7 +11,10 @@ L = 32
 g = torch.Generator(device="cuda").manual_seed(0)
 a = torch.view_as_complex(torch.randn((N, (L + 1) ** 2, 2), dtype=torch.float64, device="cuda", generator=g))
 b = torch.view_as_complex(torch.randn((N, (L + 1) ** 2, 2), dtype=torch.float64, device="cuda", generator=g))
+skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+shape = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+ops._product_device_tables((2, 0, L, -2, 0, L, 129, 129, 32, shape))[0].cfg[14] = skip
 for _ in range(2):
-    out = ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32)
+    out = ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape)
 torch.cuda.synchronize()
 print(out.abs().max().item())

@@ -20,13 +20,19 @@ def emulate(tb, a1, a2):
                 sm[perm + 2 * t + 1] = a[t0 + t].imag
         acc = np.zeros((len(tb.tiles), 8, 8))
         for c in range(n_chunks):
-            for x, ks, z, w in tb.tasks:
+            ctl = tb.ctl.view(np.uint32)
+            woff = ctl[: nwarps + 1]
+            for wp in range(nwarps):
                 C = np.zeros((8, 8))
-                for k in range(ks):
-                    A = tb.lamfrag[c, z + 32 * k : z + 32 * k + 32].reshape(8, 4)
-                    B = sm[x + 32 * k : x + 32 * k + 32].reshape(4, 8)
+                for u in ctl[woff[wp] : woff[wp + 1]]:
+                    g = int(u) & 0xFFFF
+                    A = tb.lamfrag[c, 32 * g : 32 * g + 32].reshape(8, 4)
+                    B = sm[32 * g : 32 * g + 32].reshape(4, 8)
                     C += A @ B
-                sm[w : w + 64] = C.reshape(64)
+                    if int(u) >> 31:
+                        w = offF1 + 64 * ((int(u) >> 16) & 0x7FFF)
+                        sm[w : w + 64] = C.reshape(64)
+                        C = np.zeros((8, 8))
             F1 = sm[offF1 : offF1 + 64 * (2 * ell1 + 1)].reshape(-1, 32, 2)
             F1 = F1[..., 0] + 1j * F1[..., 1]
             F2 = sm[offF2 : offF2 + 64 * (2 * ell2 + 1)].reshape(-1, 32, 2)
