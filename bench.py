@@ -460,6 +460,102 @@ def run_batch_workload(args):
         dist.destroy_process_group()
 
 
+def run_product_workload(args):
+    """BASELINE configs[3] (AsymptoticBondiData ell_max = 32, 1e5 steps): the mode product sigma x d/dt(bar sigma) of the
+    mass aspect / supermomentum (scri/asymptotic_bondi_data/bms_charges.py:40,243) on the 129 x 129 working grid through
+    the fused separable kernel K9 (scrib200_modes_product).  The time steps are independent: sharded by time over the
+    ranks with no collective (strong scaling).  Optional workload, not the default bench line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from scri_b200 import _lib, _product, ops, parallel
+
+    L, N = 32, args.n_times
+    n = (L + 1) ** 2
+    lo, hi = parallel.shard_range(N, rank, world)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    a = torch.view_as_complex(torch.randn((hi - lo, n, 2), dtype=torch.float64, device="cuda", generator=g))
+    b = torch.view_as_complex(torch.randn((hi - lo, n, 2), dtype=torch.float64, device="cuda", generator=g))
+    a[:, :4] = 0
+    b[:, :4] = 0
+    tb = _product.product_tables(2, 0, L, -2, 0, L, 2 * 2 * L + 1, 2 * 2 * L + 1, L)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        return ops.modes_product(a, 2, 0, L, b, -2, 0, L, 2 * 2 * L + 1, 2 * 2 * L + 1, L)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    dgemm = measure_dgemm_peak(torch) if rank == 0 else None
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    total = 0.0
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = total / args.steps
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    if rank == 0:
+        # CPU baseline: the reference's chain (salm2map x 2, product, map2salm) in the oracle port, a few steps
+        import time as _time
+        from oracle import abd_ref
+
+        ns = 8
+        ah, bh = a[:ns].cpu().numpy(), b[:ns].cpu().numpy()
+        t0 = _time.perf_counter()
+        ref = abd_ref.grid_multiply(ah, 2, bh, -2, working_ell_max=2 * L, output_ell_max=L)
+        cpu_s = _time.perf_counter() - t0
+        out = step()[:ns].cpu().numpy()
+        err = float(np.abs(out - ref).max() / np.abs(ref).max())
+        flops = tb.flops_per_step * (hi - lo)
+        line = {
+            "metric": "mode-timesteps/sec through ModesTimeSeries.grid_multiply (ell_max=32)", "value": float(n) * N / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[3]: product of two ell<=32 mode series (spins 2 and -2) on the 129x129 working grid, output ell<=32, {N} time steps sharded by time",
+                       "n_times": N, "n_modes": n, "grid": "129x129 (never formed in HBM)",
+                       "l2": "explicit 256 MiB L2 flush between timed iterations; inputs + output 5.2 GB"},
+            "roofline": {"kernel": "modes_product_kernel", "bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": dgemm, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / dgemm, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_launch": flops,
+                         "note": "separable algorithm: theta synthesis + m-convolution + theta quadrature; the dense grid chain would need 70x the flops"},
+            "cpu_baseline": {"value": float(n) * ns / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"first {ns} time steps through oracle.abd_ref.grid_multiply (restated spinsfast), {cpu_s:.1f} s; max rel. deviation of the GPU result {err:.1e}"},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line, default=float))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,7 +565,8 @@ def main():
     ap.add_argument("--n-times", type=int, default=100_000)
     ap.add_argument("--cpu-sample", type=int, default=4000, help="time steps in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=10_000, help="time steps per step of --impl reference")
-    ap.add_argument("--workload", default="transform", choices=["transform", "batch"], help="transform = configs[1] (the bench line); batch = configs[2]")
+    ap.add_argument("--workload", default="transform", choices=["transform", "batch", "product"],
+                    help="transform = configs[1] (the bench line); batch = configs[2]; product = configs[3] (ell<=32 mode products)")
     ap.add_argument("--batch", type=int, default=4096, help="waveforms in the batch workload (all ranks together)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -478,6 +575,8 @@ def main():
         run_reference(args)
     elif args.workload == "batch":
         run_batch_workload(args)
+    elif args.workload == "product":
+        run_product_workload(args)
     else:
         run_ours(args)
 

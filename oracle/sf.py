@@ -8,8 +8,9 @@ scri/sample_waveforms.py:353-364.
 
 Formulas: SURVEY.md Appendix A.1/A.3 (published definitions in the sf documentation,
 http://moble.github.io/spherical_functions/).  The Wigner-D sum is evaluated in extended
-precision (np.longdouble) so the oracle is *more* accurate than the double-precision Horner
-sum in sf itself; agreement with sf is expected at the 1e-15..1e-14 level, not bit-for-bit.
+precision (np.longdouble) up to l = 16 and through its Jacobi-polynomial closed form above (the
+alternating sum cancels there), so the oracle stays at the 1e-14 level up to l = 64 (config 4 works at
+l = 32 / 64); agreement with sf is expected at the 1e-15..1e-14 level, not bit-for-bit.
 """
 import math
 from functools import lru_cache
@@ -40,7 +41,10 @@ def total_size_D_matrices(ell_min, ell_max):
 
 
 # ----------------------------------------------------------------------------- Wigner D (A.3)
-def _wigner_D_element_ld(Ra, Rb, ell, mp, m):
+_EXPLICIT_SUM_ELL_MAX = 16
+
+
+def _wigner_D_element_sum(Ra, Rb, ell, mp, m):
     """D^ell_{mp,m}(R) by the explicit sum, in long double; Ra, Rb complex arrays (any shape)."""
     Ra = np.asarray(Ra, dtype=np.clongdouble)
     Rb = np.asarray(Rb, dtype=np.clongdouble)
@@ -75,6 +79,38 @@ def _wigner_D_element_ld(Ra, Rb, ell, mp, m):
         total = total + np.longdouble((-1) ** rho * c) * ra2**pa * rb2**pb
     phase = (Ra ** max(ka, 0)) * (np.conj(Ra) ** max(-ka, 0)) * (Rb ** max(kb, 0)) * (np.conj(Rb) ** max(-kb, 0))
     return pref * total * phase
+
+
+def _wigner_D_element_ld(Ra, Rb, ell, mp, m):
+    """D^ell_{mp,m}(R); Ra, Rb complex arrays (any shape), |Ra|^2 + |Rb|^2 = 1.
+
+    The explicit sum of SURVEY.md A.3,
+        D = sqrt((l+m)!(l-m)!/((l+mp)!(l-mp)!)) sum_rho (-1)^rho C(l+mp,rho) C(l-mp,l-rho-m)
+                Ra^(l+mp-rho) conj(Ra)^(l-rho-m) Rb^(rho-mp+m) conj(Rb)^rho,
+    factors into the phases Ra^(mp+m) Rb^(m-mp) (conjugates for negative powers) and a real alternating sum in
+    |Ra|^2, |Rb|^2.  That sum cancels catastrophically for l >~ 25 (1e-11 at l = 32 even in long double), so it is
+    evaluated in its closed form instead: it is Wigner's d^l_{mp,m}(beta) / (|Ra|^|mp+m| |Rb|^|m-mp|) with
+    cos(beta) = |Ra|^2 - |Rb|^2, i.e. a Jacobi polynomial (stable three-term recurrence, scipy.special.eval_jacobi):
+        sum = (-1)^max(mp-m,0) sqrt(C(2l-k, k+a) / C(k+b, b)) P_k^(a,b)(cos beta),
+        k = min(l+m, l-m, l+mp, l-mp), a = |mp-m|, b = |mp+m|.
+    Checked against a 60-digit evaluation of the sum up to l = 64 (tests/test_oracle.py): 4e-14.  Up to
+    l = _EXPLICIT_SUM_ELL_MAX the long-double sum itself is used (`_wigner_D_element_sum`, < 1e-15 there)."""
+    from scipy.special import eval_jacobi
+
+    if ell <= _EXPLICIT_SUM_ELL_MAX:
+        return _wigner_D_element_sum(Ra, Rb, ell, mp, m)
+    Ra = np.asarray(Ra, dtype=complex)
+    Rb = np.asarray(Rb, dtype=complex)
+    ra2 = (Ra * np.conj(Ra)).real
+    rb2 = (Rb * np.conj(Rb)).real
+    ka = mp + m
+    kb = m - mp
+    k = min(ell + m, ell - m, ell + mp, ell - mp)
+    a, b = abs(kb), abs(ka)
+    coef = math.sqrt(math.comb(2 * ell - k, k + a) / math.comb(k + b, b))
+    total = ((-1) ** max(mp - m, 0) * coef) * eval_jacobi(k, a, b, ra2 - rb2)
+    phase = (Ra ** max(ka, 0)) * (np.conj(Ra) ** max(-ka, 0)) * (Rb ** max(kb, 0)) * (np.conj(Rb) ** max(-kb, 0))
+    return total * phase
 
 
 def Wigner_D_matrices(Ra, Rb, ell_min, ell_max):

@@ -683,6 +683,9 @@ def test_fused_modes_product_config4_size_equals_dense_path():
     dense = ops.grid_multiply(a, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32, fused=False)
     assert fused.shape == dense.shape == (N, 33 * 33)
     assert rel(fused, dense) < RTOL
+    from oracle import abd_ref as A   # the reference's chain itself on two steps (a few seconds of CPU at this size)
+
+    assert rel(fused[:2], A.grid_multiply(a[:2], 2, b[:2], -2, working_ell_max=64, output_ell_max=32)) < RTOL
     for shape in (0, 1):   # both instantiated kernel shapes (16 warps x 5 M, 8 warps x 9 M)
         assert rel(ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape), dense) < RTOL
     a2 = _rand_modes(rng, N, L, 2)

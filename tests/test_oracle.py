@@ -296,3 +296,29 @@ def test_3j_product_equals_grid_product(s1, L1, s2, L2, Lo):
     ref = A.grid_multiply(a, s1, b, s2, working_ell_max=L1 + L2, output_ell_max=Lo)
     out = sf.modes_multiply(a, s1, L1, b, s2, L2, Lo)
     assert np.abs(out - ref).max() < 5e-15 * np.abs(ref).max()
+
+
+def test_wigner_d_high_ell_against_60_digit_sum():
+    """Above l = 16 the oracle's Wigner D switches from the long-double explicit sum (which cancels: 1e-11 at l = 32)
+    to the Jacobi-polynomial closed form; both branches against a 60-digit evaluation of the defining sum."""
+    import mpmath as mp
+
+    mp.mp.dps = 60
+
+    def d_exact(l, mp_, m, beta):
+        f = mp.factorial
+        pre = mp.sqrt(f(l + mp_) * f(l - mp_) * f(l + m) * f(l - m))
+        c, s = mp.cos(beta / 2), mp.sin(beta / 2)
+        tot = mp.mpf(0)
+        for k in range(max(0, m - mp_), min(l + m, l - mp_) + 1):
+            tot += (-1) ** (k - m + mp_) * c ** (2 * l + m - mp_ - 2 * k) * s ** (2 * k - m + mp_) / (f(l + m - k) * f(k) * f(l - k - mp_) * f(k - m + mp_))
+        return float(pre * tot)
+
+    worst = 0.0
+    for l in (8, 16, 17, 32, 64):
+        for beta in (0.3, 1.1, math.pi / 2, 2.7):
+            Ra, Rb = np.array(math.cos(beta / 2) + 0j), np.array(math.sin(beta / 2) + 0j)
+            for mp_ in range(-l, l + 1, max(1, l // 4)):
+                for m in range(-l, l + 1, max(1, l // 5)):
+                    worst = max(worst, abs(sf.Wigner_D_element(Ra, Rb, l, mp_, m).real - d_exact(l, mp_, m, mp.mpf(beta))))
+    assert worst < 1e-13
