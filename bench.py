@@ -28,6 +28,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line at init when
+    NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the JSON line alone goes to the
+    original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line, default=float) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 METRIC = "mode-timesteps/sec through WaveformModes.transform (ell_max=8)"
 UNIT = "mode-timesteps/s"
 
@@ -214,7 +238,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -376,7 +400,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
         }
-        print(json.dumps(line, default=float))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -455,7 +479,7 @@ def run_batch_workload(args):
                        "l2": "every sub-batch streams > 20 GB of intermediates: far beyond L2"},
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line, default=float))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -551,7 +575,7 @@ def run_product_workload(args):
                              "sample": f"first {ns} time steps through oracle.abd_ref.grid_multiply (restated spinsfast), {cpu_s:.1f} s; max rel. deviation of the GPU result {err:.1e}"},
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line, default=float))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -569,6 +593,7 @@ def main():
                     help="transform = configs[1] (the bench line); batch = configs[2]; product = configs[3] (ell<=32 mode products)")
     ap.add_argument("--batch", type=int, default=4096, help="waveforms in the batch workload (all ranks together)")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
