@@ -241,6 +241,7 @@ class GridPlan:
         self.d_k = torch.from_numpy(np.ascontiguousarray(kconformal)).to(self.device)
         self.d_alpha = torch.from_numpy(np.ascontiguousarray(alpha)).to(self.device)
         self._ws = None
+        self._d2h_stream = None
         self._side = None
         self._host_pool = []
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
@@ -475,6 +476,7 @@ class TransformPlan(GridPlan):
         self.d_trig = torch.from_numpy(trig).to(dev)
         self._tile = None
         self._ws = None
+        self._d2h_stream = None
         self._side = None
         self._host_pool = []
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
@@ -567,12 +569,42 @@ class TransformPlan(GridPlan):
             self._tile = int(_lib.load().scrib200_map2salm_tile_size(self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max))
         return self._tile
 
-    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None):
+    def _remap_analyze_to_host(self, t, F, uprm, prep, n_slabs):
+        """Spline remap + analysis per slab of OUTPUT times, each slab's modes copied to pinned host memory on a copy stream
+        while the next slab computes.  Slab boundaries are multiples of the hand-off tile; every slab is an ordinary
+        scrib200_spline_remap / scrib200_map2salm_tiled call on a slice of u'."""
+        torch = self.torch
+        n_out = uprm.shape[0]
+        host = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, pin_memory=True)
+        cur = torch.cuda.current_stream()
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream()
+        cs = self._d2h_stream
+        tile = self.tile
+        per = -(-n_out // n_slabs)
+        per = -(-per // tile) * tile
+        for lo in range(0, n_out, per):
+            hi = min(n_out, lo + per)
+            gridT = self._remap(t, F, uprm[lo:hi], prep, tile)
+            modes = self.analyze_tiled(gridT, hi - lo)
+            done = torch.cuda.Event()
+            done.record(cur)
+            cs.wait_event(done)
+            with torch.cuda.stream(cs):
+                host[lo:hi].copy_(modes, non_blocking=True)
+            modes.record_stream(cs)
+            del gridT, modes
+        cs.synchronize()
+        return host.numpy()
+
+    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
 
         The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
         stream while the synthesis kernel runs.  `prep` (from `prepare(t)`) can be reused for waveforms that share
-        their time axis."""
+        their time axis.  With `host_slabs` = S > 0 the modes come back as a numpy array in pinned host memory: the output
+        times are cut into S slabs, each remapped, analysed and copied out on a copy stream while the next one computes
+        (the end-to-end path of WaveformGrid.transform)."""
         cur = self.torch.cuda.current_stream()
         ready = self.torch.cuda.Event()
         ready.record(cur)
@@ -582,6 +614,8 @@ class TransformPlan(GridPlan):
         cur.wait_event(prep.done)
         uprm = prep.uprm
         if self.tile and not return_grid:
+            if host_slabs and uprm.shape[0] >= 8192:
+                return uprm, self._remap_analyze_to_host(t, F, uprm, prep, host_slabs)
             gridT = self.remap_tiled(t, F, uprm, prep)
             del F
             return uprm, self.analyze_tiled(gridT, uprm.shape[0])

@@ -148,7 +148,7 @@ class WaveformGrid(WaveformBase):
             a_fut.result()
             _lib.require_cuda().cuda.current_stream().wait_event(slabs[-1][2])
             slabs = None
-        uprm, modes = plan.run(t_d, a_d, slabs=slabs)
+        uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4)   # modes land in pinned host memory slab by slab
         if a_fut is not None:
             a_fut.result()                       # surfaces a failed copy
         if plan.leftover_kwargs:
