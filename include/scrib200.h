@@ -92,7 +92,8 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *   n_series >= 1: a batch of series sharing t, kconf, alpha and uprm: F is [n_series, n_times, G] and the outputs of
  *   series b are rows b*n_out .. (b+1)*n_out-1 of `out` (time-major) or of the time-tiled index space (tile = T).
  *   workspace: scrib200_spline_remap_workspace_bytes() - one int per (tile, grid point): the first output of each
- *   tile.  A CTA keeps its tile of F in shared memory; F is read once.
+ *   tile, and one flag per (tile, group of 8 grid points): tiles no output time falls in are skipped, so a call on a
+ *   slice of u' costs its share of the sweep.  A CTA keeps its tile of F in shared memory; F is read once.
  */
 size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, int halo, int body);
 int scrib200_spline_prepare(const double* t, int64_t n_times, double gamma_factor, int divide, double time_translation,

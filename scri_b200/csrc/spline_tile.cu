@@ -211,6 +211,22 @@ spline_jrange_kernel(const double* __restrict__ t, int N, int G, const double* _
     J[idx] = j;
 }
 
+// flags[tile][column group] = 1 when any of the group's grid points has an output in the tile.  A call that evaluates a
+// slice of the output times (a slab of u', an interpolation onto a few points) then skips the tiles it does not touch
+// instead of staging and sweeping them.
+__global__ void __launch_bounds__(256)
+spline_tile_flags_kernel(const int* __restrict__ J, int ntiles, int G, int ncg, int* __restrict__ flags) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ntiles * ncg) return;
+    const int tile = idx / ncg, cg = idx - tile * ncg;
+    int any = 0;
+    for (int c = 0; c < ST_COLS / 2; ++c) {
+        const int g = cg * (ST_COLS / 2) + c;
+        if (g < G) any |= (J[(size_t)tile * G + g] < J[(size_t)(tile + 1) * G + g]);
+    }
+    flags[idx] = any;
+}
+
 // MODE 0: evaluate at up[] (the BMS remap); MODE 1 / 2: first / second derivative at the knots; MODE 3: the
 // definite integral over [t_i, t_{i+1}] stored at row i+1 (row 0 = 0) - a column scan turns it into the antiderivative;
 // MODE 4: the increment of the second antiderivative, `up` then holding the (scanned) first antiderivative [N, G].
@@ -221,7 +237,9 @@ __global__ void __launch_bounds__(MAXT, 2)
 spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict__ F, int G,
                    const double* __restrict__ kconf, const double* __restrict__ alpha,
                    const double* __restrict__ tab, const double* __restrict__ up, int Nout,
-                   double* __restrict__ out, int tshift, int body, int halo, const int* __restrict__ J) {
+                   double* __restrict__ out, int tshift, int body, int halo, const int* __restrict__ J,
+                   const int* __restrict__ flags) {
+    if (MODE == 0 && flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // no output time falls in this tile
     extern __shared__ __align__(16) double s_mem[];
     __shared__ double s_k[ST_COLS / 2], s_al[ST_COLS / 2], s_ik[ST_COLS / 2];
     __shared__ int s_jlo[ST_COLS / 2], s_jhi[ST_COLS / 2];
@@ -602,21 +620,26 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     SCRIB200_REQUIRE(n_series >= 1 && n_series <= 65535, "%s: n_series=%d must be 1..65535", name, n_series);
     dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles, (unsigned)n_series);
     int* J = nullptr;
+    int* flags = nullptr;
     if (MODE == 0) {
-        const size_t need = (size_t)(ntiles + 1) * G * sizeof(int);
+        const size_t need = ((size_t)(ntiles + 1) * G + (size_t)ntiles * grid.x) * sizeof(int);
         SCRIB200_REQUIRE(workspace && workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", name, workspace_bytes, need);
         J = reinterpret_cast<int*>(workspace);
         const int64_t total = (ntiles + 1) * (int64_t)G;
         spline_jrange_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             t, (int)n_times, G, kconf, alpha, uprm, (int)n_out, body, (int)ntiles, J);
         SCRIB200_CHECK_LAUNCH(name);
+        flags = J + total;
+        const int64_t nflags = ntiles * (int64_t)grid.x;
+        spline_tile_flags_kernel<<<(unsigned)((nflags + 255) / 256), 256, 0, (cudaStream_t)stream>>>(J, (int)ntiles, G, (int)grid.x, flags);
+        SCRIB200_CHECK_LAUNCH(name);
     }
     if (wide)
         spline_tile_kernel<MODE, 512><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
+            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags);
     else
         spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J);
+            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }
@@ -649,7 +672,8 @@ extern "C" size_t scrib200_spline_remap_workspace_bytes(int64_t n_times, int G, 
     resolve_tile(halo, body);
     if (n_times < 2 || body <= 0) return 16;
     const int64_t ntiles = (n_times - 1 + body - 1) / body;
-    return (size_t)(ntiles + 1) * (size_t)G * sizeof(int) + 16;
+    const size_t ncg = (size_t)(2 * G + ST_COLS - 1) / ST_COLS;
+    return ((size_t)(ntiles + 1) * (size_t)G + (size_t)ntiles * ncg) * sizeof(int) + 16;
 }
 
 extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
