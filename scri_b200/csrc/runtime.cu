@@ -41,10 +41,33 @@ int64_t scrib200_launch_count(void) { return scrib200::g_launches.load(std::memo
 
 #include <condition_variable>
 #include <mutex>
+#include <emmintrin.h>
+
 #include <thread>
 #include <vector>
 
 namespace scrib200 {
+
+// Pageable -> pinned staging copy with non-temporal stores: the destination is written once and read next by the DMA
+// engine, so it should not be pulled into the cache first (no read-for-ownership traffic: ~1.4x a plain memcpy on the
+// hosts measured).  `d` is 16-byte aligned (slices of the page-aligned staging buffers start at multiples of 4096).
+static void stream_copy(char* d, const char* s, size_t n) {
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+        }
+        _mm_sfence();
+    }
+    if (i < n) memcpy(d + i, s + i, n - i);
+}
 
 class CopyPool {
   public:
@@ -70,7 +93,7 @@ class CopyPool {
             }
         }
         cv_.notify_all();
-        memcpy(dst, src, n < step ? n : step);   // the caller's share
+        stream_copy(dst, src, n < step ? n : step);   // the caller's share
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this] { return pending_ == 0; });
     }
@@ -87,7 +110,7 @@ class CopyPool {
                 j = jobs_.back();
                 jobs_.pop_back();
             }
-            memcpy(j.d, j.s, j.n);
+            stream_copy(j.d, j.s, j.n);
             {
                 std::lock_guard<std::mutex> lk(m_);
                 if (--pending_ == 0) done_.notify_all();
