@@ -46,7 +46,10 @@ def _field_layout(ell_min, ell_max):
 
 @lru_cache(maxsize=16)
 def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, shape=None):
+    if shape == 2:
+        return _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out)
     tb = ProductTables()
+    tb.cluster = False
     n_chunks = (n_theta + 7) // 8
     n_rings = 8 * n_chunks
     n_mout = 2 * L_out + 1
@@ -121,10 +124,11 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     tb.perm2 = (8 * (fields[1]["base"] + fields[1]["perm"])).astype(np.int32)
     tb.ctl = ctl.view(np.int32)
     tb.n_ctl = int(ctl.shape[0])
+    tb.n_tiles_arg = n_tiles
     tb.lamfrag = np.ascontiguousarray(lamfrag)
     tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
     tb.wtfrag = np.ascontiguousarray(wtfrag)
-    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, 0, GM, maxt, 0], dtype=np.int32)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, offF1, offF2, smem_doubles, nwarps, 0, GM, maxt, 0, 0], dtype=np.int32)
     tb.n_out = (L_out + 1) ** 2
     tb.nwarps = nwarps
     tb.gm = GM
@@ -135,4 +139,91 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
             max(0, min(ell1_max, M + ell2_max) - max(-ell1_max, M - ell2_max) + 1) for M in range(-L_out, L_out + 1))
         + 4 * n_theta * tb.n_out                                                           # (C) real weight x complex P_M
     )
+    return tb
+
+
+CLUSTER_GM, CLUSTER_MAXT, CLUSTER_DA = 5, 12, 9   # csrc/product.cu: modes_product_cluster_kernel<5, 12, 9>
+
+
+def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out):
+    """Tables of the cluster variant (a pair of CTAs per block of time steps; CTA r stages factor r only, convolves and
+    integrates its half of the M range): everything is per CTA rank."""
+    tb = ProductTables()
+    tb.cluster = True
+    GM, maxt, DA = CLUSTER_GM, CLUSTER_MAXT, CLUSTER_DA
+    n_chunks = (n_theta + 7) // 8
+    n_rings = 8 * n_chunks
+    n_mout = 2 * L_out + 1
+    fields = []
+    base = 0
+    for s, lmin, lmax in ((s1, ell1_min, ell1_max), (s2, ell2_min, ell2_max)):
+        pos, ks, PA, perm, l_lo = _field_layout(lmin, lmax)
+        fields.append(dict(s=s, lmin=lmin, lmax=lmax, pos=pos, ks=ks, PA=PA, perm=perm, l_lo=l_lo, base=base))
+        base += PA
+    PA_total = base
+    n_steps = PA_total // 4
+    szA = 8 * max(f["PA"] for f in fields)
+    nF1 = max(2 * ell1_max + 1, n_mout)
+    offF2rel = 64 * nF1 + 64 * (GM + 2)
+    bufStride = offF2rel + 64 * (2 * ell2_max + 1) + 64 * (GM - 1)
+    smem_doubles = szA + 2 * bufStride
+    ng = -(-n_mout // GM)
+    gcnt = [(ng + 1) // 2, ng - (ng + 1) // 2]
+    g0 = [0, gcnt[0]]
+    all_tiles = [(M + L_out, l0) for M in range(-L_out, L_out + 1) for l0 in range(abs(M), L_out + 1, 8)]
+    rank_tiles = [[tl for tl in all_tiles if (tl[0] // GM >= g0[r]) and (tl[0] // GM < g0[r] + gcnt[r])] for r in range(2)]
+    tiles_r = 8 * maxt
+    # control streams per rank (8 synthesis warps)
+    lam_pad = np.zeros((n_rings, PA_total + 4))
+    ctls = []
+    for r, f in enumerate(fields):
+        lam = _lambda(f["s"], f["lmax"], n_theta)
+        n = f["perm"].shape[0]
+        lam_pad[:n_theta, f["base"] + f["perm"]] = lam[:, f["lmin"] ** 2 : f["lmin"] ** 2 + n]
+        entry0 = 0 if r == 0 else offF2rel // 64
+        tasks = [((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi) for mi in range(2 * f["lmax"] + 1)]
+        tasks.sort(key=lambda x: -x[1])
+        streams = [[] for _ in range(8)]
+        for gg, ks, entry in tasks:
+            st = min(streams, key=len)
+            st.extend((gg + k) | (entry << 16) | ((1 << 31) if k == ks - 1 else 0) for k in range(ks))
+        for st in streams:
+            st.extend([n_steps] * (-len(st) % DA))
+        woff = 9 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
+        ctls.append(list(woff) + [u for st in streams for u in st] + [n_steps] * DA)
+    n_ctl_r = max(len(c) for c in ctls)
+    ctl = np.array([c + [n_steps] * (n_ctl_r - len(c)) for c in ctls], dtype=np.uint32)
+    tb.fits = (
+        max(gcnt) <= 8 and max(len(t) for t in rank_tiles) <= tiles_r and 8 * smem_doubles + 4 * n_ctl_r <= MAX_SMEM
+        and n_steps < 65535 and offF2rel // 64 + 2 * ell2_max + 1 < 32768 and n_theta >= 2
+    )
+    tb.smem_bytes = 8 * smem_doubles + 4 * n_ctl_r
+    if not tb.fits:
+        return tb
+    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8 + 32)
+    _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)
+    W_rows = np.zeros((2, tiles_r, 8, n_rings))
+    tiles = np.zeros((2, tiles_r, 2), dtype=np.int32)
+    tiles[:, :, 1] = L_out + 1                                # empty tiles: no row is stored
+    for r in range(2):
+        for ti, (Mi, l0) in enumerate(rank_tiles[r]):
+            ls = np.arange(l0, min(l0 + 8, L_out + 1))
+            W_rows[r, ti, : ls.shape[0], :n_theta] = Wt[ls * (ls + 1) + Mi - L_out]
+            tiles[r, ti] = (Mi, l0)
+    wtfrag = W_rows.reshape(2, tiles_r, 8, n_chunks, 2, 4).transpose(3, 0, 1, 2, 5, 4).reshape(n_chunks, 2 * tiles_r * 64)
+    qmax = (ell1_max + ell2_max + L_out) // n_phi
+    tb.perm1 = (8 * fields[0]["perm"]).astype(np.int32)
+    tb.perm2 = (8 * fields[1]["perm"]).astype(np.int32)
+    tb.ctl = np.ascontiguousarray(ctl).view(np.int32).reshape(-1)
+    tb.n_ctl = int(n_ctl_r)
+    tb.lamfrag = np.ascontiguousarray(lamfrag)
+    tb.tiles = np.ascontiguousarray(tiles.reshape(-1, 2))
+    tb.n_tiles_arg = tiles_r
+    tb.wtfrag = np.ascontiguousarray(wtfrag)
+    tb.cfg = np.array([ell1_max, ell2_max, L_out, n_phi, n_chunks, qmax, szA, bufStride, offF2rel, smem_doubles, 16, 0, GM, maxt, 0,
+                       1, fields[1]["base"] // 4, g0[0], gcnt[0], g0[1], gcnt[1]], dtype=np.int32)
+    tb.n_out = (L_out + 1) ** 2
+    tb.nwarps, tb.gm = 16, GM
+    tb.flops_per_step = product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, 0).flops_per_step \
+        if product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, 0).fits else 0.0
     return tb

@@ -15,6 +15,8 @@
 // One persistent CTA per SM owns 4 consecutive time steps: their modes are staged once in shared memory in m-major order
 // and the CTA walks the rings in chunks of 8; the tables (fragment-ordered by the host, L2 resident) stream through
 // registers.  Algorithmic HBM traffic: 16 (n1 + n2 + n_out) bytes per time step.
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -223,6 +225,200 @@ modes_product_kernel(const ProductParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cluster variant: a pair of CTAs (thread-block cluster of 2, two SMs) owns one block of 4 time steps.  CTA r stages only
+// factor r's modes (76 KB instead of 152), so the F buffers fit twice and the stages overlap:
+//   warps 0-7  ("A/C"): theta synthesis of the own factor for ring chunk c+1, written into the F buffers of BOTH CTAs
+//                       (distributed shared memory), then the quadrature of chunk c for the own half of the M range;
+//   warps 8-15 ("B")  : m-convolution of chunk c for the own half of the M range, P_M written over F1 of that buffer.
+// One cluster barrier per chunk publishes the remote F writes and recycles the buffers, so the L2 table stream of stage A
+// flies under the FMA work of stage B.  Measured (config-4 size, 2e4 steps): 9.3 ms against 7.4 ms for the single-CTA kernel -
+// the stages do overlap, but each role now has 8 warps per SM instead of 16 and both are latency bound, which costs more than
+// the overlap returns.  Kept as a selectable shape (product_tables(..., shape=2)); not the default.
+struct ClusterParams {
+    const double2* a[2];
+    int n[2];
+    const int* perm[2];
+    double2* out;
+    int64_t n_times;
+    int n_out;
+    const unsigned* ctl;    // [2][n_ctl_r]
+    int n_ctl_r;
+    const double* lamfrag;
+    int64_t lam_stride;
+    const int2* tiles;      // [2][tiles_r]
+    int tiles_r;
+    const double* wtfrag;   // [n_chunks][2][tiles_r * 64]
+    int ell1, ell2, L_out, n_phi, n_chunks, qmax;
+    int szA, bufStride, offF2rel, smem_doubles;
+    int gbase[2];           // first global k-step of factor r (its modes sit at k-step g - gbase in shared memory)
+    int g0[2], gcnt[2];     // groups of GM consecutive M convolved by CTA r
+    int skip;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int GM, int MAXT, int DA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+modes_product_cluster_kernel(const ClusterParams p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) double sm[];
+    double* smr = cluster.map_shared_rank(sm, rank ^ 1);          // the partner CTA's shared memory
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, w8 = warp & 7;
+    const bool isA = warp < 8;
+    const int n_mout = 2 * p.L_out + 1;
+    const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
+    const int fr = (lane & 3) * 8 + (lane >> 2);
+    const double2* __restrict__ a = p.a[rank];
+    const int n = p.n[rank];
+    const int* __restrict__ perm = p.perm[rank];
+    const int gbase = p.gbase[rank];
+
+    for (int i = tid; i < p.smem_doubles / 2; i += 512) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+    unsigned* sctl = reinterpret_cast<unsigned*>(sm + p.smem_doubles);
+    for (int i = tid; i < p.n_ctl_r; i += 512) sctl[i] = __ldg(p.ctl + rank * p.n_ctl_r + i);
+    int tile_m[MAXT];
+#pragma unroll
+    for (int s = 0; s < MAXT; ++s) tile_m[s] = __ldg(p.tiles + rank * p.tiles_r + w8 + s * 8).x * 64;
+    cluster.sync();   // both CTAs are initialised before the first remote write
+
+    auto stageA = [&](int c, int bufoff) {
+        const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
+        const int s0 = (int)sctl[w8], ns = (int)sctl[w8 + 1] - s0;
+        const unsigned* ctl = sctl + s0;
+        double fq[DA];
+        unsigned cq[DA];
+#pragma unroll
+        for (int d = 0; d < DA; ++d) {
+            cq[d] = ctl[d];
+            fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+        }
+        double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};
+        for (int base = 0; base < ns; base += DA) {
+            ctl += DA;
+#pragma unroll
+            for (int d = 0; d < DA; ++d) {
+                const unsigned u = cq[d];
+                dmma_p(c0[d % 3], c1[d % 3], fq[d], sm[((int)(u & 0xffffu) - gbase) * 32 + fr]);
+                if (u >> 31) {
+                    const int off = bufoff + (int)((u >> 16) & 0x7fffu) * 64 + 2 * lane;
+                    const double2 v = make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);
+                    *reinterpret_cast<double2*>(sm + off) = v;
+                    *reinterpret_cast<double2*>(smr + off) = v;   // distributed shared memory: the partner convolves it too
+                    c0[0] = c0[1] = c0[2] = c1[0] = c1[1] = c1[2] = 0.0;
+                }
+                cq[d] = ctl[d];
+                fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+            }
+        }
+    };
+
+    for (int64_t tg = blockIdx.x >> 1; tg < n_tg; tg += gridDim.x >> 1) {
+        const int64_t t0 = tg * PRODUCT_T;
+        const int nt = (int)min((int64_t)PRODUCT_T, p.n_times - t0);
+        if (nt < PRODUCT_T) {   // ragged last block: clear the time slots that are not loaded
+            for (int i = tid; i < p.szA / 2; i += 512) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+            __syncthreads();
+        }
+        for (int e = tid; e < nt * n; e += 512) {
+            int t = e / n, idx = e - t * n;
+            cp_async16_p(sm + __ldg(perm + idx) + 2 * t, a + t0 * n + e);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+
+        double acc[MAXT][2];
+#pragma unroll
+        for (int s = 0; s < MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
+
+        if (isA && !(p.skip & 1)) stageA(0, p.szA);
+        cluster.sync();
+        for (int c = 0; c < p.n_chunks; ++c) {
+            const int bufoff = p.szA + (c & 1) * p.bufStride;
+            if (isA) {
+                if (c + 1 < p.n_chunks && !(p.skip & 1)) stageA(c + 1, p.szA + ((c + 1) & 1) * p.bufStride);
+                double2 w[MAXT];
+                {
+                    const double2* wf = reinterpret_cast<const double2*>(p.wtfrag + ((int64_t)c * 2 + rank) * p.tiles_r * 64) + lane;
+#pragma unroll
+                    for (int s = 0; s < MAXT; ++s) w[s] = __ldg(wf + (w8 + s * 8) * 32);
+                }
+                named_bar_sync(1, 512);   // P_M of this chunk is in place
+                if (!(p.skip & 4))
+#pragma unroll
+                for (int s = 0; s < MAXT; ++s) {
+                    const double* bsrc = sm + bufoff + tile_m[s] + fr;
+                    dmma_p(acc[s][0], acc[s][1], w[s].x, bsrc[0]);
+                    dmma_p(acc[s][0], acc[s][1], w[s].y, bsrc[32]);
+                }
+            } else {
+                double2 pacc[GM];
+#pragma unroll
+                for (int q = 0; q < GM; ++q) pacc[q] = make_double2(0.0, 0.0);
+                const bool mine = w8 < p.gcnt[rank];
+                const int gq = p.g0[rank] + w8;
+                if (mine && !(p.skip & 2)) {
+                    const int M0 = -p.L_out + GM * gq;
+                    const double2* f1 = reinterpret_cast<const double2*>(sm + bufoff) + lane;
+                    const double2* f2 = reinterpret_cast<const double2*>(sm + bufoff + p.offF2rel) + lane;
+                    const int l2 = p.ell2;
+                    for (int q = -p.qmax; q <= p.qmax; ++q) {
+                        const int Me = M0 + q * p.n_phi;
+                        const int lo = max(-p.ell1, Me - l2), hi = min(p.ell1, Me + GM - 1 + l2);
+                        if (lo > hi) continue;
+                        double2 y[GM + 3];
+                        const double2* f2q = f2 + (Me + l2) * 32;
+#pragma unroll
+                        for (int k = 0; k < GM - 1; ++k) y[k] = f2q[(1 + k - lo) * 32];
+                        auto block = [&](int m1b, auto tail) {
+#pragma unroll
+                            for (int k = GM - 2; k >= 0; --k) y[k + 4] = y[k];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) y[k] = f2q[(k - 3 - m1b) * 32];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                double2 x = make_double2(0.0, 0.0);
+                                if (!decltype(tail)::value || m1b + i <= hi) x = f1[(m1b + i + p.ell1) * 32];
+#pragma unroll
+                                for (int qq = 0; qq < GM; ++qq) cfma(pacc[qq], x, y[qq - i + 3]);
+                            }
+                        };
+                        int m1b = lo;
+#pragma unroll 2
+                        for (; m1b + 3 <= hi; m1b += 4) block(m1b, std::false_type{});
+                        if (m1b <= hi) block(m1b, std::true_type{});
+                    }
+                }
+                named_bar_sync(2, 256);   // every convolution warp is done reading F1 of this buffer
+                if (mine) {
+                    double2* sP = reinterpret_cast<double2*>(sm + bufoff);
+#pragma unroll
+                    for (int qq = 0; qq < GM; ++qq)
+                        if (GM * gq + qq < n_mout) sP[(GM * gq + qq) * 32 + lane] = pacc[qq];
+                }
+                named_bar_sync(1, 512);
+            }
+            cluster.sync();   // remote F writes of chunk c+1 are visible; the buffer of chunk c may be refilled
+        }
+
+        if (isA) {
+            const int t = lane & 3;
+#pragma unroll
+            for (int s = 0; s < MAXT; ++s) {
+                const int2 tl = __ldg(p.tiles + rank * p.tiles_r + w8 + s * 8);
+                const int l = tl.y + (lane >> 2), M = tl.x - p.L_out;
+                if (l <= p.L_out && t < nt) p.out[(t0 + t) * p.n_out + l * (l + 1) + M] = make_double2(acc[s][0], acc[s][1]);
+            }
+        }
+    }
+    cluster.sync();   // no CTA exits while its partner may still write into its shared memory
+}
+
 }  // namespace scrib200
 
 extern "C" size_t scrib200_modes_product_max_shared_bytes(void) { return 227u * 1024u; }
@@ -235,6 +431,64 @@ extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2
     using namespace scrib200;
     SCRIB200_REQUIRE(a1 && a2 && perm1 && perm2 && ctl && lamfrag && tiles && wtfrag && cfg && out, "modes_product: null pointer");
     SCRIB200_REQUIRE(aligned16(a1) && aligned16(a2) && aligned16(out) && aligned16(wtfrag), "modes_product: pointers must be 16-byte aligned");
+    if (cfg[15] == 1) {   // cluster variant: per-CTA-rank tables (scri_b200/_product.py:product_tables(..., shape=2))
+        ClusterParams c;
+        c.a[0] = reinterpret_cast<const double2*>(a1);
+        c.a[1] = reinterpret_cast<const double2*>(a2);
+        c.n[0] = n1;
+        c.n[1] = n2;
+        c.perm[0] = perm1;
+        c.perm[1] = perm2;
+        c.out = reinterpret_cast<double2*>(out);
+        c.n_times = n_times;
+        c.ctl = reinterpret_cast<const unsigned*>(ctl);
+        c.n_ctl_r = n_steps;
+        c.lamfrag = lamfrag;
+        c.lam_stride = lam_stride;
+        c.tiles = reinterpret_cast<const int2*>(tiles);
+        c.tiles_r = n_tiles;
+        c.wtfrag = wtfrag;
+        c.ell1 = cfg[0];
+        c.ell2 = cfg[1];
+        c.L_out = cfg[2];
+        c.n_phi = cfg[3];
+        c.n_chunks = cfg[4];
+        c.qmax = cfg[5];
+        c.szA = cfg[6];
+        c.bufStride = cfg[7];
+        c.offF2rel = cfg[8];
+        c.smem_doubles = cfg[9];
+        c.skip = cfg[14];
+        c.gbase[0] = 0;
+        c.gbase[1] = cfg[16];
+        c.g0[0] = cfg[17];
+        c.gcnt[0] = cfg[18];
+        c.g0[1] = cfg[19];
+        c.gcnt[1] = cfg[20];
+        c.n_out = (c.L_out + 1) * (c.L_out + 1);
+        SCRIB200_REQUIRE(cfg[10] == 16 && cfg[12] == 5 && cfg[13] == 12 && n_tiles == 8 * 12, "modes_product: unsupported cluster kernel shape");
+        SCRIB200_REQUIRE(c.gcnt[0] >= 0 && c.gcnt[0] <= 8 && c.gcnt[1] >= 0 && c.gcnt[1] <= 8, "modes_product: more than 8 groups of M per CTA");
+        SCRIB200_REQUIRE(wt_stride == (int64_t)2 * n_tiles * 64, "modes_product: cluster quadrature table stride");
+        SCRIB200_REQUIRE((c.szA & 1) == 0 && (c.bufStride & 1) == 0 && (c.offF2rel & 1) == 0 && (c.smem_doubles & 1) == 0, "modes_product: shared-memory offsets must be even");
+        const size_t smem = (size_t)c.smem_doubles * sizeof(double) + (size_t)n_steps * sizeof(unsigned);
+        SCRIB200_REQUIRE(smem <= scrib200_modes_product_max_shared_bytes(), "modes_product: %zu bytes of shared memory needed (limit %zu)", smem,
+                         scrib200_modes_product_max_shared_bytes());
+        if (n_times <= 0) return SCRIB200_OK;
+        const int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
+        if (n_ctas <= 0) n_ctas = 148;
+        int64_t pairs = n_ctas / 2;
+        if (pairs > n_tg) pairs = n_tg;
+        if (pairs < 1) pairs = 1;
+        auto kern = modes_product_cluster_kernel<5, 12, 9>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("modes_product: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return SCRIB200_ECUDA;
+        }
+        kern<<<(unsigned)(2 * pairs), 512, smem, (cudaStream_t)stream>>>(c);
+        SCRIB200_CHECK_LAUNCH("modes_product(cluster)");
+        return SCRIB200_OK;
+    }
     ProductParams p;
     p.a1 = reinterpret_cast<const double2*>(a1);
     p.a2 = reinterpret_cast<const double2*>(a2);

@@ -314,7 +314,7 @@ def modes_product(a, sa, a_ell_min, a_ell_max, b, sb, b_ell_min, b_ell_max, n_th
         lib.scrib200_modes_product(
             _lib.ptr(da), da.shape[1], _lib.ptr(db), db.shape[1], N, _lib.ptr(dev["perm1"]), _lib.ptr(dev["perm2"]),
             _lib.ptr(dev["ctl"]), tb.n_ctl, _lib.ptr(dev["lamfrag"]), dev["lamfrag"].shape[1],
-            _lib.ptr(dev["tiles"]), dev["tiles"].shape[0], _lib.ptr(dev["wtfrag"]), dev["wtfrag"].shape[1],
+            _lib.ptr(dev["tiles"]), tb.n_tiles_arg, _lib.ptr(dev["wtfrag"]), dev["wtfrag"].shape[1],
             tb.cfg.ctypes.data_as(ctypes.c_void_p), _lib.ptr(out), n_ctas, _lib.stream_ptr(),
         ),
         "modes_product",

@@ -33,11 +33,11 @@ def timed(fn, reps=3):
     return min(ts)
 
 
-for shape in (0, 1):
+for shape in (0, 1, 2):
     ms = timed(lambda: ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape))
-    print(f"fused N={N} shape={_product.SHAPES[shape]}: {ms:.2f} ms  {tb.flops_per_step * N / ms / 1e9:.2f} TFLOP/s algorithmic  "
+    print(f"fused N={N} shape={shape}: {ms:.2f} ms  {tb.flops_per_step * N / ms / 1e9:.2f} TFLOP/s algorithmic  "
           f"{16 * 3 * 1089 * N / ms / 1e6:.0f} GB/s algorithmic", flush=True)
-for shape in (0, 1):
+for shape in (0, 2):
     tbs = ops._product_device_tables((2, 0, L, -2, 0, L, 129, 129, 32, shape))[0]
     for skip in (1, 2, 4, 3, 5, 6, 7):
         tbs.cfg[14] = skip

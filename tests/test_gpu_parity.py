@@ -653,6 +653,8 @@ def test_fused_modes_product_vs_oracle(case):
     out = ops.modes_product(a, s1, 0, L1, b, s2, 0, L2, n, n, L1 if Lo is None else Lo)
     assert out is not None and out.shape == ref.shape
     assert rel(out, ref) < RTOL
+    for shape in (0, 1, 2):   # 16 warps x 5 M, 8 warps x 9 M, CTA pairs (thread-block cluster, distributed shared memory)
+        assert rel(ops.modes_product(a, s1, 0, L1, b, s2, 0, L2, n, n, L1 if Lo is None else Lo, shape=shape), ref) < RTOL
 
 
 def test_fused_modes_product_ell_min_and_3j_multiply():
@@ -686,7 +688,7 @@ def test_fused_modes_product_config4_size_equals_dense_path():
     from oracle import abd_ref as A   # the reference's chain itself on two steps (a few seconds of CPU at this size)
 
     assert rel(fused[:2], A.grid_multiply(a[:2], 2, b[:2], -2, working_ell_max=64, output_ell_max=32)) < RTOL
-    for shape in (0, 1):   # both instantiated kernel shapes (16 warps x 5 M, 8 warps x 9 M)
+    for shape in (0, 1, 2):   # the instantiated kernel shapes (16 warps x 5 M, 8 warps x 9 M, CTA pairs)
         assert rel(ops.modes_product(a, 2, 0, L, b, -2, 0, L, 129, 129, 32, shape=shape), dense) < RTOL
     a2 = _rand_modes(rng, N, L, 2)
     lin = ops.grid_multiply(a + 0.5 * a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)

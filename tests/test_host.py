@@ -232,9 +232,10 @@ def test_product_tables_through_a_numpy_emulation_of_the_kernel(case):
     a, b = rnd(L1, s1), rnd(L2, s2)
     ref = abd_ref.grid_multiply(a, s1, b, s2, working_ell_max=Lw, output_ell_max=Lo)
     n = 2 * (L1 + L2 if Lw is None else Lw) + 1
-    tb = _product.product_tables(s1, 0, L1, s2, 0, L2, n, n, L1 if Lo is None else Lo)
-    assert tb.fits
-    assert np.abs(emulate(tb, a, b) - ref).max() < 1e-14 * np.abs(ref).max()
+    for shape in (None, 1, 2):   # default, 8-warp and cluster (CTA pair) table sets
+        tb = _product.product_tables(s1, 0, L1, s2, 0, L2, n, n, L1 if Lo is None else Lo, shape)
+        assert tb.fits
+        assert np.abs(emulate(tb, a, b) - ref).max() < 1e-14 * np.abs(ref).max()
 
 
 def test_product_tables_config4_fit_one_cta():
