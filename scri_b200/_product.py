@@ -44,6 +44,47 @@ def _field_layout(ell_min, ell_max):
     return pos[:-1], ks, int(pos[-1]), perm, l_lo
 
 
+def _build_streams(tasks, nwarps, DA, nop):
+    """Stage A control streams.  Every warp runs three DMMA chains side by side: the k-steps of three (field, m) tasks are
+    interleaved (stream position i belongs to chain i % 3), so each accumulator holds exactly one task and a finished task is
+    one predicated store.  Tasks go longest first to the shortest of the 3 * nwarps queues; streams are padded with no-op
+    steps (an all-zero fragment) to a multiple of the kernel's fragment ring."""
+    queues = [[] for _ in range(3 * nwarps)]
+    for g0, ks, entry in sorted(tasks, key=lambda x: -x[1]):
+        q = min(queues, key=len)
+        q.extend((g0 + k) | (entry << 16) | ((1 << 31) if k == ks - 1 else 0) for k in range(ks))
+    streams = []
+    for w in range(nwarps):
+        qs = queues[w::nwarps]
+        st = [qs[j][i] if i < len(qs[j]) else nop for i in range(max(len(q) for q in qs)) for j in range(3)]
+        st.extend([nop] * (-len(st) % DA))
+        streams.append(st)
+    return streams
+
+
+def _assign_groups(groups, n_slots, GM, L_out, ell1, ell2, n_phi, qmax):
+    """Convolution groups (GM consecutive M each) -> warp slots.  A group's work is its number of (m1, m2) blocks; warp
+    slot w runs on SM sub-partition w % 4, so groups go heaviest first to the least loaded sub-partition with a free slot.
+    Returns the group of every slot (0xffffffff = idle)."""
+    def work(g):
+        M0 = -L_out + GM * g
+        tot = 0
+        for q in range(-qmax, qmax + 1):
+            Me = M0 + q * n_phi
+            lo, hi = max(-ell1, Me - ell2), min(ell1, Me + GM - 1 + ell2)
+            tot += max(0, hi - lo + 1)
+        return tot
+
+    free = {sp: [w for w in range(n_slots) if w % 4 == sp] for sp in range(4)}
+    load = {sp: 0 for sp in range(4)}
+    out = [0xFFFFFFFF] * n_slots
+    for g in sorted(groups, key=lambda g: -work(g)):
+        sp = min((sp for sp in range(4) if free[sp]), key=lambda sp: load[sp])
+        out[free[sp].pop(0)] = g
+        load[sp] += work(g)
+    return out
+
+
 @lru_cache(maxsize=16)
 def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, shape=None):
     if shape == 2:
@@ -76,8 +117,8 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
         if -(-n_mout // gm) <= nw and len(tiles) <= nw * maxt:
             chosen = sh
             break
-    tb.fits = chosen is not None and 8 * smem_doubles + 4 * (n_steps + 17 + 17 * 18) <= MAX_SMEM and n_steps < 65536 and n_theta >= 2
-    tb.smem_bytes = 8 * smem_doubles + 4 * (n_steps + 17 + 17 * 18)
+    tb.fits = chosen is not None and 8 * smem_doubles + 4 * n_steps <= MAX_SMEM and n_steps < 65535 and n_theta >= 2
+    tb.smem_bytes = 8 * smem_doubles + 4 * n_steps
     if tb.fits:
         GM, nwarps, maxt, DA = chosen
         tiles += [(0, L_out + 1)] * (nwarps * maxt - len(tiles))     # empty tiles: every warp walks `maxt` of them
@@ -96,17 +137,16 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
         entry0 = 0 if fi == 0 else (offF2 - offF1) // 64
         for mi in range(2 * f["lmax"] + 1):
             tasks.append(((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi))   # (first k-step, k-steps, F entry)
-    # per-warp streams of k-steps: tasks longest first, each to the warp with the shortest stream so far
-    tasks.sort(key=lambda x: -x[1])
-    streams = [[] for _ in range(nwarps)]
-    for g0, ks, entry in tasks:
-        st = min(streams, key=len)
-        st.extend((g0 + k) | (entry << 16) | ((1 << 31) if k == ks - 1 else 0) for k in range(ks))
     nop = n_steps                                            # an all-zero fragment appended to every chunk row
-    for st in streams:
-        st.extend([nop] * (-len(st) % DA))
-    woff = (nwarps + 1) + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
-    ctl = np.array(list(woff) + [u for st in streams for u in st] + [nop] * DA, dtype=np.uint32)
+    streams = _build_streams(tasks, nwarps, DA, nop)
+    qmax = (ell1_max + ell2_max + L_out) // n_phi
+    grp = _assign_groups(range(-(-n_mout // GM)), nwarps, GM, L_out, ell1_max, ell2_max, n_phi, qmax)
+    woff = (2 * nwarps + 1) + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
+    ctl = np.array(list(woff) + grp + [u for st in streams for u in st] + [nop] * DA, dtype=np.uint32)
+    tb.smem_bytes = 8 * smem_doubles + 4 * int(ctl.shape[0])
+    if tb.smem_bytes > MAX_SMEM:
+        tb.fits = False
+        return tb
     lam_pad = np.concatenate([lam_pad, np.zeros((n_rings, 4))], axis=1)
     lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8 + 32)
 
@@ -182,15 +222,10 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
         lam_pad[:n_theta, f["base"] + f["perm"]] = lam[:, f["lmin"] ** 2 : f["lmin"] ** 2 + n]
         entry0 = 0 if r == 0 else offF2rel // 64
         tasks = [((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi) for mi in range(2 * f["lmax"] + 1)]
-        tasks.sort(key=lambda x: -x[1])
-        streams = [[] for _ in range(8)]
-        for gg, ks, entry in tasks:
-            st = min(streams, key=len)
-            st.extend((gg + k) | (entry << 16) | ((1 << 31) if k == ks - 1 else 0) for k in range(ks))
-        for st in streams:
-            st.extend([n_steps] * (-len(st) % DA))
-        woff = 9 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
-        ctls.append(list(woff) + [u for st in streams for u in st] + [n_steps] * DA)
+        streams = _build_streams(tasks, 8, DA, n_steps)
+        grp = _assign_groups(range(g0[r], g0[r] + gcnt[r]), 8, GM, L_out, ell1_max, ell2_max, n_phi, (ell1_max + ell2_max + L_out) // n_phi)
+        woff = 17 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
+        ctls.append(list(woff) + grp + [u for st in streams for u in st] + [n_steps] * DA)
     n_ctl_r = max(len(c) for c in ctls)
     ctl = np.array([c + [n_steps] * (n_ctl_r - len(c)) for c in ctls], dtype=np.uint32)
     tb.fits = (

@@ -71,7 +71,6 @@ modes_product_kernel(const ProductParams p) {
     double2* sF1 = reinterpret_cast<double2*>(sm + p.offF1);
     const double2* sF2 = reinterpret_cast<const double2*>(sm + p.offF2);
     const int n_mout = 2 * p.L_out + 1;
-    const int n_groups = (n_mout + GM - 1) / GM;
     const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
     const int fr = (lane & 3) * 8 + (lane >> 2);   // B fragment of an [k = 4 rows][8 columns] block stored 8 doubles per row
 
@@ -120,17 +119,16 @@ modes_product_kernel(const ProductParams p) {
                     cq[d] = ctl[d];
                     fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
                 }
-                double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};   // three short DMMA chains per task
+                double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};   // three tasks side by side: stream position i feeds chain i % 3
                 for (int base = 0; base < n; base += DA) {
                     ctl += DA;
 #pragma unroll
                     for (int d = 0; d < DA; ++d) {   // branch-free: the scheduler batches the shared-memory operand loads
                         const unsigned u = cq[d];
                         dmma_p(c0[d % 3], c1[d % 3], fq[d], sm[(u & 0xffffu) * 32 + fr]);
-                        if (u >> 31) {   // F_m[item = ring*4 + t] of this (field, m) is complete
-                            *reinterpret_cast<double2*>(sm + p.offF1 + ((u >> 16) & 0x7fffu) * 64 + 2 * lane) =
-                                make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);
-                            c0[0] = c0[1] = c0[2] = c1[0] = c1[1] = c1[2] = 0.0;
+                        if (u >> 31) {   // F_m[item = ring*4 + t] of this chain's (field, m) is complete
+                            *reinterpret_cast<double2*>(sm + p.offF1 + ((u >> 16) & 0x7fffu) * 64 + 2 * lane) = make_double2(c0[d % 3], c1[d % 3]);
+                            c0[d % 3] = c1[d % 3] = 0.0;
                         }
                         cq[d] = ctl[d];   // next turn of the ring (past the end of the stream: harmless in-range loads)
                         fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
@@ -143,8 +141,9 @@ modes_product_kernel(const ProductParams p) {
             double2 pacc[GM];
 #pragma unroll
             for (int q = 0; q < GM; ++q) pacc[q] = make_double2(0.0, 0.0);
-            if (warp < n_groups && !(p.skip & 2)) {
-                const int M0 = -p.L_out + GM * warp;
+            const int gq = (int)sctl[nwarps + 1 + warp];   // my group of GM consecutive M (balanced over the SM sub-partitions by the host), -1: none
+            if (gq >= 0 && !(p.skip & 2)) {
+                const int M0 = -p.L_out + GM * gq;
                 const double2* f1 = sF1 + lane;
                 const double2* f2 = sF2 + lane;
                 const int l2 = p.ell2;
@@ -184,10 +183,10 @@ modes_product_kernel(const ProductParams p) {
                 for (int s = 0; s < MAXT; ++s) w[s] = __ldg(wf + (warp + s * nwarps) * 32);
             }
             __syncthreads();
-            if (warp < n_groups) {
+            if (gq >= 0) {
 #pragma unroll
                 for (int qq = 0; qq < GM; ++qq)
-                    if (GM * warp + qq < n_mout) sF1[(GM * warp + qq) * 32 + lane] = pacc[qq];
+                    if (GM * gq + qq < n_mout) sF1[(GM * gq + qq) * 32 + lane] = pacc[qq];
             }
             __syncthreads();
 
@@ -306,10 +305,10 @@ modes_product_cluster_kernel(const ClusterParams p) {
                 dmma_p(c0[d % 3], c1[d % 3], fq[d], sm[((int)(u & 0xffffu) - gbase) * 32 + fr]);
                 if (u >> 31) {
                     const int off = bufoff + (int)((u >> 16) & 0x7fffu) * 64 + 2 * lane;
-                    const double2 v = make_double2(c0[0] + c0[1] + c0[2], c1[0] + c1[1] + c1[2]);
+                    const double2 v = make_double2(c0[d % 3], c1[d % 3]);
                     *reinterpret_cast<double2*>(sm + off) = v;
                     *reinterpret_cast<double2*>(smr + off) = v;   // distributed shared memory: the partner convolves it too
-                    c0[0] = c0[1] = c0[2] = c1[0] = c1[1] = c1[2] = 0.0;
+                    c0[d % 3] = c1[d % 3] = 0.0;
                 }
                 cq[d] = ctl[d];
                 fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
@@ -360,8 +359,8 @@ modes_product_cluster_kernel(const ClusterParams p) {
                 double2 pacc[GM];
 #pragma unroll
                 for (int q = 0; q < GM; ++q) pacc[q] = make_double2(0.0, 0.0);
-                const bool mine = w8 < p.gcnt[rank];
-                const int gq = p.g0[rank] + w8;
+                const int gq = (int)sctl[9 + w8];   // my group of GM consecutive M, -1: none
+                const bool mine = gq >= 0;
                 if (mine && !(p.skip & 2)) {
                     const int M0 = -p.L_out + GM * gq;
                     const double2* f1 = reinterpret_cast<const double2*>(sm + bufoff) + lane;

@@ -32,17 +32,18 @@ def emulate_cluster(tb, a1, a2):
             buf = np.zeros(bufStride)
             for r in range(2):
                 woff = ctl[r, :9]
+                assert sorted(int(x) for x in ctl[r, 9:17] if x != 0xFFFFFFFF) == list(range(g0[r], g0[r] + gcnt[r]))
                 for wp in range(8):
-                    C = np.zeros((8, 8))
-                    for u in ctl[r, woff[wp] : woff[wp + 1]]:
+                    C = np.zeros((3, 8, 8))                  # three chains: stream position i feeds chain i % 3
+                    for i, u in enumerate(ctl[r, woff[wp] : woff[wp + 1]]):
                         g = int(u) & 0xFFFF
                         A = tb.lamfrag[c, 32 * g : 32 * g + 32].reshape(8, 4)
                         B = sA[r][32 * (g - gbase[r]) : 32 * (g - gbase[r]) + 32].reshape(4, 8)
-                        C += A @ B
+                        C[i % 3] += A @ B
                         if int(u) >> 31:
                             w = 64 * ((int(u) >> 16) & 0x7FFF)
-                            buf[w : w + 64] = C.reshape(64)
-                            C = np.zeros((8, 8))
+                            buf[w : w + 64] = C[i % 3].reshape(64)
+                            C[i % 3] = 0.0
             F1 = buf[: 64 * (2 * ell1 + 1)].reshape(-1, 32, 2)
             F1 = F1[..., 0] + 1j * F1[..., 1]
             F2 = buf[offF2rel : offF2rel + 64 * (2 * ell2 + 1)].reshape(-1, 32, 2)
@@ -101,17 +102,18 @@ def emulate(tb, a1, a2):
         for c in range(n_chunks):
             ctl = tb.ctl.view(np.uint32)
             woff = ctl[: nwarps + 1]
+            assert sorted(int(x) for x in ctl[nwarps + 1 : 2 * nwarps + 1] if x != 0xFFFFFFFF) == list(range(-(-(2 * L_out + 1) // GM)))
             for wp in range(nwarps):
-                C = np.zeros((8, 8))
-                for u in ctl[woff[wp] : woff[wp + 1]]:
+                C = np.zeros((3, 8, 8))                      # three chains: stream position i feeds chain i % 3
+                for i, u in enumerate(ctl[woff[wp] : woff[wp + 1]]):
                     g = int(u) & 0xFFFF
                     A = tb.lamfrag[c, 32 * g : 32 * g + 32].reshape(8, 4)
                     B = sm[32 * g : 32 * g + 32].reshape(4, 8)
-                    C += A @ B
+                    C[i % 3] += A @ B
                     if int(u) >> 31:
                         w = offF1 + 64 * ((int(u) >> 16) & 0x7FFF)
-                        sm[w : w + 64] = C.reshape(64)
-                        C = np.zeros((8, 8))
+                        sm[w : w + 64] = C[i % 3].reshape(64)
+                        C[i % 3] = 0.0
             F1 = sm[offF1 : offF1 + 64 * (2 * ell1 + 1)].reshape(-1, 32, 2)
             F1 = F1[..., 0] + 1j * F1[..., 1]
             F2 = sm[offF2 : offF2 + 64 * (2 * ell2 + 1)].reshape(-1, 32, 2)
