@@ -225,6 +225,16 @@ int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, i
                            const int* tiles, int n_tiles, const double* wtfrag, int64_t wt_stride, const int* cfg,
                            double* out, int n_ctas, void* stream);
 
+/* Separable synthesis on spinsfast's regular grid (theta_j = pi j/(n_theta-1), phi_k = 2 pi k/n_phi), theta stage:
+ * out[t, j, m + l_max] = sum_l sY_lm(theta_j, 0) modes[t, (l, m)] - the Wigner-d contraction over l with time as the batch
+ * dimension (FP64 DMMA).  The phi stage is scrib200_swsh_synthesize over the rows (t, j) with the packed table
+ * e^{i m phi_k}: together they replace spinsfast.salm2map(salm, s, lmax, Ntheta, Nphi) (scri/modes_time_series.py:177-182)
+ * at ~(l_max+1)/2 times fewer flops than the dense synthesis.
+ *   modes [n_times, n_modes]; out [n_times, n_theta, 2 l_max + 1]; perm / ctl / lamfrag / cfg (HOST int[5] = n_theta, 2 l_max+1,
+ *   ring chunks, mode-tile doubles, shared-memory doubles) from scri_b200/_product.py:theta_tables. */
+int scrib200_theta_synth(const double* modes, int n_modes, int64_t n_times, const int* perm, const int* ctl, int n_ctl,
+                         const double* lamfrag, int64_t lam_stride, const int* cfg, double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill
  * chunk i+1 while the copy engine drains chunk i).  On return all of `src_host` has been read; the DMAs are ordered

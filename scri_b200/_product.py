@@ -262,3 +262,39 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
     tb.flops_per_step = product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, 0).flops_per_step \
         if product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_phi, L_out, 0).fits else 0.0
     return tb
+
+
+THETA_FSTRIDE, THETA_DA, THETA_MAX_SMEM = 66, 9, 113 * 1024   # csrc/product.cu: theta_synth_kernel<9>
+
+
+@lru_cache(maxsize=16)
+def theta_tables(s, ell_min, ell_max, n_theta):
+    """Tables of scrib200_theta_synth (the theta stage of the separable salm2map): the single-field subset of the product
+    tables - m-major mode permutation, lambda fragments per ring chunk, the eight warps' control streams."""
+    tb = ProductTables()
+    DA = THETA_DA
+    n_chunks = (n_theta + 7) // 8
+    n_rings = 8 * n_chunks
+    pos, ks, PA, perm, l_lo = _field_layout(ell_min, ell_max)
+    nm = 2 * ell_max + 1
+    n_steps = PA // 4
+    szA = 8 * PA
+    smem_doubles = szA + nm * THETA_FSTRIDE
+    tasks = [(int(pos[mi]) // 4, int(ks[mi]), mi) for mi in range(nm)]
+    streams = _build_streams(tasks, 8, DA, n_steps)
+    woff = 9 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
+    ctl = np.array(list(woff) + [u for st in streams for u in st] + [n_steps] * DA, dtype=np.uint32)
+    tb.smem_bytes = 8 * smem_doubles + 4 * int(ctl.shape[0])
+    tb.fits = tb.smem_bytes <= THETA_MAX_SMEM and n_steps < 65535 and n_theta >= 2
+    if not tb.fits:
+        return tb
+    lam = _lambda(s, ell_max, n_theta)
+    lam_pad = np.zeros((n_rings, PA + 4))
+    lam_pad[:n_theta, perm] = lam[:, ell_min**2 :]
+    tb.lamfrag = np.ascontiguousarray(lam_pad.reshape(n_chunks, 8, PA // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA * 8 + 32))
+    tb.perm = (8 * perm).astype(np.int32)
+    tb.ctl = ctl.view(np.int32)
+    tb.n_ctl = int(ctl.shape[0])
+    tb.cfg = np.array([n_theta, nm, n_chunks, szA, smem_doubles], dtype=np.int32)
+    tb.nm = nm
+    return tb

@@ -226,6 +226,98 @@ modes_product_kernel(const ProductParams p) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Separable synthesis on spinsfast's regular grid, theta stage: F_m(theta_j) = sum_l lambda_lm(theta_j) a_lm for every ring
+// j and every m - stage (A) of the product kernel for one field, written to HBM as [time][ring][m] complex.  The phi stage
+// f(theta_j, phi_k) = sum_m F_m(theta_j) e^{i m phi_k} is then an ordinary real GEMM over rows (time, ring)
+// (scrib200_swsh_synthesize with the DFT table as its operand).  Replaces spinsfast.salm2map (scri/modes_time_series.py:177-182,
+// scri/asymptotic_bondi_data/transformations.py) at 8 n_theta ((l_max+1)^2 / 2 + n_phi (2 l_max + 1)) flops per step
+// instead of the dense 8 n_theta n_phi (l_max+1)^2.
+struct ThetaParams {
+    const double2* a;
+    int n;
+    const int* perm;
+    const unsigned* ctl;
+    int n_ctl;
+    const double* lamfrag;
+    int64_t lam_stride;
+    double2* out;           // [n_times, n_theta, nm]
+    int64_t n_times;
+    int n_theta, nm, n_chunks, szA, smem_doubles;
+};
+
+constexpr int THETA_FSTRIDE = 66;   // doubles per F_m entry (32 items x (re, im) + 2): the transposed read below is conflict free
+
+template <int DA>
+__global__ void __launch_bounds__(256, 2)
+theta_synth_kernel(const ThetaParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = 8;
+    const int fr = (lane & 3) * 8 + (lane >> 2);
+    const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
+    double* sF = sm + p.szA;
+    unsigned* sctl = reinterpret_cast<unsigned*>(sm + p.smem_doubles);
+    for (int i = tid; i < p.n_ctl; i += 256) sctl[i] = __ldg(p.ctl + i);
+    for (int i = tid; i < p.smem_doubles / 2; i += 256) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const int s0 = (int)sctl[warp], ns = (int)sctl[warp + 1] - s0;
+
+    for (int64_t tg = blockIdx.x; tg < n_tg; tg += gridDim.x) {
+        const int64_t t0 = tg * PRODUCT_T;
+        const int nt = (int)min((int64_t)PRODUCT_T, p.n_times - t0);
+        if (nt < PRODUCT_T) {
+            for (int i = tid; i < p.szA / 2; i += 256) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+            __syncthreads();
+        }
+        for (int e = tid; e < nt * p.n; e += 256) {
+            int t = e / p.n, idx = e - t * p.n;
+            cp_async16_p(sm + __ldg(p.perm + idx) + 2 * t, p.a + t0 * p.n + e);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        for (int c = 0; c < p.n_chunks; ++c) {
+            {
+                const double* lf = p.lamfrag + (int64_t)c * p.lam_stride + lane;
+                const unsigned* ctl = sctl + s0;
+                double fq[DA];
+                unsigned cq[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    cq[d] = ctl[d];
+                    fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+                }
+                double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};
+                for (int base = 0; base < ns; base += DA) {
+                    ctl += DA;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        const unsigned u = cq[d];
+                        dmma_p(c0[d % 3], c1[d % 3], fq[d], sm[(u & 0xffffu) * 32 + fr]);
+                        if (u >> 31) {
+                            *reinterpret_cast<double2*>(sF + ((u >> 16) & 0x7fffu) * THETA_FSTRIDE + 2 * lane) = make_double2(c0[d % 3], c1[d % 3]);
+                            c0[d % 3] = c1[d % 3] = 0.0;
+                        }
+                        cq[d] = ctl[d];
+                        fq[d] = __ldg(lf + (cq[d] & 0xffffu) * 32);
+                    }
+                }
+            }
+            __syncthreads();
+            // transposed, coalesced store: item = (ring r, step t) = r * 4 + t; lanes run over m
+            for (int item = warp; item < 32; item += NW) {
+                const int r = item >> 2, t = item & 3, ring = 8 * c + r;
+                if (ring < p.n_theta && t < nt) {
+                    double2* dst = p.out + ((t0 + t) * p.n_theta + ring) * (int64_t)p.nm;
+                    for (int m = lane; m < p.nm; m += 32) dst[m] = *reinterpret_cast<const double2*>(sF + m * THETA_FSTRIDE + 2 * item);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Cluster variant: a pair of CTAs (thread-block cluster of 2, two SMs) owns one block of 4 time steps.  CTA r stages only
 // factor r's modes (76 KB instead of 152), so the F buffers fit twice and the stages overlap:
 //   warps 0-7  ("A/C"): theta synthesis of the own factor for ring chunk c+1, written into the F buffers of BOTH CTAs
@@ -421,6 +513,45 @@ modes_product_cluster_kernel(const ClusterParams p) {
 }  // namespace scrib200
 
 extern "C" size_t scrib200_modes_product_max_shared_bytes(void) { return 227u * 1024u; }
+
+extern "C" int scrib200_theta_synth(const double* modes, int n_modes, int64_t n_times, const int* perm, const int* ctl, int n_ctl,
+                                    const double* lamfrag, int64_t lam_stride, const int* cfg, double* out, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(modes && perm && ctl && lamfrag && cfg && out, "theta_synth: null pointer");
+    SCRIB200_REQUIRE(aligned16(modes) && aligned16(out), "theta_synth: pointers must be 16-byte aligned");
+    ThetaParams p;
+    p.a = reinterpret_cast<const double2*>(modes);
+    p.n = n_modes;
+    p.perm = perm;
+    p.ctl = reinterpret_cast<const unsigned*>(ctl);
+    p.n_ctl = n_ctl;
+    p.lamfrag = lamfrag;
+    p.lam_stride = lam_stride;
+    p.out = reinterpret_cast<double2*>(out);
+    p.n_times = n_times;
+    p.n_theta = cfg[0];
+    p.nm = cfg[1];
+    p.n_chunks = cfg[2];
+    p.szA = cfg[3];
+    p.smem_doubles = cfg[4];
+    SCRIB200_REQUIRE(n_modes > 0 && n_ctl > 9 && p.n_theta > 0 && p.nm > 0 && p.n_chunks > 0 && (p.szA & 1) == 0 && (p.smem_doubles & 1) == 0,
+                     "theta_synth: bad table configuration");
+    SCRIB200_REQUIRE(p.smem_doubles >= p.szA + p.nm * THETA_FSTRIDE, "theta_synth: shared-memory layout too small for %d values of m", p.nm);
+    const size_t smem = (size_t)p.smem_doubles * sizeof(double) + (size_t)n_ctl * sizeof(unsigned);
+    SCRIB200_REQUIRE(smem <= 113u * 1024u, "theta_synth: %zu bytes of shared memory needed (limit %u, two CTAs per SM); use the dense synthesis", smem, 113u * 1024u);
+    if (n_times <= 0) return SCRIB200_OK;
+    const int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
+    const int64_t grid = n_tg < 296 ? n_tg : 296;
+    auto kern = theta_synth_kernel<9>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e != cudaSuccess) {
+        set_error("theta_synth: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return SCRIB200_ECUDA;
+    }
+    kern<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(p);
+    SCRIB200_CHECK_LAUNCH("theta_synth");
+    return SCRIB200_OK;
+}
 
 extern "C" int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, int64_t n_times,
                                       const int* perm1, const int* perm2, const int* ctl, int n_steps,

@@ -261,14 +261,62 @@ def _regular_grid_synthesis_matrix(s, ell_min, ell_max, n_theta, n_phi):
     return _synth_cache[key]
 
 
-def salm2map(salm, s, ell_max, n_theta, n_phi, ell_min=0):
+_theta_cache = {}
+
+
+def _separable_synthesis_tables(s, ell_min, ell_max, n_theta, n_phi):
+    """Device tables of the separable salm2map: theta stage (scrib200_theta_synth) and the packed phi-DFT operand
+    e^{i m phi_k} for scrib200_swsh_synthesize over the rows (time, ring).  None when the theta tables do not fit."""
+    from . import _product
+    from .plan import pack_synthesis_matrix
+
+    torch = _torch()
+    key = (s, ell_min, ell_max, n_theta, n_phi, torch.cuda.current_device())
+    if key not in _theta_cache:
+        tb = _product.theta_tables(s, ell_min, ell_max, n_theta)
+        if not tb.fits:
+            _theta_cache[key] = None
+        else:
+            nm = 2 * ell_max + 1
+            phi = 2 * np.pi * np.arange(n_phi) / n_phi
+            E = np.exp(1j * phi[:, None] * np.arange(-ell_max, ell_max + 1)[None, :])        # [n_phi, nm]
+            B, Kpad, Ncpad = pack_synthesis_matrix(E, 0, nm)
+            unit = np.zeros(Ncpad)
+            unit[: 2 * n_phi] = 1.0
+            dev = {k: torch.from_numpy(getattr(tb, k)).cuda() for k in ("perm", "ctl", "lamfrag")}
+            _theta_cache[key] = (tb, dev, torch.from_numpy(B).cuda(), Kpad, Ncpad, torch.from_numpy(unit).cuda(),
+                                 torch.zeros(Ncpad, dtype=torch.float64, device="cuda"))
+    return _theta_cache[key]
+
+
+def salm2map(salm, s, ell_max, n_theta, n_phi, ell_min=0, separable=None):
     """spinsfast.salm2map replacement, batched over time: [N, n_modes] -> [N, n_theta, n_phi] (device tensor in ->
-    device tensor out).  Dense synthesis GEMM on the FP64 tensor cores (scrib200_swsh_synthesize)."""
+    device tensor out).  From ell_max = 12 up the synthesis is separable - the Wigner-d contraction over l per ring
+    (scrib200_theta_synth, FP64 DMMA) and the phi-DFT as a GEMM over the rows (time, ring); below that, or when the theta
+    tables do not fit one CTA (ell_max beyond ~32), the dense synthesis GEMM (scrib200_swsh_synthesize) on the whole grid."""
     torch = _torch()
     lib = _lib.load()
     d = to_device(salm, np.complex128)
-    dB, Kpad, Ncpad, unit, zero = _regular_grid_synthesis_matrix(s, ell_min, ell_max, n_theta, n_phi)
     N, G = d.shape[0], n_theta * n_phi
+    sep = _separable_synthesis_tables(s, ell_min, ell_max, n_theta, n_phi) if (separable or (separable is None and ell_max >= 12)) else None
+    if separable and sep is None:
+        raise _lib.Scrib200Error("salm2map: the separable synthesis tables do not fit one CTA at this ell_max")
+    if sep is not None:
+        tb, dev, dB, Kpad, Ncpad, unit, zero = sep
+        Fm = torch.empty((N, n_theta, tb.nm), dtype=torch.complex128, device="cuda")
+        _lib.check(
+            lib.scrib200_theta_synth(_lib.ptr(d), d.shape[1], N, _lib.ptr(dev["perm"]), _lib.ptr(dev["ctl"]), tb.n_ctl, _lib.ptr(dev["lamfrag"]),
+                                     dev["lamfrag"].shape[1], tb.cfg.ctypes.data_as(ctypes.c_void_p), _lib.ptr(Fm), _lib.stream_ptr()),
+            "theta_synth",
+        )
+        F = torch.empty((N, n_theta, n_phi), dtype=torch.complex128, device="cuda")
+        _lib.check(
+            lib.scrib200_swsh_synthesize(_lib.ptr(Fm), N * n_theta, tb.nm, _lib.ptr(dB), Kpad, Ncpad, _lib.ptr(zero), _lib.ptr(unit), n_phi,
+                                         _lib.ptr(F), _lib.stream_ptr()),
+            "swsh_synthesize(phi stage)",
+        )
+        return F if is_tensor(salm) else to_host(F)
+    dB, Kpad, Ncpad, unit, zero = _regular_grid_synthesis_matrix(s, ell_min, ell_max, n_theta, n_phi)
     F = torch.empty((N, G), dtype=torch.complex128, device="cuda")
     _lib.check(
         lib.scrib200_swsh_synthesize(_lib.ptr(d), N, d.shape[1], _lib.ptr(dB), Kpad, Ncpad, _lib.ptr(zero), _lib.ptr(unit), G, _lib.ptr(F),

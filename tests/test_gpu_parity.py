@@ -693,3 +693,23 @@ def test_fused_modes_product_config4_size_equals_dense_path():
     a2 = _rand_modes(rng, N, L, 2)
     lin = ops.grid_multiply(a + 0.5 * a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)
     assert rel(lin, fused + 0.5 * ops.grid_multiply(a2, 2, 0, L, b, -2, 0, L, 129, 129, 64, output_ell_max=32)) < RTOL
+
+
+@pytest.mark.parametrize("case", [(-2, 0, 8, 17, 17, 5), (2, 2, 12, 25, 25, 9), (1, 0, 16, 40, 37, 4), (0, 0, 32, 65, 65, 6), (-1, 0, 32, 129, 129, 3)])
+def test_separable_salm2map_vs_dense_and_oracle(case):
+    """The separable synthesis on spinsfast's regular grid (scrib200_theta_synth + the phi-DFT GEMM) against the dense
+    synthesis GEMM of the same library and, at the small sizes, against the restated spinsfast.salm2map
+    (scri/modes_time_series.py:177-182): spins, ell_min > 0, rectangular and oversampled grids, ragged time counts."""
+    from oracle import spinsfast as ospf
+
+    s, lmin, L, nth, nph, N = case
+    rng = np.random.default_rng(31)
+    a = _rand_modes(rng, N, L, s, ell_min=lmin)
+    sep = ops.salm2map(a, s, L, nth, nph, ell_min=lmin, separable=True)
+    dense = ops.salm2map(a, s, L, nth, nph, ell_min=lmin, separable=False)
+    assert sep.shape == dense.shape == (N, nth, nph)
+    assert rel(sep, dense) < 1e-13
+    if L <= 16:
+        full = np.zeros((N, (L + 1) ** 2), dtype=complex)
+        full[:, lmin**2 :] = a
+        assert rel(sep, ospf.salm2map(full, s, L, nth, nph)) < 1e-13
