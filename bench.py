@@ -559,6 +559,22 @@ def run_product_workload(args):
         out = step()[:ns].cpu().numpy()
         err = float(np.abs(out - ref).max() / np.abs(ref).max())
         flops = tb.flops_per_step * (hi - lo)
+        # the other half of configs[3]: SWSH grid round trip of one l <= 32 field on its 65 x 65 grid (separable salm2map / map2salm)
+        nrt = min(hi - lo, 50_000)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ops.map2salm(ops.salm2map(a[:64], 2, L, 2 * L + 1, 2 * L + 1), 2, L, 2 * L + 1, 2 * L + 1)
+        flush.zero_()
+        e0.record()
+        grid = ops.salm2map(a[:nrt], 2, L, 2 * L + 1, 2 * L + 1)
+        e1.record()
+        back = ops.map2salm(grid, 2, L, 2 * L + 1, 2 * L + 1)
+        e2.record()
+        torch.cuda.synchronize()
+        rt_err = float((back - a[:nrt]).abs().max() / a[:nrt].abs().max())
+        round_trip = {"n_times": nrt, "grid": f"{2 * L + 1}x{2 * L + 1}", "salm2map_ms": e0.elapsed_time(e1), "map2salm_ms": e1.elapsed_time(e2),
+                      "max_rel_error": rt_err,
+                      "note": "separable: scrib200_theta_synth + phi-DFT GEMM, phi-DFT GEMM + scrib200_theta_quad; grid written to and read from HBM once"}
+        del grid, back
         line = {
             "metric": "mode-timesteps/sec through ModesTimeSeries.grid_multiply (ell_max=32)", "value": float(n) * N / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -573,6 +589,7 @@ def run_product_workload(args):
                          "note": "separable algorithm: theta synthesis + m-convolution + theta quadrature; the dense grid chain would need 70x the flops"},
             "cpu_baseline": {"value": float(n) * ns / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"first {ns} time steps through oracle.abd_ref.grid_multiply (restated spinsfast), {cpu_s:.1f} s; max rel. deviation of the GPU result {err:.1e}"},
+            "grid_round_trip": round_trip,
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)

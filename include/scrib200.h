@@ -235,6 +235,16 @@ int scrib200_modes_product(const double* a1, int n1, const double* a2, int n2, i
 int scrib200_theta_synth(const double* modes, int n_modes, int64_t n_times, const int* perm, const int* ctl, int n_ctl,
                          const double* lamfrag, int64_t lam_stride, const int* cfg, double* out, void* stream);
 
+/* Separable analysis on the regular grid, theta stage: out[t, (l, M)] = sum_j W_lM(theta_j) P[t, j, M + l_max], W = 2 pi q_j
+ * sY_lM(theta_j, 0) with the Clenshaw-Curtis weights q_j (FP64 DMMA, accumulators in registers over all rings).  P is the
+ * phi-DFT of the map, (1/n_phi) sum_k f(theta_j, phi_k) e^{-i M phi_k}, produced by scrib200_swsh_synthesize over the rows
+ * (t, j) with the packed table e^{-i M phi_k}/n_phi: together they replace spinsfast.map2salm(map, s, lmax)[ell_min^2:]
+ * (scri/waveform_grid.py:303-307, scri/modes_time_series.py:188) for grids beyond the shared-memory tile kernels.
+ *   P [n_times, n_theta, 2 l_max + 1]; out [n_times, (l_max+1)^2 - ell_min^2]; tiles [8*21, 2], wtfrag [ring chunks, 8*21*64],
+ *   cfg (HOST int[6] = n_theta, 2 l_max+1, ring chunks, n_out, ell_min^2, l_max) from scri_b200/_product.py:quad_tables. */
+int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int n_tiles, const double* wtfrag,
+                        int64_t wt_stride, const int* cfg, double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill
  * chunk i+1 while the copy engine drains chunk i).  On return all of `src_host` has been read; the DMAs are ordered

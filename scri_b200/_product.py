@@ -298,3 +298,32 @@ def theta_tables(s, ell_min, ell_max, n_theta):
     tb.cfg = np.array([n_theta, nm, n_chunks, szA, smem_doubles], dtype=np.int32)
     tb.nm = nm
     return tb
+
+
+QUAD_MAXT = 21   # csrc/product.cu: theta_quad_kernel<21>
+
+
+@lru_cache(maxsize=16)
+def quad_tables(s, ell_min, ell_max, n_theta, n_phi):
+    """Tables of scrib200_theta_quad (the theta stage of the separable map2salm): output tiles of 8 consecutive l per M
+    from max(|M|, ell_min), and the quadrature weights 2 pi q_j sY_lM(theta_j, 0) as DMMA fragments per ring chunk."""
+    tb = ProductTables()
+    L = ell_max
+    n_chunks = (n_theta + 7) // 8
+    n_rings = 8 * n_chunks
+    tiles = [(M + L, l0) for M in range(-L, L + 1) for l0 in range(max(abs(M), ell_min), L + 1, 8)]
+    n_tiles = 8 * QUAD_MAXT
+    tb.fits = len(tiles) <= n_tiles and n_theta >= 2 and (2 * L + 1) * THETA_FSTRIDE * 8 <= 100 * 1024
+    if not tb.fits:
+        return tb
+    _, Wt = _sf.analysis_tables(s, 0, L, n_theta, n_phi)
+    W_rows = np.zeros((n_tiles, 8, n_rings))
+    for ti, (Mi, l0) in enumerate(tiles):
+        ls = np.arange(l0, min(l0 + 8, L + 1))
+        W_rows[ti, : ls.shape[0], :n_theta] = Wt[ls * (ls + 1) + Mi - L]
+    tiles += [(0, L + 1)] * (n_tiles - len(tiles))
+    tb.wtfrag = np.ascontiguousarray(W_rows.reshape(n_tiles, 8, n_chunks, 2, 4).transpose(2, 0, 1, 4, 3).reshape(n_chunks, n_tiles * 64))
+    tb.tiles = np.ascontiguousarray(np.array(tiles, dtype=np.int32))
+    tb.n_out = (L + 1) ** 2 - ell_min**2
+    tb.cfg = np.array([n_theta, 2 * L + 1, n_chunks, tb.n_out, ell_min**2, L], dtype=np.int32)
+    return tb

@@ -318,6 +318,73 @@ theta_synth_kernel(const ThetaParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Separable analysis on the regular grid, theta stage: a_lM = sum_j W_lM(theta_j) P_M(theta_j) - stage (C) of the product
+// kernel with P read from HBM, where P[t, j, M] = (1/n_phi) sum_k f(theta_j, phi_k) e^{-i M phi_k} comes from the phi-DFT GEMM
+// over the rows (time, ring).  Together they replace spinsfast.map2salm (scri/waveform_grid.py:303-307,
+// scri/modes_time_series.py:188) for grids too large for the shared-memory tile kernels.
+struct QuadParams {
+    const double2* P;       // [n_times, n_theta, nm]
+    double2* out;           // [n_times, n_out]
+    int64_t n_times;
+    int n_theta, nm, n_chunks, n_out, ell_min2, L;
+    const int2* tiles;      // [8 * MAXT] (M + L, l0), padded with empty tiles
+    const double* wtfrag;   // [n_chunks, 8 * MAXT * 64]
+    int64_t wt_stride;
+};
+
+template <int MAXT>
+__global__ void __launch_bounds__(256, 2)
+theta_quad_kernel(const QuadParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = (lane & 3) * 8 + (lane >> 2);
+    const int64_t n_tg = (p.n_times + PRODUCT_T - 1) / PRODUCT_T;
+    for (int i = tid; i < p.nm * THETA_FSTRIDE / 2; i += 256) reinterpret_cast<double2*>(sm)[i] = make_double2(0.0, 0.0);
+    int tile_m[MAXT];
+#pragma unroll
+    for (int s = 0; s < MAXT; ++s) tile_m[s] = __ldg(p.tiles + warp + s * 8).x * THETA_FSTRIDE;
+    __syncthreads();
+    for (int64_t tg = blockIdx.x; tg < n_tg; tg += gridDim.x) {
+        const int64_t t0 = tg * PRODUCT_T;
+        const int nt = (int)min((int64_t)PRODUCT_T, p.n_times - t0);
+        double acc[MAXT][2];
+#pragma unroll
+        for (int s = 0; s < MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
+        for (int c = 0; c < p.n_chunks; ++c) {
+            // P of 8 rings x 4 steps, transposed into [M][item] (coalesced reads over M, conflict-free stride-33 writes)
+            for (int item = warp; item < 32; item += 8) {
+                const int r = item >> 2, t = item & 3, ring = 8 * c + r;
+                if (ring < p.n_theta && t < nt) {
+                    const double2* src = p.P + ((t0 + t) * p.n_theta + ring) * (int64_t)p.nm;
+                    for (int m = lane; m < p.nm; m += 32) *reinterpret_cast<double2*>(sm + m * THETA_FSTRIDE + 2 * item) = src[m];
+                }
+            }
+            double2 w[MAXT];
+            {
+                const double2* wf = reinterpret_cast<const double2*>(p.wtfrag + (int64_t)c * p.wt_stride) + lane;
+#pragma unroll
+                for (int s = 0; s < MAXT; ++s) w[s] = __ldg(wf + (warp + s * 8) * 32);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < MAXT; ++s) {
+                const double* bsrc = sm + tile_m[s] + fr;
+                dmma_p(acc[s][0], acc[s][1], w[s].x, bsrc[0]);
+                dmma_p(acc[s][0], acc[s][1], w[s].y, bsrc[32]);
+            }
+            __syncthreads();
+        }
+        const int t = lane & 3;
+#pragma unroll
+        for (int s = 0; s < MAXT; ++s) {
+            const int2 tl = __ldg(p.tiles + warp + s * 8);
+            const int l = tl.y + (lane >> 2), M = tl.x - p.L;
+            if (l <= p.L && t < nt) p.out[(t0 + t) * p.n_out + l * (l + 1) + M - p.ell_min2] = make_double2(acc[s][0], acc[s][1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Cluster variant: a pair of CTAs (thread-block cluster of 2, two SMs) owns one block of 4 time steps.  CTA r stages only
 // factor r's modes (76 KB instead of 152), so the F buffers fit twice and the stages overlap:
 //   warps 0-7  ("A/C"): theta synthesis of the own factor for ring chunk c+1, written into the F buffers of BOTH CTAs
@@ -513,6 +580,43 @@ modes_product_cluster_kernel(const ClusterParams p) {
 }  // namespace scrib200
 
 extern "C" size_t scrib200_modes_product_max_shared_bytes(void) { return 227u * 1024u; }
+
+extern "C" int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int n_tiles, const double* wtfrag,
+                                   int64_t wt_stride, const int* cfg, double* out, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(P && tiles && wtfrag && cfg && out, "theta_quad: null pointer");
+    SCRIB200_REQUIRE(aligned16(P) && aligned16(out) && aligned16(wtfrag), "theta_quad: pointers must be 16-byte aligned");
+    QuadParams p;
+    p.P = reinterpret_cast<const double2*>(P);
+    p.out = reinterpret_cast<double2*>(out);
+    p.n_times = n_times;
+    p.n_theta = cfg[0];
+    p.nm = cfg[1];
+    p.n_chunks = cfg[2];
+    p.n_out = cfg[3];
+    p.ell_min2 = cfg[4];
+    p.L = cfg[5];
+    p.tiles = reinterpret_cast<const int2*>(tiles);
+    p.wtfrag = wtfrag;
+    p.wt_stride = wt_stride;
+    SCRIB200_REQUIRE(n_tiles == 8 * 21 && wt_stride == (int64_t)n_tiles * 64, "theta_quad: the tile table must hold 8 x 21 tiles (l_max up to ~32)");
+    SCRIB200_REQUIRE(p.n_theta > 0 && p.nm == 2 * p.L + 1 && p.n_chunks > 0 && p.n_out > 0, "theta_quad: bad table configuration");
+    const size_t smem = (size_t)p.nm * THETA_FSTRIDE * sizeof(double);
+    if (n_times <= 0) return SCRIB200_OK;
+    const int64_t n_tg = (n_times + PRODUCT_T - 1) / PRODUCT_T;
+    const int64_t grid = n_tg < 296 ? n_tg : 296;
+    auto kern = theta_quad_kernel<21>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("theta_quad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return SCRIB200_ECUDA;
+        }
+    }
+    kern<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(p);
+    SCRIB200_CHECK_LAUNCH("theta_quad");
+    return SCRIB200_OK;
+}
 
 extern "C" int scrib200_theta_synth(const double* modes, int n_modes, int64_t n_times, const int* perm, const int* ctl, int n_ctl,
                                     const double* lamfrag, int64_t lam_stride, const int* cfg, double* out, void* stream) {

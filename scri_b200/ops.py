@@ -191,11 +191,42 @@ def rotate_modes(data, R, ell_min, ell_max):
     return data
 
 
-def map2salm(grid, s, ell_max, n_theta=None, n_phi=None, ell_min=0):
-    """spinsfast.map2salm replacement, batched over leading axes: [..., n_theta, n_phi] -> [..., n_modes]."""
+_quad_cache = {}
+
+
+def _separable_analysis_tables(s, ell_min, ell_max, n_theta, n_phi):
+    """Device tables of the separable map2salm: the packed phi-DFT operand e^{-i M phi_k}/n_phi for
+    scrib200_swsh_synthesize over the rows (time, ring), and the quadrature tiles / fragments of scrib200_theta_quad."""
+    from . import _product
+    from .plan import pack_synthesis_matrix
+
+    torch = _torch()
+    key = (s, ell_min, ell_max, n_theta, n_phi, torch.cuda.current_device())
+    if key not in _quad_cache:
+        tb = _product.quad_tables(s, ell_min, ell_max, n_theta, n_phi)
+        if not tb.fits:
+            _quad_cache[key] = None
+        else:
+            nm = 2 * ell_max + 1
+            phi = 2 * np.pi * np.arange(n_phi) / n_phi
+            E = np.exp(-1j * np.arange(-ell_max, ell_max + 1)[:, None] * phi[None, :]) / n_phi      # [nm, n_phi]
+            B, Kpad, Ncpad = pack_synthesis_matrix(E, 0, n_phi)
+            unit = np.zeros(Ncpad)
+            unit[: 2 * nm] = 1.0
+            dev = {k: torch.from_numpy(getattr(tb, k)).cuda() for k in ("tiles", "wtfrag")}
+            _quad_cache[key] = (tb, dev, torch.from_numpy(B).cuda(), Kpad, Ncpad, torch.from_numpy(unit).cuda(),
+                                torch.zeros(Ncpad, dtype=torch.float64, device="cuda"))
+    return _quad_cache[key]
+
+
+def map2salm(grid, s, ell_max, n_theta=None, n_phi=None, ell_min=0, separable=None):
+    """spinsfast.map2salm replacement, batched over leading axes: [..., n_theta, n_phi] -> [..., n_modes].  From
+    ell_max = 16 up the analysis is separable on the tensor cores - the phi-DFT as a GEMM over the rows (time, ring), then the
+    theta quadrature per M (scrib200_theta_quad); below that the shared-memory kernels of scrib200_map2salm."""
     from .plan import map2salm as _m2s
 
     torch = _torch()
+    lib = _lib.load()
     if is_tensor(grid):
         g = grid
     else:
@@ -204,6 +235,27 @@ def map2salm(grid, s, ell_max, n_theta=None, n_phi=None, ell_min=0):
         n_theta, n_phi = g.shape[-2:]
     lead = g.shape[:-2] if g.dim() >= 2 and g.shape[-2:] == (n_theta, n_phi) else g.shape[:-1]
     g2 = g.reshape(-1, n_theta * n_phi)
+    sep = _separable_analysis_tables(s, ell_min, ell_max, n_theta, n_phi) if (separable or (separable is None and ell_max >= 16)) else None
+    if separable and sep is None:
+        raise _lib.Scrib200Error("map2salm: the separable analysis tables do not fit at this ell_max")
+    if sep is not None:
+        tb, dev, dB, Kpad, Ncpad, unit, zero = sep
+        N, nm = g2.shape[0], 2 * ell_max + 1
+        g2 = g2.contiguous()
+        P = torch.empty((N, n_theta, nm), dtype=torch.complex128, device="cuda")
+        _lib.check(
+            lib.scrib200_swsh_synthesize(_lib.ptr(g2), N * n_theta, n_phi, _lib.ptr(dB), Kpad, Ncpad, _lib.ptr(zero), _lib.ptr(unit), nm,
+                                         _lib.ptr(P), _lib.stream_ptr()),
+            "swsh_synthesize(phi-DFT)",
+        )
+        out = torch.empty((N, tb.n_out), dtype=torch.complex128, device="cuda")
+        _lib.check(
+            lib.scrib200_theta_quad(_lib.ptr(P), N, _lib.ptr(dev["tiles"]), dev["tiles"].shape[0], _lib.ptr(dev["wtfrag"]), dev["wtfrag"].shape[1],
+                                    tb.cfg.ctypes.data_as(ctypes.c_void_p), _lib.ptr(out), _lib.stream_ptr()),
+            "theta_quad",
+        )
+        out = out.reshape(tuple(lead) + (-1,))
+        return out if is_tensor(grid) else to_host(out)
     E, Wt = _sf.analysis_tables(s, ell_min, ell_max, n_theta, n_phi)
     dE = torch.from_numpy(np.ascontiguousarray(E)).cuda()
     dW = torch.from_numpy(Wt).cuda()

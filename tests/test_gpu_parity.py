@@ -713,3 +713,24 @@ def test_separable_salm2map_vs_dense_and_oracle(case):
         full = np.zeros((N, (L + 1) ** 2), dtype=complex)
         full[:, lmin**2 :] = a
         assert rel(sep, ospf.salm2map(full, s, L, nth, nph)) < 1e-13
+
+
+@pytest.mark.parametrize("case", [(-2, 0, 8, 17, 17, 5), (2, 2, 12, 25, 25, 9), (1, 0, 16, 40, 37, 4), (0, 0, 32, 65, 65, 6), (-1, 1, 32, 129, 129, 3)])
+def test_separable_map2salm_vs_smem_kernels_and_oracle(case):
+    """The separable analysis (phi-DFT GEMM + scrib200_theta_quad) against the shared-memory kernels of
+    scrib200_map2salm and the restated spinsfast.map2salm (scri/waveform_grid.py:303-307), on maps that are NOT band
+    limited (white noise on the grid: the quadrature itself is compared, not a round trip) and on a round trip."""
+    from oracle import spinsfast as ospf
+
+    s, lmin, L, nth, nph, N = case
+    rng = np.random.default_rng(32)
+    f = rng.normal(size=(N, nth, nph)) + 1j * rng.normal(size=(N, nth, nph))
+    sep = ops.map2salm(f, s, L, nth, nph, ell_min=lmin, separable=True)
+    old = ops.map2salm(f, s, L, nth, nph, ell_min=lmin, separable=False)
+    assert sep.shape == old.shape == (N, (L + 1) ** 2 - lmin**2)
+    assert rel(sep, old) < 1e-13
+    if L <= 16:
+        assert rel(sep, ospf.map2salm(f, s, L)[:, lmin**2 :]) < 1e-13
+    a = _rand_modes(rng, N, L, s, ell_min=lmin)
+    back = ops.map2salm(ops.salm2map(a, s, L, nth, nph, ell_min=lmin, separable=True), s, L, nth, nph, ell_min=lmin, separable=True)
+    assert rel(back, a) < RTOL
