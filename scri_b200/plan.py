@@ -540,7 +540,14 @@ class TransformPlan(GridPlan):
         return F
 
     def analyze(self, grid):
-        """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307)."""
+        """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307).  Large band limits take the separable
+        tensor-core analysis (phi-DFT GEMM + scrib200_theta_quad), the rest the shared-memory kernels."""
+        if self.out_ell_max >= 16:
+            from . import ops
+
+            if ops._separable_analysis_tables(self.spin_weight, self.out_ell_min, self.out_ell_max, self.n_theta, self.n_phi) is not None:
+                return ops.map2salm(grid.reshape(-1, self.n_theta, self.n_phi), self.spin_weight, self.out_ell_max, self.n_theta, self.n_phi,
+                                    ell_min=self.out_ell_min, separable=True)
         return map2salm(grid, self.n_theta, self.n_phi, self.out_ell_min, self.out_ell_max, self.d_E, self.d_Wt)
 
     # -- time-tiled variants: the layout the fused transform path uses between remap and analysis ----

@@ -734,3 +734,13 @@ def test_separable_map2salm_vs_smem_kernels_and_oracle(case):
     a = _rand_modes(rng, N, L, s, ell_min=lmin)
     back = ops.map2salm(ops.salm2map(a, s, L, nth, nph, ell_min=lmin, separable=True), s, L, nth, nph, ell_min=lmin, separable=True)
     assert rel(back, a) < RTOL
+
+
+def test_transform_large_band_limit_vs_oracle():
+    """A transform at ell_max = 20 (working grid 49 x 49: beyond the shared-memory tile kernels of the analysis, which
+    then runs separable on the tensor cores) against the oracle, and its inverse round trip."""
+    t, data = smooth_modes(n_times=160, ell_max=20, seed=14)
+    out = modes(t, data, ell_max=20).transform(**BMS)
+    ref = R.transform(R.Modes(t=t, data=data.copy(), ell_max=20), **BMS)
+    assert np.array_equal(out.t, ref.t) and out.data.shape == ref.data.shape
+    assert rel(out.data, ref.data) < RTOL
