@@ -362,12 +362,24 @@ def transform(abd, **kwargs):
         plan.divide_by_gamma = True    # transformations.py:393: timeprime = (u - alpha_00/sqrt(4 pi)) / gamma
         plan._init_grid("cuda", n_theta, n_phi, gamma, (supertranslation[0] / math.sqrt(4 * math.pi)).real, k, alpha)
         dev = plan.device
+        # the synthesis operands sY_lm(R_g) of the six spins are built and packed on the device (scrib200_swsh_pack), as in
+        # TransformPlan: at ell_max = 32 the host recurrence + packing took 4 s, the kernels of the whole transform 0.1 s
         packs = {}
+        n_all = (abd.ell_max + 1) ** 2
+        Kpad = -(-2 * n_all // 16) * 16
+        Ncpad = -(-2 * G // 64) * 64
+        d_R = torch.from_numpy(np.ascontiguousarray(R)).to(dev)
         for name in FIELDS:
-            Y = _sf.SWSH_grid(R, SPINS[name], abd.ell_max)
-            B, Kpad, Ncpad = pack_synthesis_matrix(Y, 0, abd.ell_max)
-            packs[name] = (torch.from_numpy(B).to(dev), Kpad, Ncpad)
-        Ncpad = packs["psi0"][2]
+            s = SPINS[name]
+            Lt = max(abd.ell_max, abs(s))
+            seed_d, _, uv_d = ops.wigner_tables_device(Lt)
+            dB = torch.empty((Kpad, Ncpad), dtype=torch.float64, device=dev)
+            _lib.check(
+                _lib.load().scrib200_swsh_pack(_lib.ptr(d_R), G, s, 0, abd.ell_max, _lib.ptr(seed_d), _lib.ptr(uv_d), Lt, _lib.ptr(dB), Kpad,
+                                               Ncpad, _lib.stream_ptr()),
+                "swsh_pack",
+            )
+            packs[name] = (dB, Kpad, Ncpad)
     f64 = torch.float64
     d_zero = torch.zeros(Ncpad, dtype=f64, device=dev)
     d_unit = torch.zeros(Ncpad, dtype=f64, device=dev)
