@@ -100,10 +100,13 @@ class ModesTimeSeries:
     @property
     def bar(self):
         """Modes of the complex-conjugate function: bar(f)_{l,m} = (-1)^{s+m} conj(f_{l,-m}), spin weight -s."""
-        LM = self.LM
-        idx = np.array([_sf.LM_index(int(l), -int(m), self.ell_min) for l, m in LM])
-        sign = (-1.0) ** (self.spin_weight + LM[:, 1])
-        return self._like(np.conj(self.ndarray[:, idx]) * sign[None, :], spin_weight=-self.spin_weight)
+        a = self.ndarray
+        out = np.empty_like(a)
+        for ell in range(self.ell_min, self.ell_max + 1):      # m -> -m is a reversal inside each ell block
+            i0, n = ell * ell - self.ell_min**2, 2 * ell + 1
+            sign = (-1.0) ** (self.spin_weight + np.arange(-ell, ell + 1))
+            np.multiply(np.conj(a[:, i0 : i0 + n][:, ::-1]), sign[None, :], out=out[:, i0 : i0 + n])
+        return self._like(out, spin_weight=-self.spin_weight)
 
     @property
     def real(self):
