@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib, _sf, ops
 from . import _quaternion as Q
 from .constants import Inertial
-from .plan import GridPlan, _quiet_blas, boosted_rotor_grid, pack_synthesis_matrix
+from .plan import GridPlan, _quiet_blas, boosted_rotor_grid
 
 # field order of the raw storage, spin weights, and the conformal weight applied by `transform`
 FIELDS = ("psi0", "psi1", "psi2", "psi3", "psi4", "sigma")
@@ -397,10 +397,17 @@ def transform(abd, **kwargs):
     prep = plan.prepare(t_d)
     n_modes = abd.n_modes
     F = {}
-    for name in FIELDS:
-        d = ops.to_device(abd._raw_data[FIELDS.index(name)], np.complex128)
+    cur = torch.cuda.current_stream()
+    # the six fields stream in on the copy stream (staging on a helper thread) while the synthesis of the previous one runs
+    incoming = [ops.to_device_slabs(abd._raw_data[FIELDS.index(name)], np.complex128, n_slabs=1) for name in FIELDS]
+    for name, (d, slabs, fut) in zip(FIELDS, incoming):
+        slabs[-1][3].wait()
+        cur.wait_event(slabs[-1][2])
         dB, Kpad, Ncp = packs[name]
         F[name] = plan.synthesize_with(d, dB, n_modes, Kpad, Ncp, d_zero, d_unit)
+    for _, _, fut in incoming:
+        fut.result()                             # surfaces a failed copy
+    del incoming
     for name in FIELDS:     # ascending order: each ladder only reads fields of higher index, still untouched
         coefs, names = _LADDERS[name]
         if name == "sigma":
@@ -409,7 +416,9 @@ def transform(abd, **kwargs):
             plan.weyl_mix([F[n] for n in names], coefs, t_d, d_A, d_C, d_k3, None, F[name])
     uprm = prep.uprm
     n_out = uprm.shape[0]
-    raw = np.zeros((len(FIELDS), n_out, (Lout + 1) ** 2), dtype=complex)
+    # the result lands field by field in ONE pinned host block (torch's caching host allocator reuses it between calls):
+    # each D2H is a DMA at PCIe rate queued behind that field's analysis, with no second host copy
+    raw_t = torch.empty((len(FIELDS), n_out, (Lout + 1) ** 2), dtype=torch.complex128, pin_memory=True)
     tile = int(_lib.load().scrib200_map2salm_tile_size(n_theta, n_phi, 0, Lout)) if n_out > 0 else 0
     for name in FIELDS:
         s = SPINS[name]
@@ -422,6 +431,8 @@ def transform(abd, **kwargs):
             grid = plan.remap(t_d, F[name], uprm, prep)
             modes = ops.map2salm(grid, s, Lout, n_theta, n_phi, ell_min=0)
         del F[name]
-        raw[FIELDS.index(name)] = ops.to_host(modes)
+        raw_t[FIELDS.index(name)].copy_(modes, non_blocking=True)
+    cur.synchronize()
+    raw = raw_t.numpy()
     out = AsymptoticBondiData(ops.to_host(uprm), Lout, abd.multiplication_truncator, abd.frameType, raw)
     return out
