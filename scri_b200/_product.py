@@ -99,7 +99,7 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     for s, lmin, lmax in ((s1, ell1_min, ell1_max), (s2, ell2_min, ell2_max)):
         pos, ks, PA, perm, l_lo = _field_layout(lmin, lmax)
         fields.append(dict(s=s, lmin=lmin, lmax=lmax, pos=pos, ks=ks, PA=PA, perm=perm, l_lo=l_lo, base=base))
-        base += PA
+        base += PA + 4                                      # one all-zero k-step after each factor: the target of no-op steps
     PA_total = base
     szA = 8 * PA_total                                     # doubles: [pos][t = 4][re, im]
     offF1 = szA
@@ -137,7 +137,7 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
         entry0 = 0 if fi == 0 else (offF2 - offF1) // 64
         for mi in range(2 * f["lmax"] + 1):
             tasks.append(((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi))   # (first k-step, k-steps, F entry)
-    nop = n_steps                                            # an all-zero fragment appended to every chunk row
+    nop = n_steps - 1                                        # the zero k-step after the second factor: zero fragment, zero modes
     streams = _build_streams(tasks, nwarps, DA, nop)
     qmax = (ell1_max + ell2_max + L_out) // n_phi
     grp = _assign_groups(range(-(-n_mout // GM)), nwarps, GM, L_out, ell1_max, ell2_max, n_phi, qmax)
@@ -147,8 +147,7 @@ def product_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_ph
     if tb.smem_bytes > MAX_SMEM:
         tb.fits = False
         return tb
-    lam_pad = np.concatenate([lam_pad, np.zeros((n_rings, 4))], axis=1)
-    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8 + 32)
+    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8)
 
     # stage C: quadrature fragments W[(l0 + lane/4, M), ring = 8c + 4ks + lane%4], the two k-steps of a lane adjacent
     _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)       # [(L_out+1)^2, n_theta]
@@ -199,10 +198,10 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
     for s, lmin, lmax in ((s1, ell1_min, ell1_max), (s2, ell2_min, ell2_max)):
         pos, ks, PA, perm, l_lo = _field_layout(lmin, lmax)
         fields.append(dict(s=s, lmin=lmin, lmax=lmax, pos=pos, ks=ks, PA=PA, perm=perm, l_lo=l_lo, base=base))
-        base += PA
+        base += PA + 4                                      # one all-zero k-step after each factor (no-op steps point there)
     PA_total = base
     n_steps = PA_total // 4
-    szA = 8 * max(f["PA"] for f in fields)
+    szA = 8 * (max(f["PA"] for f in fields) + 4)
     nF1 = max(2 * ell1_max + 1, n_mout)
     offF2rel = 64 * nF1 + 64 * (GM + 2)
     bufStride = offF2rel + 64 * (2 * ell2_max + 1) + 64 * (GM - 1)
@@ -214,7 +213,7 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
     rank_tiles = [[tl for tl in all_tiles if (tl[0] // GM >= g0[r]) and (tl[0] // GM < g0[r] + gcnt[r])] for r in range(2)]
     tiles_r = 8 * maxt
     # control streams per rank (8 synthesis warps)
-    lam_pad = np.zeros((n_rings, PA_total + 4))
+    lam_pad = np.zeros((n_rings, PA_total))
     ctls = []
     for r, f in enumerate(fields):
         lam = _lambda(f["s"], f["lmax"], n_theta)
@@ -222,12 +221,13 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
         lam_pad[:n_theta, f["base"] + f["perm"]] = lam[:, f["lmin"] ** 2 : f["lmin"] ** 2 + n]
         entry0 = 0 if r == 0 else offF2rel // 64
         tasks = [((f["base"] + int(f["pos"][mi])) // 4, int(f["ks"][mi]), entry0 + mi) for mi in range(2 * f["lmax"] + 1)]
-        streams = _build_streams(tasks, 8, DA, n_steps)
+        nop = (f["base"] + f["PA"]) // 4                    # this factor's own zero k-step: inside the CTA's (zeroed) mode tile
+        streams = _build_streams(tasks, 8, DA, nop)
         grp = _assign_groups(range(g0[r], g0[r] + gcnt[r]), 8, GM, L_out, ell1_max, ell2_max, n_phi, (ell1_max + ell2_max + L_out) // n_phi)
         woff = 17 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
-        ctls.append(list(woff) + grp + [u for st in streams for u in st] + [n_steps] * DA)
+        ctls.append(list(woff) + grp + [u for st in streams for u in st] + [nop] * DA)
     n_ctl_r = max(len(c) for c in ctls)
-    ctl = np.array([c + [n_steps] * (n_ctl_r - len(c)) for c in ctls], dtype=np.uint32)
+    ctl = np.array([c + [c[-1]] * (n_ctl_r - len(c)) for c in ctls], dtype=np.uint32)
     tb.fits = (
         max(gcnt) <= 8 and max(len(t) for t in rank_tiles) <= tiles_r and 8 * smem_doubles + 4 * n_ctl_r <= MAX_SMEM
         and n_steps < 65535 and offF2rel // 64 + 2 * ell2_max + 1 < 32768 and n_theta >= 2
@@ -235,7 +235,7 @@ def _cluster_tables(s1, ell1_min, ell1_max, s2, ell2_min, ell2_max, n_theta, n_p
     tb.smem_bytes = 8 * smem_doubles + 4 * n_ctl_r
     if not tb.fits:
         return tb
-    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4 + 1, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8 + 32)
+    lamfrag = lam_pad.reshape(n_chunks, 8, PA_total // 4, 4).transpose(0, 2, 1, 3).reshape(n_chunks, PA_total * 8)
     _, Wt = _sf.analysis_tables(s1 + s2, 0, L_out, n_theta, n_phi)
     W_rows = np.zeros((2, tiles_r, 8, n_rings))
     tiles = np.zeros((2, tiles_r, 2), dtype=np.int32)
@@ -277,13 +277,13 @@ def theta_tables(s, ell_min, ell_max, n_theta):
     n_rings = 8 * n_chunks
     pos, ks, PA, perm, l_lo = _field_layout(ell_min, ell_max)
     nm = 2 * ell_max + 1
-    n_steps = PA // 4
-    szA = 8 * PA
+    n_steps = PA // 4 + 1                                   # + one all-zero k-step: the target of no-op steps
+    szA = 8 * (PA + 4)
     smem_doubles = szA + nm * THETA_FSTRIDE
     tasks = [(int(pos[mi]) // 4, int(ks[mi]), mi) for mi in range(nm)]
-    streams = _build_streams(tasks, 8, DA, n_steps)
+    streams = _build_streams(tasks, 8, DA, n_steps - 1)
     woff = 9 + np.concatenate([[0], np.cumsum([len(st) for st in streams])])
-    ctl = np.array(list(woff) + [u for st in streams for u in st] + [n_steps] * DA, dtype=np.uint32)
+    ctl = np.array(list(woff) + [u for st in streams for u in st] + [n_steps - 1] * DA, dtype=np.uint32)
     tb.smem_bytes = 8 * smem_doubles + 4 * int(ctl.shape[0])
     tb.fits = tb.smem_bytes <= THETA_MAX_SMEM and n_steps < 65535 and n_theta >= 2
     if not tb.fits:
