@@ -12,6 +12,8 @@ The path shards two ways:
 
 The host logic here is backend-agnostic: NCCL on GPUs, gloo in the CPU tests.
 """
+import math
+
 import numpy as np
 
 HALO = 64
@@ -143,3 +145,79 @@ def sharded_fluxes(t_local, data_local, ell_min, ell_max, halo=HALO, group=None)
 def transform_batch(plan, t, data_batch):
     """Run one TransformPlan over a local shard `data_batch[B_local, N, n]` (device tensors): (u', modes'[B_local, N', n'])."""
     return plan.run_batch(t, data_batch)
+
+
+SPLINE_DECAY_ROWS = 40   # rows after which a not-a-knot spline has forgotten its end conditions (0.268^40 ~ 1e-23)
+
+
+def transform_halo(plan, t_first, t_last, dt_min):
+    """Input samples a rank must borrow from each neighbour to transform its block of [t_first, t_last] alone.
+
+    The output of input sample i sits at u'_i = (t_i - dt)/gamma; grid point g evaluates its spline there, i.e. at the
+    input time t* with k_g (t* - alpha_g) = u'_i.  With 1/(gamma k_g) = 1 - v.r_g the distance is
+    |t* - t_i| = |alpha_g - dt (1 - v.r_g) - t_i v.r_g|: bounded for supertranslations and rotations, growing like beta |t|
+    under a boost.  Linear in t_i, so the block's ends give the maximum."""
+    k = np.asarray(plan.kconformal, dtype=float)
+    alpha = np.asarray(plan.alpha, dtype=float)
+    one_minus_vr = 1.0 / (plan.gamma * k)
+    drift = 0.0
+    for ti in (t_first, t_last):
+        drift = max(drift, float(np.abs(alpha - plan.time_translation * one_minus_vr - ti * (1.0 - one_minus_vr)).max()))
+    return int(math.ceil(drift / dt_min)) + SPLINE_DECAY_ROWS + 2
+
+
+def sharded_transform(plan, t_local, data_local, halo=None, group=None):
+    """WaveformModes.transform (scri/waveform_grid.py:331-630) of ONE long series sharded by TIME: every rank holds a
+    contiguous block of (t, modes), ranks in time order.  Each rank borrows `halo` input samples from its neighbours
+    (point-to-point: the only data-path communication besides the few scalars below), synthesizes the extended block,
+    builds the splines of the extended block and evaluates them at the output times of the samples it owns, masked by the
+    GLOBAL retained range; the analysis is pointwise in time.  Returns (u'_local, modes'_local); `gather_batch` assembles
+    the full series where wanted.  `halo=None` sizes the halo from the transformation (`transform_halo`); a boost needs
+    beta |t| / dt extra samples, and when that exceeds a neighbour's block the call refuses (shard by waveform instead)."""
+    import torch
+    import torch.distributed as dist
+
+    if plan.mix:
+        raise NotImplementedError("sharded_transform does not cover psi0..psi3 (their mixing needs the companion fields)")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = t_local.device
+    n_loc = int(t_local.shape[0])
+    step = (t_local[1:] - t_local[:-1]).min() if n_loc > 1 else torch.tensor(float("inf"), dtype=torch.float64, device=dev)
+    mine = torch.stack([t_local[0], t_local[-1], step, torch.tensor(float(n_loc), dtype=torch.float64, device=dev)])
+    wire = mine.cpu() if dist.get_backend(group) == "gloo" else mine
+    ends = [torch.empty_like(wire) for _ in range(world)]
+    dist.all_gather(ends, wire, group=group)
+    ends = torch.stack(ends).cpu().numpy()                                   # [world, 4]: first, last, min step, samples
+    t0, tN = float(ends[0, 0]), float(ends[-1, 1])
+    gaps = ends[1:, 0] - ends[:-1, 1]
+    dt_min = float(min(ends[:, 2].min(), gaps.min() if gaps.size else np.inf))
+    if halo is None:
+        halo = max(transform_halo(plan, float(ends[r, 0]), float(ends[r, 1]), dt_min) for r in range(world))
+    if world > 1 and halo > int(ends[:, 3].min()):
+        raise ValueError(
+            f"time-sharded transform needs a halo of {halo} input samples but the smallest block has {int(ends[:, 3].min())}: "
+            "the boost moves the input window of late output times too far; shard by waveform index instead"
+        )
+    prev_d, next_d = exchange_halos(data_local, halo, group)
+    prev_t, next_t = exchange_halos(t_local, halo, group)
+    t_ext = torch.cat([x for x in (prev_t, t_local, next_t) if x is not None])
+    d_ext = torch.cat([x for x in (prev_d, data_local, next_d) if x is not None])
+    F = plan.synthesize(d_ext)
+    prep = plan.prepare(t_ext)                                              # spline factor table of the extended block
+    # output times of the samples this rank owns, masked by the global retained range (waveform_grid.py:564-568)
+    if plan.divide_by_gamma:
+        u_all = (t_local - plan.time_translation) / plan.gamma
+    else:
+        u_all = (1 / plan.gamma) * (t_local - plan.time_translation)
+    u_min = (plan.d_k * (t0 - plan.d_alpha)).max()
+    u_max = (plan.d_k * (tN - plan.d_alpha)).min()
+    uprm = u_all[(u_all >= u_min) & (u_all <= u_max)].contiguous()
+    n_out = int(uprm.shape[0])
+    if n_out == 0:
+        return uprm, torch.empty((0, plan.n_modes_out), dtype=torch.complex128, device=dev)
+    torch.cuda.current_stream().wait_event(prep.done)
+    if plan.tile:
+        modes = plan.analyze_tiled(plan._remap(t_ext, F, uprm, prep, plan.tile), n_out)
+    else:
+        modes = plan.analyze(plan.remap(t_ext, F, uprm, prep))
+    return uprm, modes

@@ -744,3 +744,67 @@ def test_transform_large_band_limit_vs_oracle():
     ref = R.transform(R.Modes(t=t, data=data.copy(), ell_max=20), **BMS)
     assert np.array_equal(out.t, ref.t) and out.data.shape == ref.data.shape
     assert rel(out.data, ref.data) < RTOL
+
+
+def _sharded_transform_worker(rank, world, port, q, kw, n_times, t1):
+    import torch
+    import torch.distributed as dist
+
+    from scri_b200 import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # one GPU here: gloo carries the halos (NCCL on a real node)
+    try:
+        t, data = smooth_modes(n_times=n_times, t0=0.0, t1=t1, seed=29)
+        lo, hi = parallel.shard_range(t.size, rank, world)
+        td, dd = ops.to_device(t[lo:hi].copy()), ops.to_device(data[lo:hi].copy())
+        plan = P.TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **kw)
+        try:
+            u, m = parallel.sharded_transform(plan, td, dd)
+            q.put((rank, u.cpu().numpy(), m.cpu().numpy(), None))
+        except ValueError as e:
+            q.put((rank, None, None, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_sharded_transform(kw, n_times, t1, world=2):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s_ = socket.socket()
+    s_.bind(("127.0.0.1", 0))
+    port = s_.getsockname()[1]
+    s_.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_transform_worker, args=(r, world, port, q, kw, n_times, t1)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    return res
+
+
+def test_time_sharded_transform_world2():
+    """one series sharded by time over two ranks - halo exchange of the input modes, local synthesis /
+    splines / analysis, outputs owned by the rank that owns the input sample - against the single-process transform:
+    output times bit-exact, modes to 1e-12.  A supertranslation + rotation needs a fixed halo; a boost over a short series
+    still fits; a boost that moves the input window by more than a block is refused with the reason."""
+    for kw, n_times, t1 in (
+        (dict(supertranslation=real_supertranslation(4), frame_rotation=[1.0, 2.0, 3.0, 4.0]), 6000, 600.0),
+        (dict(supertranslation=real_supertranslation(4), frame_rotation=[1.0, 2.0, 3.0, 4.0], boost_velocity=[0.01, 0.02, 0.03]), 4000, 100.0),
+    ):
+        res = _run_sharded_transform(kw, n_times, t1)
+        assert all(r[3] is None for r in res), res[0][3]
+        t, data = smooth_modes(n_times=n_times, t0=0.0, t1=t1, seed=29)
+        ref = modes(t, data).transform(**kw)
+        u = np.concatenate([r[1] for r in res])
+        m = np.concatenate([r[2] for r in res])
+        assert np.array_equal(u, ref.t)
+        assert rel(m, ref.data) < RTOL
+    res = _run_sharded_transform(dict(boost_velocity=[0.3, 0.4, 0.5]), 4000, 400.0)    # drift ~ 0.7 N samples: more than a block
+    assert all(r[3] is not None and "shard by waveform" in r[3] for r in res)

@@ -86,3 +86,26 @@ def test_gloo_world2_halo_exchange_and_gather():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_transform_halo_grows_with_boost_and_time():
+    """Halo of the time-sharded transform: spline decay + the distance between an output time and the input samples the
+    grid points need for it - constant for supertranslations, beta |t| / dt under a boost."""
+    from types import SimpleNamespace
+
+    from scri_b200 import parallel
+
+    G = 50
+    rng = np.random.default_rng(3)
+    alpha = rng.uniform(-0.3, 0.3, G)
+    still = SimpleNamespace(kconformal=np.ones(G), alpha=alpha, gamma=1.0, time_translation=0.1)
+    h0 = parallel.transform_halo(still, 0.0, 1000.0, 0.1)
+    assert h0 == int(np.ceil(np.abs(alpha - 0.1).max() / 0.1)) + parallel.SPLINE_DECAY_ROWS + 2
+    assert parallel.transform_halo(still, 5000.0, 9000.0, 0.1) == h0                  # no drift without a boost
+    beta = 0.03
+    vr = rng.uniform(-beta, beta, G)
+    gamma = 1 / np.sqrt(1 - beta**2)
+    boosted = SimpleNamespace(kconformal=1 / (gamma * (1 - vr)), alpha=alpha, gamma=gamma, time_translation=0.1)
+    h1 = parallel.transform_halo(boosted, 0.0, 1000.0, 0.1)
+    h2 = parallel.transform_halo(boosted, 0.0, 2000.0, 0.1)
+    assert h1 > h0 + 0.9 * np.abs(vr).max() * 1000.0 / 0.1 - 10 and h2 > 1.9 * (h1 - h0)
