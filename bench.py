@@ -597,6 +597,68 @@ def run_product_workload(args):
         dist.destroy_process_group()
 
 
+def run_timeshard_workload(args):
+    """BASELINE configs[1] as ONE series sharded by TIME over the ranks (strong scaling): parallel.sharded_transform -
+    point-to-point halo exchange of the input modes (NCCL), local synthesis / splines / analysis, no other collective.
+    Optional workload, not the default bench line; device-resident."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import scri_b200 as sb
+    from scri_b200 import _lib, ops, parallel
+    from scri_b200.plan import TransformPlan
+
+    kw = transformation_kwargs()
+    N = args.n_times
+    w = make_workload(N)
+    lo, hi = parallel.shard_range(N, rank, world)
+    t_d = ops.to_device(np.ascontiguousarray(w.t[lo:hi]))
+    a_d = ops.to_device(np.ascontiguousarray(w.data[lo:hi]))
+    plan = TransformPlan(w.ell_min, w.ell_max, w.dataType, r_is_scaled_out=w.r_is_scaled_out, **kw)
+    halo = parallel.transform_halo(plan, float(w.t[lo]), float(w.t[hi - 1]), float(np.diff(w.t).min()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        u, m = parallel.sharded_transform(plan, t_d, a_d)
+    barrier()
+    l0 = _lib.launch_count()
+    total = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        u, m = parallel.sharded_transform(plan, t_d, a_d)
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    ms = total / args.steps
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    n_out = torch.tensor([u.shape[0]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_out)
+    if rank == 0:
+        emit({
+            "metric": METRIC, "value": float(w.n_modes) * N / (float(tms[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": float(tms[0]), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[1] as one series of {N} steps sharded by time: halo of {halo} input samples per boundary exchanged point-to-point, no other collective",
+                       "n_times": N, "n_out": int(n_out[0]), "n_modes": int(w.n_modes), "halo": halo, "l2": "explicit 256 MiB L2 flush between timed iterations"},
+            "e2e": None, "gpu_launches": int(launches), "clocks": None,
+        })
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -606,7 +668,7 @@ def main():
     ap.add_argument("--n-times", type=int, default=100_000)
     ap.add_argument("--cpu-sample", type=int, default=4000, help="time steps in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=10_000, help="time steps per step of --impl reference")
-    ap.add_argument("--workload", default="transform", choices=["transform", "batch", "product"],
+    ap.add_argument("--workload", default="transform", choices=["transform", "batch", "product", "timeshard"],
                     help="transform = configs[1] (the bench line); batch = configs[2]; product = configs[3] (ell<=32 mode products)")
     ap.add_argument("--batch", type=int, default=4096, help="waveforms in the batch workload (all ranks together)")
     args = ap.parse_args()
@@ -619,6 +681,8 @@ def main():
         run_batch_workload(args)
     elif args.workload == "product":
         run_product_workload(args)
+    elif args.workload == "timeshard":
+        run_timeshard_workload(args)
     else:
         run_ours(args)
 
