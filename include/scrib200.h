@@ -252,6 +252,15 @@ int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int 
  */
 int scrib200_h2d(void* dst_device, const void* src_host, size_t nbytes, void* stream);
 
+/* HOST function (no device work, all pointers are host memory): rotor series with dR/dt = omega(t) R / 2, R(t[0]) = R0, on
+ * the samples t - replaces quaternion.integrate_angular_velocity((t, omega), t0, t1, R0, tolerance) as
+ * scri/mode_calculations.py:467 calls it.  Dormand-Prince 8(5,3) with the standard step controller (error norm < 1 against
+ * atol + rtol |y|), steps clipped to the samples; omega is the cubic spline whose piecewise-polynomial coefficients
+ * coef[4][n-1][3] (scipy PPoly layout) the caller provides.  out [n, 4] (w, x, y, z), not normalised; n_rhs (may be NULL)
+ * receives the number of right-hand-side evaluations. */
+int scrib200_integrate_angular_velocity(const double* t, int64_t n, const double* coef, const double* R0, double atol,
+                                        double rtol, double* out, int64_t* n_rhs);
+
 #ifdef __cplusplus
 }
 #endif

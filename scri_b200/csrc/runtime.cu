@@ -190,3 +190,114 @@ extern "C" int scrib200_h2d(void* dst_device, const void* src_host, size_t nbyte
     }
     return SCRIB200_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host-side rotor integration dR/dt = omega(t) R / 2 (quaternion.integrate_angular_velocity as scri/mode_calculations.py:467
+// calls it).  The problem is one serial ODE over the whole series - nothing for a GPU - but the reference's route (scipy's
+// DOP853 with a Python right-hand side: ~60 000 interpreter round trips for 2e4 samples, 1.3 s) is what dominates
+// to_corotating_frame once the mode kernels run on the device, so the integrator lives here as native code: Dormand-Prince
+// 8(5,3) with the standard step controller, steps clipped to the sample times (the output needs no dense interpolant),
+// omega = the not-a-knot cubic spline through the samples, evaluated from its piecewise-polynomial coefficients.
+namespace scrib200 {
+#include "dop853_tables.inc"
+
+struct RotorRhs {
+    const double* t;      // [n]
+    const double* coef;   // [4][n-1][3]: scipy PPoly layout, coef[k][i][c] multiplies (x - t_i)^(3-k)
+    int64_t n;
+    inline void operator()(int64_t i, double x, const double* y, double* f) const {
+        const double dx = x - t[i];
+        const int64_t s = (n - 1) * 3;
+        const double* c0 = coef + i * 3;
+        double w[3];
+        for (int c = 0; c < 3; ++c) w[c] = ((c0[c] * dx + c0[s + c]) * dx + c0[2 * s + c]) * dx + c0[3 * s + c];
+        // (0, w) * y / 2
+        f[0] = 0.5 * (-w[0] * y[1] - w[1] * y[2] - w[2] * y[3]);
+        f[1] = 0.5 * (w[0] * y[0] + w[1] * y[3] - w[2] * y[2]);
+        f[2] = 0.5 * (-w[0] * y[3] + w[1] * y[0] + w[2] * y[1]);
+        f[3] = 0.5 * (w[0] * y[2] - w[1] * y[1] + w[2] * y[0]);
+    }
+};
+
+}  // namespace scrib200
+
+extern "C" int scrib200_integrate_angular_velocity(const double* t, int64_t n, const double* coef, const double* R0, double atol,
+                                                   double rtol, double* out, int64_t* n_rhs) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(t && coef && R0 && out, "integrate_angular_velocity: null pointer");
+    SCRIB200_REQUIRE(n >= 2, "integrate_angular_velocity: needs at least two samples; got %lld", (long long)n);
+    SCRIB200_REQUIRE(atol > 0.0 || rtol > 0.0, "integrate_angular_velocity: atol and rtol cannot both be zero");
+    const RotorRhs rhs{t, coef, n};
+    constexpr int NS = 12, D = 4;
+    const double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, EXPO = -1.0 / 8.0;
+    double y[D], K[NS + 1][D], ynew[D];
+    for (int c = 0; c < D; ++c) out[c] = y[c] = R0[c];
+    int64_t evals = 1;
+    rhs(0, t[0], y, K[0]);
+    double h_next = t[1] - t[0];
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const double t_end = t[i + 1];
+        SCRIB200_REQUIRE(t_end > t[i], "integrate_angular_velocity: times must be strictly increasing (sample %lld)", (long long)i);
+        double tc = t[i];
+        while (tc < t_end) {
+            double h = h_next;
+            bool clipped = false;
+            if (tc + h >= t_end || t_end - (tc + h) < 1e-14 * fabs(t_end)) {
+                h = t_end - tc;
+                clipped = true;
+            }
+            bool accepted = false;
+            while (!accepted) {
+                SCRIB200_REQUIRE(fabs(h) > 16.0 * 2.220446049250313e-16 * fmax(fabs(tc), 1.0), "integrate_angular_velocity: step size underflow at t=%g", tc);
+                for (int s = 1; s < NS; ++s) {
+                    double ys[D];
+                    for (int c = 0; c < D; ++c) {
+                        double acc = 0.0;
+                        for (int j = 0; j < s; ++j) acc += DOP_A[s][j] * K[j][c];
+                        ys[c] = y[c] + h * acc;
+                    }
+                    rhs(i, tc + DOP_C[s] * h, ys, K[s]);
+                }
+                for (int c = 0; c < D; ++c) {
+                    double acc = 0.0;
+                    for (int j = 0; j < NS; ++j) acc += DOP_B[j] * K[j][c];
+                    ynew[c] = y[c] + h * acc;
+                }
+                rhs(i, tc + h, ynew, K[NS]);
+                evals += NS;
+                double e5 = 0.0, e3 = 0.0;
+                for (int c = 0; c < D; ++c) {
+                    const double scale = atol + fmax(fabs(y[c]), fabs(ynew[c])) * rtol;
+                    double a5 = 0.0, a3 = 0.0;
+                    for (int j = 0; j <= NS; ++j) {
+                        a5 += DOP_E5[j] * K[j][c];
+                        a3 += DOP_E3[j] * K[j][c];
+                    }
+                    e5 += (a5 / scale) * (a5 / scale);
+                    e3 += (a3 / scale) * (a3 / scale);
+                }
+                double err = 0.0;
+                if (e5 != 0.0 || e3 != 0.0) err = fabs(h) * e5 / sqrt((e5 + 0.01 * e3) * D);
+                if (err < 1.0) {
+                    const double factor = (err == 0.0) ? MAX_FACTOR : fmin(MAX_FACTOR, SAFETY * pow(err, EXPO));
+                    if (!clipped || factor < 1.0) h_next = h * factor;          // a clipped step says nothing about growing
+                    else h_next = fmax(h_next, h * factor);
+                    accepted = true;
+                } else {
+                    h *= fmax(MIN_FACTOR, SAFETY * pow(err, EXPO));
+                    clipped = false;
+                }
+            }
+            tc = clipped ? t_end : tc + h;
+            for (int c = 0; c < D; ++c) {
+                y[c] = ynew[c];
+                K[0][c] = K[NS][c];          // first same as last
+            }
+        }
+        for (int c = 0; c < D; ++c) out[(i + 1) * D + c] = y[c];
+        if (i + 2 < n) rhs(i + 1, t_end, y, K[0]);                      // same value, evaluated in the next interval's polynomial
+    }
+    if (n_rhs) *n_rhs = evals;
+    return SCRIB200_OK;
+}

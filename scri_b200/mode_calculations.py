@@ -7,7 +7,7 @@ numpy-quaternion - integrating the angular velocity (mode_calculations.py:467) a
 import numpy as np
 
 from . import _quaternion as Q
-from . import ops
+from . import _lib, ops
 
 
 def LdtVector(W):
@@ -59,20 +59,30 @@ def angular_velocity(W, include_frame_velocity=False):
 def integrate_angular_velocity(t, omega, R0=(1.0, 0.0, 0.0, 0.0), tolerance=1e-12):
     """Rotor series with dR/dt = omega R / 2, R(t[0]) = R0, on the samples `t`.
 
-    Host-side stand-in for quaternion.integrate_angular_velocity (scri/mode_calculations.py:467): cubic-spline
-    omega, DOP853 with absolute tolerance `tolerance`, dense output sampled at `t`.
+    Stand-in for quaternion.integrate_angular_velocity (scri/mode_calculations.py:467): cubic-spline omega, Dormand-Prince
+    8(5,3) with absolute tolerance `tolerance`.  One serial ODE over the whole series - host work by nature - run by the
+    native integrator of the library (scrib200_integrate_angular_velocity) instead of scipy's DOP853 with a Python
+    right-hand side (1.3 s for 2e4 samples, ~60 000 interpreter round trips): the steps are clipped to the samples, so no
+    dense output is needed.
     """
-    from scipy.integrate import solve_ivp
+    import ctypes
+
     from scipy.interpolate import CubicSpline
 
-    om = CubicSpline(t, omega)
-
-    def rhs(tt, y):
-        w = om(tt)
-        return 0.5 * Q.qmul(np.array([0.0, w[0], w[1], w[2]]), y)
-
-    sol = solve_ivp(rhs, (t[0], t[-1]), np.asarray(R0, dtype=float), method="DOP853", t_eval=t, atol=tolerance, rtol=1e-13)
-    return sol.y.T.copy()
+    t = np.ascontiguousarray(t, dtype=float)
+    coef = np.ascontiguousarray(CubicSpline(t, np.asarray(omega, dtype=float)).c)          # [4, n-1, 3]
+    R0 = np.ascontiguousarray(R0, dtype=float)
+    out = np.empty((t.shape[0], 4))
+    if t.shape[0] == 1:
+        out[0] = R0
+        return out
+    lib = _lib.load()
+    _lib.check(
+        lib.scrib200_integrate_angular_velocity(t.ctypes.data, t.shape[0], coef.ctypes.data, R0.ctypes.data, float(tolerance), 1e-13,
+                                                out.ctypes.data, None),
+        "integrate_angular_velocity",
+    )
+    return out
 
 
 def corotating_frame(W, R0=(1.0, 0.0, 0.0, 0.0), tolerance=1e-12, z_alignment_region=None, return_omega=False):

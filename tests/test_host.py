@@ -245,3 +245,36 @@ def test_product_tables_config4_fit_one_cta():
     assert tb.fits and tb.smem_bytes <= 227 * 1024 and (tb.gm, tb.nwarps) == (5, 16)
     assert _product.product_tables(2, 0, 32, -2, 0, 32, 129, 129, 32, shape=1).nwarps == 8
     assert not _product.product_tables(2, 0, 64, -2, 0, 64, 257, 257, 64).fits   # the dense kernels take over
+
+
+def test_native_rotor_integrator_against_closed_form_and_scipy():
+    """scrib200_integrate_angular_velocity (host code of the library; quaternion.integrate_angular_velocity at
+    scri/mode_calculations.py:467): a constant angular velocity has the closed form exp(omega t / 2); a precessing one is
+    compared with scipy's DOP853 at a tighter tolerance.  The reference's own bar for the corotating frame is 1e-10
+    (tests/test_rotations.py); the native integrator clips its steps to the samples and lands well inside it."""
+    from scipy.integrate import solve_ivp
+    from scipy.interpolate import CubicSpline
+
+    from scri_b200 import mode_calculations as mc
+
+    t = np.arange(-20.0, 400.0, 0.1)
+    om_c = np.tile(np.array([0.1, -0.2, 0.3]), (t.size, 1))
+    th = np.linalg.norm(om_c[0]) * (t - t[0]) / 2
+    n = om_c[0] / np.linalg.norm(om_c[0])
+    exact = np.stack([np.cos(th), n[0] * np.sin(th), n[1] * np.sin(th), n[2] * np.sin(th)], axis=1)
+    assert np.abs(mc.integrate_angular_velocity(t, om_c) - exact).max() < 1e-12
+    w0 = 0.05 + 0.4 * ((t - t[0]) / (t[-1] - t[0])) ** 3
+    omega = np.stack([0.02 * np.cos(0.01 * t) * w0, 0.02 * np.sin(0.01 * t) * w0, w0], axis=1)
+    R0 = Q.qnormalized(np.array([1.0, 2.0, 3.0, 4.0]))
+    Rn = mc.integrate_angular_velocity(t, omega, R0=R0, tolerance=1e-12)
+    assert np.array_equal(Rn[0], R0) and np.abs(np.linalg.norm(Rn, axis=1) - 1).max() < 1e-12
+    om = CubicSpline(t, omega)
+
+    def rhs(tt, y):
+        w = om(tt)
+        return 0.5 * Q.qmul(np.array([0.0, w[0], w[1], w[2]]), y)
+
+    sol = solve_ivp(rhs, (t[0], t[-1]), R0, method="DOP853", t_eval=t[::50], atol=1e-13, rtol=1e-13)
+    assert np.abs(sol.y.T - Rn[::50]).max() < 5e-12
+    with pytest.raises((ValueError, _lib.Scrib200Error)):
+        mc.integrate_angular_velocity(np.array([0.0, 1.0, 1.0, 2.0, 3.0]), np.zeros((5, 3)))      # times must increase
