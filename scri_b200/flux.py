@@ -126,21 +126,36 @@ def _hdot_of(hw, name):
     if hw.dataType == hdottype:
         return hw.data
     if hw.dataType == htype:
-        return hw.data_dot
+        return _device_derivative(hw)[1]
     raise ValueError(f"Input argument is expected to have data of type `h` or `hdot`; this waveform data has type `{hw.data_type_string}`")
+
+
+def _device_derivative(h):
+    """(h.data, d/dt h.data) as device tensors: the modes travel to the device once and the derivative stays there
+    (h.data_dot would bring it back to the host only for the flux kernels to send it again)."""
+    h_d = ops.to_device(h.data, np.complex128)
+    return h_d, ops.spline_calculus(ops.to_device(np.asarray(h.t, dtype=float), np.float64), h_d, "derivative", 1)
 
 
 def energy_flux(h):
     """dE/dt = sum |hdot|^2 / 16 pi (scri/flux.py:182-210, Ruiz et al. 2008 eq. 2.8)"""
     hdot = _hdot_of(h, "Energy flux")
-    return ops.norm(hdot) / (16.0 * np.pi)
+    return _energy_flux_of(hdot)
+
+
+def _energy_flux_of(hdot):
+    """`hdot` [N, n] as a host array or a device tensor; the result is a host array either way."""
+    return ops.to_host(ops.norm(hdot)) / (16.0 * np.pi)
 
 
 def momentum_flux(h):
     """dp/dt (scri/flux.py:303-342, Ruiz et al. 2008 eq. 2.11)"""
     hdot = _hdot_of(h, "Momentum flux")
-    lmin, lmax = h.ell_min, h.ell_max
-    ev = ops.sparse_expectation(hdot, hdot, [p_plus(lmin, lmax, s=-2), p_minus(lmin, lmax, s=-2), p_z(lmin, lmax, s=-2)])
+    return _momentum_flux_of(hdot, h.ell_min, h.ell_max)
+
+
+def _momentum_flux_of(hdot, lmin, lmax):
+    ev = ops.to_host(ops.sparse_expectation(hdot, hdot, [p_plus(lmin, lmax, s=-2), p_minus(lmin, lmax, s=-2), p_z(lmin, lmax, s=-2)]))
     pdot = np.zeros((hdot.shape[0], 3), dtype=float)
     pdot[:, 0] = 0.5 * (ev[:, 0].real + ev[:, 1].real)
     pdot[:, 1] = 0.5 * (ev[:, 0].imag - ev[:, 1].imag)
@@ -160,14 +175,17 @@ def angular_momentum_flux(h, hdot=None):
     if h.dataType != htype:
         raise ValueError(f"Input argument `h` is expected to have data of type `h`; this `h` waveform data has type `{h.data_type_string}`")
     if hdot is None:
-        hdot_data = h.data_dot
+        h_data, hdot_data = _device_derivative(h)
     elif hdot.dataType != hdottype:
         raise ValueError(f"Input argument `hdot` is expected to have data of type `hdot`; this `hdot` waveform data has type `{hdot.data_type_string}`")
     else:
-        hdot_data = hdot.data
-    lmin, lmax = h.ell_min, h.ell_max
-    ev = ops.sparse_expectation(hdot_data, h.data, [j_plus(lmin, lmax), j_minus(lmin, lmax), j_z(lmin, lmax)])
-    jdot = np.zeros((h.n_times, 3), dtype=float)
+        h_data, hdot_data = ops.to_device(h.data, np.complex128), ops.to_device(hdot.data, np.complex128)
+    return _angular_momentum_flux_of(h_data, hdot_data, h.ell_min, h.ell_max)
+
+
+def _angular_momentum_flux_of(h_data, hdot_data, lmin, lmax):
+    ev = ops.to_host(ops.sparse_expectation(hdot_data, h_data, [j_plus(lmin, lmax), j_minus(lmin, lmax), j_z(lmin, lmax)]))
+    jdot = np.zeros((h_data.shape[0], 3), dtype=float)
     jdot[:, 0] = 0.5 * (ev[:, 0].real + ev[:, 1].real)
     jdot[:, 1] = 0.5 * (ev[:, 0].imag - ev[:, 1].imag)
     jdot[:, 2] = ev[:, 2].real
@@ -267,12 +285,15 @@ def boost_flux(h, hdot=None):
     if h.dataType != htype:
         raise ValueError(f"Input argument `h` is expected to have data of type `h`; this `h` waveform data has type `{h.data_type_string}`")
     if hdot is None:
-        hdot_data = h.data_dot
+        h_data, hdot_data = _device_derivative(h)
     elif hdot.dataType != hdottype:
         raise ValueError(f"Input argument `hdot` is expected to have data of type `hdot`; this `hdot` waveform data has type `{h.data_type_string}`")
     else:
-        hdot_data = hdot.data
-    lo, hi = h.ell_min, h.ell_max
+        h_data, hdot_data = ops.to_device(h.data, np.complex128), ops.to_device(hdot.data, np.complex128)
+    return _boost_flux_of(h_data, hdot_data, np.asarray(h.t), h.ell_min, h.ell_max)
+
+
+def _boost_flux_of(h_data, hdot_data, t, lo, hi):
     s = -2
     comps = []
     for P, EC, EBC in (
@@ -285,16 +306,15 @@ def boost_flux(h, hdot=None):
             hn=[_dressed(P(s=-3), lo, hi, "-", "-", s), _dressed(P(s=-1), lo, hi, "+", "+", s), P(s=-2), _dressed(EBC, lo, hi, "", "+", s)],
             nn=[P(s=-2)],
         ))
-    ev_nh = ops.sparse_expectation(hdot_data, h.data, [m for c in comps for m in c["nh"]])      # <hdot| . |h>
-    ev_hn = ops.sparse_expectation(h.data, hdot_data, [m for c in comps for m in c["hn"]])      # <h| . |hdot>
-    ev_nn = ops.sparse_expectation(hdot_data, hdot_data, [m for c in comps for m in c["nn"]])   # <hdot| . |hdot>
-    t = np.asarray(h.t)
+    ev_nh = ops.to_host(ops.sparse_expectation(hdot_data, h_data, [m for c in comps for m in c["nh"]]))      # <hdot| . |h>
+    ev_hn = ops.to_host(ops.sparse_expectation(h_data, hdot_data, [m for c in comps for m in c["hn"]]))      # <h| . |hdot>
+    ev_nn = ops.to_host(ops.sparse_expectation(hdot_data, hdot_data, [m for c in comps for m in c["nn"]]))   # <hdot| . |hdot>
     total = []
     for i in range(3):
         nh, hn = ev_nh[:, 4 * i : 4 * i + 4], ev_hn[:, 4 * i : 4 * i + 4]
         first = (1 / 8) * (nh[:, 0] - nh[:, 1] + 6 * nh[:, 2] + hn[:, 0] - hn[:, 1] + 6 * hn[:, 2])
         total.append(first - (1 / 2) * t * ev_nn[:, i] - (1 / 4) * (nh[:, 3] - hn[:, 3]))
-    out = np.zeros((h.n_times, 3), dtype=float)
+    out = np.zeros((h_data.shape[0], 3), dtype=float)
     out[:, 0] = 0.5 * (total[0] + total[1]).real
     out[:, 1] = 0.5 * (total[0] - total[1]).imag
     out[:, 2] = total[2].real
@@ -303,11 +323,24 @@ def boost_flux(h, hdot=None):
 
 
 def poincare_fluxes(h, hdot=None):
-    """(energy, momentum, angular-momentum, boost) fluxes with one time derivative (scri/flux.py:750-797)."""
+    """(energy, momentum, angular-momentum, boost) fluxes with one time derivative (scri/flux.py:750-797).  The modes go
+    to the device once: the derivative is taken there and the four fluxes read the two device arrays (the reference makes
+    a full copy of the waveform to hold hdot; nothing of the kind is needed here)."""
     from .waveform_modes import WaveformModes
 
+    if not isinstance(h, WaveformModes):
+        raise ValueError(f"Poincare fluxes can only be calculated from a `WaveformModes` object; `h` is of type `{type(h)}`.")
+    if h.dataType != htype:
+        raise ValueError(f"Input argument `h` is expected to have data of type `h`; this `h` waveform data has type `{h.data_type_string}`")
     if hdot is None:
-        hdot = h.copy()
-        hdot.dataType = hdottype
-        hdot.data = h.data_dot
-    return (energy_flux(hdot), momentum_flux(hdot), angular_momentum_flux(h, hdot), boost_flux(h, hdot))
+        h_d, hdot_d = _device_derivative(h)
+    else:
+        h_d = ops.to_device(h.data, np.complex128)
+        if not isinstance(hdot, WaveformModes):
+            raise ValueError(f"Poincare fluxes can only be calculated from a `WaveformModes` object; `hdot` is of type `{type(hdot)}`.")
+        if hdot.dataType != hdottype:
+            raise ValueError(f"Input argument `hdot` is expected to have data of type `hdot`; this `hdot` waveform data has type `{hdot.data_type_string}`")
+        hdot_d = ops.to_device(hdot.data, np.complex128)
+    lo, hi = h.ell_min, h.ell_max
+    return (_energy_flux_of(hdot_d), _momentum_flux_of(hdot_d, lo, hi), _angular_momentum_flux_of(h_d, hdot_d, lo, hi),
+            _boost_flux_of(h_d, hdot_d, np.asarray(h.t), lo, hi))
