@@ -293,7 +293,9 @@ def boost_flux(h, hdot=None):
     return _boost_flux_of(h_data, hdot_data, np.asarray(h.t), h.ell_min, h.ell_max)
 
 
-def _boost_flux_of(h_data, hdot_data, t, lo, hi):
+@functools.lru_cache(maxsize=8)
+def _boost_matrices(lo, hi):
+    """The three groups of sparse matrices of the boost flux, ladder factors folded in (built once per ell range)."""
     s = -2
     comps = []
     for P, EC, EBC in (
@@ -306,9 +308,14 @@ def _boost_flux_of(h_data, hdot_data, t, lo, hi):
             hn=[_dressed(P(s=-3), lo, hi, "-", "-", s), _dressed(P(s=-1), lo, hi, "+", "+", s), P(s=-2), _dressed(EBC, lo, hi, "", "+", s)],
             nn=[P(s=-2)],
         ))
-    ev_nh = ops.to_host(ops.sparse_expectation(hdot_data, h_data, [m for c in comps for m in c["nh"]]))      # <hdot| . |h>
-    ev_hn = ops.to_host(ops.sparse_expectation(h_data, hdot_data, [m for c in comps for m in c["hn"]]))      # <h| . |hdot>
-    ev_nn = ops.to_host(ops.sparse_expectation(hdot_data, hdot_data, [m for c in comps for m in c["nn"]]))   # <hdot| . |hdot>
+    return tuple([m for c in comps for m in c[k]] for k in ("nh", "hn", "nn"))
+
+
+def _boost_flux_of(h_data, hdot_data, t, lo, hi):
+    m_nh, m_hn, m_nn = _boost_matrices(lo, hi)
+    ev_nh = ops.to_host(ops.sparse_expectation(hdot_data, h_data, m_nh))      # <hdot| . |h>
+    ev_hn = ops.to_host(ops.sparse_expectation(h_data, hdot_data, m_hn))      # <h| . |hdot>
+    ev_nn = ops.to_host(ops.sparse_expectation(hdot_data, hdot_data, m_nn))   # <hdot| . |hdot>
     total = []
     for i in range(3):
         nh, hn = ev_nh[:, 4 * i : 4 * i + 4], ev_hn[:, 4 * i : 4 * i + 4]

@@ -639,6 +639,9 @@ def solve3(A, b, scale=1.0):
     return x if is_tensor(A) else to_host(x)
 
 
+_sparse_cache = {}
+
+
 def sparse_expectation(a, b, matrices):
     """[N, K] complex: <a|M_k|b>(t) for K sparse matrices (rows, cols, vals) - scri/flux.py:40-78."""
     lib = _lib.load()
@@ -646,13 +649,21 @@ def sparse_expectation(a, b, matrices):
     ad = to_device(a, np.complex128)
     bd = ad if b is a else to_device(b, np.complex128)
     N, n = ad.shape
-    rows = np.concatenate([np.asarray(m[0], dtype=np.int32) for m in matrices])
-    cols = np.concatenate([np.asarray(m[1], dtype=np.int32) for m in matrices])
-    vals = np.concatenate([np.asarray(m[2], dtype=complex) for m in matrices])
-    seg = np.zeros(len(matrices) + 1, dtype=np.int32)
-    seg[1:] = np.cumsum([len(m[0]) for m in matrices])
     K = len(matrices)
-    dr, dc, dv, ds = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg))
+    # the COO tables are cached on the device per set of matrix objects (the generators in flux.py are lru_cached, so the
+    # same objects come back call after call; the cache keeps them alive, which keeps their ids unique)
+    key = (tuple(id(m) for m in matrices), torch.cuda.current_device())
+    hit = _sparse_cache.get(key)
+    if hit is None:
+        rows = np.concatenate([np.asarray(m[0], dtype=np.int32) for m in matrices])
+        cols = np.concatenate([np.asarray(m[1], dtype=np.int32) for m in matrices])
+        vals = np.concatenate([np.asarray(m[2], dtype=complex) for m in matrices])
+        seg = np.zeros(K + 1, dtype=np.int32)
+        seg[1:] = np.cumsum([len(m[0]) for m in matrices])
+        if len(_sparse_cache) > 64:
+            _sparse_cache.clear()
+        hit = _sparse_cache[key] = (tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg)), list(matrices))
+    dr, dc, dv, ds = hit[0]
     out = torch.empty((N, K), dtype=torch.complex128, device="cuda")
     _lib.check(
         lib.scrib200_sparse_expectation(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dc), _lib.ptr(dv), None, _lib.ptr(ds), K, _lib.ptr(out), _lib.stream_ptr()),
