@@ -604,7 +604,65 @@ class TransformPlan(GridPlan):
         cs.synchronize()
         return host.numpy()
 
-    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0):
+    def _run_streaming(self, t, data, slabs, t_host, debug_poison=False):
+        """End-to-end pipeline for modes that are still arriving from the host (`slabs` of ops.to_device_slabs): slab j is
+        synthesized as it lands, and every output time whose input window is already synthesized is remapped, analysed and
+        copied back under the transfer of the later slabs.  Output j sits at input row lo + j; grid point g reads input
+        samples at most `drift` rows away (parallel.transform_halo: alpha_g, and beta |t| / dt under a boost) and the tile
+        kernel stages whole tiles plus halos, so outputs up to row r_hi - margin - lo are ready once rows < r_hi are
+        synthesized (margin = drift + tile body + 2 halos + slack).  Returns (u', modes as a pinned host array) or None when
+        the series is too short to be worth cutting."""
+        from .parallel import SPLINE_DECAY_ROWS, transform_halo
+
+        torch = self.torch
+        lib = _lib.load()
+        cur = torch.cuda.current_stream()
+        prep = self.prepare(t)                       # the time axis is already on the device: four tiny launches
+        lo, hi = prep.resolve()                      # host wait for those only; the modes keep streaming on the copy stream
+        n_out = hi - lo
+        if n_out < 8192:
+            return None
+        uprm = prep.uprm
+        halo, body = prep.halo_body(self.spline_halo, self.spline_body)
+        drift = transform_halo(self, float(t_host[0]), float(t_host[-1]), float(np.diff(t_host).min())) - SPLINE_DECAY_ROWS
+        margin = drift + max(body, 320) + 2 * halo + 64
+        N = data.shape[0]
+        F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
+        if debug_poison:
+            F.fill_(float("nan"))                    # tests: an output that read a row before its synthesis turns into NaN
+        host = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, pin_memory=True)
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream()
+        cs = self._d2h_stream
+        tile = self.tile
+        done = 0
+        for k, (rlo, rhi, ev, flag) in enumerate(slabs):
+            flag.wait()
+            cur.wait_event(ev)
+            if rhi > rlo:
+                _lib.check(
+                    lib.scrib200_swsh_synthesize(
+                        _lib.ptr(data[rlo:rhi]), rhi - rlo, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad,
+                        _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F[rlo:rhi]), _lib.stream_ptr(),
+                    ),
+                    "swsh_synthesize",
+                )
+            out_hi = n_out if k == len(slabs) - 1 else min(n_out, max(done, ((rhi - margin - lo) // tile) * tile))
+            if out_hi > done:
+                gridT = self._remap(t, F, uprm[done:out_hi], prep, tile)
+                modes = self.analyze_tiled(gridT, out_hi - done)
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                cs.wait_event(ready)
+                with torch.cuda.stream(cs):
+                    host[done:out_hi].copy_(modes, non_blocking=True)
+                modes.record_stream(cs)
+                del gridT, modes
+                done = out_hi
+        cs.synchronize()
+        return uprm, host.numpy()
+
+    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
 
         The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
@@ -612,6 +670,10 @@ class TransformPlan(GridPlan):
         their time axis.  With `host_slabs` = S > 0 the modes come back as a numpy array in pinned host memory: the output
         times are cut into S slabs, each remapped, analysed and copied out on a copy stream while the next one computes
         (the end-to-end path of WaveformGrid.transform)."""
+        if host_slabs and slabs is not None and t_host is not None and prep is None and self.tile and not self.mix and not return_grid:
+            streamed = self._run_streaming(t, data, slabs, t_host)
+            if streamed is not None:
+                return streamed
         cur = self.torch.cuda.current_stream()
         ready = self.torch.cuda.Event()
         ready.record(cur)

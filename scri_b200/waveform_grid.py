@@ -131,7 +131,7 @@ class WaveformGrid(WaveformBase):
         # the modes stream in slab by slab on a copy stream while the plan is built; each slab is synthesized as it lands
         big = w_modes.data.nbytes >= (8 << 20)
         if big:
-            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128)
+            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, n_slabs=8)
         else:
             a_d, slabs, a_fut = ops.to_device(w_modes.data, np.complex128), None, None
         try:
@@ -148,7 +148,8 @@ class WaveformGrid(WaveformBase):
             a_fut.result()
             _lib.require_cuda().cuda.current_stream().wait_event(slabs[-1][2])
             slabs = None
-        uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4)   # modes land in pinned host memory slab by slab
+        # modes land in pinned host memory slab by slab, the first output slabs while the last input slabs are still in flight
+        uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4, t_host=np.asarray(w_modes.t, dtype=float))
         if a_fut is not None:
             a_fut.result()                       # surfaces a failed copy
         if plan.leftover_kwargs:

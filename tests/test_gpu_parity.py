@@ -808,3 +808,24 @@ def test_time_sharded_transform_world2():
         assert rel(m, ref.data) < RTOL
     res = _run_sharded_transform(dict(boost_velocity=[0.3, 0.4, 0.5]), 4000, 400.0)    # drift ~ 0.7 N samples: more than a block
     assert all(r[3] is not None and "shard by waveform" in r[3] for r in res)
+
+
+@pytest.mark.parametrize("n_slabs", [3, 8])
+def test_streaming_end_to_end_pipeline_is_bitwise_identical(n_slabs):
+    """WaveformGrid.transform's host path: input slabs synthesized as they land, output slabs remapped / analysed / copied back
+    as soon as their input window is there (TransformPlan._run_streaming).  The grid array is poisoned with NaN first, so
+    an output computed from a row that was not synthesized yet could not go unnoticed; the result equals the single-launch
+    device path bit for bit, with and without a boost."""
+    for kw in (BMS, dict(supertranslation=real_supertranslation(4), frame_rotation=[1.0, 2.0, 3.0, 4.0])):
+        t, data = smooth_modes(n_times=12000, t0=0.0, t1=1200.0, seed=41)
+        plan = P.TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **kw)
+        td = ops.to_device(t)
+        u1, m1 = plan.run(td, ops.to_device(data))
+        a_d, slabs, fut = ops.to_device_slabs(data, np.complex128, n_slabs=n_slabs)
+        u2, m2 = plan._run_streaming(td, a_d, slabs, t, debug_poison=True)
+        fut.result()
+        assert np.array_equal(u2.cpu().numpy(), u1.cpu().numpy())
+        assert np.isfinite(m2).all() and np.array_equal(m2, m1.cpu().numpy())
+    out = modes(t, data).transform(**BMS)          # the public call takes the same path
+    ref = R.transform(R.Modes(t=t, data=data.copy()), **BMS)
+    assert np.array_equal(out.t, ref.t) and rel(out.data, ref.data) < RTOL
