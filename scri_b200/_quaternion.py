@@ -119,3 +119,58 @@ def rotate_z(R):
     w, x, y, z = (R[..., i] for i in range(4))
     n = w * w + x * x + y * y + z * z
     return np.stack([2 * (x * z + w * y), 2 * (y * z - w * x), w * w - x * x - y * y + z * z], axis=-1) / n[..., None]
+
+
+def qexp(q):
+    """exp of a general quaternion (w, v) = e^w (cos|v|, sin|v| v/|v|)."""
+    q = np.asarray(q, dtype=float)
+    return np.exp(q[..., :1]) * qexp_vec(q[..., 1:])
+
+
+def slerp(q1, q2, tau):
+    """(q2 q1^-1)^tau q1 - the geodesic from q1 (tau = 0) to q2 (tau = 1); `tau` broadcasts against the leading axes."""
+    tau = np.asarray(tau, dtype=float)[..., None]
+    return qmul(qexp(tau * qlog(qmul(q2, qinverse(q1)))), q1)
+
+
+def squad(R_in, t_in, t_out):
+    """Spherical "quadrangle" interpolation of a rotor series onto new times: the C^1 analogue of a cubic spline on the
+    rotation group (Shoemake 1987), with the control points corrected for unequal time steps as numpy-quaternion's
+    `squad` does it - the routine scri/waveform_base.py:962 uses for the frame in `interpolate`.
+
+      A_i     = R_i     exp( (log(R_{i-1}^-1 R_i) h_i / h_{i-1} - log(R_i^-1 R_{i+1})) / 4 )
+      B_{i+1} = R_{i+1} exp(-(log(R_{i+1}^-1 R_{i+2}) h_i / h_{i+1} - log(R_i^-1 R_{i+1})) / 4 )
+      R(t)    = slerp( slerp(R_i, R_{i+1}, tau), slerp(A_i, B_{i+1}, tau), 2 tau (1 - tau) ),  tau = (t - t_i) / h_i,
+
+    the series continued at both ends by reflection (R_{-1} = R_0 R_1^-1 R_0, ...), which makes A_0 = R_0 and A_{n-1} = B_{n-1} =
+    R_{n-1}.  Rotor arrays are float [..., 4] (w, x, y, z).  numpy-quaternion is not available here: parity with its
+    rounding is unpinned; the defining properties (the knots are reproduced, a uniformly rotating series stays on its
+    geodesic) are tested."""
+    R_in = as_float_quat(R_in)
+    t_in = np.asarray(t_in, dtype=float)
+    t_out = np.asarray(t_out, dtype=float)
+    if R_in.size == 0 or t_out.size == 0:
+        return np.empty((0, 4))
+    n = R_in.shape[0]
+    if n == 1:
+        return np.repeat(R_in, t_out.size, axis=0)
+    roll = lambda x, k: np.roll(x, k, axis=0)
+    h = roll(t_in, -1) - t_in                                  # h_i = t_{i+1} - t_i (last entry wraps: overwritten below)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        step = qlog(qmul(qinverse(R_in), roll(R_in, -1)))      # log(R_i^-1 R_{i+1})
+        prev = qlog(qmul(qinverse(roll(R_in, 1)), R_in))       # log(R_{i-1}^-1 R_i)
+        nxt = qlog(qmul(qinverse(roll(R_in, -1)), roll(R_in, -2)))   # log(R_{i+1}^-1 R_{i+2})
+        A = qmul(R_in, qexp((prev * (h / (t_in - roll(t_in, 1)))[:, None] - step) * 0.25))
+        B = qmul(roll(R_in, -1), qexp((nxt * (h / (roll(t_in, -2) - roll(t_in, -1)))[:, None] - step) * -0.25))
+    last_next = qmul(qmul(R_in[-1], qinverse(R_in[-2])), R_in[-1])    # the reflected sample after the last one
+    A[0] = R_in[0]
+    A[-1] = R_in[-1]
+    B[-2] = R_in[-1]
+    B[-1] = last_next
+    R_ip1 = roll(R_in, -1).copy()
+    R_ip1[-1] = last_next
+    t_ip1 = roll(t_in, -1).copy()
+    t_ip1[-1] = t_in[-1] + (t_in[-1] - t_in[-2])
+    i = np.clip(t_in.searchsorted(t_out, side="right") - 1, 0, n - 1)
+    tau = (t_out - t_in[i]) / (t_ip1 - t_in)[i]
+    return slerp(slerp(R_in[i], R_ip1[i], tau), slerp(A[i], B[i], tau), 2 * tau * (1 - tau))

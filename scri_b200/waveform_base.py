@@ -160,6 +160,25 @@ class WaveformBase:
         W = type(self)(**self._copy_kwargs(), constructor_statement=f"{self}.copy()")
         return W
 
+    def interpolate(self, tprime):
+        """Interpolate the frame and the data onto the new time steps (scri/waveform_base.py:949-967): the data through
+        the not-a-knot cubic spline of every column (CubicSpline(t, data)(t') - on the GPU, scrib200_spline_remap with
+        k = 1, alpha = 0), the frame through `squad`.  Returns a new object; only `t`, `frame` and `data` change."""
+        from . import ops
+
+        tprime = np.array(tprime, dtype=float)
+        if tprime.ndim != 1:
+            raise ValueError(f"New time array must have exactly 1 dimension; it has {tprime.ndim}.")
+        kw = self._copy_kwargs()
+        kw["t"] = tprime
+        kw["frame"] = Q.squad(self.frame, self.t, tprime) if self.frame.shape[0] == self.t.shape[0] and self.frame.size else np.copy(self.frame)
+        if self.data.size and tprime.size:
+            kw["data"] = ops.spline_calculus(self.t, self.data.reshape(self.t.shape[0], -1), "evaluate", tprime=tprime).reshape(
+                (tprime.shape[0],) + self.data.shape[1:])
+        else:
+            kw["data"] = np.empty((tprime.shape[0],) + self.data.shape[1:], dtype=self.data.dtype)
+        return type(self)(**kw, constructor_statement=f"{self}.interpolate({np.array2string(tprime, threshold=6)})")
+
     def deepcopy(self):
         return _copy.deepcopy(self)
 

@@ -829,3 +829,30 @@ def test_streaming_end_to_end_pipeline_is_bitwise_identical(n_slabs):
     out = modes(t, data).transform(**BMS)          # the public call takes the same path
     ref = R.transform(R.Modes(t=t, data=data.copy()), **BMS)
     assert np.array_equal(out.t, ref.t) and rel(out.data, ref.data) < RTOL
+
+
+def test_interpolate_data_and_frame():
+    """WaveformBase.interpolate (scri/waveform_base.py:949-967; reference tests/test_waveform.py:205-260): data through the
+    not-a-knot cubic spline of every column (scipy's CubicSpline is the reference's own call), frame through squad; a
+    constant waveform is reproduced to the reference's 4.5e-16."""
+    from scipy.interpolate import CubicSpline
+
+    from scri_b200 import _quaternion as Q
+
+    t, data = smooth_modes(n_times=700, t0=0.0, t1=70.0, seed=51, uniform=False)
+    ang = 0.3 * t + 0.05 * np.sin(t)
+    frame = Q.qexp_vec(0.5 * ang[:, None] * np.array([0.1, -0.2, 0.97])[None, :])
+    w = modes(t, data, frameType=sb.Corotating, frame=frame)
+    t_out = (t[:-1] + t[1:]) / 2.0
+    w_out = w.interpolate(t_out)
+    assert w.ensure_validity(alter=False) and w_out.ensure_validity(alter=False)
+    assert w_out.frameType == sb.Corotating and w_out.dataType == sb.h and w_out.r_is_scaled_out and w_out.m_is_scaled_out
+    assert w_out.num != w.num and np.all(w_out.t == t_out) and np.all(w_out.LM == w.LM)
+    assert w_out.data.shape == (len(t_out), w.n_modes)
+    assert np.array_equal(w_out.frame, Q.squad(frame, t, t_out))
+    assert rel(w_out.data, CubicSpline(t, data)(t_out)) < RTOL
+    assert np.array_equal(w.data, data)                         # the input is untouched
+    const = modes(t, np.tile(data[:1], (t.size, 1)), frameType=sb.Corotating, frame=np.tile(frame[:1], (t.size, 1)))
+    c_out = const.interpolate(t_out)
+    assert np.abs(c_out.data - data[:1]).max() <= 4.5e-16 * np.abs(data[:1]).max() * 4
+    assert np.abs(c_out.frame - frame[:1]).max() <= 4.5e-16

@@ -278,3 +278,30 @@ def test_native_rotor_integrator_against_closed_form_and_scipy():
     assert np.abs(sol.y.T - Rn[::50]).max() < 5e-12
     with pytest.raises((ValueError, _lib.Scrib200Error)):
         mc.integrate_angular_velocity(np.array([0.0, 1.0, 1.0, 2.0, 3.0]), np.zeros((5, 3)))      # times must increase
+
+
+def test_squad_reproduces_knots_and_geodesics():
+    """quaternion.squad as used by WaveformBase.interpolate (scri/waveform_base.py:962): the samples are reproduced exactly,
+    a uniformly rotating series stays on its geodesic between unevenly spaced samples, and the interpolant of a smooth
+    rotation converges."""
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 10, 40))
+    t[0], t[-1] = 0.0, 10.0
+    axis = np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    R0 = Q.qnormalized(np.array([1.0, 2.0, 3.0, 4.0]))
+
+    def geodesic(tt):
+        return Q.qmul(Q.qexp_vec(0.35 * tt[:, None] * axis[None, :]), R0[None, :])
+
+    R = geodesic(t)
+    assert np.array_equal(Q.squad(R, t, t), R)
+    tt = np.linspace(0, 10, 333)
+    assert np.abs(Q.squad(R, t, tt) - geodesic(tt)).max() < 1e-13
+
+    def wobble(x):
+        ax = np.stack([np.sin(0.2 * x), np.cos(0.2 * x), 0.5 + 0 * x], 1)
+        return Q.qexp_vec(0.5 * (0.7 * x + 0.3 * np.sin(x))[:, None] * ax / np.linalg.norm(ax, axis=1)[:, None])
+
+    errs = [np.abs(Q.squad(wobble(np.linspace(0, 10, n)), np.linspace(0, 10, n), tt) - wobble(tt)).max() for n in (50, 100, 200)]
+    assert errs[0] > 3 * errs[1] > 9 * errs[2]
+    assert Q.squad(np.empty((0, 4)), np.empty(0), tt).shape == (0, 4)
