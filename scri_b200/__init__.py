@@ -18,7 +18,8 @@ from .mode_calculations import (  # noqa: F401
 )
 from .flux import energy_flux, momentum_flux, angular_momentum_flux, boost_flux, poincare_fluxes  # noqa: F401
 from .rotations import (  # noqa: F401
-    rotate_decomposition_basis, rotate_physical_system, to_coprecessing_frame, to_corotating_frame, to_inertial_frame,
+    align_decomposition_frame_to_modes, get_alignment_of_decomposition_frame_to_modes, rotate_decomposition_basis, rotate_physical_system,
+    to_coprecessing_frame, to_corotating_frame, to_inertial_frame,
 )
 from . import sample_waveforms  # noqa: F401
 from .asymptotic_bondi_data import AsymptoticBondiData, ModesTimeSeries  # noqa: F401

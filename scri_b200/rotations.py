@@ -3,7 +3,7 @@ import numpy as np
 
 from . import _quaternion as Q
 from . import ops
-from .constants import Coprecessing, Corotating, Inertial
+from .constants import Coorbital, Coprecessing, Corotating, Inertial
 from .waveform_base import waveform_alterations
 
 
@@ -99,3 +99,65 @@ def to_coprecessing_frame(W, RoughDirection=np.array([0.0, 0.0, 1.0]), RoughDire
     W.__history_depth__ -= 1
     W._append_history(f"{W}.to_coprecessing_frame({RoughDirection}, {RoughDirectionIndex})")
     return W
+
+
+def get_alignment_of_decomposition_frame_to_modes(w, t_fid, nHat_t_fid=(0.0, 1.0, 0.0, 0.0), ell_max=None):
+    """Rotor R_eps that fixes the attitude of a corotating / coprecessing / coorbital frame at the fiducial time: the z axis
+    of the decomposition frame goes onto the dominant eigenvector of <LL> (pointing along the angular velocity) and the
+    phases of the (2, +-2) modes are made equal; the x axis ends up closer to `nHat_t_fid` than to its opposite
+    (scri/rotations.py:114-225).  Returns a float rotor (w, x, y, z)."""
+    import math
+
+    from .mode_calculations import LLDominantEigenvector, angular_velocity
+
+    if ell_max is None:
+        ell_max = w.ell_max
+    if w.frameType not in (Coprecessing, Coorbital, Corotating):
+        raise ValueError(
+            "get_alignment_of_decomposition_frame_to_modes only takes Waveforms in the coprecessing, coorbital, or corotating "
+            f"frames.  This Waveform is in the '{w.frame_type_string}' frame."
+        )
+    if w.frame.shape[0] != w.n_times:
+        raise ValueError(
+            "get_alignment_of_decomposition_frame_to_modes requires full information about the Waveform's frame."
+            f"This Waveform has {w.n_times} time steps, but only {w.frame.shape[0]} rotors in its frame."
+        )
+    if t_fid < w.t[0] or t_fid > w.t[-1]:
+        raise ValueError(f"The requested alignment time t_fid={t_fid} is outside the range of times in this waveform ({w.t[0]}, {w.t[-1]}).")
+    nHat = np.asarray(nHat_t_fid, dtype=float).ravel()[-3:]
+    # direction of the angular velocity near t_fid, from an 11-sample window of the ell = 2 modes in the inertial frame
+    i_t_fid = int((w.t <= t_fid).nonzero()[0][-1])
+    if i_t_fid < w.t.size - 1:
+        i_t_fid += 1
+    i1 = max(0, i_t_fid - 5)
+    i2 = w.t.size if i1 + 11 > w.t.size else i1 + 11
+    region = w[i1:i2, 2].to_inertial_frame()
+    om = angular_velocity(region)[i_t_fid - i1]
+    omega_hat = np.concatenate([[0.0], om / np.linalg.norm(om)])
+    R = w.frame[i_t_fid]
+    omega_hat = Q.qmul(Q.qmul(Q.qinverse(R), omega_hat), R)        # components in this waveform's (rotating) frame
+    instant = w[i1:i2].interpolate(np.array([t_fid]))
+    R_f0 = instant.frame[0]
+    V = LLDominantEigenvector(instant[:, : ell_max + 1])[0]
+    V = V / np.linalg.norm(V)
+    if np.dot(omega_hat[1:], V) < 0:
+        V = -V
+    zq = np.array([0.0, 0.0, 0.0, 1.0])
+    R_V_f = Q.qsqrt(-Q.qmul(np.concatenate([[0.0], V]), zq))      # rotor taking z onto V
+    instant.rotate_decomposition_basis(R_V_f)
+    a22, a2m2 = instant.data[0, instant.index(2, 2)], instant.data[0, instant.index(2, -2)]
+    phase = math.atan2(a22.imag, a22.real) - math.atan2(a2m2.imag, a2m2.real)
+    R_eps = Q.qmul(R_V_f, Q.qexp_vec(np.array([0.0, 0.0, -phase / 8.0])))
+    xq = np.array([0.0, 1.0, 0.0, 0.0])
+    Rt = Q.qmul(R_f0, R_eps)
+    if np.dot(nHat, Q.qmul(Q.qmul(Rt, xq), Q.qinverse(Rt))[1:]) < 0:
+        R_eps = Q.qmul(R_eps, Q.qexp_vec(np.array([0.0, 0.0, math.pi / 2.0])))
+    return R_eps
+
+
+def align_decomposition_frame_to_modes(w, t_fid, nHat_t_fid=(0.0, 1.0, 0.0, 0.0), ell_max=None):
+    """Fix the attitude of the corotating frame at `t_fid` by the constant rotor of
+    `get_alignment_of_decomposition_frame_to_modes` (scri/rotations.py:228-265); rotates `w` in place and returns it."""
+    R_eps = get_alignment_of_decomposition_frame_to_modes(w, t_fid, nHat_t_fid, ell_max)
+    w._append_history(f"{w}.align_decomposition_frame_to_modes({t_fid}, {nHat_t_fid}, {ell_max})  # R_eps={R_eps}")
+    return w.rotate_decomposition_basis(R_eps)

@@ -157,6 +157,46 @@ class WaveformModes(WaveformBase):
 
         return WaveformGrid.to_modes(w_grid, ell_max)
 
+    def __getitem__(self, key):
+        """Subsets of the data: `w[i1:i2]` (times), `w[i1:i2, ell]` (one ell) or `w[i1:i2, ell_lo:ell_hi]` (ell_lo <= ell <
+        ell_hi) - the second index addresses ell values, not data columns (scri/waveform_modes.py:953-1021); the columns
+        kept are ell_lo^2 - ell_min^2 .. ell_hi'(ell_hi' + 2) + 1 - ell_min^2.  Returns a new object holding copies."""
+        if isinstance(key, tuple) and len(key) == 1:
+            key = key[0]
+        new_ell_min, new_ell_max = self.ell_min, self.ell_max
+        cols = slice(None)
+        if isinstance(key, tuple) and len(key) == 2:
+            tkey, lkey = key
+            if isinstance(lkey, (int, np.integer)):
+                if lkey < self.ell_min or lkey > self.ell_max:
+                    raise ValueError(f"Requested ell value {lkey} lies outside WaveformModes object's ell range ({self.ell_min},{self.ell_max}).")
+                new_ell_min = new_ell_max = int(lkey)
+            elif isinstance(lkey, slice):
+                if lkey.step and lkey.step != 1:
+                    raise ValueError(f"Can only slice WaveformModes over contiguous ell values (step={lkey.step})")
+                if not lkey.start and lkey.stop == 0:
+                    new_ell_min, new_ell_max = 0, -1
+                else:
+                    new_ell_min = lkey.start if lkey.start else self.ell_min
+                    new_ell_max = lkey.stop - 1 if lkey.stop else self.ell_max
+                    if new_ell_min < self.ell_min or new_ell_max > self.ell_max:
+                        raise ValueError(f"Requested ell range [{new_ell_min},{new_ell_max}] lies outside WaveformBase's ell range [{self.ell_min},{self.ell_max}].")
+            else:
+                raise ValueError(f"Don't know what to do with slice of type `{type(lkey)}`")
+            cols = slice(0) if new_ell_max < new_ell_min else slice(new_ell_min**2 - self.ell_min**2, new_ell_max * (new_ell_max + 2) + 1 - self.ell_min**2)
+        elif isinstance(key, (slice, int, np.integer)):
+            tkey = key
+        else:
+            raise ValueError(f"Could not understand input `{key}` (of type `{type(key)}`) ")
+        if isinstance(tkey, (int, np.integer)):
+            tkey = slice(tkey, tkey + 1 if tkey != -1 else None)
+        frame = self.frame[tkey] if self.frame.shape[0] == self.t.shape[0] else self.frame
+        return type(self)(
+            t=np.copy(self.t[tkey]), frame=np.copy(frame), data=np.copy(self.data[tkey, cols]), history=self.history[:],
+            version_hist=self.version_hist[:], frameType=self.frameType, dataType=self.dataType, r_is_scaled_out=self.r_is_scaled_out,
+            m_is_scaled_out=self.m_is_scaled_out, ell_min=new_ell_min, ell_max=new_ell_max, constructor_statement=f"{self}[{key}]",
+        )
+
     def __repr__(self):
         rep = super().__repr__()
         rep += f"\n# ell_min={self.ell_min}, ell_max={self.ell_max}"
@@ -172,6 +212,8 @@ def _attach_operators():
     WaveformModes.to_inertial_frame = rotations.to_inertial_frame
     WaveformModes.to_corotating_frame = rotations.to_corotating_frame
     WaveformModes.to_coprecessing_frame = rotations.to_coprecessing_frame
+    WaveformModes.get_alignment_of_decomposition_frame_to_modes = rotations.get_alignment_of_decomposition_frame_to_modes
+    WaveformModes.align_decomposition_frame_to_modes = rotations.align_decomposition_frame_to_modes
 
 
 _attach_operators()

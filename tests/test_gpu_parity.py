@@ -856,3 +856,34 @@ def test_interpolate_data_and_frame():
     c_out = const.interpolate(t_out)
     assert np.abs(c_out.data - data[:1]).max() <= 4.5e-16 * np.abs(data[:1]).max() * 4
     assert np.abs(c_out.frame - frame[:1]).max() <= 4.5e-16
+
+
+def test_align_decomposition_frame_to_modes_and_slicing():
+    """scri/rotations.py:114-265 and scri/waveform_modes.py:953-1021: after the alignment the dominant eigenvector of <LL>
+    at the fiducial time is the z axis of the decomposition frame, the (2, +-2) phases agree, the x axis is on nHat's side,
+    and the waveform still is the same physical waveform (back in the inertial frame it equals the original)."""
+    import math
+
+    w0 = sb.sample_waveforms.fake_precessing_waveform(t_0=-20.0, t_1=300.0, dt=0.1, ell_max=4)
+    ref = w0.data.copy()
+    w = w0.copy().to_corotating_frame()
+    t_fid = 123.456
+    sub = w[100:140, 2:4]
+    assert sub.ells == (2, 3) and sub.data.shape == (40, 12) and sub.frame.shape == (40, 4) and np.array_equal(sub.t, w.t[100:140])
+    assert np.array_equal(sub.data, w.data[100:140, :12])
+    with pytest.raises(ValueError):
+        w0.copy().align_decomposition_frame_to_modes(t_fid)      # inertial frame: refused, as in the reference
+    w.align_decomposition_frame_to_modes(t_fid)
+    i = int(np.searchsorted(w.t, t_fid))
+    inst = w[i - 6 : i + 6].interpolate(np.array([t_fid]))
+    V = inst.LLDominantEigenvector()[0]
+    assert abs(abs(V[2]) - 1.0) < 1e-9 and np.hypot(V[0], V[1]) < 1e-4
+    a22, a2m2 = inst.data[0, inst.index(2, 2)], inst.data[0, inst.index(2, -2)]
+    dphi = math.atan2(a22.imag, a22.real) - math.atan2(a2m2.imag, a2m2.real)
+    assert abs(math.remainder(dphi, 2 * math.pi)) < 1e-6
+    from scri_b200 import _quaternion as Q
+
+    xq = np.array([0.0, 1.0, 0.0, 0.0])
+    assert Q.qmul(Q.qmul(inst.frame[0], xq), Q.qinverse(inst.frame[0]))[1] > 0      # x axis on the side of nHat = x
+    back = w.copy().to_inertial_frame()
+    assert rel(back.data, ref) < 1e-10
