@@ -208,3 +208,46 @@ def bondi_four_momentum(abd, sigma_bar_dot=None):
         mass_aspect = mass_aspect + grid_multiply(abd.data["sigma"], 2, sbd, -2)
     mass_aspect = -0.5 * (mass_aspect + modes_bar(mass_aspect, 0))
     return charge_vector_from_aspect(mass_aspect[..., :4])
+
+
+# ----------------------------------------------------------------------------- BMS charges through the 3j product
+def modes_ethbar(modes, s):
+    """sf.Modes.ethbar (NP convention): multiply by -sqrt((l+s)(l-s+1)); spin weight s -> s-1."""
+    ell = _ells(int(round(math.sqrt(modes.shape[-1]))) - 1)
+    return modes * np.where(ell >= abs(s), -np.sqrt(np.maximum((ell + s) * (ell - s + 1), 0.0)), 0.0)
+
+
+def _real_part(modes):
+    return 0.5 * (modes + modes_bar(modes, 0))
+
+
+def bms_charges(abd):
+    """bms_charges.py:77-189 with every product taken as spherical_functions' Modes.multiply does (3j sums,
+    oracle.sf.modes_multiply) and truncated at ell = 1: four-momentum, angular momentum, boost charge, centre-of-mass charge."""
+    L = abd.ell_max
+    sig, psi1, psi2 = abd.data["sigma"], abd.data["psi1"], abd.data["psi2"]
+    sbar = modes_bar(sig, 2)
+    sbar_dot = CubicSpline(abd.u, sbar, axis=0).derivative()(abd.u)
+    s_eth_sbar = sf.modes_multiply(sig, 2, L, modes_eth(sbar, -2) / math.sqrt(2), -1, L, 1)
+    s_sbar = sf.modes_multiply(sig, 2, L, sbar, -2, L, 1)
+    s_sbar_dot = sf.modes_multiply(sig, 2, L, sbar_dot, -2, L, 1)
+    mass = -_real_part(psi2[:, :4] + s_sbar_dot)
+    P = charge_vector_from_aspect(mass)
+    J = charge_vector_from_aspect(1j * (psi1[:, :4] + s_eth_sbar))[:, 1:]
+    com = -(psi1[:, :4] + s_eth_sbar + 0.5 * modes_eth(s_sbar, 0) / math.sqrt(2))
+    G = charge_vector_from_aspect(com)[:, 1:]
+    boost = com + abd.u[:, None] * modes_eth(_real_part(psi2[:, :4] + s_sbar_dot), 0) / math.sqrt(2)
+    N = charge_vector_from_aspect(boost)[:, 1:]
+    return P, J, N, G
+
+
+def supermomentum(abd, kind, working_ell_max=None, integrated=False):
+    """bms_charges.py:192-269."""
+    sig = abd.data["sigma"]
+    sbar = modes_bar(sig, 2)
+    sbar_dot = CubicSpline(abd.u, sbar, axis=0).derivative()(abd.u)
+    psi = abd.data["psi2"] + grid_multiply(sig, 2, sbar_dot, -2, working_ell_max=working_ell_max)
+    eth2_sbar = modes_eth(modes_eth(sbar, -2), -1) / 2.0
+    ethbar2_s = modes_ethbar(modes_ethbar(sig, 2), 1) / 2.0
+    psi = psi + {"bs": 0.0, "m": eth2_sbar, "g": 0.5 * (eth2_sbar - ethbar2_s), "gw": -ethbar2_s}[kind]
+    return -0.5 * modes_bar(psi, 0) / math.sqrt(math.pi) if integrated else psi

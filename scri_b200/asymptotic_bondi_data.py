@@ -33,6 +33,8 @@ class ModesTimeSeries:
     uses.  Arithmetic between series of equal layout works through `ndarray`.
     """
 
+    __array_ufunc__ = None      # `ndarray * series` defers to __rmul__ (e.g. `abd.t * field`, bms_charges.py:165)
+
     def __init__(self, data, time, spin_weight, ell_max=None, ell_min=0, multiplication_truncator=max):
         self.ndarray = np.ascontiguousarray(data, dtype=complex)
         self.time = np.asarray(time, dtype=float)
@@ -79,6 +81,8 @@ class ModesTimeSeries:
     def __mul__(self, scalar):
         if isinstance(scalar, ModesTimeSeries):
             return self.grid_multiply(scalar)
+        if np.ndim(scalar) == 1 and np.shape(scalar)[0] == self.n_times:      # a function of time, e.g. `abd.t * field`
+            scalar = np.asarray(scalar)[:, None]
         return self._like(self.ndarray * scalar)
 
     __rmul__ = __mul__
@@ -224,25 +228,94 @@ class AsymptoticBondiData:
         raw = np.stack([self._get(name).interpolate(new_times).ndarray for name in FIELDS])
         return AsymptoticBondiData(new_times, self._ell_max, self.multiplication_truncator, self.frameType, raw)
 
-    # -- charges that the reference's transformation tests use (scri/asymptotic_bondi_data/bms_charges.py:14-105)
-    def mass_aspect(self):
-        """M = -Re{psi2 + sigma d/dt(bar sigma)}, truncated to ell_max (bms_charges.py:14-47 with truncate_ell=max)."""
-        prod = self.sigma.grid_multiply(self.sigma.bar.dot, output_ell_max=self._ell_max)
-        return -(self.psi2 + prod).real
+    # -- BMS charges (scri/asymptotic_bondi_data/bms_charges.py); products of fields run through the fused kernel K9
+    def mass_aspect(self, truncate_ell=max):
+        """M = -Re{psi2 + sigma d/dt(bar sigma)} (bms_charges.py:14-47).  `truncate_ell`: a callable on (ell_max1, ell_max2)
+        as in spherical_functions' Modes.multiply (default `max`), an integer (every term truncated to it), or a false value
+        (the grid product with its default working band limit)."""
+        if callable(truncate_ell):
+            return -(self.psi2 + self.sigma.multiply(self.sigma.bar.dot, truncator=truncate_ell)).real
+        if truncate_ell:
+            return -(self.psi2.truncate_ell(truncate_ell) + self.sigma.multiply(self.sigma.bar.dot, truncator=lambda tup: truncate_ell)).real
+        return -(self.psi2 + self.sigma * self.sigma.bar.dot).real
+
+    @staticmethod
+    def charge_vector_from_aspect(charge):
+        """The ell <= 1 modes of a charge aspect as a four-vector (bms_charges.py:50-66)."""
+        charge = np.asarray(charge)
+        out = np.empty(charge.shape[:-1] + (4,))
+        out[..., 0] = charge[..., 0].real
+        out[..., 1] = (charge[..., 1] - charge[..., 3]).real / math.sqrt(6)
+        out[..., 2] = (charge[..., 1] + charge[..., 3]).imag / math.sqrt(6)
+        out[..., 3] = charge[..., 2].real / math.sqrt(3)
+        return out / math.sqrt(4 * math.pi)
 
     def bondi_four_momentum(self):
-        """ell < 2 part of the mass aspect as a four-vector (bms_charges.py:50-90)."""
-        c = self.mass_aspect().ndarray[:, :4]
-        out = np.empty((self.n_times, 4))
-        out[:, 0] = c[:, 0].real
-        out[:, 1] = (c[:, 1] - c[:, 3]).real / math.sqrt(6)
-        out[:, 2] = (c[:, 1] + c[:, 3]).imag / math.sqrt(6)
-        out[:, 3] = c[:, 2].real / math.sqrt(3)
-        return out / math.sqrt(4 * math.pi)
+        """ell < 2 part of the mass aspect as a four-vector (bms_charges.py:77-85)."""
+        return self.charge_vector_from_aspect(self.mass_aspect(1).ndarray)
 
     def bondi_rest_mass(self):
         p = self.bondi_four_momentum()
         return np.sqrt(p[:, 0] ** 2 - np.sum(p[:, 1:] ** 2, axis=1))
+
+    def _sigma_eth_sigma_bar(self, ell_max):
+        return self.sigma.multiply(self.sigma.bar.eth_GHP, truncator=lambda tup: ell_max)
+
+    def bondi_angular_momentum(self):
+        """Total Bondi angular momentum, the ell = 1 part of i (psi1 + sigma eth(bar sigma)) (bms_charges.py:88-100; Dray 1985 eq. 8)."""
+        aspect = 1j * (self.psi1.truncate_ell(1) + self._sigma_eth_sigma_bar(1)).ndarray
+        return self.charge_vector_from_aspect(aspect)[:, 1:]
+
+    def bondi_CoM_charge(self):
+        """G = N + t P = -[psi1 + sigma eth(bar sigma) + eth(sigma bar sigma)/2] (bms_charges.py:173-189)."""
+        aspect = -(self.psi1.truncate_ell(1) + self._sigma_eth_sigma_bar(1)
+                   + 0.5 * self.sigma.multiply(self.sigma.bar, truncator=lambda tup: 1).eth_GHP).ndarray
+        return self.charge_vector_from_aspect(aspect)[:, 1:]
+
+    def bondi_boost_charge(self):
+        """Bondi boost charge -[psi1 + sigma eth(bar sigma) + eth(sigma bar sigma)/2 - t eth Re{psi2 + sigma d/dt(bar sigma)}]
+        (bms_charges.py:154-170)."""
+        aspect = -(self.psi1.truncate_ell(1) + self._sigma_eth_sigma_bar(1)
+                   + 0.5 * self.sigma.multiply(self.sigma.bar, truncator=lambda tup: 1).eth_GHP
+                   - self.t * (self.psi2.truncate_ell(1) + self.sigma.multiply(self.sigma.bar.dot, truncator=lambda tup: 1)).real.eth_GHP).ndarray
+        return self.charge_vector_from_aspect(aspect)[:, 1:]
+
+    def bondi_dimensionless_spin(self):
+        """Dimensionless Bondi spin vector from the boost charge, the angular momentum and the four-momentum
+        (bms_charges.py:135-151)."""
+        N, J, P = self.bondi_boost_charge(), self.bondi_angular_momentum(), self.bondi_four_momentum()
+        M_sqr = (P[:, 0] ** 2 - np.sum(P[:, 1:] ** 2, axis=1))[:, None]
+        v = P[:, 1:] / P[:, :1]
+        v_norm = np.linalg.norm(v, axis=1)
+        vhat = v.copy()
+        moving = v_norm != 0
+        vhat[moving] = v[moving] / v_norm[moving, None]
+        gamma = (1 / np.sqrt(1 - v_norm**2))[:, None]
+        J_dot_vhat = np.einsum("ij,ij->i", J, vhat)[:, None]
+        return (gamma * (J + np.cross(v, N)) - (gamma - 1) * J_dot_vhat * vhat) / M_sqr
+
+    def supermomentum(self, supermomentum_def, **kwargs):
+        """Psi = psi2 + sigma d/dt(bar sigma) + f, with f = 0 ('Bondi-Sachs' / 'BS'), eth^2 bar sigma ('Moreschi' / 'M'),
+        (eth^2 bar sigma - ethbar^2 sigma)/2 ('Geroch' / 'G') or -ethbar^2 sigma ('Geroch-Winicour' / 'GW'); with
+        `integrated=True` the modes -bar(Psi) / (2 sqrt(pi)) (bms_charges.py:192-269; arXiv:1404.2475 eqs. 6-9).  Other
+        keywords go to `grid_multiply` (working_ell_max, output_ell_max)."""
+        integrated = kwargs.pop("integrated", False)
+        base = self.psi2 + self.sigma.grid_multiply(self.sigma.bar.dot, **kwargs)
+        kind = supermomentum_def.lower()
+        if kind in ("bondi-sachs", "bs"):
+            psi = base
+        elif kind in ("moreschi", "m"):
+            psi = base + self.sigma.bar.eth_GHP.eth_GHP
+        elif kind in ("geroch", "g"):
+            psi = base + 0.5 * (self.sigma.bar.eth_GHP.eth_GHP - self.sigma.ethbar_GHP.ethbar_GHP)
+        elif kind in ("geroch-winicour", "gw"):
+            psi = base - self.sigma.ethbar_GHP.ethbar_GHP
+        else:
+            raise ValueError(
+                f"Supermomentum defintion '{supermomentum_def}' not recognized. Please choose one of the following options:\n"
+                "  * 'Bondi-Sachs' or 'BS'\n  * 'Moreschi' or 'M'\n  * 'Geroch' or 'G'\n  * 'Geroch-Winicour' or 'GW'"
+            )
+        return -0.5 * psi.bar / math.sqrt(math.pi) if integrated else psi
 
     def transform(self, **kwargs):
         """BMS transformation of all six fields (scri/asymptotic_bondi_data/transformations.py:199-431)."""

@@ -887,3 +887,32 @@ def test_align_decomposition_frame_to_modes_and_slicing():
     assert Q.qmul(Q.qmul(inst.frame[0], xq), Q.qinverse(inst.frame[0]))[1] > 0      # x axis on the side of nHat = x
     back = w.copy().to_inertial_frame()
     assert rel(back.data, ref) < 1e-10
+
+
+def test_bms_charges_vs_3j_oracle():
+    """scri/asymptotic_bondi_data/bms_charges.py:77-269 on the GPU path (every product through the fused kernel K9) against the
+    oracle, whose products are the literal 3j sums of spherical_functions' Modes.multiply: four-momentum, angular momentum,
+    boost and centre-of-mass charges, dimensionless spin, the four supermomentum definitions."""
+    from oracle import abd_ref as A
+
+    mine, ref = _random_abd(ell_max=4, n_times=120, seed=61)
+    ref.data["psi2"][:, 0] += -10.0 * np.sqrt(4 * np.pi)         # a mass monopole: the four-momentum is timelike
+    mine.psi2 = ref.data["psi2"]
+    P, J, N, G = A.bms_charges(ref)
+    assert rel(mine.bondi_four_momentum(), P) < RTOL
+    assert rel(mine.bondi_angular_momentum(), J) < RTOL
+    assert rel(mine.bondi_boost_charge(), N) < 1e-11
+    assert rel(mine.bondi_CoM_charge(), G) < RTOL
+    M2 = (P[:, 0] ** 2 - np.sum(P[:, 1:] ** 2, axis=1))[:, None]
+    v = P[:, 1:] / P[:, :1]
+    vn = np.linalg.norm(v, axis=1)[:, None]
+    gam = 1 / np.sqrt(1 - vn**2)
+    chi = (gam * (J + np.cross(v, N)) - (gam - 1) * np.sum(J * v / vn, axis=1)[:, None] * v / vn) / M2
+    assert rel(mine.bondi_dimensionless_spin(), chi) < 1e-10
+    for kind, short in (("Bondi-Sachs", "bs"), ("Moreschi", "m"), ("G", "g"), ("geroch-winicour", "gw")):
+        assert rel(mine.supermomentum(kind).ndarray, A.supermomentum(ref, short)) < RTOL
+    assert rel(mine.supermomentum("M", integrated=True, working_ell_max=10).ndarray, A.supermomentum(ref, "m", working_ell_max=10, integrated=True)) < RTOL
+    with pytest.raises(ValueError):
+        mine.supermomentum("Bondi")
+    assert rel(mine.mass_aspect(3).ndarray, -A._real_part(ref.data["psi2"][:, :16] + A.sf.modes_multiply(
+        ref.data["sigma"], 2, 4, A.CubicSpline(ref.u, A.modes_bar(ref.data["sigma"], 2), axis=0).derivative()(ref.u), -2, 4, 3))) < RTOL
