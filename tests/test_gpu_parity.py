@@ -916,3 +916,20 @@ def test_bms_charges_vs_3j_oracle():
         mine.supermomentum("Bondi")
     assert rel(mine.mass_aspect(3).ndarray, -A._real_part(ref.data["psi2"][:, :16] + A.sf.modes_multiply(
         ref.data["sigma"], 2, 4, A.CubicSpline(ref.u, A.modes_bar(ref.data["sigma"], 2), axis=0).derivative()(ref.u), -2, 4, 3))) < RTOL
+
+
+@pytest.mark.parametrize("n_times", [7000, 9000])
+def test_transform_host_path_at_the_slab_thresholds(n_times):
+    """The host path of WaveformGrid.transform switches strategy with size: below 8 MB the modes go up in one piece, from
+    8 MB they stream in slabs, and from 8192 output times the tail is pipelined - the sizes around the switches against
+    the oracle on a window, and against the device-resident path bit for bit."""
+    t, data = smooth_modes(n_times=n_times, t0=0.0, t1=0.1 * n_times, seed=71)
+    out = modes(t, data).transform(**BMS)
+    plan = P.TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **BMS)
+    u, m = plan.run(ops.to_device(t), ops.to_device(data))
+    assert np.array_equal(out.t, u.cpu().numpy()) and np.array_equal(out.data, m.cpu().numpy())
+    lo, hi = n_times // 2 - 300, n_times // 2 + 300
+    ref = R.transform(R.Modes(t=t[lo:hi], data=data[lo:hi].copy()), **BMS)
+    sel = np.searchsorted(out.t, ref.t[100:-100])
+    assert np.array_equal(out.t[sel], ref.t[100:-100])
+    assert rel(out.data[sel], ref.data[100:-100]) < 1e-10        # the window's own spline ends are ~1e-11 away after 100 steps
