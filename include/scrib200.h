@@ -252,6 +252,23 @@ int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int 
  */
 int scrib200_h2d(void* dst_device, const void* src_host, size_t nbytes, void* stream);
 
+/* Integer stages of the RPXMB waveform codec (scri/utilities.py:194-407, called from scri/SpEC/file_io/corotating_paired_xor.py and
+ * rotating_paired_xor_multishuffle_bzip2.py), bit-exact:
+ *   scrib200_xor_timeseries: [n_rows, n_cols] 64-bit words, time along rows.  reverse = 0: out[i] = in[i] ^ in[i-1], row 0 kept
+ *   (xor_timeseries; out of place); reverse = 1: the prefix XOR that undoes it (xor_timeseries_reverse; in place allowed), workspace
+ *   of scrib200_xor_timeseries_workspace_bytes().
+ *   scrib200_fletcher32: acc2 (device, 2 x uint64) receives (c0, c1) of the Fletcher-32 checksum over n_words16 16-bit words, both
+ *   already reduced modulo 65535; the checksum is c1 << 16 | c0.
+ *   scrib200_multishuffle: `widths` (HOST int[n_widths], bits per piece from the highest significance down, summing to bit_width =
+ *   8 / 16 / 32 / 64); forward = 1 shuffles n elements into the bit stream "lowest piece of every element, next piece of every
+ *   element, ...", forward = 0 undoes it.  Out of place. */
+int scrib200_xor_timeseries(const void* in, void* out, int64_t n_rows, int64_t n_cols, int reverse, void* workspace,
+                            size_t workspace_bytes, void* stream);
+size_t scrib200_xor_timeseries_workspace_bytes(int64_t n_rows, int64_t n_cols);
+int scrib200_fletcher32(const void* data, int64_t n_words16, void* acc2, void* stream);
+int scrib200_multishuffle(const void* in, void* out, int64_t n, int bit_width, const int* widths, int n_widths, int forward,
+                          void* stream);
+
 /* HOST function (no device work, all pointers are host memory): rotor series with dR/dt = omega(t) R / 2, R(t[0]) = R0, on
  * the samples t - replaces quaternion.integrate_angular_velocity((t, omega), t0, t1, R0, tolerance) as
  * scri/mode_calculations.py:467 calls it.  Dormand-Prince 8(5,3) with the standard step controller (error norm < 1 against

@@ -32,6 +32,10 @@ SIGNATURES = {
     "scrib200_theta_synth": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "scrib200_theta_quad": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "scrib200_integrate_angular_velocity": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, ctypes.c_double, c_vp, c_vp]),
+    "scrib200_xor_timeseries": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "scrib200_xor_timeseries_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "scrib200_fletcher32": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "scrib200_multishuffle": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp]),
     "scrib200_h2d": (c_int, [c_vp, c_vp, c_sz, c_vp]),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),

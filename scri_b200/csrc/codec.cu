@@ -1,0 +1,211 @@
+// Integer stages of scri's RPXMB waveform codec: XOR of successive time steps, Fletcher-32 checksum and
+// the bit-level "multishuffle" - replaces scri/utilities.py:194-407 (numba loops) bit for bit.  All three are HBM-bound
+// integer / byte kernels: every element is read once and written once.
+#include "common.cuh"
+
+namespace scrib200 {
+
+// out[i, c] = in[i, c] ^ in[i-1, c] (row 0 unchanged): what remains of each sample once the bits shared with its predecessor are gone.
+__global__ void __launch_bounds__(256)
+xor_forward_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, int64_t n_rows, int64_t n_cols) {
+    const int64_t total = n_rows * n_cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = (e >= n_cols) ? (in[e] ^ in[e - n_cols]) : in[e];
+}
+
+// The inverse is a prefix XOR along time: chunk totals, an exclusive scan of the totals per column, then the rescan.
+constexpr int XOR_CHUNK = 256;
+__global__ void __launch_bounds__(128)
+xor_chunk_totals_kernel(const unsigned long long* __restrict__ in, int64_t n_rows, int64_t n_cols, unsigned long long* __restrict__ totals) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * XOR_CHUNK, r1 = min(n_rows, r0 + XOR_CHUNK);
+    unsigned long long x = 0;
+    for (int64_t r = r0; r < r1; ++r) x ^= in[r * n_cols + c];
+    totals[(int64_t)blockIdx.y * n_cols + c] = x;
+}
+__global__ void __launch_bounds__(128)
+xor_scan_totals_kernel(unsigned long long* __restrict__ totals, int64_t n_chunks, int64_t n_cols) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    unsigned long long run = 0;
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        const unsigned long long t = totals[k * n_cols + c];
+        totals[k * n_cols + c] = run;
+        run ^= t;
+    }
+}
+__global__ void __launch_bounds__(128)
+xor_rescan_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, int64_t n_rows, int64_t n_cols,
+                  const unsigned long long* __restrict__ totals) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * XOR_CHUNK, r1 = min(n_rows, r0 + XOR_CHUNK);
+    unsigned long long run = totals[(int64_t)blockIdx.y * n_cols + c];
+    for (int64_t r = r0; r < r1; ++r) {
+        run ^= in[r * n_cols + c];
+        out[r * n_cols + c] = run;
+    }
+}
+
+// Fletcher-32 over 16-bit words with modulus 65535: c0 = sum d_j, c1 = sum (size - j) d_j (each word enters every later
+// running sum once); the block-wise reductions of the reference only keep 32-bit accumulators from overflowing.
+__global__ void __launch_bounds__(256)
+fletcher32_kernel(const unsigned short* __restrict__ d, int64_t size, unsigned long long* __restrict__ acc) {
+    unsigned long long s0 = 0, s1 = 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < size; j += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = d[j];
+        s0 += v;
+        s1 += v * (unsigned long long)((size - j) % 65535);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, s0 % 65535ull);
+        atomicAdd(acc + 1, s1 % 65535ull);
+    }
+}
+
+struct ShuffleWidths {
+    int n;                      // pieces, lowest significance first (the reference walks its widths in reverse)
+    unsigned char width[64];
+    unsigned char shift[65];    // bits below piece i inside an element = sum of the widths before it
+};
+
+// forward: output word B holds bits [B bw, (B+1) bw) of the stream "piece 0 of every element, piece 1 of every element, ..."
+template <typename T>
+__global__ void __launch_bounds__(256)
+multishuffle_forward_kernel(const T* __restrict__ a, T* __restrict__ b, int64_t n, const ShuffleWidths w) {
+    constexpr int BW = 8 * sizeof(T);
+    for (int64_t B = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; B < n; B += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long p = (unsigned long long)B * BW;
+        int i = 0;
+        while (i + 1 < w.n && p >= (unsigned long long)n * w.shift[i + 1]) ++i;
+        unsigned long long word = 0;
+        int filled = 0;
+        while (filled < BW) {
+            const unsigned long long q = p - (unsigned long long)n * w.shift[i];
+            const int wi = w.width[i];
+            const unsigned long long e = q / wi;
+            const int r = (int)(q - e * wi);
+            const int take = min(wi - r, BW - filled);
+            const unsigned long long bits = ((unsigned long long)a[e] >> (w.shift[i] + r)) & ((take == 64) ? ~0ull : ((1ull << take) - 1ull));
+            word |= bits << filled;
+            filled += take;
+            p += take;
+            if (i + 1 < w.n && p >= (unsigned long long)n * w.shift[i + 1]) ++i;
+        }
+        b[B] = (T)word;
+    }
+}
+
+// reverse: element e collects piece i from bits [n S_i + e w_i, + w_i) of the stream (possibly straddling two words)
+template <typename T>
+__global__ void __launch_bounds__(256)
+multishuffle_reverse_kernel(const T* __restrict__ b, T* __restrict__ a, int64_t n, const ShuffleWidths w) {
+    constexpr int BW = 8 * sizeof(T);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long val = 0;
+        for (int i = 0; i < w.n; ++i) {
+            const int wi = w.width[i];
+            const unsigned long long p = (unsigned long long)n * w.shift[i] + (unsigned long long)e * wi;
+            const unsigned long long B = p / BW;
+            const int off = (int)(p - B * BW);
+            unsigned long long bits = (unsigned long long)b[B] >> off;
+            if (off + wi > BW) bits |= (unsigned long long)b[B + 1] << (BW - off);
+            bits &= (wi == 64) ? ~0ull : ((1ull << wi) - 1ull);
+            val |= bits << w.shift[i];
+        }
+        a[e] = (T)val;
+    }
+}
+
+static unsigned grid_for(int64_t n, int threads) {
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = 148 * 16;
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace scrib200
+
+extern "C" int scrib200_xor_timeseries(const void* in, void* out, int64_t n_rows, int64_t n_cols, int reverse, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(in && out, "xor_timeseries: null pointer");
+    if (n_rows <= 0 || n_cols <= 0) return SCRIB200_OK;
+    auto* src = reinterpret_cast<const unsigned long long*>(in);
+    auto* dst = reinterpret_cast<unsigned long long*>(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!reverse) {
+        SCRIB200_REQUIRE(in != out, "xor_timeseries: the forward transform is out of place");
+        xor_forward_kernel<<<grid_for(n_rows * n_cols, 256), 256, 0, st>>>(src, dst, n_rows, n_cols);
+        SCRIB200_CHECK_LAUNCH("xor_timeseries");
+        return SCRIB200_OK;
+    }
+    const int64_t n_chunks = (n_rows + XOR_CHUNK - 1) / XOR_CHUNK;
+    SCRIB200_REQUIRE(workspace && workspace_bytes >= (size_t)(n_chunks * n_cols) * 8, "xor_timeseries: workspace too small (%zu < %zu)",
+                     workspace_bytes, (size_t)(n_chunks * n_cols) * 8);
+    SCRIB200_REQUIRE(n_chunks <= 65535, "xor_timeseries: series too long (%lld rows)", (long long)n_rows);
+    auto* totals = reinterpret_cast<unsigned long long*>(workspace);
+    dim3 grid((unsigned)((n_cols + 127) / 128), (unsigned)n_chunks);
+    xor_chunk_totals_kernel<<<grid, 128, 0, st>>>(src, n_rows, n_cols, totals);
+    SCRIB200_CHECK_LAUNCH("xor_timeseries");
+    xor_scan_totals_kernel<<<grid.x, 128, 0, st>>>(totals, n_chunks, n_cols);
+    SCRIB200_CHECK_LAUNCH("xor_timeseries");
+    xor_rescan_kernel<<<grid, 128, 0, st>>>(src, dst, n_rows, n_cols, totals);
+    SCRIB200_CHECK_LAUNCH("xor_timeseries");
+    return SCRIB200_OK;
+}
+
+extern "C" size_t scrib200_xor_timeseries_workspace_bytes(int64_t n_rows, int64_t n_cols) {
+    return (size_t)(((n_rows + scrib200::XOR_CHUNK - 1) / scrib200::XOR_CHUNK) * n_cols) * 8 + 16;
+}
+
+extern "C" int scrib200_fletcher32(const void* data, int64_t n_words16, void* acc2, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(data && acc2, "fletcher32: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(acc2, 0, 16, st);
+    SCRIB200_REQUIRE(e == cudaSuccess, "fletcher32: %s", cudaGetErrorString(e));
+    if (n_words16 <= 0) return SCRIB200_OK;
+    fletcher32_kernel<<<grid_for(n_words16, 256), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(data), n_words16,
+                                                               reinterpret_cast<unsigned long long*>(acc2));
+    SCRIB200_CHECK_LAUNCH("fletcher32");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_multishuffle(const void* in, void* out, int64_t n, int bit_width, const int* widths, int n_widths, int forward,
+                                     void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(in && out && widths, "multishuffle: null pointer");
+    SCRIB200_REQUIRE(in != out, "multishuffle: out of place only");
+    SCRIB200_REQUIRE(bit_width == 8 || bit_width == 16 || bit_width == 32 || bit_width == 64, "multishuffle: Total bit width must be one of [8, 16, 32, 64], not %d", bit_width);
+    SCRIB200_REQUIRE(n_widths >= 1 && n_widths <= 64, "multishuffle: %d shuffle widths", n_widths);
+    ShuffleWidths w;
+    w.n = n_widths;
+    int sum = 0;
+    for (int i = 0; i < n_widths; ++i) {           // widths come highest significance first; the stream starts at the lowest
+        const int wi = widths[n_widths - 1 - i];
+        SCRIB200_REQUIRE(wi >= 1 && wi <= 64, "multishuffle: shuffle width %d", wi);
+        w.width[i] = (unsigned char)wi;
+        w.shift[i] = (unsigned char)sum;
+        sum += wi;
+    }
+    w.shift[n_widths] = (unsigned char)(sum > 255 ? 255 : sum);
+    SCRIB200_REQUIRE(sum == bit_width, "multishuffle: the shuffle widths sum to %d, not to the bit width %d", sum, bit_width);
+    if (n <= 0) return SCRIB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = grid_for(n, 256);
+#define SCRIB200_SHUFFLE(T)                                                                                                   \
+    if (forward) multishuffle_forward_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), n, w); \
+    else multishuffle_reverse_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), n, w);
+    if (bit_width == 8) { SCRIB200_SHUFFLE(unsigned char) }
+    else if (bit_width == 16) { SCRIB200_SHUFFLE(unsigned short) }
+    else if (bit_width == 32) { SCRIB200_SHUFFLE(unsigned int) }
+    else { SCRIB200_SHUFFLE(unsigned long long) }
+#undef SCRIB200_SHUFFLE
+    SCRIB200_CHECK_LAUNCH("multishuffle");
+    return SCRIB200_OK;
+}

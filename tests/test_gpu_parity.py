@@ -933,3 +933,40 @@ def test_transform_host_path_at_the_slab_thresholds(n_times):
     sel = np.searchsorted(out.t, ref.t[100:-100])
     assert np.array_equal(out.t[sel], ref.t[100:-100])
     assert rel(out.data[sel], ref.data[100:-100]) < 1e-10        # the window's own spline ends are ~1e-11 away after 100 steps
+
+
+@pytest.mark.parametrize("bit_width", [8, 16, 32, 64])
+def test_codec_stages_bit_exact(bit_width):
+    """scri/utilities.py:194-407 on the GPU (scri_b200.utilities) against the oracle, bit for bit: multishuffle and its inverse
+    for byte-wide, bit-wide and ragged piece widths and ragged lengths (the reference's tests/test_utilities.py:20-52, HDF5
+    known answer included), the XOR transform of a mode series and its inverse, Fletcher-32 at lengths around the block size."""
+    from oracle import utilities_ref as U
+    from scri_b200 import utilities as ut
+
+    dt = np.dtype(f"u{bit_width // 8}")
+    rng = np.random.default_rng(123)
+    for n in (1, 37, 5000):
+        data = rng.integers(0, 2**bit_width, size=n, dtype=dt, endpoint=False)
+        cases = [(1,) * bit_width, (8,) * (bit_width // 8), (bit_width,), tuple([3, 5] + [1] * (bit_width - 8))]
+        if bit_width == 64:
+            cases.append((8, 8, 4, 4, 4, 4) + (2,) * 8 + (1,) * 16)
+        for widths in cases:
+            sh = ut.multishuffle(widths)(data)
+            assert sh.dtype == dt and np.array_equal(sh, U.multishuffle(widths)(data)), (n, widths)
+            assert np.array_equal(ut.multishuffle(widths, forward=False)(sh), data), (n, widths)
+        assert np.array_equal(ut.multishuffle((8,) * (bit_width // 8))(data), data.view(np.uint8).reshape(n, bit_width // 8).T.ravel().view(dt))
+    with pytest.raises(ValueError):
+        ut.multishuffle((8, 4))
+    t, modes_ = smooth_modes(n_times=700 + bit_width, seed=81)
+    x = modes_.copy()
+    ref = U.xor_timeseries(modes_)
+    out = ut.xor_timeseries(x)
+    assert out is x and np.array_equal(x.view(np.uint64), ref.view(np.uint64))
+    back = ut.xor_timeseries_reverse(x)
+    assert np.array_equal(back.view(np.uint64), modes_.view(np.uint64))
+    tt = t.copy()
+    assert np.array_equal(ut.xor_timeseries(tt).view(np.uint64), U.xor_timeseries(t).view(np.uint64))     # 1-d series (w.t, corotating_paired_xor.py:88)
+    for n in (2, 359, 360, 361, 100_003):
+        d16 = rng.integers(0, 65536, size=n, dtype=np.uint16)
+        assert ut.fletcher32(d16) == U.fletcher32(d16), n
+    assert ut.fletcher32(modes_) == U.fletcher32(modes_)

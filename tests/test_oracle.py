@@ -322,3 +322,31 @@ def test_wigner_d_high_ell_against_60_digit_sum():
                 for m in range(-l, l + 1, max(1, l // 5)):
                     worst = max(worst, abs(sf.Wigner_D_element(Ra, Rb, l, mp_, m).real - d_exact(l, mp_, m, mp.mpf(beta))))
     assert worst < 1e-13
+
+
+@pytest.mark.parametrize("bit_width", [8, 16, 32, 64])
+def test_codec_oracle_pins(bit_width):
+    """oracle/utilities_ref.py against the reference's own known answers (tests/test_utilities.py:20-52): the multishuffle with
+    byte-wide pieces IS HDF5's byte shuffle (byte 0 of every element, byte 1 of every element, ...), every multishuffle is
+    reversible, the XOR transform is reversible, and Fletcher-32 equals the literal 32-bit loop."""
+    from oracle import utilities_ref as U
+
+    dt = np.dtype(f"u{bit_width // 8}")
+    rng = np.random.default_rng(1234)
+    data = rng.integers(0, 2**bit_width, size=500, dtype=dt, endpoint=False)
+    hdf5 = data.view(np.uint8).reshape(500, bit_width // 8).T.ravel().view(dt)
+    assert np.array_equal(U.multishuffle((8,) * (bit_width // 8))(data), hdf5)
+    for widths in [(1,) * bit_width, (8,) * (bit_width // 8), tuple([3, 5] + [1] * (bit_width - 8)), (bit_width,)]:
+        assert np.array_equal(U.multishuffle(widths, False)(U.multishuffle(widths)(data)), data), widths
+    x = rng.normal(size=(50, 6)) + 1j * rng.normal(size=(50, 6))
+    assert np.array_equal(U.xor_timeseries_reverse(U.xor_timeseries(x)).view(np.uint64), x.view(np.uint64))
+    assert np.array_equal(U.xor_timeseries(x)[0], x[0])
+    d16 = rng.integers(0, 65536, size=1000 + bit_width, dtype=np.uint16)
+    c0 = c1 = 0
+    for j0 in range(0, d16.size, 360):
+        for v in d16[j0 : j0 + 360]:
+            c0 = (c0 + int(v)) & 0xFFFFFFFF
+            c1 = (c1 + c0) & 0xFFFFFFFF
+        c0 %= 65535
+        c1 %= 65535
+    assert int(U.fletcher32(d16)) == ((c1 << 16) | c0)
