@@ -83,19 +83,26 @@ multishuffle_forward_kernel(const T* __restrict__ a, T* __restrict__ b, int64_t 
         unsigned long long p = (unsigned long long)B * BW;
         int i = 0;
         while (i + 1 < w.n && p >= (unsigned long long)n * w.shift[i + 1]) ++i;
+        // position inside piece i: element e, r bits of its piece already taken - one division here, none in the loop
+        const unsigned long long q = p - (unsigned long long)n * w.shift[i];
+        int wi = w.width[i];
+        unsigned long long e = q / wi;
+        int r = (int)(q - e * wi);
         unsigned long long word = 0;
         int filled = 0;
         while (filled < BW) {
-            const unsigned long long q = p - (unsigned long long)n * w.shift[i];
-            const int wi = w.width[i];
-            const unsigned long long e = q / wi;
-            const int r = (int)(q - e * wi);
             const int take = min(wi - r, BW - filled);
             const unsigned long long bits = ((unsigned long long)a[e] >> (w.shift[i] + r)) & ((take == 64) ? ~0ull : ((1ull << take) - 1ull));
             word |= bits << filled;
             filled += take;
-            p += take;
-            if (i + 1 < w.n && p >= (unsigned long long)n * w.shift[i + 1]) ++i;
+            r += take;
+            if (r == wi) {
+                r = 0;
+                if (++e == (unsigned long long)n) {      // piece i of every element is stored: the next piece starts over at element 0
+                    e = 0;
+                    if (++i < w.n) wi = w.width[i];
+                }
+            }
         }
         b[B] = (T)word;
     }
