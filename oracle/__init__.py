@@ -21,8 +21,13 @@ PARITY PINNING: the reference stores no golden vectors and cannot be imported in
 (quaternion / spherical_functions / spinsfast / sxs / h5py are absent, no network), so the
 oracle is pinned by porting the reference's own analytic tests (tests/test_oracle_*.py, each
 citing the reference test it ports) and by independent cross-checks (sympy Wigner-d / 3j / CG,
-scipy sph_harm_y).  Two behaviours stay "parity unpinned" against the real third-party code:
+scipy sph_harm_y).  Three behaviours stay "parity unpinned" against the real third-party code:
 (1) spinsfast.map2salm on input that is not band-limited below N_theta-2 (we restate the
 published H&W algorithm, theta-Nyquist weight taken once = Clenshaw-Curtis), and
-(2) bit-level rounding of spherical_functions' Wigner-D (we agree to ~1e-15, not bit-for-bit).
+(2) bit-level rounding of spherical_functions' Wigner-D (we agree to ~1e-15, not bit-for-bit), and
+(3) numpy-quaternion's squad / integrate_angular_velocity (step selection and rounding; the product restates the
+published algorithms and tests their defining properties - the reference's own corotating-frame bar is 1e-10).
+
+``oracle.utilities_ref`` restates the integer stages of the RPXMB codec (scri/utilities.py:194-407) and IS pinned: by the
+reference's known answer (multishuffle with byte-wide pieces == HDF5's byte shuffle) and by reversibility.
 """
