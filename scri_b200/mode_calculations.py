@@ -129,3 +129,13 @@ def minimal_rotation(R, t, iterations=2):
         Rgamma = np.stack([np.cos(halfgamma), 0 * halfgamma, 0 * halfgamma, np.sin(halfgamma)], axis=-1)
         R = Q.qmul(R, Rgamma)
     return R
+
+
+def rotor_angular_velocity(R, t):
+    """omega = 2 (dR/dt) R^-1 of a rotor series, dR/dt from cubic splines (quaternion.angular_velocity as called at
+    scri/rotations.py:42)."""
+    from scipy.interpolate import CubicSpline
+
+    R = np.asarray(R, dtype=float)
+    Rdot = CubicSpline(t, R).derivative()(t)
+    return (2 * Q.qmul(Rdot, Q.qconj(R)))[:, 1:]

@@ -71,33 +71,47 @@ def to_corotating_frame(W, R0=(1.0, 0.0, 0.0, 0.0), tolerance=1e-12, z_alignment
         log_frame = Q.qlog(frame)
         power_of_2 = 2 ** int(-np.floor(np.log2(2 * tolerance)))
         log_frame = np.round(log_frame * power_of_2) / power_of_2
-        frame = Q.qexp_vec(log_frame[..., 1:])
+        frame = Q.qexp(log_frame)
     W.rotate_decomposition_basis(frame)
     W.frameType = Corotating
     W.__history_depth__ -= 1
     W._append_history(f"{W}.to_corotating_frame({R0}, {tolerance}, {z_alignment_region}, {return_omega}, {truncate_log_frame})")
+    # the reference's four return shapes (scri/rotations.py:93-103); the RPXMB writers unpack `W, log_frame = ...`
     if return_omega:
+        if truncate_log_frame:
+            return (W, omega, log_frame)
         return (W, omega)
+    if truncate_log_frame:
+        return (W, log_frame)
     return W
 
 
 @waveform_alterations
-def to_coprecessing_frame(W, RoughDirection=np.array([0.0, 0.0, 1.0]), RoughDirectionIndex=None):
-    """Transform to a coprecessing frame via the dominant eigenvector of <LL> (scri/rotations.py:14-48)."""
-    from .mode_calculations import LLDominantEigenvector, minimal_rotation
+def to_coprecessing_frame(W, RoughDirection=np.array([0.0, 0.0, 1.0]), RoughDirectionIndex=None, transition_times=None):
+    """Transform to a coprecessing frame via the dominant eigenvector of <LL> (scri/rotations.py:14-48).  With
+    `transition_times` = (t_begin, t_end) the frame's angular velocity is switched off smoothly over that span and the
+    frame re-integrated from t_begin on, so that it stops turning through the ringdown (scri/rotations.py:40-45)."""
+    from .mode_calculations import LLDominantEigenvector, integrate_angular_velocity, minimal_rotation, rotor_angular_velocity
+    from .sample_waveforms import transition_function
 
     if RoughDirectionIndex is None:
         RoughDirectionIndex = W.n_times // 8
     dpa = LLDominantEigenvector(W, RoughDirection=RoughDirection, RoughDirectionIndex=RoughDirectionIndex)
-    # rotor taking z to dpa: sqrt(-dpa * z)
-    v = np.concatenate([np.zeros((dpa.shape[0], 1)), dpa], axis=1)
+    # rotor taking z to dpa: sqrt(-dpa * z), dpa normalised as the reference does
+    v = Q.qnormalized(np.concatenate([np.zeros((dpa.shape[0], 1)), dpa], axis=1))
     zq = np.array([0.0, 0.0, 0.0, 1.0])
     R = Q.qsqrt(-Q.qmul(v, zq))
     R = minimal_rotation(R, W.t, iterations=3)
+    if transition_times is not None:
+        i0, i1 = int(np.argmin(np.abs(W.t - transition_times[0]))), int(np.argmin(np.abs(W.t - transition_times[1])))
+        transition = transition_function(W.t[i0:], W.t[i0], W.t[i1], y0=1.0, y1=0.0)
+        omega = rotor_angular_velocity(R[i0:], W.t[i0:]) * transition[:, np.newaxis]
+        slowingR = integrate_angular_velocity(W.t[i0:], omega, R0=R[i0])
+        R = np.concatenate((R[:i0], slowingR))
     W.rotate_decomposition_basis(R)
     W.frameType = Coprecessing
     W.__history_depth__ -= 1
-    W._append_history(f"{W}.to_coprecessing_frame({RoughDirection}, {RoughDirectionIndex})")
+    W._append_history(f"{W}.to_coprecessing_frame({RoughDirection}, {RoughDirectionIndex}, {transition_times})")
     return W
 
 
