@@ -1,7 +1,7 @@
 """Dev tool (GPU): AsymptoticBondiData.transform at BASELINE config 4 size (ell_max = 32), wall time from host arrays."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import scri_b200 as sb
 from scri_inputs import real_supertranslation

@@ -1,7 +1,7 @@
 """Developer script: DMMA analysis kernel vs the scalar tiled kernel (same inputs), timing at config-2 size."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import scri_b200 as sb
 from scri_b200 import ops, plan as P

@@ -1,7 +1,7 @@
 """Dev tool (GPU): end-to-end transform time and a check of the streaming pipeline against the single-launch path."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import scri_b200 as sb
 from scri_b200 import ops, plan as P

@@ -1,7 +1,7 @@
 """Developer script: host-side timeline of the end-to-end transform (same steps as WaveformGrid.transform)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import bench
 import scri_b200 as sb

@@ -6,7 +6,7 @@ import torch
 import scri_b200 as sb
 from scri_b200 import ops, plan as P, _sf
 from oracle import scri_ref as R, quat, sf as osf, spinsfast as ospf
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from scri_inputs import real_supertranslation, smooth_modes, rotor_set
 
 def rel(a, b):

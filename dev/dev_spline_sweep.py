@@ -1,7 +1,7 @@
 """Developer script: spline_remap time at config-2 size against tile body / halo / CTA size."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import scri_b200 as sb
 from scri_b200 import ops, plan as P

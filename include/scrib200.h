@@ -75,7 +75,8 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *
  * scrib200_spline_prepare (once per time axis): the knots of all grid points are affine images of t, so the
  * tridiagonal moment system is factorised once, in t-units:
- *   tab  [n_times, 8]  (P, Q, Phi, c', W, Psi, h, 1/h) per row - consumed by scrib200_spline_remap / scrib200_spline_calculus
+ *   tab  [n_times, 8]  allocation (16-byte aligned); the first 6 n_times doubles hold (P, Q, Phi, c', W, Psi) per row, rows
+ *                      contiguous - consumed by scrib200_spline_remap / scrib200_spline_calculus (one bulk copy per tile)
  *   uprm [n_times]     u'_i = gamma_factor * (t_i - time_translation) (divide = 0, gamma_factor = 1/gamma: the
  *                      WaveformGrid arithmetic) or (t_i - time_translation) / gamma_factor (divide = 1, gamma_factor =
  *                      gamma: scri/asymptotic_bondi_data/transformations.py:393); may be NULL together with kconf/alpha
@@ -247,10 +248,17 @@ int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int 
 
 /* ---------------------------------------------------------------------------------------------
  * Host -> device copy of a pageable host array through the library's pinned staging ring (worker threads fill
- * chunk i+1 while the copy engine drains chunk i).  On return all of `src_host` has been read; the DMAs are ordered
- * on `stream`.  Page-locked sources are copied directly.
+ * chunk i+1 while the copy engine drains chunk i; the number of threads is this process's share of the cores in its CPU
+ * affinity mask, divided by LOCAL_WORLD_SIZE, override: SCRIB200_COPY_THREADS).  For a pageable source all of `src_host`
+ * has been read on return and the DMAs are ordered on `stream`.  A page-locked source (cudaHostAlloc, or
+ * scrib200_host_register) goes up in one asynchronous DMA: it must stay unchanged until `stream` reaches that point.
+ * scrib200_host_register / _unregister page-lock and release a caller's array in place (cudaHostRegister): worth it
+ * for arrays that are transferred more than once - replaces the reference's host-resident `w.data` as the operand of
+ * every transform (scri/waveform_grid.py:475).
  */
 int scrib200_h2d(void* dst_device, const void* src_host, size_t nbytes, void* stream);
+int scrib200_host_register(const void* host, size_t nbytes);
+int scrib200_host_unregister(const void* host);
 
 /* Integer stages of the RPXMB waveform codec (scri/utilities.py:194-407, called from scri/SpEC/file_io/corotating_paired_xor.py and
  * rotating_paired_xor_multishuffle_bzip2.py), bit-exact:
@@ -268,6 +276,16 @@ size_t scrib200_xor_timeseries_workspace_bytes(int64_t n_rows, int64_t n_cols);
 int scrib200_fletcher32(const void* data, int64_t n_words16, void* acc2, void* stream);
 int scrib200_multishuffle(const void* in, void* out, int64_t n, int bit_width, const int* widths, int n_widths, int forward,
                           void* stream);
+
+/* Floating-point stages of the same codec (scri/waveform_modes.py:457-476, 658-703), in place on modes [n_times, n_modes]
+ * complex128, n_modes = (ell_max+1)^2 - ell_min^2:
+ *   scrib200_conjugate_pairs: inverse = 0: convert_to_conjugate_pairs, f[l,m] <- (f[l,m] + conj f[l,-m]) / sqrt 2 and
+ *   f[l,-m] <- (f[l,m] - conj f[l,-m]) / sqrt 2 for m > 0; inverse = 1: convert_from_conjugate_pairs.  Bit-identical to numpy's
+ *   arithmetic (complex division by the real sqrt 2).
+ *   scrib200_truncate: WaveformModes.truncate with tol_per_mode = tol / sqrt(n_modes): each row is rounded to a multiple of
+ *   2^-floor(-log2(|row| tol_per_mode)) (round half to even).  n_complex = complex numbers per row. */
+int scrib200_conjugate_pairs(void* data, int64_t n_times, int ell_min, int ell_max, int inverse, void* stream);
+int scrib200_truncate(void* data, int64_t n_times, int n_complex, double tol_per_mode, void* stream);
 
 /* HOST function (no device work, all pointers are host memory): rotor series with dR/dt = omega(t) R / 2, R(t[0]) = R0, on
  * the samples t - replaces quaternion.integrate_angular_velocity((t, omega), t0, t1, R0, tolerance) as

@@ -36,7 +36,11 @@ SIGNATURES = {
     "scrib200_xor_timeseries_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "scrib200_fletcher32": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "scrib200_multishuffle": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp]),
+    "scrib200_conjugate_pairs": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "scrib200_truncate": (c_int, [c_vp, c_i64, c_int, ctypes.c_double, c_vp]),
     "scrib200_h2d": (c_int, [c_vp, c_vp, c_sz, c_vp]),
+    "scrib200_host_register": (c_int, [c_vp, c_sz]),
+    "scrib200_host_unregister": (c_int, [c_vp]),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "scrib200_spline_prepare": (c_int, [c_vp, c_i64, ctypes.c_double, c_int, ctypes.c_double, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),

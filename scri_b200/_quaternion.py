@@ -129,7 +129,11 @@ def qexp(q):
 
 def slerp(q1, q2, tau):
     """(q2 q1^-1)^tau q1 - the geodesic from q1 (tau = 0) to q2 (tau = 1); `tau` broadcasts against the leading axes."""
+    q1, q2 = np.asarray(q1, dtype=float), np.asarray(q2, dtype=float)
     tau = np.asarray(tau, dtype=float)[..., None]
+    # numpy-quaternion's slerp goes the short way round: -q2 stands in for q2 when the rotors are more than sqrt(2) apart
+    far = np.sum((q1 - q2) ** 2, axis=-1, keepdims=True) > 2.0
+    q2 = np.where(far, -q2, q2)
     return qmul(qexp(tau * qlog(qmul(q2, qinverse(q1)))), q1)
 
 
@@ -143,9 +147,8 @@ def squad(R_in, t_in, t_out):
       R(t)    = slerp( slerp(R_i, R_{i+1}, tau), slerp(A_i, B_{i+1}, tau), 2 tau (1 - tau) ),  tau = (t - t_i) / h_i,
 
     the series continued at both ends by reflection (R_{-1} = R_0 R_1^-1 R_0, ...), which makes A_0 = R_0 and A_{n-1} = B_{n-1} =
-    R_{n-1}.  Rotor arrays are float [..., 4] (w, x, y, z).  numpy-quaternion is not available here: parity with its
-    rounding is unpinned; the defining properties (the knots are reproduced, a uniformly rotating series stays on its
-    geodesic) are tested."""
+    R_{n-1}.  Rotor arrays are float [..., 4] (w, x, y, z).  Checked against the output of the reference's own
+    `interpolate` (tests/golden/reference_modes.npz, reference_frames.npz)."""
     R_in = as_float_quat(R_in)
     t_in = np.asarray(t_in, dtype=float)
     t_out = np.asarray(t_out, dtype=float)

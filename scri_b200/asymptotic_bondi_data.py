@@ -69,18 +69,38 @@ class ModesTimeSeries:
     def __array__(self, dtype=None, copy=None):
         return self.ndarray if dtype is None else self.ndarray.astype(dtype)
 
+    def _aligned(self, other):
+        """Both operands of a sum on a common ell range (sf.Modes zero-pads the shorter one); spin weights must agree."""
+        if not isinstance(other, ModesTimeSeries):
+            return self.ndarray, np.asarray(other), self
+        if other.spin_weight != self.spin_weight:
+            raise ValueError(f"Cannot add modes with different spin weights ({self.spin_weight} and {other.spin_weight})")
+        if other.ell_min != self.ell_min:
+            raise ValueError(f"Cannot add modes with different ell_min ({self.ell_min} and {other.ell_min})")
+        a, b = self.ndarray, other.ndarray
+        if a.shape[-1] == b.shape[-1]:
+            return a, b, self
+        wide, narrow = (self, other) if a.shape[-1] > b.shape[-1] else (other, self)
+        padded = np.zeros(wide.ndarray.shape, dtype=complex)
+        padded[..., : narrow.ndarray.shape[-1]] = narrow.ndarray
+        return (a, padded, wide) if wide is self else (padded, b, wide)
+
     def __add__(self, other):
-        return self._like(self.ndarray + np.asarray(other))
+        a, b, like = self._aligned(other)
+        return like._like(a + b, spin_weight=self.spin_weight)
+
+    __radd__ = __add__
 
     def __sub__(self, other):
-        return self._like(self.ndarray - np.asarray(other))
+        a, b, like = self._aligned(other)
+        return like._like(a - b, spin_weight=self.spin_weight)
 
     def __neg__(self):
         return self._like(-self.ndarray)
 
     def __mul__(self, scalar):
-        if isinstance(scalar, ModesTimeSeries):
-            return self.grid_multiply(scalar)
+        if isinstance(scalar, ModesTimeSeries):      # sf.Modes `a * b` is multiply() with the object's truncator
+            return self.multiply(scalar)
         if np.ndim(scalar) == 1 and np.shape(scalar)[0] == self.n_times:      # a function of time, e.g. `abd.t * field`
             scalar = np.asarray(scalar)[:, None]
         return self._like(self.ndarray * scalar)
@@ -223,6 +243,31 @@ class AsymptoticBondiData:
     def copy(self):
         return AsymptoticBondiData(self._time.copy(), self._ell_max, self.multiplication_truncator, self.frameType, self._raw_data.copy())
 
+    @property
+    def h(self):
+        """The strain h = 2 bar(sigma) as a WaveformModes from ell = 2 (scri/asymptotic_bondi_data/__init__.py:120-131)."""
+        from .constants import h as h_DataType
+        from .waveform_modes import WaveformModes
+
+        h_mts = 2.0 * self.sigma.bar
+        s = abs(h_mts.s)
+        return WaveformModes(t=h_mts.t, data=h_mts.ndarray[:, s * s :], ell_min=s, ell_max=h_mts.ell_max, frameType=Inertial,
+                             dataType=h_DataType, r_is_scaled_out=True, m_is_scaled_out=True)
+
+    def __getitem__(self, key):
+        """Time slices `abd[i1:i2]` / `abd[i]` sharing the storage (scri/asymptotic_bondi_data/__init__.py:179-208)."""
+        if not isinstance(key, (slice, int)):
+            raise ValueError(f"Invalid key `{key}` of type `{type(key)}`.")
+        if isinstance(key, int):
+            key = slice(key, key + 1 if key != -1 else None)
+        new = AsymptoticBondiData.__new__(AsymptoticBondiData)
+        new._time = self._time[key]
+        new._ell_max = self._ell_max
+        new.frameType = self.frameType
+        new.multiplication_truncator = self.multiplication_truncator
+        new._raw_data = self._raw_data[:, key, :]
+        return new
+
     def interpolate(self, new_times):
         new_times = np.asarray(new_times, dtype=float)
         raw = np.stack([self._get(name).interpolate(new_times).ndarray for name in FIELDS])
@@ -324,6 +369,27 @@ class AsymptoticBondiData:
 
 for _name in FIELDS:
     setattr(AsymptoticBondiData, _name, property(lambda self, _n=_name: self._get(_n), lambda self, v, _n=_name: self._set(_n, v)))
+
+
+def boosted_grid(frame_rotation, boost_velocity, n_theta, n_phi):
+    """Rotors R_jk [n_theta, n_phi, 4] taking the z axis to the direction, in the original frame, of grid point (j, k) of
+    the boosted and rotated frame (scri/asymptotic_bondi_data/transformations.py:100-147)."""
+    R, _ = boosted_rotor_grid(Q.as_float_quat(frame_rotation), np.asarray(boost_velocity, dtype=float), n_theta, n_phi)
+    return R.reshape(n_theta, n_phi, 4)
+
+
+def conformal_factors(boost_velocity, distorted_grid_rotors):
+    """k, eth(k)/k, 1/k and 1/k^3 on the grid, each [1, n_theta, n_phi] so that they broadcast against time
+    (scri/asymptotic_bondi_data/transformations.py:150-196)."""
+    v = np.asarray(boost_velocity, dtype=float)
+    R = np.asarray(distorted_grid_rotors, dtype=float)
+    gamma = 1 / math.sqrt(1 - np.dot(v, v))
+    v_dot_r = (Q.rotate_z(R.reshape(-1, 4)) @ v).reshape(R.shape[:-1])[np.newaxis]
+    c1, c0 = math.sqrt(2 * math.pi / 3), math.sqrt(4 * math.pi / 3)
+    v_modes = np.array([0.0, c1 * (v[0] + 1j * v[1]), c0 * v[2], c1 * (-v[0] + 1j * v[1])], dtype=complex)
+    eth_v_dot_r = (_sf.SWSH_grid(R.reshape(-1, 4), 1, 1) @ v_modes).reshape(R.shape[:-1])[np.newaxis]
+    one_over_k = gamma * (1 - v_dot_r)
+    return 1.0 / one_over_k, eth_v_dot_r / (1 - v_dot_r), one_over_k, one_over_k**3
 
 
 def _process_transformation_kwargs(input_ell_max, **kwargs):

@@ -129,6 +129,63 @@ multishuffle_reverse_kernel(const T* __restrict__ b, T* __restrict__ a, int64_t 
     }
 }
 
+// Conjugate-pair form of a mode series (scri/waveform_modes.py:658-703), in place.  Forward: for every (l, m > 0)
+//   f[l, m] <- (f[l, m] + conj f[l, -m]) / sqrt(2),  f[l, -m] <- (f[l, m] - conj f[l, -m]) / sqrt(2);
+// inverse:  f[l, m] <- (s + d) / sqrt(2),  f[l, -m] <- conj(s - d) / sqrt(2).
+// The reference divides a complex array by the real np.sqrt(2): numpy runs its complex division (Smith's algorithm) with a zero
+// imaginary divisor, i.e. re = (a_r + a_i * 0) * (1 / sqrt 2), im = (a_i - a_r * 0) * (1 / sqrt 2) - repeated here operation by
+// operation (no contraction) so the result is bit-identical, signed zeros included.
+__device__ __forceinline__ double2 np_div_by_real(double2 a, double scl) {
+    const double rat = 0.0;
+    return make_double2(__dmul_rn(__dadd_rn(a.x, __dmul_rn(a.y, rat)), scl), __dmul_rn(__dsub_rn(a.y, __dmul_rn(a.x, rat)), scl));
+}
+
+__global__ void __launch_bounds__(256)
+conjugate_pairs_kernel(double2* __restrict__ data, int64_t n_times, int n_modes, int ell_min, int ell_max, int n_pairs, int inverse) {
+    const double scl = __ddiv_rn(1.0, 1.4142135623730951);
+    const int64_t total = n_times * (int64_t)n_pairs;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / n_pairs;
+        int p = (int)(e - row * n_pairs);
+        // pairs are numbered ell by ell: ell contributes ell pairs; pairs below ell: ell(ell-1)/2 - ell_min(ell_min-1)/2
+        int ell = ell_min;
+        const int base = ell_min * (ell_min - 1) / 2;
+        while ((ell + 1) * ell / 2 - base <= p) ++ell;
+        const int m = p - (ell * (ell - 1) / 2 - base) + 1;
+        const int centre = ell * (ell + 1) - ell_min * ell_min;
+        double2* plus = data + row * n_modes + centre + m;
+        double2* minus = data + row * n_modes + centre - m;
+        const double2 a = *plus, b = *minus;
+        if (!inverse) {
+            const double2 bc = make_double2(b.x, -b.y);
+            *plus = np_div_by_real(make_double2(__dadd_rn(a.x, bc.x), __dadd_rn(a.y, bc.y)), scl);
+            *minus = np_div_by_real(make_double2(__dsub_rn(a.x, bc.x), __dsub_rn(a.y, bc.y)), scl);
+        } else {
+            *plus = np_div_by_real(make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)), scl);
+            *minus = np_div_by_real(make_double2(__dsub_rn(a.x, b.x), -__dsub_rn(a.y, b.y)), scl);
+        }
+    }
+}
+
+// scri/waveform_modes.py:457-476: every time step is rounded to a multiple of 2^-floor(-log2(|f(t)| tol_per_mode)).  One warp per
+// row: |f|^2 by a shuffle reduction, then data <- rint(data * p) / p (np.round rounds half to even; p is a power of two, so the
+// scalings are exact).  The row norm is summed in a different order than numpy's pairwise sum: the result can differ from the
+// reference only when |f| tol sits within an ulp of a power of two.  A zero row becomes NaN, as in the reference (0 * inf).
+__global__ void __launch_bounds__(256)
+truncate_kernel(double* __restrict__ data, int64_t n_times, int n_real, double tol_per_mode) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_times; row += warps) {
+        double* x = data + row * n_real;
+        double s = 0.0;
+        for (int c = lane; c < n_real; c += 32) s = fma(x[c], x[c], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double absolute_tolerance = __dmul_rn(sqrt(s), tol_per_mode);
+        const double p = exp2(floor(-log2(absolute_tolerance)));
+        for (int c = lane; c < n_real; c += 32) x[c] = __ddiv_rn(rint(__dmul_rn(x[c], p)), p);
+    }
+}
+
 static unsigned grid_for(int64_t n, int threads) {
     int64_t blocks = (n + threads - 1) / threads;
     const int64_t cap = 148 * 16;
@@ -214,5 +271,29 @@ extern "C" int scrib200_multishuffle(const void* in, void* out, int64_t n, int b
     else { SCRIB200_SHUFFLE(unsigned long long) }
 #undef SCRIB200_SHUFFLE
     SCRIB200_CHECK_LAUNCH("multishuffle");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_conjugate_pairs(void* data, int64_t n_times, int ell_min, int ell_max, int inverse, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(data, "conjugate_pairs: null pointer");
+    SCRIB200_REQUIRE(ell_min >= 0 && ell_max >= ell_min - 1, "conjugate_pairs: ell range [%d, %d]", ell_min, ell_max);
+    const int n_modes = (ell_max + 1) * (ell_max + 1) - ell_min * ell_min;
+    const int n_pairs = ell_max * (ell_max + 1) / 2 - ell_min * (ell_min - 1) / 2;
+    if (n_times <= 0 || n_pairs <= 0) return SCRIB200_OK;
+    conjugate_pairs_kernel<<<grid_for(n_times * n_pairs, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<double2*>(data), n_times, n_modes, ell_min, ell_max, n_pairs, inverse);
+    SCRIB200_CHECK_LAUNCH("conjugate_pairs");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_truncate(void* data, int64_t n_times, int n_complex, double tol_per_mode, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(data, "truncate: null pointer");
+    SCRIB200_REQUIRE(n_complex >= 0, "truncate: n_complex=%d", n_complex);
+    if (n_times <= 0 || n_complex == 0) return SCRIB200_OK;
+    truncate_kernel<<<grid_for(n_times * 32, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<double*>(data), n_times, 2 * n_complex,
+                                                                                 tol_per_mode);
+    SCRIB200_CHECK_LAUNCH("truncate");
     return SCRIB200_OK;
 }

@@ -35,13 +35,16 @@ int64_t scrib200_launch_count(void) { return scrib200::g_launches.load(std::memo
 // Host -> device staging for pageable host arrays (numpy memory).  A pageable cudaMemcpy runs at ~10 GB/s and
 // framework-level parallel copies fight with whatever thread pools the host process already spins (BLAS, OpenMP), so
 // the library owns the path: a ring of pinned staging buffers, a few plain memcpy worker threads filling chunk i+1
-// while the copy engine drains chunk i.  On return every byte of `src` has been read (the caller may reuse it); the
-// last DMAs are ordered on `stream` like any other asynchronous copy.
+// while the copy engine drains chunk i.  For pageable `src` every byte has been read on return (the caller may reuse
+// it) and the last DMAs are ordered on `stream`.  Page-locked `src` (cudaHostAlloc'd, or registered through
+// scrib200_host_register) is copied by a single asynchronous DMA instead: it must stay unchanged until `stream` has
+// passed this point, as for any cudaMemcpyAsync.
 #include <stdlib.h>
 
 #include <condition_variable>
 #include <mutex>
 #include <emmintrin.h>
+#include <sched.h>
 
 #include <thread>
 #include <vector>
@@ -162,7 +165,15 @@ extern "C" int scrib200_h2d(void* dst_device, const void* src_host, size_t nbyte
             cudaError_t e = cudaHostAlloc((void**)&S.buf[i], STAGE_BYTES, cudaHostAllocPortable);
             SCRIB200_REQUIRE(e == cudaSuccess, "h2d: cudaHostAlloc failed: %s", cudaGetErrorString(e));
         }
-        int workers = (int)std::thread::hardware_concurrency() - 1;
+        // copy threads: this process's share of the cores it may run on (its CPU affinity mask divided by the ranks of
+        // the node, LOCAL_WORLD_SIZE under torchrun) - eight ranks each spawning one thread per core of the whole host
+        // would oversubscribe it 8x; the calling thread is one of the copiers
+        int cores = (int)std::thread::hardware_concurrency();
+        cpu_set_t mask;
+        if (sched_getaffinity(0, sizeof(mask), &mask) == 0 && CPU_COUNT(&mask) > 0) cores = CPU_COUNT(&mask);
+        int ranks = 1;
+        if (const char* env = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(env) > 0 ? atoi(env) : 1;
+        int workers = cores / ranks - 1;
         if (const char* env = getenv("SCRIB200_COPY_THREADS")) workers = atoi(env) - 1;
         workers = workers < 0 ? 0 : (workers > 15 ? 15 : workers);
         S.pool = new CopyPool(workers);
@@ -170,7 +181,10 @@ extern "C" int scrib200_h2d(void* dst_device, const void* src_host, size_t nbyte
     }
     if (S.device != dev) {   // events belong to a device
         for (int i = 0; i < STAGE_BUFS; ++i) {
-            if (S.device >= 0) cudaEventDestroy(S.ev[i]);
+            if (S.device >= 0) {
+                if (S.used[i]) cudaEventSynchronize(S.ev[i]);   // a DMA of the previous device may still read this buffer
+                cudaEventDestroy(S.ev[i]);
+            }
             cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
             S.used[i] = false;
         }
@@ -191,6 +205,29 @@ extern "C" int scrib200_h2d(void* dst_device, const void* src_host, size_t nbyte
     return SCRIB200_OK;
 }
 
+
+// Page-lock a caller's array in place so that scrib200_h2d DMAs straight from it: no staging copy, no CPU work, and
+// none of the three host-DRAM crossings of the staged path.  Worth it for arrays that go up more than once (the frame-
+// fixing optimisers transform one waveform by many transformations); registering costs about as much as one staged copy.
+extern "C" int scrib200_host_register(const void* p, size_t nbytes) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(p && nbytes > 0, "host_register: null pointer");
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), nbytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return SCRIB200_OK;
+    }
+    SCRIB200_REQUIRE(e == cudaSuccess, "host_register: %s", cudaGetErrorString(e));
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_host_unregister(const void* p) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(p, "host_unregister: null pointer");
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
+    if (e != cudaSuccess) cudaGetLastError();      // not registered (any more): nothing to undo
+    return SCRIB200_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Host-side rotor integration dR/dt = omega(t) R / 2 (quaternion.integrate_angular_velocity as scri/mode_calculations.py:467

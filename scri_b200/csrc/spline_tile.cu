@@ -27,6 +27,7 @@
 //     read once, and evaluates the outputs that fall into its intervals with lanes running along the output index,
 //     so the stores into the time-tiled output are full 128-byte runs.  No workspace, F is never re-read from HBM
 //     (the halo rows of neighbouring tiles come from L2).
+#include <cuda.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -34,25 +35,19 @@
 
 namespace scrib200 {
 
-constexpr int ST_COLS = 16;            // real columns per CTA
-constexpr int ST_PITCH = ST_COLS + 2;  // doubles per shared-memory row (144 B: consecutive rows shift by 4 banks)
+constexpr int ST_COLS = 16;            // real columns per CTA (8 complex grid points: one 128-byte row segment)
+constexpr int ST_ROWD = 16;            // doubles per shared-memory row: the TMA box row, stored with the 128-byte swizzle
 constexpr int ST_BR = 16;              // rows per sweep block (global alignment)
-constexpr int ST_TAB = 8;              // doubles per table row in HBM: P, Q, Phi, c' | W, Psi, h, 1/h
-constexpr int ST_TAB6 = 6;             // the first six live in the sweep table in shared memory, (h, 1/h) in a compact array
+constexpr int ST_TAB6 = 6;             // doubles per row in use: P, Q, Phi, c', W, Psi  (tab[i * 6 + f], rows contiguous)
 constexpr int FACTOR_RUNIN = 40;
 constexpr int ST_MAXBLK = 24;          // max sweep blocks per tile (384 threads)
 
-__device__ __forceinline__ void st_cp_async16(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void st_cp_async8(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void st_cp_async_commit_wait() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+__device__ __forceinline__ unsigned st_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Shared-memory position (in doubles) of real column c of tile row `rrel` under the TMA 128-byte swizzle: the 16-byte
+// chunk index of a row is XORed with the row index modulo 8, so the 16-byte gathers of the evaluation (one chunk, many
+// rows) and the row-wise sweeps (one row, all chunks) are both bank-conflict free on a dense 128-byte pitch.
+__device__ __forceinline__ int st_idx(int rrel, int c) { return rrel * ST_ROWD + ((((c >> 1) ^ (rrel & 7)) << 1) | (c & 1)); }
 
 // Row r (1 <= r <= N-2) of the moment system in t-units, not-a-knot conditions eliminated into rows 1 and N-2.
 __device__ __forceinline__ void nak_row(const double* __restrict__ t, int N, int r, double& sub, double& diag, double& sup,
@@ -74,7 +69,7 @@ __device__ __forceinline__ void nak_row(const double* __restrict__ t, int N, int
     }
 }
 
-// tab[i] = (P, Q, W, 1/h_i | Phi, c', Psi, h_i) for rows 1..N-2 (row 0 carries h_0, 1/h_0; row N-1 zeros); also
+// tab[i] = (P, Q, Phi, c', W, Psi) for rows 1..N-2 (rows 0 and N-1 zeros), six doubles per row, rows contiguous; also
 // u'_i = inv_gamma (t_i - tt) and the retained output block [lo, hi) = { i : umin <= u'_i <= umax }
 // (waveform_grid.py:564-568), umin/umax reduced here from k (t_0 - alpha), k (t_{N-1} - alpha) over the G grid points.
 __global__ void __launch_bounds__(256)
@@ -123,12 +118,7 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
         }
     }
     if (i >= N) return;
-    double row[ST_TAB] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (i <= N - 2) {
-        const double h = t[i + 1] - t[i];
-        row[6] = h;
-        row[7] = 1.0 / h;
-    }
+    double row[ST_TAB6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (i >= 1 && i <= N - 2) {
         const int bstart = (i & ~(ST_BR - 1)) > 1 ? (i & ~(ST_BR - 1)) : 1;
         const int bend = ((i | (ST_BR - 1)) < N - 2) ? (i | (ST_BR - 1)) : N - 2;
@@ -153,9 +143,10 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
         row[2] = phi;
         row[5] = psi;
     }
-    double4* dst = reinterpret_cast<double4*>(tab + (size_t)i * ST_TAB);
-    dst[0] = make_double4(row[0], row[1], row[2], row[3]);
-    dst[1] = make_double4(row[4], row[5], row[6], row[7]);
+    double2* dst = reinterpret_cast<double2*>(tab + (size_t)i * ST_TAB6);
+    dst[0] = make_double2(row[0], row[1]);
+    dst[1] = make_double2(row[2], row[3]);
+    dst[2] = make_double2(row[4], row[5]);
 }
 
 __global__ void spline_info_init_kernel(double* __restrict__ info, double n) {
@@ -171,8 +162,8 @@ spline_decay_kernel(const double* __restrict__ tab, int N, double* __restrict__ 
     if (i >= 64 && i <= N - 2) {
         double pw = 1.0, pc = 1.0;
         for (int r = i; r > i - 64; --r) {
-            pw *= fabs(tab[(size_t)r * ST_TAB + 4]);
-            pc *= fabs(tab[(size_t)r * ST_TAB + 3]);
+            pw *= fabs(tab[(size_t)r * ST_TAB6 + 4]);
+            pc *= fabs(tab[(size_t)r * ST_TAB6 + 3]);
             if (r == i - 31) d32 = fmax(pw, pc);
         }
         d64 = fmax(pw, pc);
@@ -232,133 +223,170 @@ spline_tile_flags_kernel(const int* __restrict__ J, int ntiles, int G, int ncg, 
 // MODE 4: the increment of the second antiderivative, `up` then holding the (scanned) first antiderivative [N, G].
 // For MODE >= 1 `out` is [N, G] complex time-major and Nout/tshift are unused.
 // blockDim.x >= 16 * (body + 2 halo) / 16 (one half-warp per sweep block), body and halo multiples of 16.
+//
+// Staging: the F rows of the tile arrive as two TMA boxes (`tmF`: F viewed as a [rows, 2G] FP64 tensor, box = 16 columns x
+// box_rows rows, 128-byte swizzle, columns / rows beyond the tensor zero-filled by the hardware) and the table rows as one
+// bulk copy, all completing on one mbarrier: no LSU instructions and no shared-memory store wavefronts are spent on
+// staging (the cp.async version of this kernel spent 40 % of its shared-memory cycles and 25 % of its instructions there).
 template <int MODE, int MAXT>
 __global__ void __launch_bounds__(MAXT, 2)
-spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict__ F, int G,
+spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __restrict__ t, int N, int G,
                    const double* __restrict__ kconf, const double* __restrict__ alpha,
                    const double* __restrict__ tab, const double* __restrict__ up, int Nout,
                    double* __restrict__ out, int tshift, int body, int halo, const int* __restrict__ J,
-                   const int* __restrict__ flags) {
-    if (MODE == 0 && flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // no output time falls in this tile
-    extern __shared__ __align__(16) double s_mem[];
-    __shared__ double s_k[ST_COLS / 2], s_al[ST_COLS / 2], s_ik[ST_COLS / 2];
-    __shared__ int s_jlo[ST_COLS / 2], s_jhi[ST_COLS / 2];
+                   const int* __restrict__ flags, int box_rows) {
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (MODE == 0 && flags[by * gridDim.x + bx] == 0) return;   // no output time falls in this tile
+    extern __shared__ unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int G2 = 2 * G;
-    const int col0 = blockIdx.x * ST_COLS;                  // first real column of this CTA
-    const int a = blockIdx.y * body;                        // intervals a .. b-1, knots a .. b
+    const int col0 = bx * ST_COLS;                          // first real column of this CTA
+    const int a = by * body;                                // intervals a .. b-1, knots a .. b
     const int b = (a + body < N - 1) ? a + body : N - 1;
     const bool last_tile = (b == N - 1);
     const int slo = (a - halo > 1) ? a - halo : 1;          // rows slo .. shi are swept
     const int shi = (b + halo - 1 < N - 2) ? b + halo - 1 : N - 2;
-    const int ylo = slo - 1, yhi = shi + 1;                 // rows resident in shared memory
-    const int nyrows = yhi - ylo + 1;
-    const int ymax = body + 2 * halo + 2;
+    const int ylo = slo - 1, yhi = shi + 1;                 // rows the tile needs
+    const int ybase = ylo & ~7;                             // row held by shared-memory row 0: keeps (r - ybase) & 7 == r & 7
+    const int nrows = 2 * box_rows;                         // shared-memory rows (>= yhi - ybase + 1)
     const int qlo = slo / ST_BR, qhi = shi / ST_BR;         // sweep blocks of this tile
-
-    double* sY = s_mem;                                     // [ymax][ST_PITCH]  F            row r -> r - ylo
-    double* sD = sY + (size_t)ymax * ST_PITCH;              // [ymax][ST_PITCH]  d0, m0, M    row r -> r - ylo
-    double* sTab = sD + (size_t)ymax * ST_PITCH;            // [ymax][ST_TAB6] P, Q, Phi, c', W, Psi   row r -> r - ylo
-    double2* sH = reinterpret_cast<double2*>(sTab + (size_t)ymax * ST_TAB6);   // [ymax] (h, 1/h): consecutive rows are
-                                                            //          contiguous, so the evaluation's gathers are conflict free
-    double* sT = reinterpret_cast<double*>(sH + ymax);      // [ymax]                         row r -> r - ylo
     const int nblk_max = (body + 2 * halo) / ST_BR;
-    double* sEdgeD = sT + ymax + (ymax & 1);                // [nblk_max][ST_COLS] d0 at the block ends
-    double* sEdgeM = sEdgeD + nblk_max * ST_COLS;           // [nblk_max][ST_COLS] m0 at the block starts
-#define SY(r_, c_) sY[((r_) - ylo) * ST_PITCH + (c_)]
-#define SD(r_, c_) sD[((r_) - ylo) * ST_PITCH + (c_)]
-#define STAB(r_, f_) sTab[((r_) - ylo) * ST_TAB6 + (f_)]
-#define SH(r_) sH[(r_) - ylo]
-#define STT(r_) sT[(r_) - ylo]
 
-    // ---- stage the tile: F rows (16-byte copies, 8 per row), the factor table rows and the sample times
-    {
-        const int ch = tid & 7;
-        const bool colok = col0 + 2 * ch < G2;
-        const double* src = F + ((size_t)blockIdx.z * N + ylo) * G2 + col0 + 2 * ch;   // blockIdx.z: series of a batch
-        for (int rr = tid >> 3; rr < nyrows; rr += nthr >> 3) {
-            double* dst = sY + rr * ST_PITCH + 2 * ch;
-            if (colok) {
-                st_cp_async16(dst, src + (size_t)rr * G2);
-            } else {
-                dst[0] = 0.0;
-                dst[1] = 0.0;
-            }
-        }
-        const double* tsrc = tab + (size_t)ylo * ST_TAB;
-        for (int e = tid; e < nyrows * (ST_TAB / 2); e += nthr) {
-            const int rr = e >> 2, ch = e & 3;             // chunks 0..2 -> sweep table, chunk 3 -> (h, 1/h)
-            if (ch < 3) st_cp_async16(sTab + rr * ST_TAB6 + 2 * ch, tsrc + 2 * e);
-            else st_cp_async16(sH + rr, tsrc + 2 * e);
-        }
-        for (int e = tid; e < nyrows; e += nthr) st_cp_async8(sT + e, t + ylo + e);
+    double* sY = reinterpret_cast<double*>(s_raw + ((1024u - (st_smem_u32(s_raw) & 1023u)) & 1023u));   // [nrows][16] F (swizzled)
+    double* sD = sY + (size_t)nrows * ST_ROWD;              // [nrows][16] moments M (same layout)
+    double* sTab = sD + (size_t)nrows * ST_ROWD;            // [nrows][6]  P, Q, Phi, c', W, Psi     row r -> r - ybase
+    double* sT = sTab + (size_t)nrows * ST_TAB6;            // [nrows]     sample times
+    double* sEdgeD = sT + nrows;                            // [nblk_max][ST_COLS] d0 at the block ends
+    double* sEdgeM = sEdgeD + nblk_max * ST_COLS;           // [nblk_max][ST_COLS] m0 at the block starts
+    // per-column constants of the evaluation, addressed from one register-held base
+    double* s_k = sEdgeM + nblk_max * ST_COLS;              // [8] conformal factor
+    double* s_al = s_k + ST_COLS / 2;                       // [8] supertranslation
+    double* s_xa = s_al + ST_COLS / 2;                      // [8] abscissa of the tile's first knot
+    float* s_slope = reinterpret_cast<float*>(s_xa + ST_COLS / 2);   // [8] intervals per unit of x
+    int* s_jlo = reinterpret_cast<int*>(s_slope + ST_COLS / 2);      // [8] first output of the column in this tile
+    int* s_jhi = s_jlo + ST_COLS / 2;                       // [8] one past the last
+    int* s_nch = s_jhi + ST_COLS / 2;                       // [8] chunks of 32 outputs
+#define SY(r_, c_) sY[st_idx((r_) - ybase, (c_))]
+#define SD(r_, c_) sD[st_idx((r_) - ybase, (c_))]
+#define STAB(r_, f_) sTab[((r_) - ybase) * ST_TAB6 + (f_)]
+#define STT(r_) sT[(r_) - ybase]
+
+    // ---- stage the tile: thread 0 arms the barrier and issues the three asynchronous copies
+    if (tid == 0) {
+        const unsigned mb = st_smem_u32(&s_mbar);
+        const int trows = ((yhi < N - 1) ? yhi : N - 1) - ybase + 1;
+        const unsigned tab_bytes = (unsigned)trows * ST_TAB6 * (unsigned)sizeof(double);
+        const unsigned box_bytes = (unsigned)box_rows * ST_ROWD * (unsigned)sizeof(double);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * box_bytes + tab_bytes) : "memory");
+        const int row0 = bz * N + ybase;                    // bz: series of a batch, stacked along the rows
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                    st_smem_u32(sY) + h2 * box_bytes),
+                "l"(&tmF), "r"(col0), "r"(row0 + h2 * box_rows), "r"(mb)
+                : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem_u32(sTab)),
+                     "l"(tab + (size_t)ybase * ST_TAB6), "r"(tab_bytes), "r"(mb)
+                     : "memory");
     }
+    for (int e = tid; e <= yhi - ybase; e += nthr) sT[e] = t[ybase + e];
     // per-column constants and (MODE 0) the output range of each complex column, found while the copies fly
-    if (tid < ST_COLS) {
-        const int c = tid >> 1, which = tid & 1;
-        const int g = blockIdx.x * (ST_COLS / 2) + c;
-        const double k = (MODE == 0 && g < G) ? kconf[g] : 1.0, al = (MODE == 0 && g < G) ? alpha[g] : 0.0;
-        if (which == 0) {
-            s_k[c] = k;
-            s_al[c] = al;
-            s_ik[c] = 1.0 / k;
+    if (tid < ST_COLS / 2) {
+        const int c = tid;
+        const int g = bx * (ST_COLS / 2) + c;
+        const bool ok = (MODE == 0 && g < G);
+        const double k = ok ? kconf[g] : 1.0, al = ok ? alpha[g] : 0.0;
+        s_k[c] = k;
+        s_al[c] = al;
+        int jlo = 0, jhi = 0;
+        if (ok) {                                           // interval guess of the evaluation: i ~ a + (u - x_a) * slope
+            const double xa = __dmul_rn(k, __dsub_rn(t[a], al));
+            const double xbv = __dmul_rn(k, __dsub_rn(t[b], al));
+            s_xa[c] = xa;
+            s_slope[c] = (float)((double)(b - a) / (xbv - xa));
+            jlo = J[(size_t)by * G + g];
+            jhi = J[(size_t)(by + 1) * G + g];
         }
-        if (MODE == 0 && g < G) {
-            if (which == 0) s_jlo[c] = J[(size_t)blockIdx.y * G + g]; else s_jhi[c] = J[(size_t)(blockIdx.y + 1) * G + g];
-        }
+        s_jlo[c] = jlo;
+        s_jhi[c] = jhi;
+        s_nch[c] = (jhi - jlo + 31) >> 5;                   // chunks of 32 outputs
     }
-    st_cp_async_commit_wait();
     __syncthreads();
 
-    // ---- sweeps: half-warp = 16 real columns of one block of 16 rows
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    // (MODE 0) evaluation work: chunks of 32 consecutive outputs of one column, dealt to the warps round robin.  (ec, el) =
+    // (column, chunk inside the column) of my current chunk; its output times are fetched one chunk ahead.
+    int ec = 0, el = warp;
+    double u_next = 0.0;
+    if (MODE == 0) {
+        while (ec < ST_COLS / 2 && el >= s_nch[ec]) el -= s_nch[ec++];
+        if (ec < ST_COLS / 2) {
+            const int jn = s_jlo[ec] + (el << 5) + lane;
+            if (jn < s_jhi[ec]) u_next = up[jn];
+        }
+    }
+    {   // the tile has landed?
+        unsigned ok = 0;
+        const unsigned mb = st_smem_u32(&s_mbar);
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb) : "memory");
+    }
+
+    // ---- sweeps: half-warp = 16 real columns of one block of 16 rows; the block's d / m values stay in registers from the
+    // forward sweep to the final store (one shared-memory load and one store per element)
     const int cc = tid & (ST_COLS - 1);
     const int q = qlo + tid / ST_COLS;
     const bool active = (q <= qhi);
-    const int r0 = (q * ST_BR > slo) ? q * ST_BR : slo;
-    const int r1 = (q * ST_BR + ST_BR - 1 < shi) ? q * ST_BR + ST_BR - 1 : shi;
-    // (MODE 0) the first output times of my column are fetched now, so their latency hides behind the sweeps
-    constexpr int UPRE = 8;
-    double upre[UPRE];
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    // evaluation work items: (complex column, part of its output range); with >= 16 warps a column is split in two
-    const int nsplit = (nwarp >= ST_COLS) ? 2 : 1;
-    auto item_range = [&](int item, int& c, int& j0, int& j1) {
-        c = item % (ST_COLS / 2);
-        const int part = item / (ST_COLS / 2);
-        const int jlo = s_jlo[c], jhi = s_jhi[c];
-        const int chunk = (((jhi - jlo + nsplit - 1) / nsplit) + 31) & ~31;
-        j0 = jlo + part * chunk;
-        j1 = (j0 + chunk < jhi) ? j0 + chunk : jhi;
-    };
-    if (MODE == 0 && warp < nsplit * (ST_COLS / 2) && blockIdx.x * (ST_COLS / 2) + warp % (ST_COLS / 2) < G) {
-        int c, j0, j1;
-        item_range(warp, c, j0, j1);
+    const int qbase = q * ST_BR;
+    const int r0 = (qbase > slo) ? qbase : slo;
+    const int r1 = (qbase + ST_BR - 1 < shi) ? qbase + ST_BR - 1 : shi;
+    const bool full = active && r0 == qbase && r1 == qbase + ST_BR - 1;   // all but the blocks at the ends of the series
+    // row qbase + k, my column: qbase - ybase is a multiple of 8, so the swizzle phase of step k is the constant k & 7
+    const int rb = qbase - ybase;
+    const int c2 = cc >> 1, c1 = cc & 1;
+    const double* yq = sY + rb * ST_ROWD + c1;
+    double* mq = sD + rb * ST_ROWD + c1;
+    const double* tq = sTab + rb * ST_TAB6;
+#define YQ(k_) yq[(k_) * ST_ROWD + ((c2 ^ ((k_) & 7)) << 1)]
+#define MQ(k_) mq[(k_) * ST_ROWD + ((c2 ^ ((k_) & 7)) << 1)]
+#define TQ2(k_, f_) (*reinterpret_cast<const double2*>(tq + (k_) * ST_TAB6 + (f_)))
+    double dreg[ST_BR];
+    if (full) {                                             // forward from a zero start
+        double yc = YQ(0);
+        double dym = yc - YQ(-1);
+        double d = 0.0;
 #pragma unroll
-        for (int it = 0; it < UPRE; ++it) {
-            const int j = j0 + lane + 32 * it;
-            upre[it] = (j < j1) ? up[j] : 0.0;
+        for (int k = 0; k < ST_BR; ++k) {
+            const double yn = YQ(k + 1);
+            const double dy = yn - yc;
+            const double2 pq = TQ2(k, 0);
+            d = fma(-tq[k * ST_TAB6 + 4], d, pq.x * dy - pq.y * dym);
+            dreg[k] = d;
+            yc = yn;
+            dym = dy;
         }
-    }
-    const bool full = active && (r1 - r0 == ST_BR - 1);     // all but the blocks at the ends of the series
-    if (active) {                                           // forward from a zero start
+        sEdgeD[(q - qlo) * ST_COLS + cc] = d;
+    } else if (active) {
         double yc = SY(r0, cc);
         double dym = yc - SY(r0 - 1, cc);
         double d = 0.0;
-        auto step = [&](int r) {
-            const double yn = SY(r + 1, cc);
-            const double dy = yn - yc;
-            const double2 pq = *reinterpret_cast<const double2*>(&STAB(r, 0));
-            d = fma(-STAB(r, 4), d, pq.x * dy - pq.y * dym);
-            SD(r, cc) = d;
-            yc = yn;
-            dym = dy;
-        };
-        if (full) {
-#pragma unroll 8
-            for (int k = 0; k < ST_BR; ++k) step(r0 + k);
-        } else {
-            for (int r = r0; r <= r1; ++r) step(r);
+#pragma unroll
+        for (int k = 0; k < ST_BR; ++k) {
+            dreg[k] = 0.0;
+            if (qbase + k >= r0 && qbase + k <= r1) {
+                const double yn = YQ(k + 1);
+                const double dy = yn - yc;
+                const double2 pq = TQ2(k, 0);
+                d = fma(-tq[k * ST_TAB6 + 4], d, pq.x * dy - pq.y * dym);
+                dreg[k] = d;
+                yc = yn;
+                dym = dy;
+            }
         }
         sEdgeD[(q - qlo) * ST_COLS + cc] = d;
     }
@@ -371,18 +399,22 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
             w *= STAB(p * ST_BR + ST_BR - 1, 2);
             if (fabs(w) < 1e-24) break;
         }
-        double m = 0.0;
-        auto step = [&](int r) {                            // backward from a zero start, on the corrected d
-            const double2 pc = *reinterpret_cast<const double2*>(&STAB(r, 2));
-            const double d = fma(pc.x, D, SD(r, cc));
-            m = fma(-pc.y, m, d);
-            SD(r, cc) = m;
-        };
+        double m = 0.0;                                     // backward from a zero start, on the corrected d
         if (full) {
-#pragma unroll 8
-            for (int k = ST_BR - 1; k >= 0; --k) step(r0 + k);
+#pragma unroll
+            for (int k = ST_BR - 1; k >= 0; --k) {
+                const double2 pc = TQ2(k, 2);
+                m = fma(-pc.y, m, fma(pc.x, D, dreg[k]));
+                dreg[k] = m;
+            }
         } else {
-            for (int r = r1; r >= r0; --r) step(r);
+#pragma unroll
+            for (int k = ST_BR - 1; k >= 0; --k)
+                if (qbase + k >= r0 && qbase + k <= r1) {
+                    const double2 pc = TQ2(k, 2);
+                    m = fma(-pc.y, m, fma(pc.x, D, dreg[k]));
+                    dreg[k] = m;
+                }
         }
         sEdgeM[(q - qlo) * ST_COLS + cc] = m;               // m0 at my block start
     }
@@ -394,15 +426,18 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
             w *= STAB(p * ST_BR, 5);
             if (fabs(w) < 1e-24) break;
         }
-        if (E != 0.0) {
-            if (full) {
+        if (full) {
 #pragma unroll
-                for (int k = 0; k < ST_BR; ++k) SD(r0 + k, cc) = fma(STAB(r0 + k, 5), E, SD(r0 + k, cc));
-            } else {
-                for (int r = r0; r <= r1; ++r) SD(r, cc) = fma(STAB(r, 5), E, SD(r, cc));
-            }
+            for (int k = 0; k < ST_BR; ++k) MQ(k) = fma(tq[k * ST_TAB6 + 5], E, dreg[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ST_BR; ++k)
+                if (qbase + k >= r0 && qbase + k <= r1) MQ(k) = fma(tq[k * ST_TAB6 + 5], E, dreg[k]);
         }
     }
+#undef YQ
+#undef MQ
+#undef TQ2
     __syncthreads();
     // end moments from the not-a-knot conditions
     if (a == 0 && tid < ST_COLS) {
@@ -420,78 +455,78 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
     if (MODE == 0) {
         double2* o2 = reinterpret_cast<double2*>(out);
         const int tmask = (1 << tshift) - 1;
-        const int64_t tileGT = (int64_t)G << tshift;
-        for (int item = warp; item < nsplit * (ST_COLS / 2); item += nwarp) {
-            int c, jlo, jhi;
-            item_range(item, c, jlo, jhi);
-            const int g = blockIdx.x * (ST_COLS / 2) + c;
-            if (g >= G) continue;
-            const double k = s_k[c], al = s_al[c], ik = s_ik[c];
-            const double xa = __dmul_rn(k, __dsub_rn(STT(a), al));
-            const double xbv = __dmul_rn(k, __dsub_rn(STT(b), al));
-            const float slope = (float)((double)(b - a) / (xbv - xa));
-            double2* og = o2 + ((tshift > 0) ? ((int64_t)g << tshift) : (int64_t)g);
-            auto eval_one = [&](int j, double u) {
-                int i = a + __float2int_rd((float)(u - xa) * slope);    // guess, verified below
-                i = max(a, min(i, b - 1));
-                double xi = __dmul_rn(k, __dsub_rn(STT(i), al));
-                double xi1 = __dmul_rn(k, __dsub_rn(STT(i + 1), al));
-                if (!((xi <= u || i == a) && (u < xi1 || i == b - 1))) {
-                    int lo_s = a, hi_s = b - 1;             // largest i in [a, b-1] with x_i <= u (a if none)
-                    while (lo_s < hi_s) {
-                        const int mid = (lo_s + hi_s + 1) >> 1;
-                        if (__dmul_rn(k, __dsub_rn(STT(mid), al)) <= u) lo_s = mid; else hi_s = mid - 1;
-                    }
-                    i = lo_s;
-                    xi = __dmul_rn(k, __dsub_rn(STT(i), al));
-                    xi1 = __dmul_rn(k, __dsub_rn(STT(i + 1), al));
-                }
-                const double2 hh = SH(i);
-                const double ht = hh.x;
-                const double hx = xi1 - xi;
-                // 1/hx: hx = k h_t up to the rounding of the abscissae, so two Newton steps from (1/k)(1/h_t) are exact to
-                // rounding; a true division only if the abscissae have lost more than 3 digits of the step
-                double inv_h = ik * hh.y;
-                double e = fma(-hx, inv_h, 1.0);
-                if (fabs(e) < 1e-3) {
-                    inv_h = fma(inv_h, e, inv_h);
-                    e = fma(-hx, inv_h, 1.0);
-                    inv_h = fma(inv_h, e, inv_h);
-                } else {
-                    inv_h = 1.0 / hx;
-                }
-                const double A = (xi1 - u) * inv_h;
-                const double B = (u - xi) * inv_h;
-                const double h26 = ht * ht * (1.0 / 6.0);
-                const double ca = (A * A * A - A) * h26;
-                const double cb = (B * B * B - B) * h26;
-                const double2 yi = *reinterpret_cast<const double2*>(&SY(i, 2 * c));
-                const double2 yi1 = *reinterpret_cast<const double2*>(&SY(i + 1, 2 * c));
-                const double2 Mi = *reinterpret_cast<const double2*>(&SD(i, 2 * c));
-                const double2 Mi1 = *reinterpret_cast<const double2*>(&SD(i + 1, 2 * c));
-                double2 r;
-                r.x = A * yi.x + B * yi1.x + (ca * Mi.x + cb * Mi1.x);
-                r.y = A * yi.y + B * yi1.y + (ca * Mi.y + cb * Mi1.y);
-                const int64_t jg = (int64_t)blockIdx.z * Nout + j;       // output row across the batch
-                const int64_t o = (tshift > 0) ? (jg >> tshift) * tileGT + (jg & tmask) : jg * G;
-                og[o] = r;
-            };
-            int j = jlo + lane;
-            if (item == warp) {                             // the prefetched output times
-#pragma unroll
-                for (int it = 0; it < UPRE; ++it, j += 32)
-                    if (j < jhi) eval_one(j, upre[it]);
+        const int64_t jbase = (int64_t)bz * Nout;           // output rows of this series across the batch
+        while (ec < ST_COLS / 2) {
+            const int c = ec;
+            const int j1 = s_jhi[c];
+            const int j = s_jlo[c] + (el << 5) + lane;
+            const double u = u_next;
+            el += nwarp;                                    // my next chunk, and its output times
+            while (ec < ST_COLS / 2 && el >= s_nch[ec]) el -= s_nch[ec++];
+            if (ec < ST_COLS / 2) {
+                const int jn = s_jlo[ec] + (el << 5) + lane;
+                if (jn < s_jhi[ec]) u_next = up[jn];
             }
-            for (; j < jhi; j += 32) eval_one(j, up[j]);
+            if (j >= j1) continue;
+            const double k = s_k[c], al = s_al[c];
+            int i = a + __float2int_rd((float)(u - s_xa[c]) * s_slope[c]);    // guess, verified below
+            i = max(a, min(i, b - 1));
+            double ti = STT(i), ti1 = STT(i + 1);
+            double xi = __dmul_rn(k, __dsub_rn(ti, al));
+            double xi1 = __dmul_rn(k, __dsub_rn(ti1, al));
+            if (!((xi <= u || i == a) && (u < xi1 || i == b - 1))) {
+                int lo_s = a, hi_s = b - 1;                 // largest i in [a, b-1] with x_i <= u (a if none)
+                while (lo_s < hi_s) {
+                    const int mid = (lo_s + hi_s + 1) >> 1;
+                    if (__dmul_rn(k, __dsub_rn(STT(mid), al)) <= u) lo_s = mid; else hi_s = mid - 1;
+                }
+                i = lo_s;
+                ti = STT(i);
+                ti1 = STT(i + 1);
+                xi = __dmul_rn(k, __dsub_rn(ti, al));
+                xi1 = __dmul_rn(k, __dsub_rn(ti1, al));
+            }
+            const double ht = ti1 - ti;                     // h_i as the table formed it (same subtraction)
+            const double hx = xi1 - xi;
+            // 1/hx: two Newton steps from a single-precision reciprocal are exact to rounding; a true division only when
+            // the step leaves the single-precision range
+            float seed;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)hx));
+            double inv_h = (double)seed;
+            double e = fma(-hx, inv_h, 1.0);
+            if (fabs(e) < 1e-3) {
+                inv_h = fma(inv_h, e, inv_h);
+                e = fma(-hx, inv_h, 1.0);
+                inv_h = fma(inv_h, e, inv_h);
+            } else {
+                inv_h = 1.0 / hx;
+            }
+            const double A = (xi1 - u) * inv_h;
+            const double B = (u - xi) * inv_h;
+            const double h26 = ht * ht * (1.0 / 6.0);
+            const double ca = (A * A * A - A) * h26;
+            const double cb = (B * B * B - B) * h26;
+            const int ir = i - ybase;
+            const int o0 = ir * ST_ROWD + ((c ^ (ir & 7)) << 1), o1 = (ir + 1) * ST_ROWD + ((c ^ ((ir + 1) & 7)) << 1);
+            const double2 yi = *reinterpret_cast<const double2*>(sY + o0);
+            const double2 yi1 = *reinterpret_cast<const double2*>(sY + o1);
+            const double2 Mi = *reinterpret_cast<const double2*>(sD + o0);
+            const double2 Mi1 = *reinterpret_cast<const double2*>(sD + o1);
+            double2 r;
+            r.x = A * yi.x + B * yi1.x + (ca * Mi.x + cb * Mi1.x);
+            r.y = A * yi.y + B * yi1.y + (ca * Mi.y + cb * Mi1.y);
+            const int g = bx * (ST_COLS / 2) + c;
+            const int64_t jg = jbase + j;
+            o2[(((jg >> tshift) * G + g) << tshift) + (jg & tmask)] = r;    // [rows / tile, G, tile]; tile = 1: time-major
         }
     } else {
         // one thread per (knot, real column): 128-byte row segments of the time-major output
         const int rstep = nthr / ST_COLS;
         const bool colok = col0 + cc < G2;
-        out += (size_t)blockIdx.z * N * G2;
-        if (MODE == 4) up += (size_t)blockIdx.z * N * G2;
+        out += (size_t)bz * N * G2;
+        if (MODE == 4) up += (size_t)bz * N * G2;
         for (int i = a + tid / ST_COLS; i < b; i += rstep) {
-            const double ht = SH(i).x;
+            const double ht = STT(i + 1) - STT(i);
             const double yi = SY(i, cc), yi1 = SY(i + 1, cc);
             const double Mi = SD(i, cc), Mi1 = SD(i + 1, cc);
             if (!colok) continue;
@@ -518,7 +553,6 @@ spline_tile_kernel(const double* __restrict__ t, int N, const double* __restrict
 #undef SY
 #undef SD
 #undef STAB
-#undef SH
 #undef STT
 }
 
@@ -584,15 +618,35 @@ static int launch_column_scan(double* x, int64_t N, int C, cudaStream_t st) {
     return SCRIB200_OK;
 }
 
+static int tile_box_rows(int body, int halo) {
+    const int ymax = body + 2 * halo + 2;                    // rows a tile needs; + 7 for the 8-row alignment of its first row
+    return (((ymax + 7 + 1) / 2) + 7) & ~7;
+}
+
 static size_t tile_smem_bytes(int body, int halo) {
-    const size_t ymax = (size_t)body + 2 * halo + 2;
+    const size_t nrows = 2 * (size_t)tile_box_rows(body, halo);
     const size_t nblk = ((size_t)body + 2 * halo) / ST_BR;
-    return (2 * ymax * ST_PITCH + ymax * ST_TAB + ymax + (ymax & 1) + 2 * nblk * ST_COLS) * sizeof(double);
+    return (2 * nrows * ST_ROWD + nrows * ST_TAB6 + nrows + 2 * nblk * ST_COLS + 5 * ST_COLS) * sizeof(double) + 1024;   // + constants, alignment slack
 }
 
 static void resolve_tile(int& halo, int& body) {
     if (halo <= 0) halo = 32;
     if (body <= 0) body = (halo <= 32) ? 240 : (halo <= 64 ? 176 : 128);   // two CTAs per SM up to halo = 64
+}
+
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+    }
+    return fn;
 }
 
 template <int MODE>
@@ -604,20 +658,31 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     SCRIB200_REQUIRE(halo % ST_BR == 0 && body % ST_BR == 0, "%s: body=%d and halo=%d must be multiples of %d", name, body, halo, ST_BR);
     const size_t smem = tile_smem_bytes(body, halo);
     const int nblk = (body + 2 * halo) / ST_BR;
-    SCRIB200_REQUIRE(nblk <= ST_MAXBLK && smem <= 220 * 1024, "%s: body=%d halo=%d does not fit one CTA", name, body, halo);
+    const int box_rows = tile_box_rows(body, halo);
+    SCRIB200_REQUIRE(nblk <= ST_MAXBLK && smem <= 220 * 1024 && box_rows <= 256, "%s: body=%d halo=%d does not fit one CTA", name, body, halo);
     const int64_t ntiles = (n_times - 1 + body - 1) / body;
     SCRIB200_REQUIRE(ntiles <= 65535, "%s: too many time tiles (%lld); raise `body`", name, (long long)ntiles);
-    int threads = ((nblk * ST_COLS + 31) / 32) * 32;         // one half-warp per sweep block
-    bool wide = false;
-    if (MODE == 0 && getenv("SCRIB200_SPLINE_WIDE") != nullptr) {   // 16 warps: two warps share a column in the evaluation
-        threads = 512;
-        wide = true;
+    SCRIB200_REQUIRE(n_series >= 1 && n_series <= 65535 && (int64_t)n_series * n_times < (int64_t)2147483000,
+                     "%s: n_series=%d (x %lld rows) out of range", name, n_series, (long long)n_times);
+    // F as a [n_series * n_times, 2G] FP64 tensor; box = one tile half: 16 columns x box_rows rows, 128-byte swizzle
+    TensorMapEncodeTiledFn encode = tensor_map_encoder();
+    SCRIB200_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from this driver", name);
+    CUtensorMap tmF;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)(2 * (int64_t)G), (cuuint64_t)((int64_t)n_series * n_times)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)(2 * (int64_t)G) * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)ST_COLS, (cuuint32_t)box_rows};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(F), gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SCRIB200_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (%d) for a [%lld, %d] grid array", name, (int)r,
+                         (long long)n_series * n_times, 2 * G);
     }
-    if (smem > 48 * 1024) {
-        if (wide) cudaFuncSetAttribute(spline_tile_kernel<MODE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else cudaFuncSetAttribute(spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    SCRIB200_REQUIRE(n_series >= 1 && n_series <= 65535, "%s: n_series=%d must be 1..65535", name, n_series);
+    const int threads = ((nblk * ST_COLS + 31) / 32) * 32;   // one half-warp per sweep block
+    const bool small = threads <= 320;                       // default tiles (19 blocks): 102 registers per thread at 2 CTAs / SM
+    if (small) cudaFuncSetAttribute(spline_tile_kernel<MODE, 320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles, (unsigned)n_series);
     int* J = nullptr;
     int* flags = nullptr;
@@ -634,12 +699,12 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
         spline_tile_flags_kernel<<<(unsigned)((nflags + 255) / 256), 256, 0, (cudaStream_t)stream>>>(J, (int)ntiles, G, (int)grid.x, flags);
         SCRIB200_CHECK_LAUNCH(name);
     }
-    if (wide)
-        spline_tile_kernel<MODE, 512><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags);
+    if (small)
+        spline_tile_kernel<MODE, 320><<<grid, threads, smem, (cudaStream_t)stream>>>(
+            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows);
     else
         spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            t, (int)n_times, F, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags);
+            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }

@@ -75,6 +75,51 @@ def to_device_async(x, dtype=None):
 
 _copy_streams = {}
 
+# Arrays that go up more than once are page-locked in place on their second trip (scrib200_host_register), after which
+# scrib200_h2d DMAs straight from them; a finalizer releases the registration when the array dies.  One-shot callers
+# never pay for a registration.
+_seen_hosts = {}          # (address, nbytes) -> trips so far (small: pruned as the arrays die)
+_registered = {}          # (address, nbytes) -> finalizer
+REGISTER_MIN_BYTES = 8 << 20
+REGISTER_MAX_BYTES = 8 << 30
+
+
+def _maybe_register(a):
+    """Count this trip of host array `a`; page-lock it when it has been up before.  Returns True if `a` is page-locked."""
+    import weakref
+
+    if a.nbytes < REGISTER_MIN_BYTES or not a.flags.c_contiguous:
+        return False
+    key = (a.ctypes.data, a.nbytes)
+    if key in _registered:
+        return True
+    trips = _seen_hosts.get(key, 0)
+    owner = a if a.base is None else a.base
+    if trips == 0:
+        _seen_hosts[key] = 1
+        try:
+            weakref.finalize(owner, _seen_hosts.pop, key, None)
+        except TypeError:          # owner does not support weak references: never register it
+            _seen_hosts.pop(key, None)
+        return False
+    if sum(k[1] for k in _registered) + a.nbytes > REGISTER_MAX_BYTES:
+        return False
+    lib = _lib.load()
+    if lib.scrib200_host_register(a.ctypes.data, a.nbytes) != 0:
+        return False
+
+    def release(ptr=a.ctypes.data, k=key):
+        _registered.pop(k, None)
+        try:
+            _torch().cuda.synchronize()            # no DMA may still be reading the pages
+            lib.scrib200_host_unregister(ptr)
+        except Exception:
+            pass
+
+    _registered[key] = weakref.finalize(owner, release)
+    return True
+
+
 
 def to_device_slabs(x, dtype=None, n_slabs=4):
     """Start copying a large host array to the device in `n_slabs` row slabs on a dedicated copy stream (helper thread,
@@ -87,6 +132,7 @@ def to_device_slabs(x, dtype=None, n_slabs=4):
     if dtype is not None and a.dtype != dtype:
         a = a.astype(dtype)
     N = a.shape[0]
+    _maybe_register(a)
     dev = torch.cuda.current_device()
     if dev not in _copy_streams:
         _copy_streams[dev] = torch.cuda.Stream()
@@ -457,6 +503,26 @@ def norm(data):
     out = torch.empty(d.shape[0], dtype=torch.float64, device="cuda")
     _lib.check(lib.scrib200_norm(_lib.ptr(d), d.shape[0], d.shape[1], _lib.ptr(out), _lib.stream_ptr()), "norm")
     return out if is_tensor(data) else to_host(out)
+
+
+def conjugate_pairs(data, ell_min, ell_max, inverse=False):
+    """Mode data [n_times, n_modes] to / from conjugate-pair form (scri/waveform_modes.py:658-703); returns a new array
+    (a tensor for tensor input, modified in place)."""
+    lib = _lib.load()
+    d = to_device(data, np.complex128)
+    _lib.check(lib.scrib200_conjugate_pairs(_lib.ptr(d), d.shape[0], int(ell_min), int(ell_max), int(bool(inverse)), _lib.stream_ptr()),
+               "conjugate_pairs")
+    return d if is_tensor(data) else to_host(d)
+
+
+def truncate(data, tol_per_mode):
+    """Round every time step of [n_times, ...] complex data to a multiple of 2^-floor(-log2(|row| tol_per_mode))
+    (scri/waveform_modes.py:457-476)."""
+    lib = _lib.load()
+    d = to_device(data, np.complex128)
+    n_complex = int(np.prod(d.shape[1:]))
+    _lib.check(lib.scrib200_truncate(_lib.ptr(d), d.shape[0], n_complex, float(tol_per_mode), _lib.stream_ptr()), "truncate")
+    return d if is_tensor(data) else to_host(d)
 
 
 def _ones_zeros(n):

@@ -283,6 +283,8 @@ class GridPlan:
             out = torch.empty((-(-rows // tile), self.G, tile), dtype=torch.complex128, device=self.device)
         else:
             out = torch.empty((rows, self.G), dtype=torch.complex128, device=self.device)
+        if rows == 0:          # no output time inside the span every grid point covers: an empty result, as in the reference
+            return out
         halo, body = prep.halo_body(self.spline_halo, self.spline_body)
         need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
         if self._ws is None or self._ws.numel() < need:
@@ -542,6 +544,8 @@ class TransformPlan(GridPlan):
     def analyze(self, grid):
         """[N', G] complex128 -> [N', n_modes_out] (waveform_grid.py:303-307).  Large band limits take the separable
         tensor-core analysis (phi-DFT GEMM + scrib200_theta_quad), the rest the shared-memory kernels."""
+        if grid.shape[0] == 0:
+            return self.torch.empty((0, self.n_modes_out), dtype=self.torch.complex128, device=self.device)
         if self.out_ell_max >= 16:
             from . import ops
 
@@ -560,6 +564,8 @@ class TransformPlan(GridPlan):
         torch = self.torch
         lib = _lib.load()
         out = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, device=self.device)
+        if n_out == 0:
+            return out
         _lib.check(
             lib.scrib200_map2salm_tiled(
                 _lib.ptr(gridT), self.tile, n_out, self.n_theta, self.n_phi, _lib.ptr(self.d_trig), _lib.ptr(self.d_Wt),
@@ -638,6 +644,7 @@ class TransformPlan(GridPlan):
         done = 0
         for k, (rlo, rhi, ev, flag) in enumerate(slabs):
             flag.wait()
+            _trace(f"slab {k} queued on the copy stream")
             cur.wait_event(ev)
             if rhi > rlo:
                 _lib.check(
@@ -659,7 +666,9 @@ class TransformPlan(GridPlan):
                 modes.record_stream(cs)
                 del gridT, modes
                 done = out_hi
+        _trace("all launches queued")
         cs.synchronize()
+        _trace("last result slab landed")
         return uprm, host.numpy()
 
     def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None):
@@ -693,6 +702,62 @@ class TransformPlan(GridPlan):
         if return_grid:
             return uprm, grid
         return uprm, self.analyze(grid)
+
+
+TRACE = None        # dev aid: set to a list to collect (label, perf_counter) marks of the end-to-end pipeline
+
+
+def _trace(label):
+    if TRACE is not None:
+        import time
+
+        TRACE.append((label, time.perf_counter()))
+
+
+_plan_cache = {}
+PLAN_CACHE_SIZE = 8
+
+
+def _kwargs_key(kwargs):
+    """Hashable identity of a set of transformation keywords, or None when one of them is not plain numbers (the
+    psi*_modes companions of psi0..psi3 carry whole waveforms: such plans are built per call)."""
+    items = []
+    for k in sorted(kwargs):
+        v = kwargs[k]
+        if hasattr(v, "components") and not isinstance(v, np.ndarray):      # np.quaternion
+            v = np.asarray(v.components, dtype=float)
+        if isinstance(v, (bool, int, float, complex, np.number)):
+            items.append((k, type(v).__name__, complex(v)))
+            continue
+        try:
+            a = np.asarray(v)
+        except Exception:
+            return None
+        if a.dtype.kind not in "biufc":
+            return None
+        items.append((k, a.dtype.str, a.shape, a.tobytes()))
+    return tuple(items)
+
+
+def cached_transform_plan(ell_min, ell_max, dataType, r_is_scaled_out=True, out_ell_max=None, **kwargs):
+    """TransformPlan for this waveform layout and transformation, reused when the same transformation was planned
+    before (the device tables depend on nothing else).  The plan's host algebra - rotor grid, SWSH tables of the
+    supertranslation, conformal factor: ~2 ms of small numpy calls, what scri/waveform_grid.py:431-474 redoes on every
+    call - is then off the critical path of every call after the first; a small LRU keeps the last few transformations."""
+    torch = _lib.require_cuda()
+    key = _kwargs_key(kwargs)
+    if key is not None:
+        key = (int(ell_min), int(ell_max), int(dataType), bool(r_is_scaled_out), out_ell_max, torch.cuda.current_device(), key)
+        plan = _plan_cache.pop(key, None)
+        if plan is not None:
+            _plan_cache[key] = plan            # most recently used last
+            return plan
+    plan = TransformPlan(ell_min, ell_max, dataType, r_is_scaled_out=r_is_scaled_out, out_ell_max=out_ell_max, **kwargs)
+    if key is not None and not plan.mix and not plan.leftover_kwargs:
+        _plan_cache[key] = plan
+        while len(_plan_cache) > PLAN_CACHE_SIZE:
+            _plan_cache.pop(next(iter(_plan_cache)))
+    return plan
 
 
 def _run_batch(self, t, data_batch, prep=None):

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib, _sf, ops
 from .constants import Inertial, SpinWeights
-from .plan import TransformPlan
+from .plan import TransformPlan, cached_transform_plan
 from .waveform_base import WaveformBase
 from .waveform_modes import WaveformModes
 
@@ -94,7 +94,7 @@ class WaveformGrid(WaveformBase):
         original_kwargs = kwargs.copy()
         a_fut = ops.to_device_async(w_modes.data, np.complex128)   # streams in while the plan is built
         try:
-            plan = TransformPlan(
+            plan = cached_transform_plan(
                 w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out, **kwargs
             )
         finally:
@@ -135,7 +135,7 @@ class WaveformGrid(WaveformBase):
         else:
             a_d, slabs, a_fut = ops.to_device(w_modes.data, np.complex128), None, None
         try:
-            plan = TransformPlan(
+            plan = cached_transform_plan(
                 w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out,
                 out_ell_max=ell_max, **kwargs,
             )

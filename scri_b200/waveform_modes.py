@@ -136,6 +136,34 @@ class WaveformModes(WaveformBase):
         """Spin-lowered mode data (scri/waveform_modes.py:569-572)."""
         return self.apply_eth(operations="-")
 
+    @waveform_alterations
+    def truncate(self, tol=1e-10):
+        """Zero the bits of `data` that typically contribute less than `tol` times the norm at that instant, in place
+        (scri/waveform_modes.py:457-476): tol is spread over the modes as tol / sqrt(n_modes)."""
+        from . import ops
+
+        if tol != 0.0:
+            tol_per_mode = tol / np.sqrt(self.n_modes)
+            self.data = ops.truncate(self.data, tol_per_mode)
+        self._append_history(f"{self}.truncate(tol={tol})")
+
+    @waveform_alterations
+    def convert_to_conjugate_pairs(self):
+        """Store s[l,m] = (f[l,m] + conj f[l,-m]) / sqrt 2 at m > 0 and d[l,m] = (f[l,m] - conj f[l,-m]) / sqrt 2 at -m, in
+        place (scri/waveform_modes.py:658-686)."""
+        from . import ops
+
+        self.data = ops.conjugate_pairs(self.data, self.ell_min, self.ell_max, inverse=False)
+        self._append_history(f"{self}.convert_to_conjugate_pairs()")
+
+    @waveform_alterations
+    def convert_from_conjugate_pairs(self):
+        """Undo `convert_to_conjugate_pairs` in place (scri/waveform_modes.py:688-703)."""
+        from . import ops
+
+        self.data = ops.conjugate_pairs(self.data, self.ell_min, self.ell_max, inverse=True)
+        self._append_history(f"{self}.convert_from_conjugate_pairs()")
+
     def transform(self, **kwargs):
         """Apply a BMS transformation; returns a new WaveformModes (scri/waveform_modes.py:705-719).
 
