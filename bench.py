@@ -241,6 +241,147 @@ def run_reference(args):
     emit(line)
 
 
+def extra_batch(args, torch, dist, world, rank, kw):
+    """BASELINE configs[2] next to the headline line: 4096 random-mode waveforms (ell 2..8, 2048 steps each), one shared
+    transformation, the batch sharded by waveform index over the ranks (STRONG scaling, no data-path collective).
+    Two legs: device-resident (plan.run_batch over the rank's shard) and end to end from pinned host memory
+    (parallel.transform_batch_host: H2D, kernels and D2H of every sub-batch inside the timed region)."""
+    import scri_b200 as sb
+    from scri_b200 import parallel
+    from scri_b200.plan import TransformPlan
+
+    B, N, n, sub = args.batch, 2048, 77, 512
+    lo, hi = parallel.shard_range(B, rank, world)
+    plan = TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **kw)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    t = torch.linspace(0.0, 204.7, N, dtype=torch.float64, device="cuda")
+    chunks = []
+    for b0 in range(lo, hi, sub):
+        bn = min(sub, hi - b0)
+        wf = torch.rand(bn, 1, n, dtype=torch.float64, device="cuda", generator=g) * 0.45 + 0.05
+        c = torch.randn(bn, 1, n, dtype=torch.complex128, device="cuda", generator=g)
+        chunks.append(c * torch.exp(1j * wf * t[None, :, None]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        n_out = 0
+        for d in chunks:
+            up, out = plan.run_batch(t, d)
+            n_out = up.shape[0]
+        return n_out
+
+    steps = max(3, min(args.steps, 5))
+    for _ in range(3):
+        n_out = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        n_out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    # end to end: the rank's shard lives in pinned host memory as ONE sub-batch worth of waveforms that is sent again for
+    # every sub-batch of the shard (same bytes over PCIe as a full host copy of the shard, a twelfth of the host RAM)
+    host_in = torch.empty((min(sub, hi - lo), N, n), dtype=torch.complex128, pin_memory=True)
+    host_in.copy_(chunks[0][: host_in.shape[0]])
+    torch.cuda.synchronize()
+    t_host = t.cpu().numpy()
+    shard = hi - lo
+    reps = -(-shard // host_in.shape[0])
+    host_out = None
+
+    def e2e_step():
+        nonlocal host_out
+        done = 0
+        for r in range(reps):
+            nb = min(host_in.shape[0], shard - done)
+            u, host_out_np = parallel.transform_batch_host(plan, t_host, host_in.numpy()[:nb], sub_batch=sub // 4,
+                                                           out=None if host_out is None else host_out[:nb])
+            if host_out is None:
+                host_out = torch.from_numpy(host_out_np)
+            done += nb
+        return u
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    e2e_ms = 1e3 * float(np.mean(times))
+    tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    del chunks
+    torch.cuda.empty_cache()
+    units = float(n) * N * B
+    return {
+        "workload": f"configs[2]: batch of {B} random-mode waveforms, ell 2..8 (77 modes), {N} steps each, one shared transformation; sharded by waveform index (sub-batches of {sub}), no collective",
+        "scaling": "strong", "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_out": int(n_out),
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(shard) * N * n * 16 * world, "d2h_bytes_per_step": int(shard) * int(n_out) * n * 16 * world,
+                "note": f"host arrays in pinned memory ({sub} waveforms per call of parallel.transform_batch_host, sub-batches of {sub // 4} double-buffered on three streams); H2D, kernels and D2H of every sub-batch inside the timed region"},
+    }
+
+
+def extra_timeshard(args, torch, dist, world, rank, kw, w):
+    """BASELINE configs[1] as ONE series sharded by TIME over the ranks (strong scaling): parallel.sharded_transform, whose
+    only data-path communication is the point-to-point halo exchange of the input modes plus a 4-scalar all_gather; the two
+    are timed separately with CUDA events."""
+    from scri_b200 import ops, parallel
+    from scri_b200.plan import TransformPlan
+
+    N = w.t.shape[0]
+    lo, hi = parallel.shard_range(N, rank, world)
+    t_d = ops.to_device(np.ascontiguousarray(w.t[lo:hi]))
+    a_d = ops.to_device(np.ascontiguousarray(w.data[lo:hi]))
+    plan = TransformPlan(w.ell_min, w.ell_max, w.dataType, r_is_scaled_out=w.r_is_scaled_out, **kw)
+    halo = parallel.transform_halo(plan, float(w.t[lo]), float(w.t[hi - 1]), float(np.diff(w.t).min()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        u, m = parallel.sharded_transform(plan, t_d, a_d)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    total = ag = p2p = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        barrier()
+        tm = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        u, m = parallel.sharded_transform(plan, t_d, a_d, timings=tm)
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+        ag += tm["all_gather_begin"].elapsed_time(tm["all_gather_end"])
+        p2p += tm["halo_begin"].elapsed_time(tm["halo_end"])
+    tms = torch.tensor([total / steps, ag / steps, p2p / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    n_out = torch.tensor([u.shape[0]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_out)
+    ms = float(tms[0])
+    return {
+        "workload": f"configs[1] as one series of {N} steps sharded by time over {world} rank(s): halo of {halo} input samples per boundary exchanged point-to-point (NCCL), 4-scalar all_gather, no other collective",
+        "scaling": "strong", "value": float(w.n_modes) * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "halo_samples": int(halo),
+        "all_gather_4_scalars_ms": float(tms[1]), "halo_p2p_ms": float(tms[2]), "n_out": int(n_out[0]),
+        "halo_bytes_per_boundary": int(halo) * (int(w.n_modes) * 16 + 8) * 2,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -344,9 +485,27 @@ def run_ours(args):
     value = units / (ms_step_max * 1e-3)
     e2e_value = units / (e2e_ms_max * 1e-3)
 
+    # ---- what north_star asks of the 1 -> 8 GPU runs besides the headline line (extra keys of the same JSON line)
+    extras = {}
+    G, grid_str = plan.G, f"{plan.n_theta}x{plan.n_phi}"
+    if not args.no_extras:
+        del plan, a_d, flush
+        torch.cuda.empty_cache()
+        try:
+            extras["batch_config2"] = extra_batch(args, torch, dist, world, rank, kw)
+        except Exception as exc:   # the headline line must survive a failure here
+            extras["batch_config2"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            if not dist.is_initialized():
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", str(29500 + os.getpid() % 2000))
+                dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+            extras["timeshard_config1"] = extra_timeshard(args, torch, dist, world, rank, kw, w)
+        except Exception as exc:
+            extras["timeshard_config1"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        G = plan.G
         # dominant kernel by time decides which roofline is quoted; all three are listed under "kernels"
         dgemm_tf = measure_dgemm_peak(torch)
         synth_flops = 8.0 * n_modes * G * N
@@ -391,7 +550,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {
                 "workload": "configs[1]: fake_precessing_waveform ell_max=8 (77 modes), transform(supertranslation ell<=4 + frame_rotation + boost_velocity), 25x25 grid; one such waveform per GPU (batch sharded by waveform index)",
-                "n_times": N, "n_out": n_out, "n_modes": n_modes, "grid": f"{plan.n_theta}x{plan.n_phi}",
+                "n_times": N, "n_out": n_out, "n_modes": n_modes, "grid": grid_str,
                 "l2": "explicit 256 MiB L2 flush between timed iterations; intermediates (2 x 1 GB) exceed L2",
             },
             "roofline": roof, "kernels": kern, "fp64_dgemm_tflops_measured": dgemm_tf,
@@ -400,8 +559,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
         }
+        line.update(extras)
         emit(line)
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
@@ -671,6 +831,7 @@ def main():
     ap.add_argument("--workload", default="transform", choices=["transform", "batch", "product", "timeshard"],
                     help="transform = configs[1] (the bench line); batch = configs[2]; product = configs[3] (ell<=32 mode products)")
     ap.add_argument("--batch", type=int, default=4096, help="waveforms in the batch workload (all ranks together)")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only: skip the configs[2] batch and the time-sharded run")
     args = ap.parse_args()
     claim_stdout()
     if args.warmup < 3 and args.impl == "ours":

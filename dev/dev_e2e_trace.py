@@ -31,9 +31,12 @@ wrap(sb.WaveformModes, "__init__", "WaveformModes ctor")
 for trial in range(3):
     marks.clear()
     P.TRACE = []
+    ops.TIMING_EVENTS = []
     torch.cuda.synchronize(); T0 = time.perf_counter()
     out = w.transform(**kw)
     torch.cuda.synchronize(); print("total %.2f ms" % ((time.perf_counter() - T0) * 1e3))
     for m in marks: print("   %-22s %7.2f -> %7.2f ms" % m)
     for label, tt in P.TRACE: print("   [trace] %-40s %7.2f ms" % (label, (tt - T0) * 1e3))
+    ev0 = ops.TIMING_EVENTS[0][1]
+    for label, ev in ops.TIMING_EVENTS[1:]: print("   [gpu] %-44s %7.2f ms after the first DMA was queued" % (label, ev0.elapsed_time(ev)))
 print("registered host arrays:", len(ops._registered))

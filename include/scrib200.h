@@ -82,7 +82,7 @@ int scrib200_swsh_synthesize(const double* modes, int64_t n_times, int n_modes, 
  *                      gamma: scri/asymptotic_bondi_data/transformations.py:393); may be NULL together with kconf/alpha
  *   info [8] (device)  [0] lo, [1] hi: the retained block is uprm[lo:hi];  [2], [3]: worst decay of the spline
  *                      recurrences over any 32 / 64 consecutive rows (choose halo = 32 if [2] <= 1e-15, else 64 if
- *                      [3] <= 1e-15, else 128);  [4], [5]: u'min, u'max
+ *                      [3] <= 1e-15, else 128);  [4], [5]: u'min, u'max;  [6]: the smallest sample spacing min(t[i+1] - t[i])
  *
  * scrib200_spline_remap: t [n_times], F [n_times, G] complex128, kconf [G], alpha [G], uprm [n_out] increasing,
  *   tile == 0: out [n_out, G] complex128 time-major;  tile = T (power of two >= 2): out written time-tiled,
@@ -104,6 +104,12 @@ int scrib200_spline_remap(const double* t, int64_t n_times, const double* F, int
                           const double* alpha, const double* tab, const double* uprm, int64_t n_out, double* out,
                           int tile, int halo, int body, int n_series, void* workspace, size_t workspace_bytes,
                           void* stream);
+/* The same, for a caller that evaluates a slice of the output times and knows that no grid point needs input samples outside
+ * rows [row_lo, row_hi) for it (a slab of the end-to-end pipeline): only the tiles holding those rows are launched. */
+int scrib200_spline_remap_rows(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
+                               const double* alpha, const double* tab, const double* uprm, int64_t n_out, double* out,
+                               int tile, int halo, int body, int n_series, int64_t row_lo, int64_t row_hi, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWSH analysis, batched over time steps.

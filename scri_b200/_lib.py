@@ -48,6 +48,10 @@ SIGNATURES = {
         c_int,
         [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp],
     ),
+    "scrib200_spline_remap_rows": (
+        c_int,
+        [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_i64, c_i64, c_vp, c_sz, c_vp],
+    ),
     "scrib200_spline_remap_workspace_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "scrib200_map2salm_tile_size": (c_int, [c_int, c_int, c_int, c_int]),
     "scrib200_map2salm_tiled": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),

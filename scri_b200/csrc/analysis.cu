@@ -382,27 +382,33 @@ map2salm_dmma_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_t
 // ---- persistent DMMA kernel: one CTA per SM walks the time tiles with two tile buffers in shared memory, so the TMA
 // bulk load of tile i+1 flies under the arithmetic of tile i, and the tables are set up once per CTA instead of once
 // per 8 time steps.  Both contractions run on the FP64 tensor cores:
-//   phi-DFT   (as map2salm_dmma_kernel): M = (Re/Im part, t), K = k, N = trig columns;
+//   phi-DFT, folded: cos(m phi_k) = cos(m phi_{n-k}) and sin(m phi_k) = -sin(m phi_{n-k}), so with p_k = f_k + f_{n-k} and
+//   q_k = f_k - f_{n-k} (k = 1 .. n/2; p_0 = f_0, q_0 = 0) the cosine sums run over p and the sine sums over q with
+//   K = n/2 + 1 instead of n: 16 DMMA per ring instead of 28 at n_phi = 25.  M = t, K = k, N = m; the A fragments are
+//   two 16-byte loads from the [G][8] tile the spline kernel wrote, the trig fragments live in registers for the whole
+//   kernel (NT = 1) or in a conflict-free shared table (NT = 2);
 //   theta quadrature, per m:  a[(l, m), (t, part)] = sum_j W[(l, m), j] f_m[t][j][part]:  M = l (rows of Wt, read through
 //   L1), K = j, N = t for the Re and the Im tile - the B fragment of both is one 16-byte load of f_m(theta_j) from the
 //   buffer the DFT results were written to (which is the tile buffer itself, after a barrier).
 template <int NT>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(576, 1)
 map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_theta, int n_phi,
                         const double2* __restrict__ trig, const double* __restrict__ Wt, int ell_min, int ell_max,
                         double2* __restrict__ out) {
     constexpr int T = 8;
-    constexpr int BP = 16 * NT + 8;
+    constexpr int BP = 16 * NT + 4;                                          // pitch of the folded trig table: conflict free
+    constexpr int KF = 4;                                                    // k-steps of the folded DFT (n_phi <= 31)
     extern __shared__ __align__(128) double2 smp[];
     __shared__ __align__(8) unsigned long long mbar[2];
     const int L = ell_max, nm = 2 * L + 1, np1 = L + 1;
     const int G = n_theta * n_phi;
-    const int KS = (n_phi + 3) / 4, KQ = (n_theta + 3) / 4;
+    const int KQ = (n_theta + 3) / 4;
+    const int half = n_phi / 2;                                              // folded index k = 0 .. half
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
     const size_t tile_elems = (size_t)G * T;
     const size_t buf_elems = (size_t)(G + 4) * T;
     double2* sBuf[2] = {smp, smp + buf_elems};
-    double* sB = reinterpret_cast<double*>(smp + 2 * buf_elems);             // [4 KS][BP]
+    double* sB = reinterpret_cast<double*>(smp + 2 * buf_elems);             // [4 KF][BP]: cos | sin of (m phi_k) / n_phi
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int64_t ntiles = (n_times + T - 1) / T;
@@ -427,12 +433,10 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
         if ((int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
         if ((int64_t)blockIdx.x + gridDim.x < ntiles) issue((int64_t)blockIdx.x + gridDim.x, 1);
     }
-    for (int b = 0; b < 2; ++b)
-        for (int i = tid; i < 4 * T; i += nt) sBuf[b][tile_elems + i] = make_double2(0.0, 0.0);
-    for (int i = tid; i < 4 * KS * BP; i += nt) {
+    for (int i = tid; i < 4 * KF * BP; i += nt) {
         const int k = i / BP, n = i - k * BP;
         double v = 0.0;
-        if (k < n_phi && n < 16 * NT) {
+        if (k <= half && n < 16 * NT) {
             const int m = (n % (8 * NT)) + 1;
             if (m <= L) {
                 const double2 cs = trig[k * np1 + m];
@@ -445,7 +449,15 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
     const int tq = lane >> 2, kk = lane & 3;
     const double inv_nphi = trig[0].x;
     const int MT = (L - ell_min + 8) / 8;                                    // 8-row blocks of l for the longest m column
-
+    // trig fragments of this lane (B[k = kk][n = tq]) for every k-step: registers when NT = 1
+    double bfrag[KF][2];
+    if (NT == 1) {
+#pragma unroll
+        for (int ks = 0; ks < KF; ++ks) {
+            bfrag[ks][0] = sB[(4 * ks + kk) * BP + tq];
+            bfrag[ks][1] = sB[(4 * ks + kk) * BP + 8 + tq];
+        }
+    }
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
@@ -462,7 +474,7 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
         const double2* sTile = sBuf[b];
         double2* sFm = sBuf[b];                                              // [T][nm][n_theta] after the barrier
         // ---- phi-DFT: rings warp, warp + nwarp
-        double acc[2][2][2 * NT][2];
+        double acc[2][2][2 * NT][2];                                         // [ring][Re / Im part][cos tiles | sin tiles][2]
         double s0[2][2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -473,19 +485,26 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
                 for (int n = 0; n < 2 * NT; ++n) acc[r][p][n][0] = acc[r][p][n][1] = 0.0;
             const int j = warp + r * nwarp;
             if (j < n_theta) {
-                const double2* arow = sTile + ((size_t)j * n_phi + kk) * T + tq;
-                const double* brow = sB + kk * BP + tq;
-#pragma unroll 2
-                for (int ks = 0; ks < KS; ++ks) {
-                    double2 a = arow[(size_t)ks * 4 * T];
-                    if (ks == KS - 1 && 4 * ks + kk >= n_phi) a = make_double2(0.0, 0.0);   // K padding: next ring's samples
-                    s0[r][0] += a.x;
-                    s0[r][1] += a.y;
+                const double2* ring = sTile + (size_t)j * n_phi * T + tq;
 #pragma unroll
-                    for (int n = 0; n < 2 * NT; ++n) {
-                        const double bv = brow[ks * 4 * BP + n * 8];
-                        dmma884(acc[r][0][n][0], acc[r][0][n][1], a.x, bv);
-                        dmma884(acc[r][1][n][0], acc[r][1][n][1], a.y, bv);
+                for (int ks = 0; ks < KF; ++ks) {
+                    const int k = 4 * ks + kk;                               // folded index and its mirror n_phi - k
+                    const bool mirrored = (k >= 1 && k <= half && 2 * k != n_phi);
+                    double2 a1 = make_double2(0.0, 0.0), a2 = make_double2(0.0, 0.0);
+                    if (k <= half) a1 = ring[k * T];
+                    if (mirrored) a2 = ring[(n_phi - k) * T];
+                    const double2 pp = make_double2(a1.x + a2.x, a1.y + a2.y);
+                    const double2 qq = mirrored ? make_double2(a1.x - a2.x, a1.y - a2.y) : make_double2(0.0, 0.0);
+                    s0[r][0] += pp.x;
+                    s0[r][1] += pp.y;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const double bc = (NT == 1) ? bfrag[ks][0] : sB[(4 * ks + kk) * BP + n * 8 + tq];
+                        const double bs = (NT == 1) ? bfrag[ks][1] : sB[(4 * ks + kk) * BP + (NT + n) * 8 + tq];
+                        dmma884(acc[r][0][n][0], acc[r][0][n][1], pp.x, bc);
+                        dmma884(acc[r][1][n][0], acc[r][1][n][1], pp.y, bc);
+                        dmma884(acc[r][0][NT + n][0], acc[r][0][NT + n][1], qq.x, bs);
+                        dmma884(acc[r][1][NT + n][0], acc[r][1][NT + n][1], qq.y, bs);
                     }
                 }
 #pragma unroll
@@ -560,8 +579,7 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
 }
 
 static size_t persist_smem(int n_theta, int n_phi, int NT) {
-    const size_t KS = (n_phi + 3) / 4;
-    return 2 * ((size_t)n_theta * n_phi + 4) * 8 * sizeof(double2) + 4 * KS * (16 * NT + 8) * sizeof(double);
+    return 2 * ((size_t)n_theta * n_phi + 4) * 8 * sizeof(double2) + 4 * 4 * (16 * NT + 4) * sizeof(double);
 }
 
 static size_t dmma_smem(int n_theta, int n_phi, int ell_min, int ell_max, int NT) {
@@ -663,7 +681,7 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
         const bool disabled = getenv("SCRIB200_ANALYSIS_SCALAR") != nullptr;
         const size_t smem_p = persist_smem(n_theta, n_phi, NT);
         if (!disabled && !getenv("SCRIB200_ANALYSIS_NONPERSISTENT") && T == 8 && ell_max >= 1 && NT <= 2 && nwarp <= 20 &&
-            2 * ell_max + 1 <= n_phi && 2 * ell_max + 1 <= n_theta + 0 * n_phi && smem_p <= 225 * 1024) {
+            2 * ell_max + 1 <= n_phi && 2 * ell_max + 1 <= n_theta + 0 * n_phi && n_phi <= 31 && nwarp <= 18 && smem_p <= 225 * 1024) {
             static int n_sm = 0;
             if (n_sm == 0) {
                 int dev = 0;
@@ -672,7 +690,13 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
             }
             const int64_t ntiles = (n_times + T - 1) / T;
             const unsigned blocks = (unsigned)(ntiles < n_sm ? ntiles : n_sm);
-            const int threads = 32 * (nwarp < 4 ? 4 : nwarp);
+            // warps: at least one per two rings (the DFT keeps two rings' accumulators) and, if it fits, one per quadrature
+            // unit (2 ell_max + 1 columns of m), so that neither phase needs a second, half-empty round
+            int pw = nwarp < 4 ? 4 : nwarp;
+            const int units = (2 * ell_max + 1) * ((ell_max - ell_min + 8) / 8);
+            if (units > pw) pw = units < 18 ? units : 18;
+            if (const char* env = getenv("SCRIB200_ANALYSIS_WARPS")) pw = atoi(env) >= nwarp && atoi(env) <= 18 ? atoi(env) : pw;
+            const int threads = 32 * pw;
             if (NT == 1) {
                 cudaFuncSetAttribute(map2salm_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
                 map2salm_persist_kernel<1><<<blocks, threads, smem_p, (cudaStream_t)stream>>>(

@@ -117,6 +117,12 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
             }
         }
     }
+    {   // info[6] = smallest sample spacing (the host sizes the halo of its pipelines with it): positive doubles order like their bits
+        double h = (i < N - 1) ? t[i + 1] - t[i] : CUDART_INF;
+        for (int o = 16; o > 0; o >>= 1) h = fmin(h, __shfl_xor_sync(0xffffffffu, h, o));
+        if ((threadIdx.x & 31) == 0 && h > 0.0 && h < CUDART_INF)
+            atomicMin(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)__double_as_longlong(h));
+    }
     if (i >= N) return;
     double row[ST_TAB6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (i >= 1 && i <= N - 2) {
@@ -150,7 +156,7 @@ spline_factor_kernel(const double* __restrict__ t, int N, double* __restrict__ t
 }
 
 __global__ void spline_info_init_kernel(double* __restrict__ info, double n) {
-    if (threadIdx.x < 8) info[threadIdx.x] = (threadIdx.x < 2) ? n : 0.0;
+    if (threadIdx.x < 8) info[threadIdx.x] = (threadIdx.x < 2) ? n : (threadIdx.x == 6 ? CUDART_INF : 0.0);
 }
 
 // Worst decay of the two recurrences over any window of 32 / 64 consecutive rows:
@@ -234,8 +240,8 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
                    const double* __restrict__ kconf, const double* __restrict__ alpha,
                    const double* __restrict__ tab, const double* __restrict__ up, int Nout,
                    double* __restrict__ out, int tshift, int body, int halo, const int* __restrict__ J,
-                   const int* __restrict__ flags, int box_rows) {
-    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+                   const int* __restrict__ flags, int box_rows, int tile_off) {
+    const int bx = blockIdx.x, by = blockIdx.y + tile_off, bz = blockIdx.z;
     if (MODE == 0 && flags[by * gridDim.x + bx] == 0) return;   // no output time falls in this tile
     extern __shared__ unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -652,7 +658,8 @@ static TensorMapEncodeTiledFn tensor_map_encoder() {
 template <int MODE>
 static int launch_tile(const double* t, int64_t n_times, const double* F, int G, const double* kconf, const double* alpha,
                        const double* tab, const double* uprm, int64_t n_out, double* out, int tshift, int halo, int body,
-                       void* workspace, size_t workspace_bytes, void* stream, const char* name, int n_series = 1) {
+                       void* workspace, size_t workspace_bytes, void* stream, const char* name, int n_series = 1,
+                       int64_t row_lo = 0, int64_t row_hi = -1) {
     SCRIB200_REQUIRE(n_times < (int64_t)2147483000 && n_out < (int64_t)2147483000, "%s: series longer than 2^31 samples", name);
     resolve_tile(halo, body);
     SCRIB200_REQUIRE(halo % ST_BR == 0 && body % ST_BR == 0, "%s: body=%d and halo=%d must be multiples of %d", name, body, halo, ST_BR);
@@ -683,11 +690,20 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     const bool small = threads <= 320;                       // default tiles (19 blocks): 102 registers per thread at 2 CTAs / SM
     if (small) cudaFuncSetAttribute(spline_tile_kernel<MODE, 320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else cudaFuncSetAttribute(spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)ntiles, (unsigned)n_series);
+    // tiles to launch: all of them, or only those that hold input rows [row_lo, row_hi) (a caller that evaluates a slice of
+    // the output times and knows which input rows it can touch)
+    int64_t tile_lo = 0, tile_hi = ntiles;
+    if (row_hi >= 0) {
+        tile_lo = (row_lo > 0 ? row_lo : 0) / body;
+        tile_hi = (row_hi + body - 1) / body;
+        if (tile_hi > ntiles) tile_hi = ntiles;
+        if (tile_lo >= tile_hi) return SCRIB200_OK;
+    }
+    dim3 grid((2 * G + ST_COLS - 1) / ST_COLS, (unsigned)(tile_hi - tile_lo), (unsigned)n_series);
     int* J = nullptr;
     int* flags = nullptr;
     if (MODE == 0) {
-        const size_t need = ((size_t)(ntiles + 1) * G + (size_t)ntiles * grid.x) * sizeof(int);
+        const size_t need = ((size_t)(ntiles + 1) * G + (size_t)ntiles * grid.x) * sizeof(int);   // tables cover every tile
         SCRIB200_REQUIRE(workspace && workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", name, workspace_bytes, need);
         J = reinterpret_cast<int*>(workspace);
         const int64_t total = (ntiles + 1) * (int64_t)G;
@@ -701,10 +717,10 @@ static int launch_tile(const double* t, int64_t n_times, const double* F, int G,
     }
     if (small)
         spline_tile_kernel<MODE, 320><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows);
+            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows, (int)tile_lo);
     else
         spline_tile_kernel<MODE, ST_MAXBLK * ST_COLS><<<grid, threads, smem, (cudaStream_t)stream>>>(
-            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows);
+            tmF, t, (int)n_times, G, kconf, alpha, tab, uprm, (int)n_out, out, tshift, body, halo, J, flags, box_rows, (int)tile_lo);
     SCRIB200_CHECK_LAUNCH(name);
     return SCRIB200_OK;
 }
@@ -757,6 +773,24 @@ extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const dou
     if (n_out <= 0) return SCRIB200_OK;
     return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, workspace,
                           workspace_bytes, stream, "spline_remap", n_series);
+}
+
+extern "C" int scrib200_spline_remap_rows(const double* t, int64_t n_times, const double* F, int G, const double* kconf,
+                                          const double* alpha, const double* tab, const double* uprm, int64_t n_out,
+                                          double* out, int tile, int halo, int body, int n_series, int64_t row_lo,
+                                          int64_t row_hi, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(t && F && kconf && alpha && tab && uprm && out, "spline_remap_rows: null pointer");
+    SCRIB200_REQUIRE(n_times >= 4, "spline_remap_rows: a cubic interpolating spline needs at least 4 knots; got %lld", (long long)n_times);
+    int tshift = 0;
+    while ((1 << tshift) < tile) ++tshift;
+    SCRIB200_REQUIRE(G > 0 && (tile == 0 || (tile >= 2 && (1 << tshift) == tile)),
+                     "spline_remap_rows: G=%d, tile=%d must be 0 (time-major output) or a power of two >= 2", G, tile);
+    SCRIB200_REQUIRE(aligned16(F) && aligned16(out) && aligned16(tab), "spline_remap_rows: pointers must be 16-byte aligned");
+    SCRIB200_REQUIRE(row_lo >= 0 && row_hi >= row_lo, "spline_remap_rows: rows [%lld, %lld)", (long long)row_lo, (long long)row_hi);
+    if (n_out <= 0) return SCRIB200_OK;
+    return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, workspace,
+                          workspace_bytes, stream, "spline_remap_rows", n_series, row_lo, row_hi);
 }
 
 extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const double* data, int ncol,

@@ -106,16 +106,78 @@ def sparse_expectation_value(abar, rows, columns, values, b):
     return ops.sparse_expectation(np.conj(abar), b, [(rows, columns, values)])[:, 0]
 
 
+def intersection(t1, t2, min_step=None, min_time=None, max_time=None):
+    """Common time axis of two sequences (scri/extrapolation.py:47-125): it starts at the later of the two first samples
+    (or `min_time`), ends before the earlier of the two last samples (or `max_time`), and at each point steps by the smaller
+    of the two local sample spacings, but at least `min_step` (default: the smallest spacing in either input)."""
+    t1 = np.asarray(t1, dtype=float)
+    t2 = np.asarray(t2, dtype=float)
+    if t1.size == 0:
+        raise ValueError("t1 is empty.  Assuming this is not desired.")
+    if t2.size == 0:
+        raise ValueError("t2 is empty.  Assuming this is not desired.")
+    min1, min2, max1, max2 = t1[0], t2[0], t1[-1], t2[-1]
+    mint = max(min1, min2) if min_time is None else max(max(min1, min2), min_time)
+    maxt = min(max1, max2) if max_time is None else min(min(max1, max2), max_time)
+    if mint > max1 or mint > max2:
+        raise ValueError(f"Empty intersection in t1=[{min1}, ..., {max1}], t2=[{min2}, ..., {max2}] with min_time={min_time}")
+    if maxt < min1 or maxt < min2:
+        raise ValueError(f"Empty intersection in t1=[{min1}, ..., {max1}], t2=[{min2}, ..., {max2}] with max_time={max_time}")
+    if min_step is None:
+        min_step = min(np.min(np.diff(t1)), np.min(np.diff(t2)))
+    t = np.empty(t1.size + t2.size)
+    t[0] = mint
+    i = i1 = i2 = 0
+    n1, n2 = t1.size, t2.size
+    while t[i] < maxt:
+        # i1: t[i] lies in (t1[i1-1], t1[i1]]  (0 when t[i] is outside t1); the same for i2
+        if t[i] < min1 or t[i] > max1:
+            i1 = 0
+        else:
+            i1 = max(i1, 1)
+            while t[i] > t1[i1] and i1 < n1:
+                i1 += 1
+        if t[i] < min2 or t[i] > max2:
+            i2 = 0
+        else:
+            i2 = max(i2, 1)
+            while t[i] > t2[i2] and i2 < n2:
+                i2 += 1
+        t[i + 1] = t[i] + max(min(t1[i1] - t1[i1 - 1], t2[i2] - t2[i2 - 1]), min_step)
+        i += 1
+        if t[i] > maxt:
+            break
+    return t[:i]
+
+
 def matrix_expectation_value(a, M, b, allow_LM_differ=False, allow_times_differ=False):
-    """(times, <a|M|b>(u)) (scri/flux.py:81-179).  `M(ell_min, ell_max)` returns (rows, columns, values)."""
+    """(times, <a|M|b>(u)) (scri/flux.py:81-179).  `M(ell_min, ell_max)` returns (rows, columns, values).  With
+    `allow_LM_differ` the product runs over the ell range the two waveforms share; with `allow_times_differ` both are
+    interpolated onto the `intersection` of their time axes first (cubic splines on the GPU)."""
     if a.spin_weight != b.spin_weight:
         raise ValueError("Spin weights must match in matrix_expectation_value")
+    ell_min, ell_max = a.ell_min, a.ell_max
+    clip = False
     if (a.ell_min != b.ell_min) or (a.ell_max != b.ell_max):
-        raise ValueError("ell_min and ell_max must match in matrix_expectation_value (allow_LM_differ is not supported on the GPU path)")
+        if not allow_LM_differ:
+            raise ValueError("ell_min and ell_max must match in matrix_expectation_value (use allow_LM_differ=True to override)")
+        ell_min, ell_max = max(a.ell_min, b.ell_min), min(a.ell_max, b.ell_max)
+        if ell_min >= ell_max + 1:
+            raise ValueError("Intersection of (ell,m) modes is empty.  Assuming this is not desired.")
+        clip = True
+    t_clip = None
     if not np.array_equal(a.t, b.t):
-        raise ValueError("Time samples must match in matrix_expectation_value (allow_times_differ is not supported on the GPU path)")
-    rows, columns, values = M(a.ell_min, a.ell_max)
-    return (a.t, ops.sparse_expectation(a.data, b.data, [(rows, columns, values)])[:, 0])
+        if not allow_times_differ:
+            raise ValueError("Time samples must match in matrix_expectation_value (use allow_times_differ=True to override)")
+        t_clip = intersection(a.t, b.t)
+    times, A, B = a.t, a, b
+    if clip:
+        A, B = A[:, ell_min : ell_max + 1], B[:, ell_min : ell_max + 1]
+    if t_clip is not None:
+        times = t_clip
+        A, B = A.interpolate(t_clip), B.interpolate(t_clip)
+    rows, columns, values = M(ell_min, ell_max)
+    return (times, ops.sparse_expectation(A.data, B.data, [(rows, columns, values)])[:, 0])
 
 
 def _hdot_of(hw, name):

@@ -74,6 +74,7 @@ def to_device_async(x, dtype=None):
 
 
 _copy_streams = {}
+TIMING_EVENTS = None      # dev aid: set to a list to collect (label, timing event) pairs of the transfers
 
 # Arrays that go up more than once are page-locked in place on their second trip (scrib200_host_register), after which
 # scrib200_h2d DMAs straight from them; a finalizer releases the registration when the array dies.  One-shot callers
@@ -121,7 +122,7 @@ def _maybe_register(a):
 
 
 
-def to_device_slabs(x, dtype=None, n_slabs=4):
+def to_device_slabs(x, dtype=None, n_slabs=4, weights=None):
     """Start copying a large host array to the device in `n_slabs` row slabs on a dedicated copy stream (helper thread,
     GIL-free staging).  Returns (device tensor, slabs, future): slabs = [(row_lo, row_hi, event, flag)], the event of a slab
     fires when its rows have landed (the host flag says the event has been recorded); `future.result()` returns once every slab has been queued.  Consumers order their
@@ -132,7 +133,7 @@ def to_device_slabs(x, dtype=None, n_slabs=4):
     if dtype is not None and a.dtype != dtype:
         a = a.astype(dtype)
     N = a.shape[0]
-    _maybe_register(a)
+    locked = _maybe_register(a)
     dev = torch.cuda.current_device()
     if dev not in _copy_streams:
         _copy_streams[dev] = torch.cuda.Stream()
@@ -140,14 +141,43 @@ def to_device_slabs(x, dtype=None, n_slabs=4):
     out = torch.empty(a.shape, dtype=getattr(torch, a.dtype.name), device="cuda")
     out.record_stream(cs)
     cs.wait_stream(torch.cuda.current_stream())          # the allocation (and whatever freed it before) is ordered first
-    bounds = [N * k // n_slabs for k in range(n_slabs + 1)]
+    if weights is not None:      # slabs of unequal size (small first: the consumer starts early; small last: short tail)
+        n_slabs = len(weights)
+        cum = np.concatenate([[0.0], np.cumsum(np.asarray(weights, dtype=float))])
+        bounds = [int(round(N * c / cum[-1])) for c in cum]
+    else:
+        bounds = [N * k // n_slabs for k in range(n_slabs + 1)]
     import threading
 
     # (row_lo, row_hi, CUDA event recorded once the slab's copies are queued, host flag set once that event exists:
     #  waiting on an event that has not been recorded yet is a no-op in CUDA, so consumers wait for the flag first)
-    slabs = [(bounds[k], bounds[k + 1], torch.cuda.Event(), threading.Event()) for k in range(n_slabs)]
+    timed = TIMING_EVENTS is not None
+    slabs = [(bounds[k], bounds[k + 1], torch.cuda.Event(enable_timing=timed), threading.Event()) for k in range(n_slabs)]
     lib = _lib.load()
     row_bytes = a.nbytes // max(N, 1)
+    if timed:
+        start = torch.cuda.Event(enable_timing=True)
+        start.record(cs)
+        TIMING_EVENTS.append(("h2d start", start))
+        TIMING_EVENTS.extend((f"h2d slab {k} landed", sl[2]) for k, sl in enumerate(slabs))
+    if locked:
+        # page-locked source: every slab is one DMA queued right here - nothing for a helper thread to do, and the first
+        # bytes move before the caller has done anything else
+        for lo, hi, ev, flag in slabs:
+            if hi > lo:
+                _lib.check(
+                    lib.scrib200_h2d(out.data_ptr() + lo * row_bytes, a.ctypes.data + lo * row_bytes, (hi - lo) * row_bytes,
+                                     ctypes_void(cs.cuda_stream)),
+                    "h2d",
+                )
+            ev.record(cs)
+            flag.set()
+
+        class _Done:
+            def result(self):
+                return out
+
+        return out, slabs, _Done()
     if _h2d_pool is None:
         from concurrent.futures import ThreadPoolExecutor
 

@@ -147,6 +147,63 @@ def transform_batch(plan, t, data_batch):
     return plan.run_batch(t, data_batch)
 
 
+def transform_batch_host(plan, t, data_host, sub_batch=512, out=None):
+    """BASELINE configs[2] from host memory: `data_host` [B, N, n_modes] complex128 numpy (this rank's shard of the batch;
+    page-locked memory goes up by DMA, anything else through the staging ring) -> (u' [N'] numpy, modes' [B, N', n_out]
+    numpy in pinned memory).  Sub-batches are double-buffered on the device: the H2D of sub-batch i+1 and the D2H of
+    sub-batch i-1 run on their own streams under the kernels of sub-batch i (plan.run_batch)."""
+    import ctypes
+
+    import torch
+
+    from . import _lib, ops
+
+    lib = _lib.load()
+    t_d = ops.to_device(t, np.float64)
+    B, N, n = data_host.shape
+    if data_host.dtype != np.complex128 or not data_host.flags.c_contiguous:
+        data_host = np.ascontiguousarray(data_host, dtype=np.complex128)
+    sub = max(1, min(int(sub_batch), B))
+    cur = torch.cuda.current_stream()
+    cin, cout = torch.cuda.Stream(), torch.cuda.Stream()
+    bufs = [torch.empty((sub, N, n), dtype=torch.complex128, device="cuda") for _ in range(2)]
+    free = [None, None]                                   # event: the kernels that read buffer b are done
+    row_bytes = N * n * 16
+    u_host = None
+    host_out = out
+    for i, b0 in enumerate(range(0, B, sub)):
+        nb = min(sub, B - b0)
+        b = i & 1
+        if free[b] is not None:
+            cin.wait_event(free[b])
+        else:
+            cin.wait_stream(cur)
+        _lib.check(lib.scrib200_h2d(bufs[b].data_ptr(), data_host.ctypes.data + b0 * row_bytes, nb * row_bytes,
+                                    ctypes.c_void_p(cin.cuda_stream)), "h2d")
+        landed = torch.cuda.Event()
+        landed.record(cin)
+        cur.wait_event(landed)
+        u, m = plan.run_batch(t_d, bufs[b][:nb])
+        done = torch.cuda.Event()
+        done.record(cur)
+        free[b] = done
+        if host_out is None:
+            host_out = torch.empty((B, m.shape[1], m.shape[2]), dtype=torch.complex128, pin_memory=True)
+        elif not torch.is_tensor(host_out):
+            host_out = torch.from_numpy(host_out)
+        cout.wait_event(done)
+        with torch.cuda.stream(cout):
+            host_out[b0 : b0 + nb].copy_(m, non_blocking=True)
+            if u_host is None:
+                u_host = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+                u_host.copy_(u, non_blocking=True)
+        m.record_stream(cout)
+        u.record_stream(cout)
+    cout.synchronize()
+    cur.synchronize()
+    return u_host.numpy(), host_out.numpy()
+
+
 SPLINE_DECAY_ROWS = 40   # rows after which a not-a-knot spline has forgotten its end conditions (0.268^40 ~ 1e-23)
 
 
@@ -166,7 +223,7 @@ def transform_halo(plan, t_first, t_last, dt_min):
     return int(math.ceil(drift / dt_min)) + SPLINE_DECAY_ROWS + 2
 
 
-def sharded_transform(plan, t_local, data_local, halo=None, group=None):
+def sharded_transform(plan, t_local, data_local, halo=None, group=None, timings=None):
     """WaveformModes.transform (scri/waveform_grid.py:331-630) of ONE long series sharded by TIME: every rank holds a
     contiguous block of (t, modes), ranks in time order.  Each rank borrows `halo` input samples from its neighbours
     (point-to-point: the only data-path communication besides the few scalars below), synthesizes the extended block,
@@ -186,7 +243,16 @@ def sharded_transform(plan, t_local, data_local, halo=None, group=None):
     mine = torch.stack([t_local[0], t_local[-1], step, torch.tensor(float(n_loc), dtype=torch.float64, device=dev)])
     wire = mine.cpu() if dist.get_backend(group) == "gloo" else mine
     ends = [torch.empty_like(wire) for _ in range(world)]
+
+    def mark(name):                                                          # `timings`: name -> CUDA timing event
+        if timings is not None and dev.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timings[name] = ev
+
+    mark("all_gather_begin")
     dist.all_gather(ends, wire, group=group)
+    mark("all_gather_end")
     ends = torch.stack(ends).cpu().numpy()                                   # [world, 4]: first, last, min step, samples
     t0, tN = float(ends[0, 0]), float(ends[-1, 1])
     gaps = ends[1:, 0] - ends[:-1, 1]
@@ -198,8 +264,10 @@ def sharded_transform(plan, t_local, data_local, halo=None, group=None):
             f"time-sharded transform needs a halo of {halo} input samples but the smallest block has {int(ends[:, 3].min())}: "
             "the boost moves the input window of late output times too far; shard by waveform index instead"
         )
+    mark("halo_begin")
     prev_d, next_d = exchange_halos(data_local, halo, group)
     prev_t, next_t = exchange_halos(t_local, halo, group)
+    mark("halo_end")
     t_ext = torch.cat([x for x in (prev_t, t_local, next_t) if x is not None])
     d_ext = torch.cat([x for x in (prev_d, data_local, next_d) if x is not None])
     F = plan.synthesize(d_ext)

@@ -271,8 +271,10 @@ class GridPlan:
         backward compatibility and ignored (the block is found on the device)."""
         return self.prepare(t).uprm
 
-    def _remap(self, t, F, uprm, prep, tile, n_series=1):
-        """F [n_series * N, G] (series stacked along time) -> remapped grid; rows b*n_out.. belong to series b."""
+    def _remap(self, t, F, uprm, prep, tile, n_series=1, rows_needed=None):
+        """F [n_series * N, G] (series stacked along time) -> remapped grid; rows b*n_out.. belong to series b.
+        `rows_needed` = (row_lo, row_hi): the caller knows that these output times read input rows [row_lo, row_hi) only
+        (`input_rows_for_outputs`); only the tiles holding them are launched."""
         torch = self.torch
         lib = _lib.load()
         if prep is None:
@@ -289,6 +291,16 @@ class GridPlan:
         need = lib.scrib200_spline_remap_workspace_bytes(N, self.G, halo, body)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if rows_needed is not None:
+            _lib.check(
+                lib.scrib200_spline_remap_rows(
+                    _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
+                    _lib.ptr(uprm), n_out, _lib.ptr(out), tile, halo, body, n_series, int(rows_needed[0]), int(rows_needed[1]),
+                    _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr(),
+                ),
+                "spline_remap_rows",
+            )
+            return out
         _lib.check(
             lib.scrib200_spline_remap(
                 _lib.ptr(t), N, _lib.ptr(F), self.G, _lib.ptr(self.d_k), _lib.ptr(self.d_alpha), _lib.ptr(prep.tab),
@@ -298,6 +310,18 @@ class GridPlan:
             "spline_remap",
         )
         return out
+
+    def input_rows_for_outputs(self, t_host, u_first, u_last):
+        """[row_lo, row_hi): the input samples any grid point can need for output times in [u_first, u_last].  Grid point g
+        evaluates its spline at x = u, x_i = k_g (t_i - alpha_g), i.e. inside the input interval around t = u / k_g +
+        alpha_g: the extremes over the grid, widened by two samples."""
+        k = np.asarray(self.kconformal, dtype=float).ravel()
+        al = np.asarray(self.alpha, dtype=float).ravel()
+        t_lo = float(np.min(u_first / k + al))
+        t_hi = float(np.max(u_last / k + al))
+        lo = int(np.searchsorted(t_host, t_lo, side="left")) - 3
+        hi = int(np.searchsorted(t_host, t_hi, side="right")) + 3
+        return max(lo, 0), min(hi, int(t_host.shape[0]))
 
     def remap(self, t, F, uprm, prep=None):
         """Spline each grid point's series from knots k(t-alpha) onto u' (waveform_grid.py:576-588); [N', G]."""
@@ -629,19 +653,33 @@ class TransformPlan(GridPlan):
         if n_out < 8192:
             return None
         uprm = prep.uprm
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream()
+        cs = self._d2h_stream
+        # the output times go home first, under everything else
+        u_host = torch.empty(n_out, dtype=torch.float64, pin_memory=True)
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            u_host.copy_(uprm, non_blocking=True)
+        t_host = np.asarray(t_host, dtype=float)
+        u_of_row = lambda i: (t_host[i] - self.time_translation) / self.gamma   # output time of input row i, to rounding (bounds only)
         halo, body = prep.halo_body(self.spline_halo, self.spline_body)
-        drift = transform_halo(self, float(t_host[0]), float(t_host[-1]), float(np.diff(t_host).min())) - SPLINE_DECAY_ROWS
+        drift = transform_halo(self, float(t_host[0]), float(t_host[-1]), prep.dt_min) - SPLINE_DECAY_ROWS
         margin = drift + max(body, 320) + 2 * halo + 64
         N = data.shape[0]
         F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
         if debug_poison:
             F.fill_(float("nan"))                    # tests: an output that read a row before its synthesis turns into NaN
         host = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, pin_memory=True)
-        if self._d2h_stream is None:
-            self._d2h_stream = torch.cuda.Stream()
-        cs = self._d2h_stream
+        if (n_out, self.n_modes_out) not in _spared:
+            # first result of this size: leave a second page-locked block of the same size in the caching allocator, so that
+            # a caller who still holds this result during the next call does not stall in cudaHostAlloc then (~90 ms)
+            _spared.add((n_out, self.n_modes_out))
+            del_me = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, pin_memory=True)
+            del del_me
         tile = self.tile
         done = 0
+        timing = ops_timing()
         for k, (rlo, rhi, ev, flag) in enumerate(slabs):
             flag.wait()
             _trace(f"slab {k} queued on the copy stream")
@@ -656,20 +694,26 @@ class TransformPlan(GridPlan):
                 )
             out_hi = n_out if k == len(slabs) - 1 else min(n_out, max(done, ((rhi - margin - lo) // tile) * tile))
             if out_hi > done:
-                gridT = self._remap(t, F, uprm[done:out_hi], prep, tile)
+                rows_needed = self.input_rows_for_outputs(t_host, u_of_row(lo + done), u_of_row(lo + out_hi - 1))
+                gridT = self._remap(t, F, uprm[done:out_hi], prep, tile, rows_needed=rows_needed)
                 modes = self.analyze_tiled(gridT, out_hi - done)
-                ready = torch.cuda.Event()
+                ready = torch.cuda.Event(enable_timing=timing is not None)
                 ready.record(cur)
                 cs.wait_event(ready)
                 with torch.cuda.stream(cs):
                     host[done:out_hi].copy_(modes, non_blocking=True)
+                    if timing is not None:
+                        landed = torch.cuda.Event(enable_timing=True)
+                        landed.record(cs)
+                        timing.append((f"outputs {done}:{out_hi} computed", ready))
+                        timing.append((f"outputs {done}:{out_hi} landed on the host", landed))
                 modes.record_stream(cs)
                 del gridT, modes
                 done = out_hi
         _trace("all launches queued")
         cs.synchronize()
         _trace("last result slab landed")
-        return uprm, host.numpy()
+        return u_host.numpy(), host.numpy()
 
     def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
@@ -707,6 +751,12 @@ class TransformPlan(GridPlan):
 TRACE = None        # dev aid: set to a list to collect (label, perf_counter) marks of the end-to-end pipeline
 
 
+def ops_timing():
+    from . import ops
+
+    return ops.TIMING_EVENTS
+
+
 def _trace(label):
     if TRACE is not None:
         import time
@@ -716,6 +766,7 @@ def _trace(label):
 
 _plan_cache = {}
 PLAN_CACHE_SIZE = 8
+_spared = set()
 
 
 def _kwargs_key(kwargs):
@@ -851,6 +902,7 @@ class TimePrep:
             self._pool.append(self._host)
             self._host = None
             self._resolved = (int(v[0]), max(int(v[0]), int(v[1])), float(v[2]), float(v[3]))
+            self.dt_min = float(v[6])          # smallest sample spacing of the time axis
         return self._resolved[:2]
 
     @property

@@ -1,7 +1,7 @@
 """Integer stages of the RPXMB waveform codec on the GPU: the drop-in for scri/utilities.py:194-407 (`xor_timeseries`,
 `xor_timeseries_reverse`, `fletcher32`, `multishuffle`) as scri/SpEC/file_io/corotating_paired_xor.py and
-rotating_paired_xor_multishuffle_bzip2.py call them.  Bit-exact; numpy arrays in, numpy arrays out (CUDA tensors are accepted and
-returned as such).  No CPU fallback."""
+rotating_paired_xor_multishuffle_bzip2.py call them, and `corotating_paired_xor_encode`, the numerical part of the former's
+`save`.  Bit-exact; numpy arrays in, numpy arrays out.  No CPU fallback."""
 import ctypes
 import functools
 
@@ -93,3 +93,41 @@ def multishuffle(shuffle_widths, forward=True):
         return ops.to_host(out).view(dtype)
 
     return run
+
+
+def corotating_paired_xor_encode(w, L2norm_fractional_tolerance=1e-10, log_frame=None):
+    """The numerical part of scri/SpEC/file_io/corotating_paired_xor.py:save (lines 46-91, 121-126) on the GPU path: the
+    waveform goes to the corotating frame if it is inertial (tolerance 1e-10, z aligned over (0.1, 0.95), log of the frame
+    on its lattice), to conjugate pairs, is truncated to `L2norm_fractional_tolerance` of its norm, -0.0 becomes 0.0, and
+    successive instants are XORed.  Returns (w, streams, checksums): `w` the encoded copy, `streams` = {"time", "modes",
+    "log_frame"} as the uint64 arrays the reference writes to HDF5, `checksums` their Fletcher-32 values (the "validation"
+    block of the JSON file).  The HDF5 / JSON container itself stays with the reference."""
+    from . import _quaternion as Q
+    from .constants import Corotating, Inertial
+
+    if L2norm_fractional_tolerance == 0.0:
+        log_frame = Q.qlog(w.frame)[:, 1:]
+    else:
+        w = w.copy()
+        if log_frame is not None:
+            log_frame = np.array(log_frame, dtype=float)
+        if w.frameType == Inertial:
+            w, log_frame = w.to_corotating_frame(tolerance=1e-10, z_alignment_region=(0.1, 0.95), truncate_log_frame=True)
+            log_frame = log_frame[:, 1:]
+        if w.frameType != Corotating:
+            raise ValueError(f"Frame type of input waveform must be 'Corotating' or 'Inertial'; it is {w.frame_type_string}")
+        w.convert_to_conjugate_pairs()
+        w.truncate(tol=L2norm_fractional_tolerance)
+        if log_frame is None:
+            log_frame = Q.qlog(w.frame)[:, 1:]
+            power_of_2 = 2 ** (-np.floor(np.log2(L2norm_fractional_tolerance / 10))).astype("int")
+            log_frame = np.round(log_frame * power_of_2) / power_of_2
+        w.t = w.t + 0.0
+        w.data = w.data + 0.0
+        log_frame = np.ascontiguousarray(log_frame + 0.0)
+        w.t = xor_timeseries(np.ascontiguousarray(w.t))
+        w.data = xor_timeseries(np.ascontiguousarray(w.data))
+        log_frame = xor_timeseries(log_frame)
+    streams = {"time": w.t.view(np.uint64), "modes": w.data.view(np.uint64), "log_frame": np.ascontiguousarray(log_frame).view(np.uint64)}
+    checksums = {k: int(fletcher32(v)) for k, v in streams.items()}
+    return w, streams, checksums

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib, _sf, ops
 from .constants import Inertial, SpinWeights
-from .plan import TransformPlan, cached_transform_plan
+from .plan import TransformPlan, _trace, cached_transform_plan
 from .waveform_base import WaveformBase
 from .waveform_modes import WaveformModes
 
@@ -130,8 +130,9 @@ class WaveformGrid(WaveformBase):
         original_kwargs = kwargs.copy()
         # the modes stream in slab by slab on a copy stream while the plan is built; each slab is synthesized as it lands
         big = w_modes.data.nbytes >= (8 << 20)
+        t_d = ops.to_device(w_modes.t, np.float64)       # before the modes: a copy queued behind them would wait for all of them
         if big:
-            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, n_slabs=8)
+            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, weights=(1, 2, 3, 4, 4, 4, 3, 2, 1))
         else:
             a_d, slabs, a_fut = ops.to_device(w_modes.data, np.complex128), None, None
         try:
@@ -139,7 +140,6 @@ class WaveformGrid(WaveformBase):
                 w_modes.ell_min, w_modes.ell_max, w_modes.dataType, r_is_scaled_out=w_modes.r_is_scaled_out,
                 out_ell_max=ell_max, **kwargs,
             )
-            t_d = ops.to_device(w_modes.t, np.float64)
         except BaseException:
             if a_fut is not None:
                 a_fut.result()                   # let the copy thread finish with w_modes.data before unwinding
@@ -148,8 +148,11 @@ class WaveformGrid(WaveformBase):
             a_fut.result()
             _lib.require_cuda().cuda.current_stream().wait_event(slabs[-1][2])
             slabs = None
+        # (the provenance string is formatted while the first slabs are in flight, not after the results have landed)
+        statement = f"WaveformGrid.from_modes({w_modes}, **{original_kwargs}).to_modes({ell_max})"
         # modes land in pinned host memory slab by slab, the first output slabs while the last input slabs are still in flight
         uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4, t_host=np.asarray(w_modes.t, dtype=float))
+        _trace("plan.run returned")
         if a_fut is not None:
             a_fut.result()                       # surfaces a failed copy
         if plan.leftover_kwargs:
@@ -164,7 +167,7 @@ class WaveformGrid(WaveformBase):
             dataType=w_modes.dataType,
             r_is_scaled_out=w_modes.r_is_scaled_out,
             m_is_scaled_out=w_modes.m_is_scaled_out,
-            constructor_statement=f"WaveformGrid.from_modes({w_modes}, **{original_kwargs}).to_modes({ell_max})",
+            constructor_statement=statement,
         )
 
     def __repr__(self):

@@ -280,7 +280,68 @@ def abd():
     save("reference_abd.npz", **out)
 
 
+# ------------------------------------------------------------------------------------------------ 7. the codec chain of save()
+def codec_chain():
+    """The numerical part of scri/SpEC/file_io/corotating_paired_xor.py:save (lines 46-91 and 121-126; the HDF5 / JSON
+    container around it needs h5py and is not part of the path), executed with the reference's own methods on a
+    corotating-frame waveform: conjugate pairs -> truncate -> log(frame) on its lattice -> +0.0 -> XOR of successive
+    instants -> Fletcher-32 of the three streams, plus the RPXMB multishuffle of the mode stream."""
+    from scri.utilities import fletcher32, multishuffle, xor_timeseries
+
+    fr = np.load(os.path.join(HERE, "reference_frames.npz"))
+    tol = 1e-10
+    w = wm(fr["t"], fr["to_corot_data"], ell_min=int(fr["ell_min"]), ell_max=int(fr["ell_max"]), frame=fr["to_corot_frame"],
+           frameType=scri.Corotating)
+    out = dict(t=fr["t"], data=fr["to_corot_data"], frame=fr["to_corot_frame"], ell_min=fr["ell_min"], ell_max=fr["ell_max"], tol=tol)
+    w = w.copy()
+    w.convert_to_conjugate_pairs()
+    w.truncate(tol=tol)
+    out["truncated"] = w.data.copy()
+    log_frame = quaternion.as_float_array(np.log(w.frame))[:, 1:]
+    power_of_2 = 2 ** (-np.floor(np.log2(tol / 10))).astype("int")
+    log_frame = np.round(log_frame * power_of_2) / power_of_2
+    w.t += 0.0
+    w.data += 0.0
+    log_frame += 0.0
+    out["log_frame"] = log_frame.copy()
+    xor_timeseries(w.t)
+    xor_timeseries(w.data)
+    xor_timeseries(log_frame)
+    out["t_xor"] = w.t.view(np.uint64).copy()
+    out["modes_xor"] = w.data.view(np.uint64).copy()
+    out["log_frame_xor"] = log_frame.view(np.uint64).copy()
+    out["fletcher32"] = np.array([fletcher32(out["t_xor"]), fletcher32(out["modes_xor"]), fletcher32(out["log_frame_xor"])], dtype=np.uint64)
+    widths = (8, 8, 4, 4, 4, 2) + (1,) * 34
+    out["widths"] = np.array(widths)
+    out["modes_shuffled"] = multishuffle(tuple(widths))(out["modes_xor"].ravel().copy())
+    save("reference_codec_chain.npz", **out)
+
+
+# ------------------------------------------------------------------------------------------------ 8. <a|M|b> on differing layouts
+def expectation():
+    """scri/flux.py:81-179 with allow_LM_differ / allow_times_differ, and scri/extrapolation.py:47-125 (`intersection`)."""
+    from scri.extrapolation import intersection
+    from scri.flux import j_z, matrix_expectation_value, p_z
+
+    rng = np.random.default_rng(41)
+    ta, da = smooth_modes(n_times=140, ell_min=2, ell_max=6, t0=0.0, t1=60.0, seed=42, uniform=False)
+    tb, db = smooth_modes(n_times=171, ell_min=3, ell_max=8, t0=5.0, t1=72.0, seed=43)
+    a = wm(ta, da, ell_min=2, ell_max=6)
+    b = wm(tb, db, ell_min=3, ell_max=8)
+    out = dict(a_t=ta, a_data=da, b_t=tb, b_data=db)
+    for name, M in (("p_z", p_z), ("j_z", j_z)):
+        tt, val = matrix_expectation_value(a, M, b, allow_LM_differ=True, allow_times_differ=True)
+        out[f"{name}_t"], out[f"{name}_val"] = tt, val
+    b2 = wm(ta, smooth_modes(n_times=140, ell_min=3, ell_max=8, t0=0.0, t1=60.0, seed=44, uniform=False)[1], ell_min=3, ell_max=8)
+    out["b2_data"] = b2.data
+    out["lm_only_val"] = matrix_expectation_value(a, p_z, b2, allow_LM_differ=True)[1]
+    t1 = np.sort(rng.uniform(0, 100, size=130))
+    t2 = np.sort(rng.uniform(-10, 120, size=211))
+    out.update(i_t1=t1, i_t2=t2, i_out=intersection(t1, t2), i_out_kw=intersection(t1, t2, min_step=0.9, min_time=5.0, max_time=70.0))
+    save("reference_expectation.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["transforms", "modes", "frames", "samples", "codec", "abd"]
+    which = sys.argv[1:] or ["transforms", "modes", "frames", "samples", "codec", "abd", "codec_chain", "expectation"]
     for name in which:
         globals()[name]()

@@ -305,3 +305,19 @@ def test_squad_reproduces_knots_and_geodesics():
     errs = [np.abs(Q.squad(wobble(np.linspace(0, 10, n)), np.linspace(0, 10, n), tt) - wobble(tt)).max() for n in (50, 100, 200)]
     assert errs[0] > 3 * errs[1] > 9 * errs[2]
     assert Q.squad(np.empty((0, 4)), np.empty(0), tt).shape == (0, 4)
+
+
+def test_intersection_matches_reference_output():
+    """scri/extrapolation.py:47-125 as run by the reference (tests/golden/reference_expectation.npz) vs the host restatement
+    scri_b200.flux.intersection used by matrix_expectation_value(allow_times_differ=True): bit for bit."""
+    import os
+
+    from scri_b200.flux import intersection
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_expectation.npz"))
+    assert np.array_equal(intersection(g["i_t1"], g["i_t2"]), g["i_out"])
+    assert np.array_equal(intersection(g["i_t1"], g["i_t2"], min_step=0.9, min_time=5.0, max_time=70.0), g["i_out_kw"])
+    with pytest.raises(ValueError):
+        intersection(np.array([]), g["i_t2"])
+    with pytest.raises(ValueError):
+        intersection(g["i_t1"], g["i_t2"] + 1000.0)

@@ -173,3 +173,22 @@ def test_abd_matches_reference():
     assert rel(Rg, g["boosted_grid"]) < 1e-14
     k, ethk, ok, ok3 = abd_ref.conformal_factors(g["boost_velocity"], Rg)
     assert rel(k, g["cf_k"][0]) < 1e-14 and rel(ethk, g["cf_ethk_over_k"][0]) < 1e-14 and rel(ok3, g["cf_one_over_k_cubed"][0]) < 1e-14
+
+
+def test_codec_chain_matches_reference_bit_for_bit():
+    """scri/SpEC/file_io/corotating_paired_xor.py:46-91,121-126 executed with the reference's own methods vs the oracle's
+    restatements chained the same way."""
+    c = gold("reference_codec_chain.npz")
+    tol = float(c["tol"])
+    d = FR.truncate(FR.convert_to_conjugate_pairs(c["data"], int(c["ell_min"]), int(c["ell_max"])), tol)
+    assert np.array_equal(d.view(np.uint64), c["truncated"].view(np.uint64))
+    lf = quat.log(c["frame"])[:, 1:]
+    p2 = 2 ** (-np.floor(np.log2(tol / 10))).astype("int")
+    lf = np.round(lf * p2) / p2 + 0.0
+    assert np.array_equal(lf, c["log_frame"])
+    streams = [U.xor_timeseries(c["t"] + 0.0), U.xor_timeseries(d + 0.0), U.xor_timeseries(lf.copy())]
+    for got, key in zip(streams, ("t_xor", "modes_xor", "log_frame_xor")):
+        assert np.array_equal(np.ascontiguousarray(got).view(np.uint64), c[key]), key
+    assert [int(U.fletcher32(c[k])) for k in ("t_xor", "modes_xor", "log_frame_xor")] == [int(v) for v in c["fletcher32"]]
+    w = tuple(int(v) for v in c["widths"])
+    assert np.array_equal(U.multishuffle(w)(c["modes_xor"].ravel().copy()), c["modes_shuffled"])
