@@ -391,13 +391,14 @@ map2salm_dmma_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_t
 //   L1), K = j, N = t for the Re and the Im tile - the B fragment of both is one 16-byte load of f_m(theta_j) from the
 //   buffer the DFT results were written to (which is the tile buffer itself, after a barrier).
 template <int NT>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(544, 1)
 map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int n_theta, int n_phi,
                         const double2* __restrict__ trig, const double* __restrict__ Wt, int ell_min, int ell_max,
                         double2* __restrict__ out) {
     constexpr int T = 8;
     constexpr int BP = 16 * NT + 4;                                          // pitch of the folded trig table: conflict free
     constexpr int KF = 4;                                                    // k-steps of the folded DFT (n_phi <= 31)
+    constexpr int KQM = 8;                                                   // k-steps of the quadrature held in registers (n_theta <= 32)
     extern __shared__ __align__(128) double2 smp[];
     __shared__ __align__(8) unsigned long long mbar[2];
     const int L = ell_max, nm = 2 * L + 1, np1 = L + 1;
@@ -407,8 +408,10 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
     const size_t tile_elems = (size_t)G * T;
     const size_t buf_elems = (size_t)(G + 4) * T;
-    double2* sBuf[2] = {smp, smp + buf_elems};
-    double* sB = reinterpret_cast<double*>(smp + 2 * buf_elems);             // [4 KF][BP]: cos | sin of (m phi_k) / n_phi
+    // two tile buffers (TMA destinations), then f_m(theta_j) in a buffer of its own: a tile buffer is free for its refill as
+    // soon as the DFT has read it, one and a half tiles of work before the refill is needed
+    double2* sFm = smp + 2 * buf_elems;                                      // [T][nm][n_theta]
+    double* sB = reinterpret_cast<double*>(sFm + (size_t)T * nm * n_theta);  // [4 KF][BP]: cos | sin of (m phi_k) / n_phi
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int64_t ntiles = (n_times + T - 1) / T;
@@ -417,11 +420,10 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
     auto issue = [&](int64_t tile, int b) {   // thread 0 only
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[b])), "r"(tile_bytes) : "memory");
         const char* src = reinterpret_cast<const char*>(gridT + tile * (int64_t)tile_elems);
-        char* dst = reinterpret_cast<char*>(sBuf[b]);
+        const unsigned dst = smem_u32(smp + (size_t)b * buf_elems);
         for (unsigned off = 0; off < tile_bytes; off += 32768u) {
             const unsigned n = (tile_bytes - off < 32768u) ? (tile_bytes - off) : 32768u;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(dst + off)),
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
                          "l"(src + off), "r"(n), "r"(smem_u32(&mbar[b]))
                          : "memory");
         }
@@ -458,6 +460,28 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
             bfrag[ks][1] = sB[(4 * ks + kk) * BP + 8 + tq];
         }
     }
+    // quadrature unit of this warp when every unit has a warp of its own (the usual case): its weights W[(l, m), j] are the
+    // A fragments of every tile - read once, kept in registers
+    const bool own_unit = (nm * MT <= nwarp);
+    double wfrag[KQM];
+    int u_mi = 0, u_m = 0, u_la = 0;
+    bool u_valid = false, u_rowok = false;
+    if (own_unit && warp < nm * MT) {
+        u_mi = warp / MT;
+        const int mt = warp - u_mi * MT;
+        u_m = u_mi - L;
+        const int am = u_m < 0 ? -u_m : u_m;
+        const int lstart = (am > ell_min ? am : ell_min) + 8 * mt;
+        u_valid = lstart <= L;
+        u_la = lstart + tq;
+        u_rowok = u_valid && u_la <= L;
+#pragma unroll
+        for (int kq = 0; kq < KQM; ++kq) {
+            const int jj = 4 * kq + kk;
+            wfrag[kq] = (u_rowok && jj < n_theta) ? Wt[(size_t)(u_la * (u_la + 1) - ell_min * ell_min + u_m) * n_theta + jj] : 0.0;
+        }
+    }
+
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
@@ -471,8 +495,7 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
                              : "memory");
             }
         }
-        const double2* sTile = sBuf[b];
-        double2* sFm = sBuf[b];                                              // [T][nm][n_theta] after the barrier
+        const double2* sTile = smp + (size_t)b * buf_elems;
         // ---- phi-DFT: rings warp, warp + nwarp
         double acc[2][2][2 * NT][2];                                         // [ring][Re / Im part][cos tiles | sin tiles][2]
         double s0[2][2];
@@ -514,7 +537,11 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
                 }
             }
         }
-        __syncthreads();   // every warp is done reading the tile: f_m(theta_j) may overwrite it
+        __syncthreads();   // every warp is done reading the tile (and, from the previous tile, f_m): refill and overwrite
+        if (tid == 0) {
+            const int64_t nxt = tile + 2 * (int64_t)gridDim.x;
+            if (nxt < ntiles) issue(nxt, b);
+        }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int j = warp + r * nwarp;
@@ -538,48 +565,65 @@ map2salm_persist_kernel(const double2* __restrict__ gridT, int64_t n_times, int 
         __syncthreads();
         // ---- theta quadrature on the tensor cores: units (mi, 8-row block of l)
         const int64_t t0 = tile * T;
-        for (int unit = warp; unit < nm * MT; unit += nwarp) {
-            const int mi = unit / MT, mt = unit - mi * MT;
-            const int m = mi - L;
-            const int am = m < 0 ? -m : m;
-            const int lstart = (am > ell_min ? am : ell_min) + 8 * mt;
-            if (lstart > L) continue;
-            const int la = lstart + tq;                                      // my row of the A fragment
-            const bool rowok = la <= L;
-            const double* wrow = Wt + (size_t)(la * (la + 1) - ell_min * ell_min + m) * n_theta;
-            const double2* fcol = sFm + ((size_t)tq * nm + mi) * n_theta;    // B fragment: column t = tq, rows j
-            double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
-#pragma unroll 2
-            for (int kq = 0; kq < KQ; ++kq) {
-                const int jj = 4 * kq + kk;
-                const bool jok = jj < n_theta;
-                const double av = (rowok && jok) ? __ldg(wrow + jj) : 0.0;
-                const double2 bv = jok ? fcol[jj] : make_double2(0.0, 0.0);
-                dmma884(cre[0], cre[1], av, bv.x);
-                dmma884(cim[0], cim[1], av, bv.y);
-            }
-            if (rowok) {
-                const int lm = la * (la + 1) - ell_min * ell_min + m;
+        if (own_unit) {
+            if (u_valid) {
+                const double2* fcol = sFm + ((size_t)tq * nm + u_mi) * n_theta + kk;   // B fragment: column t = tq, rows j
+                double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int64_t tt = t0 + 2 * kk + i;
-                    if (tt < n_times) out[tt * n_modes + lm] = make_double2(cre[i], cim[i]);
+                for (int kq = 0; kq < KQM; ++kq) {
+                    if (kq < KQ) {
+                        const double2 bv = (4 * kq + kk < n_theta) ? fcol[4 * kq] : make_double2(0.0, 0.0);
+                        dmma884(cre[0], cre[1], wfrag[kq], bv.x);
+                        dmma884(cim[0], cim[1], wfrag[kq], bv.y);
+                    }
+                }
+                if (u_rowok) {
+                    const int lm = u_la * (u_la + 1) - ell_min * ell_min + u_m;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int64_t tt = t0 + 2 * kk + i;
+                        if (tt < n_times) out[tt * n_modes + lm] = make_double2(cre[i], cim[i]);
+                    }
+                }
+            }
+        } else {
+            for (int unit = warp; unit < nm * MT; unit += nwarp) {
+                const int mi = unit / MT, mt = unit - mi * MT;
+                const int m = mi - L;
+                const int am = m < 0 ? -m : m;
+                const int lstart = (am > ell_min ? am : ell_min) + 8 * mt;
+                if (lstart > L) continue;
+                const int la = lstart + tq;                                  // my row of the A fragment
+                const bool rowok = la <= L;
+                const double* wrow = Wt + (size_t)(la * (la + 1) - ell_min * ell_min + m) * n_theta;
+                const double2* fcol = sFm + ((size_t)tq * nm + mi) * n_theta;
+                double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
+#pragma unroll 2
+                for (int kq = 0; kq < KQ; ++kq) {
+                    const int jj = 4 * kq + kk;
+                    const bool jok = jj < n_theta;
+                    const double av = (rowok && jok) ? __ldg(wrow + jj) : 0.0;
+                    const double2 bv = jok ? fcol[jj] : make_double2(0.0, 0.0);
+                    dmma884(cre[0], cre[1], av, bv.x);
+                    dmma884(cim[0], cim[1], av, bv.y);
+                }
+                if (rowok) {
+                    const int lm = la * (la + 1) - ell_min * ell_min + m;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int64_t tt = t0 + 2 * kk + i;
+                        if (tt < n_times) out[tt * n_modes + lm] = make_double2(cre[i], cim[i]);
+                    }
                 }
             }
         }
-        __syncthreads();   // the buffer is free again
-        if (tid == 0) {
-            const int64_t nxt = tile + 2 * (int64_t)gridDim.x;
-            if (nxt < ntiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (f_m) before the async-proxy refill
-                issue(nxt, b);
-            }
-        }
+        // (no barrier here: the next tile's DFT touches only its own tile buffer; f_m is overwritten after the next barrier)
     }
 }
 
-static size_t persist_smem(int n_theta, int n_phi, int NT) {
-    return 2 * ((size_t)n_theta * n_phi + 4) * 8 * sizeof(double2) + 4 * 4 * (16 * NT + 4) * sizeof(double);
+static size_t persist_smem(int n_theta, int n_phi, int ell_max, int NT) {
+    return (2 * ((size_t)n_theta * n_phi + 4) * 8 + (size_t)8 * (2 * ell_max + 1) * n_theta) * sizeof(double2) +
+           4 * 4 * (16 * NT + 4) * sizeof(double);
 }
 
 static size_t dmma_smem(int n_theta, int n_phi, int ell_min, int ell_max, int NT) {
@@ -679,9 +723,9 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
         const int nwarp = (n_theta + 1) / 2;
         const size_t smem_d = dmma_smem(n_theta, n_phi, ell_min, ell_max, NT);
         const bool disabled = getenv("SCRIB200_ANALYSIS_SCALAR") != nullptr;
-        const size_t smem_p = persist_smem(n_theta, n_phi, NT);
+        const size_t smem_p = persist_smem(n_theta, n_phi, ell_max, NT);
         if (!disabled && !getenv("SCRIB200_ANALYSIS_NONPERSISTENT") && T == 8 && ell_max >= 1 && NT <= 2 && nwarp <= 20 &&
-            2 * ell_max + 1 <= n_phi && 2 * ell_max + 1 <= n_theta + 0 * n_phi && n_phi <= 31 && nwarp <= 18 && smem_p <= 225 * 1024) {
+            2 * ell_max + 1 <= n_phi && 2 * ell_max + 1 <= n_theta + 0 * n_phi && n_phi <= 31 && n_theta <= 32 && nwarp <= 17 && smem_p <= 225 * 1024) {
             static int n_sm = 0;
             if (n_sm == 0) {
                 int dev = 0;
@@ -694,8 +738,8 @@ extern "C" int scrib200_map2salm_tiled(const double* gridT, int tile, int64_t n_
             // unit (2 ell_max + 1 columns of m), so that neither phase needs a second, half-empty round
             int pw = nwarp < 4 ? 4 : nwarp;
             const int units = (2 * ell_max + 1) * ((ell_max - ell_min + 8) / 8);
-            if (units > pw) pw = units < 18 ? units : 18;
-            if (const char* env = getenv("SCRIB200_ANALYSIS_WARPS")) pw = atoi(env) >= nwarp && atoi(env) <= 18 ? atoi(env) : pw;
+            if (units > pw) pw = units < 17 ? units : 17;
+            if (const char* env = getenv("SCRIB200_ANALYSIS_WARPS")) pw = atoi(env) >= nwarp && atoi(env) <= 17 ? atoi(env) : pw;
             const int threads = 32 * pw;
             if (NT == 1) {
                 cudaFuncSetAttribute(map2salm_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);

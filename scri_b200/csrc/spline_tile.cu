@@ -325,13 +325,20 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    // (MODE 0) evaluation work: chunks of 32 consecutive outputs of one column, dealt to the warps round robin.  (ec, el) =
-    // (column, chunk inside the column) of my current chunk; its output times are fetched one chunk ahead.
-    int ec = 0, el = warp;
+    // (MODE 0) evaluation work: chunks of 32 consecutive outputs of one column; the flattened (column, chunk) list is cut
+    // into one contiguous range per warp, so a warp stays in one column for several chunks (its constants and its output
+    // pointer are then loop invariants).  (ec, el) = first (column, chunk) of my range, erem = chunks left in it.
+    int ec = 0, el = 0, erem = 0;
     double u_next = 0.0;
     if (MODE == 0) {
+        int total = 0;
+#pragma unroll
+        for (int c = 0; c < ST_COLS / 2; ++c) total += s_nch[c];
+        const int per = (total + nwarp - 1) / nwarp;
+        el = warp * per;
+        erem = (total - el < per) ? total - el : per;
         while (ec < ST_COLS / 2 && el >= s_nch[ec]) el -= s_nch[ec++];
-        if (ec < ST_COLS / 2) {
+        if (erem > 0 && ec < ST_COLS / 2) {               // output times of my first chunk: their latency hides behind the sweeps
             const int jn = s_jlo[ec] + (el << 5) + lane;
             if (jn < s_jhi[ec]) u_next = up[jn];
         }
@@ -462,20 +469,24 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
         double2* o2 = reinterpret_cast<double2*>(out);
         const int tmask = (1 << tshift) - 1;
         const int64_t jbase = (int64_t)bz * Nout;           // output rows of this series across the batch
-        while (ec < ST_COLS / 2) {
+        const int64_t ostride = ((int64_t)32 >> tshift) * ((int64_t)G << tshift);   // 32 outputs further down one column
+        while (erem > 0 && ec < ST_COLS / 2) {
             const int c = ec;
+            const int nrun = (s_nch[c] - el < erem) ? s_nch[c] - el : erem;       // my chunks in this column
             const int j1 = s_jhi[c];
-            const int j = s_jlo[c] + (el << 5) + lane;
-            const double u = u_next;
-            el += nwarp;                                    // my next chunk, and its output times
-            while (ec < ST_COLS / 2 && el >= s_nch[ec]) el -= s_nch[ec++];
-            if (ec < ST_COLS / 2) {
-                const int jn = s_jlo[ec] + (el << 5) + lane;
-                if (jn < s_jhi[ec]) u_next = up[jn];
-            }
-            if (j >= j1) continue;
-            const double k = s_k[c], al = s_al[c];
-            int i = a + __float2int_rd((float)(u - s_xa[c]) * s_slope[c]);    // guess, verified below
+            const int g = bx * (ST_COLS / 2) + c;
+            const double k = s_k[c], al = s_al[c], xa = s_xa[c];
+            const float slope = s_slope[c];
+            int j = s_jlo[c] + (el << 5) + lane;
+            const int64_t jg0 = jbase + j;
+            double2* optr = o2 + ((((jg0 >> tshift) * G + g) << tshift) + (jg0 & tmask));   // [rows / tile, G, tile]; tile 1: time-major
+            double u = u_next;
+            for (int run = 0; run < nrun; ++run, j += 32, optr += ostride) {
+                if (run + 1 < nrun) {                       // next chunk of the same column
+                    u_next = (j + 32 < j1) ? up[j + 32] : 0.0;
+                }
+                if (j < j1) {
+            int i = a + __float2int_rd((float)(u - xa) * slope);    // guess, verified below
             i = max(a, min(i, b - 1));
             double ti = STT(i), ti1 = STT(i + 1);
             double xi = __dmul_rn(k, __dsub_rn(ti, al));
@@ -521,9 +532,17 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
             double2 r;
             r.x = A * yi.x + B * yi1.x + (ca * Mi.x + cb * Mi1.x);
             r.y = A * yi.y + B * yi1.y + (ca * Mi.y + cb * Mi1.y);
-            const int g = bx * (ST_COLS / 2) + c;
-            const int64_t jg = jbase + j;
-            o2[(((jg >> tshift) * G + g) << tshift) + (jg & tmask)] = r;    // [rows / tile, G, tile]; tile = 1: time-major
+                    *optr = r;
+                }
+                u = u_next;
+            }
+            erem -= nrun;
+            el = 0;
+            ++ec;
+            if (erem > 0 && ec < ST_COLS / 2) {             // first chunk of the next column
+                const int jn = s_jlo[ec] + lane;
+                u_next = (jn < s_jhi[ec]) ? up[jn] : 0.0;
+            }
         }
     } else {
         // one thread per (knot, real column): 128-byte row segments of the time-major output
@@ -767,8 +786,8 @@ extern "C" int scrib200_spline_remap(const double* t, int64_t n_times, const dou
                      (long long)n_times);
     int tshift = 0;
     while ((1 << tshift) < tile) ++tshift;
-    SCRIB200_REQUIRE(G > 0 && (tile == 0 || (tile >= 2 && (1 << tshift) == tile)),
-                     "spline_remap: G=%d, tile=%d must be 0 (time-major output) or a power of two >= 2", G, tile);
+    SCRIB200_REQUIRE(G > 0 && (tile == 0 || (tile >= 2 && tile <= 32 && (1 << tshift) == tile)),
+                     "spline_remap: G=%d, tile=%d must be 0 (time-major output) or a power of two in 2..32", G, tile);
     SCRIB200_REQUIRE(aligned16(F) && aligned16(out) && aligned16(tab), "spline_remap: pointers must be 16-byte aligned");
     if (n_out <= 0) return SCRIB200_OK;
     return launch_tile<0>(t, n_times, F, G, kconf, alpha, tab, uprm, n_out, out, tile ? tshift : 0, halo, body, workspace,
@@ -784,8 +803,8 @@ extern "C" int scrib200_spline_remap_rows(const double* t, int64_t n_times, cons
     SCRIB200_REQUIRE(n_times >= 4, "spline_remap_rows: a cubic interpolating spline needs at least 4 knots; got %lld", (long long)n_times);
     int tshift = 0;
     while ((1 << tshift) < tile) ++tshift;
-    SCRIB200_REQUIRE(G > 0 && (tile == 0 || (tile >= 2 && (1 << tshift) == tile)),
-                     "spline_remap_rows: G=%d, tile=%d must be 0 (time-major output) or a power of two >= 2", G, tile);
+    SCRIB200_REQUIRE(G > 0 && (tile == 0 || (tile >= 2 && tile <= 32 && (1 << tshift) == tile)),
+                     "spline_remap_rows: G=%d, tile=%d must be 0 (time-major output) or a power of two in 2..32", G, tile);
     SCRIB200_REQUIRE(aligned16(F) && aligned16(out) && aligned16(tab), "spline_remap_rows: pointers must be 16-byte aligned");
     SCRIB200_REQUIRE(row_lo >= 0 && row_hi >= row_lo, "spline_remap_rows: rows [%lld, %lld)", (long long)row_lo, (long long)row_hi);
     if (n_out <= 0) return SCRIB200_OK;

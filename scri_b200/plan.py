@@ -258,13 +258,26 @@ class GridPlan:
             return self._host_pool.pop()
         return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
-    def prepare(self, t, overlapped=False, after=None):
+    def prepare(self, t, overlapped=False, after=None, speculate=False):
         """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
         the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`.
         `overlapped=True` launches on the plan's side stream so the (tiny, latency-bound) kernels run under the
         synthesis GEMM; the caller's stream must then `wait_event(prep.done)` before it consumes the tables.  `after`
-        (an event recorded when `t` became ready) lets the side stream start without waiting for work queued since."""
-        return TimePrep(self, t, overlapped, after)
+        (an event recorded when `t` became ready) lets the side stream start without waiting for work queued since.
+        `speculate=True`: if this very tensor (same storage, same version counter, same length) was prepared before, the
+        retained block and halo found then are assumed at once, so the caller can queue every later launch without waiting
+        for the 64-byte read-back in the middle of the step; `TimePrep.verify()` compares with what the kernels found
+        this time (and the caller repeats the step in the rare case they differ)."""
+        prep = TimePrep(self, t, overlapped, after)
+        if speculate:
+            if not hasattr(self, "_prep_memo"):
+                self._prep_memo = {}
+            prep._memo = self._prep_memo
+            prep._memo_key = (t.data_ptr(), getattr(t, "_version", 0), int(t.shape[0]))
+            seen = self._prep_memo.get(prep._memo_key)
+            if seen is not None:
+                prep._assumed = seen
+        return prep
 
     def output_times(self, t, t_ends=None):
         """u'_i and the retained block (waveform_grid.py:564-568) as a device tensor.  `t_ends` is accepted for
@@ -731,21 +744,27 @@ class TransformPlan(GridPlan):
         ready = self.torch.cuda.Event()
         ready.record(cur)
         F = self.synthesize(data, t, slabs)     # queued first: the GPU is busy while the host launches the preparation
-        if prep is None:
-            prep = self.prepare(t, overlapped=True, after=ready)
-        cur.wait_event(prep.done)
-        uprm = prep.uprm
-        if self.tile and not return_grid:
-            if host_slabs and uprm.shape[0] >= 8192:
-                return uprm, self._remap_analyze_to_host(t, F, uprm, prep, host_slabs)
-            gridT = self.remap_tiled(t, F, uprm, prep)
-            del F
-            return uprm, self.analyze_tiled(gridT, uprm.shape[0])
-        grid = self.remap(t, F, uprm, prep)
-        del F
-        if return_grid:
-            return uprm, grid
-        return uprm, self.analyze(grid)
+        mine = prep is None
+        for attempt in range(2):
+            if mine:
+                # a time axis seen before: its retained block is assumed, so nothing waits for the read-back mid-step
+                prep = self.prepare(t, overlapped=True, after=ready, speculate=(attempt == 0))
+            cur.wait_event(prep.done)
+            uprm = prep.uprm
+            if self.tile and not return_grid:
+                if host_slabs and uprm.shape[0] >= 8192:
+                    out = self._remap_analyze_to_host(t, F, uprm, prep, host_slabs)
+                else:
+                    gridT = self.remap_tiled(t, F, uprm, prep)
+                    out = self.analyze_tiled(gridT, uprm.shape[0])
+                    del gridT
+            else:
+                grid = self.remap(t, F, uprm, prep)
+                out = grid if return_grid else self.analyze(grid)
+            if not mine or prep.verify():
+                return uprm, out
+            ready = self.torch.cuda.Event()       # the time axis changed behind the same storage: once more, unassumed
+            ready.record(cur)
 
 
 TRACE = None        # dev aid: set to a list to collect (label, perf_counter) marks of the end-to-end pipeline
@@ -894,16 +913,39 @@ class TimePrep:
         for x in (self.info, self.tab, self.uprm_full):
             x.record_stream(side)
         self._resolved = None
+        self._assumed = None
+        self._memo = None
+        self._memo_key = None
+
+    def _read_back(self):
+        self._ready.synchronize()
+        v = self._host.tolist()
+        self._pool.append(self._host)
+        self._host = None
+        return (int(v[0]), max(int(v[0]), int(v[1])), float(v[2]), float(v[3]), float(v[6]))
 
     def resolve(self):
         if self._resolved is None:
-            self._ready.synchronize()
-            v = self._host.tolist()
-            self._pool.append(self._host)
-            self._host = None
-            self._resolved = (int(v[0]), max(int(v[0]), int(v[1])), float(v[2]), float(v[3]))
-            self.dt_min = float(v[6])          # smallest sample spacing of the time axis
+            if self._assumed is not None:          # speculation: nothing to wait for (see GridPlan.prepare)
+                self._resolved = self._assumed
+            else:
+                self._resolved = self._read_back()
+                if self._memo is not None:
+                    if len(self._memo) > 64:
+                        self._memo.clear()
+                    self._memo[self._memo_key] = self._resolved
+            self.dt_min = self._resolved[4]        # smallest sample spacing of the time axis
         return self._resolved[:2]
+
+    def verify(self):
+        """True when the assumed retained block / decay diagnostics are what the kernels found this time (always true
+        without speculation).  Waits for the read-back only - it completes right after the four preparation kernels."""
+        if self._assumed is None or self._host is None:
+            return True
+        actual = self._read_back()
+        self._memo[self._memo_key] = actual
+        halo = lambda r: 32 if r[2] <= 1e-15 else (64 if r[3] <= 1e-15 else 128)
+        return actual[:2] == self._assumed[:2] and halo(actual) == halo(self._assumed)
 
     @property
     def uprm(self):
@@ -914,7 +956,7 @@ class TimePrep:
         """Rows of run-in per tile side from the measured decay of the recurrences (0.268^k on uniform samples)."""
         self.resolve()
         if not halo:
-            d32, d64 = self._resolved[2:]
+            d32, d64 = self._resolved[2:4]
             halo = 32 if d32 <= 1e-15 else (64 if d64 <= 1e-15 else 128)
         return int(halo), int(body)
 

@@ -341,7 +341,29 @@ def expectation():
     save("reference_expectation.npz", **out)
 
 
+# ------------------------------------------------------------------------------------------------ 9. coprecessing frame
+def coprecessing():
+    """scri/rotations.py:14-48 on a waveform sampled finely enough for the reference's sign rule to be well posed.
+    mode_calculations.py:316-363 flips the raw eigenvector of step i when |v_i - v_{i-1}|^2 > |v_i|^2, i.e. when their dot
+    product is below 1/2 - not below 0 - so when consecutive principal axes are more than 60 degrees apart the result depends
+    on the sign LAPACK's eigh happened to give the raw vector.  In reference_frames.npz (dt = 0.5 M) that happens around the
+    merger (|dot| down to 0.32); here (dt = 0.25 M) the smallest |dot| is 0.81 and the outcome is a property of the waveform."""
+    out = {}
+    W = scri.sample_waveforms.fake_precessing_waveform(t_0=-20.0, t_1=300.0, dt=0.25, ell_max=4)
+    out.update(t=W.t, data=W.data, ell_min=W.ell_min, ell_max=W.ell_max)
+    ev, evec = np.linalg.eigh(W.LLMatrix())
+    out["min_abs_dot"] = np.abs(np.sum(evec[1:, :, 2] * evec[:-1, :, 2], axis=1)).min()
+    out["dpa"] = W.LLDominantEigenvector(RoughDirectionIndex=W.n_times // 8)
+    Wp = W.copy().to_coprecessing_frame()
+    out["coprec_data"], out["coprec_frame"] = Wp.data, F(Wp.frame)
+    Wpt = W.copy().to_coprecessing_frame(transition_times=(200.0, 260.0))
+    out["coprec_tt_data"], out["coprec_tt_frame"] = Wpt.data, F(Wpt.frame)
+    Wpr = W.copy().to_coprecessing_frame(RoughDirection=np.array([0.1, 0.1, -1.0]), RoughDirectionIndex=40)
+    out["coprec_rough_frame"] = F(Wpr.frame)
+    save("reference_coprecessing.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["transforms", "modes", "frames", "samples", "codec", "abd", "codec_chain", "expectation"]
+    which = sys.argv[1:] or ["transforms", "modes", "frames", "samples", "codec", "abd", "codec_chain", "expectation", "coprecessing"]
     for name in which:
         globals()[name]()

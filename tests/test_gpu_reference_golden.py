@@ -162,13 +162,13 @@ def test_frames_match_reference_output():
     assert rel(w.data, R.rotate_decomposition_basis(Wo(), w.frame.copy()).data) < RTOL
     assert rel(w.data, g["to_corot_data"]) < 1e-6                           # modes amplify the 3e-8 frame difference by ~2 ell
     assert rel(w.to_inertial_frame().data, g["to_inertial_data"]) < 1e-12
-    w = W().to_coprecessing_frame()
-    assert w.frameType == sb.Coprecessing
-    assert rel(w.frame, g["coprec_frame"]) < 1e-10 and rel(w.data, g["coprec_data"]) < 1e-10, (rel(w.frame, g["coprec_frame"]), rel(w.data, g["coprec_data"]))
-    w = W().to_coprecessing_frame(transition_times=(300.0, 360.0))
-    assert rel(w.frame, g["coprec_tt_frame"]) < 1e-7 and rel(w.data, g["coprec_tt_data"]) < 1e-6    # re-integrated tail
-    w = W().to_coprecessing_frame(RoughDirection=np.array([0.1, 0.1, -1.0]), RoughDirectionIndex=40)
-    assert rel(w.frame, g["coprec_rough_frame"]) < 1e-10
+    # coprecessing frame: this fixture is sampled so coarsely (0.5 M) that around the merger consecutive principal axes
+    # are up to 71 degrees apart; the reference flips step i when dot(v_i, v_{i-1}) < 1/2 (mode_calculations.py:316-363), so
+    # there its result depends on the sign LAPACK's eigh gave the raw vector.  Here only the axis itself is compared; the
+    # well-posed case is test_coprecessing_frame_matches_reference_output.
+    dpa = W().LLDominantEigenvector(RoughDirectionIndex=len(g["t"]) // 8)
+    dpo = R.LLDominantEigenvector(Wo(), RoughDirectionIndex=len(g["t"]) // 8)
+    assert np.abs(np.abs(np.sum(dpa * dpo, axis=1)) - 1).max() < 1e-12
     from scri_b200.mode_calculations import minimal_rotation
 
     assert rel(minimal_rotation(g["corot_frame"], g["t"], 3), g["minimal_rotation"]) < 1e-12
@@ -291,3 +291,24 @@ def test_matrix_expectation_value_on_differing_layouts_matches_reference_output(
         matrix_expectation_value(a, p_z, b2)
     with pytest.raises(ValueError):
         matrix_expectation_value(a, p_z, b, allow_LM_differ=True)
+
+
+def test_coprecessing_frame_matches_reference_output():
+    """scri/rotations.py:14-48 as run by the reference on a waveform sampled at 0.25 M (consecutive principal axes never more
+    than 36 degrees apart, so the reference's sign rule is well posed): LLDominantEigenvector with its sign walk, sqrt(-dpa z),
+    minimal_rotation, and the `transition_times` branch that damps and re-integrates the frame's angular velocity."""
+    g = gold("reference_coprecessing.npz")
+    lmin, lmax = int(g["ell_min"]), int(g["ell_max"])
+    assert float(g["min_abs_dot"]) > 0.8
+
+    def W():
+        return wm(g["t"], g["data"], ell_min=lmin, ell_max=lmax)
+
+    assert rel(W().LLDominantEigenvector(RoughDirectionIndex=len(g["t"]) // 8), g["dpa"]) < 1e-11
+    w = W().to_coprecessing_frame()
+    assert w.frameType == sb.Coprecessing
+    assert rel(w.frame, g["coprec_frame"]) < 1e-10 and rel(w.data, g["coprec_data"]) < 1e-10, (rel(w.frame, g["coprec_frame"]), rel(w.data, g["coprec_data"]))
+    w = W().to_coprecessing_frame(transition_times=(200.0, 260.0))
+    assert rel(w.frame, g["coprec_tt_frame"]) < 1e-7 and rel(w.data, g["coprec_tt_data"]) < 1e-6    # re-integrated tail: ODE tolerance
+    w = W().to_coprecessing_frame(RoughDirection=np.array([0.1, 0.1, -1.0]), RoughDirectionIndex=40)
+    assert rel(w.frame, g["coprec_rough_frame"]) < 1e-10

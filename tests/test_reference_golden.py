@@ -192,3 +192,13 @@ def test_codec_chain_matches_reference_bit_for_bit():
     assert [int(U.fletcher32(c[k])) for k in ("t_xor", "modes_xor", "log_frame_xor")] == [int(v) for v in c["fletcher32"]]
     w = tuple(int(v) for v in c["widths"])
     assert np.array_equal(U.multishuffle(w)(c["modes_xor"].ravel().copy()), c["modes_shuffled"])
+
+
+def test_coprecessing_matches_reference_finely_sampled():
+    g = gold("reference_coprecessing.npz")
+    W = R.Modes(t=g["t"], data=g["data"].copy(), ell_min=int(g["ell_min"]), ell_max=int(g["ell_max"]))
+    assert rel(R.LLDominantEigenvector(W, RoughDirectionIndex=W.n_times // 8), g["dpa"]) < 1e-12
+    o, fr = FR.to_coprecessing_frame(W)
+    assert rel(fr, g["coprec_frame"]) < 1e-12 and rel(o.data, g["coprec_data"]) < 1e-12
+    o, fr = FR.to_coprecessing_frame(W, transition_times=(200.0, 260.0))
+    assert rel(fr, g["coprec_tt_frame"]) < 1e-7 and rel(o.data, g["coprec_tt_data"]) < 1e-7
