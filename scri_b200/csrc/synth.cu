@@ -49,7 +49,7 @@ template <int BK, int STAGES, int BM>
 __global__ void __launch_bounds__(2 * BM, 256 / BM)
 swsh_synth_dmma_kernel(const double* __restrict__ A, int64_t M, int K, const double* __restrict__ B, int Kpad,
                        int Ncpad, const double* __restrict__ offset, const double* __restrict__ scale, int Nc,
-                       double* __restrict__ C) {
+                       double* __restrict__ C, int band) {
     constexpr int AS = SynthCfg<BK, STAGES, BM>::AS, A_STAGE = SynthCfg<BK, STAGES, BM>::A_STAGE, B_STAGE = SynthCfg<BK, STAGES, BM>::B_STAGE;
     constexpr int SYNTH_THREADS = 2 * BM;
     extern __shared__ __align__(16) double smem_d[];
@@ -59,8 +59,22 @@ swsh_synth_dmma_kernel(const double* __restrict__ A, int64_t M, int K, const dou
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;           // 4 x 2 warps
-    const int64_t row0 = (int64_t)blockIdx.y * BM;
-    const int col0 = blockIdx.x * BN;
+    // Tile walk: CTAs are dealt in launch order to bands of `band` column tiles; inside a band the column tiles of one row
+    // tile come first (they share the A row tile through L2), then the next row tile.  The B panel of a band (band x Kpad
+    // x 64 doubles, sized by the host to sit in L2) is then read from HBM once, and A once per band - without this a
+    // table larger than L2 (ell_max = 32: 616 MB) was streamed from HBM once per row tile.
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (band < (int)gridDim.x) {
+        const int64_t lin = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const int64_t per_band = (int64_t)band * gridDim.y;
+        const int bnd = (int)(lin / per_band);
+        const int width = min(band, (int)gridDim.x - bnd * band);      // the last band may be narrower
+        const int64_t rem = lin - (int64_t)bnd * per_band;
+        by = (int)(rem / width);
+        bx = bnd * band + (int)(rem - (int64_t)by * width);
+    }
+    const int64_t row0 = (int64_t)by * BM;
+    const int col0 = bx * BN;
     const int KT = Kpad / BK;
 
     auto load_stage = [&](int stage, int kt) {
@@ -167,6 +181,9 @@ extern "C" int scrib200_swsh_synthesize(const double* modes, int64_t n_times, in
     // column tiles fastest so the CTAs sharing an A row-tile run together (A is then read from HBM once);
     // gridDim.y is limited to 65535, so very long series go in slabs of rows
     const int64_t max_rows = (int64_t)65535 * 64;
+    // column tiles per band: 48 MB of the table (B200: 126 MB of L2, shared with the A rows and the output in flight)
+    int band = (int)(((size_t)48 << 20) / ((size_t)Kpad * BN * sizeof(double)));
+    if (band < 1) band = 1;
     for (int64_t r0 = 0; r0 < n_times; r0 += max_rows) {
         int64_t rows = n_times - r0 < max_rows ? n_times - r0 : max_rows;
 #define SYNTH_LAUNCH(BK_, ST_, BM_)                                                                                    \
@@ -175,7 +192,7 @@ extern "C" int scrib200_swsh_synthesize(const double* modes, int64_t n_times, in
         cudaFuncSetAttribute(swsh_synth_dmma_kernel<BK_, ST_, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                              (int)SynthCfg<BK_, ST_, BM_>::SMEM);                                                      \
         swsh_synth_dmma_kernel<BK_, ST_, BM_><<<grid_, 2 * BM_, SynthCfg<BK_, ST_, BM_>::SMEM, (cudaStream_t)stream>>>( \
-            modes + r0 * K, rows, K, Bmat, Kpad, Ncpad, offset, scale, Nc, F + r0 * Nc);                               \
+            modes + r0 * K, rows, K, Bmat, Kpad, Ncpad, offset, scale, Nc, F + r0 * Nc, band);                         \
     } while (0)
         // measured at config 2 (K = 160): 128x64 / BK16 / 3 stages 1.47 ms, 64x64 / BK16 / 3 stages 1.33 ms, 64x64 / BK8 / 4 stages 1.30 ms
         if (variant == 1) SYNTH_LAUNCH(16, 3, 128);

@@ -151,7 +151,9 @@ def transform_batch_host(plan, t, data_host, sub_batch=512, out=None):
     """BASELINE configs[2] from host memory: `data_host` [B, N, n_modes] complex128 numpy (this rank's shard of the batch;
     page-locked memory goes up by DMA, anything else through the staging ring) -> (u' [N'] numpy, modes' [B, N', n_out]
     numpy in pinned memory).  Sub-batches are double-buffered on the device: the H2D of sub-batch i+1 and the D2H of
-    sub-batch i-1 run on their own streams under the kernels of sub-batch i (plan.run_batch)."""
+    sub-batch i-1 run on their own streams under the kernels of sub-batch i (plan.run_batch).  `data_host` may also be a
+    sequence of such arrays (a shard that lives in several host blocks): they flow through ONE pipeline without draining
+    in between, and `out`, if given, is the matching sequence of result arrays (a list of results is returned)."""
     import ctypes
 
     import torch
@@ -160,48 +162,54 @@ def transform_batch_host(plan, t, data_host, sub_batch=512, out=None):
 
     lib = _lib.load()
     t_d = ops.to_device(t, np.float64)
-    B, N, n = data_host.shape
-    if data_host.dtype != np.complex128 or not data_host.flags.c_contiguous:
-        data_host = np.ascontiguousarray(data_host, dtype=np.complex128)
-    sub = max(1, min(int(sub_batch), B))
+    single = isinstance(data_host, np.ndarray)
+    blocks = [data_host] if single else list(data_host)
+    outs = [out] if single else (list(out) if out is not None else [None] * len(blocks))
+    blocks = [b if (b.dtype == np.complex128 and b.flags.c_contiguous) else np.ascontiguousarray(b, dtype=np.complex128) for b in blocks]
+    N, n = blocks[0].shape[1:]
+    sub = max(1, min(int(sub_batch), max(b.shape[0] for b in blocks)))
     cur = torch.cuda.current_stream()
     cin, cout = torch.cuda.Stream(), torch.cuda.Stream()
     bufs = [torch.empty((sub, N, n), dtype=torch.complex128, device="cuda") for _ in range(2)]
     free = [None, None]                                   # event: the kernels that read buffer b are done
     row_bytes = N * n * 16
     u_host = None
-    host_out = out
-    for i, b0 in enumerate(range(0, B, sub)):
-        nb = min(sub, B - b0)
-        b = i & 1
-        if free[b] is not None:
-            cin.wait_event(free[b])
-        else:
-            cin.wait_stream(cur)
-        _lib.check(lib.scrib200_h2d(bufs[b].data_ptr(), data_host.ctypes.data + b0 * row_bytes, nb * row_bytes,
-                                    ctypes.c_void_p(cin.cuda_stream)), "h2d")
-        landed = torch.cuda.Event()
-        landed.record(cin)
-        cur.wait_event(landed)
-        u, m = plan.run_batch(t_d, bufs[b][:nb])
-        done = torch.cuda.Event()
-        done.record(cur)
-        free[b] = done
-        if host_out is None:
-            host_out = torch.empty((B, m.shape[1], m.shape[2]), dtype=torch.complex128, pin_memory=True)
-        elif not torch.is_tensor(host_out):
-            host_out = torch.from_numpy(host_out)
-        cout.wait_event(done)
-        with torch.cuda.stream(cout):
-            host_out[b0 : b0 + nb].copy_(m, non_blocking=True)
-            if u_host is None:
-                u_host = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
-                u_host.copy_(u, non_blocking=True)
-        m.record_stream(cout)
-        u.record_stream(cout)
+    i = 0
+    for k, block in enumerate(blocks):
+        B = block.shape[0]
+        for b0 in range(0, B, sub):
+            nb = min(sub, B - b0)
+            b = i & 1
+            i += 1
+            if free[b] is not None:
+                cin.wait_event(free[b])
+            else:
+                cin.wait_stream(cur)
+            _lib.check(lib.scrib200_h2d(bufs[b].data_ptr(), block.ctypes.data + b0 * row_bytes, nb * row_bytes,
+                                        ctypes.c_void_p(cin.cuda_stream)), "h2d")
+            landed = torch.cuda.Event()
+            landed.record(cin)
+            cur.wait_event(landed)
+            u, m = plan.run_batch(t_d, bufs[b][:nb])
+            done = torch.cuda.Event()
+            done.record(cur)
+            free[b] = done
+            if outs[k] is None:
+                outs[k] = torch.empty((B, m.shape[1], m.shape[2]), dtype=torch.complex128, pin_memory=True)
+            elif not torch.is_tensor(outs[k]):
+                outs[k] = torch.from_numpy(outs[k])
+            cout.wait_event(done)
+            with torch.cuda.stream(cout):
+                outs[k][b0 : b0 + nb].copy_(m, non_blocking=True)
+                if u_host is None:
+                    u_host = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+                    u_host.copy_(u, non_blocking=True)
+            m.record_stream(cout)
+            u.record_stream(cout)
     cout.synchronize()
     cur.synchronize()
-    return u_host.numpy(), host_out.numpy()
+    results = [o.numpy() for o in outs]
+    return u_host.numpy(), (results[0] if single else results)
 
 
 SPLINE_DECAY_ROWS = 40   # rows after which a not-a-knot spline has forgotten its end conditions (0.268^40 ~ 1e-23)
