@@ -84,9 +84,12 @@ def load(build_if_missing=True):
 
             if _build.needs_build() and os.path.exists("/usr/local/cuda/bin/nvcc"):
                 _build.build()
-        except Exception:
+        except Exception as exc:
             if not os.path.exists(LIB_PATH):
                 raise
+            import warnings
+
+            warnings.warn(f"scri_b200: rebuilding libscrib200.so failed ({exc}); loading the existing, possibly stale, library")
     if not os.path.exists(LIB_PATH):
         raise Scrib200Error(
             f"{LIB_PATH} is missing: build it with `python -m scri_b200.build` (nvcc, sm_100a). "

@@ -259,6 +259,186 @@ rotate_modes_reg_kernel(double2* __restrict__ data, int64_t n_times, int ell_min
     }
 }
 
+// ---- third-generation kernel (ell_max <= 16): lanes run along TIME, a warp owns one |m| (and the opposite end L - |m|
+// of the range, for balance).  Everything that steers the m' and l loops - the start l0 = max(m', |m|), the recurrence
+// coefficients, the seeds - is then uniform across the warp (read from constant memory, no predication, every lane
+// busy), and each thread serves FOUR matrix elements per recurrence step through the symmetries
+//     P(-m', -m) = (-1)^{m'+m} P(m', m),      P(m', -m) = (-1)^{m'+m} P(-m', m):
+// the chains P = P(m', m) and N = P(-m', m) give   out[+m] += P b[+m'] + N b[-m'],   out[-m] += (-1)^{m'+m} (N b[+m'] + P b[-m']).
+// The tile of 32 time steps is staged through shared memory transposed ([mode][time], pitch 33) and premultiplied by
+// e^{i m'(A-B)}; the accumulators of up to 9 values of l live in registers (ell_max > 8 takes two passes over l, the
+// recurrence restarted), the result is multiplied by e^{i m(A+B)} and stored.  A time step whose Rb is exactly zero is
+// finished by an exact diagonal pass so that the identity rotation stays bit-exact.
+__constant__ double c_rot_seed[33 * 33];      // [m' + 16][m + 16]
+__constant__ double2 c_rot_uv[17 * 33];       // [l][m + 16]
+
+constexpr int ROT3_TB = 32;
+constexpr int ROT3_PITCH = ROT3_TB + 1;
+
+// constant tables at a fixed pitch: seed[(m' + 16) * 33 + m + 16], uv[l * 33 + m + 16] - with l a compile-time constant in
+// the unrolled ladder every index is an immediate plus one register
+constexpr int ROT3_C = 16, ROT3_NM = 33;
+
+template <int LA, int LB>
+__device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const double* __restrict__ s_ra, const double* __restrict__ s_rb,
+                                          const double2* __restrict__ s_pw, double cosb, bool diagonal, int tt, int m, int L, int ell_min,
+                                          double2* __restrict__ orow) {
+    constexpr int NA = LB - LA + 1;
+    const int lmin2 = ell_min * ell_min;
+    double pr[NA], pi[NA], nr[NA], ni[NA];                  // out[+m] and out[-m] for l = LA .. LB
+#pragma unroll
+    for (int i = 0; i < NA; ++i) pr[i] = pi[i] = nr[i] = ni[i] = 0.0;
+    const int lend = LB < L ? LB : L;
+    const double2* uvm = c_rot_uv + ROT3_C + m;             // + l * 33
+    for (int mp = 0; mp <= L; ++mp) {
+        const int l0 = mp > m ? mp : m;
+        if (l0 > lend) break;                                // l0 grows with m'
+        const int ka = mp + m, kb = mp > m ? mp - m : m - mp;            // exponents of ra, rb for (m', m); swapped for (-m', m)
+        double P = c_rot_seed[(mp + ROT3_C) * ROT3_NM + m + ROT3_C] * (s_ra[ka * ROT3_TB + tt] * s_rb[kb * ROT3_TB + tt]);
+        double N = (mp > 0) ? c_rot_seed[(ROT3_C - mp) * ROT3_NM + m + ROT3_C] * (s_ra[kb * ROT3_TB + tt] * s_rb[ka * ROT3_TB + tt]) : 0.0;
+        double P1 = 0.0, N1 = 0.0;
+        const double sg = ((mp + m) & 1) ? -1.0 : 1.0;
+        const double mmp = (double)(m * mp);
+        const double2* bpp = s_b + (mp - lmin2) * ROT3_PITCH + tt;      // + l (l + 1) * 33: row of (l, +m')
+        const double2* bnp = s_b + (-mp - lmin2) * ROT3_PITCH + tt;     //                   row of (l, -m')
+        const double2* uvp = c_rot_uv + ROT3_C + mp;                    // + l * 33
+        // the unrolled ladder over l is entered at l0 (uniform across the warp): no test per skipped rung
+#define ROT3_STEP(l_)                                                                                          \
+    case l_:                                                                                                   \
+        if (l_ <= LB && l_ <= lend) {                                                                          \
+            if (l_ >= LA && l_ >= ell_min) {                                                                   \
+                const double2 bp = bpp[l_ * (l_ + 1) * ROT3_PITCH], bn = bnp[l_ * (l_ + 1) * ROT3_PITCH];      \
+                constexpr int ia = (l_ >= LA) ? l_ - LA : 0;                                                   \
+                pr[ia] = fma(P, bp.x, fma(N, bn.x, pr[ia]));                                                   \
+                pi[ia] = fma(P, bp.y, fma(N, bn.y, pi[ia]));                                                   \
+                nr[ia] = fma(sg, fma(N, bp.x, P * bn.x), nr[ia]);                                              \
+                ni[ia] = fma(sg, fma(N, bp.y, P * bn.y), ni[ia]);                                              \
+            }                                                                                                  \
+            if (l_ < LB && l_ < lend) {                                                                        \
+                const double2 f1 = uvp[l_ * ROT3_NM], f2 = uvm[l_ * ROT3_NM];                                  \
+                constexpr double rl = (l_ > 0) ? 1.0 / (double)(l_ * (l_ + 1)) : 0.0;                          \
+                const double a_ = f1.x * f2.x, c_ = f1.y * f2.y, tb = mmp * rl;                                \
+                const double Pq = a_ * (cosb - tb) * P - c_ * P1;                                              \
+                const double Nq = a_ * (cosb + tb) * N - c_ * N1;                                              \
+                P1 = P;                                                                                        \
+                N1 = N;                                                                                        \
+                P = Pq;                                                                                        \
+                N = Nq;                                                                                        \
+            }                                                                                                  \
+        }
+        switch (l0) {
+            ROT3_STEP(0) ROT3_STEP(1) ROT3_STEP(2) ROT3_STEP(3) ROT3_STEP(4) ROT3_STEP(5) ROT3_STEP(6) ROT3_STEP(7) ROT3_STEP(8)
+            ROT3_STEP(9) ROT3_STEP(10) ROT3_STEP(11) ROT3_STEP(12) ROT3_STEP(13) ROT3_STEP(14) ROT3_STEP(15) ROT3_STEP(16)
+            default: break;
+        }
+#undef ROT3_STEP
+    }
+    if (diagonal) {   // Rb == 0 exactly: D^l_{m'm} = delta_{m'm} ra^{2|m|} (phases applied outside)
+        const double mag = s_ra[2 * m * ROT3_TB + tt];
+#pragma unroll
+        for (int l = LA; l <= LB; ++l)
+            if (l >= m && l >= ell_min && l <= L) {
+                const double2 bp = s_b[(l * (l + 1) - lmin2 + m) * ROT3_PITCH + tt];
+                const double2 bn = s_b[(l * (l + 1) - lmin2 - m) * ROT3_PITCH + tt];
+                pr[l - LA] = mag * bp.x;
+                pi[l - LA] = mag * bp.y;
+                nr[l - LA] = mag * bn.x;
+                ni[l - LA] = mag * bn.y;
+            }
+    }
+    const double2 pw = s_pw[m * ROT3_TB + tt];
+#pragma unroll
+    for (int l = LA; l <= LB; ++l)
+        if (l >= m && l >= ell_min && l <= L) {
+            orow[l * (l + 1) - lmin2 + m] = cmul(make_double2(pr[l - LA], pi[l - LA]), pw);
+            if (m > 0) orow[l * (l + 1) - lmin2 - m] = cmul(make_double2(nr[l - LA], ni[l - LA]), cconj(pw));
+        }
+}
+
+template <int LT>
+__global__ void __launch_bounds__(32 * (LT / 2 + 1))
+rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_min, int ell_max,
+                         const double2* __restrict__ spinors, int64_t spinor_stride) {
+    extern __shared__ double2 sm3[];
+    const int L = ell_max, nm = 2 * L + 1;
+    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    double2* s_b = sm3;                                     // [n_modes][33]   a_{l m'} e^{i m'(A-B)}, time along the lanes
+    double2* s_pw = s_b + (size_t)n_modes * ROT3_PITCH;     // [L+1][32]       e^{i k (A+B)}
+    double2* s_pu = s_pw + (size_t)(L + 1) * ROT3_TB;       // [L+1][32]       e^{i k (A-B)}
+    double* s_ra = reinterpret_cast<double*>(s_pu + (size_t)(L + 1) * ROT3_TB);   // [2L+1][32] ra^k
+    double* s_rb = s_ra + (size_t)nm * ROT3_TB;             // [2L+1][32]
+    double* s_cos = s_rb + (size_t)nm * ROT3_TB;            // [32]  cos(beta), or 2 if Rb == 0 exactly
+    const int64_t t0 = (int64_t)blockIdx.x * ROT3_TB;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid < ROT3_TB) {
+        const int tt = tid;
+        int64_t t = t0 + tt;
+        if (t >= n_times) t = n_times - 1;
+        const double2 Ra = spinors[t * spinor_stride + 0], Rb = spinors[t * spinor_stride + 1];
+        const double ra2 = Ra.x * Ra.x + Ra.y * Ra.y, rb2 = Rb.x * Rb.x + Rb.y * Rb.y;
+        const double n2 = ra2 + rb2;
+        const double ra = sqrt(ra2 / n2), rb = sqrt(rb2 / n2);
+        // unit phases; the phase of an exact zero is 1 (its magnitude powers kill every term it would enter)
+        const double2 ea = ra2 > 0.0 ? cscale(1.0 / sqrt(ra2), Ra) : make_double2(1.0, 0.0);
+        const double2 eb = rb2 > 0.0 ? cscale(1.0 / sqrt(rb2), Rb) : make_double2(1.0, 0.0);
+        const double2 u = cmul(ea, cconj(eb)), w = cmul(ea, eb);
+        double2 pu = make_double2(1.0, 0.0), pw = pu;
+        for (int k = 0; k <= L; ++k) {
+            s_pu[k * ROT3_TB + tt] = pu;
+            s_pw[k * ROT3_TB + tt] = pw;
+            pu = cmul(pu, u);
+            pw = cmul(pw, w);
+        }
+        double pa = 1.0, pb = 1.0;
+        for (int k = 0; k < nm; ++k) {
+            s_ra[k * ROT3_TB + tt] = pa;
+            s_rb[k * ROT3_TB + tt] = pb;
+            pa *= ra;
+            pb *= rb;
+        }
+        s_cos[tt] = (rb2 == 0.0) ? 2.0 : (ra2 - rb2) / n2;
+    }
+    __syncthreads();
+    // stage the tile transposed, premultiplied by e^{i m'(A-B)}: lanes run along the modes for the (coalesced) global read
+    for (int idx = tid; idx < ROT3_TB * n_modes; idx += nthreads) {
+        const int tt = idx / n_modes, lm = idx - tt * n_modes;
+        const int64_t t = t0 + tt;
+        double2 v = make_double2(0.0, 0.0);
+        if (t < n_times) {
+            const int full = lm + ell_min * ell_min;
+            int l = (int)sqrt((double)full);
+            while (l * l > full) --l;
+            while ((l + 1) * (l + 1) <= full) ++l;
+            const int mp = full - l * (l + 1);
+            const double2 ph = s_pu[(mp < 0 ? -mp : mp) * ROT3_TB + tt];
+            v = cmul(data[t0 * n_modes + idx], mp < 0 ? cconj(ph) : ph);
+        }
+        s_b[lm * ROT3_PITCH + tt] = v;
+    }
+    __syncthreads();
+    const int tt = tid & 31, w = tid >> 5;
+    if (t0 + tt >= n_times) return;
+    const double cosb = s_cos[tt];
+    const bool diagonal = cosb > 1.5;
+    double2* orow = data + (t0 + tt) * n_modes;
+    // warp w owns m = w and m = L - w (one of them when they coincide)
+    for (int which = 0; which < 2; ++which) {
+        const int m = which == 0 ? w : L - w;
+        if (m > L || m < 0 || (which == 1 && m <= w)) continue;
+        if (LT <= 8) {
+            rot3_pass<0, 8>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
+        } else {
+            if (m <= 8) rot3_pass<0, 8>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
+            rot3_pass<9, 16>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
+        }
+    }
+}
+
+static size_t rotate_time_smem(int L, int n_modes) {
+    const size_t nm = 2 * L + 1;
+    return ((size_t)n_modes * ROT3_PITCH + 2 * (size_t)(L + 1) * ROT3_TB) * sizeof(double2) + (2 * nm * ROT3_TB + ROT3_TB) * sizeof(double);
+}
+
 static size_t rotate_reg_smem(int TB, int L, int n_modes) {
     const size_t nm = 2 * L + 1;
     return ((size_t)TB * n_modes + (size_t)(L > 0 ? L : 1) * nm + 2 * (size_t)TB * (L + 1)) * sizeof(double2) +
@@ -278,6 +458,37 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
     if (n_times <= 0) return SCRIB200_OK;
     const int L = ell_max, nm = 2 * L + 1;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr && getenv("SCRIB200_ROTATE_V2") == nullptr &&
+        rotate_time_smem(L, n_modes) <= 200 * 1024) {
+        SCRIB200_REQUIRE(aligned16(uv), "rotate_modes: uv must be 16-byte aligned");
+        cudaStream_t st = (cudaStream_t)stream;
+        // the two small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic)
+        // (re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max)
+        void *p_seed = nullptr, *p_uv = nullptr;
+        cudaError_t e = cudaGetSymbolAddress(&p_seed, c_rot_seed);
+        if (e == cudaSuccess) e = cudaGetSymbolAddress(&p_uv, c_rot_uv);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(reinterpret_cast<double*>(p_seed) + (16 - L) * 33 + (16 - L), 33 * sizeof(double), seed, nm * sizeof(double),
+                                  nm * sizeof(double), nm, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && L > 0)
+            e = cudaMemcpy2DAsync(reinterpret_cast<double2*>(p_uv) + (16 - L), 33 * sizeof(double2), uv, nm * sizeof(double2),
+                                  nm * sizeof(double2), L, cudaMemcpyDeviceToDevice, st);
+        SCRIB200_REQUIRE(e == cudaSuccess, "rotate_modes: %s", cudaGetErrorString(e));
+        const size_t smem = rotate_time_smem(L, n_modes);
+        const int64_t blocks = (n_times + ROT3_TB - 1) / ROT3_TB;
+        const int warps = L / 2 + 1;
+        if (L <= 8) {
+            cudaFuncSetAttribute(rotate_modes_time_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            rotate_modes_time_kernel<8><<<(unsigned)blocks, 32 * warps, smem, st>>>(reinterpret_cast<double2*>(data), n_times, ell_min, ell_max,
+                                                                              reinterpret_cast<const double2*>(spinors), spinor_stride);
+        } else {
+            cudaFuncSetAttribute(rotate_modes_time_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            rotate_modes_time_kernel<16><<<(unsigned)blocks, 32 * warps, smem, st>>>(reinterpret_cast<double2*>(data), n_times, ell_min, ell_max,
+                                                                               reinterpret_cast<const double2*>(spinors), spinor_stride);
+        }
+        SCRIB200_CHECK_LAUNCH("rotate_modes");
+        return SCRIB200_OK;
+    }
     if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr) {
         SCRIB200_REQUIRE(aligned16(uv), "rotate_modes: uv must be 16-byte aligned");
         int TB = (L <= 8 ? 256 : 512) / nm;

@@ -45,19 +45,23 @@ def to_device(x, dtype=None):
 _h2d_pool = None
 
 
+class _Done:
+    """A finished future.  (Module level on purpose: a class defined per call is cyclic garbage that keeps whatever its
+    methods close over - here a 124 MB device tensor - alive until the cycle collector gets round to it.)"""
+
+    def __init__(self, v):
+        self.v = v
+
+    def result(self):
+        return self.v
+
+
 def to_device_async(x, dtype=None):
     """Start `to_device(x)` on a helper thread and return a future: the staging copy is C code that does not hold the
     GIL, so the caller can keep building host-side tables (the transformation plan) while the waveform streams in."""
     global _h2d_pool
     torch = _torch()
     if is_tensor(x) or np.asarray(x).nbytes < (1 << 20):
-        class _Done:
-            def __init__(self, v):
-                self.v = v
-
-            def result(self):
-                return self.v
-
         return _Done(to_device(x, dtype))
     if _h2d_pool is None:
         from concurrent.futures import ThreadPoolExecutor
@@ -173,11 +177,7 @@ def to_device_slabs(x, dtype=None, n_slabs=4, weights=None):
             ev.record(cs)
             flag.set()
 
-        class _Done:
-            def result(self):
-                return out
-
-        return out, slabs, _Done()
+        return out, slabs, _Done(out)
     if _h2d_pool is None:
         from concurrent.futures import ThreadPoolExecutor
 

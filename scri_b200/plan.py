@@ -284,7 +284,7 @@ class GridPlan:
         backward compatibility and ignored (the block is found on the device)."""
         return self.prepare(t).uprm
 
-    def _remap(self, t, F, uprm, prep, tile, n_series=1, rows_needed=None):
+    def _remap(self, t, F, uprm, prep, tile, n_series=1, rows_needed=None, out=None):
         """F [n_series * N, G] (series stacked along time) -> remapped grid; rows b*n_out.. belong to series b.
         `rows_needed` = (row_lo, row_hi): the caller knows that these output times read input rows [row_lo, row_hi) only
         (`input_rows_for_outputs`); only the tiles holding them are launched."""
@@ -294,7 +294,9 @@ class GridPlan:
             prep = self.prepare(t)
         N, n_out = t.shape[0], uprm.shape[0]
         rows = n_out * n_series
-        if tile:
+        if out is not None:
+            pass                                   # caller's buffer (scratch of the streaming pipeline)
+        elif tile:
             out = torch.empty((-(-rows // tile), self.G, tile), dtype=torch.complex128, device=self.device)
         else:
             out = torch.empty((rows, self.G), dtype=torch.complex128, device=self.device)
@@ -596,11 +598,12 @@ class TransformPlan(GridPlan):
         """Same spline remap, result stored time-tiled: [ceil(N'/T), G, T] (T = self.tile)."""
         return self._remap(t, F, uprm, prep, self.tile)
 
-    def analyze_tiled(self, gridT, n_out):
+    def analyze_tiled(self, gridT, n_out, out=None):
         """gridT [ceil(N'/T), G, T] complex128 (time-tiled) -> [n_out, n_modes_out]."""
         torch = self.torch
         lib = _lib.load()
-        out = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, device=self.device)
+        if out is None:
+            out = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, device=self.device)
         if n_out == 0:
             return out
         _lib.check(
@@ -680,7 +683,12 @@ class TransformPlan(GridPlan):
         drift = transform_halo(self, float(t_host[0]), float(t_host[-1]), prep.dt_min) - SPLINE_DECAY_ROWS
         margin = drift + max(body, 320) + 2 * halo + 64
         N = data.shape[0]
-        F = torch.empty((N, self.G), dtype=torch.complex128, device=self.device)
+        # the three large intermediates live in buffers kept across calls (see _scratch): the synthesized grid, one remapped
+        # slab (reused slab after slab: remap and analysis of successive slabs are ordered on this stream) and the modes
+        c128 = torch.complex128
+        F = _scratch("F", (N, self.G), c128, self.device)
+        gridT_all = _scratch("gridT", (-(-n_out // self.tile) + 1, self.G, self.tile), c128, self.device)
+        modes_all = _scratch("modes", (n_out, self.n_modes_out), c128, self.device)
         if debug_poison:
             F.fill_(float("nan"))                    # tests: an output that read a row before its synthesis turns into NaN
         host = torch.empty((n_out, self.n_modes_out), dtype=torch.complex128, pin_memory=True)
@@ -708,8 +716,9 @@ class TransformPlan(GridPlan):
             out_hi = n_out if k == len(slabs) - 1 else min(n_out, max(done, ((rhi - margin - lo) // tile) * tile))
             if out_hi > done:
                 rows_needed = self.input_rows_for_outputs(t_host, u_of_row(lo + done), u_of_row(lo + out_hi - 1))
-                gridT = self._remap(t, F, uprm[done:out_hi], prep, tile, rows_needed=rows_needed)
-                modes = self.analyze_tiled(gridT, out_hi - done)
+                gridT = self._remap(t, F, uprm[done:out_hi], prep, tile, rows_needed=rows_needed,
+                                    out=gridT_all[: -(-(out_hi - done) // tile)])
+                modes = self.analyze_tiled(gridT, out_hi - done, out=modes_all[done:out_hi])
                 ready = torch.cuda.Event(enable_timing=timing is not None)
                 ready.record(cur)
                 cs.wait_event(ready)
@@ -720,8 +729,6 @@ class TransformPlan(GridPlan):
                         landed.record(cs)
                         timing.append((f"outputs {done}:{out_hi} computed", ready))
                         timing.append((f"outputs {done}:{out_hi} landed on the host", landed))
-                modes.record_stream(cs)
-                del gridT, modes
                 done = out_hi
         _trace("all launches queued")
         cs.synchronize()
@@ -786,6 +793,25 @@ def _trace(label):
 _plan_cache = {}
 PLAN_CACHE_SIZE = 8
 _spared = set()
+_scratch_pool = {}
+
+
+def _scratch(name, shape, dtype, device):
+    """A device buffer that lives across calls (grow-only, one per name and device).  The end-to-end pipeline asks for
+    the same few large intermediates on every call, interleaved on three streams; routed through the caching allocator
+    the slab-sized requests found their blocks still parked behind record_stream events every few calls and fell through
+    to cudaMalloc in the middle of the pipeline (5 - 95 ms stalls).  Calls on one device are serialised by their final
+    synchronisation, so one buffer per role is enough."""
+    import torch
+
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    key = (name, str(device), dtype)
+    buf = _scratch_pool.get(key)
+    if buf is None or buf.numel() < numel:
+        _scratch_pool[key] = buf = torch.empty(max(numel, 1), dtype=dtype, device=device)
+    return buf[:numel].view(*shape)
 
 
 def _kwargs_key(kwargs):
