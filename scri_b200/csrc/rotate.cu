@@ -284,18 +284,29 @@ __device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const
                                           const double2* __restrict__ s_pw, double cosb, bool diagonal, int tt, int m, int L, int ell_min,
                                           double2* __restrict__ orow) {
     constexpr int NA = LB - LA + 1;
-    const int lmin2 = ell_min * ell_min;
+    const int lo = LA > ell_min ? LA : ell_min;             // the tile holds l = lo .. min(LB, L)
+    const int lmin2 = lo * lo, omin2 = ell_min * ell_min;
     double pr[NA], pi[NA], nr[NA], ni[NA];                  // out[+m] and out[-m] for l = LA .. LB
 #pragma unroll
     for (int i = 0; i < NA; ++i) pr[i] = pi[i] = nr[i] = ni[i] = 0.0;
     const int lend = LB < L ? LB : L;
     const double2* uvm = c_rot_uv + ROT3_C + m;             // + l * 33
+    // seeds P^{l0}(+-m', m) ra^.. rb^.. of the NEXT m' are formed while the ladder of the current one runs (their shared-
+    // memory and constant loads would otherwise sit in front of every ladder with only two warps per scheduler to hide them)
+    auto seeds = [&](int mp, double& P, double& N) {
+        const int ka = mp + m, kb = mp > m ? mp - m : m - mp;            // exponents of ra, rb for (m', m); swapped for (-m', m)
+        const double ra_a = s_ra[ka * ROT3_TB + tt], rb_b = s_rb[kb * ROT3_TB + tt];
+        const double ra_b = s_ra[kb * ROT3_TB + tt], rb_a = s_rb[ka * ROT3_TB + tt];
+        P = c_rot_seed[(mp + ROT3_C) * ROT3_NM + m + ROT3_C] * (ra_a * rb_b);
+        N = (mp > 0) ? c_rot_seed[(ROT3_C - mp) * ROT3_NM + m + ROT3_C] * (ra_b * rb_a) : 0.0;
+    };
+    double Pn, Nn;
+    seeds(0, Pn, Nn);
     for (int mp = 0; mp <= L; ++mp) {
         const int l0 = mp > m ? mp : m;
         if (l0 > lend) break;                                // l0 grows with m'
-        const int ka = mp + m, kb = mp > m ? mp - m : m - mp;            // exponents of ra, rb for (m', m); swapped for (-m', m)
-        double P = c_rot_seed[(mp + ROT3_C) * ROT3_NM + m + ROT3_C] * (s_ra[ka * ROT3_TB + tt] * s_rb[kb * ROT3_TB + tt]);
-        double N = (mp > 0) ? c_rot_seed[(ROT3_C - mp) * ROT3_NM + m + ROT3_C] * (s_ra[kb * ROT3_TB + tt] * s_rb[ka * ROT3_TB + tt]) : 0.0;
+        double P = Pn, N = Nn;
+        if (mp < L) seeds(mp + 1, Pn, Nn);
         double P1 = 0.0, N1 = 0.0;
         const double sg = ((mp + m) & 1) ? -1.0 : 1.0;
         const double mmp = (double)(m * mp);
@@ -350,26 +361,29 @@ __device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const
 #pragma unroll
     for (int l = LA; l <= LB; ++l)
         if (l >= m && l >= ell_min && l <= L) {
-            orow[l * (l + 1) - lmin2 + m] = cmul(make_double2(pr[l - LA], pi[l - LA]), pw);
-            if (m > 0) orow[l * (l + 1) - lmin2 - m] = cmul(make_double2(nr[l - LA], ni[l - LA]), cconj(pw));
+            orow[l * (l + 1) - omin2 + m] = cmul(make_double2(pr[l - LA], pi[l - LA]), pw);
+            if (m > 0) orow[l * (l + 1) - omin2 - m] = cmul(make_double2(nr[l - LA], ni[l - LA]), cconj(pw));
         }
 }
 
-template <int LT>
-__global__ void __launch_bounds__(32 * (LT / 2 + 1))
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * (LB / 2 + 1))
 rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_min, int ell_max,
                          const double2* __restrict__ spinors, int64_t spinor_stride) {
     extern __shared__ double2 sm3[];
     const int L = ell_max, nm = 2 * L + 1;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
-    double2* s_b = sm3;                                     // [n_modes][33]   a_{l m'} e^{i m'(A-B)}, time along the lanes
-    double2* s_pw = s_b + (size_t)n_modes * ROT3_PITCH;     // [L+1][32]       e^{i k (A+B)}
-    double2* s_pu = s_pw + (size_t)(L + 1) * ROT3_TB;       // [L+1][32]       e^{i k (A-B)}
-    double* s_ra = reinterpret_cast<double*>(s_pu + (size_t)(L + 1) * ROT3_TB);   // [2L+1][32] ra^k
-    double* s_rb = s_ra + (size_t)nm * ROT3_TB;             // [2L+1][32]
-    double* s_cos = s_rb + (size_t)nm * ROT3_TB;            // [32]  cos(beta), or 2 if Rb == 0 exactly
+    const int lo = LA > ell_min ? LA : ell_min, hi = LB < L ? LB : L;   // this launch rotates l = lo .. hi
+    const int n_blk = (hi + 1) * (hi + 1) - lo * lo, col0 = lo * lo - ell_min * ell_min;
+    double2* s_b = sm3;                                     // [n_blk][33]     a_{l m'} e^{i m'(A-B)}, time along the lanes
+    double2* s_pw = s_b + (size_t)n_blk * ROT3_PITCH;       // [hi+1][32]      e^{i k (A+B)}
+    double2* s_pu = s_pw + (size_t)(hi + 1) * ROT3_TB;      // [hi+1][32]      e^{i k (A-B)}
+    double* s_ra = reinterpret_cast<double*>(s_pu + (size_t)(hi + 1) * ROT3_TB);   // [2 hi + 1][32] ra^k
+    double* s_rb = s_ra + (size_t)(2 * hi + 1) * ROT3_TB;   // [2 hi + 1][32]
+    double* s_cos = s_rb + (size_t)(2 * hi + 1) * ROT3_TB;  // [32]  cos(beta), or 2 if Rb == 0 exactly
     const int64_t t0 = (int64_t)blockIdx.x * ROT3_TB;
     const int tid = threadIdx.x, nthreads = blockDim.x;
+    (void)nm;
     if (tid < ROT3_TB) {
         const int tt = tid;
         int64_t t = t0 + tt;
@@ -383,14 +397,14 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
         const double2 eb = rb2 > 0.0 ? cscale(1.0 / sqrt(rb2), Rb) : make_double2(1.0, 0.0);
         const double2 u = cmul(ea, cconj(eb)), w = cmul(ea, eb);
         double2 pu = make_double2(1.0, 0.0), pw = pu;
-        for (int k = 0; k <= L; ++k) {
+        for (int k = 0; k <= hi; ++k) {
             s_pu[k * ROT3_TB + tt] = pu;
             s_pw[k * ROT3_TB + tt] = pw;
             pu = cmul(pu, u);
             pw = cmul(pw, w);
         }
         double pa = 1.0, pb = 1.0;
-        for (int k = 0; k < nm; ++k) {
+        for (int k = 0; k <= 2 * hi; ++k) {
             s_ra[k * ROT3_TB + tt] = pa;
             s_rb[k * ROT3_TB + tt] = pb;
             pa *= ra;
@@ -399,19 +413,19 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
         s_cos[tt] = (rb2 == 0.0) ? 2.0 : (ra2 - rb2) / n2;
     }
     __syncthreads();
-    // stage the tile transposed, premultiplied by e^{i m'(A-B)}: lanes run along the modes for the (coalesced) global read
-    for (int idx = tid; idx < ROT3_TB * n_modes; idx += nthreads) {
-        const int tt = idx / n_modes, lm = idx - tt * n_modes;
+    // stage the l-block of the tile transposed, premultiplied by e^{i m'(A-B)}: lanes along the modes for the global read
+    for (int idx = tid; idx < ROT3_TB * n_blk; idx += nthreads) {
+        const int tt = idx / n_blk, lm = idx - tt * n_blk;
         const int64_t t = t0 + tt;
         double2 v = make_double2(0.0, 0.0);
         if (t < n_times) {
-            const int full = lm + ell_min * ell_min;
+            const int full = lm + lo * lo;
             int l = (int)sqrt((double)full);
             while (l * l > full) --l;
             while ((l + 1) * (l + 1) <= full) ++l;
             const int mp = full - l * (l + 1);
             const double2 ph = s_pu[(mp < 0 ? -mp : mp) * ROT3_TB + tt];
-            v = cmul(data[t0 * n_modes + idx], mp < 0 ? cconj(ph) : ph);
+            v = cmul(data[t * n_modes + col0 + lm], mp < 0 ? cconj(ph) : ph);
         }
         s_b[lm * ROT3_PITCH + tt] = v;
     }
@@ -421,22 +435,17 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     const double cosb = s_cos[tt];
     const bool diagonal = cosb > 1.5;
     double2* orow = data + (t0 + tt) * n_modes;
-    // warp w owns m = w and m = L - w (one of them when they coincide)
+    // warp w owns m = w and m = hi - w (one of them when they coincide)
     for (int which = 0; which < 2; ++which) {
-        const int m = which == 0 ? w : L - w;
-        if (m > L || m < 0 || (which == 1 && m <= w)) continue;
-        if (LT <= 8) {
-            rot3_pass<0, 8>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
-        } else {
-            if (m <= 8) rot3_pass<0, 8>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
-            rot3_pass<9, 16>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
-        }
+        const int m = which == 0 ? w : hi - w;
+        if (m > hi || m < 0 || (which == 1 && m <= w)) continue;
+        rot3_pass<LA, LB>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
     }
 }
 
-static size_t rotate_time_smem(int L, int n_modes) {
-    const size_t nm = 2 * L + 1;
-    return ((size_t)n_modes * ROT3_PITCH + 2 * (size_t)(L + 1) * ROT3_TB) * sizeof(double2) + (2 * nm * ROT3_TB + ROT3_TB) * sizeof(double);
+static size_t rotate_time_smem(int lo, int hi) {
+    const size_t n_blk = (size_t)(hi + 1) * (hi + 1) - (size_t)lo * lo;
+    return (n_blk * ROT3_PITCH + 2 * (size_t)(hi + 1) * ROT3_TB) * sizeof(double2) + (2 * (size_t)(2 * hi + 1) * ROT3_TB + ROT3_TB) * sizeof(double);
 }
 
 static size_t rotate_reg_smem(int TB, int L, int n_modes) {
@@ -458,12 +467,11 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
     if (n_times <= 0) return SCRIB200_OK;
     const int L = ell_max, nm = 2 * L + 1;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
-    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr && getenv("SCRIB200_ROTATE_V2") == nullptr &&
-        rotate_time_smem(L, n_modes) <= 200 * 1024) {
+    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr && getenv("SCRIB200_ROTATE_V2") == nullptr) {
         SCRIB200_REQUIRE(aligned16(uv), "rotate_modes: uv must be 16-byte aligned");
         cudaStream_t st = (cudaStream_t)stream;
-        // the two small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic)
-        // (re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max)
+        // the two small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic),
+        // re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max
         void *p_seed = nullptr, *p_uv = nullptr;
         cudaError_t e = cudaGetSymbolAddress(&p_seed, c_rot_seed);
         if (e == cudaSuccess) e = cudaGetSymbolAddress(&p_uv, c_rot_uv);
@@ -474,19 +482,22 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
             e = cudaMemcpy2DAsync(reinterpret_cast<double2*>(p_uv) + (16 - L), 33 * sizeof(double2), uv, nm * sizeof(double2),
                                   nm * sizeof(double2), L, cudaMemcpyDeviceToDevice, st);
         SCRIB200_REQUIRE(e == cudaSuccess, "rotate_modes: %s", cudaGetErrorString(e));
-        const size_t smem = rotate_time_smem(L, n_modes);
         const int64_t blocks = (n_times + ROT3_TB - 1) / ROT3_TB;
-        const int warps = L / 2 + 1;
-        if (L <= 8) {
-            cudaFuncSetAttribute(rotate_modes_time_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            rotate_modes_time_kernel<8><<<(unsigned)blocks, 32 * warps, smem, st>>>(reinterpret_cast<double2*>(data), n_times, ell_min, ell_max,
-                                                                              reinterpret_cast<const double2*>(spinors), spinor_stride);
-        } else {
-            cudaFuncSetAttribute(rotate_modes_time_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            rotate_modes_time_kernel<16><<<(unsigned)blocks, 32 * warps, smem, st>>>(reinterpret_cast<double2*>(data), n_times, ell_min, ell_max,
-                                                                               reinterpret_cast<const double2*>(spinors), spinor_stride);
-        }
-        SCRIB200_CHECK_LAUNCH("rotate_modes");
+        // one launch per block of l (0..8, 9..12, 13..16): each stages only its own modes (39 / 47 / 63 KB of shared memory
+        // instead of 150 KB: 5, 3 and 2 CTAs per SM), reads and writes its own columns of `data`, restarts the recurrences at l0
+#define ROT3_LAUNCH(LA_, LB_)                                                                                                     \
+    if (ell_min <= LB_ && L >= LA_) {                                                                                             \
+        const int lo = ell_min > LA_ ? ell_min : LA_, hi = L < LB_ ? L : LB_;                                                     \
+        const size_t smem = rotate_time_smem(lo, hi);                                                                             \
+        cudaFuncSetAttribute(rotate_modes_time_kernel<LA_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        rotate_modes_time_kernel<LA_, LB_><<<(unsigned)blocks, 32 * (hi / 2 + 1), smem, st>>>(                                    \
+            reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride); \
+        SCRIB200_CHECK_LAUNCH("rotate_modes");                                                                                    \
+    }
+        ROT3_LAUNCH(0, 8)
+        ROT3_LAUNCH(9, 12)
+        ROT3_LAUNCH(13, 16)
+#undef ROT3_LAUNCH
         return SCRIB200_OK;
     }
     if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr) {
