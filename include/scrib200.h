@@ -191,6 +191,13 @@ int scrib200_solve3(const double* A, const double* b, int64_t n, double scale, d
 int scrib200_sparse_expectation(const double* a, const double* b, int64_t n_times, int n_modes, const int* rows,
                                 const int* cols, const double* vals, const int* seg_host, const int* seg_dev, int K,
                                 double* out, void* stream);
+/* The same contraction with the K matrices in column-major ELL form (what scri_b200.ops.sparse_expectation builds from the COO
+ * triples of scri/flux.py:182-441): entry w of column c of matrix k at [off_k + w n_modes + c], off_k = n_modes * (widths[0] +
+ * ... + widths[k-1]); ell_rows int32 (row index, -1 = no entry), ell_vals double (real_values = 1) or complex128 (0) in the
+ * same order; widths HOST int[K] (entries per column, <= 64), K <= 32.  3 loads per non-zero instead of 5. */
+int scrib200_sparse_expectation_ell(const double* a, const double* b, int64_t n_times, int n_modes, const int* ell_rows,
+                                    const double* ell_vals, const int* widths_host, int K, int real_values, double* out,
+                                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Weyl-scalar mixing under a BMS transformation, elementwise over synthesized grids.

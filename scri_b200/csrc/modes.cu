@@ -438,6 +438,63 @@ sparse_expectation_kernel(const double2* __restrict__ a, const double2* __restri
     }
 }
 
+// Column-major ELL form of the same contraction (round 2).  The flux matrices are banded in (l, m): every column has at most
+// a handful of entries (3 for the momentum operators, 1 for L_z, ...).  Entry w of column c of matrix k sits at
+// [off_k + w n + c]: row index (or -1) and value.  A lane owns columns c = lane, lane + 32, ...: b[c] is loaded once and
+// serves every entry of the column in up to four matrices, the index and value loads are coalesced along c, and only a[r]
+// is a gather (into the 16 n bytes of the time step, next to its neighbours' rows).  3 loads per non-zero instead of 5
+// for the COO kernel, which is bound by load issue.
+struct EllLayout {
+    int width[32];
+    int offset[32];   // in entries
+};
+
+template <int KB, bool REALV>
+__global__ void __launch_bounds__(128)
+sparse_expectation_ell_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t n_times, int n,
+                              const int* __restrict__ ell_r, const double* __restrict__ ell_v, EllLayout lay, int k0, int K,
+                              double2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_times) return;
+    const double2* ra = a + t * n;
+    const double2* rb = b + t * n;
+    double2 acc[KB];
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) acc[kk] = make_double2(0.0, 0.0);
+    for (int c = lane; c < n; c += 32) {
+        const double2 bc = rb[c];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+            if (k0 + kk < K) {
+                const int W = lay.width[k0 + kk];
+                const int* rr = ell_r + lay.offset[k0 + kk] + c;
+                const double* vv = ell_v + (size_t)(REALV ? 1 : 2) * (lay.offset[k0 + kk] + c);
+                for (int w = 0; w < W; ++w) {
+                    const int r = rr[(size_t)w * n];
+                    if (r >= 0) {
+                        const double2 p = cmul(cconj(ra[r]), bc);
+                        if (REALV) {
+                            const double v = vv[(size_t)w * n];
+                            acc[kk].x = fma(p.x, v, acc[kk].x);
+                            acc[kk].y = fma(p.y, v, acc[kk].y);
+                        } else {
+                            const double2 v = *reinterpret_cast<const double2*>(vv + (size_t)2 * w * n);
+                            cfma(acc[kk], p, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+        acc[kk].x = warp_sum(acc[kk].x);
+        acc[kk].y = warp_sum(acc[kk].y);
+        if (lane == 0 && k0 + kk < K) out[t * K + k0 + kk] = acc[kk];
+    }
+}
+
 static inline unsigned warp_blocks(int64_t n_times) { return (unsigned)((n_times * 32 + 127) / 128); }
 
 }  // namespace scrib200
@@ -546,5 +603,34 @@ extern "C" int scrib200_sparse_expectation(const double* a, const double* b, int
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, rows, cols,
         reinterpret_cast<const double2*>(vals), seg_dev, K, reinterpret_cast<double2*>(out));
     SCRIB200_CHECK_LAUNCH("sparse_expectation");
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_sparse_expectation_ell(const double* a, const double* b, int64_t n_times, int n_modes, const int* ell_rows,
+                                               const double* ell_vals, const int* widths_host, int K, int real_values, double* out,
+                                               void* stream) {
+    SCRIB200_REQUIRE(a && b && ell_rows && ell_vals && widths_host && out, "sparse_expectation_ell: null pointer");
+    SCRIB200_REQUIRE(K >= 1 && K <= 32, "sparse_expectation_ell: K=%d must be 1..32", K);
+    if (n_times <= 0) return SCRIB200_OK;
+    EllLayout lay;
+    int off = 0;
+    for (int k = 0; k < 32; ++k) {
+        lay.width[k] = k < K ? widths_host[k] : 0;
+        lay.offset[k] = off;
+        SCRIB200_REQUIRE(lay.width[k] >= 0 && lay.width[k] <= 64, "sparse_expectation_ell: width %d", lay.width[k]);
+        off += lay.width[k] * n_modes;
+    }
+    const unsigned blocks = warp_blocks(n_times);
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        if (real_values)
+            sparse_expectation_ell_kernel<4, true><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, ell_rows, ell_vals, lay, k0, K,
+                reinterpret_cast<double2*>(out));
+        else
+            sparse_expectation_ell_kernel<4, false><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, ell_rows, ell_vals, lay, k0, K,
+                reinterpret_cast<double2*>(out));
+        SCRIB200_CHECK_LAUNCH("sparse_expectation_ell");
+    }
     return SCRIB200_OK;
 }

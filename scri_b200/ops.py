@@ -738,31 +738,74 @@ def solve3(A, b, scale=1.0):
 _sparse_cache = {}
 
 
+def _ell_tables(matrices, n):
+    """Column-major ELL form of K COO matrices (see scrib200_sparse_expectation_ell): (rows int32, values, widths, real)."""
+    rows_all, vals_all, widths = [], [], []
+    real = all(not np.iscomplexobj(m[2]) or np.all(np.asarray(m[2]).imag == 0.0) for m in matrices)
+    for r, c, v in matrices:
+        r, c = np.asarray(r, dtype=np.int64), np.asarray(c, dtype=np.int64)
+        v = np.asarray(v, dtype=complex)
+        order = np.argsort(c, kind="stable")
+        r, c, v = r[order], c[order], v[order]
+        counts = np.bincount(c, minlength=n) if c.size else np.zeros(n, dtype=np.int64)
+        W = int(counts.max()) if c.size else 0
+        slot = np.arange(c.size) - np.repeat(np.cumsum(counts) - counts, counts)      # position of each entry inside its column
+        er = np.full((W, n), -1, dtype=np.int32)
+        ev = np.zeros((W, n), dtype=complex)
+        er[slot, c] = r
+        ev[slot, c] = v
+        rows_all.append(er.ravel())
+        vals_all.append(ev.real.ravel() if real else ev.ravel())
+        widths.append(W)
+    rows = np.concatenate(rows_all) if rows_all else np.zeros(0, dtype=np.int32)
+    vals = np.concatenate(vals_all) if vals_all else np.zeros(0)
+    if rows.size == 0:
+        rows, vals = np.full(1, -1, dtype=np.int32), np.zeros(1, dtype=float if real else complex)
+    return rows, vals, widths, real
+
+
 def sparse_expectation(a, b, matrices):
     """[N, K] complex: <a|M_k|b>(t) for K sparse matrices (rows, cols, vals) - scri/flux.py:40-78."""
+    import ctypes
+
     lib = _lib.load()
     torch = _torch()
     ad = to_device(a, np.complex128)
     bd = ad if b is a else to_device(b, np.complex128)
     N, n = ad.shape
     K = len(matrices)
-    # the COO tables are cached on the device per set of matrix objects (the generators in flux.py are lru_cached, so the
+    # the tables are cached on the device per set of matrix objects (the generators in flux.py are lru_cached, so the
     # same objects come back call after call; the cache keeps them alive, which keeps their ids unique)
-    key = (tuple(id(m) for m in matrices), torch.cuda.current_device())
+    key = (tuple(id(m) for m in matrices), n, torch.cuda.current_device())
     hit = _sparse_cache.get(key)
     if hit is None:
-        rows = np.concatenate([np.asarray(m[0], dtype=np.int32) for m in matrices])
-        cols = np.concatenate([np.asarray(m[1], dtype=np.int32) for m in matrices])
-        vals = np.concatenate([np.asarray(m[2], dtype=complex) for m in matrices])
-        seg = np.zeros(K + 1, dtype=np.int32)
-        seg[1:] = np.cumsum([len(m[0]) for m in matrices])
         if len(_sparse_cache) > 64:
             _sparse_cache.clear()
-        hit = _sparse_cache[key] = (tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg)), list(matrices))
-    dr, dc, dv, ds = hit[0]
+        rows, vals, widths, real = _ell_tables(matrices, n) if K <= 32 else (None, None, [0], False)
+        # matrices with several entries per column (the momentum and boost operators) go through the ELL kernel, which
+        # loads b[c] once per column; with one entry per column (L_z, L_+-) the flat COO loop is the faster one (measured)
+        if K <= 32 and max(widths) >= 2:
+            dev = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, vals))
+            hit = _sparse_cache[key] = ("ell", dev, (ctypes.c_int * K)(*widths), real, list(matrices))
+        else:
+            rows = np.concatenate([np.asarray(m[0], dtype=np.int32) for m in matrices])
+            cols = np.concatenate([np.asarray(m[1], dtype=np.int32) for m in matrices])
+            vals = np.concatenate([np.asarray(m[2], dtype=complex) for m in matrices])
+            seg = np.zeros(K + 1, dtype=np.int32)
+            seg[1:] = np.cumsum([len(m[0]) for m in matrices])
+            hit = _sparse_cache[key] = ("coo", tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg)), None, None, list(matrices))
     out = torch.empty((N, K), dtype=torch.complex128, device="cuda")
-    _lib.check(
-        lib.scrib200_sparse_expectation(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dc), _lib.ptr(dv), None, _lib.ptr(ds), K, _lib.ptr(out), _lib.stream_ptr()),
-        "sparse_expectation",
-    )
+    if hit[0] == "ell":
+        (dr, dv), widths, real = hit[1], hit[2], hit[3]
+        _lib.check(
+            lib.scrib200_sparse_expectation_ell(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dv), widths, K, int(real), _lib.ptr(out),
+                                                _lib.stream_ptr()),
+            "sparse_expectation_ell",
+        )
+    else:
+        dr, dc, dv, ds = hit[1]
+        _lib.check(
+            lib.scrib200_sparse_expectation(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dc), _lib.ptr(dv), None, _lib.ptr(ds), K, _lib.ptr(out), _lib.stream_ptr()),
+            "sparse_expectation",
+        )
     return out if is_tensor(a) else to_host(out)
