@@ -529,17 +529,18 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": remap_bytes}
         else:
             ach = kern["swsh_synth_dmma"]["achieved_tflops"]
-            roof = {"kernel": "swsh_synth_dmma_kernel<8, 4, 64>", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
+            roof = {"kernel": "swsh_synth3m_kernel", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
                     "frac": ach / dgemm_tf, "traffic": None,
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    "algorithmic_flops_per_launch": synth_flops}
+                    "algorithmic_flops_per_launch": synth_flops,
+                    "note": "algorithmic flops = 8 n G per time step (SURVEY 8d, a complex GEMM); the kernel forms the complex product with three real multiplications, so the tensor cores execute 6 n G"}
         # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same kernels at this size from the round's
         # committed `ncu --set full` capture (profiles/r02_traffic.json, made with dev/dev_ncu_traffic.py; ncu cannot run
         # inside a timed region)
         try:
             with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 traffic = json.load(f)
-            names = {"swsh_synth_dmma": "swsh_synth_dmma_kernel<8, 4, 64>", "spline_tile(spline_remap)": "spline_tile_kernel<0, 320>",
+            names = {"swsh_synth_dmma": "swsh_synth3m_kernel", "spline_tile(spline_remap)": "spline_tile_kernel<0, 320>",
                      "map2salm_tiled": "map2salm_persist_kernel<1>"}
             for kname, ncu_name in names.items():
                 if ncu_name in traffic:

@@ -43,6 +43,8 @@ SIGNATURES = {
     "scrib200_host_unregister": (c_int, [c_vp]),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "scrib200_swsh_pack3m": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "scrib200_swsh_synthesize_3m": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "scrib200_spline_prepare": (c_int, [c_vp, c_i64, ctypes.c_double, c_int, ctypes.c_double, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "scrib200_spline_remap": (
         c_int,

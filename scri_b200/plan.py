@@ -498,6 +498,15 @@ class TransformPlan(GridPlan):
             ),
             "swsh_pack",
         )
+        # the same table as three real planes Y_r, Y_i, Y_r + Y_i for the three-multiplication synthesis kernel
+        self.npad3 = -(-self.n_modes_in // 8) * 8
+        self.Gpad3 = -(-self.G // 32) * 32
+        self.d_B3 = torch.empty((3, self.npad3, self.Gpad3), dtype=f64, device=dev)
+        _lib.check(
+            _lib.load().scrib200_swsh_pack3m(_lib.ptr(self.d_B), self.Kpad, self.Ncpad, self.n_modes_in, self.G, _lib.ptr(self.d_B3),
+                                             self.npad3, self.Gpad3, _lib.stream_ptr()),
+            "swsh_pack3m",
+        )
         self.d_offset = torch.from_numpy(off).to(dev)
         self.d_scale = torch.from_numpy(scl).to(dev)
         if self.mix:
@@ -523,6 +532,29 @@ class TransformPlan(GridPlan):
         self.spline_halo = 0   # 0 = chosen from the decay diagnostics of scrib200_spline_prepare
         self.spline_body = 0   # 0 = default intervals per tile
 
+    def _synthesize_rows(self, data, F):
+        """F[rows] = synthesis of data[rows] (one launch): the three-multiplication kernel, or the folded real GEMM with
+        SCRIB200_SYNTH_FOLDED set."""
+        import os
+
+        lib = _lib.load()
+        if os.environ.get("SCRIB200_SYNTH_FOLDED"):
+            _lib.check(
+                lib.scrib200_swsh_synthesize(
+                    _lib.ptr(data), data.shape[0], self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad,
+                    _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F), _lib.stream_ptr(),
+                ),
+                "swsh_synthesize",
+            )
+        else:
+            _lib.check(
+                lib.scrib200_swsh_synthesize_3m(
+                    _lib.ptr(data), data.shape[0], self.n_modes_in, _lib.ptr(self.d_B3), self.npad3, self.Gpad3,
+                    _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F), _lib.stream_ptr(),
+                ),
+                "swsh_synthesize_3m",
+            )
+
     def synthesize(self, data, t=None, slabs=None):
         """[N, n_modes] complex128 -> F [N, G] complex128 (waveform_grid.py:475-559).  `t` (device) is needed for
         psi0..psi3 only, whose mixing factor depends on time.  `slabs` = [(row_lo, row_hi, event, flag), ...]: the rows of
@@ -541,13 +573,7 @@ class TransformPlan(GridPlan):
                 cur.wait_event(ev)
             if hi <= lo:
                 continue
-            _lib.check(
-                lib.scrib200_swsh_synthesize(
-                    _lib.ptr(data[lo:hi]), hi - lo, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad,
-                    _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F[lo:hi]), _lib.stream_ptr(),
-                ),
-                "swsh_synthesize",
-            )
+            self._synthesize_rows(data[lo:hi], F[lo:hi])
         if not self.mix:
             return F
         if t is None:
@@ -706,13 +732,7 @@ class TransformPlan(GridPlan):
             _trace(f"slab {k} queued on the copy stream")
             cur.wait_event(ev)
             if rhi > rlo:
-                _lib.check(
-                    lib.scrib200_swsh_synthesize(
-                        _lib.ptr(data[rlo:rhi]), rhi - rlo, self.n_modes_in, _lib.ptr(self.d_B), self.Kpad, self.Ncpad,
-                        _lib.ptr(self.d_offset), _lib.ptr(self.d_scale), self.G, _lib.ptr(F[rlo:rhi]), _lib.stream_ptr(),
-                    ),
-                    "swsh_synthesize",
-                )
+                self._synthesize_rows(data[rlo:rhi], F[rlo:rhi])
             out_hi = n_out if k == len(slabs) - 1 else min(n_out, max(done, ((rhi - margin - lo) // tile) * tile))
             if out_hi > done:
                 rows_needed = self.input_rows_for_outputs(t_host, u_of_row(lo + done), u_of_row(lo + out_hi - 1))
