@@ -216,12 +216,13 @@ extern "C" int scrib200_swsh_synthesize(const double* modes, int64_t n_times, in
 // (48 accumulator doubles per thread), K streamed in slabs of 8 modes through a 3-stage cp.async ring, three CTAs per SM.
 namespace scrib200 {
 
-constexpr int M3_BM = 64, M3_BNC = 32, M3_BKM = 8, M3_STAGES = 3;     // 57.6 KB per CTA: three CTAs per SM
+constexpr int M3_BM = 64, M3_BNC = 32, M3_BKM = 8;
 constexpr int M3_AS = M3_BKM + 4;        // A row stride in double2 (12: two rows of a quarter-warp hit different bank halves)
 constexpr int M3_BS = M3_BNC + 4;        // B row stride in doubles
 constexpr int M3_A_STAGE = M3_BM * M3_AS;            // double2
 constexpr int M3_B_STAGE = 3 * M3_BKM * M3_BS;       // double
-constexpr size_t M3_SMEM = (size_t)M3_STAGES * (M3_A_STAGE * sizeof(double2) + M3_B_STAGE * sizeof(double));
+template <int STAGES>
+constexpr size_t m3_smem() { return (size_t)STAGES * (M3_A_STAGE * sizeof(double2) + M3_B_STAGE * sizeof(double)); }
 
 __global__ void __launch_bounds__(256)
 swsh_pack3m_kernel(const double* __restrict__ Bmat, int Ncpad, int n_modes, int G, double* __restrict__ B3, int npad, int Gpad) {
@@ -239,7 +240,8 @@ swsh_pack3m_kernel(const double* __restrict__ Bmat, int Ncpad, int n_modes, int 
     B3[2 * plane + idx] = yr + yi;
 }
 
-__global__ void __launch_bounds__(128, 3)
+template <int M3_STAGES>
+__global__ void __launch_bounds__(128, M3_STAGES <= 3 ? 3 : 2)
 swsh_synth3m_kernel(const double2* __restrict__ A, int64_t M, int n, const double* __restrict__ B3, int npad, int Gpad,
                     const double* __restrict__ offset, const double* __restrict__ scale, int G, double2* __restrict__ C, int band) {
     extern __shared__ __align__(16) unsigned char smem3[];
@@ -385,14 +387,23 @@ extern "C" int scrib200_swsh_synthesize_3m(const double* modes, int64_t n_times,
     if (n_times <= 0) return SCRIB200_OK;
     int band = (int)(((size_t)48 << 20) / ((size_t)3 * npad * M3_BNC * sizeof(double)));
     if (band < 1) band = 1;
-    cudaFuncSetAttribute(swsh_synth3m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3_SMEM);
+    int variant = 3;                                       // ring depth: 3 stages (57.6 KB, three CTAs per SM) measured best
+    if (const char* env = getenv("SCRIB200_SYNTH3M_STAGES")) variant = atoi(env);
     const int64_t max_rows = (int64_t)65535 * M3_BM;
     for (int64_t r0 = 0; r0 < n_times; r0 += max_rows) {
         const int64_t rows = n_times - r0 < max_rows ? n_times - r0 : max_rows;
         dim3 grid(Gpad / M3_BNC, (unsigned)((rows + M3_BM - 1) / M3_BM));
-        swsh_synth3m_kernel<<<grid, 128, M3_SMEM, (cudaStream_t)stream>>>(
-            reinterpret_cast<const double2*>(modes) + r0 * n_modes, rows, n_modes, B3, npad, Gpad, offset, scale, G,
-            reinterpret_cast<double2*>(F) + r0 * G, band);
+#define M3_LAUNCH(ST_)                                                                                                     \
+    do {                                                                                                                   \
+        cudaFuncSetAttribute(swsh_synth3m_kernel<ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_smem<ST_>());   \
+        swsh_synth3m_kernel<ST_><<<grid, 128, m3_smem<ST_>(), (cudaStream_t)stream>>>(                                      \
+            reinterpret_cast<const double2*>(modes) + r0 * n_modes, rows, n_modes, B3, npad, Gpad, offset, scale, G,        \
+            reinterpret_cast<double2*>(F) + r0 * G, band);                                                                  \
+    } while (0)
+        if (variant == 2) M3_LAUNCH(2);
+        else if (variant == 4) M3_LAUNCH(4);
+        else M3_LAUNCH(3);
+#undef M3_LAUNCH
         SCRIB200_CHECK_LAUNCH("swsh_synthesize_3m");
     }
     return SCRIB200_OK;
