@@ -406,9 +406,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def staged_step():
-        # same calls as TransformPlan.run(), with events between the stages
+    def staged_step(hold_cycles=0):
+        # same calls as TransformPlan.run(), with events between the stages.  hold_cycles > 0 parks the stream on a spin
+        # kernel first, so that the host has queued the whole step before the first stage starts: the intervals between
+        # the events are then kernel time only, whatever the host's launch rate is
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        if hold_cycles:
+            torch.cuda._sleep(int(hold_cycles))
         ev[0].record()
         F = plan.synthesize(a_d)
         ev[1].record()
@@ -428,9 +432,24 @@ def run_ours(args):
         assert prep.verify()       # the retained block assumed from the previous step (same time axis) is what the kernels found
         return ev, up, m
 
-    # ---- device-resident value
+    # ---- device-resident value.  Two loops over the same kernels: (1) the step as ONE CUDA-graph launch
+    # (TransformPlan.capture) - this is `value`: the host is off the critical path, so a busy host cannot put gaps between
+    # the kernels; (2) the eager step with events between the stages, for the per-kernel split and the roofline of the
+    # dominant kernel: each eager step is queued behind a ~10 ms spin kernel, so that its event intervals hold kernel time
+    # and no launch gaps even when the host launches slowly (seen on ~1 box in 3: eager steps of 3-4 ms over 2.3 ms of kernels).
     for _ in range(args.warmup):
         staged_step()
+    barrier()
+    captured = None
+    try:
+        captured = plan.capture(t_d, a_d)
+        for _ in range(args.warmup):
+            captured.replay()
+        torch.cuda.synchronize()
+        assert captured.verify()
+    except Exception as exc:          # no graph: the eager loop below provides the value
+        sys.stderr.write(f"[rank {rank}] CUDA-graph capture of the step failed ({type(exc).__name__}: {exc}); timing the eager step\n")
+        captured = None
     barrier()
     # the collector stays off inside the timed regions, as in timeit: a generation-2 sweep of a process that has torch and
     # scipy loaded takes 40-120 ms and, landing in the middle of one step's launches, was charged to that step's kernels
@@ -443,23 +462,39 @@ def run_ours(args):
         sampler.start()
     launches0 = _lib.launch_count()
     per_kernel = np.zeros(4)
-    total_ms = 0.0
+    eager_ms = 0.0
     n_out = 0
+    n_eager = args.steps if captured is None else max(3, min(args.steps, 50))
     barrier()
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_eager):
         flush.fill_(1)   # L2 flush between timed iterations (outside the per-step event pairs)
-        ev, up, m = staged_step()
+        ev, up, m = staged_step(hold_cycles=2e7)
         torch.cuda.synchronize()
-        total_ms += ev[0].elapsed_time(ev[4])
+        eager_ms += ev[0].elapsed_time(ev[4])
         per_kernel += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
         n_out = up.shape[0]
+    launches_per_step = (_lib.launch_count() - launches0) // n_eager
+    per_kernel /= n_eager
+    eager_ms /= n_eager
+    if captured is not None:
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            captured.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        assert captured.verify()
+        ms_step = total_ms / args.steps
+    else:
+        ms_step = eager_ms
     barrier()
     wall = time.perf_counter() - wall0
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * args.steps      # kernels of ours per step (counted in the eager loop) x timed steps
     clocks = sampler.stop() if rank == 0 else None
-    ms_step = total_ms / args.steps
-    per_kernel /= args.steps
 
     # ---- e2e: the public API on host arrays (plan construction + H2D + kernels + D2H inside the timed region)
     # warm-up: the pinned-host caching allocator needs a few calls before result buffers are recycled
@@ -494,7 +529,7 @@ def run_ours(args):
     extras = {}
     G, grid_str = plan.G, f"{plan.n_theta}x{plan.n_phi}"
     if not args.no_extras:
-        del plan, a_d, flush
+        del plan, a_d, flush, captured
         torch.cuda.empty_cache()
         try:
             extras["batch_config2"] = extra_batch(args, torch, dist, world, rank, kw)
@@ -529,7 +564,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": remap_bytes}
         else:
             ach = kern["swsh_synth_dmma"]["achieved_tflops"]
-            roof = {"kernel": "swsh_synth3m_kernel", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
+            roof = {"kernel": "swsh_synth3m_kernel<3>", "bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s",
                     "frac": ach / dgemm_tf, "traffic": None,
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "algorithmic_flops_per_launch": synth_flops,
@@ -540,7 +575,7 @@ def run_ours(args):
         try:
             with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 traffic = json.load(f)
-            names = {"swsh_synth_dmma": "swsh_synth3m_kernel", "spline_tile(spline_remap)": "spline_tile_kernel<0, 320>",
+            names = {"swsh_synth_dmma": "swsh_synth3m_kernel<3>", "spline_tile(spline_remap)": "spline_tile_kernel<0, 320>",
                      "map2salm_tiled": "map2salm_persist_kernel<1>"}
             for kname, ncu_name in names.items():
                 if ncu_name in traffic:
@@ -571,6 +606,8 @@ def run_ours(args):
                              "sample": f"first {args.cpu_sample} time steps of the same waveform through oracle/ (port of scri's algorithm, scipy FITPACK splines; reference packages not installable here), {csec:.1f} s; host has {os.cpu_count()} cores"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+            "step_launch": "one CUDA-graph launch per step (TransformPlan.capture)" if captured is not None else "eager",
+            "eager_ms_per_step": eager_ms,
         }
         line.update(extras)
         emit(line)

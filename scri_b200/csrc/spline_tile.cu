@@ -550,28 +550,83 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
         const bool colok = col0 + cc < G2;
         out += (size_t)bz * N * G2;
         if (MODE == 4) up += (size_t)bz * N * G2;
-        for (int i = a + tid / ST_COLS; i < b; i += rstep) {
+        auto value = [&](int i, bool& last_row, double& last_val) -> double {
             const double ht = STT(i + 1) - STT(i);
             const double yi = SY(i, cc), yi1 = SY(i + 1, cc);
             const double Mi = SD(i, cc), Mi1 = SD(i + 1, cc);
-            if (!colok) continue;
+            last_row = false;
             if (MODE == 1) {
                 const double dl = (yi1 - yi) / ht, h6 = ht * (1.0 / 6.0);
-                out[(size_t)i * G2 + col0 + cc] = dl - h6 * (2.0 * Mi + Mi1);
-                if (i == N - 2) out[(size_t)(N - 1) * G2 + col0 + cc] = dl + h6 * (Mi + 2.0 * Mi1);
+                if (i == N - 2) {
+                    last_row = true;
+                    last_val = dl + h6 * (Mi + 2.0 * Mi1);
+                }
+                return dl - h6 * (2.0 * Mi + Mi1);
             } else if (MODE == 2) {
-                out[(size_t)i * G2 + col0 + cc] = Mi;
-                if (i == N - 2) out[(size_t)(N - 1) * G2 + col0 + cc] = Mi1;
+                if (i == N - 2) {
+                    last_row = true;
+                    last_val = Mi1;
+                }
+                return Mi;
             } else if (MODE == 3) {
-                out[(size_t)(i + 1) * G2 + col0 + cc] = 0.5 * ht * (yi + yi1) - (ht * ht * ht) * (1.0 / 24.0) * (Mi + Mi1);
-                if (i == 0) out[col0 + cc] = 0.0;
+                return 0.5 * ht * (yi + yi1) - (ht * ht * ht) * (1.0 / 24.0) * (Mi + Mi1);
             } else {
                 // second antiderivative over the interval: II_{i+1} - II_i = h I_i + int int of the cubic piece
                 const double c1 = (yi1 - yi) / ht - ht * (1.0 / 6.0) * (2.0 * Mi + Mi1);
                 const double h2 = ht * ht;
-                const double J = h2 * (0.5 * yi + ht * (1.0 / 6.0) * c1 + h2 * ((1.0 / 24.0) * Mi + (1.0 / 120.0) * (Mi1 - Mi)));
-                out[(size_t)(i + 1) * G2 + col0 + cc] = J + ht * up[(size_t)i * G2 + col0 + cc];
-                if (i == 0) out[col0 + cc] = 0.0;
+                const double Jv = h2 * (0.5 * yi + ht * (1.0 / 6.0) * c1 + h2 * ((1.0 / 24.0) * Mi + (1.0 / 120.0) * (Mi1 - Mi)));
+                return Jv + (colok ? ht * up[(size_t)i * G2 + col0 + cc] : 0.0);
+            }
+        };
+        if (MODE <= 2) {
+            for (int i = a + tid / ST_COLS; i < b; i += rstep) {
+                bool lr;
+                double lv = 0.0;
+                const double v = value(i, lr, lv);
+                if (!colok) continue;
+                out[(size_t)i * G2 + col0 + cc] = v;
+                if (lr) out[(size_t)(N - 1) * G2 + col0 + cc] = lv;
+            }
+        } else {
+            // antiderivatives: the increments of the tile's intervals are summed up inside the tile (row i + 1 receives the
+            // sum over the intervals a .. i), so the column scan that follows only has to carry one total per tile across
+            // the tiles - one read-modify-write pass over the output less than scanning the raw increments
+            constexpr int VMAX = 16;                        // rows per thread: body / (threads / 16) < 16
+            double val[VMAX];
+            bool lr;
+            double lv;
+#pragma unroll
+            for (int k = 0; k < VMAX; ++k) {
+                const int i = a + tid / ST_COLS + k * rstep;
+                val[k] = (i < b) ? value(i, lr, lv) : 0.0;
+            }
+            __syncthreads();                                // every moment has been read: the M tile becomes the work area
+#pragma unroll
+            for (int k = 0; k < VMAX; ++k) {
+                const int i = a + tid / ST_COLS + k * rstep;
+                if (i < b) SD(i, cc) = val[k];
+            }
+            __syncthreads();
+            const int nr = b - a, slen = (nr + ST_BR - 1) / ST_BR;      // 16 strips of slen rows per column
+            for (int id = tid; id < ST_BR * ST_COLS; id += nthr) {
+                const int s = id / ST_COLS, c = id - s * ST_COLS;
+                const int r0s = a + s * slen, r1s = (r0s + slen < b) ? r0s + slen : b;
+                double run = 0.0;
+                for (int r = r0s; r < r1s; ++r) {
+                    run += SD(r, c);
+                    SD(r, c) = run;
+                }
+                sEdgeD[s * ST_COLS + c] = run;
+            }
+            __syncthreads();
+            if (colok) {
+                for (int i = a + tid / ST_COLS; i < b; i += rstep) {
+                    const int s = (i - a) / slen;
+                    double pre = 0.0;
+                    for (int p = 0; p < s; ++p) pre += sEdgeD[p * ST_COLS + cc];
+                    out[(size_t)(i + 1) * G2 + col0 + cc] = SD(i, cc) + pre;
+                    if (i == 0) out[col0 + cc] = 0.0;
+                }
             }
         }
     }
@@ -628,18 +683,43 @@ column_scan_add_kernel(double* __restrict__ x, int64_t N, int C) {
     for (int64_t r = r0; r < r1; ++r, p += C) *p += base;
 }
 
-static int launch_column_scan(double* x, int64_t N, int C, cudaStream_t st) {
-    const unsigned gx = (unsigned)((C + 127) / 128);
-    const int64_t nch = (N + SCAN_ROWS - 1) / SCAN_ROWS;
-    SCRIB200_REQUIRE(nch <= 65535, "spline_calculus(scan): series too long (%lld rows)", (long long)N);
-    column_scan_local_kernel<<<dim3(gx, (unsigned)nch), 128, 0, st>>>(x, N, C);
-    SCRIB200_CHECK_LAUNCH("spline_calculus(scan: local)");
-    if (nch > 1) {
-        column_scan_totals_kernel<<<gx, 128, 0, st>>>(x, N, C);
-        SCRIB200_CHECK_LAUNCH("spline_calculus(scan: totals)");
-        column_scan_add_kernel<<<dim3(gx, (unsigned)(nch - 1)), 128, 0, st>>>(x, N, C);
-        SCRIB200_CHECK_LAUNCH("spline_calculus(scan: add)");
+// After spline_tile_kernel<3 / 4>: rows k body + 1 .. min((k + 1) body, N - 1) of x hold the running sums of tile k; its last
+// row holds the tile total.  (B) one thread per column turns the tile totals into global values (N / body steps); (C) every
+// tile but the first adds the (now global) value at the end of the previous tile to all its rows but the last.
+__global__ void __launch_bounds__(128)
+tile_scan_totals_kernel(double* __restrict__ x, int64_t N, int C, int body) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= C) return;
+    double run = 0.0;
+    for (int64_t last = body; ; last += body) {
+        const int64_t row = last < N - 1 ? last : N - 1;
+        run += x[row * C + col];
+        x[row * C + col] = run;
+        if (last >= N - 1) break;
     }
+}
+
+__global__ void __launch_bounds__(128)
+tile_scan_add_kernel(double* __restrict__ x, int64_t N, int C, int body) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= C) return;
+    const int64_t first = (int64_t)(blockIdx.y + 1) * body;             // last row of the previous tile: already global
+    if (first >= N - 1) return;
+    const int64_t last = first + body < N - 1 ? first + body : N - 1;   // my own last row: already global
+    const double base = x[first * C + col];
+    double* p = x + (first + 1) * C + col;
+#pragma unroll 8
+    for (int64_t r = first + 1; r < last; ++r, p += C) *p += base;
+}
+
+static int launch_tile_scan(double* x, int64_t N, int C, int body, cudaStream_t st) {
+    const unsigned gx = (unsigned)((C + 127) / 128);
+    const int64_t ntiles = (N - 1 + body - 1) / body;
+    if (ntiles <= 1) return SCRIB200_OK;
+    tile_scan_totals_kernel<<<gx, 128, 0, st>>>(x, N, C, body);
+    SCRIB200_CHECK_LAUNCH("spline_calculus(scan: totals)");
+    tile_scan_add_kernel<<<dim3(gx, (unsigned)(ntiles - 1)), 128, 0, st>>>(x, N, C, body);
+    SCRIB200_CHECK_LAUNCH("spline_calculus(scan: add)");
     return SCRIB200_OK;
 }
 
@@ -829,12 +909,14 @@ extern "C" int scrib200_spline_calculus(const double* t, int64_t n_times, const 
         return launch_tile<2>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     const int C = 2 * ncol;
     double* first = (order == -1) ? out : aux;
+    int rbody = body, rhalo = halo;
+    resolve_tile(rhalo, rbody);                              // the tile height the launches below will use
     int rc = launch_tile<3>(t, n_times, data, ncol, nullptr, nullptr, tab, nullptr, 0, first, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
-    rc = launch_column_scan(first, n_times, C, (cudaStream_t)stream);
+    rc = launch_tile_scan(first, n_times, C, rbody, (cudaStream_t)stream);
     if (rc != SCRIB200_OK) return rc;
     if (order == -1) return SCRIB200_OK;
     rc = launch_tile<4>(t, n_times, data, ncol, nullptr, nullptr, tab, first, 0, out, 0, halo, body, nullptr, 0, stream, "spline_calculus");
     if (rc != SCRIB200_OK) return rc;
-    return launch_column_scan(out, n_times, C, (cudaStream_t)stream);
+    return launch_tile_scan(out, n_times, C, rbody, (cudaStream_t)stream);
 }

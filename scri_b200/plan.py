@@ -258,7 +258,7 @@ class GridPlan:
             return self._host_pool.pop()
         return self.torch.empty(8, dtype=self.torch.float64, pin_memory=True)
 
-    def prepare(self, t, overlapped=False, after=None, speculate=False):
+    def prepare(self, t, overlapped=False, after=None, speculate=False, memo_key=None):
         """Launch the per-time-axis preparation (scrib200_spline_prepare): spline factor table, u' for every sample,
         the retained block and the decay diagnostics.  Nothing is read back here; see `TimePrep.resolve`.
         `overlapped=True` launches on the plan's side stream so the (tiny, latency-bound) kernels run under the
@@ -273,7 +273,9 @@ class GridPlan:
             if not hasattr(self, "_prep_memo"):
                 self._prep_memo = {}
             prep._memo = self._prep_memo
-            prep._memo_key = (t.data_ptr(), getattr(t, "_version", 0), int(t.shape[0]))
+            # identity of the time axis: the device tensor itself, or what the caller says (a host array that is uploaded
+            # afresh on every call); a stale identity costs one repeated step, never a wrong result (see verify)
+            prep._memo_key = memo_key if memo_key is not None else (t.data_ptr(), getattr(t, "_version", 0), int(t.shape[0]))
             seen = self._prep_memo.get(prep._memo_key)
             if seen is not None:
                 prep._assumed = seen
@@ -676,7 +678,7 @@ class TransformPlan(GridPlan):
         cs.synchronize()
         return host.numpy()
 
-    def _run_streaming(self, t, data, slabs, t_host, debug_poison=False):
+    def _run_streaming(self, t, data, slabs, t_host, debug_poison=False, on_queued=None, _speculate=True):
         """End-to-end pipeline for modes that are still arriving from the host (`slabs` of ops.to_device_slabs): slab j is
         synthesized as it lands, and every output time whose input window is already synthesized is remapped, analysed and
         copied back under the transfer of the later slabs.  Output j sits at input row lo + j; grid point g reads input
@@ -689,10 +691,15 @@ class TransformPlan(GridPlan):
         torch = self.torch
         lib = _lib.load()
         cur = torch.cuda.current_stream()
-        prep = self.prepare(t)                       # the time axis is already on the device: four tiny launches
+        # the time axis is already on the device: four tiny launches.  If this host axis was transformed before, its retained
+        # block and spline halo are assumed, so the pipeline is queued without waiting for them (checked at the end)
+        t_host = np.asarray(t_host, dtype=float)
+        key = ("host", t_host.ctypes.data, int(t_host.shape[0]), float(t_host[0]), float(t_host[-1]), float(t_host[t_host.shape[0] // 2]))
+        prep = self.prepare(t, speculate=_speculate, memo_key=key)
         lo, hi = prep.resolve()                      # host wait for those only; the modes keep streaming on the copy stream
         n_out = hi - lo
         if n_out < 8192:
+            prep.verify()
             return None
         uprm = prep.uprm
         if self._d2h_stream is None:
@@ -751,11 +758,16 @@ class TransformPlan(GridPlan):
                         timing.append((f"outputs {done}:{out_hi} landed on the host", landed))
                 done = out_hi
         _trace("all launches queued")
+        if on_queued is not None:
+            on_queued()                              # host work of the caller that can run under the pipeline
+        ok = prep.verify()
         cs.synchronize()
         _trace("last result slab landed")
+        if not ok:                                   # the axis changed behind the same identity: once more, nothing assumed
+            return self._run_streaming(t, data, slabs, t_host, debug_poison=debug_poison, _speculate=False)
         return u_host.numpy(), host.numpy()
 
-    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None):
+    def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None, on_queued=None):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
 
         The only host round trip is the 64-byte `info` read-back (size of the retained block); it travels on a side
@@ -764,7 +776,7 @@ class TransformPlan(GridPlan):
         times are cut into S slabs, each remapped, analysed and copied out on a copy stream while the next one computes
         (the end-to-end path of WaveformGrid.transform)."""
         if host_slabs and slabs is not None and t_host is not None and prep is None and self.tile and not self.mix and not return_grid:
-            streamed = self._run_streaming(t, data, slabs, t_host)
+            streamed = self._run_streaming(t, data, slabs, t_host, on_queued=on_queued)
             if streamed is not None:
                 return streamed
         cur = self.torch.cuda.current_stream()
@@ -792,6 +804,62 @@ class TransformPlan(GridPlan):
                 return uprm, out
             ready = self.torch.cuda.Event()       # the time axis changed behind the same storage: once more, unassumed
             ready.record(cur)
+
+
+class CapturedTransform:
+    """One device-resident transform (synthesis, spline preparation on its side stream, remap, analysis) recorded as a
+    CUDA graph: `replay()` re-runs it on the CURRENT contents of the `t` and `data` tensors it was captured with, in one
+    launch - the host is then no longer on the critical path of a step (eager, a step is ~25 launches and a few dozen
+    tensor allocations; a busy or throttled host shows up as gaps between the kernels).  The retained block found when the
+    graph was captured is baked into it; `verify()` checks it against what the last replay found."""
+
+    def __init__(self, plan, t, data):
+        torch = plan.torch
+        self.plan, self.t, self.data = plan, t, data
+        plan.run(t, data)                                   # warms every cache the capture must not touch (memo, workspace, pinned pool)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            F = plan.synthesize(data, t)
+            self.prep = plan.prepare(t, overlapped=True, after=ready, speculate=True)
+            if self.prep._assumed is None:
+                raise RuntimeError("CapturedTransform: the time axis must have been prepared once before the capture")
+            cur.wait_event(self.prep.done)
+            self.uprm = self.prep.uprm
+            if plan.tile:
+                gridT = plan.remap_tiled(t, F, self.uprm, self.prep)
+                self.modes = plan.analyze_tiled(gridT, self.uprm.shape[0])
+            else:
+                self.modes = plan.analyze(plan.remap(t, F, self.uprm, self.prep))
+            # the side stream (preparation + read-back of `info`) rejoins the capturing stream
+            cur.wait_stream(plan._side_stream())
+        self._info_host = self.prep._host                   # the graph's read-back lands here on every replay
+        self.prep._host = None
+
+    def replay(self):
+        """Queue one transform on the current stream; returns (u', modes') - the same tensors on every call."""
+        self.graph.replay()
+        return self.uprm, self.modes
+
+    def verify(self):
+        """After a replay has finished: is the retained block baked into the graph the one the kernels found?"""
+        self.plan.torch.cuda.current_stream().synchronize()
+        v = self._info_host.tolist()
+        lo, hi = int(v[0]), max(int(v[0]), int(v[1]))
+        return (lo, hi) == tuple(self.prep._assumed[:2])
+
+
+def _capture(self, t, data):
+    """See CapturedTransform."""
+    if self.mix:
+        raise NotImplementedError("capture does not cover psi0..psi3 (their companion fields are uploaded per call)")
+    return CapturedTransform(self, t, data)
+
+
+TransformPlan.capture = _capture
 
 
 TRACE = None        # dev aid: set to a list to collect (label, perf_counter) marks of the end-to-end pipeline
@@ -956,8 +1024,9 @@ class TimePrep:
         with torch.cuda.stream(side):
             self._host.copy_(self.info, non_blocking=True)
             self._ready.record(side)
-        for x in (self.info, self.tab, self.uprm_full):
-            x.record_stream(side)
+        if not torch.cuda.is_current_stream_capturing():     # (a graph's private pool keeps its tensors for the graph's lifetime)
+            for x in (self.info, self.tab, self.uprm_full):
+                x.record_stream(side)
         self._resolved = None
         self._assumed = None
         self._memo = None

@@ -130,7 +130,7 @@ class WaveformGrid(WaveformBase):
         original_kwargs = kwargs.copy()
         # the modes stream in slab by slab on a copy stream while the plan is built; each slab is synthesized as it lands
         big = w_modes.data.nbytes >= (8 << 20)
-        t_d = ops.to_device(w_modes.t, np.float64)       # before the modes: a copy queued behind them would wait for all of them
+        t_d = ops.to_device_nowait(w_modes.t, np.float64)   # before the modes: a copy queued behind them would wait for all of them
         if big:
             a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, weights=(1, 2, 3, 4, 4, 4, 3, 2, 1))
         else:
@@ -148,11 +148,18 @@ class WaveformGrid(WaveformBase):
             a_fut.result()
             _lib.require_cuda().cuda.current_stream().wait_event(slabs[-1][2])
             slabs = None
-        # (the provenance string is formatted while the first slabs are in flight, not after the results have landed)
-        statement = f"WaveformGrid.from_modes({w_modes}, **{original_kwargs}).to_modes({ell_max})"
+        # (the provenance string is formatted while the pipeline runs: neither before the first launch nor after the last byte)
+        note = {}
+
+        def provenance():
+            note["statement"] = f"WaveformGrid.from_modes({w_modes}, **{original_kwargs}).to_modes({ell_max})"
+
         # modes land in pinned host memory slab by slab, the first output slabs while the last input slabs are still in flight
-        uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4, t_host=np.asarray(w_modes.t, dtype=float))
+        uprm, modes = plan.run(t_d, a_d, slabs=slabs, host_slabs=4, t_host=np.asarray(w_modes.t, dtype=float), on_queued=provenance)
         _trace("plan.run returned")
+        if "statement" not in note:
+            provenance()
+        statement = note["statement"]
         if a_fut is not None:
             a_fut.result()                       # surfaces a failed copy
         if plan.leftover_kwargs:

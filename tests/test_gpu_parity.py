@@ -1179,3 +1179,23 @@ def test_abd_conformal_factors_reference_test():
     # the ell = 32 floor by 23 before 1089 of them are summed on the grid, which is the 3e-13 seen on eth(k)/k.  The
     # functions under test agree with the reference's own output to 1e-14 (test_gpu_reference_golden.py).
     assert errs[0] < tolerance and errs[2] < tolerance and errs[3] < 1e-13 and errs[1] < 1e-12, errs
+
+
+def test_captured_transform_replays_the_eager_path():
+    """TransformPlan.capture: the device-resident step recorded as one CUDA graph gives the eager path's result bit for bit,
+    follows new contents of its input tensors, and its baked-in retained block is verified after the replay."""
+    import torch
+
+    t, data = smooth_modes(n_times=20000, t0=0.0, t1=2000.0, seed=91)
+    plan = P.TransformPlan(2, 8, sb.h, r_is_scaled_out=True, **BMS)
+    td, ad = ops.to_device(t), ops.to_device(data)
+    u1, m1 = plan.run(td, ad)
+    cap = plan.capture(td, ad)
+    u2, m2 = cap.replay()
+    assert cap.verify()
+    assert torch.equal(u1, u2) and torch.equal(m1, m2)
+    ad.mul_(2.0)                                   # same tensor, new contents: h is linear in the modes up to the supertranslation term
+    u3, m3 = cap.replay()
+    torch.cuda.synchronize()
+    u4, m4 = plan.run(td, ad)
+    assert torch.equal(u3, u4) and torch.equal(m3, m4)
