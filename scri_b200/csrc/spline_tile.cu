@@ -258,7 +258,8 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
     const int ybase = ylo & ~7;                             // row held by shared-memory row 0: keeps (r - ybase) & 7 == r & 7
     const int nrows = 2 * box_rows;                         // shared-memory rows (>= yhi - ybase + 1)
     const int qlo = slo / ST_BR, qhi = shi / ST_BR;         // sweep blocks of this tile
-    const int nblk_max = (body + 2 * halo) / ST_BR;
+    const int nblk_raw = (body + 2 * halo) / ST_BR;
+    const int nblk_max = nblk_raw > ST_BR ? nblk_raw : ST_BR;   // the antiderivative modes keep ST_BR strip totals in sEdgeD
 
     double* sY = reinterpret_cast<double*>(s_raw + ((1024u - (st_smem_u32(s_raw) & 1023u)) & 1023u));   // [nrows][16] F (swizzled)
     double* sD = sY + (size_t)nrows * ST_ROWD;              // [nrows][16] moments M (same layout)
@@ -619,12 +620,23 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
                 sEdgeD[s * ST_COLS + c] = run;
             }
             __syncthreads();
+            if (tid < ST_COLS) {                            // strip totals -> what precedes each strip
+                double run = 0.0;
+#pragma unroll
+                for (int p = 0; p < ST_BR; ++p) {
+                    const double v = sEdgeD[p * ST_COLS + tid];
+                    sEdgeD[p * ST_COLS + tid] = run;
+                    run += v;
+                }
+            }
+            __syncthreads();
             if (colok) {
+                const float rs = 1.0f / (float)slen;
                 for (int i = a + tid / ST_COLS; i < b; i += rstep) {
-                    const int s = (i - a) / slen;
-                    double pre = 0.0;
-                    for (int p = 0; p < s; ++p) pre += sEdgeD[p * ST_COLS + cc];
-                    out[(size_t)(i + 1) * G2 + col0 + cc] = SD(i, cc) + pre;
+                    int s = (int)((float)(i - a) * rs);    // (i - a) / slen: both below 2^9, one correction step at most
+                    s -= (s * slen > i - a);
+                    s += ((s + 1) * slen <= i - a);
+                    out[(size_t)(i + 1) * G2 + col0 + cc] = SD(i, cc) + sEdgeD[s * ST_COLS + cc];
                     if (i == 0) out[col0 + cc] = 0.0;
                 }
             }
@@ -636,66 +648,49 @@ spline_tile_kernel(const __grid_constant__ CUtensorMap tmF, const double* __rest
 #undef STT
 }
 
-// Inclusive scan down the columns of x[N, C] (in place): turns the per-interval integrals into the antiderivative
-// (waveform_base.py:697-703).  Three phases, no workspace: (A) every (chunk of SCAN_ROWS rows, 128 columns) CTA scans
-// its chunk locally - its last row then holds the chunk total; (B) one thread per column turns the chunk totals into
-// global values (N / SCAN_ROWS steps); (C) every chunk but the first adds the value at the end of the previous chunk to
-// all its rows but the last.  Lanes run along the columns: every access is a coalesced 1 KB row segment.
-constexpr int SCAN_ROWS = 512;
-
-__global__ void __launch_bounds__(128)
-column_scan_local_kernel(double* __restrict__ x, int64_t N, int C) {
-    const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col >= C) return;
-    const int64_t r0 = (int64_t)blockIdx.y * SCAN_ROWS, r1 = (r0 + SCAN_ROWS < N) ? r0 + SCAN_ROWS : N;
-    double run = 0.0;
-    double* p = x + r0 * C + col;
-#pragma unroll 8
-    for (int64_t r = r0; r < r1; ++r, p += C) {
-        run += *p;
-        *p = run;
-    }
-}
-
-__global__ void __launch_bounds__(128)
-column_scan_totals_kernel(double* __restrict__ x, int64_t N, int C) {
-    const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col >= C) return;
-    double run = 0.0;
-#pragma unroll 8
-    for (int64_t last = SCAN_ROWS - 1; last < N; last += SCAN_ROWS) {   // full chunks only: a partial last chunk has no successor
-        run += x[last * C + col];
-        x[last * C + col] = run;
-    }
-}
-
-__global__ void __launch_bounds__(128)
-column_scan_add_kernel(double* __restrict__ x, int64_t N, int C) {
-    const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col >= C) return;
-    const int64_t r0 = (int64_t)(blockIdx.y + 1) * SCAN_ROWS;          // chunk 0 needs nothing
-    if (r0 >= N) return;
-    const bool full = r0 + SCAN_ROWS <= N;
-    const int64_t r1 = full ? r0 + SCAN_ROWS - 1 : N;                   // the last row of a full chunk is already global
-    const double base = x[(r0 - 1) * C + col];
-    double* p = x + r0 * C + col;
-#pragma unroll 8
-    for (int64_t r = r0; r < r1; ++r, p += C) *p += base;
-}
-
-// After spline_tile_kernel<3 / 4>: rows k body + 1 .. min((k + 1) body, N - 1) of x hold the running sums of tile k; its last
+// Column scan that turns the per-interval integrals into the antiderivative (waveform_base.py:697-703), in place and
+// without a workspace.  After spline_tile_kernel<3 / 4>: rows k body + 1 .. min((k + 1) body, N - 1) of x hold the running sums of tile k; its last
 // row holds the tile total.  (B) one thread per column turns the tile totals into global values (N / body steps); (C) every
 // tile but the first adds the (now global) value at the end of the previous tile to all its rows but the last.
-__global__ void __launch_bounds__(128)
-tile_scan_totals_kernel(double* __restrict__ x, int64_t N, int C, int body) {
-    const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col >= C) return;
+__global__ void __launch_bounds__(1024)
+tile_scan_totals_kernel(double* __restrict__ x, int64_t N, int C, int body, int ntiles) {
+    // 32 columns x 32 segments of the tile range per CTA: a serial walk over N / body totals per column is a chain of
+    // dependent DRAM round trips (4 ms for 1e6 rows); here every thread walks ntiles / 32 of them with 8 loads in flight
+    __shared__ double tot[32][33];
+    const int col = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
+    const int per = (ntiles + 31) / 32;
+    const int k0 = seg * per, k1 = (k0 + per < ntiles) ? k0 + per : ntiles;
+    const bool ok = col < C;
+    auto at = [&](int k) -> double* {
+        const int64_t last = (int64_t)(k + 1) * body;
+        return x + (last < N - 1 ? last : N - 1) * C + col;
+    };
     double run = 0.0;
-    for (int64_t last = body; ; last += body) {
-        const int64_t row = last < N - 1 ? last : N - 1;
-        run += x[row * C + col];
-        x[row * C + col] = run;
-        if (last >= N - 1) break;
+    if (ok) {
+        for (int k = k0; k < k1; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (k + j < k1) ? *at(k + j) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (k + j < k1) {
+                    run += v[j];
+                    *at(k + j) = run;
+                }
+        }
+    }
+    tot[seg][threadIdx.x] = run;
+    __syncthreads();
+    if (!ok || seg == 0) return;
+    double pre = 0.0;
+    for (int p = 0; p < seg; ++p) pre += tot[p][threadIdx.x];
+    for (int k = k0; k < k1; k += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k + j < k1) ? *at(k + j) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (k + j < k1) *at(k + j) = v[j] + pre;
     }
 }
 
@@ -708,15 +703,22 @@ tile_scan_add_kernel(double* __restrict__ x, int64_t N, int C, int body) {
     const int64_t last = first + body < N - 1 ? first + body : N - 1;   // my own last row: already global
     const double base = x[first * C + col];
     double* p = x + (first + 1) * C + col;
-#pragma unroll 8
-    for (int64_t r = first + 1; r < last; ++r, p += C) *p += base;
+    int left = (int)(last - first - 1);
+    for (; left >= 8; left -= 8, p += 8 * (size_t)C) {       // 8 loads in flight before the first store
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p[(size_t)j * C];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[(size_t)j * C] = v[j] + base;
+    }
+    for (; left > 0; --left, p += C) *p += base;
 }
 
 static int launch_tile_scan(double* x, int64_t N, int C, int body, cudaStream_t st) {
     const unsigned gx = (unsigned)((C + 127) / 128);
     const int64_t ntiles = (N - 1 + body - 1) / body;
     if (ntiles <= 1) return SCRIB200_OK;
-    tile_scan_totals_kernel<<<gx, 128, 0, st>>>(x, N, C, body);
+    tile_scan_totals_kernel<<<(unsigned)((C + 31) / 32), dim3(32, 32), 0, st>>>(x, N, C, body, (int)ntiles);
     SCRIB200_CHECK_LAUNCH("spline_calculus(scan: totals)");
     tile_scan_add_kernel<<<dim3(gx, (unsigned)(ntiles - 1)), 128, 0, st>>>(x, N, C, body);
     SCRIB200_CHECK_LAUNCH("spline_calculus(scan: add)");
@@ -730,13 +732,16 @@ static int tile_box_rows(int body, int halo) {
 
 static size_t tile_smem_bytes(int body, int halo) {
     const size_t nrows = 2 * (size_t)tile_box_rows(body, halo);
-    const size_t nblk = ((size_t)body + 2 * halo) / ST_BR;
+    const size_t nblk = std::max<size_t>(((size_t)body + 2 * halo) / ST_BR, ST_BR);
     return (2 * nrows * ST_ROWD + nrows * ST_TAB6 + nrows + 2 * nblk * ST_COLS + 5 * ST_COLS) * sizeof(double) + 1024;   // + constants, alignment slack
 }
 
 static void resolve_tile(int& halo, int& body) {
     if (halo <= 0) halo = 32;
-    if (body <= 0) body = (halo <= 32) ? 240 : (halo <= 64 ? 176 : 128);   // two CTAs per SM up to halo = 64
+    if (body <= 0) {
+        static const int env_body = [] { const char* e = std::getenv("SCRIB200_TILE_BODY"); return e ? std::atoi(e) : 0; }();
+        body = env_body > 0 ? env_body : ((halo <= 32) ? 240 : (halo <= 64 ? 176 : 128));   // two CTAs per SM up to halo = 64
+    }
 }
 
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -297,6 +297,11 @@ def test_spline_calculus_vs_scipy():
         # antiderivatives (scri/waveform_base.py:697-703): exact integrals of the piecewise cubic, zero at t[0]
         assert rel(ops.spline_calculus(t, data, "antiderivative", 1), CubicSpline(t, data).antiderivative(1)(t)) < 1e-13
         assert rel(ops.spline_calculus(t, data, "antiderivative", 2), CubicSpline(t, data).antiderivative(2)(t)) < 1e-13
+    # many tiles: the tile totals are carried across the tiles by 32 segments per column (spline_tile.cu: tile_scan_*)
+    t, data = smooth_modes(n_times=20011, uniform=False, seed=22)
+    data = data[:, :21] + 0.3                     # a non-zero mean, so that the running totals grow along the series
+    for order in (1, 2):
+        assert rel(ops.spline_calculus(t, data, "antiderivative", order), CubicSpline(t, data).antiderivative(order)(t)) < 1e-13
     # linear data is reproduced exactly (reference tests/test_waveform.py:183-270)
     t = np.linspace(-10.0, 100.0, 1000)
     lin = (np.arange(77) - 1j * np.arange(77))[None, :] * t[:, None]
