@@ -277,7 +277,8 @@ int scrib200_theta_quad(const double* P, int64_t n_times, const int* tiles, int 
  * scrib200_host_register) goes up in one asynchronous DMA: it must stay unchanged until `stream` reaches that point.
  * scrib200_host_register / _unregister page-lock and release a caller's array in place (cudaHostRegister): worth it
  * for arrays that are transferred more than once - replaces the reference's host-resident `w.data` as the operand of
- * every transform (scri/waveform_grid.py:475).
+ * every transform (scri/waveform_grid.py:475).  scrib200_host_register returns 0 when it page-locked the array (the
+ * caller owes a scrib200_host_unregister), 1 when the memory was page-locked already (nothing to undo), < 0 on failure.
  */
 int scrib200_h2d(void* dst_device, const void* src_host, size_t nbytes, void* stream);
 int scrib200_host_register(const void* host, size_t nbytes);

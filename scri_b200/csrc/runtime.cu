@@ -212,11 +212,17 @@ extern "C" int scrib200_h2d(void* dst_device, const void* src_host, size_t nbyte
 extern "C" int scrib200_host_register(const void* p, size_t nbytes) {
     using namespace scrib200;
     SCRIB200_REQUIRE(p && nbytes > 0, "host_register: null pointer");
-    cudaError_t e = cudaHostRegister(const_cast<void*>(p), nbytes, cudaHostRegisterPortable);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    // memory that is page-locked already (cudaHostAlloc'd, e.g. a numpy view of a pinned torch tensor, or registered by
+    // someone else) needs nothing - and cudaHostRegister on it fails with "invalid argument"
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) {
+        if (attr.type == cudaMemoryTypeHost) return 1;      // page-locked by someone else: theirs to release
+    } else {
         cudaGetLastError();
-        return SCRIB200_OK;
     }
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), nbytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) cudaGetLastError();      // never leave the error for the next launch check to find
+    if (e == cudaErrorHostMemoryAlreadyRegistered) return 1;
     SCRIB200_REQUIRE(e == cudaSuccess, "host_register: %s", cudaGetErrorString(e));
     return SCRIB200_OK;
 }

@@ -125,11 +125,15 @@ def _maybe_register(a):
     if sum(k[1] for k in _registered) + a.nbytes > REGISTER_MAX_BYTES:
         return False
     lib = _lib.load()
-    if lib.scrib200_host_register(a.ctypes.data, a.nbytes) != 0:
+    rc = lib.scrib200_host_register(a.ctypes.data, a.nbytes)
+    if rc < 0:
         return False
+    ours = rc == 0                                 # 1: page-locked already (e.g. a view of a pinned torch tensor)
 
     def release(ptr=a.ctypes.data, k=key):
         _registered.pop(k, None)
+        if not ours:
+            return
         try:
             _torch().cuda.synchronize()            # no DMA may still be reading the pages
             lib.scrib200_host_unregister(ptr)

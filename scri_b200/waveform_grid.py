@@ -4,6 +4,7 @@ Mirrors scri/waveform_grid.py: `from_modes` (:331-613), `to_modes` (:274-329), `
 with the numerics executed on the GPU by scri_b200.plan.TransformPlan.
 """
 import numbers
+import os
 import pprint
 import warnings
 
@@ -14,6 +15,12 @@ from .constants import Inertial, SpinWeights
 from .plan import TransformPlan, _trace, cached_transform_plan
 from .waveform_base import WaveformBase
 from .waveform_modes import WaveformModes
+
+# relative sizes of the slabs the modes are uploaded in (small first: the kernels start early; small last: a short tail).
+# SCRIB200_SLAB_WEIGHTS is a developer knob for measuring other cuts.
+_SLAB_WEIGHTS = tuple(float(x) for x in os.environ.get("SCRIB200_SLAB_WEIGHTS", "1,2,3,4,4,4,3,2,1").split(","))
+
+
 
 
 class WaveformGrid(WaveformBase):
@@ -132,7 +139,7 @@ class WaveformGrid(WaveformBase):
         big = w_modes.data.nbytes >= (8 << 20)
         t_d = ops.to_device_nowait(w_modes.t, np.float64)   # before the modes: a copy queued behind them would wait for all of them
         if big:
-            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, weights=(1, 2, 3, 4, 4, 4, 3, 2, 1))
+            a_d, slabs, a_fut = ops.to_device_slabs(w_modes.data, np.complex128, weights=_SLAB_WEIGHTS)
         else:
             a_d, slabs, a_fut = ops.to_device(w_modes.data, np.complex128), None, None
         try:

@@ -940,6 +940,30 @@ def test_transform_host_path_at_the_slab_thresholds(n_times):
     assert rel(out.data[sel], ref.data[100:-100]) < 1e-10        # the window's own spline ends are ~1e-11 away after 100 steps
 
 
+def test_transform_of_modes_in_page_locked_memory():
+    """Modes that live in page-locked memory already (a numpy view of a pinned torch tensor): the library must neither try
+    to register them (cudaHostRegister fails with "invalid argument" there, and the pending error used to surface at the
+    next launch) nor release them; the result is the pageable-input result bit for bit, call after call."""
+    import torch
+
+    t, data = smooth_modes(n_times=30000, t0=0.0, t1=3000.0, seed=72)
+    ref = modes(t, data).transform(**BMS)
+    pinned = torch.empty(data.shape, dtype=torch.complex128, pin_memory=True)
+    view = pinned.numpy()
+    view[...] = data
+    w = modes(t, data)
+    w.data = view
+    for _ in range(3):                      # second sighting is where pageable arrays get registered
+        out = w.transform(**BMS)
+        assert np.array_equal(out.t, ref.t) and np.array_equal(out.data, ref.data)
+    lib = _lib.load()
+    assert lib.scrib200_host_register(view.ctypes.data, view.nbytes) == 1      # "page-locked already", nothing to undo
+    scratch = np.ones(1 << 20)
+    assert lib.scrib200_host_register(scratch.ctypes.data, scratch.nbytes) == 0
+    assert lib.scrib200_host_register(scratch.ctypes.data, scratch.nbytes) == 1
+    assert lib.scrib200_host_unregister(scratch.ctypes.data) == 0
+
+
 @pytest.mark.parametrize("bit_width", [8, 16, 32, 64])
 def test_codec_stages_bit_exact(bit_width):
     """scri/utilities.py:194-407 on the GPU (scri_b200.utilities) against the oracle, bit for bit: multishuffle and its inverse
