@@ -506,15 +506,36 @@ def run_ours(args):
     barrier()
     gc.collect()
     gc.disable()
-    e2e_times = []
-    for _ in range(max(3, min(args.steps, 10))):
-        t0 = time.perf_counter()
-        out = w.transform(**kw)
-        torch.cuda.synchronize()
-        e2e_times.append(time.perf_counter() - t0)
-    e2e_ms = 1e3 * float(np.mean(e2e_times))
+    def e2e_loop():
+        times = []
+        for _ in range(max(3, min(args.steps, 10))):
+            t0 = time.perf_counter()
+            o = w.transform(**kw)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        return times, o
+
+    # (a) the modes in an ordinary numpy array: the library page-locks it in place at its second sighting (warm-up above)
+    pageable_times, out = e2e_loop()
+    # (b) the modes in page-locked host memory from the start (the contract's "from pinned host memory"): the headline e2e
+    pageable_data = w.data
+    pinned_block = torch.empty(w.data.shape, dtype=torch.complex128, pin_memory=True)
+    pinned_view = pinned_block.numpy()
+    pinned_view[...] = w.data
+    w.data = pinned_view
     gc.enable()
-    sys.stderr.write(f"[rank {rank}] e2e per call (ms): " + " ".join(f"{1e3 * x:.2f}" for x in e2e_times) + "\n")
+    for _ in range(3):
+        out = w.transform(**kw)
+    barrier()
+    gc.collect()
+    gc.disable()
+    e2e_times, out = e2e_loop()
+    w.data = pageable_data
+    e2e_ms = 1e3 * float(np.mean(e2e_times))
+    e2e_pageable_ms = 1e3 * float(np.mean(pageable_times))
+    gc.enable()
+    sys.stderr.write(f"[rank {rank}] e2e per call (ms), pinned input: " + " ".join(f"{1e3 * x:.2f}" for x in e2e_times) + "\n")
+    sys.stderr.write(f"[rank {rank}] e2e per call (ms), numpy input (registered in place): " + " ".join(f"{1e3 * x:.2f}" for x in pageable_times) + "\n")
     h2d = w.t.nbytes + w.data.nbytes
     d2h = out.t.nbytes + out.data.nbytes
 
@@ -544,10 +565,10 @@ def run_ours(args):
     except Exception as exc:
         sys.stderr.write(f"[rank {rank}] copy-only floor not measured ({type(exc).__name__}: {exc})\n")
     barrier()
-    tms = torch.tensor([ms_step, e2e_ms, copy_ms if copy_ms is not None else 0.0], dtype=torch.float64, device="cuda")
+    tms = torch.tensor([ms_step, e2e_ms, copy_ms if copy_ms is not None else 0.0, e2e_pageable_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_step_max, e2e_ms_max = float(tms[0]), float(tms[1])
+    ms_step_max, e2e_ms_max, e2e_pageable_ms_max = float(tms[0]), float(tms[1]), float(tms[3])
     copy_ms_max = float(tms[2]) if copy_ms is not None else None
     units = float(n_modes) * N * world
     value = units / (ms_step_max * 1e-3)
@@ -633,6 +654,9 @@ def run_ours(args):
             "cpu_baseline": {"value": cval, "unit": UNIT, "cores": cpu_cores, "kind": "port",
                              "sample": f"first {args.cpu_sample} time steps of the same waveform through oracle/ (port of scri's algorithm, scipy FITPACK splines; reference packages not installable here), {csec:.1f} s; host has {os.cpu_count()} cores"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
+                    "input": "modes in page-locked host memory (numpy view of a pinned block); result in pinned memory from the library's pool",
+                    "numpy_input_ms_per_step": e2e_pageable_ms_max,
+                    "numpy_input_note": "the same call on an ordinary numpy array, which the library page-locks in place (cudaHostRegister) at its second sighting",
                     "copy_only_ms_per_step": copy_ms_max,
                     "copy_only_note": "the same H2D + D2H bytes as two bare DMAs (pinned memory, two streams, no kernels), all ranks at once, max over ranks: what the host link allows at this N"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,

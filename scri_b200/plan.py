@@ -710,6 +710,8 @@ class TransformPlan(GridPlan):
         cs.wait_stream(cur)
         with torch.cuda.stream(cs):
             u_host.copy_(uprm, non_blocking=True)
+            u_landed = torch.cuda.Event()
+            u_landed.record(cs)
         t_host = np.asarray(t_host, dtype=float)
         u_of_row = lambda i: (t_host[i] - self.time_translation) / self.gamma   # output time of input row i, to rounding (bounds only)
         halo, body = prep.halo_body(self.spline_halo, self.spline_body)
@@ -758,14 +760,18 @@ class TransformPlan(GridPlan):
                         timing.append((f"outputs {done}:{out_hi} landed on the host", landed))
                 done = out_hi
         _trace("all launches queued")
+        u_np, host_np = u_host.numpy(), host.numpy()         # the very objects handed to on_queued are the ones returned
         if on_queued is not None:
-            on_queued()                              # host work of the caller that can run under the pipeline
+            # host work of the caller that can run under the pipeline: it is handed the result arrays - u' has landed, the
+            # modes are still arriving - so that it can wrap them (checks on the time axis included) before the last byte
+            u_landed.synchronize()
+            on_queued(u_np, host_np)
         ok = prep.verify()
         cs.synchronize()
         _trace("last result slab landed")
         if not ok:                                   # the axis changed behind the same identity: once more, nothing assumed
             return self._run_streaming(t, data, slabs, t_host, debug_poison=debug_poison, _speculate=False)
-        return u_host.numpy(), host.numpy()
+        return u_np, host_np
 
     def run(self, t, data, return_grid=False, t_ends=None, prep=None, slabs=None, host_slabs=0, t_host=None, on_queued=None):
         """Whole path on device tensors: returns (u', modes') or (u', grid' [time-major]).
