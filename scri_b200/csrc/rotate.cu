@@ -13,6 +13,9 @@
 // HBM-bound by design: 2*16*n_modes + 32 bytes per time step.
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace scrib200 {
@@ -259,40 +262,62 @@ rotate_modes_reg_kernel(double2* __restrict__ data, int64_t n_times, int ell_min
     }
 }
 
-// ---- third-generation kernel (ell_max <= 16): lanes run along TIME, a warp owns one |m| (and the opposite end L - |m|
-// of the range, for balance).  Everything that steers the m' and l loops - the start l0 = max(m', |m|), the recurrence
+// ---- time-lane kernel (ell_max <= 16): lanes run along TIME, a warp owns one |m| (and the opposite end hi - |m| of the
+// range, for balance).  Everything that steers the m' and l loops - the start l0 = max(m', |m|), the recurrence
 // coefficients, the seeds - is then uniform across the warp (read from constant memory, no predication, every lane
 // busy), and each thread serves FOUR matrix elements per recurrence step through the symmetries
 //     P(-m', -m) = (-1)^{m'+m} P(m', m),      P(m', -m) = (-1)^{m'+m} P(-m', m):
 // the chains P = P(m', m) and N = P(-m', m) give   out[+m] += P b[+m'] + N b[-m'],   out[-m] += (-1)^{m'+m} (N b[+m'] + P b[-m']).
 // The tile of 32 time steps is staged through shared memory transposed ([mode][time], pitch 33) and premultiplied by
-// e^{i m'(A-B)}; the accumulators of up to 9 values of l live in registers (ell_max > 8 takes two passes over l, the
-// recurrence restarted), the result is multiplied by e^{i m(A+B)} and stored.  A time step whose Rb is exactly zero is
-// finished by an exact diagonal pass so that the identity rotation stays bit-exact.
+// e^{i m'(A-B)}; the accumulators of one block of l live in registers (ell_max > 8 takes three launches over blocks of l,
+// the recurrence restarted), the result is multiplied by e^{i m(A+B)} and stored.  A time step whose Rb is exactly zero
+// is finished by an exact diagonal pass so that the identity rotation stays bit-exact.
+//
+// What one rung of the ladder (one l, four matrix elements) costs decides the kernel - the tensor cores have no part in a
+// product whose matrix changes with every time step - so the rung is written down to the instruction:
+//   * the l -> l+1 coefficients (a, b, c) of (m', m) come ready-made from a compact constant table (1496 triples, all
+//     l <= 16): x = a cos(beta) -+ b, P' = x P - c P'' is 6 FP64 instructions for the two chains;
+//   * the sign (-1)^{m'} is a compile-time property of the ladder (the m' loop is unrolled by two), (-1)^m is applied once at
+//     the end: the four accumulations are 8 FMAs with no multiplication by a sign;
+//   * the two shared-memory operands are read at [register + immediate] (inline PTX: left to itself the compiler
+//     recomputed both addresses on every rung to save two registers);
+//   * in the EXACT instantiations (the block of l is covered completely: ell_min <= LA, ell_max >= LB) no rung tests anything.
 __constant__ double c_rot_seed[33 * 33];      // [m' + 16][m + 16]
-__constant__ double2 c_rot_uv[17 * 33];       // [l][m + 16]
+__constant__ double c_rot_rec[1496 * 3];      // (a, b, c) of the step l -> l+1 for 0 <= m, m' <= 16, l = max(m, m') .. 15
+__constant__ int c_rot_off[17 * 17];          // [m][m']: index of the (m, m', l = max(m, m')) triple
 
 constexpr int ROT3_TB = 32;
 constexpr int ROT3_PITCH = ROT3_TB + 1;
 
-// constant tables at a fixed pitch: seed[(m' + 16) * 33 + m + 16], uv[l * 33 + m + 16] - with l a compile-time constant in
-// the unrolled ladder every index is an immediate plus one register
+// seed table at a fixed pitch: seed[(m' + 16) * 33 + m + 16] - the kernel's table indices do not depend on ell_max
 constexpr int ROT3_C = 16, ROT3_NM = 33;
 
-template <int LA, int LB>
-__device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const double* __restrict__ s_ra, const double* __restrict__ s_rb,
-                                          const double2* __restrict__ s_pw, double cosb, bool diagonal, int tt, int m, int L, int ell_min,
-                                          double2* __restrict__ orow) {
+__device__ __forceinline__ double2 rot_lds_reg(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int OFF>
+__device__ __forceinline__ double2 rot_lds_imm(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+template <int LA, int LB, bool EXACT>
+__device__ __forceinline__ void rot4_pass(unsigned sb_addr, const double2* __restrict__ s_b, const double* __restrict__ s_ra,
+                                          const double* __restrict__ s_rb, const double2* __restrict__ s_pw, double cosb, bool diagonal,
+                                          int tt, int m, int L, int ell_min, double2* __restrict__ orow) {
     constexpr int NA = LB - LA + 1;
-    const int lo = LA > ell_min ? LA : ell_min;             // the tile holds l = lo .. min(LB, L)
+    const int lo = EXACT ? LA : (LA > ell_min ? LA : ell_min);          // the tile holds l = lo .. min(LB, L)
     const int lmin2 = lo * lo, omin2 = ell_min * ell_min;
-    double pr[NA], pi[NA], nr[NA], ni[NA];                  // out[+m] and out[-m] for l = LA .. LB
+    double pr[NA], pi[NA], nr[NA], ni[NA];                  // out[+m] and (-1)^m out[-m] for l = LA .. LB
 #pragma unroll
     for (int i = 0; i < NA; ++i) pr[i] = pi[i] = nr[i] = ni[i] = 0.0;
-    const int lend = LB < L ? LB : L;
-    const double2* uvm = c_rot_uv + ROT3_C + m;             // + l * 33
+    const int lend = EXACT ? LB : (LB < L ? LB : L);
     // seeds P^{l0}(+-m', m) ra^.. rb^.. of the NEXT m' are formed while the ladder of the current one runs (their shared-
-    // memory and constant loads would otherwise sit in front of every ladder with only two warps per scheduler to hide them)
+    // memory and constant loads would otherwise sit in front of every ladder with only a few warps per scheduler to hide them)
     auto seeds = [&](int mp, double& P, double& N) {
         const int ka = mp + m, kb = mp > m ? mp - m : m - mp;            // exponents of ra, rb for (m', m); swapped for (-m', m)
         const double ra_a = s_ra[ka * ROT3_TB + tt], rb_b = s_rb[kb * ROT3_TB + tt];
@@ -302,48 +327,101 @@ __device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const
     };
     double Pn, Nn;
     seeds(0, Pn, Nn);
-    for (int mp = 0; mp <= L; ++mp) {
-        const int l0 = mp > m ? mp : m;
-        if (l0 > lend) break;                                // l0 grows with m'
-        double P = Pn, N = Nn;
-        if (mp < L) seeds(mp + 1, Pn, Nn);
-        double P1 = 0.0, N1 = 0.0;
-        const double sg = ((mp + m) & 1) ? -1.0 : 1.0;
-        const double mmp = (double)(m * mp);
-        const double2* bpp = s_b + (mp - lmin2) * ROT3_PITCH + tt;      // + l (l + 1) * 33: row of (l, +m')
-        const double2* bnp = s_b + (-mp - lmin2) * ROT3_PITCH + tt;     //                   row of (l, -m')
-        const double2* uvp = c_rot_uv + ROT3_C + mp;                    // + l * 33
-        // the unrolled ladder over l is entered at l0 (uniform across the warp): no test per skipped rung
-#define ROT3_STEP(l_)                                                                                          \
+    // one ladder: m' = mp_, ODD says whether m' is odd (the sign of the out[-m] accumulation)
+#define ROT4_OFF(l_) (((l_) * ((l_) + 1) - LB * (LB + 1)) * ROT3_PITCH * 16)
+    // Software pipeline: a rung works on operands that are in registers already (set l & 1) and first issues the loads of
+    // the next rung into the other set - every rung is a switch label, i.e. a basic block of its own, and left to itself
+    // each block would start by waiting for its own shared-memory and constant loads (measured: 6 warps stalled on the
+    // short scoreboard per instruction issued).  The entry rung's operands are loaded before the switch, into both sets.
+#define ROT4_RUNG(l_, ODD)                                                                                     \
     case l_:                                                                                                   \
-        if (l_ <= LB && l_ <= lend) {                                                                          \
-            if (l_ >= LA && l_ >= ell_min) {                                                                   \
-                const double2 bp = bpp[l_ * (l_ + 1) * ROT3_PITCH], bn = bnp[l_ * (l_ + 1) * ROT3_PITCH];      \
+        if (l_ <= LB && (EXACT || l_ <= lend)) {                                                               \
+            constexpr int cur = (l_) & 1, nxt = cur ^ 1;                                                       \
+            if (l_ + 1 <= LB && (EXACT || l_ + 1 <= lend)) {                                                   \
+                if (l_ + 1 >= LA && (EXACT || l_ + 1 >= ell_min)) {                                            \
+                    bpv[nxt] = rot_lds_imm<ROT4_OFF(l_ + 1)>(bp_addr);                                         \
+                    bnv[nxt] = rot_lds_imm<ROT4_OFF(l_ + 1)>(bn_addr);                                         \
+                }                                                                                              \
+                if (l_ + 1 < LB && (EXACT || l_ + 1 < lend)) {                                                 \
+                    cav[nxt] = recp[(l_ + 1) * 3];                                                             \
+                    cbv[nxt] = recp[(l_ + 1) * 3 + 1];                                                         \
+                    ccv[nxt] = recp[(l_ + 1) * 3 + 2];                                                         \
+                }                                                                                              \
+            }                                                                                                  \
+            if (l_ >= LA && (EXACT || l_ >= ell_min)) {                                                        \
+                const double2 bp = bpv[cur], bn = bnv[cur];                                                    \
                 constexpr int ia = (l_ >= LA) ? l_ - LA : 0;                                                   \
                 pr[ia] = fma(P, bp.x, fma(N, bn.x, pr[ia]));                                                   \
                 pi[ia] = fma(P, bp.y, fma(N, bn.y, pi[ia]));                                                   \
-                nr[ia] = fma(sg, fma(N, bp.x, P * bn.x), nr[ia]);                                              \
-                ni[ia] = fma(sg, fma(N, bp.y, P * bn.y), ni[ia]);                                              \
+                if (ODD) {                                                                                     \
+                    nr[ia] = fma(-N, bp.x, fma(-P, bn.x, nr[ia]));                                             \
+                    ni[ia] = fma(-N, bp.y, fma(-P, bn.y, ni[ia]));                                             \
+                } else {                                                                                       \
+                    nr[ia] = fma(N, bp.x, fma(P, bn.x, nr[ia]));                                               \
+                    ni[ia] = fma(N, bp.y, fma(P, bn.y, ni[ia]));                                               \
+                }                                                                                              \
             }                                                                                                  \
-            if (l_ < LB && l_ < lend) {                                                                        \
-                const double2 f1 = uvp[l_ * ROT3_NM], f2 = uvm[l_ * ROT3_NM];                                  \
-                constexpr double rl = (l_ > 0) ? 1.0 / (double)(l_ * (l_ + 1)) : 0.0;                          \
-                const double a_ = f1.x * f2.x, c_ = f1.y * f2.y, tb = mmp * rl;                                \
-                const double Pq = a_ * (cosb - tb) * P - c_ * P1;                                              \
-                const double Nq = a_ * (cosb + tb) * N - c_ * N1;                                              \
+            if (l_ < LB && (EXACT || l_ < lend)) {                                                             \
+                const double ca = cav[cur], cb = cbv[cur], cc = ccv[cur];                                      \
+                const double Pq = fma(fma(ca, cosb, -cb), P, -(cc * P1));                                      \
+                const double Nq = fma(fma(ca, cosb, cb), N, -(cc * N1));                                       \
                 P1 = P;                                                                                        \
                 N1 = N;                                                                                        \
                 P = Pq;                                                                                        \
                 N = Nq;                                                                                        \
             }                                                                                                  \
         }
-        switch (l0) {
-            ROT3_STEP(0) ROT3_STEP(1) ROT3_STEP(2) ROT3_STEP(3) ROT3_STEP(4) ROT3_STEP(5) ROT3_STEP(6) ROT3_STEP(7) ROT3_STEP(8)
-            ROT3_STEP(9) ROT3_STEP(10) ROT3_STEP(11) ROT3_STEP(12) ROT3_STEP(13) ROT3_STEP(14) ROT3_STEP(15) ROT3_STEP(16)
-            default: break;
-        }
-#undef ROT3_STEP
+#define ROT4_LADDER(mp_, ODD)                                                                                  \
+    {                                                                                                          \
+        const int l0 = (mp_) > m ? (mp_) : m;                                                                  \
+        double P = Pn, N = Nn;                                                                                 \
+        if ((mp_) < lend) seeds((mp_) + 1, Pn, Nn);                                                            \
+        double P1 = 0.0, N1 = 0.0;                                                                             \
+        /* rows of (LB, +m') and (LB, -m') as shared-memory byte addresses held in registers (the rungs read at */ \
+        /* negative immediates from there: a base at l = 0 would lie below the tile)                           */ \
+        unsigned bp_addr = sb_addr + (unsigned)(((LB * (LB + 1) - lmin2 + (mp_)) * ROT3_PITCH + tt) * 16);     \
+        unsigned bn_addr = sb_addr + (unsigned)(((LB * (LB + 1) - lmin2 - (mp_)) * ROT3_PITCH + tt) * 16);     \
+        asm volatile("" : "+r"(bp_addr), "+r"(bn_addr));                                                       \
+        int rec_i = 3 * (c_rot_off[m * 17 + (mp_)] - l0);                          /* + 3 l */                 \
+        asm volatile("" : "+r"(rec_i));                                                                        \
+        const double* recp = c_rot_rec + rec_i;                                                                \
+        double2 bpv[2], bnv[2];                                                                                \
+        double cav[2], cbv[2], ccv[2];                                                                         \
+        {   /* operands of the entry rung */                                                                   \
+            const int o0 = (l0 * (l0 + 1) - LB * (LB + 1)) * ROT3_PITCH * 16;                                  \
+            bpv[0] = bnv[0] = make_double2(0.0, 0.0);                                                          \
+            if (l0 >= lo) {                                                                                    \
+                bpv[0] = rot_lds_reg(bp_addr + (unsigned)o0);                                                  \
+                bnv[0] = rot_lds_reg(bn_addr + (unsigned)o0);                                                  \
+            }                                                                                                  \
+            cav[0] = cbv[0] = ccv[0] = 0.0;                                                                    \
+            if (l0 < lend) {                                                                                   \
+                cav[0] = recp[l0 * 3];                                                                         \
+                cbv[0] = recp[l0 * 3 + 1];                                                                     \
+                ccv[0] = recp[l0 * 3 + 2];                                                                     \
+            }                                                                                                  \
+            bpv[1] = bpv[0];                                                                                   \
+            bnv[1] = bnv[0];                                                                                   \
+            cav[1] = cav[0];                                                                                   \
+            cbv[1] = cbv[0];                                                                                   \
+            ccv[1] = ccv[0];                                                                                   \
+        }                                                                                                      \
+        /* the unrolled ladder over l is entered at l0 (uniform across the warp): no test per skipped rung */  \
+        switch (l0) {                                                                                          \
+            ROT4_RUNG(0, ODD) ROT4_RUNG(1, ODD) ROT4_RUNG(2, ODD) ROT4_RUNG(3, ODD) ROT4_RUNG(4, ODD) ROT4_RUNG(5, ODD)       \
+            ROT4_RUNG(6, ODD) ROT4_RUNG(7, ODD) ROT4_RUNG(8, ODD) ROT4_RUNG(9, ODD) ROT4_RUNG(10, ODD) ROT4_RUNG(11, ODD)     \
+            ROT4_RUNG(12, ODD) ROT4_RUNG(13, ODD) ROT4_RUNG(14, ODD) ROT4_RUNG(15, ODD) ROT4_RUNG(16, ODD)                    \
+            default: break;                                                                                    \
+        }                                                                                                      \
     }
+    for (int mp = 0; mp <= lend; mp += 2) {                  // l0 = max(m', m) > lend ends the loop: l0 grows with m'
+        ROT4_LADDER(mp, false)
+        if (mp + 1 <= lend) ROT4_LADDER(mp + 1, true)
+    }
+#undef ROT4_LADDER
+#undef ROT4_RUNG
+#undef ROT4_OFF
+    const double sgm = (m & 1) ? -1.0 : 1.0;                // the (-1)^m left out of the out[-m] sums
     if (diagonal) {   // Rb == 0 exactly: D^l_{m'm} = delta_{m'm} ra^{2|m|} (phases applied outside)
         const double mag = s_ra[2 * m * ROT3_TB + tt];
 #pragma unroll
@@ -353,25 +431,26 @@ __device__ __forceinline__ void rot3_pass(const double2* __restrict__ s_b, const
                 const double2 bn = s_b[(l * (l + 1) - lmin2 - m) * ROT3_PITCH + tt];
                 pr[l - LA] = mag * bp.x;
                 pi[l - LA] = mag * bp.y;
-                nr[l - LA] = mag * bn.x;
-                ni[l - LA] = mag * bn.y;
+                nr[l - LA] = sgm * mag * bn.x;
+                ni[l - LA] = sgm * mag * bn.y;
             }
     }
     const double2 pw = s_pw[m * ROT3_TB + tt];
+    const double2 pwn = cscale(sgm, cconj(pw));
 #pragma unroll
     for (int l = LA; l <= LB; ++l)
         if (l >= m && l >= ell_min && l <= L) {
             orow[l * (l + 1) - omin2 + m] = cmul(make_double2(pr[l - LA], pi[l - LA]), pw);
-            if (m > 0) orow[l * (l + 1) - omin2 - m] = cmul(make_double2(nr[l - LA], ni[l - LA]), cconj(pw));
+            if (m > 0) orow[l * (l + 1) - omin2 - m] = cmul(make_double2(nr[l - LA], ni[l - LA]), pwn);
         }
 }
 
-template <int LA, int LB>
+template <int LA, int LB, bool EXACT>
 __global__ void __launch_bounds__(32 * (LB / 2 + 1))
 rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_min, int ell_max,
                          const double2* __restrict__ spinors, int64_t spinor_stride) {
     extern __shared__ double2 sm3[];
-    const int L = ell_max, nm = 2 * L + 1;
+    const int L = ell_max;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
     const int lo = LA > ell_min ? LA : ell_min, hi = LB < L ? LB : L;   // this launch rotates l = lo .. hi
     const int n_blk = (hi + 1) * (hi + 1) - lo * lo, col0 = lo * lo - ell_min * ell_min;
@@ -383,7 +462,6 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     double* s_cos = s_rb + (size_t)(2 * hi + 1) * ROT3_TB;  // [32]  cos(beta), or 2 if Rb == 0 exactly
     const int64_t t0 = (int64_t)blockIdx.x * ROT3_TB;
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    (void)nm;
     if (tid < ROT3_TB) {
         const int tt = tid;
         int64_t t = t0 + tt;
@@ -413,21 +491,25 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
         s_cos[tt] = (rb2 == 0.0) ? 2.0 : (ra2 - rb2) / n2;
     }
     __syncthreads();
-    // stage the l-block of the tile transposed, premultiplied by e^{i m'(A-B)}: lanes along the modes for the global read
-    for (int idx = tid; idx < ROT3_TB * n_blk; idx += nthreads) {
-        const int tt = idx / n_blk, lm = idx - tt * n_blk;
-        const int64_t t = t0 + tt;
-        double2 v = make_double2(0.0, 0.0);
-        if (t < n_times) {
-            const int full = lm + lo * lo;
-            int l = (int)sqrt((double)full);
-            while (l * l > full) --l;
-            while ((l + 1) * (l + 1) <= full) ++l;
-            const int mp = full - l * (l + 1);
-            const double2 ph = s_pu[(mp < 0 ? -mp : mp) * ROT3_TB + tt];
-            v = cmul(data[t * n_modes + col0 + lm], mp < 0 ? cconj(ph) : ph);
+    // stage the l-block of the tile transposed, premultiplied by e^{i m'(A-B)}: a thread keeps its mode (lanes along the
+    // modes: coalesced rows of the global read) and walks the 32 time steps - the (l, m') of the mode is decoded once
+    const int nt = (n_times - t0 < ROT3_TB) ? (int)(n_times - t0) : ROT3_TB;
+    for (int lm = tid; lm < n_blk; lm += nthreads) {
+        const int full = lm + lo * lo;
+        int l = (int)sqrt((double)full);
+        while (l * l > full) --l;
+        while ((l + 1) * (l + 1) <= full) ++l;
+        const int mp = full - l * (l + 1);
+        const double2* ph = s_pu + (mp < 0 ? -mp : mp) * ROT3_TB;
+        const double sg = mp < 0 ? -1.0 : 1.0;
+        const double2* src = data + t0 * n_modes + col0 + lm;
+        double2* dst = s_b + lm * ROT3_PITCH;
+#pragma unroll 4
+        for (int tt = 0; tt < nt; ++tt) {
+            const double2 p = ph[tt];
+            dst[tt] = cmul(src[(size_t)tt * n_modes], make_double2(p.x, sg * p.y));
         }
-        s_b[lm * ROT3_PITCH + tt] = v;
+        for (int tt = nt; tt < ROT3_TB; ++tt) dst[tt] = make_double2(0.0, 0.0);
     }
     __syncthreads();
     const int tt = tid & 31, w = tid >> 5;
@@ -435,11 +517,12 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     const double cosb = s_cos[tt];
     const bool diagonal = cosb > 1.5;
     double2* orow = data + (t0 + tt) * n_modes;
+    const unsigned sb_addr = (unsigned)__cvta_generic_to_shared(s_b);
     // warp w owns m = w and m = hi - w (one of them when they coincide)
     for (int which = 0; which < 2; ++which) {
         const int m = which == 0 ? w : hi - w;
         if (m > hi || m < 0 || (which == 1 && m <= w)) continue;
-        rot3_pass<LA, LB>(s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
+        rot4_pass<LA, LB, EXACT>(sb_addr, s_b, s_ra, s_rb, s_pw, cosb, diagonal, tt, m, L, ell_min, orow);
     }
 }
 
@@ -452,6 +535,43 @@ static size_t rotate_reg_smem(int TB, int L, int n_modes) {
     const size_t nm = 2 * L + 1;
     return ((size_t)TB * n_modes + (size_t)(L > 0 ? L : 1) * nm + 2 * (size_t)TB * (L + 1)) * sizeof(double2) +
            (2 * (size_t)TB * nm + TB + (TB & 1)) * sizeof(double);
+}
+
+// (a, b, c) of the step l -> l+1, P^{l+1}(m', m) = (a cos(beta) - b) P^l - c P^{l-1}  [+ b for (-m', m)], with
+// a = U_l(m') U_l(m), c = V_l(m') V_l(m), b = a m' m / (l (l + 1)) - the factors of scri_b200/_sf.py:wigner_factor_table,
+// multiplied out here so that a rung reads three numbers instead of forming them.  Compact: for every 0 <= m, m' <= 16
+// the l = max(m, m') .. 15 are contiguous; c_rot_off[m][m'] is where they start.  Built once, uploaded once per device.
+static int upload_rotation_recurrence(cudaStream_t st) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return SCRIB200_OK;
+    std::vector<double> rec;
+    std::vector<int> off(17 * 17, 0);
+    auto U = [](int l, int m) { return sqrt((double)((2 * l + 1) * (l + 1)) / (double)((l + 1) * (l + 1) - m * m)); };
+    auto V = [](int l, int m) {
+        return l > 0 ? sqrt((double)((l + 1) * (l * l - m * m)) / (double)(l * ((l + 1) * (l + 1) - m * m))) : 0.0;
+    };
+    for (int m = 0; m <= 16; ++m)
+        for (int mp = 0; mp <= 16; ++mp) {
+            off[m * 17 + mp] = (int)(rec.size() / 3);
+            for (int l = (m > mp ? m : mp); l < 16; ++l) {
+                const double a = U(l, mp) * U(l, m);
+                const double tb = l > 0 ? (double)(m * mp) * (1.0 / (double)(l * (l + 1))) : 0.0;
+                rec.push_back(a);
+                rec.push_back(a * tb);
+                rec.push_back(V(l, mp) * V(l, m));
+            }
+        }
+    SCRIB200_REQUIRE(rec.size() == 1496 * 3, "rotate_modes: recurrence table has %zu entries", rec.size());
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_rot_rec, rec.data(), rec.size() * sizeof(double), 0, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_rot_off, off.data(), off.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the host vectors go out of scope
+    SCRIB200_REQUIRE(e == cudaSuccess, "rotate_modes: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return SCRIB200_OK;
 }
 
 }  // namespace scrib200
@@ -468,36 +588,40 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
     const int L = ell_max, nm = 2 * L + 1;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
     if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr && getenv("SCRIB200_ROTATE_V2") == nullptr) {
-        SCRIB200_REQUIRE(aligned16(uv), "rotate_modes: uv must be 16-byte aligned");
         cudaStream_t st = (cudaStream_t)stream;
-        // the two small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic),
-        // re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max
-        void *p_seed = nullptr, *p_uv = nullptr;
+        // the small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic).  The seeds are
+        // re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max; the
+        // recurrence triples are the same for every ell_max <= 16 and go up once per device
+        int rc = upload_rotation_recurrence(st);
+        if (rc != SCRIB200_OK) return rc;
+        void* p_seed = nullptr;
         cudaError_t e = cudaGetSymbolAddress(&p_seed, c_rot_seed);
-        if (e == cudaSuccess) e = cudaGetSymbolAddress(&p_uv, c_rot_uv);
         if (e == cudaSuccess)
             e = cudaMemcpy2DAsync(reinterpret_cast<double*>(p_seed) + (16 - L) * 33 + (16 - L), 33 * sizeof(double), seed, nm * sizeof(double),
                                   nm * sizeof(double), nm, cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess && L > 0)
-            e = cudaMemcpy2DAsync(reinterpret_cast<double2*>(p_uv) + (16 - L), 33 * sizeof(double2), uv, nm * sizeof(double2),
-                                  nm * sizeof(double2), L, cudaMemcpyDeviceToDevice, st);
         SCRIB200_REQUIRE(e == cudaSuccess, "rotate_modes: %s", cudaGetErrorString(e));
         const int64_t blocks = (n_times + ROT3_TB - 1) / ROT3_TB;
         // one launch per block of l (0..8, 9..12, 13..16): each stages only its own modes (39 / 47 / 63 KB of shared memory
-        // instead of 150 KB: 5, 3 and 2 CTAs per SM), reads and writes its own columns of `data`, restarts the recurrences at l0
-#define ROT3_LAUNCH(LA_, LB_)                                                                                                     \
-    if (ell_min <= LB_ && L >= LA_) {                                                                                             \
-        const int lo = ell_min > LA_ ? ell_min : LA_, hi = L < LB_ ? L : LB_;                                                     \
-        const size_t smem = rotate_time_smem(lo, hi);                                                                             \
-        cudaFuncSetAttribute(rotate_modes_time_kernel<LA_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        rotate_modes_time_kernel<LA_, LB_><<<(unsigned)blocks, 32 * (hi / 2 + 1), smem, st>>>(                                    \
+        // instead of 150 KB: 5, 3 and 2 CTAs per SM), reads and writes its own columns of `data`, restarts the recurrences at
+        // l0.  A block that is covered completely takes the instantiation without per-rung tests (LA = its first l).
+#define ROT4_LAUNCH(LA_, LB_, EX_, lo_, hi_)                                                                                      \
+    {                                                                                                                             \
+        const size_t smem = rotate_time_smem(lo_, hi_);                                                                           \
+        cudaFuncSetAttribute(rotate_modes_time_kernel<LA_, LB_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        rotate_modes_time_kernel<LA_, LB_, EX_><<<(unsigned)blocks, 32 * ((hi_) / 2 + 1), smem, st>>>(                            \
             reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride); \
         SCRIB200_CHECK_LAUNCH("rotate_modes");                                                                                    \
     }
-        ROT3_LAUNCH(0, 8)
-        ROT3_LAUNCH(9, 12)
-        ROT3_LAUNCH(13, 16)
-#undef ROT3_LAUNCH
+#define ROT4_BLOCK(LA_, LB_)                                                                                                      \
+    if (ell_min <= LB_ && L >= LA_) {                                                                                             \
+        const int lo = ell_min > LA_ ? ell_min : LA_, hi = L < LB_ ? L : LB_;                                                     \
+        ROT4_LAUNCH(LA_, LB_, false, lo, hi)                                                                                      \
+    }
+        if (ell_min == 2 && L >= 8) ROT4_LAUNCH(2, 8, true, 2, 8) else ROT4_BLOCK(0, 8)
+        if (ell_min <= 9 && L >= 12) ROT4_LAUNCH(9, 12, true, 9, 12) else ROT4_BLOCK(9, 12)
+        if (ell_min <= 13 && L >= 16) ROT4_LAUNCH(13, 16, true, 13, 16) else ROT4_BLOCK(13, 16)
+#undef ROT4_BLOCK
+#undef ROT4_LAUNCH
         return SCRIB200_OK;
     }
     if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr) {

@@ -77,6 +77,23 @@ def test_rotation_poles_and_large_ell():
     assert rel(d, Wo.data) < 1e-12
 
 
+@pytest.mark.parametrize("ell_min,ell_max", [(2, 8), (2, 16), (0, 16), (0, 8), (3, 11), (10, 14), (2, 5), (13, 16), (9, 12), (2, 12), (1, 1), (0, 0)])
+def test_rotation_every_block_instantiation(ell_min, ell_max):
+    """rotate.cu launches one kernel per block of l (0..8, 9..12, 13..16), in an instantiation without per-rung tests when
+    the block is covered completely and a general one otherwise: every combination against the oracle, on a series that
+    does not fill its last tile of 32 steps and contains an exact identity and an exact pole."""
+    n = 77
+    t, data = smooth_modes(n_times=n, ell_min=ell_min, ell_max=ell_max, seed=31 + ell_min + 17 * ell_max)
+    Rs = quat.normalized(np.random.default_rng(ell_max).normal(size=(n, 4)))
+    Rs[5] = [1.0, 0.0, 0.0, 0.0]
+    Rs[40] = [0.0, 1.0, 0.0, 0.0]
+    d = data.copy()
+    ops.rotate_modes(d, Rs, ell_min, ell_max)
+    Wo = R.rotate_decomposition_basis(R.Modes(t=t, data=data.copy(), ell_min=ell_min, ell_max=ell_max), Rs)
+    assert rel(d, Wo.data) < 1e-12
+    assert np.array_equal(d[5], data[5])
+
+
 def test_rotation_full_size_round_trip():
     """1e5 steps (config sizes): R(t) then ~R(t) restores the modes; norm invariant."""
     N = 100_000
