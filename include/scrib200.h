@@ -51,6 +51,17 @@ int64_t scrib200_launch_count(void);
 int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
                           int64_t spinor_stride, const double* seed, const double* rec, const double* uv, void* stream);
 
+/* The same rotation on the FP64 tensor cores (ell_max <= 16): D^l(R) = phases * Delta^l * phases(beta) * Delta^l^T * phases
+ * with the constant real matrices Delta^l = d^l(pi/2), so that the 16 time steps of a tile and one l are two small DMMA
+ * products and three diagonal multiplications (scri_b200/csrc/rotate.cu).  Replaces the same reference loop as
+ * scrib200_rotate_modes (scri/rotations.py:346-392, one sf.Wigner_D_matrices call per time step there).
+ *   frags: DEVICE table of m8n8k4 A fragments from scri_b200/ops.py:wigner_delta_fragments - for every l = 0 .. ell_max the
+ *          tiles [Kt][Mt][32] of Delta^l^T followed by those of Delta^l (Mt = ceil((2l+1)/8), Kt = ceil((2l+1)/4), zero padded);
+ *   frag_offsets_host: HOST int[ell_max + 1], start of l's tiles in `frags` (in doubles).
+ * A time step whose rotor is a pure z rotation (Rb == 0 exactly) is finished by its diagonal: the identity is bit-exact. */
+int scrib200_rotate_modes_dmma(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
+                               int64_t spinor_stride, const double* frags, const int* frag_offsets_host, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * SWSH synthesis with the BMS epilogue.
  * Replaces  scri/waveform_grid.py:475-484 (np.tensordot of the modes with sf.SWSH_grid), the constant

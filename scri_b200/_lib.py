@@ -42,6 +42,7 @@ SIGNATURES = {
     "scrib200_host_register": (c_int, [c_vp, c_sz]),
     "scrib200_host_unregister": (c_int, [c_vp]),
     "scrib200_rotate_modes": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "scrib200_rotate_modes_dmma": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "scrib200_swsh_synthesize": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "scrib200_swsh_pack3m": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
     "scrib200_swsh_synthesize_3m": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),

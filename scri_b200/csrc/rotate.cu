@@ -526,6 +526,247 @@ rotate_modes_time_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     }
 }
 
+// ---- tensor-core kernel (ell_max <= 16).  The matrix of a rotation changes with every time step, so applying it is not a
+// GEMM - but it factors into constant matrices and diagonal phases.  With Ra = ra e^{iA}, Rb = rb e^{iB},
+// cos(beta) = ra^2 - rb^2, sin(beta) = 2 ra rb and Delta^l = d^l(pi/2) (real, orthogonal, the same for every time step)
+//     D^l_{m'm}(R) = e^{i m'(A-B)} i^{-m'} [ sum_mu Delta_{m' mu} e^{-i mu beta} Delta_{m mu} ] i^{m} e^{i m(A+B)},
+// i.e. for the 16 time steps of a tile and one l:   x = a (-i e^{i(A-B)})^{m'}   (diagonal),   y = Delta^T x   (DMMA),
+// z = y e^{-i mu beta}   (diagonal),   o = Delta z   (DMMA),   a' = o (i e^{i(A+B)})^m   (diagonal).
+// 8 (2l+1)^2 flops per mode-vector instead of a recurrence per matrix element, on the FP64 tensor cores, and nothing
+// depends on beta being away from the poles.  One CTA owns 16 time steps; its warps take the values of l from a queue
+// (largest first), each staging its [16 x (2l+1)] slab in its own shared-memory tile (time-major, pitch 88 doubles: the
+// B fragments of m8n8k4 - lane (k, n) reads mode 4kk + k of step n/2, re or im - touch 32 distinct 8-byte words).  The
+// complex pair of one (mode, step) lands in one thread's accumulator pair, so the diagonal steps are register work.
+// A time step whose Rb is exactly zero is finished at load time by its (exact) diagonal so that the identity rotation stays
+// bit-exact: every factor is then a power of +-i or 1.
+constexpr int RG_T = 16;          // time steps per work item (one warp, one l): 4 n-tiles of 8 real columns
+constexpr int RG_NT = 4;
+constexpr int RG_WARPS = 8;
+struct RotGemmOffsets {
+    int off[17];                  // start (in doubles) of the A fragments of l: Delta^T tiles [Kt][Mt][32], then Delta tiles
+};
+
+__device__ __forceinline__ void rot_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int rot_phase_pitch(int L) { return ((L + 1 + 5) & ~7) + 2; }   // >= L + 1, = 2 (mod 8)
+
+// One product of the pair: acc[mm][nn] = sum_kk A(mm, kk) B(kk, nn) for the MA m-tiles this l needs (compile time: no
+// predicated-off DMMAs, no per-step tests).  A fragments [kk][mm][lane] from the packed table, fetched one k-step ahead
+// (they come from L2 more often than not); B fragments from the tile at [register + immediate].
+template <int MT, int MA, int PITCH>
+__device__ __forceinline__ void rot_gemm_pass(double (&acc)[MT][RG_NT][2], const double* __restrict__ af, const double* __restrict__ bp, int Kt) {
+#pragma unroll
+    for (int mm = 0; mm < MA; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < RG_NT; ++nn) acc[mm][nn][0] = acc[mm][nn][1] = 0.0;
+    double a_nxt[MA];
+#pragma unroll
+    for (int mm = 0; mm < MA; ++mm) a_nxt[mm] = __ldg(af + mm * 32);
+    for (int kk = 0; kk < Kt; ++kk) {
+        double a_cur[MA], b[RG_NT];
+#pragma unroll
+        for (int mm = 0; mm < MA; ++mm) a_cur[mm] = a_nxt[mm];
+        af += MA * 32;
+        if (kk + 1 < Kt) {
+#pragma unroll
+            for (int mm = 0; mm < MA; ++mm) a_nxt[mm] = __ldg(af + mm * 32);
+        }
+#pragma unroll
+        for (int nn = 0; nn < RG_NT; ++nn) b[nn] = bp[4 * nn * PITCH];
+        bp += 8;
+#pragma unroll
+        for (int mm = 0; mm < MA; ++mm)
+#pragma unroll
+            for (int nn = 0; nn < RG_NT; ++nn) rot_dmma(acc[mm][nn][0], acc[mm][nn][1], a_cur[mm], b[nn]);
+    }
+}
+
+// accumulators -> tile, multiplied by the diagonal phase of their row (table[t][|k|], conjugated for k < 0)
+template <int MT, int MA, int PITCH>
+__device__ __forceinline__ void rot_phase_store(const double (&acc)[MT][RG_NT][2], double* __restrict__ tile, const double2* __restrict__ table,
+                                                int PK, int ts0, int l, int n, int g, int q) {
+#pragma unroll
+    for (int mm = 0; mm < MA; ++mm) {
+        const int row = 8 * mm + g, k = row - l, ak = k < 0 ? -k : k;
+        const bool live = row < n;
+#pragma unroll
+        for (int nn = 0; nn < RG_NT; ++nn) {
+            const int t = 4 * nn + q;
+            double2 v = make_double2(acc[mm][nn][0], acc[mm][nn][1]);
+            if (live) {
+                double2 p = table[(ts0 + t) * PK + ak];
+                if (k < 0) p.y = -p.y;
+                v = cmul(v, p);
+            }
+            *reinterpret_cast<double2*>(tile + t * PITCH + 2 * row) = v;
+        }
+    }
+}
+
+template <int MT, int MA, int PITCH>
+__device__ __forceinline__ void rot_two_products(double* __restrict__ tile, const double* __restrict__ af, const double2* __restrict__ s_eb,
+                                                 const double2* __restrict__ s_q3, int PK, int ts0, int l, int n, int Kt, int lane) {
+    if constexpr (MA <= MT) {
+        double acc[MT][RG_NT][2];
+        const int g = lane >> 2, q = lane & 3;
+        const double* bp = tile + (lane >> 3) * PITCH + 2 * q + ((lane >> 2) & 1);   // B fragment: column n = lane / 4 -> step n / 2, re / im
+        rot_gemm_pass<MT, MA, PITCH>(acc, af, bp, Kt);                                // y = Delta^T x
+        __syncwarp();                                  // every lane has read its B fragments: the tile can be overwritten
+        rot_phase_store<MT, MA, PITCH>(acc, tile, s_eb, PK, ts0, l, n, g, q);         // z = y e^{-i mu beta}
+        __syncwarp();
+        rot_gemm_pass<MT, MA, PITCH>(acc, af + MA * Kt * 32, bp, Kt);                 // o = Delta z
+        __syncwarp();
+        rot_phase_store<MT, MA, PITCH>(acc, tile, s_q3, PK, ts0, l, n, g, q);         // a' = o (i e^{i(A+B)})^m
+        __syncwarp();
+    }
+}
+
+// MT: m-tiles the accumulators are sized for (3: ell_max <= 11, 5: ell_max <= 16); S (run time): sub-tiles of 16 time steps
+// per CTA - the warps take (sub-tile, l) pairs from a queue, largest l first, so that a short ell range still fills 8 warps.
+template <int MT>
+__global__ void __launch_bounds__(32 * RG_WARPS, 2)
+rotate_modes_dmma_kernel(double2* __restrict__ data, int64_t n_times, int ell_min, int ell_max, const double2* __restrict__ spinors,
+                         int64_t spinor_stride, const double* __restrict__ frags, const __grid_constant__ RotGemmOffsets offs, int S) {
+    constexpr int PITCH = 16 * MT + 8;                 // doubles per time row of a tile: 88 / 56 (odd multiples of 8)
+    extern __shared__ double2 smg[];
+    const int L = ell_max, TS = RG_T * S;              // time steps of this CTA
+    // phase tables [time step][k], k = 0 .. L at a pitch = 2 (mod 8) complex numbers: a quarter-warp of the accumulator
+    // layout (2 adjacent k x 4 time steps) and of the staging loop (8 adjacent k) each read 128 distinct bytes
+    const int PK = rot_phase_pitch(L);
+    double2* s_q1 = smg;                               // (-i e^{i(A-B)})^k
+    double2* s_eb = s_q1 + PK * TS;                    // e^{-i k beta}
+    double2* s_q3 = s_eb + PK * TS;                    // (i e^{i(A+B)})^k
+    double* s_tiles = reinterpret_cast<double*>(s_q3 + PK * TS);        // [warps][16][PITCH]
+    __shared__ int s_next;
+    __shared__ int s_diag[RG_T * 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
+    const int64_t t0 = (int64_t)blockIdx.x * TS;
+    if (tid == 0) s_next = 0;
+    // the three phase tables: thread (table, time step)
+    for (int id = tid; id < 3 * TS; id += 32 * RG_WARPS) {
+        const int which = id / TS, tt = id - which * TS;
+        int64_t t = t0 + tt;
+        if (t >= n_times) t = n_times - 1;
+        const double2 Ra = spinors[t * spinor_stride + 0], Rb = spinors[t * spinor_stride + 1];
+        const double ra2 = Ra.x * Ra.x + Ra.y * Ra.y, rb2 = Rb.x * Rb.x + Rb.y * Rb.y;
+        const double n2 = ra2 + rb2;
+        // unit phases; the phase of an exact zero is 1 (then beta is 0 or pi and the other angle carries the rotation)
+        const double2 ea = ra2 > 0.0 ? cscale(1.0 / sqrt(ra2), Ra) : make_double2(1.0, 0.0);
+        const double2 eb = rb2 > 0.0 ? cscale(1.0 / sqrt(rb2), Rb) : make_double2(1.0, 0.0);
+        double2 base;
+        double2* table;
+        if (which == 0) {
+            base = cmul(make_double2(0.0, -1.0), cmul(ea, cconj(eb)));
+            table = s_q1;
+            s_diag[tt] = (rb2 == 0.0);
+        } else if (which == 1) {
+            const double ra = sqrt(ra2 / n2), rb = sqrt(rb2 / n2);
+            base = make_double2(ra * ra - rb * rb, -2.0 * ra * rb);
+            table = s_eb;
+        } else {
+            base = cmul(make_double2(0.0, 1.0), cmul(ea, eb));
+            table = s_q3;
+        }
+        double2 p = make_double2(1.0, 0.0);
+        for (int k = 0; k <= L; ++k) {
+            table[tt * PK + k] = p;
+            p = cmul(p, base);
+        }
+    }
+    __syncthreads();
+    double* tile = s_tiles + (size_t)warp * RG_T * PITCH;
+    const int n_ell = L - ell_min + 1;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_ell * S) break;
+        const int l = L - item / S, sub = item - (item / S) * S;       // largest l first, its sub-tiles next to each other
+        const int ts0 = sub * RG_T;                                    // first time step of the sub-tile within the CTA
+        if (t0 + ts0 >= n_times) continue;
+        const int n = 2 * l + 1, Mt = (n + 7) >> 3, Kt = (n + 3) >> 2;
+        const int col_l = l * l - ell_min * ell_min;
+        // (a) stage the slab, premultiplied by (-i e^{i(A-B)})^{m'} - eight loads in flight per lane; zero the padding
+        // columns.  A lane walks the flattened (time step, mode) index in strides of 32 without dividing.
+        const int q32 = 32 / n, r32 = 32 - q32 * n;
+        const int rows = (n_times - (t0 + ts0) < RG_T) ? (int)(n_times - (t0 + ts0)) : RG_T;      // time steps that exist
+        double2* gbase = data + (t0 + ts0) * n_modes + col_l;
+        {
+            int t = lane / n, j = lane - t * n;
+            while (t < RG_T) {
+                double2 v[8];
+                int tu[8], ju[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    tu[u] = t;
+                    ju[u] = j;
+                    v[u] = make_double2(0.0, 0.0);
+                    if (t < rows) v[u] = gbase[(size_t)t * n_modes + j];
+                    t += q32;
+                    j += r32;
+                    if (j >= n) {
+                        j -= n;
+                        ++t;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (tu[u] >= RG_T) continue;
+                    double2 x = v[u];
+                    if (tu[u] < rows) {
+                        const int k = ju[u] - l, ak = k < 0 ? -k : k;
+                        double2 p = s_q1[(ts0 + tu[u]) * PK + ak];
+                        if (k < 0) p.y = -p.y;
+                        x = cmul(x, p);
+                        if (s_diag[ts0 + tu[u]]) {
+                            double2 p3 = s_q3[(ts0 + tu[u]) * PK + ak];
+                            if (k < 0) p3.y = -p3.y;
+                            gbase[(size_t)tu[u] * n_modes + ju[u]] = cmul(x, p3);
+                        }
+                    }
+                    *reinterpret_cast<double2*>(tile + tu[u] * PITCH + 2 * ju[u]) = x;
+                }
+            }
+        }
+        const int npad = 8 * Mt - n;
+        for (int idx = lane; idx < RG_T * npad; idx += 32) {
+            const int t = idx / npad, j = n + idx - t * npad;
+            *reinterpret_cast<double2*>(tile + t * PITCH + 2 * j) = make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+        const double* af = frags + offs.off[l] + lane;
+        switch (Mt) {
+            case 1: rot_two_products<MT, 1, PITCH>(tile, af, s_eb, s_q3, PK, ts0, l, n, Kt, lane); break;
+            case 2: rot_two_products<MT, 2, PITCH>(tile, af, s_eb, s_q3, PK, ts0, l, n, Kt, lane); break;
+            case 3: rot_two_products<MT, 3, PITCH>(tile, af, s_eb, s_q3, PK, ts0, l, n, Kt, lane); break;
+            case 4: rot_two_products<MT, 4, PITCH>(tile, af, s_eb, s_q3, PK, ts0, l, n, Kt, lane); break;
+            default: rot_two_products<MT, 5, PITCH>(tile, af, s_eb, s_q3, PK, ts0, l, n, Kt, lane); break;
+        }
+        // (g) rows back to global memory (steps finished by their diagonal excepted)
+        {
+            int t = lane / n, j = lane - t * n;
+            while (t < rows) {
+                if (!s_diag[ts0 + t]) gbase[(size_t)t * n_modes + j] = *reinterpret_cast<const double2*>(tile + t * PITCH + 2 * j);
+                t += q32;
+                j += r32;
+                if (j >= n) {
+                    j -= n;
+                    ++t;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static size_t rotate_dmma_smem(int L, int S, int MT) {
+    return 3 * (size_t)rot_phase_pitch(L) * RG_T * S * sizeof(double2) + (size_t)RG_WARPS * RG_T * (16 * MT + 8) * sizeof(double);
+}
+
+
 static size_t rotate_time_smem(int lo, int hi) {
     const size_t n_blk = (size_t)(hi + 1) * (hi + 1) - (size_t)lo * lo;
     return (n_blk * ROT3_PITCH + 2 * (size_t)(hi + 1) * ROT3_TB) * sizeof(double2) + (2 * (size_t)(2 * hi + 1) * ROT3_TB + ROT3_TB) * sizeof(double);
@@ -575,6 +816,37 @@ static int upload_rotation_recurrence(cudaStream_t st) {
 }
 
 }  // namespace scrib200
+
+extern "C" int scrib200_rotate_modes_dmma(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
+                                          int64_t spinor_stride, const double* frags, const int* frag_offsets_host, void* stream) {
+    using namespace scrib200;
+    SCRIB200_REQUIRE(data && spinors && frags && frag_offsets_host, "rotate_modes_dmma: null pointer");
+    SCRIB200_REQUIRE(ell_min >= 0 && ell_max >= ell_min && ell_max <= 16, "rotate_modes_dmma: bad ell range [%d, %d] (ell_max <= 16)", ell_min, ell_max);
+    SCRIB200_REQUIRE(spinor_stride == 0 || spinor_stride == 2, "rotate_modes_dmma: spinor_stride must be 0 or 2");
+    SCRIB200_REQUIRE(aligned16(data) && aligned16(spinors) && aligned16(frags), "rotate_modes_dmma: pointers must be 16-byte aligned");
+    if (n_times <= 0) return SCRIB200_OK;
+    RotGemmOffsets offs;
+    for (int l = 0; l < 17; ++l) offs.off[l] = l <= ell_max ? frag_offsets_host[l] : 0;
+    // sub-tiles of 16 steps per CTA: enough (sub-tile, l) pairs for the 8 warps, within 2 CTAs per SM of shared memory
+    const int n_ell = ell_max - ell_min + 1;
+    const int MT = ell_max <= 11 ? 3 : 5;
+    int S = n_ell >= 12 ? 1 : (n_ell >= 6 ? 4 : 8);
+    while (S > 1 && rotate_dmma_smem(ell_max, S, MT) > 110 * 1024) S /= 2;
+    const size_t smem = rotate_dmma_smem(ell_max, S, MT);
+    const int64_t blocks = (n_times + RG_T * S - 1) / (RG_T * S);
+    SCRIB200_REQUIRE(blocks < (int64_t)2147483647, "rotate_modes_dmma: too many time steps");
+    if (MT == 3) {
+        cudaFuncSetAttribute(rotate_modes_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rotate_modes_dmma_kernel<3><<<(unsigned)blocks, 32 * RG_WARPS, smem, (cudaStream_t)stream>>>(
+            reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride, frags, offs, S);
+    } else {
+        cudaFuncSetAttribute(rotate_modes_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rotate_modes_dmma_kernel<5><<<(unsigned)blocks, 32 * RG_WARPS, smem, (cudaStream_t)stream>>>(
+            reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride, frags, offs, S);
+    }
+    SCRIB200_CHECK_LAUNCH("rotate_modes_dmma");
+    return SCRIB200_OK;
+}
 
 extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
                                      int64_t spinor_stride, const double* seed, const double* rec, const double* uv,

@@ -6,6 +6,8 @@ tensors (then nothing is copied and a CUDA tensor is returned), which is what be
 device-resident `value` uses.  No CPU fallback: without a CUDA device these raise Scrib200Error.
 """
 import ctypes
+import math
+import os
 
 import numpy as np
 
@@ -257,6 +259,35 @@ def wigner_tables_device(ell_max):
     return _table_cache[key]
 
 
+def wigner_delta_fragments(ell_max):
+    """Operand table of scrib200_rotate_modes_dmma: for l = 0 .. ell_max the real matrices Delta^l = d^l(pi/2) (this
+    package's D-matrix convention, scri_b200/_sf.py:wigner_D_matrices at Ra = Rb = cos(pi/4)) cut into the A fragments of
+    mma.m8n8k4 - tiles [Kt][Mt][32 lanes] of Delta^T, then of Delta, zero padded; lane holds A[8 mm + lane / 4][4 kk + lane % 4].
+    Returns (device table, host int32 offsets in doubles)."""
+    torch = _torch()
+    key = ("delta", ell_max, torch.cuda.current_device())
+    if key not in _table_cache:
+        c = math.cos(math.pi / 4.0)
+        flat = _sf.wigner_D_matrices(np.array(c + 0j), np.array(c + 0j), 0, ell_max)
+        assert np.abs(flat.imag).max() == 0.0
+        lane = np.arange(32)
+        chunks, offsets, pos = [], np.zeros(ell_max + 1, dtype=np.int32), 0
+        for ell in range(ell_max + 1):
+            n = 2 * ell + 1
+            delta = flat.real[_sf.D_offset(ell, 0) : _sf.D_offset(ell + 1, 0)].reshape(n, n)      # [m', mu]
+            Mt, Kt = (n + 7) // 8, (n + 3) // 4
+            offsets[ell] = pos
+            for A in (delta.T, delta):
+                pad = np.zeros((8 * Mt, 4 * Kt))
+                pad[:n, :n] = A
+                tiles = pad.reshape(Mt, 8, Kt, 4).transpose(2, 0, 1, 3).reshape(Kt, Mt, 32)       # [kk][mm][lane = 4 g + q]
+                chunks.append(tiles.ravel())
+                pos += Mt * Kt * 32
+        table = torch.from_numpy(np.ascontiguousarray(np.concatenate(chunks))).cuda()
+        _table_cache[key] = (table, offsets)
+    return _table_cache[key]
+
+
 def rotate_modes(data, R, ell_min, ell_max):
     """In-place Wigner-D rotation  a'_{lm} = sum_m' a_{lm'} D^l_{m'm}(R)  (scri/rotations.py:346-392).
 
@@ -274,12 +305,22 @@ def rotate_modes(data, R, ell_min, ell_max):
         sp_np = Q.as_spinor_array(Rf)
         stride = 2 if Rf.ndim == 2 else 0
         sp = to_device(sp_np, np.complex128)
-    seed, rec, uv = wigner_tables_device(ell_max)
-    _lib.check(
-        lib.scrib200_rotate_modes(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(seed), _lib.ptr(rec),
-                                  _lib.ptr(uv), _lib.stream_ptr()),
-        "rotate_modes",
-    )
+    if ell_max <= 16 and not os.environ.get("SCRIB200_ROTATE_RECURRENCE"):
+        # constant-matrix factorisation on the FP64 tensor cores
+        frags, offsets = wigner_delta_fragments(ell_max)
+        _lib.check(
+            lib.scrib200_rotate_modes_dmma(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(frags),
+                                           offsets.ctypes.data, _lib.stream_ptr()),
+            "rotate_modes_dmma",
+        )
+    else:
+        # ell_max > 16: one Wigner recurrence per matrix element
+        seed, rec, uv = wigner_tables_device(ell_max)
+        _lib.check(
+            lib.scrib200_rotate_modes(_lib.ptr(d), d.shape[0], ell_min, ell_max, _lib.ptr(sp), stride, _lib.ptr(seed), _lib.ptr(rec),
+                                      _lib.ptr(uv), _lib.stream_ptr()),
+            "rotate_modes",
+        )
     if is_tensor(data):
         return data
     data[...] = to_host(d)
