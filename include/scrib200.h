@@ -220,6 +220,20 @@ int scrib200_sparse_expectation_ell(const double* a, const double* b, int64_t n_
                                     const double* ell_vals, const int* widths_host, int K, int real_values, double* out,
                                     void* stream);
 
+/* Time-lane form of the same contraction (the default when the matrices are banded enough for shared memory): a CTA owns
+ * 32 time steps (lanes along time), stages the mode rows it needs transposed in shared memory and walks the matrix columns
+ * with warp-uniform table reads - scri/flux.py:40-78 (sparse_expectation_value) as called by the flux functions
+ * (scri/flux.py:301-441).
+ *   entries: DEVICE table [n_modes][K][width] of 16-byte {int32 row, int32 0, double value} (real values) or 32-byte
+ *            {int32 row, int32 0, double re, double im, double 0} entries: matrix k's entries of column c, padded to `width`
+ *            (1..4) slots by entries of value 0 on a row the column touches anyway; a column without entries in any matrix
+ *            has row -1 in all its slots (scri_b200/ops.py:_time_tables);
+ *   blocks_host: HOST int[4 * n_blocks] = (c0, c1, rlo, rhi) per column block: columns [c0, c1) touch rows [rlo, rhi) of `a`
+ *            only; when a == b the columns of a block must lie inside its row window.  Tiles over 110 KB are refused. */
+int scrib200_sparse_expectation_time(const double* a, const double* b, int64_t n_times, int n_modes, const void* entries,
+                                     int width, int K, int complex_values, const int* blocks_host, int n_blocks,
+                                     double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Weyl-scalar mixing under a BMS transformation, elementwise over synthesized grids.
  * Replaces  scri/waveform_grid.py:504-550,559 (psi0..psi3 <- higher Weyl scalars times powers of eth u'/k) and the

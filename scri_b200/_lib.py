@@ -69,6 +69,7 @@ SIGNATURES = {
     "scrib200_solve3": (c_int, [c_vp, c_vp, c_i64, ctypes.c_double, c_vp, c_vp]),
     "scrib200_sparse_expectation": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "scrib200_sparse_expectation_ell": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "scrib200_sparse_expectation_time": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "scrib200_map2salm": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
 }
 

@@ -11,6 +11,8 @@
 // All are HBM-bound: one warp per time step, lanes striding over modes (coalesced 16-byte loads of the
 // [time, mode] row), warp-shuffle reduction, a few bytes out per step.  The reference loops mode-outer /
 // time-inner with stride-n access; here each row is read exactly once.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace scrib200 {
@@ -495,6 +497,152 @@ sparse_expectation_ell_kernel(const double2* __restrict__ a, const double2* __re
     }
 }
 
+// Time-lane form of the same contraction.  Lanes run along TIME: a CTA owns 32 time steps, stages the mode rows it needs
+// transposed in shared memory ([mode][time], pitch 33: conflict-free both ways) and walks the columns of the matrices with
+// everything that steers the walk - row index, value, emptiness of a slot - uniform across the warp (one broadcast
+// 16-byte load per non-zero instead of per-lane index / value loads and a gather).  The non-zeros of column c of matrix k
+// are first folded into q = sum_w v_w conj(a[r_w]) (2 FMAs each), then acc_k += q b[c] (4 FMAs per column and matrix): for the
+// momentum operators (3 entries per column) that is 3.3 FP64 instructions per non-zero where the warp-per-time-step
+// kernels issue ~40 instructions of all kinds.  The columns are cut into blocks whose rows of `a` fit shared memory (the
+// flux matrices are banded in (l, m): scri/flux.py:213-298), computed on the host with the tables
+// (scri_b200/ops.py:_time_tables); the warps of a CTA split the columns of a block and their sums are added at the end.
+constexpr int XT_T = 32;
+constexpr int XT_PITCH = 33;
+constexpr int XT_WARPS = 8;
+constexpr int XT_MAXBLK = 32;
+constexpr int XT_MAXW = 4;     // entries per column and matrix the unrolled walk covers
+struct XtPlan {
+    int n_blocks;
+    int c0[XT_MAXBLK], c1[XT_MAXBLK], rlo[XT_MAXBLK], rhi[XT_MAXBLK];
+    int width[4];              // slots of the (up to) four matrices of this launch
+    int slot0;                 // first slot of matrix k0 within a column
+    int slots;                 // slots per column (all matrices)
+    int max_rows, max_cols;    // shared-memory tile heights
+};
+
+__device__ __forceinline__ void xt_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// stage rows [m0, m1) of x for the CTA's 32 time steps, transposed ([mode][time]): a thread keeps its mode and issues the
+// 32 asynchronous 16-byte copies of its time steps back to back (coalesced along the modes in global memory, conflict-free
+// in shared memory; time steps past the end of the series are zero-filled) - one memory latency per block, no registers
+__device__ __forceinline__ void xt_stage(double2* __restrict__ dst, const double2* __restrict__ x, int64_t t0, int64_t n_times, int n,
+                                         int m0, int m1, int tid, int nthreads) {
+    const int rows = (n_times - t0 < XT_T) ? (int)(n_times - t0) : XT_T;
+    for (int lm = tid; lm < m1 - m0; lm += nthreads) {
+        const double2* src = x + t0 * n + m0 + lm;
+        double2* d = dst + lm * XT_PITCH;
+#pragma unroll 8
+        for (int tt = 0; tt < XT_T; ++tt) xt_cp_async16(d + tt, tt < rows ? src + (size_t)tt * n : x, tt < rows ? 16 : 0);
+    }
+}
+
+__device__ __forceinline__ double2 xt_lds(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// CPLX: 32-byte entries {int row, int 0, double re, double im, double 0}; else 16-byte {int row, int 0, double value}.
+// Every matrix has WMAX slots per column; an unused slot names a row the column touches anyway, with value 0 (a column
+// without any entry has row -1 in all its slots and is skipped), so the walk is free of tests.  Shared memory is
+// addressed with 32-bit shared-space addresses (one IMAD per operand).
+template <int WMAX, bool CPLX, bool SAME>
+__global__ void __launch_bounds__(32 * XT_WARPS, 2)
+sparse_expectation_time_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t n_times, int n,
+                               const double2* __restrict__ tab, const __grid_constant__ XtPlan plan, int k0, int K, double2* __restrict__ out) {
+    constexpr int EW = CPLX ? 2 : 1;                                 // double2 words per entry
+    constexpr int KB = 4;
+    extern __shared__ double2 smx[];
+    double2* sA = smx;                                               // [max_rows][33]
+    double2* sB = SAME ? smx : smx + (size_t)plan.max_rows * XT_PITCH;   // [max_cols][33]
+    double2* sT = smx + (size_t)(plan.max_rows + (SAME ? 0 : plan.max_cols)) * XT_PITCH;   // [max_cols][slots] entries of the block
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * XT_T;
+    const int slots = plan.slots;
+    const int nk = K - k0 < KB ? K - k0 : KB;
+    double2 acc[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) acc[k] = make_double2(0.0, 0.0);
+    const unsigned sA_addr = (unsigned)__cvta_generic_to_shared(sA) + lane * 16;
+    const unsigned sB_addr = (unsigned)__cvta_generic_to_shared(sB) + lane * 16;
+    const unsigned sT_addr = (unsigned)__cvta_generic_to_shared(sT);
+    for (int blk = 0; blk < plan.n_blocks; ++blk) {
+        const int c0 = plan.c0[blk], c1 = plan.c1[blk], rlo = plan.rlo[blk], rhi = plan.rhi[blk];
+        if (blk > 0) __syncthreads();                                // the previous block's tiles are no longer read
+        xt_stage(sA, a, t0, n_times, n, rlo, rhi, tid, 32 * XT_WARPS);
+        if (!SAME) xt_stage(sB, b, t0, n_times, n, c0, c1, tid, 32 * XT_WARPS);
+        {   // the block's entries: contiguous in the table
+            const double2* src = tab + (size_t)c0 * slots * EW;
+            const int words = (c1 - c0) * slots * EW;
+            for (int i = tid; i < words; i += 32 * XT_WARPS) xt_cp_async16(sT + i, src + i, 16);
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();
+        const unsigned bcol = SAME ? sA_addr + (unsigned)(c0 - rlo) * (XT_PITCH * 16) : sB_addr;
+        const unsigned arow = sA_addr - (unsigned)rlo * (XT_PITCH * 16);          // + r * 528
+        for (int c = c0 + warp; c < c1; c += XT_WARPS) {
+            unsigned e = sT_addr + (unsigned)(((c - c0) * slots + plan.slot0) * (EW * 16));
+            const double2 first = xt_lds(e);
+            if ((int)(__double_as_longlong(first.x) & 0xffffffffLL) < 0) continue;   // a column no matrix has entries in
+            const double2 bc = xt_lds(bcol + (unsigned)(c - c0) * (XT_PITCH * 16));
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                if (k < nk) {
+                    // the entries of (column, matrix) first, then the rows they name, then the arithmetic: the loads
+                    // overlap instead of queueing behind each other's use
+                    double2 ent[WMAX], ent2[WMAX], ar[WMAX];
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) {
+                        ent[w] = xt_lds(e + w * (EW * 16));
+                        if (CPLX) ent2[w] = xt_lds(e + w * (EW * 16) + 16);
+                    }
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) {
+                        const unsigned r = (unsigned)(__double_as_longlong(ent[w].x) & 0xffffffffLL);
+                        ar[w] = xt_lds(arow + r * (XT_PITCH * 16));
+                    }
+                    double2 q = make_double2(0.0, 0.0);              // sum_w v_w conj(a[r_w])
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) {
+                        if (CPLX) {
+                            const double vx = ent[w].y, vy = ent2[w].x;
+                            q.x = fma(vx, ar[w].x, fma(vy, ar[w].y, q.x));        // (vx + i vy)(ar.x - i ar.y)
+                            q.y = fma(vy, ar[w].x, fma(-vx, ar[w].y, q.y));
+                        } else {
+                            const double v = ent[w].y;
+                            q.x = fma(v, ar[w].x, q.x);
+                            q.y = fma(-v, ar[w].y, q.y);
+                        }
+                    }
+                    cfma(acc[k], q, bc);
+                    e += WMAX * (EW * 16);
+                }
+            }
+        }
+    }
+    // add the warps' partial sums: [warp][k][lane] through shared memory (the tiles are free after a barrier)
+    __syncthreads();
+    double2* red = smx;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) red[(warp * KB + k) * 32 + lane] = acc[k];
+    __syncthreads();
+    for (int id = tid; id < KB * 32; id += 32 * XT_WARPS) {
+        const int k = id >> 5, tt = id & 31;
+        if (k0 + k >= K || t0 + tt >= n_times) continue;
+        double2 ssum = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < XT_WARPS; ++w) {
+            const double2 v = red[(w * KB + k) * 32 + tt];
+            ssum.x += v.x;
+            ssum.y += v.y;
+        }
+        out[(t0 + tt) * K + k0 + k] = ssum;
+    }
+}
+
 static inline unsigned warp_blocks(int64_t n_times) { return (unsigned)((n_times * 32 + 127) / 128); }
 
 }  // namespace scrib200
@@ -631,6 +779,71 @@ extern "C" int scrib200_sparse_expectation_ell(const double* a, const double* b,
                 reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes, ell_rows, ell_vals, lay, k0, K,
                 reinterpret_cast<double2*>(out));
         SCRIB200_CHECK_LAUNCH("sparse_expectation_ell");
+    }
+    return SCRIB200_OK;
+}
+
+extern "C" int scrib200_sparse_expectation_time(const double* a, const double* b, int64_t n_times, int n_modes, const void* entries,
+                                                int width, int K, int complex_values, const int* blocks_host, int n_blocks,
+                                                double* out, void* stream) {
+    SCRIB200_REQUIRE(a && b && entries && blocks_host && out, "sparse_expectation_time: null pointer");
+    SCRIB200_REQUIRE(aligned16(a) && aligned16(b) && aligned16(entries), "sparse_expectation_time: pointers must be 16-byte aligned");
+    SCRIB200_REQUIRE(K >= 1 && K <= 32, "sparse_expectation_time: K=%d must be 1..32", K);
+    SCRIB200_REQUIRE(width >= 1 && width <= XT_MAXW, "sparse_expectation_time: width %d (1..%d)", width, XT_MAXW);
+    SCRIB200_REQUIRE(n_blocks >= 1 && n_blocks <= XT_MAXBLK, "sparse_expectation_time: %d column blocks (1..%d)", n_blocks, XT_MAXBLK);
+    if (n_times <= 0) return SCRIB200_OK;
+    XtPlan plan;
+    plan.n_blocks = n_blocks;
+    plan.max_rows = plan.max_cols = 0;
+    for (int i = 0; i < XT_MAXBLK; ++i) {
+        const bool live = i < n_blocks;
+        plan.c0[i] = live ? blocks_host[4 * i] : 0;
+        plan.c1[i] = live ? blocks_host[4 * i + 1] : 0;
+        plan.rlo[i] = live ? blocks_host[4 * i + 2] : 0;
+        plan.rhi[i] = live ? blocks_host[4 * i + 3] : 0;
+        if (live) {
+            SCRIB200_REQUIRE(0 <= plan.c0[i] && plan.c0[i] < plan.c1[i] && plan.c1[i] <= n_modes && 0 <= plan.rlo[i] && plan.rlo[i] < plan.rhi[i] &&
+                                 plan.rhi[i] <= n_modes,
+                             "sparse_expectation_time: bad column block %d", i);
+            plan.max_rows = std::max(plan.max_rows, plan.rhi[i] - plan.rlo[i]);
+            plan.max_cols = std::max(plan.max_cols, plan.c1[i] - plan.c0[i]);
+        }
+    }
+    const bool same = (a == b);
+    if (same)      // b[c] is read from the rows staged for a: every block's columns must lie inside its row window
+        for (int i = 0; i < n_blocks; ++i)
+            SCRIB200_REQUIRE(plan.rlo[i] <= plan.c0[i] && plan.c1[i] <= plan.rhi[i], "sparse_expectation_time: block %d: columns outside the row window", i);
+    plan.slots = K * width;
+    for (int k = 0; k < 4; ++k) plan.width[k] = width;
+    const size_t tile_rows = (size_t)plan.max_rows + (same ? 0 : plan.max_cols);
+    const size_t table_words = (size_t)plan.max_cols * plan.slots * (complex_values ? 2 : 1);
+    const size_t smem = std::max(tile_rows * XT_PITCH + table_words, (size_t)XT_WARPS * 4 * 32) * sizeof(double2);
+    SCRIB200_REQUIRE(smem <= 110 * 1024, "sparse_expectation_time: blocks need %zu bytes of shared memory", smem);
+    const unsigned grid = (unsigned)((n_times + XT_T - 1) / XT_T);
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        plan.slot0 = k0 * width;
+#define XT_LAUNCH(W_, CPLX_, SAME_)                                                                                          \
+    {                                                                                                                        \
+        cudaFuncSetAttribute(sparse_expectation_time_kernel<W_, CPLX_, SAME_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        sparse_expectation_time_kernel<W_, CPLX_, SAME_><<<grid, 32 * XT_WARPS, smem, (cudaStream_t)stream>>>(               \
+            reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), n_times, n_modes,                      \
+            reinterpret_cast<const double2*>(entries), plan, k0, K, reinterpret_cast<double2*>(out));                        \
+    }
+#define XT_PICK(W_)                                                                                                          \
+    if (complex_values) {                                                                                                    \
+        if (same) XT_LAUNCH(W_, true, true) else XT_LAUNCH(W_, true, false)                                                  \
+    } else {                                                                                                                 \
+        if (same) XT_LAUNCH(W_, false, true) else XT_LAUNCH(W_, false, false)                                                \
+    }
+        switch (width) {
+            case 1: XT_PICK(1) break;
+            case 2: XT_PICK(2) break;
+            case 3: XT_PICK(3) break;
+            default: XT_PICK(4) break;
+        }
+#undef XT_PICK
+#undef XT_LAUNCH
+        SCRIB200_CHECK_LAUNCH("sparse_expectation_time");
     }
     return SCRIB200_OK;
 }

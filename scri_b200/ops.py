@@ -824,6 +824,84 @@ def _ell_tables(matrices, n):
     return rows, vals, widths, real
 
 
+XT_BUDGET_BYTES = 108 * 1024  # shared memory per CTA (mode tiles at 528 bytes per row + the block's entries): two CTAs per SM
+XT_MAX_WIDTH = 4              # entries per column and matrix the kernel's unrolled walk covers
+
+
+def _time_tables(matrices, n, same):
+    """Tables of scrib200_sparse_expectation_time: the per-column entry table [n][K][width] and the column blocks whose rows
+    of `a` (plus, when a is not b, whose own columns of b) and entries fit the shared-memory budget.  None when the
+    matrices are too wide or a column's rows do not fit."""
+    rows, vals, widths, real = _ell_tables(matrices, n)
+    K, width = len(matrices), int(max(widths)) if widths else 0
+    if width == 0 or width > XT_MAX_WIDTH:
+        return None
+    esize = 16 if real else 32
+    slots = K * width
+    er = np.full((K, width, n), -1, dtype=np.int64)
+    ev = np.zeros((K, width, n), dtype=complex)
+    off = 0
+    for k, W in enumerate(widths):
+        er[k, :W] = rows[off : off + W * n].reshape(W, n)
+        ev[k, :W] = vals[off : off + W * n].reshape(W, n)
+        off += W * n
+    used = er >= 0
+    lo = np.where(used, er, n).min(axis=(0, 1))                 # rows touched by each column (n / -1: none)
+    hi = er.max(axis=(0, 1))
+    empty = hi < 0
+    # unused slots: value 0 on the column's lowest row (a row its window holds anyway); all-empty columns keep row -1
+    fill = np.broadcast_to(np.where(empty, -1, lo), er.shape)
+    er = np.where(used, er, fill)
+    dt = np.dtype([("r", "<i4"), ("p", "<i4"), ("v", "<f8")]) if real else np.dtype(
+        [("r", "<i4"), ("p", "<i4"), ("v", "<f8"), ("vi", "<f8"), ("q", "<f8")])
+    tab = np.zeros((n, K, width), dtype=dt)
+    tab["r"] = er.transpose(2, 0, 1)
+    tab["v"] = ev.real.transpose(2, 0, 1)
+    if not real:
+        tab["vi"] = ev.imag.transpose(2, 0, 1)
+
+    def cost(rlo, rhi, c0, c1):          # bytes of shared memory for columns [c0, c1] touching rows [rlo, rhi]
+        return ((rhi + 1 - rlo) + (0 if same else c1 + 1 - c0)) * 528 + (c1 + 1 - c0) * slots * esize
+
+    def window(c):                       # rows column c needs staged (its own row too when b is read from a's tile)
+        if empty[c]:
+            return (c, c) if same else None
+        return (min(int(lo[c]), c), max(int(hi[c]), c)) if same else (int(lo[c]), int(hi[c]))
+
+    def cut(budget):
+        blocks, c = [], 0
+        while c < n:
+            w = window(c)
+            if w is None:                # nothing to do for a leading empty column
+                c += 1
+                continue
+            c0, (rlo, rhi) = c, w
+            if cost(rlo, rhi, c0, c0) > budget:
+                return None              # one column alone exceeds the budget
+            c += 1
+            while c < n:
+                w = window(c)
+                nlo, nhi = (rlo, rhi) if w is None else (min(rlo, w[0]), max(rhi, w[1]))
+                if cost(nlo, nhi, c0, c) > budget:
+                    break
+                rlo, rhi = nlo, nhi
+                c += 1
+            blocks.append((c0, c, rlo, rhi + 1))
+        return blocks
+
+    # the kernel sizes its tiles for the tallest row window and the widest column block of ALL blocks: cut with a smaller
+    # per-block budget until that total fits
+    for budget in (XT_BUDGET_BYTES, 96 << 10, 84 << 10, 72 << 10, 60 << 10, 48 << 10):
+        blocks = cut(budget)
+        if not blocks or len(blocks) > 32:
+            return None
+        max_rows = max(b[3] - b[2] for b in blocks)
+        max_cols = max(b[1] - b[0] for b in blocks)
+        if (max_rows + (0 if same else max_cols)) * 528 + max_cols * slots * esize <= XT_BUDGET_BYTES:
+            return tab, np.asarray(blocks, dtype=np.int32).ravel(), width, real
+    return None
+
+
 def sparse_expectation(a, b, matrices):
     """[N, K] complex: <a|M_k|b>(t) for K sparse matrices (rows, cols, vals) - scri/flux.py:40-78."""
     import ctypes
@@ -836,11 +914,20 @@ def sparse_expectation(a, b, matrices):
     K = len(matrices)
     # the tables are cached on the device per set of matrix objects (the generators in flux.py are lru_cached, so the
     # same objects come back call after call; the cache keeps them alive, which keeps their ids unique)
-    key = (tuple(id(m) for m in matrices), n, torch.cuda.current_device())
+    key = (tuple(id(m) for m in matrices), n, torch.cuda.current_device(), bd is ad)
     hit = _sparse_cache.get(key)
     if hit is None:
         if len(_sparse_cache) > 64:
             _sparse_cache.clear()
+        timed = _time_tables(matrices, n, bd is ad) if K <= 32 and not os.environ.get("SCRIB200_EXPECTATION_WARP") else None
+        if timed is not None and timed[2] == 1 and bd is not ad:
+            timed = None        # one entry per column, two arrays to stage: the warp-per-step kernels are as fast (measured)
+        if timed is not None:
+            tab, blocks, width, real = timed
+            dev = torch.from_numpy(tab.view(np.uint8).reshape(-1)).cuda()
+            _sparse_cache[key] = ("time", dev, width, real, list(matrices), blocks)
+        hit = _sparse_cache.get(key)
+    if hit is None:
         rows, vals, widths, real = _ell_tables(matrices, n) if K <= 32 else (None, None, [0], False)
         # matrices with several entries per column (the momentum and boost operators) go through the ELL kernel, which
         # loads b[c] once per column; with one entry per column (L_z, L_+-) the flat COO loop is the faster one (measured)
@@ -855,7 +942,14 @@ def sparse_expectation(a, b, matrices):
             seg[1:] = np.cumsum([len(m[0]) for m in matrices])
             hit = _sparse_cache[key] = ("coo", tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (rows, cols, vals, seg)), None, None, list(matrices))
     out = torch.empty((N, K), dtype=torch.complex128, device="cuda")
-    if hit[0] == "ell":
+    if hit[0] == "time":
+        dev, width, real, blocks = hit[1], hit[2], hit[3], hit[5]
+        _lib.check(
+            lib.scrib200_sparse_expectation_time(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dev), width, K, int(not real), blocks.ctypes.data,
+                                                 len(blocks) // 4, _lib.ptr(out), _lib.stream_ptr()),
+            "sparse_expectation_time",
+        )
+    elif hit[0] == "ell":
         (dr, dv), widths, real = hit[1], hit[2], hit[3]
         _lib.check(
             lib.scrib200_sparse_expectation_ell(_lib.ptr(ad), _lib.ptr(bd), N, n, _lib.ptr(dr), _lib.ptr(dv), widths, K, int(real), _lib.ptr(out),
