@@ -29,7 +29,7 @@ def report(name, ms, bytes_, note=""):
     rows.append(f"| {name} | {ms:.3f} | {bytes_/1e9:.2f} | {gbs:.0f} | {100*gbs/hbm:.0f} % | {note} |")
 B = 16.0 * n * N
 ms, ddot = timeit(lambda: ops.spline_calculus(t, data, "derivative", 1)); report("K8 data_dot (spline_prepare + spline_tile<1>)", ms, 2 * B, "read a, write a-dot")
-ms, _ = timeit(lambda: ops.spline_calculus(t, data, "antiderivative", 1)); report("K8 data_int (spline_tile<3> + column scan)", ms, 2 * B, "scan re-reads/re-writes the output: 4 passes of traffic")
+ms, _ = timeit(lambda: ops.spline_calculus(t, data, "antiderivative", 1)); report("K8 data_int (spline_tile<3> with in-tile sums + tile totals + add pass)", ms, 2 * B, "one extra pass over the output")
 ms, _ = timeit(lambda: ops.norm(data)); report("norm", ms, B + 8 * N)
 ms, (LL, Ldt) = timeit(lambda: ops.ll_ldt(data, ddot, LMIN, LMAX)); report("K5 <LL> + <L d/dt>", ms, 2 * B + 96 * N, "reads a and a-dot")
 ms, _ = timeit(lambda: ops.ll_ldt(data, None, LMIN, LMAX)); report("K5 <LL> only", ms, B + 72 * N)
@@ -37,14 +37,14 @@ rd = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64, device="cuda")
 ms, dpa = timeit(lambda: ops.dominant_eigenvector(LL, np.array([0.0, 0.0, 1.0]), 0)); report("K6 dominant eigenvector (Jacobi + sign scan)", ms, (72 + 24) * N)
 ms, om = timeit(lambda: ops.solve3(LL, Ldt, -1.0)); report("solve3 (angular velocity)", ms, (72 + 24 + 24) * N)
 mats = [flux.p_plus(LMIN, LMAX, s=-2), flux.p_minus(LMIN, LMAX, s=-2), flux.p_z(LMIN, LMAX, s=-2)]
-ms, _ = timeit(lambda: ops.sparse_expectation(ddot, ddot, mats)); report("K7 momentum flux (3 matrices, one pass)", ms, B + 48 * N, "a = b = a-dot")
+ms, _ = timeit(lambda: ops.sparse_expectation(ddot, ddot, mats)); report("K7 momentum flux (3 matrices, one pass, time-lane kernel)", ms, B + 48 * N, "a = b = a-dot")
 jm = [flux.j_plus(LMIN, LMAX), flux.j_minus(LMIN, LMAX), flux.j_z(LMIN, LMAX)]
 ms, _ = timeit(lambda: ops.sparse_expectation(ddot, data, jm)); report("K7 angular-momentum flux (3 matrices)", ms, 2 * B + 48 * N)
 q = torch.randn(N, 4, dtype=torch.float64, device="cuda", generator=g); q = q / q.norm(dim=1, keepdim=True)
 sp = torch.complex(q[:, 0], q[:, 3]), torch.complex(q[:, 2], q[:, 1])
 spin = torch.stack(sp, dim=1).contiguous()
 d2 = data.clone()
-ms, _ = timeit(lambda: ops.rotate_modes(d2, spin, LMIN, LMAX)); report("K4 rotation by a rotor series (in place)", ms, 2 * B + 32 * N)
+ms, _ = timeit(lambda: ops.rotate_modes(d2, spin, LMIN, LMAX)); report("K4 rotation by a rotor series (in place, DMMA)", ms, 2 * B + 32 * N)
 print(f"\ninputs: N = {N}, ell = {LMIN}..{LMAX} (n = {n}), modes {B/1e9:.2f} GB; HBM peak (MEASURED_PEAKS.json) {hbm:.0f} GB/s; kernels launched {_lib.launch_count()}\n")
 print("| kernel | ms | algorithmic GB | GB/s | of HBM peak | note |\n|---|---|---|---|---|---|")
 print("\n".join(rows))
