@@ -646,7 +646,7 @@ rotate_modes_dmma_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     const int64_t t0 = (int64_t)blockIdx.x * TS;
     if (tid == 0) s_next = 0;
     // the three phase tables: thread (table, time step)
-    for (int id = tid; id < 3 * TS; id += 32 * RG_WARPS) {
+    for (int id = tid; id < 3 * TS; id += (int)blockDim.x) {
         const int which = id / TS, tt = id - which * TS;
         int64_t t = t0 + tt;
         if (t >= n_times) t = n_times - 1;
@@ -762,8 +762,8 @@ rotate_modes_dmma_kernel(double2* __restrict__ data, int64_t n_times, int ell_mi
     }
 }
 
-static size_t rotate_dmma_smem(int L, int S, int MT) {
-    return 3 * (size_t)rot_phase_pitch(L) * RG_T * S * sizeof(double2) + (size_t)RG_WARPS * RG_T * (16 * MT + 8) * sizeof(double);
+static size_t rotate_dmma_smem(int L, int S, int MT, int warps) {
+    return 3 * (size_t)rot_phase_pitch(L) * RG_T * S * sizeof(double2) + (size_t)warps * RG_T * (16 * MT + 8) * sizeof(double);
 }
 
 
@@ -827,21 +827,28 @@ extern "C" int scrib200_rotate_modes_dmma(double* data, int64_t n_times, int ell
     if (n_times <= 0) return SCRIB200_OK;
     RotGemmOffsets offs;
     for (int l = 0; l < 17; ++l) offs.off[l] = l <= ell_max ? frag_offsets_host[l] : 0;
-    // sub-tiles of 16 steps per CTA: enough (sub-tile, l) pairs for the 8 warps, within 2 CTAs per SM of shared memory
     const int n_ell = ell_max - ell_min + 1;
     const int MT = ell_max <= 11 ? 3 : 5;
-    int S = n_ell >= 12 ? 1 : (n_ell >= 6 ? 4 : 8);
-    while (S > 1 && rotate_dmma_smem(ell_max, S, MT) > 110 * 1024) S /= 2;
-    const size_t smem = rotate_dmma_smem(ell_max, S, MT);
+    // (sub-tiles per CTA, warps): the items of a CTA are few and of very different size (l = 16 costs 20 x l = 2), so one
+    // sub-tile per CTA leaves the warps that drew small items idle until the largest is done (15 items on 8 warps: 70 %);
+    // two sub-tiles on 7 warps pack to 97 % and still fit two CTAs per SM
+    int S = MT == 5 ? 2 : (n_ell >= 6 ? 4 : 8), warps = MT == 5 ? 7 : RG_WARPS;       // measured (1e6 x 285: S, warps = 1, 8: 6.54 ms; 2, 7: 6.09; 3, 6: 6.21; 4, 6: 6.76)
+    static const int env_s = [] { const char* e = getenv("SCRIB200_ROTATE_SUBTILES"); return e ? atoi(e) : 0; }();
+    static const int env_w = [] { const char* e = getenv("SCRIB200_ROTATE_WARPS"); return e ? atoi(e) : 0; }();
+    if (env_s > 0) S = env_s > 8 ? 8 : env_s;
+    if (env_w > 0) warps = env_w > (MT == 5 ? 7 : RG_WARPS) ? (MT == 5 ? 7 : RG_WARPS) : env_w;
+    while (warps > 4 && rotate_dmma_smem(ell_max, S, MT, warps) > 113 * 1024) --warps;
+    while (S > 1 && rotate_dmma_smem(ell_max, S, MT, warps) > 113 * 1024) S /= 2;
+    const size_t smem = rotate_dmma_smem(ell_max, S, MT, warps);
     const int64_t blocks = (n_times + RG_T * S - 1) / (RG_T * S);
     SCRIB200_REQUIRE(blocks < (int64_t)2147483647, "rotate_modes_dmma: too many time steps");
     if (MT == 3) {
         cudaFuncSetAttribute(rotate_modes_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        rotate_modes_dmma_kernel<3><<<(unsigned)blocks, 32 * RG_WARPS, smem, (cudaStream_t)stream>>>(
+        rotate_modes_dmma_kernel<3><<<(unsigned)blocks, 32 * warps, smem, (cudaStream_t)stream>>>(
             reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride, frags, offs, S);
     } else {
         cudaFuncSetAttribute(rotate_modes_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        rotate_modes_dmma_kernel<5><<<(unsigned)blocks, 32 * RG_WARPS, smem, (cudaStream_t)stream>>>(
+        rotate_modes_dmma_kernel<5><<<(unsigned)blocks, 32 * warps, smem, (cudaStream_t)stream>>>(
             reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors), spinor_stride, frags, offs, S);
     }
     SCRIB200_CHECK_LAUNCH("rotate_modes_dmma");
