@@ -515,7 +515,10 @@ def run_ours(args):
             times.append(time.perf_counter() - t0)
         return times, o
 
-    # (a) the modes in an ordinary numpy array: the library page-locks it in place at its second sighting (warm-up above)
+    # (a) the modes in an ordinary numpy array: the library page-locks it in place at its second sighting (warm-up above).
+    # (`out` is dropped first: the loop holds one result while the next is produced - a third live result would need a third
+    # page-locked block, i.e. a 60-80 ms cudaHostAlloc inside the timed region)
+    out = None
     pageable_times, out = e2e_loop()
     # (b) the modes in page-locked host memory from the start (the contract's "from pinned host memory"): the headline e2e
     pageable_data = w.data
@@ -526,6 +529,7 @@ def run_ours(args):
     gc.enable()
     for _ in range(3):
         out = w.transform(**kw)
+    out = None
     barrier()
     gc.collect()
     gc.disable()
