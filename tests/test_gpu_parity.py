@@ -416,6 +416,42 @@ def test_corotating_frame_round_trip():
     assert np.allclose(w.data, ref, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("same", [True, False])
+@pytest.mark.parametrize("width,cplx", [(1, False), (2, True), (3, False), (4, True), (6, False)])
+def test_sparse_expectation_every_kernel_against_dense(same, width, cplx, monkeypatch):
+    """<a|M_k|b>(t) (scri/flux.py:40-78) for random banded matrices through every kernel the product can pick: lanes along
+    time (real / complex values, one array / two arrays, 1..4 entries per column, a column block count above one), the
+    warp-per-step ELL and COO kernels (forced by SCRIB200_EXPECTATION_WARP, or chosen for 6 entries per column), against the
+    dense contraction.  Columns without entries, matrices of different widths and 5 matrices (two launches of <= 4) included."""
+    rng = np.random.default_rng(100 * width + 10 * cplx + same)
+    n, N, K = 285, 333, 5
+    a = rng.normal(size=(N, n)) + 1j * rng.normal(size=(N, n))
+    b = a if same else rng.normal(size=(N, n)) + 1j * rng.normal(size=(N, n))
+    mats, dense = [], []
+    for k in range(K):
+        wk = width if k != 1 else max(1, width - 1)            # one narrower matrix: its slots are padded
+        rows, cols, vals = [], [], []
+        for c in range(n):
+            if c % 17 == 5:                                     # columns without entries
+                continue
+            r = np.unique(np.clip(c + rng.integers(-35, 36, size=wk), 0, n - 1))
+            v = rng.normal(size=r.size) + (1j * rng.normal(size=r.size) if cplx else 0.0)
+            rows += list(r)
+            cols += [c] * r.size
+            vals += list(v)
+        M = np.zeros((n, n), dtype=complex)
+        M[rows, cols] = vals
+        dense.append(M)
+        mats.append((np.array(rows), np.array(cols), np.array(vals, dtype=complex if cplx else float)))
+    want = np.stack([np.einsum("tr,rc,tc->t", a.conj(), M, b) for M in dense], axis=1)
+    got = ops.sparse_expectation(a, b, mats)
+    assert rel(got, want) < 1e-13
+    monkeypatch.setenv("SCRIB200_EXPECTATION_WARP", "1")
+    ops._sparse_cache.clear()
+    assert rel(ops.sparse_expectation(a, b, mats), want) < 1e-13
+    ops._sparse_cache.clear()
+
+
 def test_full_size_fluxes_config5_slice():
     """l<=16 fluxes on 1e5 steps (a slice of config 5): linearity / scaling properties + oracle on a window."""
     N = 100_000
