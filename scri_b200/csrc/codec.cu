@@ -1,6 +1,9 @@
 // Integer stages of scri's RPXMB waveform codec: XOR of successive time steps, Fletcher-32 checksum and
 // the bit-level "multishuffle" - replaces scri/utilities.py:194-407 (numba loops) bit for bit.  All three are HBM-bound
 // integer / byte kernels: every element is read once and written once.
+#include <algorithm>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace scrib200 {
@@ -105,6 +108,92 @@ multishuffle_forward_kernel(const T* __restrict__ a, T* __restrict__ b, int64_t 
             }
         }
         b[B] = (T)word;
+    }
+}
+
+// forward, 32- and 64-bit elements: a bit transpose through the warp instead of a gather from global memory.  A warp owns 32
+// consecutive elements (one coalesced load); piece i of those elements is a run of 32 w_i bits = w_i words, lane l's bits at
+// offset l w_i: a ballot for 1-bit pieces, a shuffle butterfly for widths that divide 32 (all words of the run at once), and for
+// the rest every word of the run is an OR-reduction (`redux.sync`) over the lanes of their overlap with it.  The 8 warps of a CTA put their segments side by side in shared memory (256 w_i bits per piece, word aligned,
+// nobody shares a word), then the CTA writes each piece's run at its place in the stream, n S_i + e0 w_i bits in: funnel-shifted
+// by that position's offset inside a word, whole words stored, the first and last (shared with the neighbouring CTAs' runs,
+// or with the next piece's region) OR-ed atomically into the zeroed output.
+constexpr int MS_WARPS = 8;
+constexpr int MS_ELEMS = 32 * MS_WARPS;
+
+template <typename T>
+__global__ void __launch_bounds__(32 * MS_WARPS)
+multishuffle_forward_warp_kernel(const T* __restrict__ a, unsigned int* __restrict__ out, int64_t n, int64_t n_chunks, const ShuffleWidths w) {
+    constexpr int BW = 8 * sizeof(T);
+    __shared__ unsigned int run[MS_WARPS * BW + 2];          // the pieces' runs back to back: piece i at 8 S_i, 8 w_i words
+    __shared__ unsigned short item_piece[MS_WARPS * BW + 64];
+    __shared__ unsigned short item_k[MS_WARPS * BW + 64];
+    __shared__ int n_items;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the CTA's output items (piece, word of its shifted run): 8 w_i + 1 per piece
+    if (tid < w.n) {
+        const int base = MS_WARPS * w.shift[tid] + tid, cnt = MS_WARPS * w.width[tid] + 1;
+        for (int k = 0; k < cnt; ++k) {
+            item_piece[base + k] = (unsigned short)tid;
+            item_k[base + k] = (unsigned short)k;
+        }
+        if (tid == w.n - 1) n_items = base + cnt;
+    }
+    __syncthreads();
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t e0 = chunk * MS_ELEMS;
+        const int64_t e = e0 + tid;
+        const unsigned long long v = e < n ? (unsigned long long)a[e] : 0ull;
+        for (int i = 0; i < w.n; ++i) {
+            const int wi = w.width[i];
+            const unsigned long long val = (v >> w.shift[i]) & (wi == 64 ? ~0ull : ((1ull << wi) - 1ull));
+            unsigned int* seg = run + MS_WARPS * w.shift[i] + warp * wi;     // this warp's wi words of piece i
+            if (wi == 1) {
+                const unsigned int word = __ballot_sync(0xffffffffu, val & 1ull);
+                if (lane == 0) seg[0] = word;
+            } else if (wi <= 32 && (wi & (wi - 1)) == 0) {
+                // 32 / wi pieces per word: a shuffle butterfly builds all wi words at once (lane q 32 / wi ends up with word q)
+                unsigned int x = (unsigned int)val;
+                for (int step = 1, bits = wi; bits < 32; step <<= 1, bits <<= 1) x |= __shfl_down_sync(0xffffffffu, x, step) << bits;
+                const int lg = 6 - __ffs(wi);                                // log2(32 / wi): no division by a run-time width
+                if ((lane & ((1 << lg) - 1)) == 0) seg[lane >> lg] = x;
+            } else {
+                const int o = lane * wi;                                     // my first bit within the segment
+                for (int q = 0; q < wi; ++q) {
+                    const int d = 32 * q - o;                                // word q starts d bits into my piece
+                    unsigned int c = 0;
+                    if (d >= 0) {
+                        if (d < wi) c = (unsigned int)(val >> d);
+                    } else if (d > -32) {
+                        c = (unsigned int)(val << (-d));
+                    }
+                    c = __reduce_or_sync(0xffffffffu, c);
+                    if (lane == (q & 31)) seg[q] = c;
+                }
+            }
+        }
+        __syncthreads();
+        const bool partial = e0 + MS_ELEMS > n;                              // the last chunk: its runs end inside a piece's region
+        for (int it = tid; it < n_items; it += 32 * MS_WARPS) {
+            const int i = item_piece[it], k = item_k[it], wi = w.width[i], nw = MS_WARPS * wi;
+            const unsigned long long pos = (unsigned long long)n * w.shift[i] + (unsigned long long)e0 * wi;   // bit position of the run
+            const int sh = (int)(pos & 31ull);
+            const unsigned int* r = run + MS_WARPS * w.shift[i];
+            const unsigned int lo = k < nw ? r[k] : 0u, prev = k > 0 ? r[k - 1] : 0u;
+            const unsigned int word = sh ? ((lo << sh) | (prev >> (32 - sh))) : lo;
+            if (k == nw && sh == 0) continue;                                // nothing spills into the word after the run
+            const unsigned long long wordidx = (pos >> 5) + (unsigned long long)k;
+            if (partial) {
+                const unsigned long long end = (unsigned long long)n * (w.shift[i] + wi);      // first bit after piece i's region
+                if (wordidx * 32ull >= end) continue;
+                if (word) atomicOr(out + wordidx, word);
+            } else if ((k == 0 && sh != 0) || k == nw) {
+                if (word) atomicOr(out + wordidx, word);
+            } else {
+                out[wordidx] = word;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -262,6 +351,19 @@ extern "C" int scrib200_multishuffle(const void* in, void* out, int64_t n, int b
     if (n <= 0) return SCRIB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = grid_for(n, 256);
+    if (forward && bit_width >= 32 && getenv("SCRIB200_MULTISHUFFLE_GATHER") == nullptr) {
+        // bit transpose through the warp (whole 32-bit words of output: the element types whose streams are word multiples)
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)n * (bit_width / 8), st);
+        SCRIB200_REQUIRE(e == cudaSuccess, "multishuffle: %s", cudaGetErrorString(e));
+        const int64_t n_chunks = (n + MS_ELEMS - 1) / MS_ELEMS;
+        const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, 148 * 8);
+        if (bit_width == 32)
+            multishuffle_forward_warp_kernel<unsigned int><<<grid, 32 * MS_WARPS, 0, st>>>(reinterpret_cast<const unsigned int*>(in), reinterpret_cast<unsigned int*>(out), n, n_chunks, w);
+        else
+            multishuffle_forward_warp_kernel<unsigned long long><<<grid, 32 * MS_WARPS, 0, st>>>(reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned int*>(out), n, n_chunks, w);
+        SCRIB200_CHECK_LAUNCH("multishuffle");
+        return SCRIB200_OK;
+    }
 #define SCRIB200_SHUFFLE(T)                                                                                                   \
     if (forward) multishuffle_forward_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), n, w); \
     else multishuffle_reverse_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), n, w);
