@@ -77,11 +77,16 @@ def test_rotation_poles_and_large_ell():
     assert rel(d, Wo.data) < 1e-12
 
 
-@pytest.mark.parametrize("ell_min,ell_max", [(2, 8), (2, 16), (0, 16), (0, 8), (3, 11), (10, 14), (2, 5), (13, 16), (9, 12), (2, 12), (1, 1), (0, 0)])
-def test_rotation_every_block_instantiation(ell_min, ell_max):
-    """rotate.cu launches one kernel per block of l (0..8, 9..12, 13..16), in an instantiation without per-rung tests when
-    the block is covered completely and a general one otherwise: every combination against the oracle, on a series that
-    does not fill its last tile of 32 steps and contains an exact identity and an exact pole."""
+@pytest.mark.parametrize("recurrence", [False, True])
+@pytest.mark.parametrize("ell_min,ell_max", [(2, 8), (2, 16), (0, 16), (0, 8), (3, 11), (10, 14), (2, 5), (13, 16), (9, 12), (2, 12), (1, 1), (0, 0), (2, 20)])
+def test_rotation_every_block_instantiation(ell_min, ell_max, recurrence, monkeypatch):
+    """rotate.cu has two rotation kernels for ell_max <= 16 - the DMMA kernel (tiles sized for ell_max <= 11 or <= 16, 1..5
+    m-tiles per l) and the recurrence kernel (one launch per block of l: 0..8, 9..12, 13..16, in an instantiation without
+    per-rung tests when the block is covered completely and a general one otherwise; SCRIB200_ROTATE_RECURRENCE) - and the
+    first-generation kernel above: every combination against the oracle, on a series that does not fill its last tile
+    and contains an exact identity and an exact pole."""
+    if recurrence:
+        monkeypatch.setenv("SCRIB200_ROTATE_RECURRENCE", "1")
     n = 77
     t, data = smooth_modes(n_times=n, ell_min=ell_min, ell_max=ell_max, seed=31 + ell_min + 17 * ell_max)
     Rs = quat.normalized(np.random.default_rng(ell_max).normal(size=(n, 4)))
