@@ -298,7 +298,7 @@ def extra_batch(args, torch, dist, world, rank, kw):
     def e2e_step():
         # the shard as `reps` host blocks flowing through one pipeline (the same pinned blocks each time, see above)
         sizes = [min(host_in.shape[0], shard - r * host_in.shape[0]) for r in range(reps)]
-        u, res = parallel.transform_batch_host(plan, t_host, [host_in.numpy()[:nb] for nb in sizes], sub_batch=sub // 4,
+        u, res = parallel.transform_batch_host(plan, t_host, [host_in.numpy()[:nb] for nb in sizes], sub_batch=sub // 8,
                                                out=[host_out[:nb] for nb in sizes])
         return u
 
@@ -324,7 +324,7 @@ def extra_batch(args, torch, dist, world, rank, kw):
         "scaling": "strong", "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_out": int(n_out),
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(shard) * N * n * 16 * world, "d2h_bytes_per_step": int(shard) * int(n_out) * n * 16 * world,
-                "note": f"host arrays in pinned memory ({sub} waveforms per call of parallel.transform_batch_host, sub-batches of {sub // 4} double-buffered on three streams); H2D, kernels and D2H of every sub-batch inside the timed region"},
+                "note": f"host arrays in pinned memory ({sub} waveforms per call of parallel.transform_batch_host, sub-batches of {sub // 8} double-buffered on three streams, one spline preparation for the whole batch); H2D, kernels and D2H of every sub-batch inside the timed region"},
     }
 
 

@@ -170,6 +170,8 @@ def transform_batch_host(plan, t, data_host, sub_batch=512, out=None):
     sub = max(1, min(int(sub_batch), max(b.shape[0] for b in blocks)))
     cur = torch.cuda.current_stream()
     cin, cout = torch.cuda.Stream(), torch.cuda.Stream()
+    prep = plan.prepare(t_d)             # one time axis for the whole batch: its spline tables and retained block, once
+    prep.resolve()
     bufs = [torch.empty((sub, N, n), dtype=torch.complex128, device="cuda") for _ in range(2)]
     free = [None, None]                                   # event: the kernels that read buffer b are done
     row_bytes = N * n * 16
@@ -190,7 +192,7 @@ def transform_batch_host(plan, t, data_host, sub_batch=512, out=None):
             landed = torch.cuda.Event()
             landed.record(cin)
             cur.wait_event(landed)
-            u, m = plan.run_batch(t_d, bufs[b][:nb])
+            u, m = plan.run_batch(t_d, bufs[b][:nb], prep=prep)
             done = torch.cuda.Event()
             done.record(cur)
             free[b] = done
