@@ -607,6 +607,20 @@ def test_batched_transform_equals_single_transforms():
 
     up2, out2 = parallel.transform_batch(pl, td, bd)
     assert torch.equal(out2, out)
+    # the second call on the same time-axis tensor assumes its retained block; a time axis rewritten IN PLACE (same storage,
+    # other retained block) must be noticed and the call repeated unassumed; host blocks through one shared preparation
+    up3, out3 = pl.run_batch(td, bd)
+    assert torch.equal(up3, up) and torch.equal(out3, out)
+    t_new = np.linspace(0.0, 25.0, N)          # a finer axis: another retained block under the same supertranslation
+    td.copy_(torch.from_numpy(t_new).to(td.device))
+    up4, out4 = pl.run_batch(td, bd)
+    fresh = P.TransformPlan(2, 8, sb.h, **BMS)
+    up5, out5 = fresh.run_batch(ops.to_device(t_new), bd)
+    assert torch.equal(up4, up5)
+    assert torch.equal(out4, out5)
+    assert up4.shape[0] != up.shape[0] or not torch.equal(up4, up)
+    uh, mh = parallel.transform_batch_host(fresh, t_new, batch, sub_batch=2)
+    assert np.array_equal(uh, up5.cpu().numpy()) and np.array_equal(mh, out5.cpu().numpy())
 
 
 def test_million_step_transform_window_vs_oracle():
