@@ -44,16 +44,28 @@ __global__ void norm_kernel(const double2* __restrict__ data, int64_t n_times, i
 //                   ladder(l,-(m-1))ladder(l,-m) [0 if m-2<-l], m }
 constexpr int NCOEF = 5;
 
+// Eight lanes per time step, four time steps per warp: the nine sums of a step are reduced over 8 lanes (3 butterfly levels
+// instead of 5) for four steps at once - with a whole warp per step the reductions, not the arithmetic, were most of the time
+// (9 modes per lane at ell <= 16, 3 at ell <= 8).
+constexpr int LL_GROUP = 8;
+
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = LL_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 template <bool WITH_LDT>
 __global__ void ll_ldt_kernel(const double2* __restrict__ data, const double2* __restrict__ datadot, int64_t n_times,
                               int n, const double* __restrict__ coef, double* __restrict__ LL, double* __restrict__ Ldt) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= n_times) return;
+    const int lane = threadIdx.x & (LL_GROUP - 1);
+    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LL_GROUP;
+    const bool live = t < n_times;
+    if (!live) t = n_times - 1;                          // keeps the whole warp in the shuffles
     const double2* row = data + t * n;
     const double2* rowd = WITH_LDT ? datadot + t * n : nullptr;
     double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0, lx = 0, ly = 0, lz = 0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += LL_GROUP) {
         const double* c = coef + i * NCOEF;
         const double cp = c[0], cm = c[1], cpp = c[2], cmm = c[3], M = c[4];
         const double2 a = row[i];
@@ -92,10 +104,10 @@ __global__ void ll_ldt_kernel(const double2* __restrict__ data, const double2* _
             lz += Lz.y;
         }
     }
-    sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
-    syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
-    if (WITH_LDT) { lx = warp_sum(lx); ly = warp_sum(ly); lz = warp_sum(lz); }
-    if (lane == 0) {
+    sxx = group_sum(sxx); sxy = group_sum(sxy); sxz = group_sum(sxz);
+    syy = group_sum(syy); syz = group_sum(syz); szz = group_sum(szz);
+    if (WITH_LDT) { lx = group_sum(lx); ly = group_sum(ly); lz = group_sum(lz); }
+    if (lane == 0 && live) {
         double* o = LL + t * 9;
         o[0] = sxx; o[1] = sxy; o[2] = sxz;
         o[3] = sxy; o[4] = syy; o[5] = syz;
@@ -663,11 +675,12 @@ extern "C" int scrib200_ll_ldt(const double* data, const double* datadot, int64_
     SCRIB200_REQUIRE(data && coef && LL, "ll_ldt: null pointer");
     SCRIB200_REQUIRE((datadot == nullptr) == (Ldt == nullptr), "ll_ldt: datadot and Ldt go together");
     if (n_times <= 0) return SCRIB200_OK;
+    const unsigned ll_blocks = (unsigned)((n_times * LL_GROUP + 127) / 128);
     if (datadot)
-        ll_ldt_kernel<true><<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+        ll_ldt_kernel<true><<<ll_blocks, 128, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const double2*>(data), reinterpret_cast<const double2*>(datadot), n_times, n_modes, coef, LL, Ldt);
     else
-        ll_ldt_kernel<false><<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(
+        ll_ldt_kernel<false><<<ll_blocks, 128, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const double2*>(data), nullptr, n_times, n_modes, coef, LL, nullptr);
     SCRIB200_CHECK_LAUNCH("ll_ldt");
     return SCRIB200_OK;
