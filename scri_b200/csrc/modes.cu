@@ -24,19 +24,24 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------ norm
+// eight lanes per time step, four steps per warp: at ell <= 8 (77 modes) a whole warp per step leaves most lanes with two
+// loads and a five-level reduction per step
 __global__ void norm_kernel(const double2* __restrict__ data, int64_t n_times, int n, double* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= n_times) return;
+    const int lane = threadIdx.x & 7;
+    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = t < n_times;
+    if (!live) t = n_times - 1;                          // keeps the whole warp in the shuffles
     const double2* row = data + t * n;
     double acc = 0.0;
-    for (int i = lane; i < n; i += 32) {
+#pragma unroll 4
+    for (int i = lane; i < n; i += 8) {
         const double2 a = row[i];
         acc = fma(a.x, a.x, acc);
         acc = fma(a.y, a.y, acc);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[t] = acc;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && live) out[t] = acc;
 }
 
 // ------------------------------------------------------------------------------------------ <LL>, <L dt>
@@ -664,8 +669,8 @@ using namespace scrib200;
 extern "C" int scrib200_norm(const double* data, int64_t n_times, int n_modes, double* out, void* stream) {
     SCRIB200_REQUIRE(data && out, "norm: null pointer");
     if (n_times <= 0) return SCRIB200_OK;
-    norm_kernel<<<warp_blocks(n_times), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(data), n_times,
-                                                                       n_modes, out);
+    norm_kernel<<<(unsigned)((n_times * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(data), n_times,
+                                                                                         n_modes, out);
     SCRIB200_CHECK_LAUNCH("norm");
     return SCRIB200_OK;
 }
