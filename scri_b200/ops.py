@@ -259,32 +259,37 @@ def wigner_tables_device(ell_max):
     return _table_cache[key]
 
 
+def delta_fragment_tables(ell_max):
+    """Host (numpy) form of the operand table of scrib200_rotate_modes_dmma: for l = 0 .. ell_max the real matrices
+    Delta^l = d^l(pi/2) (this package's D-matrix convention, scri_b200/_sf.py:wigner_D_matrices at Ra = Rb = cos(pi/4)) cut into
+    the A fragments of mma.m8n8k4 - tiles [Kt][Mt][32 lanes] of Delta^T, then of Delta, zero padded; lane holds
+    A[8 mm + lane / 4][4 kk + lane % 4].  Returns (table float64 [total], int32 offsets in doubles).  The CPU tests rebuild the
+    matrices from it and run the kernel's five steps in numpy (tests/test_host.py)."""
+    c = math.cos(math.pi / 4.0)
+    flat = _sf.wigner_D_matrices(np.array(c + 0j), np.array(c + 0j), 0, ell_max)
+    assert np.abs(flat.imag).max() == 0.0
+    chunks, offsets, pos = [], np.zeros(ell_max + 1, dtype=np.int32), 0
+    for ell in range(ell_max + 1):
+        n = 2 * ell + 1
+        delta = flat.real[_sf.D_offset(ell, 0) : _sf.D_offset(ell + 1, 0)].reshape(n, n)      # [m', mu]
+        Mt, Kt = (n + 7) // 8, (n + 3) // 4
+        offsets[ell] = pos
+        for A in (delta.T, delta):
+            pad = np.zeros((8 * Mt, 4 * Kt))
+            pad[:n, :n] = A
+            tiles = pad.reshape(Mt, 8, Kt, 4).transpose(2, 0, 1, 3).reshape(Kt, Mt, 32)       # [kk][mm][lane = 4 g + q]
+            chunks.append(tiles.ravel())
+            pos += Mt * Kt * 32
+    return np.ascontiguousarray(np.concatenate(chunks)), offsets
+
+
 def wigner_delta_fragments(ell_max):
-    """Operand table of scrib200_rotate_modes_dmma: for l = 0 .. ell_max the real matrices Delta^l = d^l(pi/2) (this
-    package's D-matrix convention, scri_b200/_sf.py:wigner_D_matrices at Ra = Rb = cos(pi/4)) cut into the A fragments of
-    mma.m8n8k4 - tiles [Kt][Mt][32 lanes] of Delta^T, then of Delta, zero padded; lane holds A[8 mm + lane / 4][4 kk + lane % 4].
-    Returns (device table, host int32 offsets in doubles)."""
+    """Device copy of delta_fragment_tables(ell_max), cached per device: (device table, host int32 offsets)."""
     torch = _torch()
     key = ("delta", ell_max, torch.cuda.current_device())
     if key not in _table_cache:
-        c = math.cos(math.pi / 4.0)
-        flat = _sf.wigner_D_matrices(np.array(c + 0j), np.array(c + 0j), 0, ell_max)
-        assert np.abs(flat.imag).max() == 0.0
-        lane = np.arange(32)
-        chunks, offsets, pos = [], np.zeros(ell_max + 1, dtype=np.int32), 0
-        for ell in range(ell_max + 1):
-            n = 2 * ell + 1
-            delta = flat.real[_sf.D_offset(ell, 0) : _sf.D_offset(ell + 1, 0)].reshape(n, n)      # [m', mu]
-            Mt, Kt = (n + 7) // 8, (n + 3) // 4
-            offsets[ell] = pos
-            for A in (delta.T, delta):
-                pad = np.zeros((8 * Mt, 4 * Kt))
-                pad[:n, :n] = A
-                tiles = pad.reshape(Mt, 8, Kt, 4).transpose(2, 0, 1, 3).reshape(Kt, Mt, 32)       # [kk][mm][lane = 4 g + q]
-                chunks.append(tiles.ravel())
-                pos += Mt * Kt * 32
-        table = torch.from_numpy(np.ascontiguousarray(np.concatenate(chunks))).cuda()
-        _table_cache[key] = (table, offsets)
+        table, offsets = delta_fragment_tables(ell_max)
+        _table_cache[key] = (torch.from_numpy(table).cuda(), offsets)
     return _table_cache[key]
 
 

@@ -321,3 +321,98 @@ def test_intersection_matches_reference_output():
         intersection(np.array([]), g["i_t2"])
     with pytest.raises(ValueError):
         intersection(g["i_t1"], g["i_t2"] + 1000.0)
+
+
+def _unpack_fragments(table, offsets, ell):
+    """(Delta^T, Delta) of one l rebuilt from the m8n8k4 A-fragment table: lane holds A[8 mm + lane / 4][4 kk + lane % 4]."""
+    n = 2 * ell + 1
+    Mt, Kt = (n + 7) // 8, (n + 3) // 4
+    out = []
+    for part in range(2):
+        tiles = table[offsets[ell] + part * Mt * Kt * 32 : offsets[ell] + (part + 1) * Mt * Kt * 32].reshape(Kt, Mt, 8, 4)
+        A = tiles.transpose(1, 2, 0, 3).reshape(8 * Mt, 4 * Kt)
+        assert not A[n:].any() and not A[:, n:].any()            # padding is exactly zero
+        out.append(A[:n, :n])
+    return out
+
+
+@pytest.mark.parametrize("ell_min,ell_max", [(2, 8), (0, 16), (3, 11)])
+def test_rotation_tables_through_a_numpy_emulation_of_the_dmma_kernel(ell_min, ell_max):
+    """scrib200_rotate_modes_dmma in numpy, from the product's own operand table (ops.delta_fragment_tables): unpack the
+    fragments, check Delta^l = d^l(pi/2) is orthogonal with the reflection symmetries the factorisation rests on, then run the
+    kernel's five steps - phases, Delta^T, phases of beta, Delta, phases - against the oracle's rotation (poles, an exact
+    identity and a 1e-9 neighbourhood of a pole included)."""
+    table, offsets = ops.delta_fragment_tables(ell_max)
+    rng = np.random.default_rng(ell_max)
+    n_t = 24
+    t, data = smooth_modes(n_times=n_t, ell_min=ell_min, ell_max=ell_max, seed=7)
+    Rs = quat.normalized(rng.normal(size=(n_t, 4)))
+    Rs[0] = [1.0, 0.0, 0.0, 0.0]
+    Rs[1] = [0.0, 0.0, 1.0, 0.0]
+    Rs[2] = [0.0, 1.0, 0.0, 0.0]
+    Rs[3] = np.array([1e-9, 0.0, 1.0, 0.0]) / np.sqrt(1.0 + 1e-18)
+    want = R.rotate_decomposition_basis(R.Modes(t=t, data=data.copy(), ell_min=ell_min, ell_max=ell_max), Rs).data
+    sp = Q.as_spinor_array(Rs)
+    Ra, Rb = sp[:, 0], sp[:, 1]
+    ra2, rb2 = np.abs(Ra) ** 2, np.abs(Rb) ** 2
+    n2 = ra2 + rb2
+    ea = np.where(ra2 > 0, Ra / np.where(ra2 > 0, np.abs(Ra), 1.0), 1.0)
+    eb = np.where(rb2 > 0, Rb / np.where(rb2 > 0, np.abs(Rb), 1.0), 1.0)
+    ra, rb = np.sqrt(ra2 / n2), np.sqrt(rb2 / n2)
+    q1, ebeta, q3 = -1j * ea * np.conj(eb), (ra * ra - rb * rb) - 2j * ra * rb, 1j * ea * eb
+    got = np.empty_like(data)
+    for ell in range(ell_min, ell_max + 1):
+        dT, d = _unpack_fragments(table, offsets, ell)
+        assert np.array_equal(dT, d.T)
+        n = 2 * ell + 1
+        m = np.arange(-ell, ell + 1)
+        assert np.abs(d @ d.T - np.eye(n)).max() < 4e-15
+        assert np.array_equal(d[::-1, :], d * (-1.0) ** (ell + m)[None, :])       # Delta[-m', mu] = (-1)^(l + mu) Delta[m', mu]
+        assert np.array_equal(d[:, ::-1], d * (-1.0) ** (ell + m)[:, None])       # Delta[m', -mu] = (-1)^(l + m') Delta[m', mu]
+        col = ell * ell - ell_min * ell_min
+        x = data[:, col : col + n] * q1[:, None] ** m[None, :]
+        y = x @ dT.T                                                               # y[mu] = sum_m' Delta[m', mu] x[m']
+        z = y * ebeta[:, None] ** m[None, :]
+        o = z @ d.T                                                                # o[m] = sum_mu Delta[m, mu] z[mu]
+        got[:, col : col + n] = o * q3[:, None] ** m[None, :]
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-14
+
+
+@pytest.mark.parametrize("same", [True, False])
+def test_expectation_tables_through_a_numpy_emulation_of_the_time_lane_kernel(same):
+    """ops._time_tables (entry table + column blocks of scrib200_sparse_expectation_time) for the momentum operators at
+    ell <= 16: every column with entries lies in exactly one block, every row an entry names (padding slots included) lies in
+    its block's window, the tiles fit the budget the way the C side adds them up - and walking the table block by block the
+    way the kernel does gives the dense contraction."""
+    lmin, lmax = 2, 16
+    n = lmax * (lmax + 2) - lmin * lmin + 1
+    mats = [flux.p_plus(lmin, lmax, s=-2), flux.p_minus(lmin, lmax, s=-2), flux.p_z(lmin, lmax, s=-2)]
+    tab, blocks, width, real = ops._time_tables(mats, n, same)
+    blocks = blocks.reshape(-1, 4)
+    assert real and width == 3 and tab.shape == (n, 3, 3) and tab.dtype.itemsize == 16
+    covered = np.zeros(n, dtype=int)
+    for c0, c1, rlo, rhi in blocks:
+        covered[c0:c1] += 1
+        r = tab["r"][c0:c1]
+        assert r.min() >= rlo and r.max() < rhi
+        if same:
+            assert rlo <= c0 and c1 <= rhi
+    assert (covered == 1).all() and len(blocks) >= 2
+    max_rows, max_cols = (blocks[:, 3] - blocks[:, 2]).max(), (blocks[:, 1] - blocks[:, 0]).max()
+    assert (max_rows + (0 if same else max_cols)) * 528 + max_cols * 9 * 16 <= ops.XT_BUDGET_BYTES
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(5, n)) + 1j * rng.normal(size=(5, n))
+    b = a if same else rng.normal(size=(5, n)) + 1j * rng.normal(size=(5, n))
+    got = np.zeros((5, 3), dtype=complex)
+    for c0, c1, rlo, rhi in blocks:
+        for c in range(c0, c1):
+            for k in range(3):
+                q = sum(tab["v"][c, k, w] * np.conj(a[:, tab["r"][c, k, w]]) for w in range(width))
+                got[:, k] += q * b[:, c]
+    want = np.zeros((5, 3), dtype=complex)
+    for k, (rows, cols, vals) in enumerate(mats):
+        M = np.zeros((n, n), dtype=complex)
+        M[np.asarray(rows), np.asarray(cols)] = vals
+        want[:, k] = np.einsum("tr,rc,tc->t", a.conj(), M, b)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-14
+
