@@ -40,6 +40,11 @@ def to_device(x, dtype=None):
         return torch.from_numpy(a).cuda()
     out = torch.empty(a.shape, dtype=getattr(torch, a.dtype.name), device="cuda")
     lib = _lib.load()
+    # an array that goes up a second time (a waveform whose fluxes, frames, ... are computed one after the other) is
+    # page-locked in place and DMA'd directly from then on; the copy is then asynchronous on the current stream - every
+    # operator that was handed numpy arrays synchronises before it returns numpy results, which is when the caller may
+    # touch the array again
+    _maybe_register(a)
     _lib.check(lib.scrib200_h2d(_lib.ptr(out), a.ctypes.data, a.nbytes, _lib.stream_ptr()), "h2d")
     return out
 
