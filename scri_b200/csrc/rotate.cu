@@ -3,14 +3,15 @@
 // Replaces scri/rotations.py:346-392 (numba loops) + sf._Wigner_D_matrices (per time step).
 // a'_{l m}(t) = sum_{m'} a_{l m'}(t) D^l_{m',m}(R(t)).
 //
-// D is never materialised: D^l_{m'm} = PhA(m'+m) PhB(m-m') P^l_{m'm}(cos beta), with the phases taken
-// from per-step tables of powers of Ra, Rb (no trigonometry, regular at the poles) and the real
-// polynomial P advanced in l by the three-term recurrence from an exact seed at l0 = max(|m'|,|m|)
-// (tables built once on the host: scri_b200/_sf.py:wigner_tables).
-//
-// Mapping: a CTA owns TB consecutive time steps; the [TB, n_modes] tile is staged through shared
-// memory with coalesced loads/stores; one thread per (time step, output m) walks m' and l.
-// HBM-bound by design: 2*16*n_modes + 32 bytes per time step.
+// Three kernels, newest last (see each one's header):
+//   * rotate_modes_kernel (any ell_max; used above 16): D is never materialised, D^l_{m'm} = PhA(m'+m) PhB(m-m')
+//     P^l_{m'm}(cos beta) with the phases from per-step tables of powers of Ra, Rb (no trigonometry, regular at the poles) and
+//     the real polynomial P advanced in l by the three-term recurrence from an exact seed at l0 = max(|m'|, |m|) (tables:
+//     scri_b200/_sf.py:wigner_tables); a CTA owns TB time steps staged through shared memory, one thread per (step, m);
+//   * rotate_modes_time_kernel (ell_max <= 16, SCRIB200_ROTATE_RECURRENCE): the same recurrences with lanes along time, four
+//     matrix elements per recurrence step by symmetry, a rung of ~22 instructions;
+//   * rotate_modes_dmma_kernel (ell_max <= 16, the default): D^l(R) factored into the constant matrices d^l(pi/2) and diagonal
+//     phases - two FP64 tensor-core products per (16 time steps, l).
 #include <stdlib.h>
 
 #include <mutex>
@@ -112,153 +113,6 @@ __global__ void rotate_modes_kernel(double2* __restrict__ data, int64_t n_times,
     for (int idx = tid; idx < tile; idx += nthreads) {
         int64_t t = t0 + idx / n_modes;
         if (t < n_times) data[t0 * n_modes + idx] = s_out[idx];
-    }
-}
-
-// ---- second-generation kernel (ell_max <= LT, LT = 8 or 16).
-//   D^l_{m'm} = [ra^{|m'+m|} rb^{|m-m'|} P^l_{m'm}(cos beta)] e^{i m'(A-B)} e^{i m(A+B)},   Ra = ra e^{iA}, Rb = rb e^{iB}:
-// the phases separate, so the modes are premultiplied by e^{i m'(A-B)} once while the tile is staged, the m'-sum is a
-// REAL matrix times a complex vector, and e^{i m(A+B)} is applied once per output.  One thread owns one (time step,
-// m): it walks m' and advances P in l by the three-term recurrence with the accumulators for every l in REGISTERS
-// (the l loop is unrolled to LT+1 predicated steps; no read-modify-write of shared memory), and the recurrence
-// coefficients are rebuilt from two small factor tables,  a = U[l][m'] U[l][m],  c = V[l][m'] V[l][m],
-// b = a m' m / (l (l+1)), instead of three loads per step from an [L, 2L+1, 2L+1, 3] table that outgrows L1.
-template <int LT>
-__global__ void __launch_bounds__(512)
-rotate_modes_reg_kernel(double2* __restrict__ data, int64_t n_times, int ell_min, int ell_max,
-                        const double2* __restrict__ spinors, int64_t spinor_stride, const double* __restrict__ seed,
-                        const double2* __restrict__ uv, int TB) {
-    extern __shared__ double2 smr[];
-    const int L = ell_max;
-    const int nm = 2 * L + 1;
-    const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
-    double2* s_b = smr;                                    // [TB][n_modes]  a_{l m'} e^{i m'(A-B)}
-    double2* s_uv = s_b + (size_t)TB * n_modes;            // [L][nm]       (U, V)[l][m + L]
-    double2* s_pw = s_uv + (size_t)(L > 0 ? L : 1) * nm;   // [TB][L+1]     e^{i k (A+B)}
-    double* s_ra = reinterpret_cast<double*>(s_pw + (size_t)TB * (L + 1));   // [TB][nm] ra^k, k = 0..2L
-    double* s_rb = s_ra + (size_t)TB * nm;                 // [TB][nm]
-    double* s_cos = s_rb + (size_t)TB * nm;                // [TB]   cos(beta), or 2 if Rb == 0 exactly
-    double2* s_pu = reinterpret_cast<double2*>(s_cos + TB + (TB & 1));       // [TB][L+1]  e^{i k (A-B)}
-
-    const int64_t t0 = (int64_t)blockIdx.x * TB;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-
-    for (int i = tid; i < L * nm; i += nthreads) s_uv[i] = uv[i];
-    for (int tt = tid; tt < TB; tt += nthreads) {
-        int64_t t = t0 + tt;
-        if (t >= n_times) t = n_times - 1;
-        const double2 Ra = spinors[t * spinor_stride + 0], Rb = spinors[t * spinor_stride + 1];
-        const double ra2 = Ra.x * Ra.x + Ra.y * Ra.y, rb2 = Rb.x * Rb.x + Rb.y * Rb.y;
-        const double n2 = ra2 + rb2;
-        const double ra = sqrt(ra2 / n2), rb = sqrt(rb2 / n2);
-        // unit phases; the phase of an exact zero is 1 (its magnitude powers kill every term it would enter)
-        const double2 ea = ra2 > 0.0 ? cscale(1.0 / sqrt(ra2), Ra) : make_double2(1.0, 0.0);
-        const double2 eb = rb2 > 0.0 ? cscale(1.0 / sqrt(rb2), Rb) : make_double2(1.0, 0.0);
-        const double2 u = cmul(ea, cconj(eb)), w = cmul(ea, eb);
-        double2 pu = make_double2(1.0, 0.0), pw = pu;
-        for (int k = 0; k <= L; ++k) {
-            s_pu[tt * (L + 1) + k] = pu;
-            s_pw[tt * (L + 1) + k] = pw;
-            pu = cmul(pu, u);
-            pw = cmul(pw, w);
-        }
-        double pa = 1.0, pb = 1.0;
-        for (int k = 0; k < nm; ++k) {
-            s_ra[tt * nm + k] = pa;
-            s_rb[tt * nm + k] = pb;
-            pa *= ra;
-            pb *= rb;
-        }
-        s_cos[tt] = (rb2 == 0.0) ? 2.0 : (ra2 - rb2) / n2;
-    }
-    __syncthreads();
-    // stage the tile, premultiplied by e^{i m'(A-B)}
-    const int tile = TB * n_modes;
-    for (int idx = tid; idx < tile; idx += nthreads) {
-        const int tt = idx / n_modes, lm = idx - tt * n_modes;
-        const int64_t t = t0 + tt;
-        double2 v = make_double2(0.0, 0.0);
-        if (t < n_times) {
-            const int full = lm + ell_min * ell_min;
-            int l = (int)sqrt((double)full);
-            while (l * l > full) --l;
-            while ((l + 1) * (l + 1) <= full) ++l;
-            const int mp = full - l * (l + 1);
-            const double2 ph = s_pu[tt * (L + 1) + (mp < 0 ? -mp : mp)];
-            v = cmul(data[t0 * n_modes + idx], mp < 0 ? cconj(ph) : ph);
-        }
-        s_b[idx] = v;
-    }
-    __syncthreads();
-
-    const int tt = tid / nm, mi = tid - tt * nm;
-    if (tt >= TB || t0 + tt >= n_times) return;
-    const int m = mi - L, am = m < 0 ? -m : m;
-    const double cosb = s_cos[tt];
-    const bool diagonal = cosb > 1.5;
-    const double* rap = s_ra + tt * nm;
-    const double* rbp = s_rb + tt * nm;
-    const double2* bin = s_b + (size_t)tt * n_modes;
-    const int lmin2 = ell_min * ell_min;
-    double accr[17], acci[17];   // entries above LT are never touched (dead code after unrolling)
-#pragma unroll
-    for (int l = 0; l <= 16; ++l) accr[l] = acci[l] = 0.0;
-    if (diagonal) {   // Rb == 0 exactly: D^l_{m'm} = delta_{m'm} ra^{2|m|} (phases applied outside): bit-exact for the identity
-        const double mag = rap[2 * am];
-#pragma unroll
-        for (int l = 0; l <= 16; ++l)
-            if (l <= LT && l >= am && l >= ell_min && l <= L) {
-                const double2 bv = bin[l * (l + 1) - lmin2 + m];
-                accr[l] = mag * bv.x;
-                acci[l] = mag * bv.y;
-            }
-    } else {
-        // m' and -m' start at the same l0 and share U, V (even in m'): two independent recurrence chains per ladder step
-        for (int mp = 0; mp <= L; ++mp) {
-            const int l0 = mp > am ? mp : am;
-            const int kap = mp + m, kbp = m - mp;            // +m': exponents of ra, rb;  -m': (kbp, kap)
-            const int akap = kap < 0 ? -kap : kap, akbp = kbp < 0 ? -kbp : kbp;
-            double Pp = seed[(mp + L) * nm + mi] * (rap[akap] * rbp[akbp]);
-            double Pn_ = (mp > 0) ? seed[(L - mp) * nm + mi] * (rap[akbp] * rbp[akap]) : 0.0;
-            double Pp1 = 0.0, Pn1 = 0.0;
-            const double mmp = (double)(m * mp);
-            // enter the unrolled l ladder at the smallest l0 of the WARP (a warp-uniform jump, so the lanes stay
-            // converged); lanes whose own l0 is larger are predicated off until they start
-#define ROT_STEP(l_)                                                                                      \
-    case l_:                                                                                              \
-        if (l_ <= LT && l_ <= L && l_ >= l0) {                                                            \
-            if (l_ >= ell_min) {                                                                          \
-                const double2 bp = bin[l_ * (l_ + 1) - lmin2 + mp];                                       \
-                const double2 bn = bin[l_ * (l_ + 1) - lmin2 - mp];                                       \
-                accr[l_] = fma(Pp, bp.x, fma(Pn_, bn.x, accr[l_]));                                       \
-                acci[l_] = fma(Pp, bp.y, fma(Pn_, bn.y, acci[l_]));                                       \
-            }                                                                                             \
-            if (l_ < L) {                                                                                 \
-                const double2 f1 = s_uv[l_ * nm + mp + L], f2 = s_uv[l_ * nm + mi];                       \
-                const double rl = (l_ > 0) ? 1.0 / (double)(l_ * (l_ + 1)) : 0.0;                         \
-                const double a_ = f1.x * f2.x, c_ = f1.y * f2.y, tb = mmp * rl;                           \
-                const double Pq = a_ * (cosb - tb) * Pp - c_ * Pp1;                                       \
-                const double Nq = a_ * (cosb + tb) * Pn_ - c_ * Pn1;                                      \
-                Pp1 = Pp;                                                                                 \
-                Pn1 = Pn_;                                                                                \
-                Pp = Pq;                                                                                  \
-                Pn_ = Nq;                                                                                 \
-            }                                                                                             \
-        }
-            switch (__reduce_min_sync(__activemask(), l0)) {
-                ROT_STEP(0) ROT_STEP(1) ROT_STEP(2) ROT_STEP(3) ROT_STEP(4) ROT_STEP(5) ROT_STEP(6) ROT_STEP(7) ROT_STEP(8)
-                ROT_STEP(9) ROT_STEP(10) ROT_STEP(11) ROT_STEP(12) ROT_STEP(13) ROT_STEP(14) ROT_STEP(15) ROT_STEP(16)
-                default: break;
-            }
-#undef ROT_STEP
-        }
-    }
-    const double2 pw = s_pw[tt * (L + 1) + am];
-    const double2 phw = m < 0 ? cconj(pw) : pw;
-    double2* orow = data + (t0 + tt) * n_modes;
-#pragma unroll
-    for (int l = 0; l <= 16; ++l) {
-        if (l <= LT && l >= am && l >= ell_min && l <= L) orow[l * (l + 1) - lmin2 + m] = cmul(make_double2(accr[l], acci[l]), phw);
     }
 }
 
@@ -772,12 +626,6 @@ static size_t rotate_time_smem(int lo, int hi) {
     return (n_blk * ROT3_PITCH + 2 * (size_t)(hi + 1) * ROT3_TB) * sizeof(double2) + (2 * (size_t)(2 * hi + 1) * ROT3_TB + ROT3_TB) * sizeof(double);
 }
 
-static size_t rotate_reg_smem(int TB, int L, int n_modes) {
-    const size_t nm = 2 * L + 1;
-    return ((size_t)TB * n_modes + (size_t)(L > 0 ? L : 1) * nm + 2 * (size_t)TB * (L + 1)) * sizeof(double2) +
-           (2 * (size_t)TB * nm + TB + (TB & 1)) * sizeof(double);
-}
-
 // (a, b, c) of the step l -> l+1, P^{l+1}(m', m) = (a cos(beta) - b) P^l - c P^{l-1}  [+ b for (-m', m)], with
 // a = U_l(m') U_l(m), c = V_l(m') V_l(m), b = a m' m / (l (l + 1)) - the factors of scri_b200/_sf.py:wigner_factor_table,
 // multiplied out here so that a rung reads three numbers instead of forming them.  Compact: for every 0 <= m, m' <= 16
@@ -866,7 +714,7 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
     if (n_times <= 0) return SCRIB200_OK;
     const int L = ell_max, nm = 2 * L + 1;
     const int n_modes = L * (L + 2) - ell_min * ell_min + 1;
-    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr && getenv("SCRIB200_ROTATE_V2") == nullptr) {
+    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
         // the small tables steer warp-uniform loops: constant memory (broadcast, no load/store-unit traffic).  The seeds are
         // re-laid out at pitch 33 around index 16, so that the kernel's table indices do not depend on ell_max; the
@@ -901,27 +749,6 @@ extern "C" int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min,
         if (ell_min <= 13 && L >= 16) ROT4_LAUNCH(13, 16, true, 13, 16) else ROT4_BLOCK(13, 16)
 #undef ROT4_BLOCK
 #undef ROT4_LAUNCH
-        return SCRIB200_OK;
-    }
-    if (uv && L <= 16 && getenv("SCRIB200_ROTATE_V1") == nullptr) {
-        SCRIB200_REQUIRE(aligned16(uv), "rotate_modes: uv must be 16-byte aligned");
-        int TB = (L <= 8 ? 256 : 512) / nm;
-        if (TB < 1) TB = 1;
-        const size_t smem = rotate_reg_smem(TB, L, n_modes);
-        int threads = ((TB * nm + 31) / 32) * 32;
-        const int64_t blocks = (n_times + TB - 1) / TB;
-        if (L <= 8) {
-            cudaFuncSetAttribute(rotate_modes_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            rotate_modes_reg_kernel<8><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
-                reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors),
-                spinor_stride, seed, reinterpret_cast<const double2*>(uv), TB);
-        } else {
-            cudaFuncSetAttribute(rotate_modes_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            rotate_modes_reg_kernel<16><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
-                reinterpret_cast<double2*>(data), n_times, ell_min, ell_max, reinterpret_cast<const double2*>(spinors),
-                spinor_stride, seed, reinterpret_cast<const double2*>(uv), TB);
-        }
-        SCRIB200_CHECK_LAUNCH("rotate_modes");
         return SCRIB200_OK;
     }
     SCRIB200_REQUIRE(rec, "rotate_modes: the recurrence table `rec` is needed for ell_max > 16");
