@@ -46,7 +46,9 @@ int64_t scrib200_launch_count(void);
  *   seed    [(2L+1)^2], rec [L, 2L+1, 2L+1, 3]  recurrence tables for L = ell_max
  *           (scri_b200._sf.wigner_tables); uv [L, 2L+1, 2] the factored coefficients
  *           U[l][m] = sqrt((2l+1)(l+1)/((l+1)^2-m^2)), V[l][m] = sqrt((l+1)(l^2-m^2)/(l((l+1)^2-m^2)))
- *           (scri_b200._sf.wigner_factor_table).  ell_max <= 16 uses `uv` (rec may be NULL); larger uses `rec`.
+ *           (scri_b200._sf.wigner_factor_table).  ell_max <= 16 with `uv` non-NULL takes the lanes-along-time recurrence
+ *           kernel (rec may be NULL; the kernel reads the multiplied-out coefficients a = U U, b, c = V V from a table the
+ *           library builds itself from the same formulas, `uv` only selects it); larger ell_max, or uv == NULL, uses `rec`.
  */
 int scrib200_rotate_modes(double* data, int64_t n_times, int ell_min, int ell_max, const double* spinors,
                           int64_t spinor_stride, const double* seed, const double* rec, const double* uv, void* stream);
